@@ -1,0 +1,208 @@
+/*
+ * m17b200.h -- C ABI of libm17b200.so: the batched, B200-native (sm_100a) replacement for the
+ * m17gismo baseband hot path of G4GUO/m17_sdr.
+ *
+ * The reference has no FFI layer: its boundary is the set of free C++ functions declared in
+ * m17gismo/m17defines.h and linked statically.  Every entry point below is the batched
+ * form of one of those functions and cites the reference definition it replaces (paths relative to
+ * /root/reference/m17gismo).  The header-only C++ shim include/m17gismo_b200.hpp re-creates the
+ * original names/signatures at batch = 1 on top of this ABI.
+ *
+ * Conventions
+ *   - plain C, no torch/CUDA types: streams are passed as void* (a cudaStream_t; NULL = default stream);
+ *   - pointers named d_* are DEVICE pointers, h_* are HOST pointers; all buffers are caller-owned;
+ *   - every function returns 0 on success or a negative M17B_E_* code (the reference returns void or a
+ *     length and has no error channel; lengths are implied by the arguments here);
+ *   - functions only enqueue work on the stream unless their name ends in _host;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with M17B_E_CUDA.
+ *   - a context / rx / tx object is thread-compatible, not thread-safe (the reference runs the whole
+ *     path on one thread, m17_tx_rx.cpp:238-257).
+ */
+#ifndef M17B200_H
+#define M17B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define M17B_VERSION 100
+
+#define M17B_OK            0
+#define M17B_E_ARG        -1   /* bad argument                                   */
+#define M17B_E_CUDA       -2   /* CUDA runtime error (see m17b_last_cuda_error)  */
+#define M17B_E_NOMEM      -3
+#define M17B_E_UNSUPPORTED -4  /* e.g. AFC on the block-parallel front end       */
+#define M17B_E_CAPACITY   -5   /* nblocks exceeds the capacity given at create   */
+
+#define M17B_BLOCK_SAMPLES 1920   /* N_SAMPLES         m17defines.h:17 */
+#define M17B_DISC_PER_BLOCK 384   /* N_SAMPLES/5       m17_dsp.cpp:463 */
+#define M17B_FRAME_SYMS     192   /* FRAME_SYM_LENGTH  m17defines.h:66 */
+#define M17B_SOFT_BITS      368
+#define M17B_SYM_CAP_PER_BLOCK 200
+
+/* sync / frame types, m17_rx_frame.cpp:5-12 */
+enum { M17B_T_PREAMBLE = 0, M17B_T_LSF = 1, M17B_T_STREAM = 2, M17B_T_PACKET = 3, M17B_T_BERT = 4, M17B_T_EOT = 5 };
+
+/* record flags */
+#define M17B_F_SYNC_OK    0x01 /* m17_locked_sync_check() passed            m17_rx_frame.cpp:144 */
+#define M17B_F_PARSED     0x02 /* m17_rx_parse() semantics applied          m17_rx_frame.cpp:145,153 */
+#define M17B_F_LOS        0x04 /* framer dropped lock on this frame         m17_rx_frame.cpp:138-150 */
+#define M17B_F_DELIVERED  0x08 /* stream payload passed upward              m17_rx_parse.cpp:148-158 */
+#define M17B_F_LSF_EVENT  0x10 /* parse_lsf() would have run                m17_rx_parse.cpp:82,99 */
+#define M17B_F_PKT_EOF    0x20 /* packet frame with EOF bit                 m17_rx_parse.cpp:173 */
+
+/*
+ * One record per completed 192-symbol frame.  Replaces the reference's synchronous up-calls
+ * (m17_aos/m17_los, m17_db_*, gui_*, m17_txrx_spkr_audio, m17_net_new_rx_data:
+ * m17_rx_parse.cpp:20-32,128,145,153-157; m17_rx_frame.cpp:139,149,169).
+ */
+typedef struct {
+    int32_t  sym_off;      /* index of the frame's first symbol in the channel's emitted symbol stream */
+    uint8_t  type;         /* M17B_T_*  (m17_sync_check winner)                                        */
+    uint8_t  flags;        /* M17B_F_*                                                                 */
+    uint8_t  golay_err;    /* stream frames: sum of the 4 Golay error counts                            */
+    uint8_t  nbytes;       /* bytes in data[]: 30 LSF / 18 stream (FN+16) / 26 packet / 0               */
+    uint8_t  lich[6];      /* stream frames: corrected LICH chunk                                       */
+    uint8_t  data[30];     /* Viterbi output, MSB first, tail discarded                                 */
+    uint16_t crc;          /* CRC-16/M17 over data[0..nbytes): 0 = valid for LSF frames                 */
+    uint8_t  votes;        /* sync-word sign mismatches                                                 */
+    uint8_t  frame_errors; /* consecutive bad sync words so far                                         */
+    float    variance;     /* sync-word magnitude spread                                                */
+    float    cor;          /* demap normaliser                                                          */
+    uint8_t  rsvd[8];
+} m17b_frame_rec;          /* 64 bytes */
+
+#define M17B_EV_AOS 1
+#define M17B_EV_LOS 2
+typedef struct { int32_t sym_idx; int32_t kind; } m17b_event_rec;
+
+typedef struct m17b_ctx m17b_ctx;   /* per-GPU: lookup tables, filter banks (replaces the init chain main.cpp:108-126) */
+typedef struct m17b_rx  m17b_rx;    /* per-batch RX: per-channel state blobs + stage buffers                          */
+typedef struct m17b_tx  m17b_tx;    /* per-batch TX: per-channel modulator/formatter state                            */
+typedef struct m17b_eq  m17b_eq;    /* per-batch equaliser state                                                      */
+
+int         m17b_version(void);
+const char *m17b_error_string(int code);
+const char *m17b_last_cuda_error(void);
+
+/* m17_prbs9_init, m17_crc_init, m17_init_conv, m17_init_de_correlate, m17_dsp_init, m17_fmt_init,
+   m17_golay_init, m17_rx_sync_init, m17_mod_init  (main.cpp:108-126) */
+int m17b_ctx_create(int device, m17b_ctx **out);
+int m17b_ctx_destroy(m17b_ctx *ctx);
+/* filter design, host side, double math: m17_dsp_build_rrc_filter (m17_dsp.cpp:295-315),
+   m17_dsp_set_filter_gain (m17_dsp.cpp:420-429) */
+int m17b_build_rrc_filter(float *h_taps, float rolloff, int ntaps, int samples_per_symbol);
+int m17b_set_filter_gain(float *h_taps, float gain, int stride, int ntaps);
+/* copies of the RX polyphase banks m_mf/m_md [40][31] (m17_rx_sync.cpp:12-14,101-123) */
+int m17b_get_sync_taps(const m17b_ctx *ctx, float *h_mf, float *h_md);
+
+/* ------------------------------------------------------------------ batched primitives (device buffers) */
+/* m17_crc_array_encode (m17_crc.cpp:26-35): n arrays of len bytes, stride bytes apart -> n CRCs */
+int m17b_crc_array_encode(m17b_ctx *ctx, const uint8_t *d_in, int64_t stride, int len, int64_t n, uint16_t *d_crc, void *stream);
+/* m17_golay_encode (m17_golay.cpp:94-102) */
+int m17b_golay_encode(m17b_ctx *ctx, const uint16_t *d_data, int64_t n, uint32_t *d_words, void *stream);
+/* m_17_golay_decode (m17_golay.cpp:103-116): corrected data + error count 0..4 */
+int m17b_golay_decode(m17b_ctx *ctx, const uint32_t *d_words, int64_t n, uint16_t *d_data, uint8_t *d_err, void *stream);
+/* m17_conv_encode_8 (m17_conv.cpp:53-71): n x nbytes -> n x 2*(8*nbytes+4) bit-bytes */
+int m17b_conv_encode_8(m17b_ctx *ctx, const uint8_t *d_in, int nbytes, int64_t n, uint8_t *d_out, void *stream);
+/* m17_conv_encode_1 (m17_conv.cpp:33-49): n x nbits -> n x 2*(nbits+4) */
+int m17b_conv_encode_1(m17b_ctx *ctx, const uint8_t *d_in, int nbits, int64_t n, uint8_t *d_out, void *stream);
+/* m17_viterbi_decode (m17_conv.cpp:148-168): n x len soft values -> n x len/2 bit-bytes (out[0]=0 quirk kept) */
+int m17b_viterbi_decode(m17b_ctx *ctx, const float *d_soft, int len, int64_t n, uint8_t *d_bits, void *stream);
+/* m17_punc_p1/p2/p3 (m17_puncture.cpp:12-41): returns kept length through *out_len (host int) */
+int m17b_punc(m17b_ctx *ctx, int pattern, const uint8_t *d_in, int len, int64_t n, uint8_t *d_out, int *out_len, void *stream);
+/* m17_de_punc_p1/p2/p3 (m17_puncture.cpp:47-79): len = OUTPUT length; in_len = kept length */
+int m17b_de_punc(m17b_ctx *ctx, int pattern, const float *d_in, int in_len, int len, int64_t n, float *d_out, void *stream);
+/* m17_interleave / m17_de_interleave (m17_interleave.cpp:3-12), n frames of 368 */
+int m17b_interleave(m17b_ctx *ctx, const uint8_t *d_in, int64_t n, uint8_t *d_out, void *stream);
+int m17b_de_interleave(m17b_ctx *ctx, const float *d_in, int64_t n, float *d_out, void *stream);
+/* m17_de_correlate_8 / _1(uint8) / _1(float) (m17_correlate.cpp:11-31); in-place allowed */
+int m17b_de_correlate_8(m17b_ctx *ctx, uint8_t *d_io, int len, int64_t n, void *stream);
+int m17b_de_correlate_1_u8(m17b_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, int len, int64_t n, void *stream);
+int m17b_de_correlate_1_f32(m17b_ctx *ctx, const float *d_in, float *d_out, int len, int64_t n, void *stream);
+/* m17_dsp_demap_frame (m17_dsp.cpp:82-95): n x 192 symbols -> n x 368 soft bits */
+int m17b_demap_frame(m17b_ctx *ctx, const float *d_sym, int64_t n, float *d_soft, void *stream);
+/* m17_sync_check (m17_rx_frame.cpp:47-81): n x 8 symbols -> type, votes, variance */
+int m17b_sync_check(m17b_ctx *ctx, const float *d_vec, int64_t n, uint8_t *d_type, uint8_t *d_votes, float *d_var, void *stream);
+/* m17_prbs9_tx_load (m17_prbs9.cpp:27-32): n sequences of len bits starting at phase start[i] (NULL = 0) */
+int m17b_prbs9_tx_load(m17b_ctx *ctx, const int32_t *d_start, int len, int64_t n, uint8_t *d_out, void *stream);
+/* m17_rx_parse for n independent frames (m17_rx_parse.cpp:185-226) WITHOUT cross-frame LICH state:
+   d_sym [n][192], d_type [n]; fills type-dependent record fields; d_soft (optional) [n][368] demapped bits */
+int m17b_rx_parse_frames(m17b_ctx *ctx, const float *d_sym, const uint8_t *d_type, int64_t n, m17b_frame_rec *d_rec, float *d_soft, void *stream);
+/* config-4 microbenchmark path: n punctured soft frames (pattern 1/2/3: 368/272/368 values) ->
+   depuncture + Viterbi + pack -> n x {30,18,26} bytes */
+int m17b_viterbi_punctured(m17b_ctx *ctx, int pattern, const float *d_soft, int64_t n, uint8_t *d_bytes, void *stream);
+
+/* ------------------------------------------------------------------ RX chain */
+/* nchan channels, at most max_blocks 40-ms blocks per call */
+int m17b_rx_create(m17b_ctx *ctx, int64_t nchan, int64_t max_blocks, m17b_rx **out);
+int m17b_rx_destroy(m17b_rx *rx);
+/* m17_rx_init + m17_rx_sync_init initial state for every channel (m17_rx_frame.cpp:183-186, m17_rx_sync.cpp:124-127) */
+int m17b_rx_reset(m17b_rx *rx, void *stream);
+/* radio_set_afc_on/off: only 'off' is supported by the block-parallel front end (returns M17B_E_UNSUPPORTED otherwise) */
+int m17b_rx_set_afc(m17b_rx *rx, int on);
+/* m17_dsp_rx (m17_dsp.cpp:461-476) for nchan channels x nblocks blocks: d_iq = int16 [nchan][nblocks*1920][2] */
+int m17b_dsp_rx(m17b_rx *rx, const int16_t *d_iq, int64_t nblocks, void *stream);
+/* baseband seam (m17_test.cpp:49-51): m17_rx_sync_samples + m17_rx_symbols on d_disc = float [nchan][nblocks*384] */
+int m17b_rx_baseband(m17b_rx *rx, const float *d_disc, int64_t nblocks, void *stream);
+/* device views of the last call's results (valid until the next call on this rx) */
+typedef struct {
+    int64_t nchan, nblocks;
+    const m17b_frame_rec *d_frames; int64_t frame_cap; const int32_t *d_nframes;   /* [nchan][frame_cap], [nchan] */
+    const float *d_syms; int64_t sym_pitch, sym_carry; const int32_t *d_nsym;      /* [nchan][sym_pitch] (new symbols start at sym_carry), [nchan][nblocks] */
+    const int32_t *d_sym_base;                                                     /* [nchan] stream index of d_syms[c][sym_carry] */
+    const float *d_disc; const float *d_mean;                                      /* [nchan][nblocks][384] raw, [nchan][nblocks] (NULL on the baseband seam) */
+    const m17b_event_rec *d_events; int64_t event_cap; const int32_t *d_nevents;   /* [nchan][event_cap], [nchan] */
+    const uint64_t *d_stats;                                                       /* [nchan][8]: frames, stream frames, golay errs, delivered, aos, los, lsf events, symbols */
+} m17b_rx_view;
+int m17b_rx_get_view(m17b_rx *rx, m17b_rx_view *out);
+/* end-to-end form with HOST buffers (pinned or pageable): H2D of the IQ, the chain, D2H of records.
+   h_frames [nchan][frame_cap] (frame_cap from m17b_rx_frame_cap), h_nframes [nchan]; synchronises the stream. */
+int64_t m17b_rx_frame_cap(const m17b_rx *rx);
+int m17b_dsp_rx_host(m17b_rx *rx, const int16_t *h_iq, int64_t nblocks, m17b_frame_rec *h_frames, int32_t *h_nframes, void *stream);
+/* number of kernels the last m17b_dsp_rx / m17b_rx_baseband call launched */
+int m17b_rx_last_launches(const m17b_rx *rx);
+
+/* ------------------------------------------------------------------ TX chain */
+/* oversample: radio_get_oversample() (radio.cpp:211-219), 10 or 80; m17_mod_init (m17_modulate.cpp:65-76) */
+int m17b_tx_create(m17b_ctx *ctx, int64_t nchan, int oversample, m17b_tx **out);
+int m17b_tx_destroy(m17b_tx *tx);
+int m17b_tx_reset(m17b_tx *tx, void *stream);
+/* build_lich (m17_tx_routines.cpp:37-53): d_lsf [nchan][30] becomes each channel's m_lich; counters reset (:98-99) */
+int m17b_tx_set_lsf(m17b_tx *tx, const uint8_t *d_lsf, void *stream);
+/* m17_fmt_add_tx_preamble / m17_fmt_add_eot (m17_tx_routines.cpp:24-31,242-255): [192] dibits, host helper */
+int m17b_fmt_preamble(uint8_t *h_dibits);
+int m17b_fmt_eot(uint8_t *h_dibits);
+/* m17_fmt_add_link_setup_frame (m17_tx_routines.cpp:92-117, encoded with adequately sized buffers: SURVEY D1):
+   d_lsf [n][30] -> d_dibits [n][192] */
+int m17b_fmt_link_setup_frame(m17b_ctx *ctx, const uint8_t *d_lsf, int64_t n, uint8_t *d_dibits, void *stream);
+/* m17_fmt_add_stream_frame (m17_tx_routines.cpp:143-187) for F consecutive frames per channel:
+   d_payload [nchan][F][16] -> d_dibits [nchan][F][192]; advances each channel's m_lich_count / m_fn */
+int m17b_fmt_stream_frames(m17b_tx *tx, const uint8_t *d_payload, int64_t F, uint8_t *d_dibits, void *stream);
+/* m17_fmt_add_packet (m17_tx_routines.cpp:201-222, safe buffers: D2): d_chunk [n][25], d_meta [n] (= eof<<7 | nf<<2) */
+int m17b_fmt_packet_frames(m17b_ctx *ctx, const uint8_t *d_chunk, const uint8_t *d_meta, int64_t n, uint8_t *d_dibits, void *stream);
+/* m17_fmt_add_bert_frame (m17_tx_routines.cpp:226-238, intended behaviour: D5): F frames per channel */
+int m17b_fmt_bert_frames(m17b_tx *tx, int64_t F, uint8_t *d_dibits, void *stream);
+/* m17_mod_dibits / m17_mod_carrier (m17_modulate.cpp:42-61,79-92): d_syms [nchan][nsym] (0..3 dibit, 4 = carrier)
+   -> d_iq int16 [nchan][nsym*os][2]; d_freq (optional) float [nchan][nsym*os] = the filtered deviation m_sum */
+int m17b_mod_dibits(m17b_tx *tx, const uint8_t *d_syms, int64_t nsym, int16_t *d_iq, float *d_freq, void *stream);
+
+/* ------------------------------------------------------------------ equaliser (m17_equalize.cpp) */
+int m17b_eq_create(m17b_ctx *ctx, int64_t nchan, m17b_eq **out);   /* eq_open  :217-224 */
+int m17b_eq_destroy(m17b_eq *eq);
+int m17b_eq_reset(m17b_eq *eq, void *stream);                       /* eq_reset :137-141 */
+/* eq_train_known / eq_train_unknown (:163-213) for nsym symbols per channel: d_in [nchan][nsym][2],
+   d_train [nchan][nsym] or NULL (decision-directed) -> d_out [nchan][nsym] */
+int m17b_eq_train(m17b_eq *eq, const float *d_in, const float *d_train, int64_t nsym, float *d_out, void *stream);
+
+/* ------------------------------------------------------------------ synthetic channel (bench input only) */
+/* in-place AWGN on int16 IQ + carrier rotation; per-channel sigma (LSB units) and f0 (cycles/sample);
+   counter-based RNG, deterministic in (seed, channel, sample); never emits an exact (0,0) sample */
+int m17b_synth_channel(m17b_ctx *ctx, int16_t *d_iq, int64_t nchan, int64_t nsamp, const float *d_sigma, const float *d_f0,
+                       uint64_t seed, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* M17B200_H */

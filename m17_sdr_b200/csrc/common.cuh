@@ -1,0 +1,106 @@
+// common.cuh -- shared declarations for libm17b200 (single translation unit: m17b200.cu includes every part).
+//
+// Arithmetic contract: the whole TU is compiled with -fmad=false (no FMA contraction), IEEE sqrt/div
+// (nvcc defaults, no fast-math), no flush-to-zero.  The reference is a generic x86-64 -O3 build
+// (makefile:6: no -mfma, no -ffast-math), so with the same operand types and the same evaluation
+// order the fp32 results are bit-identical.  m17b_ctx_create() runs a self-test that fails loudly if
+// the library was built with contraction enabled.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdlib.h>
+#include <math.h>
+#include "m17b200.h"
+
+#define M17B_NF 40          // polyphase branches      m17_rx_sync.cpp:3
+#define M17B_FN 31          // taps per branch         m17_rx_sync.cpp:4
+#define M17B_SYM_CARRY 192  // symbols of the previous call kept in front of the stream buffer
+
+void m17b_set_cuda_error(cudaError_t e, const char *file, int line);
+
+#define CUDA_TRY(x)                                                              \
+    do {                                                                         \
+        cudaError_t e__ = (x);                                                   \
+        if (e__ != cudaSuccess) { m17b_set_cuda_error(e__, __FILE__, __LINE__); return M17B_E_CUDA; } \
+    } while (0)
+#define KERNEL_CHECK() CUDA_TRY(cudaGetLastError())
+
+static inline cudaStream_t as_stream(void *s) { return (cudaStream_t)s; }
+
+// ---------------------------------------------------------------- soft-bit gather maps (constant memory)
+// One uint16 per CODED position of a frame type (or per LICH bit): where in the 192-symbol frame the soft
+// value comes from after de-randomise (m17_correlate.cpp:27-31), de-interleave (m17_interleave.cpp:8-12)
+// and de-puncture (m17_puncture.cpp:47-79) are folded together.
+//   bits 0..7 : frame symbol index 8..191        bit 8 : 1 = LSB soft bit (|m|-0.6666), 0 = MSB (-m)
+//   bit 9     : 1 = negate (randomiser bit set)  0xFFFF: punctured position -> 0.0f erasure
+#define MAP_ERASE 0xFFFFu
+#define MAP_LSB   0x100u
+#define MAP_NEG   0x200u
+
+struct GatherMaps {
+    uint16_t p1[488];    // LSF    : 244 steps
+    uint16_t p2[296];    // stream : 148 steps (type-3 bits 96..367)
+    uint16_t p3[420];    // packet : 210 steps
+    uint16_t lich[96];   // stream : 4 x 24 Golay bits
+};
+// TX-side maps: for final (interleaved, randomised) bit i of a frame -> which type-3 bit feeds it
+// (QPP is an involution) and, per type-3 bit, which coded (pre-puncture) position it is.
+struct TxMaps {
+    uint16_t qpp[368];   // pi(i) = (45 i + 92 i^2) mod 368          m17_interleave.cpp:5
+    uint8_t  rnd[368];   // randomiser bits, MSB first               m17_correlate.cpp:35-42
+    uint16_t unp1[368];  // kept index -> coded position, P1         m17_puncture.cpp:4-6
+    uint16_t unp2[368];  // P2 (first 368 kept positions)            m17_puncture.cpp:8
+    uint16_t unp3[368];  // P3                                       m17_puncture.cpp:10
+};
+
+// per-GPU context
+struct m17b_ctx {
+    int device;
+    uint16_t *d_crc;     // [256]   CRC-16/M17 byte table            m17_crc.cpp:8-24
+    uint16_t *d_genc;    // [4096]  Golay parity table               m17_golay.cpp:31-40
+    uint16_t *d_gerr;    // [4096]  Golay syndrome table             m17_golay.cpp:49-72
+    float    *d_mf;      // [40][31] matched-filter bank             m17_rx_sync.cpp:13
+    float    *d_md;      // [40][31] derivative bank                 m17_rx_sync.cpp:14
+    uint8_t  *d_prbs;    // [511]   PRBS9 sequence                   m17_prbs9.cpp:16-26
+    float     h_mf[M17B_NF * M17B_FN], h_md[M17B_NF * M17B_FN];
+};
+
+// ---------------------------------------------------------------- per-channel persistent RX state
+// Everything the reference keeps in file statics for one channel (SURVEY 8b "persistent state").
+struct RxChanState {
+    // front end: dsp_arctan_disc2 statics (m17_dsp.cpp:195-196)
+    float z0re, z0im, z1re, z1im;
+    float nz0re, nz0im, nz1re, nz1im;   // written by the front-end kernel, committed by the sync kernel (no read/write race
+                                        // between the block-parallel items of one channel)
+    int   disc_count;
+    // timing loop (m17_rx_sync.cpp:7-12,78)
+    int   clk, thr, index;
+    float sum, dif;
+    float tail[30];          // last 30 (mean-removed) discriminator samples = m_buff[1..30]
+    // framer (m17_rx_frame.cpp:14-18,104)
+    int   flock, fclk, ferr;
+    float win[8];            // m_sync sliding window (zeros after reset_sync)
+    float head[8];           // first 8 symbols of the frame being collected (m_f_sym[0..7])
+    int   frame_start;       // stream index of m_f_sym[0]
+    int   sym_total;         // symbols emitted so far (stream index of the next symbol)
+    int   prev_n;            // symbols written by the previous call (for the carry copy)
+    // parser (m17_rx_parse.cpp:5-7)
+    int   packet_idx;
+    uint8_t lsf[2][32];      // m_lsf[2][30] padded
+    uint8_t packet[800];     // m_packet
+};
+
+// ---------------------------------------------------------------- small device helpers
+__device__ __forceinline__ uint16_t crc16_step(uint16_t crc, uint8_t byte, const uint16_t *tab) {
+    // m17_crc.cpp:30-33
+    return (uint16_t)((crc << 8) ^ tab[((crc >> 8) ^ byte) & 0xFF]);
+}
+
+// demap one soft bit from a frame's symbols (m17_dsp.cpp:35-42): m = sym*cor; MSB soft = -m;
+// LSB soft = (float)(fabs(m) - 0.6666) with the subtraction in double, as the double literal forces.
+__device__ __forceinline__ float demap_soft(float sym, float cor, bool lsb) {
+    float m = sym * cor;
+    return lsb ? __double2float_rn((double)fabsf(m) - 0.6666) : -m;
+}

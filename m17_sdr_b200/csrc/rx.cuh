@@ -1,0 +1,260 @@
+// rx.cuh -- the batched RX chain object: per-channel state, stage buffers, kernel sequencing, and the
+// sequential per-channel LICH / packet bookkeeping.  Replaces m17_dsp_rx (m17_dsp.cpp:461-476) and the
+// stateful tail of m17_rx_parse.cpp (update_lich :71-85, parse_packet :34-51, delivery gate :148-158).
+//
+// Kernel sequence for one call over [nchan] x [nblocks]:
+//   k_frontend      (items = channel x block, lane per item)      int16 IQ -> raw discriminator + block mean
+//   k_sync_frame    (warp per channel, blocks in order)           -> symbol stream, frame records (type/flags)
+//   k_decode_frames (thread per frame)                            -> decoded bytes, Golay, CRC into the records
+//   k_post          (thread per channel, frames in order)         -> LICH cache, delivery / LSF-event flags, stats
+#pragma once
+#include "sync.cuh"
+
+struct m17b_rx {
+    m17b_ctx *ctx;
+    int64_t nchan, max_blocks, last_blocks;
+    int64_t sym_pitch, fcap, ecap;
+    RxChanState *d_state;
+    float *d_disc, *d_mean;
+    float *d_syms;
+    int32_t *d_nsym, *d_sym_base, *d_nframes, *d_nevents;
+    m17b_frame_rec *d_frames;
+    m17b_event_rec *d_events;
+    unsigned long long *d_stats;
+    int16_t *d_iq_stage[2];           // staging for the _host entry point (double buffered over channel chunks)
+    int64_t stage_chunk;
+    cudaStream_t copy_stream;
+    cudaEvent_t ev_h2d[2], ev_done[2];
+    int afc, last_launches, seam_last;
+};
+
+__global__ void k_rx_reset(RxChanState *st, int64_t nchan) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchan) return;
+    // zero-initialised statics, then m17_rx_sync_init: m_clk = 1, m_thr = 0, m_index = 10 (m17_rx_sync.cpp:124-127)
+    uint32_t *w = (uint32_t *)(st + c);
+    for (int i = 0; i < (int)(sizeof(RxChanState) / 4); i++) w[i] = 0;
+    st[c].clk = 1;
+    st[c].index = 10;
+}
+
+// Sequential per-channel tail of m17_rx_parse: thread per channel, records in order.
+__global__ void k_post(m17b_frame_rec *frames, int64_t fcap, const int32_t *__restrict__ nframes, int64_t nchan, RxChanState *st,
+                       const uint16_t *__restrict__ g_crc, unsigned long long *stats) {
+    __shared__ uint16_t tab[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = g_crc[i];
+    __syncthreads();
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchan) return;
+    RxChanState *S = st + c;
+    auto crc30 = [&](const uint8_t *p) { uint16_t k = 0xFFFF; for (int i = 0; i < 30; i++) k = crc16_step(k, p[i], tab); return k; };
+    bool lsf_ok = crc30(S->lsf[1]) == 0;
+    unsigned long long n_stream = 0, n_gerr = 0, n_deliv = 0, n_lsf = 0;
+    const int n = nframes[c];
+    for (int k = 0; k < n; k++) {
+        m17b_frame_rec *r = frames + c * fcap + k;
+        int flags = r->flags;
+        if (!(flags & M17B_F_PARSED)) continue;
+        const int type = r->type;
+        if (type == M17B_T_LSF) {
+            // decode_link_frame checks the CRC of m_packet, not of the decoded bytes (m17_rx_parse.cpp:98);
+            // the honest verdict for the decoded LSF is r->crc == 0
+            if (crc30(S->packet) == 0) { flags |= M17B_F_LSF_EVENT; n_lsf++; }
+        } else if (type == M17B_T_STREAM) {
+            n_stream++;
+            n_gerr += r->golay_err;
+            const int seq = r->lich[5] >> 5;                                    // update_lich, m17_rx_parse.cpp:71-85
+            if (seq < 6) {
+                for (int i = 0; i < 5; i++) S->lsf[0][seq * 5 + i] = r->lich[i];
+                if (crc30(S->lsf[0]) == 0) {
+                    for (int i = 0; i < 30; i++) S->lsf[1][i] = S->lsf[0][i];
+                    lsf_ok = true;
+                    flags |= M17B_F_LSF_EVENT; n_lsf++;
+                }
+            }
+            if (lsf_ok) { flags |= M17B_F_DELIVERED; n_deliv++; }               // :148-158
+        } else if (type == M17B_T_PACKET) {
+            // parse_packet (m17_rx_parse.cpp:34-51) including its index bug; the copy is clamped to the buffer
+            const int eof = r->data[25] >> 7, fn = (r->data[25] >> 2) & 0x1F;
+            if (eof) {
+                int room = 800 - S->packet_idx, m = fn < room ? fn : room;
+                for (int i = 0; i < m; i++) S->packet[S->packet_idx + i] = r->data[i];
+                S->packet_idx = 0;
+            } else {
+                for (int i = 0; i < 25; i++) S->packet[fn * 25 + i] = r->data[i];
+                S->packet_idx = fn * 25;
+            }
+        }
+        r->flags = (uint8_t)flags;
+    }
+    unsigned long long *q = stats + c * 8;
+    q[1] += n_stream; q[2] += n_gerr; q[3] += n_deliv; q[6] += n_lsf;
+}
+
+extern "C" int m17b_rx_destroy(m17b_rx *rx) {
+    if (!rx) return M17B_E_ARG;
+    cudaFree(rx->d_state); cudaFree(rx->d_disc); cudaFree(rx->d_mean); cudaFree(rx->d_syms); cudaFree(rx->d_nsym); cudaFree(rx->d_sym_base);
+    cudaFree(rx->d_nframes); cudaFree(rx->d_nevents); cudaFree(rx->d_frames); cudaFree(rx->d_events); cudaFree(rx->d_stats);
+    for (int i = 0; i < 2; i++) {
+        if (rx->d_iq_stage[i]) cudaFree(rx->d_iq_stage[i]);
+        if (rx->ev_h2d[i]) cudaEventDestroy(rx->ev_h2d[i]);
+        if (rx->ev_done[i]) cudaEventDestroy(rx->ev_done[i]);
+    }
+    if (rx->copy_stream) cudaStreamDestroy(rx->copy_stream);
+    free(rx);
+    return M17B_OK;
+}
+
+extern "C" int m17b_rx_reset(m17b_rx *rx, void *stream) {
+    if (!rx) return M17B_E_ARG;
+    cudaStream_t st = as_stream(stream);
+    k_rx_reset<<<grid_for(rx->nchan, 128), 128, 0, st>>>(rx->d_state, rx->nchan);
+    KERNEL_CHECK();
+    CUDA_TRY(cudaMemsetAsync(rx->d_syms, 0, sizeof(float) * rx->nchan * rx->sym_pitch, st));
+    CUDA_TRY(cudaMemsetAsync(rx->d_stats, 0, sizeof(unsigned long long) * rx->nchan * 8, st));
+    CUDA_TRY(cudaMemsetAsync(rx->d_nframes, 0, sizeof(int32_t) * rx->nchan, st));
+    CUDA_TRY(cudaMemsetAsync(rx->d_nevents, 0, sizeof(int32_t) * rx->nchan, st));
+    return M17B_OK;
+}
+
+extern "C" int m17b_rx_create(m17b_ctx *ctx, int64_t nchan, int64_t max_blocks, m17b_rx **out) {
+    if (!ctx || !out || nchan <= 0 || max_blocks <= 0) return M17B_E_ARG;
+    *out = nullptr;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    m17b_rx *rx = (m17b_rx *)calloc(1, sizeof(m17b_rx));
+    if (!rx) return M17B_E_NOMEM;
+    rx->ctx = ctx; rx->nchan = nchan; rx->max_blocks = max_blocks;
+    rx->sym_pitch = (M17B_SYM_CARRY + max_blocks * M17B_SYM_CAP_PER_BLOCK + 3) & ~(int64_t)3;
+    rx->fcap = max_blocks + max_blocks / 64 + 4;
+    rx->ecap = 2 * rx->fcap + 4;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+    A((void **)&rx->d_state, sizeof(RxChanState) * nchan);
+    A((void **)&rx->d_disc, sizeof(float) * nchan * max_blocks * 384);
+    A((void **)&rx->d_mean, sizeof(float) * nchan * max_blocks);
+    A((void **)&rx->d_syms, sizeof(float) * nchan * rx->sym_pitch);
+    A((void **)&rx->d_nsym, sizeof(int32_t) * nchan * max_blocks);
+    A((void **)&rx->d_sym_base, sizeof(int32_t) * nchan);
+    A((void **)&rx->d_nframes, sizeof(int32_t) * nchan);
+    A((void **)&rx->d_nevents, sizeof(int32_t) * nchan);
+    A((void **)&rx->d_frames, sizeof(m17b_frame_rec) * nchan * rx->fcap);
+    A((void **)&rx->d_events, sizeof(m17b_event_rec) * nchan * rx->ecap);
+    A((void **)&rx->d_stats, sizeof(unsigned long long) * nchan * 8);
+    if (e != cudaSuccess) { m17b_set_cuda_error(e, __FILE__, __LINE__); m17b_rx_destroy(rx); return e == cudaErrorMemoryAllocation ? M17B_E_NOMEM : M17B_E_CUDA; }
+    int rc = m17b_rx_reset(rx, nullptr);
+    if (rc) { m17b_rx_destroy(rx); return rc; }
+    CUDA_TRY(cudaStreamSynchronize(nullptr));
+    *out = rx;
+    return M17B_OK;
+}
+
+extern "C" int m17b_rx_set_afc(m17b_rx *rx, int on) {
+    if (!rx) return M17B_E_ARG;
+    // dsp_nco_mixer + radio_afc (m17_dsp.cpp:390-408, radio.cpp:196-208) make the front end block-serial; not built yet
+    if (on) return M17B_E_UNSUPPORTED;
+    rx->afc = 0;
+    return M17B_OK;
+}
+
+// stages 2..4 for channels [c0, c0+nc)
+static int rx_back_half(m17b_rx *rx, int64_t c0, int64_t nc, const float *disc, const float *mean, int64_t T, int commit_fe, cudaStream_t st) {
+    m17b_ctx *ctx = rx->ctx;
+    const unsigned g = grid_for(nc, SY_WARPS);
+    float *syms = rx->d_syms + c0 * rx->sym_pitch;
+    m17b_frame_rec *frames = rx->d_frames + c0 * rx->fcap;
+    if (mean)
+        k_sync_frame<true><<<g, SY_WARPS * 32, 0, st>>>(disc, mean, nc, T, rx->d_state + c0, ctx->d_mf, ctx->d_md, syms, rx->sym_pitch,
+                                                       rx->d_nsym + c0 * T, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0,
+                                                       rx->d_events + c0 * rx->ecap, rx->ecap, rx->d_nevents + c0, rx->d_stats + c0 * 8, commit_fe);
+    else
+        k_sync_frame<false><<<g, SY_WARPS * 32, 0, st>>>(disc, nullptr, nc, T, rx->d_state + c0, ctx->d_mf, ctx->d_md, syms, rx->sym_pitch,
+                                                        rx->d_nsym + c0 * T, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0,
+                                                        rx->d_events + c0 * rx->ecap, rx->ecap, rx->d_nevents + c0, rx->d_stats + c0 * 8, commit_fe);
+    KERNEL_CHECK();
+    int rc = launch_decode(ctx, syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0, nc, nullptr, st);
+    if (rc) return rc;
+    k_post<<<grid_for(nc, 64), 64, 0, st>>>(frames, rx->fcap, rx->d_nframes + c0, nc, rx->d_state + c0, ctx->d_crc, rx->d_stats + c0 * 8);
+    KERNEL_CHECK();
+    rx->last_launches += 3;
+    return M17B_OK;
+}
+
+static int rx_chain(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t *d_iq, int64_t T, cudaStream_t st) {
+    float *disc = rx->d_disc + c0 * T * 384, *mean = rx->d_mean + c0 * T;
+    k_frontend<<<grid_for(nc * T, FE_WARPS * 32), FE_WARPS * 32, 0, st>>>((const uint32_t *)d_iq, nc, T, rx->d_state + c0, disc, mean);
+    KERNEL_CHECK();
+    rx->last_launches += 1;
+    return rx_back_half(rx, c0, nc, disc, mean, T, 1, st);
+}
+
+extern "C" int m17b_dsp_rx(m17b_rx *rx, const int16_t *d_iq, int64_t nblocks, void *stream) {
+    if (!rx || !d_iq || nblocks <= 0) return M17B_E_ARG;
+    if (nblocks > rx->max_blocks) return M17B_E_CAPACITY;
+    if (rx->afc) return M17B_E_UNSUPPORTED;
+    rx->last_launches = 0; rx->last_blocks = nblocks; rx->seam_last = 0;
+    return rx_chain(rx, 0, rx->nchan, d_iq, nblocks, as_stream(stream));
+}
+
+extern "C" int m17b_rx_baseband(m17b_rx *rx, const float *d_disc, int64_t nblocks, void *stream) {
+    if (!rx || !d_disc || nblocks <= 0) return M17B_E_ARG;
+    if (nblocks > rx->max_blocks) return M17B_E_CAPACITY;
+    rx->last_launches = 0; rx->last_blocks = nblocks; rx->seam_last = 1;
+    return rx_back_half(rx, 0, rx->nchan, d_disc, nullptr, nblocks, 0, as_stream(stream));
+}
+
+extern "C" int m17b_rx_get_view(m17b_rx *rx, m17b_rx_view *v) {
+    if (!rx || !v) return M17B_E_ARG;
+    v->nchan = rx->nchan; v->nblocks = rx->last_blocks;
+    v->d_frames = rx->d_frames; v->frame_cap = rx->fcap; v->d_nframes = rx->d_nframes;
+    v->d_syms = rx->d_syms; v->sym_pitch = rx->sym_pitch; v->sym_carry = M17B_SYM_CARRY; v->d_nsym = rx->d_nsym;
+    v->d_sym_base = rx->d_sym_base;
+    v->d_disc = rx->seam_last ? nullptr : rx->d_disc; v->d_mean = rx->seam_last ? nullptr : rx->d_mean;
+    v->d_events = rx->d_events; v->event_cap = rx->ecap; v->d_nevents = rx->d_nevents;
+    v->d_stats = (const uint64_t *)rx->d_stats;
+    return M17B_OK;
+}
+extern "C" int64_t m17b_rx_frame_cap(const m17b_rx *rx) { return rx ? rx->fcap : 0; }
+extern "C" int m17b_rx_last_launches(const m17b_rx *rx) { return rx ? rx->last_launches : 0; }
+
+// End-to-end entry point with host buffers: channels are processed in chunks so the H2D copy of chunk k+1
+// overlaps the kernels of chunk k (two staging buffers, a dedicated copy stream); records stream back per chunk.
+extern "C" int m17b_dsp_rx_host(m17b_rx *rx, const int16_t *h_iq, int64_t nblocks, m17b_frame_rec *h_frames, int32_t *h_nframes, void *stream) {
+    if (!rx || !h_iq || !h_frames || !h_nframes || nblocks <= 0) return M17B_E_ARG;
+    if (nblocks > rx->max_blocks) return M17B_E_CAPACITY;
+    if (rx->afc) return M17B_E_UNSUPPORTED;
+    cudaStream_t st = as_stream(stream);
+    const int64_t T = nblocks;
+    if (!rx->copy_stream) {
+        // chunk: about 64 MiB of IQ per staging buffer, at least 32 channels
+        int64_t per_chan = rx->max_blocks * 7680;
+        int64_t chunk = (64ll << 20) / per_chan;
+        if (chunk < 32) chunk = 32;
+        if (chunk > rx->nchan) chunk = rx->nchan;
+        rx->stage_chunk = chunk;
+        CUDA_TRY(cudaStreamCreateWithFlags(&rx->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CUDA_TRY(cudaMalloc((void **)&rx->d_iq_stage[i], (size_t)chunk * per_chan));
+            CUDA_TRY(cudaEventCreateWithFlags(&rx->ev_h2d[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&rx->ev_done[i], cudaEventDisableTiming));
+        }
+    }
+    rx->last_launches = 0; rx->last_blocks = nblocks; rx->seam_last = 0;
+    const int64_t chunk = rx->stage_chunk;
+    int k = 0;
+    for (int64_t c0 = 0; c0 < rx->nchan; c0 += chunk, k ^= 1) {
+        const int64_t nc = (rx->nchan - c0 < chunk) ? rx->nchan - c0 : chunk;
+        // the staging buffer may only be overwritten once the kernels that read it two chunks ago are done
+        CUDA_TRY(cudaStreamWaitEvent(rx->copy_stream, rx->ev_done[k], 0));
+        CUDA_TRY(cudaMemcpyAsync(rx->d_iq_stage[k], h_iq + c0 * T * 3840, (size_t)nc * T * 7680, cudaMemcpyHostToDevice, rx->copy_stream));
+        CUDA_TRY(cudaEventRecord(rx->ev_h2d[k], rx->copy_stream));
+        CUDA_TRY(cudaStreamWaitEvent(st, rx->ev_h2d[k], 0));
+        // note: the per-chunk front-end output lands at the chunk's own offset of d_disc (laid out for T = nblocks)
+        int rc = rx_chain(rx, c0, nc, rx->d_iq_stage[k], T, st);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(rx->ev_done[k], st));
+        CUDA_TRY(cudaMemcpyAsync(h_frames + c0 * rx->fcap, rx->d_frames + c0 * rx->fcap, sizeof(m17b_frame_rec) * nc * rx->fcap, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(h_nframes + c0, rx->d_nframes + c0, sizeof(int32_t) * nc, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return M17B_OK;
+}

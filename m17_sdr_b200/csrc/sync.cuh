@@ -1,0 +1,270 @@
+// sync.cuh -- RX matched filter + symbol-timing loop + sync-word correlator / framer, one WARP per channel.
+// Replaces m17_rx_sync_samples (+ rx_sync_filter, sync_update, m17_sync_adjust: m17_rx_sync.cpp:25-99) and
+// m17_rx_symbols / m17_rx_sym / m17_sync_check (m17_rx_frame.cpp:47-177).
+//
+// The timing loop is recursive (the polyphase branch m_index depends on an up/down counter fed by every
+// symbol), but the counter moves by at most 1 per symbol and the branch only changes when |m_thr| crosses the
+// threshold (10 unlocked / 80 locked).  So the warp SPECULATES: 32 lanes compute the next 32 symbols
+// (matched + derivative 31-tap dot products, sequential fp32 adds exactly as rx_sync_filter does) with the
+// current branch, a warp prefix-sum over the +-1 votes finds the first symbol at which the threshold would
+// trip, symbols up to there are committed, the branch is stepped and speculation restarts.  Results are
+// identical to the serial loop, including the forward bit-slip (a zero symbol inserted, one sample skipped),
+// the backward slip (a symbol dropped) and votes that straddle a block boundary.
+// The framer's unlocked search evaluates the 8-symbol sync window at 32 positions per step (warp ballot,
+// first hit wins); the locked path only counts symbols and checks each completed frame's head.
+#pragma once
+#include "frontend.cuh"
+
+#define SY_WARPS 4
+#define SY_XHALF 208          // (30 + 384) / 2 = 207 entries per parity
+#define SY_HIST  (8 + 208)
+
+struct SyncWarpSmem {
+    float xe[SY_XHALF], xo[SY_XHALF];   // discriminator samples incl. 30 of history, split by parity (conflict-free stride-2 windows)
+    float hist[SY_HIST];                // [0,8): sliding sync window carried in; [8, 8+n): symbols emitted in this block
+    float head[8];                      // m_f_sym[0..7] of the frame being collected
+};
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += o; }
+    return v;
+}
+
+// m17_sync_adjust (m17_rx_sync.cpp:45-72).  clk is the value m_clk has before the NEXT sample is processed.
+__device__ __forceinline__ void sync_adjust(int TH, int &thr, int &index, int &clk, int &m_idx, float *out, int lane) {
+    if (thr > TH) {
+        index = (index + 1 == M17B_NF) ? 0 : index + 1;
+        thr = 0;
+        if (index == 0) { clk = 1; if (m_idx >= 0 && lane == 0) out[m_idx] = 0.0f; m_idx++; }
+    }
+    if (thr < -TH) {
+        thr = 0;
+        index = (index == 0) ? M17B_NF - 1 : index - 1;
+        if (index == M17B_NF - 1) { clk = 1; m_idx--; }
+    }
+}
+
+template <bool HAS_MEAN>
+__global__ void __launch_bounds__(SY_WARPS * 32) k_sync_frame(const float *__restrict__ disc, const float *__restrict__ mean, int64_t nchan, int64_t T,
+                                                              RxChanState *st, const float *__restrict__ g_mf, const float *__restrict__ g_md,
+                                                              float *syms, int64_t sym_pitch, int32_t *__restrict__ nsym, int32_t *__restrict__ sym_base,
+                                                              m17b_frame_rec *frames, int64_t fcap, int32_t *__restrict__ nframes,
+                                                              m17b_event_rec *events, int64_t ecap, int32_t *__restrict__ nevents,
+                                                              unsigned long long *stats, int commit_fe) {
+    __shared__ SyncWarpSmem sm_all[SY_WARPS];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t c = (int64_t)blockIdx.x * SY_WARPS + wid;
+    if (c >= nchan) return;
+    SyncWarpSmem &sm = sm_all[wid];
+    RxChanState *S = st + c;
+    float *out = sm.hist + 8;
+
+    // ---- load state (uniform loads)
+    if (commit_fe && lane == 0) { S->z0re = S->nz0re; S->z0im = S->nz0im; S->z1re = S->nz1re; S->z1im = S->nz1im; }
+    int clk = S->clk, thr = S->thr, index = S->index;
+    float sumc = S->sum, difc = S->dif;
+    int flock = S->flock, fclk = S->fclk, ferr = S->ferr, frame_start = S->frame_start, sym_total = S->sym_total;
+    const int base_g = sym_total;
+    if (lane < 30) { float v = S->tail[lane]; ((lane & 1) ? sm.xo : sm.xe)[lane >> 1] = v; }
+    if (lane < 8) { sm.hist[lane] = S->win[lane]; sm.head[lane] = S->head[lane]; }
+    // carry: the last 192 symbols of the previous call move in front of the new ones
+    float *sbuf = syms + c * sym_pitch;
+    {
+        const int prev_n = S->prev_n;
+        float tmp[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) tmp[k] = sbuf[prev_n + lane + 32 * k];     // = sbuf[CARRY + prev_n - 192 + idx]
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 6; k++) sbuf[lane + 32 * k] = tmp[k];
+    }
+    if (lane == 0) sym_base[c] = base_g;
+    int nfr = 0, nev = 0, n_aos = 0, n_los = 0;
+    float cmf[M17B_FN], cmd[M17B_FN];
+    int tap_index = -1;
+    __syncwarp();
+
+    for (int64_t t = 0; t < T; t++) {
+        // ---- stage the block's 384 discriminator samples behind the 30 of history
+        {
+            const float *src = disc + (c * T + t) * 384;
+            const float mu = HAS_MEAN ? mean[c * T + t] : 0.0f;
+#pragma unroll
+            for (int q = 0; q < 12; q++) {
+                int j = lane + 32 * q;
+                float v = __ldg(src + j);
+                if (HAS_MEAN) v = v - mu;                                   // m17_dsp.cpp:217-219
+                int n = 30 + j;
+                ((n & 1) ? sm.xo : sm.xe)[n >> 1] = v;
+            }
+        }
+        __syncwarp();
+
+        // ---- timing loop (m17_rx_sync.cpp:77-99); m17_rx_lock() is constant inside a block
+        const int TH = flock ? 80 : 10;
+        int i = 0, m_idx = 0;
+        while (i < 384) {
+            if (clk == 1) {
+                // even-clock sample with no fresh symbol in this round: vote with the carried sum/dif (sync_update :38-42)
+                float dd = (sumc < 0) ? -difc : difc;
+                if (dd > 0) thr++;
+                if (dd < 0) thr--;
+                clk = 0;
+                sync_adjust(TH, thr, index, clk, m_idx, out, lane);
+                i++;
+                continue;
+            }
+            if (index != tap_index) {
+#pragma unroll
+                for (int k = 0; k < M17B_FN; k++) { cmf[k] = __ldg(g_mf + index * M17B_FN + k); cmd[k] = __ldg(g_md + index * M17B_FN + k); }
+                tap_index = index;
+            }
+            // speculate: lane l computes the symbol at sample j = i + 2l
+            const int j = i + 2 * lane;
+            const bool valid = j < 384;
+            float s = 0.0f, d = 0.0f;
+            if (valid) {
+                const float *A = (i & 1) ? sm.xo : sm.xe;
+                const float *B = (i & 1) ? sm.xe : sm.xo;
+                const int h = (i >> 1) + lane, ob = i & 1;
+                float x = A[h];
+                s = x * cmf[0];
+                d = x * cmd[0];
+#pragma unroll
+                for (int k = 1; k < M17B_FN; k++) {
+                    x = (k & 1) ? B[h + (k >> 1) + ob] : A[h + (k >> 1)];
+                    s += x * cmf[k];
+                    d += x * cmd[k];
+                }
+            }
+            const bool has_vote = valid && (j + 1 < 384);
+            int v = 0;
+            if (has_vote) { float dd = (s < 0) ? -d : d; v = (dd > 0) - (dd < 0); }
+            const int th = thr + warp_incl_scan(v, lane);
+            const unsigned trig = __ballot_sync(0xffffffffu, has_vote && (th > TH || th < -TH));
+            if (trig == 0) {
+                const int nv = __popc(__ballot_sync(0xffffffffu, valid));
+                if (valid && m_idx + lane >= 0) out[m_idx + lane] = s;
+                m_idx += nv;
+                thr = __shfl_sync(0xffffffffu, th, 31);
+                sumc = __shfl_sync(0xffffffffu, s, nv - 1);
+                difc = __shfl_sync(0xffffffffu, d, nv - 1);
+                const int last_j = i + 2 * (nv - 1);
+                if (last_j + 1 < 384) { i = last_j + 2; clk = 0; } else { i = 384; clk = 1; }
+            } else {
+                const int l = __ffs(trig) - 1;
+                if (lane <= l && m_idx + lane >= 0) out[m_idx + lane] = s;
+                m_idx += l + 1;
+                thr = __shfl_sync(0xffffffffu, th, l);
+                sumc = __shfl_sync(0xffffffffu, s, l);
+                difc = __shfl_sync(0xffffffffu, d, l);
+                clk = 0;
+                __syncwarp();
+                sync_adjust(TH, thr, index, clk, m_idx, out, lane);
+                i = i + 2 * l + 2;
+            }
+        }
+        const int n = m_idx < 0 ? 0 : m_idx;
+        __syncwarp();
+
+        // ---- emit the block's symbols to the channel's stream
+        {
+            float *dst = sbuf + M17B_SYM_CARRY + (sym_total - base_g);
+            for (int q = lane; q < n; q += 32) dst[q] = out[q];
+            if (lane == 0) nsym[c * T + t] = n;
+        }
+
+        // ---- framer (m17_rx_frame.cpp:126-172)
+        int p = 0, reset_at = -8;
+        while (p < n) {
+            if (!flock) {
+                int found = -1;
+                for (int q0 = p; q0 < n && found < 0; q0 += 32) {
+                    const int q = q0 + lane;
+                    bool ok = false;
+                    if (q < n) {
+                        float w[8];
+#pragma unroll
+                        for (int k = 0; k < 8; k++) { int idx = q - 7 + k; w[k] = (idx >= reset_at) ? sm.hist[8 + idx] : 0.0f; }
+                        ok = sync_accept(sync_check8(w), false);
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, ok);
+                    if (m) found = q0 + __ffs(m) - 1;
+                }
+                if (found < 0) { p = n; break; }
+                // acquisition: copy_sync(), m_fclk = 8 (m17_rx_frame.cpp:161-169)
+                if (lane < 8) { int idx = found - 7 + lane; sm.head[lane] = (idx >= reset_at) ? sm.hist[8 + idx] : 0.0f; }
+                fclk = 8; ferr = 0; flock = 1;
+                frame_start = sym_total + found - 7;
+                if (lane == 0 && nev < ecap) { events[c * ecap + nev].sym_idx = sym_total + found; events[c * ecap + nev].kind = M17B_EV_AOS; }
+                nev++; n_aos++;
+                p = found + 1;
+                __syncwarp();
+            } else {
+                const int need = M17B_FRAME_SYMS - fclk, avail = n - p;
+                const int take = need < avail ? need : avail;
+                if (fclk < 8 && lane < 8 && lane >= fclk && lane < fclk + take) sm.head[lane] = sm.hist[8 + p + lane - fclk];
+                fclk += take;
+                p += take;
+                __syncwarp();
+                if (fclk == M17B_FRAME_SYMS) {
+                    fclk = 0;
+                    float w[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) w[k] = sm.head[k];
+                    const SyncResult r = sync_check8(w);
+                    const bool ok = sync_accept(r, true);
+                    int flags = ok ? M17B_F_SYNC_OK : 0, fe;
+                    bool los = false;
+                    if (r.type == M17B_T_EOT) { los = true; fe = ferr; }                       // :137-140
+                    else if (ok) { flags |= M17B_F_PARSED; ferr = 0; fe = 0; }                 // :144-146
+                    else { ferr++; fe = ferr; if (ferr > 5) los = true; else flags |= M17B_F_PARSED; }   // :147-154
+                    if (los) flags |= M17B_F_LOS;
+                    if (nfr < fcap && lane < 16) {
+                        uint32_t word = 0;
+                        if (lane == 0) word = (uint32_t)frame_start;
+                        else if (lane == 1) word = (uint32_t)r.type | ((uint32_t)flags << 8);
+                        else if (lane == 11) word = ((uint32_t)r.votes << 16) | ((uint32_t)fe << 24);
+                        else if (lane == 12) word = __float_as_uint(r.variance);
+                        ((uint32_t *)(frames + c * fcap + nfr))[lane] = word;
+                    }
+                    nfr++;
+                    if (los) {
+                        flock = 0;
+                        reset_at = p;                                                           // reset_sync(): window reads as zeros
+                        if (lane == 0 && nev < ecap) { events[c * ecap + nev].sym_idx = sym_total + p - 1; events[c * ecap + nev].kind = M17B_EV_LOS; }
+                        nev++; n_los++;
+                    }
+                    frame_start = sym_total + p;
+                    __syncwarp();
+                }
+            }
+        }
+        // ---- carry: sliding window = last 8 symbols (zeros before a reset), filter history = last 30 samples
+        {
+            float wv = 0.0f, a = 0.0f, b = 0.0f;
+            if (lane < 8) { int idx = n - 8 + lane; wv = (idx >= reset_at) ? sm.hist[8 + idx] : 0.0f; }
+            if (lane < 15) { a = sm.xe[192 + lane]; b = sm.xo[192 + lane]; }
+            __syncwarp();
+            if (lane < 8) sm.hist[lane] = wv;
+            if (lane < 15) { sm.xe[lane] = a; sm.xo[lane] = b; }
+        }
+        sym_total += n;
+        __syncwarp();
+    }
+
+    // ---- store state
+    if (lane < 30) S->tail[lane] = ((lane & 1) ? sm.xo : sm.xe)[lane >> 1];
+    if (lane < 8) { S->win[lane] = sm.hist[lane]; S->head[lane] = sm.head[lane]; }
+    if (lane == 0) {
+        S->clk = clk; S->thr = thr; S->index = index; S->sum = sumc; S->dif = difc;
+        S->flock = flock; S->fclk = fclk; S->ferr = ferr; S->frame_start = frame_start; S->sym_total = sym_total;
+        S->prev_n = sym_total - base_g;
+        nframes[c] = nfr < fcap ? nfr : (int)fcap;
+        nevents[c] = nev < ecap ? nev : (int)ecap;
+        unsigned long long *q = stats + c * 8;
+        q[0] += (unsigned long long)nfr; q[4] += (unsigned long long)n_aos; q[5] += (unsigned long long)n_los;
+        q[7] += (unsigned long long)(sym_total - base_g);
+    }
+}

@@ -1,0 +1,438 @@
+// tx.cuh -- batched TX: frame formatters (CRC'd LSF / stream / packet / BERT -> 192 dibits) and the 4FSK
+// modulator (polyphase RRC x os -> fp32 phase accumulator -> cos/sin -> int16 IQ).
+// Replaces m17_fmt_add_* (m17_tx_routines.cpp:24-31,92-117,143-187,201-255) and m17_mod_dibits / mod_filter /
+// sub_filter / mod_fsk (m17_modulate.cpp:22-61,79-92).
+//
+// Formatter mapping: one thread per OUTPUT DIBIT.  Interleave + randomise + puncture are folded into
+// constant-memory index maps, and a convolutional-code output bit depends on only 5 input bits, so every
+// dibit of every frame is computed independently (fully coalesced stores, no per-frame scratch).
+// Modulator mapping: (1) FIR: thread per output sample, 31 sequential fp32 MACs (the reference's order);
+// (2) phase scan: the accumulator m_acc is a sequential fp32 sum per channel, so one lane per channel walks
+// its samples through [32 ch][32 sample] shared-memory tiles; (3) cos/sin + int16 conversion: thread per sample.
+#pragma once
+#include "rx.cuh"
+
+struct TxChanState {
+    float hist[31];      // deviation of the last 31 symbols = m_tx_s (m17_modulate.cpp:8)
+    float acc;           // m_acc (m17_modulate.cpp:14)
+    uint8_t lich[32];    // m_lich (m17_tx_routines.cpp:13)
+    int lich_count, fn, prbs_idx;
+};
+struct m17b_tx {
+    m17b_ctx *ctx;
+    int64_t nchan;
+    int os;
+    float *d_taps;       // 31*os
+    TxChanState *d_state;
+    float *d_work; int64_t work_syms;
+};
+__constant__ float c_dev[5];   // dibit -> deviation (rad/sample), m17_modulate.cpp:9; [4] = blank carrier
+
+// ---------------------------------------------------------------- formatters
+struct FmtSrc {
+    const uint8_t *bytes;   // info bytes of this frame (LSF 30 / stream payload 16 / packet chunk 25) or PRBS table
+    int fn;                 // stream: frame number
+    int meta;               // packet: byte 25
+    int prbs0;              // bert: PRBS phase of the frame's first bit
+};
+template <int MODE> __device__ __forceinline__ uint32_t info_bit(const FmtSrc &s, int q) {
+    if (MODE == 1) return (s.bytes[q >> 3] >> (7 - (q & 7))) & 1u;                                   // LSF, 240 bits
+    if (MODE == 2) {                                                                                 // FN(16) + payload(128)
+        if (q < 16) return ((uint32_t)s.fn >> (15 - q)) & 1u;
+        int r = q - 16;
+        return (s.bytes[r >> 3] >> (7 - (r & 7))) & 1u;
+    }
+    if (MODE == 3) {                                                                                 // chunk(200) + meta(8)
+        if (q < 200) return (s.bytes[q >> 3] >> (7 - (q & 7))) & 1u;
+        return ((uint32_t)s.meta >> (207 - q)) & 1u;
+    }
+    return s.bytes[(s.prbs0 + q) % 511];                                                             // BERT, 197 PRBS9 bits
+}
+template <int MODE> __device__ __forceinline__ uint32_t coded_bit(const FmtSrc &s, int p) {
+    constexpr int NB = MODE == 1 ? 240 : MODE == 2 ? 144 : MODE == 3 ? 208 : 197;
+    uint32_t pr = conv_pair(conv_reg([&](int q) { return info_bit<MODE>(s, q); }, p >> 1, NB));
+    return (p & 1) ? (pr & 1u) : (pr >> 1);
+}
+// type-3 bit j (before interleaving) of a frame
+template <int MODE> __device__ __forceinline__ uint32_t type3_bit(const FmtSrc &s, const uint32_t *golay, int j) {
+    if (MODE == 1) return coded_bit<1>(s, c_tx.unp1[j]);
+    if (MODE == 2) {
+        if (j < 96) return (golay[j / 24] >> (23 - (j % 24))) & 1u;                                  // pack_24_to_1
+        return coded_bit<2>(s, c_tx.unp2[j - 96]);
+    }
+    if (MODE == 3) return coded_bit<3>(s, c_tx.unp3[j]);
+    return coded_bit<4>(s, c_tx.unp2[j]);
+}
+template <int MODE>
+__global__ void k_fmt(const uint8_t *src, const uint8_t *meta, int64_t nframes, int64_t F, const TxChanState *st, uint8_t *dibits,
+                      const uint16_t *genc, const uint8_t *prbs) {
+    int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= nframes * 192) return;
+    const int64_t f = gid / 192;
+    const int sidx = (int)(gid % 192);
+    constexpr uint32_t SYNCW = MODE == 1 ? 0x55F7u : MODE == 2 ? 0xFF5Du : MODE == 3 ? 0x75FFu : 0xDF55u;
+    if (sidx < 8) { dibits[gid] = (uint8_t)((SYNCW >> (14 - 2 * sidx)) & 3u); return; }               // pack_16_to_2
+    FmtSrc s; s.fn = 0; s.meta = 0; s.prbs0 = 0; s.bytes = nullptr;
+    uint32_t golay[4] = {0, 0, 0, 0};
+    if (MODE == 1) s.bytes = src + f * 30;
+    if (MODE == 3) { s.bytes = src + f * 25; s.meta = meta[f]; }
+    if (MODE == 2 || MODE == 4) {
+        const int64_t c = f / F;
+        const int k = (int)(f % F);
+        const TxChanState &S = st[c];
+        if (MODE == 2) {
+            s.bytes = src + f * 16;
+            s.fn = (S.fn + k) & 0xFFFF;
+            const int lc = (S.lich_count + k) % 6;
+            uint32_t b[6];
+#pragma unroll
+            for (int i = 0; i < 5; i++) b[i] = S.lich[lc * 5 + i];
+            b[5] = (uint32_t)(lc & 7) << 5;
+            uint32_t dw[4] = {(b[0] << 4) | (b[1] >> 4), ((b[1] & 15u) << 8) | b[2], (b[3] << 4) | (b[4] >> 4), ((b[4] & 15u) << 8) | b[5]};
+#pragma unroll
+            for (int i = 0; i < 4; i++) golay[i] = (dw[i] << 12) | __ldg(&genc[dw[i]]);               // m17_golay_encode
+        } else {
+            s.bytes = prbs;
+            s.prbs0 = (S.prbs_idx + k * 197) % 511;
+        }
+    }
+    const int i0 = 2 * (sidx - 8), i1 = i0 + 1;
+    // interleave (out[pi(j)] = in[j], pi an involution) then randomise (XOR), then dibit = b[i]<<1 | b[i+1]
+    uint32_t b0 = type3_bit<MODE>(s, golay, c_tx.qpp[i0]) ^ c_tx.rnd[i0];
+    uint32_t b1 = type3_bit<MODE>(s, golay, c_tx.qpp[i1]) ^ c_tx.rnd[i1];
+    dibits[gid] = (uint8_t)((b0 << 1) | b1);
+}
+__global__ void k_tx_advance(TxChanState *st, int64_t nchan, int dfn, int dlich, int dprbs) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchan) return;
+    st[c].fn = (st[c].fn + dfn) & 0xFFFF;
+    st[c].lich_count = (st[c].lich_count + dlich) % 6;
+    st[c].prbs_idx = (st[c].prbs_idx + dprbs) % 511;
+}
+__global__ void k_tx_set_lsf(TxChanState *st, int64_t nchan, const uint8_t *lsf) {
+    int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= nchan * 32) return;
+    int64_t c = gid / 32;
+    int i = (int)(gid % 32);
+    st[c].lich[i] = i < 30 ? lsf[c * 30 + i] : 0;
+    if (i == 0) { st[c].lich_count = 0; st[c].fn = 0; }                                              // m17_tx_routines.cpp:98-99
+}
+
+extern "C" int m17b_fmt_preamble(uint8_t *d) { if (!d) return M17B_E_ARG; for (int i = 0; i < 192; i += 2) { d[i] = 1; d[i + 1] = 3; } return M17B_OK; }
+extern "C" int m17b_fmt_eot(uint8_t *d) { if (!d) return M17B_E_ARG; for (int i = 0; i < 192; i++) d[i] = (i & 7) == 6 ? 3 : 1; return M17B_OK; }
+extern "C" int m17b_fmt_link_setup_frame(m17b_ctx *ctx, const uint8_t *d_lsf, int64_t n, uint8_t *d_dibits, void *stream) {
+    if (!ctx || !d_lsf || !d_dibits || n < 0) return M17B_E_ARG;
+    if (n == 0) return M17B_OK;
+    k_fmt<1><<<grid_for(n * 192, 192), 192, 0, as_stream(stream)>>>(d_lsf, nullptr, n, 1, nullptr, d_dibits, ctx->d_genc, ctx->d_prbs);
+    KERNEL_CHECK();
+    return M17B_OK;
+}
+extern "C" int m17b_fmt_packet_frames(m17b_ctx *ctx, const uint8_t *d_chunk, const uint8_t *d_meta, int64_t n, uint8_t *d_dibits, void *stream) {
+    if (!ctx || !d_chunk || !d_meta || !d_dibits || n < 0) return M17B_E_ARG;
+    if (n == 0) return M17B_OK;
+    k_fmt<3><<<grid_for(n * 192, 192), 192, 0, as_stream(stream)>>>(d_chunk, d_meta, n, 1, nullptr, d_dibits, ctx->d_genc, ctx->d_prbs);
+    KERNEL_CHECK();
+    return M17B_OK;
+}
+extern "C" int m17b_fmt_stream_frames(m17b_tx *tx, const uint8_t *d_payload, int64_t F, uint8_t *d_dibits, void *stream) {
+    if (!tx || !d_payload || !d_dibits || F < 0) return M17B_E_ARG;
+    if (F == 0) return M17B_OK;
+    cudaStream_t st = as_stream(stream);
+    k_fmt<2><<<grid_for(tx->nchan * F * 192, 192), 192, 0, st>>>(d_payload, nullptr, tx->nchan * F, F, tx->d_state, d_dibits, tx->ctx->d_genc, tx->ctx->d_prbs);
+    KERNEL_CHECK();
+    k_tx_advance<<<grid_for(tx->nchan, 128), 128, 0, st>>>(tx->d_state, tx->nchan, (int)(F & 0xFFFF), (int)(F % 6), 0);
+    KERNEL_CHECK();
+    return M17B_OK;
+}
+extern "C" int m17b_fmt_bert_frames(m17b_tx *tx, int64_t F, uint8_t *d_dibits, void *stream) {
+    if (!tx || !d_dibits || F < 0) return M17B_E_ARG;
+    if (F == 0) return M17B_OK;
+    cudaStream_t st = as_stream(stream);
+    k_fmt<4><<<grid_for(tx->nchan * F * 192, 192), 192, 0, st>>>(nullptr, nullptr, tx->nchan * F, F, tx->d_state, d_dibits, tx->ctx->d_genc, tx->ctx->d_prbs);
+    KERNEL_CHECK();
+    k_tx_advance<<<grid_for(tx->nchan, 128), 128, 0, st>>>(tx->d_state, tx->nchan, 0, 0, (int)((F * 197) % 511));
+    KERNEL_CHECK();
+    return M17B_OK;
+}
+extern "C" int m17b_tx_set_lsf(m17b_tx *tx, const uint8_t *d_lsf, void *stream) {
+    if (!tx || !d_lsf) return M17B_E_ARG;
+    k_tx_set_lsf<<<grid_for(tx->nchan * 32, 256), 256, 0, as_stream(stream)>>>(tx->d_state, tx->nchan, d_lsf);
+    KERNEL_CHECK();
+    return M17B_OK;
+}
+
+// ---------------------------------------------------------------- modulator
+// (1) polyphase RRC: sample n of channel c = sum_j s[j] * taps[(os-1-ph) + j*os], s = deviations of symbols k-30..k
+__global__ void k_mod_fir(const uint8_t *syms, int64_t nsym_total, int64_t k0, int64_t nk, int os, const float *__restrict__ taps,
+                          const TxChanState *st, int64_t nchan, float *work, float *freq) {
+    const int64_t per = nk * os;
+    int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= nchan * per) return;
+    const int64_t c = gid / per;
+    const int64_t n = gid % per;
+    const int64_t k = n / os;                  // symbol within the chunk
+    const int ph = (int)(n % os);
+    const float *cf = taps + (os - 1 - ph);
+    const uint8_t *sy = syms + c * nsym_total + k0;
+    const float *hist = st[c].hist;
+    float sum = 0;
+#pragma unroll
+    for (int j = 0; j < 31; j++) {
+        const int64_t kk = k - 30 + j;         // chunk-relative symbol index
+        const float s = (kk >= 0) ? c_dev[sy[kk]] : hist[31 + kk];
+        const float prod = s * __ldg(cf + j * os);
+        sum = (j == 0) ? prod : sum + prod;    // sum = s[0]*c[0]; sum += s[i]*c[i*os]  (m17_modulate.cpp:42-48)
+    }
+    work[gid] = sum;
+    if (freq) freq[c * nsym_total * os + k0 * os + n] = sum;
+}
+// (2) phase accumulation, lane per channel (m17_modulate.cpp:22-37): m_acc += f per sample (fp32), and once per symbol
+// the accumulator is wrapped through double: acc = acc/(2 pi); acc = modf(acc); acc = acc*2 pi, each store rounding to fp32.
+__global__ void __launch_bounds__(128) k_mod_scan(float *work, int64_t per, int os, TxChanState *st, int64_t nchan) {
+    __shared__ float tile[4][32][33];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t c0 = ((int64_t)blockIdx.x * 4 + wid) * 32;
+    if (c0 >= nchan) return;
+    const int64_t c = c0 + lane;
+    const bool live = c < nchan;
+    float acc = live ? st[c].acc : 0.0f;
+    int cnt = 0;
+    for (int64_t n0 = 0; n0 < per; n0 += 32) {
+        for (int r = 0; r < 32; r++) {
+            float v = 0;
+            if (c0 + r < nchan && n0 + lane < per) v = work[(c0 + r) * per + n0 + lane];
+            tile[wid][r][lane] = v;
+        }
+        __syncwarp();
+        const int lim = (per - n0 < 32) ? (int)(per - n0) : 32;
+        for (int s = 0; s < lim; s++) {
+            acc += tile[wid][lane][s];
+            tile[wid][lane][s] = acc;
+            if (++cnt == os) {
+                cnt = 0;
+                acc = (float)((double)acc / (2.0 * M_PI));
+                double ip = trunc((double)acc);
+                acc = (float)((double)acc - ip);                              // modf fractional part (exact)
+                acc = (float)((double)acc * 2.0 * M_PI);
+            }
+        }
+        __syncwarp();
+        for (int r = 0; r < 32; r++)
+            if (c0 + r < nchan && n0 + lane < per) work[(c0 + r) * per + n0 + lane] = tile[wid][r][lane];
+        __syncwarp();
+    }
+    if (live) st[c].acc = acc;
+}
+// (3) IQ: re = (int16)(cos(acc) * 0x3FFF), im = (int16)(sin(acc) * 0x3FFF), truncating (m17_modulate.cpp:25-26)
+__global__ void k_mod_iq(const float *work, int64_t per, int64_t out_pitch, int64_t out_off, int64_t nchan, int16_t *iq) {
+    int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= nchan * per) return;
+    const int64_t c = gid / per, n = gid % per;
+    float sn, cs;
+    sincosf(work[gid], &sn, &cs);
+    short2 o;
+    o.x = (short)__float2int_rz(cs * 16383.0f);
+    o.y = (short)__float2int_rz(sn * 16383.0f);
+    ((short2 *)iq)[c * out_pitch + out_off + n] = o;
+}
+__global__ void k_mod_hist(const uint8_t *syms, int64_t nsym_total, int64_t k0, int64_t nk, TxChanState *st, int64_t nchan) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchan) return;
+    float nh[31];
+#pragma unroll
+    for (int j = 0; j < 31; j++) {
+        int64_t kk = nk - 31 + j;
+        nh[j] = (kk >= 0) ? c_dev[syms[c * nsym_total + k0 + kk]] : st[c].hist[31 + kk];
+    }
+#pragma unroll
+    for (int j = 0; j < 31; j++) st[c].hist[j] = nh[j];
+}
+
+extern "C" int m17b_tx_destroy(m17b_tx *tx) {
+    if (!tx) return M17B_E_ARG;
+    cudaFree(tx->d_taps); cudaFree(tx->d_state); cudaFree(tx->d_work);
+    free(tx);
+    return M17B_OK;
+}
+extern "C" int m17b_tx_reset(m17b_tx *tx, void *stream) {
+    if (!tx) return M17B_E_ARG;
+    CUDA_TRY(cudaMemsetAsync(tx->d_state, 0, sizeof(TxChanState) * tx->nchan, as_stream(stream)));
+    return M17B_OK;
+}
+extern "C" int m17b_tx_create(m17b_ctx *ctx, int64_t nchan, int os, m17b_tx **out) {
+    if (!ctx || !out || nchan <= 0 || os <= 0 || os > 160) return M17B_E_ARG;
+    *out = nullptr;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    m17b_tx *tx = (m17b_tx *)calloc(1, sizeof(m17b_tx));
+    if (!tx) return M17B_E_NOMEM;
+    tx->ctx = ctx; tx->nchan = nchan; tx->os = os;
+    // m17_mod_init (m17_modulate.cpp:65-76): RRC alpha 0.5, 31*os taps, os samples/symbol, taps sum to 10
+    const int nt = 31 * os;
+    float *h = (float *)malloc(sizeof(float) * nt);
+    m17b_build_rrc_filter(h, 0.5f, nt, os);
+    m17b_set_filter_gain(h, 10, 1, nt);
+    int rc = upload(&tx->d_taps, h, nt);
+    free(h);
+    if (rc) { free(tx); return rc; }
+    const float dev[5] = {(float)(M_PI / 30.0), (float)(M_PI / 10.0), (float)(-M_PI / 30), (float)(-M_PI / 10.0), 0.0f};
+    CUDA_TRY(cudaMemcpyToSymbol(c_dev, dev, sizeof(dev)));
+    CUDA_TRY(cudaMalloc((void **)&tx->d_state, sizeof(TxChanState) * nchan));
+    CUDA_TRY(cudaMemset(tx->d_state, 0, sizeof(TxChanState) * nchan));
+    *out = tx;
+    return M17B_OK;
+}
+extern "C" int m17b_mod_dibits(m17b_tx *tx, const uint8_t *d_syms, int64_t nsym, int16_t *d_iq, float *d_freq, void *stream) {
+    if (!tx || !d_syms || !d_iq || nsym < 0) return M17B_E_ARG;
+    if (nsym == 0) return M17B_OK;
+    cudaStream_t st = as_stream(stream);
+    const int os = tx->os;
+    // chunk the time axis so the fp32 work buffer stays small (about 64 MiB)
+    int64_t chunk = (16ll << 20) / (tx->nchan * os);
+    if (chunk < 192) chunk = 192;
+    if (chunk > nsym) chunk = nsym;
+    if (tx->work_syms < chunk) {
+        if (tx->d_work) CUDA_TRY(cudaFree(tx->d_work));
+        tx->d_work = nullptr;
+        CUDA_TRY(cudaMalloc((void **)&tx->d_work, sizeof(float) * tx->nchan * chunk * os));
+        tx->work_syms = chunk;
+    }
+    for (int64_t k0 = 0; k0 < nsym; k0 += chunk) {
+        const int64_t nk = (nsym - k0 < chunk) ? nsym - k0 : chunk;
+        const int64_t per = nk * os;
+        k_mod_fir<<<grid_for(tx->nchan * per, 256), 256, 0, st>>>(d_syms, nsym, k0, nk, os, tx->d_taps, tx->d_state, tx->nchan, tx->d_work, d_freq);
+        k_mod_scan<<<grid_for(tx->nchan, 128), 128, 0, st>>>(tx->d_work, per, os, tx->d_state, tx->nchan);
+        k_mod_iq<<<grid_for(tx->nchan * per, 256), 256, 0, st>>>(tx->d_work, per, nsym * os, k0 * os, tx->nchan, d_iq);
+        k_mod_hist<<<grid_for(tx->nchan, 128), 128, 0, st>>>(d_syms, nsym, k0, nk, tx->d_state, tx->nchan);
+        KERNEL_CHECK();
+    }
+    return M17B_OK;
+}
+
+// ---------------------------------------------------------------- equaliser (m17_equalize.cpp), thread per channel
+struct EqState { float c[5], g[5], u[5][5], d[5], E, q, y, fbr, samples[5]; };
+struct m17b_eq { m17b_ctx *ctx; int64_t nchan; EqState *d_state; };
+__global__ void k_eq_reset(EqState *st, int64_t nchan, int full) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchan) return;
+    EqState &e = st[c];
+    if (full) {                                     // eq_open :217-224 (statics start at zero)
+        float *w = (float *)&e;
+        for (int i = 0; i < (int)(sizeof(EqState) / 4); i++) w[i] = 0.0f;
+        e.q = 0.08f; e.E = 0.01f;
+    }
+    for (int j = 0; j < 5; j++) { for (int i = 0; i < j; i++) e.u[i][j] = 0.0f; e.d[j] = 0.1f; }   // eq_k_reset_ud :25-36
+    for (int i = 0; i < 5; i++) e.c[i] = 0.0f;                                                     // eq_k_reset_coffs :14-22
+}
+__global__ void k_eq_train(EqState *st, int64_t nchan, const float *in, const float *train, int64_t nsym, float *out) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchan) return;
+    EqState e = st[c];
+    const float *x2 = in + c * nsym * 2;
+    for (int64_t n = 0; n < nsym; n++) {
+        // eq_update_samples :152-159
+        e.samples[0] = e.samples[2]; e.samples[1] = e.samples[3]; e.samples[2] = e.samples[4];
+        e.samples[3] = x2[2 * n]; e.samples[4] = x2[2 * n + 1];
+        // eq_equalize :122-135
+        float sym = e.samples[0] * e.c[0];
+#pragma unroll
+        for (int i = 1; i < 5; i++) sym += e.samples[i] * e.c[i];
+        float tr;
+        if (train) tr = train[c * nsym + n];
+        else if (sym > 0) tr = ((double)sym >= 0.66) ? 1.0f : 0.333f;                              // :195-205 (double literals)
+        else tr = ((double)sym <= -0.66) ? -1.0f : -0.333f;
+        float err = tr - sym;
+        // eq_k_calculate :40-100
+        float f[5], h[5], a[5];
+        const float *x = e.samples;
+        f[0] = x[0];
+#pragma unroll
+        for (int j = 1; j < 5; j++) { f[j] = e.u[0][j] * x[0] + x[j]; for (int i = 1; i < j; i++) f[j] += e.u[i][j] * x[i]; }
+#pragma unroll
+        for (int j = 0; j < 5; j++) e.g[j] = e.d[j] * f[j];
+        a[0] = e.E + e.g[0] * f[0];
+#pragma unroll
+        for (int j = 1; j < 5; j++) a[j] = a[j - 1] + e.g[j] * f[j];
+        const float hq = 1 + e.q, ht = a[4] * e.q;
+        e.y = 1.0f / (a[0] + ht);
+        e.d[0] = e.d[0] * hq * (e.E + ht) * e.y;
+#pragma unroll
+        for (int j = 1; j < 5; j++) {
+            const float B = a[j - 1] + ht;
+            h[j] = -f[j] * e.y;
+            e.y = 1.0f / (a[j] + ht);
+            e.d[j] = e.d[j] * hq * B * e.y;
+            for (int i = 0; i < j; i++) { const float B0 = e.u[i][j]; e.u[i][j] = B0 + h[j] * e.g[i]; e.g[i] += e.g[j] * B0; }
+        }
+        // eq_k_update :105-121
+        err *= e.y;
+#pragma unroll
+        for (int i = 0; i < 5; i++) e.c[i] += err * e.g[i];
+        e.fbr = tr;
+        out[c * nsym + n] = sym;
+    }
+    st[c] = e;
+}
+extern "C" int m17b_eq_create(m17b_ctx *ctx, int64_t nchan, m17b_eq **out) {
+    if (!ctx || !out || nchan <= 0) return M17B_E_ARG;
+    m17b_eq *eq = (m17b_eq *)calloc(1, sizeof(m17b_eq));
+    if (!eq) return M17B_E_NOMEM;
+    eq->ctx = ctx; eq->nchan = nchan;
+    CUDA_TRY(cudaMalloc((void **)&eq->d_state, sizeof(EqState) * nchan));
+    k_eq_reset<<<grid_for(nchan, 128), 128>>>(eq->d_state, nchan, 1);
+    KERNEL_CHECK();
+    *out = eq;
+    return M17B_OK;
+}
+extern "C" int m17b_eq_destroy(m17b_eq *eq) { if (!eq) return M17B_E_ARG; cudaFree(eq->d_state); free(eq); return M17B_OK; }
+extern "C" int m17b_eq_reset(m17b_eq *eq, void *stream) {
+    if (!eq) return M17B_E_ARG;
+    k_eq_reset<<<grid_for(eq->nchan, 128), 128, 0, as_stream(stream)>>>(eq->d_state, eq->nchan, 0);
+    KERNEL_CHECK();
+    return M17B_OK;
+}
+extern "C" int m17b_eq_train(m17b_eq *eq, const float *d_in, const float *d_train, int64_t nsym, float *d_out, void *stream) {
+    if (!eq || !d_in || !d_out || nsym < 0) return M17B_E_ARG;
+    if (nsym == 0) return M17B_OK;
+    k_eq_train<<<grid_for(eq->nchan, 64), 64, 0, as_stream(stream)>>>(eq->d_state, eq->nchan, d_in, d_train, nsym, d_out);
+    KERNEL_CHECK();
+    return M17B_OK;
+}
+
+// ---------------------------------------------------------------- synthetic channel (bench / demo input only)
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31);
+}
+__global__ void k_synth(int16_t *iq, int64_t nchan, int64_t nsamp, const float *sigma, const float *f0, uint64_t seed) {
+    int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= nchan * nsamp) return;
+    const int64_t c = gid / nsamp, n = gid % nsamp;
+    short2 v = ((short2 *)iq)[gid];
+    double re = v.x, im = v.y;
+    const float f = f0 ? f0[c] : 0.0f;
+    if (f != 0.0f) {
+        double sn, cs;
+        sincospi(2.0 * (double)f * (double)n, &sn, &cs);
+        const double r2 = re * cs - im * sn, i2 = re * sn + im * cs;
+        re = r2; im = i2;
+    }
+    const float sg = sigma ? sigma[c] : 0.0f;
+    if (sg > 0.0f) {
+        const uint64_t r = mix64(seed ^ mix64((uint64_t)gid));
+        const float u1 = ((uint32_t)(r >> 40) + 1) * (1.0f / 16777216.0f);      // (0,1]
+        const float u2 = (uint32_t)(r & 0xFFFFFF) * (1.0f / 16777216.0f);
+        const float mag = sg * sqrtf(-2.0f * logf(u1));
+        float sn, cs;
+        sincospif(2.0f * u2, &sn, &cs);
+        re += mag * cs; im += mag * sn;
+    }
+    int ri = (int)rint(fmin(fmax(re, -32768.0), 32767.0)), ii = (int)rint(fmin(fmax(im, -32768.0), 32767.0));
+    if (ri == 0 && ii == 0) ri = 1;                                             // dsp_limit divides by |z|
+    ((short2 *)iq)[gid] = make_short2((short)ri, (short)ii);
+}
+extern "C" int m17b_synth_channel(m17b_ctx *ctx, int16_t *d_iq, int64_t nchan, int64_t nsamp, const float *d_sigma, const float *d_f0,
+                                  uint64_t seed, void *stream) {
+    if (!ctx || !d_iq || nchan <= 0 || nsamp <= 0) return M17B_E_ARG;
+    k_synth<<<grid_for(nchan * nsamp, 256), 256, 0, as_stream(stream)>>>(d_iq, nchan, nsamp, d_sigma, d_f0, seed);
+    KERNEL_CHECK();
+    return M17B_OK;
+}

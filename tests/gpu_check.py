@@ -1,0 +1,410 @@
+"""GPU parity checks of libm17b200 against the CPU oracle (oracle/libm17oracle.so).
+
+Used two ways: imported by the pytest -m gpu tests (each check raises AssertionError on a mismatch), and run
+directly (`python tests/gpu_check.py`) for a verbose report while bringing kernels up on the GPU box.
+Every call goes through the C ABI via m17_sdr_b200.api; the oracle is only the checker.
+"""
+import os
+import sys
+import traceback
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import torch  # noqa: E402
+
+from m17_oracles import F_DELIVERED, REC_DTYPE, Port, lsf_for  # noqa: E402
+import signals  # noqa: E402
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def bits_eq(a, b):
+    a = np.ascontiguousarray(a); b = np.ascontiguousarray(b)
+    return a.shape == b.shape and np.array_equal(a.view(np.uint8), b.view(np.uint8))
+
+
+def first_diff(a, b):
+    a = np.asarray(a).reshape(-1); b = np.asarray(b).reshape(-1)
+    n = min(len(a), len(b))
+    d = np.nonzero(a[:n].view(np.uint32 if a.dtype == np.float32 else a.dtype) != b[:n].view(np.uint32 if b.dtype == np.float32 else b.dtype))[0]
+    return None if len(d) == 0 else (int(d[0]), a[d[0]], b[d[0]], len(d))
+
+
+# ---------------------------------------------------------------------------------------------- primitives
+def check_primitives(ctx, P, seed=11, n=64):
+    rng = np.random.default_rng(seed)
+    # CRC
+    for ln in (1, 2, 9, 30, 52, 256):
+        d = rng.integers(0, 256, (n, ln), dtype=np.uint8)
+        got = ctx.m17_crc_array_encode(dev(d)).cpu().numpy()
+        exp = np.array([P.crc(bytes(r)) for r in d], np.uint16)
+        assert np.array_equal(got, exp), ("crc", ln)
+    # Golay
+    d12 = np.arange(4096, dtype=np.uint16)
+    enc = ctx.m17_golay_encode(dev(d12)).cpu().numpy().astype(np.uint32)
+    assert np.array_equal(enc, np.array([P.golay_encode(x) for x in d12], np.uint32)), "golay encode"
+    w = rng.integers(0, 1 << 24, 20000).astype(np.int32)
+    gd, ge = ctx.m_17_golay_decode(dev(w))
+    exp = [P.golay_decode(int(x)) for x in w]
+    assert np.array_equal(gd.cpu().numpy(), np.array([e[0] for e in exp], np.uint16)), "golay decode data"
+    assert np.array_equal(ge.cpu().numpy(), np.array([e[1] for e in exp], np.uint8)), "golay decode errs"
+    # conv encoders
+    for nb in (18, 26, 30):
+        d = rng.integers(0, 256, (n, nb), dtype=np.uint8)
+        got = ctx.m17_conv_encode_8(dev(d)).cpu().numpy()
+        assert np.array_equal(got, np.stack([P.conv_encode_8(r) for r in d])), ("conv8", nb)
+    b = rng.integers(0, 2, (n, 197), dtype=np.uint8)
+    assert np.array_equal(ctx.m17_conv_encode_1(dev(b)).cpu().numpy(), np.stack([P.conv_encode_1(r) for r in b])), "conv1"
+    # puncture / depuncture
+    for p, ln in ((1, 488), (2, 296), (3, 420), (2, 402)):
+        b = rng.integers(0, 2, (n, ln), dtype=np.uint8)
+        got = ctx.m17_punc(p, dev(b)).cpu().numpy()
+        exp = np.stack([P.punc(p, r) for r in b])
+        assert np.array_equal(got, exp), ("punc", p, ln)
+        s = rng.normal(0, 1, (n, exp.shape[1])).astype(np.float32)
+        got = ctx.m17_de_punc(p, dev(s), ln).cpu().numpy()
+        assert bits_eq(got, np.stack([P.depunc(p, r, ln) for r in s])), ("depunc", p, ln)
+    # interleave, randomiser
+    b = rng.integers(0, 2, (n, 368), dtype=np.uint8)
+    s = rng.normal(0, 1, (n, 368)).astype(np.float32)
+    assert np.array_equal(ctx.m17_interleave(dev(b)).cpu().numpy(), np.stack([P.interleave(r) for r in b])), "interleave"
+    assert bits_eq(ctx.m17_de_interleave(dev(s)).cpu().numpy(), np.stack([P.deinterleave(r) for r in s])), "deinterleave"
+    assert np.array_equal(ctx.m17_de_correlate_1(dev(b)).cpu().numpy(), np.stack([P.derand_bits(r) for r in b])), "derand u8"
+    assert bits_eq(ctx.m17_de_correlate_1(dev(s)).cpu().numpy(), np.stack([P.derand_soft(r) for r in s])), "derand f32"
+    by = rng.integers(0, 256, (n, 54), dtype=np.uint8)
+    assert np.array_equal(ctx.m17_de_correlate_8(dev(by)).cpu().numpy(), np.stack([P.derand_bytes(r) for r in by])), "derand bytes"
+    # demap, sync check
+    sy = (rng.normal(0, 1, (n, 192)) * rng.uniform(0.1, 3, (n, 1))).astype(np.float32)
+    assert bits_eq(ctx.m17_dsp_demap_frame(dev(sy)).cpu().numpy(), np.stack([P.demap_frame(r) for r in sy])), "demap"
+    v = rng.normal(0, 1, (4000, 8)).astype(np.float32)
+    tpl = np.array([[1, 1, 1, 1, -1, -1, 1, -1], [-1, -1, -1, -1, 1, 1, -1, 1], [1, -1, 1, 1, -1, -1, -1, -1], [1, 1, 1, 1, 1, 1, -1, 1]], np.float32)
+    v[:2000] = tpl[rng.integers(0, 4, 2000)] * (1 + 0.15 * rng.normal(0, 1, (2000, 8))).astype(np.float32)
+    v[5] = 0
+    ty, vo, va = ctx.m17_sync_check(dev(v))
+    exp = [P.sync_check(r) for r in v]
+    assert np.array_equal(ty.cpu().numpy(), np.array([e[0] for e in exp], np.uint8)), "sync type"
+    assert np.array_equal(vo.cpu().numpy(), np.array([e[1] for e in exp], np.uint8)), "sync votes"
+    assert bits_eq(va.cpu().numpy(), np.array([e[2] for e in exp], np.float32)), "sync variance"
+    # PRBS9
+    seq = P.prbs9()
+    got = ctx.m17_prbs9_tx_load(3, 600).cpu().numpy()
+    assert np.array_equal(got[0], np.concatenate([seq, seq])[:600]), "prbs9"
+    # filter design (host side of the library)
+    for args in ((0.5, 1240, 80), (0.5, 310, 10), (0.5, 62, 2), (0.5, 2480, 80)):
+        assert bits_eq(ctx.m17_dsp_build_rrc_filter(*args), P.rrc(*args)), ("rrc", args)
+    mf, md = ctx.sync_taps()
+    pmf, pmd = P.sync_taps()
+    assert bits_eq(mf, pmf) and bits_eq(md, pmd), "sync taps"
+    return "primitives ok"
+
+
+def check_viterbi(ctx, P, seed=12, n=300):
+    rng = np.random.default_rng(seed)
+    for ln in (296, 420, 488, 24, 2):
+        s = rng.normal(0, 1, (n, ln)).astype(np.float32)
+        s[0] = 0                                   # pure tie-break frame
+        s[1] = np.round(s[1] * 4) / 4              # many exact ties
+        s[2, ::3] = 0
+        got = ctx.m17_viterbi_decode(dev(s)).cpu().numpy()
+        exp = np.stack([P.viterbi(r) for r in s])
+        assert np.array_equal(got, exp), ("viterbi", ln, first_diff(got, exp))
+    # punctured + packed form on encoded noisy frames
+    for p, nb, full in ((1, 30, 488), (2, 18, 296), (3, 26, 420)):
+        data = rng.integers(0, 256, (n, nb), dtype=np.uint8)
+        soft = []
+        exp = []
+        for r in data:
+            cod = P.conv_encode_8(r)[:full]
+            x = (2.0 * P.punc(p, cod) - 1.0) + rng.normal(0, 0.8, len(P.punc(p, cod)))
+            x = (np.round(np.clip(x, -2, 2) * 32) / 32).astype(np.float32)
+            soft.append(x)
+            bits = P.viterbi(P.depunc(p, x, full))
+            exp.append(np.packbits(bits[1:1 + 8 * nb]))
+        got = ctx.viterbi_punctured(p, dev(np.stack(soft))).cpu().numpy()
+        assert np.array_equal(got, np.stack(exp)), ("viterbi_punctured", p, first_diff(got, np.stack(exp)))
+    return "viterbi ok"
+
+
+def oracle_parse_frame(P, sym, ty):
+    """m17_rx_parse for one frame, composed from oracle primitives (no LICH state)."""
+    r = np.zeros((), REC_DTYPE)
+    r["type"] = ty
+    r["flags"] = 2
+    if ty < 1 or ty > 4:
+        return r, None
+    sb = P.demap_frame(sym)
+    acc = np.float32(0)
+    for k in range(8):
+        acc = np.float32(acc + np.abs(np.float32(sym[k])))
+    r["cor"] = np.float32(8.0 / np.float64(acc))
+    if ty == 4:
+        return r, sb
+    so = P.deinterleave(P.derand_soft(sb))
+    if ty == 1:
+        bits = P.viterbi(P.depunc(1, so, 488)); nb = 30
+    elif ty == 2:
+        e = 0; w = []
+        for k in range(4):
+            d, ee = P.golay_decode(P.hard24(so[24 * k:24 * k + 24])); w.append(d); e += ee
+        r["golay_err"] = e
+        w01, w23 = (w[0] << 12) | w[1], (w[2] << 12) | w[3]
+        r["lich"] = [(w01 >> 16) & 255, (w01 >> 8) & 255, w01 & 255, (w23 >> 16) & 255, (w23 >> 8) & 255, w23 & 255]
+        bits = P.viterbi(P.depunc(2, so[96:], 296)); nb = 18
+    else:
+        bits = P.viterbi(P.depunc(3, so, 420)); nb = 26
+    data = np.packbits(bits[1:1 + 8 * nb])
+    r["data"][:nb] = data
+    r["nbytes"] = nb
+    r["crc"] = P.crc(bytes(data))
+    if ty == 3 and data[25] & 0x80:
+        r["flags"] |= 0x20
+    return r, sb
+
+
+def check_parse_frames(ctx, P, seed=13, n=200):
+    rng = np.random.default_rng(seed)
+    lsf = lsf_for(P)
+    frames = [P.fmt_lsf(lsf)] + list(P.fmt_stream_frames(lsf, rng.integers(0, 256, (8, 16), dtype=np.uint8))) + \
+             [P.fmt_packet(bytes(rng.integers(0, 256, 25, dtype=np.uint8)), 0, 3), P.fmt_packet(b"hello", 1, 5)] + list(P.fmt_bert(2))
+    lu = np.array([1 / 3, 1.0, -1 / 3, -1.0], np.float32)
+    sym = np.zeros((n, 192), np.float32)
+    types = np.zeros(n, np.uint8)
+    for i in range(n):
+        d = frames[i % len(frames)]
+        s = lu[d] * np.float32(rng.uniform(0.3, 2.0)) + rng.normal(0, 0.25 if i % 3 else 0.02, 192).astype(np.float32)
+        sym[i] = s
+        types[i] = P.sync_check(s[:8])[0] if i % 11 else rng.integers(0, 6)
+    rec, soft = ctx.m17_rx_parse(dev(sym), dev(types), want_soft=True)
+    rec = rec.cpu().numpy().view(REC_DTYPE).reshape(n)
+    soft = soft.cpu().numpy()
+    for i in range(n):
+        e, sb = oracle_parse_frame(P, sym[i], int(types[i]))
+        for name in ("type", "golay_err", "nbytes", "lich", "data", "crc"):
+            assert np.array_equal(rec[i][name], e[name]), ("parse", i, int(types[i]), name, rec[i][name], e[name])
+        assert (rec[i]["flags"] & 0x22) == (e["flags"] & 0x22), ("parse flags", i, rec[i]["flags"], e["flags"])
+        if sb is not None:
+            assert bits_eq(rec[i]["cor"], e["cor"]), ("cor", i, rec[i]["cor"], e["cor"])
+            assert bits_eq(soft[i], sb), ("soft bits", i, first_diff(soft[i], sb))
+    return "parse_frames ok"
+
+
+# ---------------------------------------------------------------------------------------------- RX chain
+def compare_chain(res, o, seam, Cn, verbose=False):
+    """res = Rx.results() of the CUDA chain, o = oracle rx_run output."""
+    msgs = []
+    T = o.nsym.shape[1]
+    if seam == 0:
+        disc = res["disc_raw"] - res["mean"][:, :, None]
+        if not bits_eq(disc, o.disc):
+            msgs.append(("disc", first_diff(disc, o.disc)))
+    if not np.array_equal(res["nsym"], o.nsym):
+        msgs.append(("nsym", first_diff(res["nsym"], o.nsym)))
+    for c in range(Cn):
+        ns = int(o.counts[c, 1]); nf = int(o.counts[c, 2]); ne = int(o.counts[c, 3])
+        if int(res["nsym"][c].sum()) != ns:
+            msgs.append(("sym count", c, int(res["nsym"][c].sum()), ns)); continue
+        if not bits_eq(res["syms"][c, :ns], o.syms[c, :ns]):
+            msgs.append(("syms", c, first_diff(res["syms"][c, :ns], o.syms[c, :ns])))
+        if int(res["nframes"][c]) != nf:
+            msgs.append(("nframes", c, int(res["nframes"][c]), nf)); continue
+        fa, fb = res["frames"][c, :nf], o.frames[c, :nf]
+        for name in REC_DTYPE.names:
+            if name == "rsvd":
+                continue
+            if not bits_eq(fa[name], fb[name]):
+                bad = [k for k in range(nf) if not bits_eq(fa[name][k], fb[name][k])]
+                msgs.append(("rec." + name, c, bad[:5], fa[name][bad[0]], fb[name][bad[0]], int(fb["type"][bad[0]])))
+        if int(res["nevents"][c]) != ne or not np.array_equal(res["events"][c, :ne], o.events[c, :ne]):
+            msgs.append(("events", c, res["events"][c, :ne], o.events[c, :ne]))
+    if verbose:
+        for m in msgs[:20]:
+            print("   MISMATCH", m)
+    assert not msgs, msgs[:4]
+
+
+def run_chain(ctx, X, seam=0, split=None):
+    """Run the CUDA chain over X; split = list of block counts to process in successive calls (state carry)."""
+    import m17_sdr_b200 as m
+    Cn = X.shape[0]
+    per = 1920 if seam == 0 else 384
+    T = X.shape[1] // per
+    parts = list(split or [])
+    assert sum(parts) <= T
+    if sum(parts) < T:
+        parts.append(T - sum(parts))
+    rx = m.Rx(ctx, Cn, max(parts))
+    out = []
+    t0 = 0
+    for nb in parts:
+        xs = np.ascontiguousarray(X[:, t0 * per:(t0 + nb) * per])
+        if seam == 0:
+            rx.m17_dsp_rx(torch.from_numpy(xs).cuda())
+        else:
+            rx.m17_rx_baseband(torch.from_numpy(xs).cuda())
+        out.append(rx.results())
+        t0 += nb
+    rx.close()
+    if len(out) == 1:
+        return out[0]
+    # stitch successive calls into one result in the oracle's layout
+    res = {}
+    res["nsym"] = np.concatenate([r["nsym"] for r in out], 1)
+    res["nframes"] = sum(r["nframes"] for r in out)
+    res["nevents"] = sum(r["nevents"] for r in out)
+    if seam == 0:
+        res["disc_raw"] = np.concatenate([r["disc_raw"] for r in out], 1)
+        res["mean"] = np.concatenate([r["mean"] for r in out], 1)
+    nsyms = [r["nsym"].sum(1) for r in out]
+    mx = max(int(sum(n[c] for n in nsyms)) for c in range(Cn))
+    res["syms"] = np.zeros((Cn, mx), np.float32)
+    for c in range(Cn):
+        v = np.concatenate([out[k]["syms"][c, :nsyms[k][c]] for k in range(len(out))])
+        res["syms"][c, :len(v)] = v
+    fcap = sum(r["frames"].shape[1] for r in out)
+    res["frames"] = np.zeros((Cn, fcap), REC_DTYPE)
+    ecap = sum(r["events"].shape[1] for r in out)
+    res["events"] = np.zeros((Cn, ecap), out[0]["events"].dtype)
+    for c in range(Cn):
+        f = np.concatenate([r["frames"][c, :r["nframes"][c]] for r in out]); res["frames"][c, :len(f)] = f
+        e = np.concatenate([r["events"][c, :r["nevents"][c]] for r in out]); res["events"][c, :len(e)] = e
+    return res
+
+
+def check_rx_chain(ctx, P, nchan=16, nframes=30, seed=21, verbose=False, split=None):
+    eb = [None, None, 30, 28, 26, 24, 23, 22, 21, 20, 26, 26, 24, 24, 22, 22][:nchan] + [26] * max(0, nchan - 16)
+    X, pl = signals.stream_channels(P, nchan, nframes, seed, ebn0=eb, f0_max=1000.0)
+    o = P.rx_run(X, seam=0)
+    res = run_chain(ctx, X, 0, split)
+    compare_chain(res, o, 0, nchan, verbose)
+    deliv = sum(int(((o.frames[c, :o.counts[c, 2]]["flags"] & F_DELIVERED) != 0).sum()) for c in range(nchan))
+    return f"rx chain ok ({nchan} ch x {X.shape[1] // 1920} blocks, {int(o.counts[:, 2].sum())} frames, {deliv} delivered)"
+
+
+def check_rx_baseband(ctx, P, nchan=14, nframes=30, seed=22, verbose=False, split=None):
+    eb = [None, 12, 10, 8, 6, 4, 2, 0, 12, 10, 8, 6, 4, 2][:nchan]
+    D, pl = signals.baseband_channels(P, nchan, nframes, seed, eb)
+    o = P.rx_run(D, seam=1)
+    res = run_chain(ctx, D, 1, split)
+    compare_chain(res, o, 1, nchan, verbose)
+    return f"rx baseband ok ({nchan} ch, Eb/N0 sweep 0..12 dB, {int(o.counts[:, 2].sum())} frames)"
+
+
+# ---------------------------------------------------------------------------------------------- TX
+def check_tx(ctx, P, nchan=6, F=12, seed=31, os_=10):
+    import m17_sdr_b200 as m
+    rng = np.random.default_rng(seed)
+    lsfs = np.stack([P.build_lsf(0xFFFFFFFFFFFF, P.encode_call("G4GUO    "), 5, bytes(rng.integers(0, 256, 14, dtype=np.uint8))) for _ in range(nchan)])
+    pl = rng.integers(0, 256, (nchan, F, 16), dtype=np.uint8)
+    tx = m.Tx(ctx, nchan, os_)
+    assert np.array_equal(tx.fmt_preamble(), P.fmt_preamble()) and np.array_equal(tx.fmt_eot(), P.fmt_eot())
+    got = tx.m17_fmt_add_link_setup_frame(dev(lsfs)).cpu().numpy()
+    assert np.array_equal(got, np.stack([P.fmt_lsf(l) for l in lsfs])), "fmt lsf"
+    tx.set_lsf(dev(lsfs))
+    d1 = tx.m17_fmt_add_stream_frame(dev(pl[:, :5])).cpu().numpy()
+    d2 = tx.m17_fmt_add_stream_frame(dev(pl[:, 5:])).cpu().numpy()          # state carry: m_fn / m_lich_count
+    got = np.concatenate([d1, d2], 1)
+    exp = np.stack([P.fmt_stream_frames(lsfs[c], pl[c]) for c in range(nchan)])
+    assert np.array_equal(got, exp), ("fmt stream", first_diff(got, exp))
+    ch = rng.integers(0, 256, (9, 25), dtype=np.uint8)
+    meta = np.array([(k << 2) | (0x80 if k == 8 else 0) for k in range(9)], np.uint8)
+    got = tx.m17_fmt_add_packet(dev(ch), dev(meta)).cpu().numpy()
+    exp = np.stack([P.fmt_packet(bytes(ch[k]), meta[k] >> 7, (meta[k] >> 2) & 31) for k in range(9)])
+    assert np.array_equal(got, exp), "fmt packet"
+    got = tx.m17_fmt_add_bert_frame(4).cpu().numpy()
+    assert np.array_equal(got[0], P.fmt_bert(4)), "fmt bert"
+    # modulator: one over per channel, in two calls (state carry); frequency samples bit-exact, IQ within 1 LSB
+    scripts = []
+    for c in range(nchan):
+        s = [np.full(192, 4, np.uint8), P.fmt_preamble(), P.fmt_lsf(lsfs[c])] + list(exp_stream(P, lsfs[c], pl[c])) + [P.fmt_eot(), np.full(192, 4, np.uint8)]
+        scripts.append(np.concatenate(s))
+    scripts = np.stack(scripts)
+    tx.reset()
+    cut = 192 * 5 + 77
+    iq1, f1 = tx.m17_mod_dibits(dev(scripts[:, :cut]), want_freq=True)
+    iq2, f2 = tx.m17_mod_dibits(dev(scripts[:, cut:]), want_freq=True)
+    iq = torch.cat([iq1, iq2], 1).cpu().numpy(); fr = torch.cat([f1, f2], 1).cpu().numpy()
+    for c in range(nchan):
+        eiq, efr = P.mod(scripts[c], os_, want_freq=True)
+        assert bits_eq(fr[c], efr), ("mod freq", c, first_diff(fr[c], efr))
+        dmax = np.abs(iq[c].astype(np.int32) - eiq.astype(np.int32)).max()
+        assert dmax <= 1, ("mod iq", c, int(dmax))
+    tx.close()
+    return "tx ok"
+
+
+def exp_stream(P, lsf, pl):
+    return P.fmt_stream_frames(lsf, pl)
+
+
+def check_equalizer(ctx, P, nchan=5, nsym=400, seed=41):
+    import m17_sdr_b200 as m
+    rng = np.random.default_rng(seed)
+    lv = np.array([1.0, 1 / 3, -1 / 3, -1.0], np.float32)
+    tr = lv[rng.integers(0, 4, (nchan, nsym))]
+    pairs = np.zeros((nchan, nsym, 2), np.float32)
+    for c in range(nchan):
+        x = np.repeat(tr[c], 2).astype(np.float64)
+        x = np.convolve(x, [0.15, 0.8, 0.25, -0.1])[: 2 * nsym] + rng.normal(0, 0.02, 2 * nsym)
+        pairs[c] = x.reshape(nsym, 2).astype(np.float32)
+    eq = m.Equalizer(ctx, nchan)
+    y1 = eq.eq_train(dev(pairs[:, :150]), dev(np.ascontiguousarray(tr[:, :150])))      # known symbols
+    y2 = eq.eq_train(dev(pairs[:, 150:]))                                             # decision directed, state carried
+    got = torch.cat([y1, y2], 1).cpu().numpy()
+    for c in range(nchan):
+        exp = eq_oracle(P, pairs[c], tr[c], 150)
+        assert bits_eq(got[c], exp), ("equalizer", c, first_diff(got[c], exp))
+    eq.close()
+    return "equalizer ok"
+
+
+def eq_oracle(P, pairs, train, nknown):
+    import ctypes as C
+    st = np.zeros(64, np.float32)
+    L = P.L
+    L.m17o_eq_open(st.ctypes.data_as(C.c_void_p))
+    y = np.zeros(len(pairs), np.float32)
+    for i in range(len(pairs)):
+        p = np.ascontiguousarray(pairs[i])
+        if i < nknown:
+            y[i] = L.m17o_eq_train_known(st.ctypes.data_as(C.c_void_p), p.ctypes.data_as(C.c_void_p), float(train[i]))
+        else:
+            y[i] = L.m17o_eq_train_unknown(st.ctypes.data_as(C.c_void_p), p.ctypes.data_as(C.c_void_p))
+    return y
+
+
+CHECKS = [
+    ("primitives", lambda c, P: check_primitives(c, P)),
+    ("viterbi", lambda c, P: check_viterbi(c, P)),
+    ("parse_frames", lambda c, P: check_parse_frames(c, P)),
+    ("rx_baseband", lambda c, P: check_rx_baseband(c, P, verbose=True)),
+    ("rx_chain", lambda c, P: check_rx_chain(c, P, verbose=True)),
+    ("rx_chain_split", lambda c, P: check_rx_chain(c, P, nchan=6, seed=23, verbose=True, split=[1, 7, 2, 1, 13])),
+    ("tx", lambda c, P: check_tx(c, P)),
+    ("tx_os80", lambda c, P: check_tx(c, P, nchan=2, F=3, os_=80)),
+    ("equalizer", lambda c, P: check_equalizer(c, P)),
+]
+
+if __name__ == "__main__":
+    import m17_sdr_b200 as m
+    m.build()
+    ctx = m.Context(0)
+    P = Port()
+    only = sys.argv[1:]
+    fails = 0
+    for name, fn in CHECKS:
+        if only and name not in only:
+            continue
+        try:
+            print(f"[{name}] {fn(ctx, P)}", flush=True)
+        except Exception as e:  # noqa: BLE001
+            fails += 1
+            print(f"[{name}] FAILED: {type(e).__name__}: {str(e)[:1500]}", flush=True)
+            traceback.print_exc(limit=3)
+        torch.cuda.synchronize()
+    print("FAILS", fails)
+    sys.exit(1 if fails else 0)
