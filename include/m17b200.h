@@ -161,6 +161,11 @@ int m17b_rx_get_view(m17b_rx *rx, m17b_rx_view *out);
    h_frames [nchan][frame_cap] (frame_cap from m17b_rx_frame_cap), h_nframes [nchan]; synchronises the stream. */
 int64_t m17b_rx_frame_cap(const m17b_rx *rx);
 int m17b_dsp_rx_host(m17b_rx *rx, const int16_t *h_iq, int64_t nblocks, m17b_frame_rec *h_frames, int32_t *h_nframes, void *stream);
+/* bench instrumentation: mark stage boundaries with CUDA events on the launching stream; stage_ms returns the device
+   time of {front end, matched filter+timing+framer, frame decode, LICH/packet post} of device call number call_index
+   (0-based, counted since timing was switched on; the last 64 calls are kept).  Not recorded by the _host entry point. */
+int m17b_rx_set_timing(m17b_rx *rx, int on);
+int m17b_rx_stage_ms(m17b_rx *rx, int64_t call_index, float *h_out4);
 /* number of kernels the last m17b_dsp_rx / m17b_rx_baseband call launched */
 int m17b_rx_last_launches(const m17b_rx *rx);
 

@@ -265,6 +265,14 @@ class Rx:
         _l.check(self.L.m17b_dsp_rx_host(self.h, _ptr(iq_host), nblocks, _ptr(frames_host), _ptr(nframes_host), _stream()))
         return frames_host, nframes_host
 
+    def set_timing(self, on=True):
+        _l.check(self.L.m17b_rx_set_timing(self.h, int(on)))
+
+    def stage_ms(self, call_index):
+        out = (C.c_float * 4)()
+        _l.check(self.L.m17b_rx_stage_ms(self.h, call_index, out))
+        return dict(zip(("frontend", "sync_frame", "decode", "post"), [float(x) for x in out]))
+
     def launches(self):
         return self.L.m17b_rx_last_launches(self.h)
 

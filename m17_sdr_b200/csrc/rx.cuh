@@ -10,6 +10,7 @@
 #pragma once
 #include "sync.cuh"
 
+#define M17B_TIMING_RING 64
 struct m17b_rx {
     m17b_ctx *ctx;
     int64_t nchan, max_blocks, last_blocks;
@@ -26,6 +27,9 @@ struct m17b_rx {
     cudaStream_t copy_stream;
     cudaEvent_t ev_h2d[2], ev_done[2];
     int afc, last_launches, seam_last;
+    int timing;                       // record cudaEvents around each stage of the next calls (bench only)
+    cudaEvent_t ev_stage[M17B_TIMING_RING][5];
+    int64_t tcount;                   // calls made since timing was enabled
 };
 
 __global__ void k_rx_reset(RxChanState *st, int64_t nchan) {
@@ -101,6 +105,7 @@ extern "C" int m17b_rx_destroy(m17b_rx *rx) {
         if (rx->ev_done[i]) cudaEventDestroy(rx->ev_done[i]);
     }
     if (rx->copy_stream) cudaStreamDestroy(rx->copy_stream);
+    for (int r = 0; r < M17B_TIMING_RING; r++) for (int i = 0; i < 5; i++) if (rx->ev_stage[r][i]) cudaEventDestroy(rx->ev_stage[r][i]);
     free(rx);
     return M17B_OK;
 }
@@ -157,8 +162,10 @@ extern "C" int m17b_rx_set_afc(m17b_rx *rx, int on) {
 }
 
 // stages 2..4 for channels [c0, c0+nc)
+#define STAGE_MARK(i) do { if (rx->timing) CUDA_TRY(cudaEventRecord(rx->ev_stage[rx->tcount % M17B_TIMING_RING][i], st)); } while (0)
 static int rx_back_half(m17b_rx *rx, int64_t c0, int64_t nc, const float *disc, const float *mean, int64_t T, int commit_fe, cudaStream_t st) {
     m17b_ctx *ctx = rx->ctx;
+    STAGE_MARK(1);
     const unsigned g = grid_for(nc, SY_WARPS);
     float *syms = rx->d_syms + c0 * rx->sym_pitch;
     m17b_frame_rec *frames = rx->d_frames + c0 * rx->fcap;
@@ -171,16 +178,20 @@ static int rx_back_half(m17b_rx *rx, int64_t c0, int64_t nc, const float *disc, 
                                                         rx->d_nsym + c0 * T, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0,
                                                         rx->d_events + c0 * rx->ecap, rx->ecap, rx->d_nevents + c0, rx->d_stats + c0 * 8, commit_fe);
     KERNEL_CHECK();
+    STAGE_MARK(2);
     int rc = launch_decode(ctx, syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0, nc, nullptr, st);
     if (rc) return rc;
+    STAGE_MARK(3);
     k_post<<<grid_for(nc, 64), 64, 0, st>>>(frames, rx->fcap, rx->d_nframes + c0, nc, rx->d_state + c0, ctx->d_crc, rx->d_stats + c0 * 8);
     KERNEL_CHECK();
+    STAGE_MARK(4);
     rx->last_launches += 3;
     return M17B_OK;
 }
 
 static int rx_chain(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t *d_iq, int64_t T, cudaStream_t st) {
     float *disc = rx->d_disc + c0 * T * 384, *mean = rx->d_mean + c0 * T;
+    STAGE_MARK(0);
     k_frontend<<<grid_for(nc * T, FE_WARPS * 32), FE_WARPS * 32, 0, st>>>((const uint32_t *)d_iq, nc, T, rx->d_state + c0, disc, mean);
     KERNEL_CHECK();
     rx->last_launches += 1;
@@ -192,14 +203,18 @@ extern "C" int m17b_dsp_rx(m17b_rx *rx, const int16_t *d_iq, int64_t nblocks, vo
     if (nblocks > rx->max_blocks) return M17B_E_CAPACITY;
     if (rx->afc) return M17B_E_UNSUPPORTED;
     rx->last_launches = 0; rx->last_blocks = nblocks; rx->seam_last = 0;
-    return rx_chain(rx, 0, rx->nchan, d_iq, nblocks, as_stream(stream));
+    int rc = rx_chain(rx, 0, rx->nchan, d_iq, nblocks, as_stream(stream));
+    if (rx->timing) rx->tcount++;
+    return rc;
 }
 
 extern "C" int m17b_rx_baseband(m17b_rx *rx, const float *d_disc, int64_t nblocks, void *stream) {
     if (!rx || !d_disc || nblocks <= 0) return M17B_E_ARG;
     if (nblocks > rx->max_blocks) return M17B_E_CAPACITY;
     rx->last_launches = 0; rx->last_blocks = nblocks; rx->seam_last = 1;
-    return rx_back_half(rx, 0, rx->nchan, d_disc, nullptr, nblocks, 0, as_stream(stream));
+    int rc = rx_back_half(rx, 0, rx->nchan, d_disc, nullptr, nblocks, 0, as_stream(stream));
+    if (rx->timing) rx->tcount++;
+    return rc;
 }
 
 extern "C" int m17b_rx_get_view(m17b_rx *rx, m17b_rx_view *v) {
@@ -211,6 +226,27 @@ extern "C" int m17b_rx_get_view(m17b_rx *rx, m17b_rx_view *v) {
     v->d_disc = rx->seam_last ? nullptr : rx->d_disc; v->d_mean = rx->seam_last ? nullptr : rx->d_mean;
     v->d_events = rx->d_events; v->event_cap = rx->ecap; v->d_nevents = rx->d_nevents;
     v->d_stats = (const uint64_t *)rx->d_stats;
+    return M17B_OK;
+}
+// bench instrumentation: when enabled, stage boundaries of m17b_dsp_rx / m17b_rx_baseband are marked with CUDA events
+// on the launching stream; m17b_rx_stage_ms returns {front end, sync+framer, decode, post} of the last call (0 if absent).
+extern "C" int m17b_rx_set_timing(m17b_rx *rx, int on) {
+    if (!rx) return M17B_E_ARG;
+    if (on && !rx->ev_stage[0][0])
+        for (int r = 0; r < M17B_TIMING_RING; r++) for (int i = 0; i < 5; i++) CUDA_TRY(cudaEventCreate(&rx->ev_stage[r][i]));
+    rx->timing = on != 0;
+    rx->tcount = 0;
+    return M17B_OK;
+}
+extern "C" int m17b_rx_stage_ms(m17b_rx *rx, int64_t call_index, float *out4) {
+    if (!rx || !out4 || !rx->ev_stage[0][0] || call_index < 0 || call_index >= rx->tcount || call_index < rx->tcount - M17B_TIMING_RING) return M17B_E_ARG;
+    cudaEvent_t *ev = rx->ev_stage[call_index % M17B_TIMING_RING];
+    CUDA_TRY(cudaEventSynchronize(ev[4]));
+    for (int i = 0; i < 4; i++) {
+        out4[i] = 0;
+        if (i == 0 && rx->seam_last) continue;
+        CUDA_TRY(cudaEventElapsedTime(&out4[i], ev[i], ev[i + 1]));
+    }
     return M17B_OK;
 }
 extern "C" int64_t m17b_rx_frame_cap(const m17b_rx *rx) { return rx ? rx->fcap : 0; }

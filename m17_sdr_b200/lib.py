@@ -53,6 +53,8 @@ _SIGS = {
     "m17b_rx_frame_cap": ([_vp], _i64),
     "m17b_dsp_rx_host": ([_vp, _vp, _i64, _vp, _vp, _vp], _i32),
     "m17b_rx_last_launches": ([_vp], _i32),
+    "m17b_rx_set_timing": ([_vp, _i32], _i32),
+    "m17b_rx_stage_ms": ([_vp, _i64, _vp], _i32),
     "m17b_tx_create": ([_vp, _i64, _i32, C.POINTER(_vp)], _i32),
     "m17b_tx_destroy": ([_vp], _i32),
     "m17b_tx_reset": ([_vp, _vp], _i32),

@@ -5,7 +5,9 @@
  * state in file statics so a process is a channel).  TEST/BENCH INFRASTRUCTURE ONLY.
  *
  *   m17ref_bench <iq.bin> <C> <T> <nproc> [reps]
- * iq.bin = raw int16 [C][T*1920][2].  Prints one JSON line with frames/s over all workers.
+ * iq.bin = raw int16 [C][T*1920][2].  nproc workers; each decodes its channels one after another, every channel in a
+ * freshly forked child (pristine statics).  The clock runs around the m17_dsp_rx loop only.  Prints one JSON line:
+ * frames/s = all frames / slowest worker's summed loop time; delivered = stream payloads passed up in one pass.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -44,6 +46,8 @@ int main(int argc, char **argv) {
     const int16_t *iq = (const int16_t *)mmap(0, bytes, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
     if (iq == MAP_FAILED) { perror("mmap"); return 2; }
     struct Res { double secs; long frames, delivered, aos, los; };
+    /* one slot per channel (filled by the per-channel child) and one per worker */
+    Res *chan = (Res *)mmap(0, sizeof(Res) * C, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
     Res *res = (Res *)mmap(0, sizeof(Res) * nproc, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
     /* main.cpp:108-126 init order */
     m17_prbs9_init(); m17_crc_init(); m17_init_conv(); m17_init_de_correlate(); m17_dsp_init(); m17_fmt_init();
@@ -51,17 +55,26 @@ int main(int argc, char **argv) {
     double w0 = now_s();
     for (int w = 0; w < nproc; w++) {
         if (fork() == 0) {
-            int16_t blk[3840];
             /* touch my slice once (page-in) before timing */
             volatile long sink = 0;
             for (long c = w; c < C; c += nproc) for (long i = 0; i < T * 3840; i += 2048) sink += iq[c * T * 3840 + i];
-            double t0 = now_s(); long frames = 0;
+            double secs = 0; long frames = 0, deliv = 0;
             for (int r = 0; r < reps; r++)
                 for (long c = w; c < C; c += nproc) {
-                    const int16_t *p = iq + c * T * 3840;
-                    for (long t = 0; t < T; t++) { memcpy(blk, p + t * 3840, sizeof(blk)); m17_dsp_rx((scmplx *)blk, 1920); frames++; }
+                    /* the reference keeps its state in file statics: a pristine process per channel */
+                    pid_t p = fork();
+                    if (p == 0) {
+                        int16_t blk[3840];
+                        const int16_t *src = iq + c * T * 3840;
+                        double t0 = now_s();
+                        for (long t = 0; t < T; t++) { memcpy(blk, src + t * 3840, sizeof(blk)); m17_dsp_rx((scmplx *)blk, 1920); }
+                        chan[c].secs = now_s() - t0; chan[c].frames = T; chan[c].delivered = g_delivered; chan[c].aos = g_aos; chan[c].los = g_los;
+                        _exit(0);
+                    }
+                    int st; waitpid(p, &st, 0);
+                    secs += chan[c].secs; frames += chan[c].frames; if (r == 0) deliv += chan[c].delivered;
                 }
-            res[w].secs = now_s() - t0; res[w].frames = frames; res[w].delivered = g_delivered; res[w].aos = g_aos; res[w].los = g_los;
+            res[w].secs = secs; res[w].frames = frames; res[w].delivered = deliv;
             _exit(0);
         }
     }

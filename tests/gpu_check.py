@@ -305,8 +305,8 @@ def check_tx(ctx, P, nchan=6, F=12, seed=31, os_=10):
     got = tx.m17_fmt_add_link_setup_frame(dev(lsfs)).cpu().numpy()
     assert np.array_equal(got, np.stack([P.fmt_lsf(l) for l in lsfs])), "fmt lsf"
     tx.set_lsf(dev(lsfs))
-    d1 = tx.m17_fmt_add_stream_frame(dev(pl[:, :5])).cpu().numpy()
-    d2 = tx.m17_fmt_add_stream_frame(dev(pl[:, 5:])).cpu().numpy()          # state carry: m_fn / m_lich_count
+    d1 = tx.m17_fmt_add_stream_frame(dev(pl[:, :F // 2])).cpu().numpy()
+    d2 = tx.m17_fmt_add_stream_frame(dev(pl[:, F // 2:])).cpu().numpy()          # state carry: m_fn / m_lich_count
     got = np.concatenate([d1, d2], 1)
     exp = np.stack([P.fmt_stream_frames(lsfs[c], pl[c]) for c in range(nchan)])
     assert np.array_equal(got, exp), ("fmt stream", first_diff(got, exp))

@@ -1,0 +1,170 @@
+"""GPU tier (pytest -m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the same seeded
+inputs, against the committed golden fixtures (reference outputs), and -- at the bench's full size -- through
+size-independent properties.  Bit-exact for every integer/byte/index result; fp32 symbol streams and soft bits
+are compared bit-for-bit as well (tolerance of the spec: 1e-5 relative RMS; measured: 0)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import gpu_check as gc
+from m17_oracles import REC_DTYPE
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "m17_golden.npz"))
+SOFT_RMS_TOL = 1e-5      # BASELINE.json north_star tolerance for filter outputs / soft symbols
+
+
+def test_primitives(ctx, port):
+    gc.check_primitives(ctx, port)
+
+
+def test_viterbi(ctx, port):
+    gc.check_viterbi(ctx, port)
+
+
+def test_parse_frames(ctx, port):
+    gc.check_parse_frames(ctx, port)
+
+
+def test_rx_baseband_ebn0_sweep(ctx, port):
+    gc.check_rx_baseband(ctx, port)
+
+
+def test_rx_chain_from_iq(ctx, port):
+    gc.check_rx_chain(ctx, port)
+
+
+def test_rx_chain_state_carry_across_calls(ctx, port):
+    gc.check_rx_chain(ctx, port, nchan=6, seed=23, split=[1, 7, 2, 1, 13])
+    gc.check_rx_baseband(ctx, port, nchan=6, seed=24, split=[3, 1, 1, 9])
+
+
+def test_tx(ctx, port):
+    gc.check_tx(ctx, port)
+    gc.check_tx(ctx, port, nchan=2, F=4, os_=80)
+
+
+def test_equalizer(ctx, port):
+    gc.check_equalizer(ctx, port)
+
+
+def _rel_rms(a, b):
+    a = a.astype(np.float64); b = b.astype(np.float64)
+    return float(np.sqrt(np.mean((a - b) ** 2)) / (np.sqrt(np.mean(b ** 2)) + 1e-30))
+
+
+def test_golden_rx_chain_reference_outputs(ctx):
+    """CUDA chain vs outputs of the reference's own objects (fixture), no oracle library involved."""
+    res = gc.run_chain(ctx, G["rx_iq"], 0)
+    counts = G["rx_counts"]
+    fr = G["rx_frames"].view(REC_DTYPE).reshape(4, -1)
+    assert np.array_equal(res["nsym"], G["rx_nsym"])
+    for c in range(4):
+        ns, nf, ne = (int(x) for x in counts[c, 1:4])
+        assert _rel_rms(res["syms"][c, :ns], G["rx_syms"][c, :ns]) <= SOFT_RMS_TOL
+        assert gc.bits_eq(res["syms"][c, :ns], G["rx_syms"][c, :ns])
+        assert int(res["nframes"][c]) == nf and int(res["nevents"][c]) == ne
+        for name in REC_DTYPE.names:
+            if name != "rsvd":
+                assert gc.bits_eq(res["frames"][c, :nf][name], fr[c, :nf][name]), (c, name)
+        assert np.array_equal(res["events"][c, :ne].view(np.int32).reshape(-1, 2), G["rx_events"][c, :ne])
+    disc0 = res["disc_raw"][0] - res["mean"][0][:, None]
+    assert gc.bits_eq(disc0, G["rx_disc_c0"])
+
+
+def test_golden_baseband_and_primitives(ctx):
+    res = gc.run_chain(ctx, G["bb_disc"], 1)
+    fr = G["bb_frames"].view(REC_DTYPE).reshape(3, -1)
+    for c in range(3):
+        ns, nf = int(G["bb_counts"][c, 1]), int(G["bb_counts"][c, 2])
+        assert gc.bits_eq(res["syms"][c, :ns], G["bb_syms"][c, :ns]) and int(res["nframes"][c]) == nf
+        for name in ("type", "flags", "golay_err", "lich", "data", "crc"):
+            assert gc.bits_eq(res["frames"][c, :nf][name], fr[c, :nf][name]), (c, name)
+    d = gc.dev
+    for ln in (296, 420, 488):
+        assert np.array_equal(ctx.m17_viterbi_decode(d(G[f"vit_in_{ln}"])).cpu().numpy(), G[f"vit_out_{ln}"])
+    gd, ge = ctx.m_17_golay_decode(d(G["golay_dec_in"].astype(np.int32)))
+    assert np.array_equal(gd.cpu().numpy(), G["golay_dec_data"]) and np.array_equal(ge.cpu().numpy(), G["golay_dec_err"])
+    assert gc.bits_eq(ctx.m17_dsp_demap_frame(d(G["demap_in"])).cpu().numpy(), G["demap_out"])
+    ty, vo, va = ctx.m17_sync_check(d(G["sync_in"]))
+    assert np.array_equal(ty.cpu().numpy(), G["sync_type"]) and np.array_equal(vo.cpu().numpy(), G["sync_votes"]) and gc.bits_eq(va.cpu().numpy(), G["sync_var"])
+    import m17_sdr_b200 as m
+    tx = m.Tx(ctx, 1, 10)
+    tx.set_lsf(d(G["lsf"][None]))
+    assert np.array_equal(tx.m17_fmt_add_stream_frame(d(G["stream_payload"][None])).cpu().numpy()[0], G["dibits_stream"])
+    assert np.array_equal(tx.m17_fmt_add_link_setup_frame(d(G["lsf"][None])).cpu().numpy()[0], G["dibits_lsf"])
+    tx.reset()
+    script = np.concatenate([np.full(192, 4, np.uint8), G["tx_dibits"], np.full(192, 4, np.uint8)])
+    iq = tx.m17_mod_dibits(d(script[None])).cpu().numpy()[0]
+    n = len(G["tx_iq"])
+    assert np.abs(iq[:n].astype(np.int32) - G["tx_iq"].astype(np.int32)).max() <= 1      # cosf/sinf: CUDA vs glibc, +-1 LSB
+    tx.close()
+
+
+def test_edge_cases(ctx, port):
+    import m17_sdr_b200 as m
+    # single channel, single block; then the same capture fed one block per call must equal the one-shot run
+    X = np.ascontiguousarray(G["rx_iq"][:1])
+    one = gc.run_chain(ctx, X, 0)
+    step = gc.run_chain(ctx, X, 0, split=[1] * (X.shape[1] // 1920))
+    assert gc.bits_eq(one["syms"][0, : one["nsym"][0].sum()], step["syms"][0, : step["nsym"][0].sum()])
+    assert gc.bits_eq(one["frames"][0, : one["nframes"][0]].view(np.uint8), step["frames"][0, : step["nframes"][0]].view(np.uint8))
+    # extremes of the int16 range and noise only: must agree with the oracle, lock or no lock
+    rng = np.random.default_rng(9)
+    Z = np.zeros((3, 1920 * 4, 2), np.int16)
+    Z[0] = 32767; Z[1] = -32768
+    Z[2] = rng.integers(-32768, 32767, (1920 * 4, 2))
+    Z[2][(Z[2][:, 0] == 0) & (Z[2][:, 1] == 0)] = 1
+    gc.compare_chain(gc.run_chain(ctx, Z, 0), port.rx_run(Z, seam=0), 0, 3)
+    # capacity / argument errors are reported, not ignored
+    rx = m.Rx(ctx, 2, 2)
+    with pytest.raises(m.M17Error):
+        rx.m17_dsp_rx(torch.zeros((2, 3 * 1920, 2), dtype=torch.int16, device="cuda"))
+    with pytest.raises(m.M17Error):
+        rx.set_afc(True)
+    rx.close()
+
+
+def test_full_size_properties(ctx):
+    """BASELINE configs[1] size (1024 channels x 250 blocks): loopback exactness on the noise-free channels,
+    idempotence, and split-call equivalence; plus the host-buffer entry point returning identical records."""
+    import bench
+    import m17_sdr_b200 as m
+    C, T = 1024, 250
+    iq, payload = bench.make_workload(ctx, m, torch, C, T, seed=4242)
+    rx = m.Rx(ctx, C, T)
+    rx.m17_dsp_rx(iq)
+    a = rx.results()
+    pl = payload.cpu().numpy()
+    # every noise-free channel (sweep index 4) delivers frames 5..243 and every delivered payload is exact
+    for c in range(4, C, 5 * 8):
+        f = a["frames"][c, : a["nframes"][c]]
+        dl = f[(f["type"] == 2) & ((f["flags"] & 8) != 0)]
+        fn = (dl["data"][:, 0].astype(int) << 8) | dl["data"][:, 1]
+        assert len(dl) >= 236, (c, len(dl))
+        assert all(np.array_equal(dl["data"][i, 2:18], pl[c, fn[i]]) for i in range(len(dl))), c
+        assert int((f["flags"] & 4 != 0).sum()) == 1 and f[-1]["type"] == 5          # one LOS, on the EOT frame
+    rx.reset()
+    rx.m17_dsp_rx(iq)
+    b = rx.results()
+    assert np.array_equal(a["frames"].view(np.uint8), b["frames"].view(np.uint8)) and np.array_equal(a["nsym"], b["nsym"])   # idempotent
+    rx.reset()
+    parts = [25] * 10
+    nf = np.zeros(C, np.int64)
+    chunks = []
+    for k, nb in enumerate(parts):
+        rx.m17_dsp_rx(iq[:, k * 25 * 1920:(k + 1) * 25 * 1920].contiguous())
+        r = rx.results()
+        chunks.append((r["frames"], r["nframes"]))
+    for c in range(0, C, 37):
+        cat = np.concatenate([f[c, :n[c]] for f, n in chunks])
+        assert np.array_equal(cat.view(np.uint8), a["frames"][c, : a["nframes"][c]].view(np.uint8)), c
+    rx.reset()
+    fh, nh = rx.m17_dsp_rx_host(iq.cpu().pin_memory())
+    fh = fh.numpy().view(REC_DTYPE).reshape(C, -1)
+    assert np.array_equal(nh.numpy(), a["nframes"])
+    for c in range(0, C, 53):
+        assert np.array_equal(fh[c, : nh[c]].view(np.uint8), a["frames"][c, : a["nframes"][c]].view(np.uint8))
+    rx.close()
