@@ -35,6 +35,13 @@ METRIC = "M17 channel-seconds decoded per second"
 UNIT = "channel-s/s"
 
 
+def clean_env():
+    """environment for helper subprocesses (nvidia-smi, the CPU baseline binary): drop profiler injection so that a run
+    under ncu does not try to attach to them"""
+    bad = ("CUDA_INJECTION", "NV_COMPUTE_PROFILER", "NV_NSIGHT", "NSIGHT", "LD_PRELOAD", "NVTX_INJECTION", "CUPTI")
+    return {k: v for k, v in os.environ.items() if not k.startswith(bad)}
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -50,7 +57,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=clean_env())
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
@@ -150,9 +157,9 @@ def cpu_baseline(iq_host_sample, T, budget_s=12.0):
         iq_host_sample.tofile(path)
         try:
             # calibrate with one pass, then size reps to the budget
-            out = json.loads(subprocess.run([ref_bin, path, str(S), str(T), str(cores), "1"], capture_output=True, text=True, check=True).stdout)
+            out = json.loads(subprocess.run([ref_bin, path, str(S), str(T), str(cores), "1"], capture_output=True, text=True, check=True, env=clean_env()).stdout)
             reps = max(1, int(budget_s / max(out["secs_max_worker"], 1e-3)))
-            out = json.loads(subprocess.run([ref_bin, path, str(S), str(T), str(cores), str(reps)], capture_output=True, text=True, check=True).stdout)
+            out = json.loads(subprocess.run([ref_bin, path, str(S), str(T), str(cores), str(reps)], capture_output=True, text=True, check=True, env=clean_env()).stdout)
         finally:
             os.unlink(path)
         fps = out["frames_per_s"]
@@ -202,7 +209,7 @@ def run_reference(args):
         X.tofile(path)
         try:
             for s in range(args.warmup + args.steps):
-                out = json.loads(subprocess.run([ref_bin, path, str(S), str(T), str(cores), "1"], capture_output=True, text=True, check=True).stdout)
+                out = json.loads(subprocess.run([ref_bin, path, str(S), str(T), str(cores), "1"], capture_output=True, text=True, check=True, env=clean_env()).stdout)
                 if s >= args.warmup:
                     vals.append(out["secs_max_worker"])
         finally:

@@ -169,6 +169,12 @@ int m17b_rx_stage_ms(m17b_rx *rx, int64_t call_index, float *h_out4);
 /* number of kernels the last m17b_dsp_rx / m17b_rx_baseband call launched */
 int m17b_rx_last_launches(const m17b_rx *rx);
 
+/* exhaustive check that the front end's fast limiter arithmetic equals the reference formulation (double product,
+   sqrtf, 1.0/m) bit-for-bit on raw IQ words [first, first+count) of the 2^32 possible int16 pairs; returns the number
+   of mismatching samples (must be 0) and optionally the first dump_cap offending raw words.  The full range takes a few
+   seconds on a B200. */
+int m17b_selftest_frontend(m17b_ctx *ctx, uint64_t first, uint64_t count, uint64_t *h_mismatches, uint32_t *h_dump, int dump_cap, void *stream);
+
 /* ------------------------------------------------------------------ TX chain */
 /* oversample: radio_get_oversample() (radio.cpp:211-219), 10 or 80; m17_mod_init (m17_modulate.cpp:65-76) */
 int m17b_tx_create(m17b_ctx *ctx, int64_t nchan, int oversample, m17b_tx **out);

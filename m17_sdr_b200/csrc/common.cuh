@@ -39,7 +39,7 @@ static inline cudaStream_t as_stream(void *s) { return (cudaStream_t)s; }
 #define MAP_LSB   0x100u
 #define MAP_NEG   0x200u
 
-struct GatherMaps {
+struct __align__(16) GatherMaps {
     uint16_t p1[488];    // LSF    : 244 steps
     uint16_t p2[296];    // stream : 148 steps (type-3 bits 96..367)
     uint16_t p3[420];    // packet : 210 steps
@@ -47,7 +47,7 @@ struct GatherMaps {
 };
 // TX-side maps: for final (interleaved, randomised) bit i of a frame -> which type-3 bit feeds it
 // (QPP is an involution) and, per type-3 bit, which coded (pre-puncture) position it is.
-struct TxMaps {
+struct __align__(16) TxMaps {
     uint16_t qpp[368];   // pi(i) = (45 i + 92 i^2) mod 368          m17_interleave.cpp:5
     uint8_t  rnd[368];   // randomiser bits, MSB first               m17_correlate.cpp:35-42
     uint16_t unp1[368];  // kept index -> coded position, P1         m17_puncture.cpp:4-6

@@ -25,28 +25,39 @@ template <int X> __device__ __forceinline__ float pick4(float m0, float m1, floa
 // One trellis step (m17_conv.cpp:73-113).  New state v is reached from w = (2v)&15 (even) and y = w+1 (odd);
 // the branch symbol is the encoder output for register (v>>3)<<4 | predecessor.  Strict '>' keeps the even
 // predecessor, ties go to the odd one.  Returns the 16 decisions (bit v set = odd predecessor chosen).
+// one butterfly: a = acm[w]+met[x], b = acm[y]+met[z]; keep a iff a > b (ties and NaN go to the odd predecessor, exactly
+// like 'if(tempa>tempb)' in the BF macro); the decision bit is OR-ed in under the predicate (no select + shift + or).
+__device__ __forceinline__ float acs_select(float a, float b, unsigned &dec, unsigned bit) {
+    float r;
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %2, %3;\n\tselp.f32 %0, %2, %3, p;\n\t@!p or.b32 %1, %1, %4;\n\t}"
+        : "=f"(r), "+r"(dec) : "f"(a), "f"(b), "r"(bit));
+    return r;
+}
 template <int V> struct Acs {
     __device__ __forceinline__ static void run(const float (&acm)[16], float (&tm)[16], float m0, float m1, float m2, float m3, unsigned &dec) {
         constexpr int w = (2 * V) & 15, y = w + 1, hi = (V >> 3) << 4;
         constexpr int x = conv_sym(hi | w), z = conv_sym(hi | y);
-        float a = acm[w] + pick4<x>(m0, m1, m2, m3);
-        float b = acm[y] + pick4<z>(m0, m1, m2, m3);
-        bool even = a > b;
-        tm[V] = even ? a : b;
-        dec |= even ? 0u : (1u << V);
+        const float a = acm[w] + pick4<x>(m0, m1, m2, m3);
+        const float b = acm[y] + pick4<z>(m0, m1, m2, m3);
+        tm[V] = acs_select(a, b, dec, 1u << V);
         Acs<V + 1>::run(acm, tm, m0, m1, m2, m3, dec);
     }
 };
 template <> struct Acs<16> {
     __device__ __forceinline__ static void run(const float (&)[16], float (&)[16], float, float, float, float, unsigned &) {}
 };
-__device__ __forceinline__ unsigned viterbi_step(float (&acm)[16], float s1, float s2) {
+// one trellis step from metrics `from` into `to` (ping-pong, so no register copies); returns the 16 decisions
+__device__ __forceinline__ unsigned viterbi_step_pp(const float (&from)[16], float (&to)[16], float s1, float s2) {
     // branch metrics: correlation of (+-s1, +-s2) with the expected pair, each a single rounded add
-    float n1 = -s1, n2 = -s2;
-    float m0 = n1 + n2, m1 = n1 + s2, m2 = s1 + n2, m3 = s1 + s2;
-    float tm[16];
+    const float n1 = -s1, n2 = -s2;
+    const float m0 = n1 + n2, m1 = n1 + s2, m2 = s1 + n2, m3 = s1 + s2;
     unsigned dec = 0;
-    Acs<0>::run(acm, tm, m0, m1, m2, m3, dec);
+    Acs<0>::run(from, to, m0, m1, m2, m3, dec);
+    return dec;
+}
+__device__ __forceinline__ unsigned viterbi_step(float (&acm)[16], float s1, float s2) {
+    float tm[16];
+    const unsigned dec = viterbi_step_pp(acm, tm, s1, s2);
 #pragma unroll
     for (int v = 0; v < 16; v++) acm[v] = tm[v];
     return dec;
@@ -110,23 +121,28 @@ struct FrameLsf    { static constexpr int STEPS = 244, NBYTES = 30; __device__ s
 struct FrameStream { static constexpr int STEPS = 148, NBYTES = 18; __device__ static const uint16_t *map() { return c_maps.p2; } };
 struct FramePacket { static constexpr int STEPS = 210, NBYTES = 26; __device__ static const uint16_t *map() { return c_maps.p3; } };
 
-__device__ __forceinline__ float gather_soft(const float *row, float cor, unsigned e) {
+// soft value for one gather-map entry; the row already holds m = sym * cor (m17_dsp.cpp:38) for the payload symbols
+__device__ __forceinline__ float gather_soft(const float *row, unsigned e) {
     if (e == MAP_ERASE) return 0.0f;                                        // m17_puncture.cpp:52,63,75
-    float v = demap_soft(row[e & 0xFFu], cor, (e & MAP_LSB) != 0);
+    const float m = row[e & 0xFFu];
+    const float v = (e & MAP_LSB) ? __double2float_rn((double)fabsf(m) - 0.6666) : -m;   // m17_dsp.cpp:40-41
     return (e & MAP_NEG) ? -v : v;                                          // m17_correlate.cpp:29
 }
 
-// Viterbi + traceback + pack for one frame; row = this thread's 192 symbols in smem (reused as byte scratch
+// Viterbi + traceback + pack for one frame; row = this thread's scaled symbols in smem (reused as byte scratch
 // afterwards), dec = this thread's decision column.  Writes NBYTES decoded bytes to obytes (smem).
 template <class F, int NT>
-__device__ __forceinline__ void decode_conv(const float *row, float cor, uint16_t *dec, int tid, uint8_t *obytes) {
+__device__ __forceinline__ void decode_conv(const float *row, uint16_t *dec, int tid, uint8_t *obytes) {
     const uint16_t *map = F::map();
-    float acm[16];
-    viterbi_init(acm);
-    for (int t = 0; t < F::STEPS; t++) {
-        float s1 = gather_soft(row, cor, map[2 * t]);
-        float s2 = gather_soft(row, cor, map[2 * t + 1]);
-        dec[t * NT + tid] = (uint16_t)viterbi_step(acm, s1, s2);
+    float ma[16], mb[16];
+    viterbi_init(ma);
+    static_assert(F::STEPS % 2 == 0, "two steps per iteration");
+    for (int t = 0; t < F::STEPS; t += 2) {
+        const uint2 e = *(const uint2 *)(map + 2 * t);                      // four uint16 entries, warp-uniform
+        const float s1 = gather_soft(row, e.x & 0xFFFFu), s2 = gather_soft(row, e.x >> 16);
+        const float s3 = gather_soft(row, e.y & 0xFFFFu), s4 = gather_soft(row, e.y >> 16);
+        dec[t * NT + tid] = (uint16_t)viterbi_step_pp(ma, mb, s1, s2);
+        dec[(t + 1) * NT + tid] = (uint16_t)viterbi_step_pp(mb, ma, s3, s4);
     }
     // traceback from state 0; out[t] = MSB of the state at step t = input bit t-1.  Callers discard out[0] and pack
     // out[1..8*NBYTES] MSB first (pack_1_to_8(&bits[1],...), m17_rx_parse.cpp:97,142,171).
@@ -142,7 +158,9 @@ __device__ __forceinline__ void decode_conv(const float *row, float cor, uint16_
 
 // frames: records pre-filled with sym_off/type/flags by the framer (or by k_parse_init); the symbols of record r
 // of channel c start at syms[c*sym_pitch + sym_carry + (rec.sym_off - sym_base[c])].
-template <int NT>
+// STREAM = true : handles stream frames only (148-step survivor store -> more CTAs per SM);
+// STREAM = false: handles LSF / packet / BERT frames (244-step store); CTAs without such a frame exit at once.
+template <int NT, bool STREAM>
 __global__ void __launch_bounds__(NT) k_decode_frames(const float *__restrict__ syms, int64_t sym_pitch, int sym_carry,
                                                       const int32_t *__restrict__ sym_base, m17b_frame_rec *frames, int64_t fcap,
                                                       const int32_t *__restrict__ nframes, int tiles_per_chan, float *soft_out,
@@ -151,25 +169,28 @@ __global__ void __launch_bounds__(NT) k_decode_frames(const float *__restrict__ 
     extern __shared__ unsigned char smem_raw[];
     constexpr int PITCH = 193;
     float *rows = (float *)smem_raw;                                        // [NT][193]
-    uint16_t *dec = (uint16_t *)(smem_raw + (size_t)NT * PITCH * 4);        // [244][NT]
+    uint16_t *dec = (uint16_t *)(smem_raw + (size_t)NT * PITCH * 4);        // [148 or 244][NT]
     __shared__ uint16_t crc_tab[256];
     const int tid = threadIdx.x, lane = tid & 31, wbase = tid & ~31;
-    for (int i = tid; i < 256; i += NT) crc_tab[i] = g_crc[i];
-    __syncthreads();
     const int64_t c = blockIdx.x / tiles_per_chan;
     const int tile = blockIdx.x % tiles_per_chan;
     const int nfr = min((int64_t)nframes[c], fcap);
     const int slot = tile * NT + tid;
     m17b_frame_rec *rec = frames + c * fcap + slot;
     int type = -1, flags = 0;
+    uint32_t w0 = 0;
     int64_t src = 0;
     if (slot < nfr) {
-        uint2 hd = *(const uint2 *)rec;
+        const uint2 hd = *(const uint2 *)rec;
+        w0 = hd.x;
         type = (hd.y & 0xFF);
         flags = (hd.y >> 8) & 0xFF;
         src = c * sym_pitch + sym_carry + ((int32_t)hd.x - (sym_base ? sym_base[c] : 0));
     }
-    const bool work = (slot < nfr) && (flags & M17B_F_PARSED) && type >= 1 && type <= 4;
+    const bool mine = STREAM ? (type == M17B_T_STREAM) : (type == M17B_T_LSF || type == M17B_T_PACKET || type == M17B_T_BERT);
+    const bool work = (slot < nfr) && (flags & M17B_F_PARSED) && mine;
+    if (!__syncthreads_or(work)) return;
+    for (int i = tid; i < 256; i += NT) crc_tab[i] = g_crc[i];
     // stage: each warp loads the rows of its own 32 frames (coalesced 128-byte requests)
     for (int r = 0; r < 32; r++) {
         const bool w_r = __shfl_sync(0xffffffffu, (int)work, r) != 0;
@@ -180,59 +201,70 @@ __global__ void __launch_bounds__(NT) k_decode_frames(const float *__restrict__ 
             for (int k = 0; k < 6; k++) dst[lane + 32 * k] = __ldg(&syms[s_r + lane + 32 * k]);
         }
     }
-    __syncwarp();
+    __syncthreads();
     if (!work) return;
     float *row = &rows[tid * PITCH];
     float hdr[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) hdr[i] = row[i];
     const float cor = demap_cor(hdr);
+    for (int k = 8; k < 192; k++) row[k] = row[k] * cor;                    // m = in * mag  (m17_dsp.cpp:38), once per symbol
     if (soft_out) {
         float *so = soft_out + (c * fcap + slot) * 368;
-        for (int k = 0; k < 184; k++) { so[2 * k] = demap_soft(row[8 + k], cor, false); so[2 * k + 1] = demap_soft(row[8 + k], cor, true); }
+        for (int k = 0; k < 184; k++) {
+            const float m = row[8 + k];
+            so[2 * k] = -m;
+            so[2 * k + 1] = __double2float_rn((double)fabsf(m) - 0.6666);
+        }
     }
-    uint32_t golay_e = 0, nbytes = 0;
-    uint32_t lw01 = 0, lw23 = 0;
-    uint8_t *ob = (uint8_t *)&rows[tid * PITCH] ;                           // byte scratch AFTER the ACS pass (row no longer needed)
-    uint8_t dbytes[32];
-    if (type == M17B_T_STREAM) {
+    uint32_t golay_e = 0, nbytes = 0, lw01 = 0, lw23 = 0;
+    uint8_t *ob = (uint8_t *)row;                                           // byte scratch AFTER the ACS pass (row no longer needed)
+    if (STREAM) {
         // 4 x hard_decode_24_bits (m17_bit_utils.cpp:180-187: bit = soft >= 0) + m_17_golay_decode
         uint32_t w[4];
         for (int q = 0; q < 4; q++) {
             uint32_t word = 0;
-            for (int b = 0; b < 24; b++) word = (word << 1) | (gather_soft(row, cor, c_maps.lich[24 * q + b]) >= 0 ? 1u : 0u);
+            for (int b = 0; b < 24; b++) word = (word << 1) | (gather_soft(row, c_maps.lich[24 * q + b]) >= 0 ? 1u : 0u);
             golay_e += (uint32_t)golay_decode_word(word, genc, gerr, &w[q]);
         }
         lw01 = (w[0] << 12) | w[1];                                          // pack_12_to_8_x4x6, m17_bit_utils.cpp:152-172
         lw23 = (w[2] << 12) | w[3];
-        decode_conv<FrameStream, NT>(row, cor, dec, tid, ob);
+        decode_conv<FrameStream, NT>(row, dec, tid, ob);
         nbytes = FrameStream::NBYTES;
     } else if (type == M17B_T_LSF) {
-        decode_conv<FrameLsf, NT>(row, cor, dec, tid, ob);
+        decode_conv<FrameLsf, NT>(row, dec, tid, ob);
         nbytes = FrameLsf::NBYTES;
     } else if (type == M17B_T_PACKET) {
-        decode_conv<FramePacket, NT>(row, cor, dec, tid, ob);
+        decode_conv<FramePacket, NT>(row, dec, tid, ob);
         nbytes = FramePacket::NBYTES;
     }
-    uint16_t crc = 0;
+    uint32_t crc = 0;
     if (nbytes) {
-        crc = 0xFFFF;
-        for (uint32_t i = 0; i < nbytes; i++) crc = crc16_step(crc, ob[i], crc_tab);
+        uint16_t k = 0xFFFF;
+        for (uint32_t i = 0; i < nbytes; i++) k = crc16_step(k, ob[i], crc_tab);
+        crc = k;
+        for (uint32_t i = nbytes; i < 32; i++) ob[i] = 0;
+    } else {
+        for (int i = 0; i < 32; i++) ob[i] = 0;
     }
-#pragma unroll
-    for (int i = 0; i < 32; i++) dbytes[i] = (i < (int)nbytes) ? ob[i] : 0;
-    // assemble bytes 4..47 and 52..55 of the record (0..3, 46..51 belong to the framer)
-    uint8_t *rb = (uint8_t *)rec;
-    if (type == M17B_T_PACKET && (dbytes[25] & 0x80)) flags |= M17B_F_PKT_EOF;
-    rb[5] = (uint8_t)flags;
-    rb[6] = (uint8_t)golay_e;
-    rb[7] = (uint8_t)nbytes;
-    rb[8] = (uint8_t)(lw01 >> 16); rb[9] = (uint8_t)(lw01 >> 8); rb[10] = (uint8_t)lw01;
-    rb[11] = (uint8_t)(lw23 >> 16); rb[12] = (uint8_t)(lw23 >> 8); rb[13] = (uint8_t)lw23;
-#pragma unroll
-    for (int i = 0; i < 30; i++) rb[14 + i] = dbytes[i];
-    *(uint16_t *)(rb + 44) = crc;
-    rec->cor = cor;
+    const uint16_t *oh = (const uint16_t *)ob;                              // data[] as 15 half-words
+    if (type == M17B_T_PACKET && (ob[25] & 0x80)) flags |= M17B_F_PKT_EOF;
+    // assemble the 64-byte record in registers: words 0/1 (sym_off, type) and the votes/errors/variance fields come
+    // from the framer, everything else from this kernel
+    uint32_t *rw = (uint32_t *)rec;
+    const uint32_t w11_old = rw[11], w12 = rw[12];
+    uint4 q0, q1, q2, q3;
+    q0.x = w0;
+    q0.y = (uint32_t)type | ((uint32_t)flags << 8) | (golay_e << 16) | (nbytes << 24);
+    q0.z = ((lw01 >> 16) & 0xFF) | (((lw01 >> 8) & 0xFF) << 8) | ((lw01 & 0xFF) << 16) | (((lw23 >> 16) & 0xFF) << 24);
+    q0.w = ((lw23 >> 8) & 0xFF) | ((lw23 & 0xFF) << 8) | ((uint32_t)oh[0] << 16);
+    q1.x = oh[1] | ((uint32_t)oh[2] << 16);   q1.y = oh[3] | ((uint32_t)oh[4] << 16);
+    q1.z = oh[5] | ((uint32_t)oh[6] << 16);   q1.w = oh[7] | ((uint32_t)oh[8] << 16);
+    q2.x = oh[9] | ((uint32_t)oh[10] << 16);  q2.y = oh[11] | ((uint32_t)oh[12] << 16);
+    q2.z = oh[13] | ((uint32_t)oh[14] << 16); q2.w = crc | (w11_old & 0xFFFF0000u);
+    q3.x = w12; q3.y = __float_as_uint(cor); q3.z = 0; q3.w = 0;
+    uint4 *r4 = (uint4 *)rec;
+    r4[0] = q0; r4[1] = q1; r4[2] = q2; r4[3] = q3;
 }
 
 // stand-alone m17_rx_parse for n independent frames: initialise records, then run the fused decode
@@ -246,18 +278,24 @@ __global__ void k_parse_init(const uint8_t *type, int64_t n, m17b_frame_rec *rec
 }
 __global__ void k_set_i32(int32_t *p, int32_t v) { *p = v; }
 
-template <int NT> static size_t decode_smem() { return (size_t)NT * 193 * 4 + (size_t)244 * NT * 2; }
-#define DECODE_NT 64
+#define DECODE_NT 32
+template <int NT, bool STREAM> static size_t decode_smem() { return (size_t)NT * 193 * 4 + (size_t)(STREAM ? 148 : 244) * NT * 2; }
 
 static int launch_decode(m17b_ctx *ctx, const float *syms, int64_t sym_pitch, int sym_carry, const int32_t *sym_base,
                          m17b_frame_rec *frames, int64_t fcap, const int32_t *nframes, int64_t nchan, float *soft_out, cudaStream_t st) {
     const int tiles = (int)((fcap + DECODE_NT - 1) / DECODE_NT);
-    const size_t smem = decode_smem<DECODE_NT>();
     static bool attr_set = false;
-    if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(k_decode_frames<DECODE_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(k_decode_frames<DECODE_NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_smem<DECODE_NT, true>()));
+        CUDA_TRY(cudaFuncSetAttribute(k_decode_frames<DECODE_NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_smem<DECODE_NT, false>()));
+        attr_set = true;
+    }
     if ((int64_t)tiles * nchan > 0x7fffffffLL) return M17B_E_ARG;
-    k_decode_frames<DECODE_NT><<<(unsigned)(tiles * nchan), DECODE_NT, smem, st>>>(syms, sym_pitch, sym_carry, sym_base, frames, fcap, nframes, tiles,
-                                                                                 soft_out, ctx->d_crc, ctx->d_genc, ctx->d_gerr);
+    const unsigned grid = (unsigned)(tiles * nchan);
+    k_decode_frames<DECODE_NT, true><<<grid, DECODE_NT, decode_smem<DECODE_NT, true>(), st>>>(syms, sym_pitch, sym_carry, sym_base, frames, fcap, nframes,
+                                                                                          tiles, soft_out, ctx->d_crc, ctx->d_genc, ctx->d_gerr);
+    k_decode_frames<DECODE_NT, false><<<grid, DECODE_NT, decode_smem<DECODE_NT, false>(), st>>>(syms, sym_pitch, sym_carry, sym_base, frames, fcap, nframes,
+                                                                                           tiles, soft_out, ctx->d_crc, ctx->d_genc, ctx->d_gerr);
     KERNEL_CHECK();
     return M17B_OK;
 }

@@ -7,92 +7,187 @@
 // With AFC off (the reference default, radio.cpp:146-155) nothing but two input samples and the /5 phase
 // crosses a block boundary, so every (channel, block) item is independent.  The only serial work inside an
 // item is the fp32 running sum, whose order must be kept for bit-exactness, hence:
-//   mapping: one LANE per item, one warp per 32 items.  The warp loads a [32 items][32 samples] tile with
-//   32 coalesced 128-byte row requests, stages it in shared memory (pitch 33), and each lane then walks its
-//   own row sequentially.  Kept outputs collect in a second [32][33] tile that is flushed with coalesced row
-//   stores every 160 samples (160 = 32 outputs x 5).  HBM traffic per item: 7680 B in, 1536 + 4 B out.
+//   mapping: one LANE per item, one warp per 32 items.  Each lane streams its own 7680-byte row with 16-byte
+//   loads (software-pipelined one 20-sample chunk ahead; the 32-byte sectors are fully consumed through L1), and
+//   walks it sequentially with the discriminator history in registers.  Because 20 = lcm(4 samples per load,
+//   5 = decimation), the kept sample of every group of five sits at a lane-constant position: no counters.
+//   Kept outputs collect in a [32][33] shared tile that is flushed with coalesced 128-byte row stores every
+//   160 samples.  HBM traffic per item: 7680 B in, 1536 + 4 B out (the algorithmic minimum of the staged design).
 // The raw (not mean-removed) discriminator samples and the block mean are written; the consumer applies
 // out[i] - mean (one fp32 subtract, identical to m17_dsp.cpp:217-219).
+//
+// Arithmetic (all verified EXHAUSTIVELY on the GPU by m17b_selftest_frontend over the 2^32 possible IQ samples):
+//   * (float)((double)x * 0.00003) == fmaf(x, c_hi, x * c_lo) with c_hi + c_lo the two-float split of 0.00003;
+//   * m = sqrtf(re^2 + im^2) and g = (float)(1.0 / m) (== correctly rounded fp32 reciprocal, 2p+2 theorem) are
+//     produced from ONE rsqrt.approx seed with FMA residual corrections instead of the branchy library sequences.
 #pragma once
 #include "decode.cuh"
 
 #define FE_WARPS 4
 
 struct LimSample { float re, im; };
-__device__ __forceinline__ LimSample fe_limit(uint32_t raw) {
-    // dsp_short_to_float: int16 * 0.00003 evaluated in double, rounded once to float (m17_dsp.cpp:138-139)
+
+// reference formulation, kept for the exhaustive self-test
+__device__ __forceinline__ LimSample fe_limit_ieee(uint32_t raw, float *mo = nullptr, float *go = nullptr) {
     const int re_i = (int)(int16_t)(raw & 0xFFFFu), im_i = (int)(int16_t)(raw >> 16);
-    float re = __double2float_rn((double)re_i * 0.00003);
+    float re = __double2float_rn((double)re_i * 0.00003);     // dsp_short_to_float, m17_dsp.cpp:138-139
     float im = __double2float_rn((double)im_i * 0.00003);
-    // dsp_limit: m = sqrtf(re*re + im*im); g = (float)(1.0 / m) == correctly rounded fp32 reciprocal (2p+2 theorem)
-    float m = sqrtf(re * re + im * im);
+    float m = sqrtf(re * re + im * im);                       // dsp_limit, m17_dsp.cpp:414-417
     float g = 1.0f / m;
+    if (mo) { *mo = m; *go = g; }
     LimSample s;
     s.re = re * g;
     s.im = im * g;
     return s;
 }
 
+__device__ __forceinline__ LimSample fe_limit(uint32_t raw, float *mo = nullptr, float *go = nullptr) {
+    // int16 -> float without the conversion pipe: (x + 32768) planted in the mantissa of 2^23
+    const float bias = 8388608.0f + 32768.0f;
+    const float xr = __uint_as_float(((raw & 0xFFFFu) ^ 0x8000u) | 0x4B000000u) - bias;
+    const float xi = __uint_as_float(((raw >> 16) ^ 0x8000u) | 0x4B000000u) - bias;
+    constexpr float c_hi = 0.00003f;
+    constexpr float c_lo = (float)(0.00003 - (double)0.00003f);
+    const float re = __fmaf_rn(xr, c_hi, xr * c_lo);
+    const float im = __fmaf_rn(xi, c_hi, xi * c_lo);
+    const float s = re * re + im * im;                        // two rounded products, one rounded sum (no contraction)
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(s));
+    // m = RN(sqrt(s)): Newton step on the residual
+    float m = s * y;
+    const float h = 0.5f * y;
+    m = __fmaf_rn(__fmaf_rn(-m, m, s), h, m);
+    // g = RN(1/m): two residual corrections starting from y ~ 1/m (Markstein).  The one input class this cannot round
+    // correctly is a divisor whose significand is all ones: the Newton iterate then lands exactly on a rounding midpoint
+    // while the true quotient 2^-(e+1) (1 + 2^-24 + 2^-48 + ..) lies just above it; its correctly rounded value is known in
+    // closed form, 2^-(e+1) (1 + 2^-23), whose bit pattern is 0x7F000000 - bits(m).
+    float g = __fmaf_rn(__fmaf_rn(-m, y, 1.0f), y, y);
+    g = __fmaf_rn(__fmaf_rn(-m, g, 1.0f), g, g);
+    const uint32_t mb = __float_as_uint(m);
+    if (((mb + 1u) & 0x7FFFFFu) == 0u) g = __uint_as_float(0x7F000000u - mb);
+    if (mo) { *mo = m; *go = g; }
+    LimSample o;
+    o.re = re * g;
+    o.im = im * g;
+    return o;
+}
+
+// 5-way select by a lane-constant position
+__device__ __forceinline__ float sel5(float a0, float a1, float a2, float a3, float a4, int k) {
+    float lo = (k == 0) ? a0 : a1;
+    float hi = (k == 2) ? a2 : a3;
+    float r = (k < 2) ? lo : hi;
+    return (k == 4) ? a4 : r;
+}
+
 __global__ void __launch_bounds__(FE_WARPS * 32) k_frontend(const uint32_t *__restrict__ iq, int64_t nchan, int64_t T, RxChanState *st,
                                                             float *__restrict__ disc, float *__restrict__ mean) {
-    __shared__ uint32_t tin[FE_WARPS][32][33];
     __shared__ float tout[FE_WARPS][32][33];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t nitems = nchan * T;
     const int64_t item0 = ((int64_t)blockIdx.x * FE_WARPS + wid) * 32;
     if (item0 >= nitems) return;
-    const int64_t item = item0 + lane;
-    const bool live = item < nitems;
-    const int64_t ch = live ? item / T : 0;
-    const int64_t t = live ? item % T : 0;
+    const bool live = item0 + lane < nitems;
+    const int64_t item = live ? item0 + lane : nitems - 1;       // dead lanes shadow the last item (results discarded)
+    const int64_t ch = item / T, t = item % T;
+    const uint4 *row = (const uint4 *)(iq + item * 1920);
 
     // carried discriminator state: z[0], z[1] are the two previous LIMITED samples (m17_dsp.cpp:196,205-206)
-    float z0re = 0, z0im = 0, z1re = 0, z1im = 0;
-    int count = 0;
-    if (live) {
-        count = st[ch].disc_count;                       // 1920 % 5 == 0: the /5 phase is the same in every block
-        if (t == 0) { z0re = st[ch].z0re; z0im = st[ch].z0im; z1re = st[ch].z1re; z1im = st[ch].z1im; }
-        else {
-            const uint32_t *prev = iq + item * 1920;
-            LimSample a = fe_limit(__ldg(prev - 1)), b = fe_limit(__ldg(prev - 2));
-            z0re = a.re; z0im = a.im; z1re = b.re; z1im = b.im;
-        }
+    float z0re, z0im, z1re, z1im;
+    const int count0 = st[ch].disc_count;                        // 1920 % 5 == 0: the /5 phase is the same in every block
+    if (t == 0) { z0re = st[ch].z0re; z0im = st[ch].z0im; z1re = st[ch].z1re; z1im = st[ch].z1im; }
+    else {
+        const uint32_t *prev = iq + item * 1920;
+        LimSample a = fe_limit(__ldg(prev - 1)), b = fe_limit(__ldg(prev - 2));
+        z0re = a.re; z0im = a.im; z1re = b.re; z1im = b.im;
     }
-    float offset = 0;
-    int nout = 0;                                        // outputs in the current 160-sample group
-    for (int tile = 0; tile < 60; tile++) {
-        // coalesced loads: row r = item0 + r, 32 consecutive samples
-        uint32_t v[32];
+    const int keep = 4 - count0;                                 // count = (count+1)%5 hits 0 at samples = keep (mod 5)
+    float acc = 0.0f;                                            // sum of u; sum of u*0.5 == 0.5*sum (exact power-of-two scaling)
+    uint4 cur[5], nxt[5];
 #pragma unroll
-        for (int r = 0; r < 32; r++) v[r] = (item0 + r < nitems) ? __ldg(iq + (item0 + r) * 1920 + tile * 32 + lane) : 0x00010001u;
+    for (int q = 0; q < 5; q++) cur[q] = __ldg(row + q);
+    for (int grp = 0; grp < 12; grp++) {
+#pragma unroll 1
+        for (int chk = 0; chk < 8; chk++) {
+            const int c20 = grp * 8 + chk;
+            if (c20 < 95) {
 #pragma unroll
-        for (int r = 0; r < 32; r++) tin[wid][r][lane] = v[r];
-        __syncwarp();
-#pragma unroll 8
-        for (int s = 0; s < 32; s++) {
-            LimSample x = fe_limit(tin[wid][lane][s]);
-            // dsp_arctan_disc2 (m17_dsp.cpp:203-212)
-            float a = z0im * (x.re - z1re);
-            float b = z0re * (x.im - z1im);
-            float u = b - a;
-            z1re = z0re; z1im = z0im; z0re = x.re; z0im = x.im;
-            float uc = u * 0.5f;
-            count = (count + 1 == 5) ? 0 : count + 1;
-            if (count == 0) tout[wid][lane][nout++] = uc;
-            offset += uc;
+                for (int q = 0; q < 5; q++) nxt[q] = __ldg(row + (c20 + 1) * 5 + q);
+            }
+            float u[20];
+#pragma unroll
+            for (int s = 0; s < 20; s++) {
+                const uint4 w = cur[s >> 2];
+                const uint32_t raw = (s & 3) == 0 ? w.x : (s & 3) == 1 ? w.y : (s & 3) == 2 ? w.z : w.w;
+                const LimSample x = fe_limit(raw);
+                // dsp_arctan_disc2 (m17_dsp.cpp:203-212)
+                const float a = z0im * (x.re - z1re);
+                const float b = z0re * (x.im - z1im);
+                u[s] = b - a;
+                z1re = z0re; z1im = z0im; z0re = x.re; z0im = x.im;
+                acc += u[s];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                tout[wid][lane][chk * 4 + j] = sel5(u[5 * j], u[5 * j + 1], u[5 * j + 2], u[5 * j + 3], u[5 * j + 4], keep) * 0.5f;
+#pragma unroll
+            for (int q = 0; q < 5; q++) cur[q] = nxt[q];
         }
         __syncwarp();
-        if (tile % 5 == 4) {                             // 160 samples done: exactly 32 outputs per lane
-            const int grp = tile / 5;
 #pragma unroll 4
-            for (int r = 0; r < 32; r++)
-                if (item0 + r < nitems) disc[(item0 + r) * 384 + grp * 32 + lane] = tout[wid][r][lane];
-            nout = 0;
-            __syncwarp();
-        }
+        for (int r = 0; r < 32; r++)
+            if (item0 + r < nitems) disc[(item0 + r) * 384 + grp * 32 + lane] = tout[wid][r][lane];
+        __syncwarp();
     }
     if (live) {
-        mean[item] = offset / 1920.0f;                   // offset/len (m17_dsp.cpp:214)
+        mean[item] = (acc * 0.5f) / 1920.0f;                     // offset/len (m17_dsp.cpp:214)
         if (t == T - 1) { st[ch].nz0re = z0re; st[ch].nz0im = z0im; st[ch].nz1re = z1re; st[ch].nz1im = z1im; }
     }
+}
+
+// Exhaustive proof-by-enumeration that fe_limit == fe_limit_ieee for every possible int16 IQ pair except (0,0)
+// (which the reference itself turns into NaN).  Counts bitwise mismatches of either output component.
+__global__ void k_selftest_frontend(unsigned long long *mism, uint32_t lo, uint32_t count, uint32_t *dump, int dump_cap) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned bad = 0;
+    for (uint32_t k = i; k < count; k += gridDim.x * blockDim.x) {
+        const uint32_t raw = lo + k;
+        if (raw == 0) continue;
+        float m1, g1, m2, g2;
+        const LimSample a = fe_limit(raw, &m1, &g1), b = fe_limit_ieee(raw, &m2, &g2);
+        if ((__float_as_uint(a.re) != __float_as_uint(b.re)) | (__float_as_uint(a.im) != __float_as_uint(b.im))) {
+            bad++;
+            if (dump) {
+                unsigned long long slot = atomicAdd(mism + 1, 1ull);
+                if (5 * slot + 4 < (unsigned long long)dump_cap) {
+                    dump[5 * slot] = raw; dump[5 * slot + 1] = __float_as_uint(m1); dump[5 * slot + 2] = __float_as_uint(m2);
+                    dump[5 * slot + 3] = __float_as_uint(g1); dump[5 * slot + 4] = __float_as_uint(g2);
+                }
+            }
+        }
+    }
+    if (bad) atomicAdd(mism, (unsigned long long)bad);
+}
+// h_dump (optional, dump_cap words) receives {raw, m_fast, m_ieee, g_fast, g_ieee} of the first mismatches found
+extern "C" int m17b_selftest_frontend(m17b_ctx *ctx, uint64_t first, uint64_t count, uint64_t *h_mismatches, uint32_t *h_dump, int dump_cap, void *stream) {
+    if (!ctx || !h_mismatches || first + count > (1ull << 32) || dump_cap < 0) return M17B_E_ARG;
+    cudaStream_t st = as_stream(stream);
+    unsigned long long *d;
+    uint32_t *d_dump = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&d, 16));
+    CUDA_TRY(cudaMemsetAsync(d, 0, 16, st));
+    if (h_dump && dump_cap) { CUDA_TRY(cudaMalloc((void **)&d_dump, 4 * (size_t)dump_cap)); CUDA_TRY(cudaMemsetAsync(d_dump, 0, 4 * (size_t)dump_cap, st)); }
+    for (uint64_t off = 0; off < count; off += (1ull << 30)) {
+        const uint64_t n = count - off < (1ull << 30) ? count - off : (1ull << 30);
+        k_selftest_frontend<<<148 * 16, 256, 0, st>>>(d, (uint32_t)(first + off), (uint32_t)n, d_dump, dump_cap);
+    }
+    KERNEL_CHECK();
+    unsigned long long h = 0;
+    CUDA_TRY(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, st));
+    if (d_dump) CUDA_TRY(cudaMemcpyAsync(h_dump, d_dump, 4 * (size_t)dump_cap, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaFree(d));
+    if (d_dump) CUDA_TRY(cudaFree(d_dump));
+    *h_mismatches = h;
+    return M17B_OK;
 }

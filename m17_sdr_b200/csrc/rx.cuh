@@ -42,57 +42,93 @@ __global__ void k_rx_reset(RxChanState *st, int64_t nchan) {
     st[c].index = 10;
 }
 
-// Sequential per-channel tail of m17_rx_parse: thread per channel, records in order.
-__global__ void k_post(m17b_frame_rec *frames, int64_t fcap, const int32_t *__restrict__ nframes, int64_t nchan, RxChanState *st,
-                       const uint16_t *__restrict__ g_crc, unsigned long long *stats) {
+// Sequential per-channel tail of m17_rx_parse (update_lich / parse_packet / delivery gate).  One WARP per channel:
+// the lanes stage 32 record headers at a time into shared memory with one strided 16-byte load each, lane 0 walks
+// them in order against the channel's LICH cache (kept in shared memory for the duration of the call), and the
+// lanes write the updated flag bytes back.  The 30-byte CRC of m_lsf[0] is only recomputed when a LICH chunk
+// actually changes the cache -- while a stream runs the same six chunks repeat, so the cached verdict is reused
+// (identical result: the CRC is a pure function of the 30 bytes).
+#define POST_WARPS 4
+struct PostWarpSmem { uint4 hdr[32]; uint8_t lsf0[32], lsf1[32]; };
+__global__ void __launch_bounds__(POST_WARPS * 32) k_post(m17b_frame_rec *frames, int64_t fcap, const int32_t *__restrict__ nframes, int64_t nchan,
+                                                          RxChanState *st, const uint16_t *__restrict__ g_crc, unsigned long long *stats) {
     __shared__ uint16_t tab[256];
+    __shared__ PostWarpSmem sm_all[POST_WARPS];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = g_crc[i];
     __syncthreads();
-    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t c = (int64_t)blockIdx.x * POST_WARPS + wid;
     if (c >= nchan) return;
+    PostWarpSmem &sm = sm_all[wid];
     RxChanState *S = st + c;
+    sm.lsf0[lane] = S->lsf[0][lane];
+    sm.lsf1[lane] = S->lsf[1][lane];
+    __syncwarp();
     auto crc30 = [&](const uint8_t *p) { uint16_t k = 0xFFFF; for (int i = 0; i < 30; i++) k = crc16_step(k, p[i], tab); return k; };
-    bool lsf_ok = crc30(S->lsf[1]) == 0;
+    bool lsf0_ok = false, lsf1_ok = false;
+    if (lane == 0) { lsf0_ok = crc30(sm.lsf0) == 0; lsf1_ok = crc30(sm.lsf1) == 0; }
     unsigned long long n_stream = 0, n_gerr = 0, n_deliv = 0, n_lsf = 0;
     const int n = nframes[c];
-    for (int k = 0; k < n; k++) {
-        m17b_frame_rec *r = frames + c * fcap + k;
-        int flags = r->flags;
-        if (!(flags & M17B_F_PARSED)) continue;
-        const int type = r->type;
-        if (type == M17B_T_LSF) {
-            // decode_link_frame checks the CRC of m_packet, not of the decoded bytes (m17_rx_parse.cpp:98);
-            // the honest verdict for the decoded LSF is r->crc == 0
-            if (crc30(S->packet) == 0) { flags |= M17B_F_LSF_EVENT; n_lsf++; }
-        } else if (type == M17B_T_STREAM) {
-            n_stream++;
-            n_gerr += r->golay_err;
-            const int seq = r->lich[5] >> 5;                                    // update_lich, m17_rx_parse.cpp:71-85
-            if (seq < 6) {
-                for (int i = 0; i < 5; i++) S->lsf[0][seq * 5 + i] = r->lich[i];
-                if (crc30(S->lsf[0]) == 0) {
-                    for (int i = 0; i < 30; i++) S->lsf[1][i] = S->lsf[0][i];
-                    lsf_ok = true;
-                    flags |= M17B_F_LSF_EVENT; n_lsf++;
+    m17b_frame_rec *base = frames + c * fcap;
+    for (int k0 = 0; k0 < n; k0 += 32) {
+        const int k = k0 + lane;
+        uint4 h = make_uint4(0, 0, 0, 0);
+        if (k < n) h = *(const uint4 *)(base + k);                 // bytes 0..15: sym_off, type, flags, golay_err, nbytes, lich[6], data[0..1]
+        sm.hdr[lane] = h;
+        __syncwarp();
+        if (lane == 0) {
+            const int m = (n - k0 < 32) ? n - k0 : 32;
+            for (int j = 0; j < m; j++) {
+                const uint4 q = sm.hdr[j];
+                const int type = q.y & 0xFF;
+                int flags = (q.y >> 8) & 0xFF;
+                if (!(flags & M17B_F_PARSED)) continue;
+                if (type == M17B_T_LSF) {
+                    // decode_link_frame checks the CRC of m_packet, not of the decoded bytes (m17_rx_parse.cpp:98);
+                    // the honest verdict for the decoded LSF is the record's crc field
+                    if (crc30(S->packet) == 0) { flags |= M17B_F_LSF_EVENT; n_lsf++; }
+                } else if (type == M17B_T_STREAM) {
+                    n_stream++;
+                    n_gerr += (q.y >> 16) & 0xFF;
+                    const uint8_t l[6] = {(uint8_t)q.z, (uint8_t)(q.z >> 8), (uint8_t)(q.z >> 16), (uint8_t)(q.z >> 24), (uint8_t)q.w, (uint8_t)(q.w >> 8)};
+                    const int seq = l[5] >> 5;                                          // update_lich, m17_rx_parse.cpp:71-85
+                    if (seq < 6) {
+                        bool changed = false;
+                        for (int i = 0; i < 5; i++) { changed |= sm.lsf0[seq * 5 + i] != l[i]; sm.lsf0[seq * 5 + i] = l[i]; }
+                        if (changed) lsf0_ok = crc30(sm.lsf0) == 0;
+                        if (lsf0_ok) {
+                            for (int i = 0; i < 30; i++) sm.lsf1[i] = sm.lsf0[i];       // copy_lich
+                            lsf1_ok = true;
+                            flags |= M17B_F_LSF_EVENT; n_lsf++;
+                        }
+                    }
+                    if (lsf1_ok) { flags |= M17B_F_DELIVERED; n_deliv++; }              // :148-158
+                } else if (type == M17B_T_PACKET) {
+                    // parse_packet (m17_rx_parse.cpp:34-51) including its index bug; the copy is clamped to the buffer
+                    const m17b_frame_rec *r = base + k0 + j;
+                    const int eof = r->data[25] >> 7, fn = (r->data[25] >> 2) & 0x1F;
+                    if (eof) {
+                        int room = 800 - S->packet_idx, mm = fn < room ? fn : room;
+                        for (int i = 0; i < mm; i++) S->packet[S->packet_idx + i] = r->data[i];
+                        S->packet_idx = 0;
+                    } else {
+                        for (int i = 0; i < 25; i++) S->packet[fn * 25 + i] = r->data[i];
+                        S->packet_idx = fn * 25;
+                    }
                 }
-            }
-            if (lsf_ok) { flags |= M17B_F_DELIVERED; n_deliv++; }               // :148-158
-        } else if (type == M17B_T_PACKET) {
-            // parse_packet (m17_rx_parse.cpp:34-51) including its index bug; the copy is clamped to the buffer
-            const int eof = r->data[25] >> 7, fn = (r->data[25] >> 2) & 0x1F;
-            if (eof) {
-                int room = 800 - S->packet_idx, m = fn < room ? fn : room;
-                for (int i = 0; i < m; i++) S->packet[S->packet_idx + i] = r->data[i];
-                S->packet_idx = 0;
-            } else {
-                for (int i = 0; i < 25; i++) S->packet[fn * 25 + i] = r->data[i];
-                S->packet_idx = fn * 25;
+                sm.hdr[j].y = (q.y & 0xFFFF00FFu) | ((uint32_t)flags << 8);
             }
         }
-        r->flags = (uint8_t)flags;
+        __syncwarp();
+        if (k < n) { const uint32_t y = sm.hdr[lane].y; if (y != h.y) ((uint8_t *)(base + k))[5] = (uint8_t)(y >> 8); }
+        __syncwarp();
     }
-    unsigned long long *q = stats + c * 8;
-    q[1] += n_stream; q[2] += n_gerr; q[3] += n_deliv; q[6] += n_lsf;
+    S->lsf[0][lane] = sm.lsf0[lane];
+    S->lsf[1][lane] = sm.lsf1[lane];
+    if (lane == 0) {
+        unsigned long long *q = stats + c * 8;
+        q[1] += n_stream; q[2] += n_gerr; q[3] += n_deliv; q[6] += n_lsf;
+    }
 }
 
 extern "C" int m17b_rx_destroy(m17b_rx *rx) {
@@ -182,7 +218,7 @@ static int rx_back_half(m17b_rx *rx, int64_t c0, int64_t nc, const float *disc, 
     int rc = launch_decode(ctx, syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0, nc, nullptr, st);
     if (rc) return rc;
     STAGE_MARK(3);
-    k_post<<<grid_for(nc, 64), 64, 0, st>>>(frames, rx->fcap, rx->d_nframes + c0, nc, rx->d_state + c0, ctx->d_crc, rx->d_stats + c0 * 8);
+    k_post<<<grid_for(nc, POST_WARPS), POST_WARPS * 32, 0, st>>>(frames, rx->fcap, rx->d_nframes + c0, nc, rx->d_state + c0, ctx->d_crc, rx->d_stats + c0 * 8);
     KERNEL_CHECK();
     STAGE_MARK(4);
     rx->last_launches += 3;

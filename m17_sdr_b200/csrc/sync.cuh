@@ -4,9 +4,10 @@
 //
 // The timing loop is recursive (the polyphase branch m_index depends on an up/down counter fed by every
 // symbol), but the counter moves by at most 1 per symbol and the branch only changes when |m_thr| crosses the
-// threshold (10 unlocked / 80 locked).  So the warp SPECULATES: 32 lanes compute the next 32 symbols
-// (matched + derivative 31-tap dot products, sequential fp32 adds exactly as rx_sync_filter does) with the
-// current branch, a warp prefix-sum over the +-1 votes finds the first symbol at which the threshold would
+// threshold (10 unlocked / 80 locked).  So the warp SPECULATES: 32 lanes compute the next 64 symbols, two
+// consecutive ones per lane (matched + derivative 31-tap dot products, sequential fp32 adds exactly as
+// rx_sync_filter does, four independent chains per lane, the 33 window samples loaded once), with the
+// current branch; a warp prefix-sum over the +-1 votes finds the first symbol at which the threshold would
 // trip, symbols up to there are committed, the branch is stepped and speculation restarts.  Results are
 // identical to the serial loop, including the forward bit-slip (a zero symbol inserted, one sample skipped),
 // the backward slip (a symbol dropped) and votes that straddle a block boundary.
@@ -16,11 +17,12 @@
 #include "frontend.cuh"
 
 #define SY_WARPS 4
-#define SY_XHALF 208          // (30 + 384) / 2 = 207 entries per parity
+#define SY_XQ   106           // (30 + 384 + 2 + 8 pad) / 4 entries per residue class
 #define SY_HIST  (8 + 208)
 
 struct SyncWarpSmem {
-    float xe[SY_XHALF], xo[SY_XHALF];   // discriminator samples incl. 30 of history, split by parity (conflict-free stride-2 windows)
+    float x[4][SY_XQ];                  // discriminator samples incl. 30 of history: sample n lives at x[n & 3][n >> 2], so the
+                                        // stride-4 windows of the 32 lanes (two symbols per lane) hit 32 different banks
     float hist[SY_HIST];                // [0,8): sliding sync window carried in; [8, 8+n): symbols emitted in this block
     float head[8];                      // m_f_sym[0..7] of the frame being collected
 };
@@ -45,6 +47,23 @@ __device__ __forceinline__ void sync_adjust(int TH, int &thr, int &index, int &c
     }
 }
 
+// Two consecutive symbols for one lane: windows xs[n0 .. n0+30] and xs[n0+2 .. n0+32], n0 = i + 4*lane.  R = i & 3 is
+// warp-uniform, so array / offset of every tap are compile-time and the 32 lanes read consecutive words.
+template <int R>
+__device__ __forceinline__ void dot2(const float (*X)[SY_XQ], int base, const float (&cmf)[M17B_FN], const float (&cmd)[M17B_FN],
+                                     float &sa, float &da, float &sb, float &db) {
+    float x[M17B_FN + 2];
+#pragma unroll
+    for (int k = 0; k < M17B_FN + 2; k++) x[k] = X[(R + k) & 3][base + ((R + k) >> 2)];
+    sa = x[0] * cmf[0]; da = x[0] * cmd[0];                  // sum = in[0]*c[0]; sum += in[i]*c[i]   (m17_rx_sync.cpp:25-31)
+    sb = x[2] * cmf[0]; db = x[2] * cmd[0];
+#pragma unroll
+    for (int k = 1; k < M17B_FN; k++) {
+        sa += x[k] * cmf[k]; da += x[k] * cmd[k];
+        sb += x[k + 2] * cmf[k]; db += x[k + 2] * cmd[k];
+    }
+}
+
 template <bool HAS_MEAN>
 __global__ void __launch_bounds__(SY_WARPS * 32) k_sync_frame(const float *__restrict__ disc, const float *__restrict__ mean, int64_t nchan, int64_t T,
                                                               RxChanState *st, const float *__restrict__ g_mf, const float *__restrict__ g_md,
@@ -66,7 +85,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32) k_sync_frame(const float *__res
     float sumc = S->sum, difc = S->dif;
     int flock = S->flock, fclk = S->fclk, ferr = S->ferr, frame_start = S->frame_start, sym_total = S->sym_total;
     const int base_g = sym_total;
-    if (lane < 30) { float v = S->tail[lane]; ((lane & 1) ? sm.xo : sm.xe)[lane >> 1] = v; }
+    if (lane < 30) sm.x[lane & 3][lane >> 2] = S->tail[lane];
     if (lane < 8) { sm.hist[lane] = S->win[lane]; sm.head[lane] = S->head[lane]; }
     // carry: the last 192 symbols of the previous call move in front of the new ones
     float *sbuf = syms + c * sym_pitch;
@@ -84,20 +103,26 @@ __global__ void __launch_bounds__(SY_WARPS * 32) k_sync_frame(const float *__res
     float cmf[M17B_FN], cmd[M17B_FN];
     int tap_index = -1;
     __syncwarp();
+    // the block's samples are fetched one block ahead (registers), so the DRAM latency hides behind the timing loop
+    float pf[12], pmu = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 12; q++) pf[q] = __ldg(disc + (c * T) * 384 + lane + 32 * q);
+    if (HAS_MEAN) pmu = mean[c * T];
 
     for (int64_t t = 0; t < T; t++) {
         // ---- stage the block's 384 discriminator samples behind the 30 of history
-        {
-            const float *src = disc + (c * T + t) * 384;
-            const float mu = HAS_MEAN ? mean[c * T + t] : 0.0f;
 #pragma unroll
-            for (int q = 0; q < 12; q++) {
-                int j = lane + 32 * q;
-                float v = __ldg(src + j);
-                if (HAS_MEAN) v = v - mu;                                   // m17_dsp.cpp:217-219
-                int n = 30 + j;
-                ((n & 1) ? sm.xo : sm.xe)[n >> 1] = v;
-            }
+        for (int q = 0; q < 12; q++) {
+            float v = pf[q];
+            if (HAS_MEAN) v = v - pmu;                                      // m17_dsp.cpp:217-219
+            const int n = 30 + lane + 32 * q;
+            sm.x[n & 3][n >> 2] = v;
+        }
+        if (t + 1 < T) {
+            const float *src = disc + (c * T + t + 1) * 384;
+#pragma unroll
+            for (int q = 0; q < 12; q++) pf[q] = __ldg(src + lane + 32 * q);
+            if (HAS_MEAN) pmu = mean[c * T + t + 1];
         }
         __syncwarp();
 
@@ -120,49 +145,58 @@ __global__ void __launch_bounds__(SY_WARPS * 32) k_sync_frame(const float *__res
                 for (int k = 0; k < M17B_FN; k++) { cmf[k] = __ldg(g_mf + index * M17B_FN + k); cmd[k] = __ldg(g_md + index * M17B_FN + k); }
                 tap_index = index;
             }
-            // speculate: lane l computes the symbol at sample j = i + 2l
-            const int j = i + 2 * lane;
-            const bool valid = j < 384;
-            float s = 0.0f, d = 0.0f;
-            if (valid) {
-                const float *A = (i & 1) ? sm.xo : sm.xe;
-                const float *B = (i & 1) ? sm.xe : sm.xo;
-                const int h = (i >> 1) + lane, ob = i & 1;
-                float x = A[h];
-                s = x * cmf[0];
-                d = x * cmd[0];
-#pragma unroll
-                for (int k = 1; k < M17B_FN; k++) {
-                    x = (k & 1) ? B[h + (k >> 1) + ob] : A[h + (k >> 1)];
-                    s += x * cmf[k];
-                    d += x * cmd[k];
+            // speculate: lane l computes the symbols at samples ja = i + 4l and jb = ja + 2
+            const int ja = i + 4 * lane, jb = ja + 2;
+            const bool valid_a = ja < 384, valid_b = jb < 384;
+            float sa = 0.0f, da = 0.0f, sb = 0.0f, db = 0.0f;
+            if (valid_a) {
+                const int base = (i >> 2) + lane;
+                switch (i & 3) {
+                    case 0: dot2<0>(sm.x, base, cmf, cmd, sa, da, sb, db); break;
+                    case 1: dot2<1>(sm.x, base, cmf, cmd, sa, da, sb, db); break;
+                    case 2: dot2<2>(sm.x, base, cmf, cmd, sa, da, sb, db); break;
+                    default: dot2<3>(sm.x, base, cmf, cmd, sa, da, sb, db); break;
                 }
             }
-            const bool has_vote = valid && (j + 1 < 384);
-            int v = 0;
-            if (has_vote) { float dd = (s < 0) ? -d : d; v = (dd > 0) - (dd < 0); }
-            const int th = thr + warp_incl_scan(v, lane);
-            const unsigned trig = __ballot_sync(0xffffffffu, has_vote && (th > TH || th < -TH));
-            if (trig == 0) {
-                const int nv = __popc(__ballot_sync(0xffffffffu, valid));
-                if (valid && m_idx + lane >= 0) out[m_idx + lane] = s;
+            // votes happen on the sample after each symbol (sync_update, m17_rx_sync.cpp:38-42) if it is in this block
+            const bool vote_a = valid_a && (ja + 1 < 384), vote_b = valid_b && (jb + 1 < 384);
+            int va = 0, vb = 0;
+            if (vote_a) { float dd = (sa < 0) ? -da : da; va = (dd > 0) - (dd < 0); }
+            if (vote_b) { float dd = (sb < 0) ? -db : db; vb = (dd > 0) - (dd < 0); }
+            const int incl = warp_incl_scan(va + vb, lane);
+            const int th_b = thr + incl, th_a = th_b - vb;
+            const unsigned ta = __ballot_sync(0xffffffffu, vote_a && (th_a > TH || th_a < -TH));
+            const unsigned tb = __ballot_sync(0xffffffffu, vote_b && (th_b > TH || th_b < -TH));
+            const int pa = ta ? 2 * (__ffs(ta) - 1) : 1 << 20, pb = tb ? 2 * (__ffs(tb) - 1) + 1 : 1 << 20;
+            const int P = pa < pb ? pa : pb;                                  // first symbol (in stream order) whose vote trips
+            if (P >= (1 << 20)) {
+                const int nv = __popc(__ballot_sync(0xffffffffu, valid_a)) + __popc(__ballot_sync(0xffffffffu, valid_b));
+                if (valid_a && m_idx + 2 * lane >= 0) out[m_idx + 2 * lane] = sa;
+                if (valid_b && m_idx + 2 * lane + 1 >= 0) out[m_idx + 2 * lane + 1] = sb;
                 m_idx += nv;
-                thr = __shfl_sync(0xffffffffu, th, 31);
-                sumc = __shfl_sync(0xffffffffu, s, nv - 1);
-                difc = __shfl_sync(0xffffffffu, d, nv - 1);
+                thr = __shfl_sync(0xffffffffu, th_b, 31);
+                const int L = (nv - 1) >> 1;
+                const float s0 = __shfl_sync(0xffffffffu, sa, L), s1 = __shfl_sync(0xffffffffu, sb, L);
+                const float d0 = __shfl_sync(0xffffffffu, da, L), d1 = __shfl_sync(0xffffffffu, db, L);
+                sumc = ((nv - 1) & 1) ? s1 : s0;
+                difc = ((nv - 1) & 1) ? d1 : d0;
                 const int last_j = i + 2 * (nv - 1);
                 if (last_j + 1 < 384) { i = last_j + 2; clk = 0; } else { i = 384; clk = 1; }
             } else {
-                const int l = __ffs(trig) - 1;
-                if (lane <= l && m_idx + lane >= 0) out[m_idx + lane] = s;
-                m_idx += l + 1;
-                thr = __shfl_sync(0xffffffffu, th, l);
-                sumc = __shfl_sync(0xffffffffu, s, l);
-                difc = __shfl_sync(0xffffffffu, d, l);
+                const int L = P >> 1;
+                if (2 * lane <= P && m_idx + 2 * lane >= 0) out[m_idx + 2 * lane] = sa;
+                if (2 * lane + 1 <= P && m_idx + 2 * lane + 1 >= 0) out[m_idx + 2 * lane + 1] = sb;
+                m_idx += P + 1;
+                const int t0 = __shfl_sync(0xffffffffu, th_a, L), t1 = __shfl_sync(0xffffffffu, th_b, L);
+                const float s0 = __shfl_sync(0xffffffffu, sa, L), s1 = __shfl_sync(0xffffffffu, sb, L);
+                const float d0 = __shfl_sync(0xffffffffu, da, L), d1 = __shfl_sync(0xffffffffu, db, L);
+                thr = (P & 1) ? t1 : t0;
+                sumc = (P & 1) ? s1 : s0;
+                difc = (P & 1) ? d1 : d0;
                 clk = 0;
                 __syncwarp();
                 sync_adjust(TH, thr, index, clk, m_idx, out, lane);
-                i = i + 2 * l + 2;
+                i = i + 2 * P + 2;
             }
         }
         const int n = m_idx < 0 ? 0 : m_idx;
@@ -243,19 +277,19 @@ __global__ void __launch_bounds__(SY_WARPS * 32) k_sync_frame(const float *__res
         }
         // ---- carry: sliding window = last 8 symbols (zeros before a reset), filter history = last 30 samples
         {
-            float wv = 0.0f, a = 0.0f, b = 0.0f;
+            float wv = 0.0f, a = 0.0f;
             if (lane < 8) { int idx = n - 8 + lane; wv = (idx >= reset_at) ? sm.hist[8 + idx] : 0.0f; }
-            if (lane < 15) { a = sm.xe[192 + lane]; b = sm.xo[192 + lane]; }
+            if (lane < 30) a = sm.x[lane & 3][96 + (lane >> 2)];            // sample 384 + lane -> slot lane
             __syncwarp();
             if (lane < 8) sm.hist[lane] = wv;
-            if (lane < 15) { sm.xe[lane] = a; sm.xo[lane] = b; }
+            if (lane < 30) sm.x[lane & 3][lane >> 2] = a;
         }
         sym_total += n;
         __syncwarp();
     }
 
     // ---- store state
-    if (lane < 30) S->tail[lane] = ((lane & 1) ? sm.xo : sm.xe)[lane >> 1];
+    if (lane < 30) S->tail[lane] = sm.x[lane & 3][lane >> 2];
     if (lane < 8) { S->win[lane] = sm.hist[lane]; S->head[lane] = sm.head[lane]; }
     if (lane == 0) {
         S->clk = clk; S->thr = thr; S->index = index; S->sum = sumc; S->dif = difc;

@@ -377,7 +377,15 @@ def eq_oracle(P, pairs, train, nknown):
     return y
 
 
+def check_frontend_math(ctx, P, count=1 << 32):
+    """fast limiter arithmetic == reference formulation for EVERY possible int16 IQ sample (proof by enumeration)"""
+    bad = ctx.selftest_frontend(0, count)
+    assert bad == 0, f"{bad} of {count} IQ samples differ between the fast and the IEEE limiter path; first (raw, m_fast, m_ieee, g_fast, g_ieee): {[[hex(int(x)) for x in r] for r in ctx.last_selftest_dump[:8]]}"
+    return f"frontend math ok ({count} samples enumerated)"
+
+
 CHECKS = [
+    ("frontend_math", lambda c, P: check_frontend_math(c, P)),
     ("primitives", lambda c, P: check_primitives(c, P)),
     ("viterbi", lambda c, P: check_viterbi(c, P)),
     ("parse_frames", lambda c, P: check_parse_frames(c, P)),
