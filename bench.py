@@ -42,6 +42,13 @@ def clean_env():
     return {k: v for k, v in os.environ.items() if not k.startswith(bad)}
 
 
+def under_profiler():
+    """true when a CUDA profiler (ncu) injected itself: helper subprocesses are then skipped altogether -- a number printed
+    under a profiler is never a bench value, and ncu on this pool crashes when the traced process forks helpers"""
+    bad = ("CUDA_INJECTION", "NV_COMPUTE_PROFILER", "NV_NSIGHT", "NSIGHT", "NVTX_INJECTION")
+    return any(k.startswith(bad) for k in os.environ)
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -55,6 +62,8 @@ class ClockSampler:
         self.rows, self.proc, self.idx = [], None, gpu_index
 
     def start(self):
+        if under_profiler():
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=clean_env())
@@ -348,7 +357,7 @@ def run_cuda(args):
     achieved = STAGE_BYTES[dom] * C * T / (stage[dom] * 1e-3) / 1e9
     # bounded CPU baseline on the same IQ (rank 0 only)
     S = min(C, max(2 * (os.cpu_count() or 1), 16))
-    cb = cpu_baseline(iq_host[:S].numpy(), T)
+    cb = cpu_baseline(iq_host[:S].numpy(), T) if not under_profiler() else {"value": None, "unit": UNIT, "cores": 0, "kind": "skipped under profiler", "sample": ""}
     gpu_deliv_sample = int(sum(int((((res["frames"][c, :nfr[c]]["flags"] & 8) != 0) & (res["frames"][c, :nfr[c]]["type"] == 2)).sum()) for c in range(S)))
     if "delivered" in cb:
         cb["check"] = f"delivered stream frames on the sample: reference {cb.pop('delivered')} vs CUDA {gpu_deliv_sample}"
