@@ -1,0 +1,76 @@
+// shim_loopback.cpp -- the reference's own call sequence, unchanged names, running on the GPU through
+// include/m17gismo_b200.hpp: init chain (main.cpp:108-126), one "over" sent with m17_send_* (m17_tx_rx.cpp:95-115),
+// the transmitted IQ looped straight back into m17_dsp_rx block by block (what m17_test.cpp:42-52 does at baseband),
+// plus the known-answer values of SURVEY.md section 4 on the primitive entry points.
+#define M17GISMO_B200_IMPLEMENTATION
+#include "m17gismo_b200.hpp"
+#include <stdio.h>
+#include <vector>
+
+static std::vector<scmplx> g_iq;
+static std::vector<m17b_frame_rec> g_frames;
+static int g_aos = 0, g_los = 0, g_fail = 0;
+static void on_tx(const scmplx *iq, uint32_t n, void *) { g_iq.insert(g_iq.end(), iq, iq + n); }
+static void on_frame(const m17b_frame_rec *r, void *) { g_frames.push_back(*r); }
+static void on_event(const m17b_event_rec *e, void *) { if (e->kind == M17B_EV_AOS) g_aos++; else g_los++; }
+#define EXPECT(c) do { if (!(c)) { printf("FAIL line %d: %s\n", __LINE__, #c); g_fail++; } } while (0)
+
+int main() {
+    m17b_shim_callbacks cb = {on_frame, on_event, on_tx, nullptr};
+    m17b_shim_set_callbacks(&cb);
+    m17_prbs9_init(); m17_crc_init(); m17_init_conv(); m17_init_de_correlate(); m17_dsp_init(); m17_fmt_init();
+    m17_golay_init(); m17_rx_sync_init(); m17_mod_init();
+    if (m17b_shim_last_error()) { printf("init failed: %d (%s)\n", m17b_shim_last_error(), m17b_last_cuda_error()); return 2; }
+
+    // ---- known answers
+    uint8_t msg[] = "123456789";
+    EXPECT(m17_crc_array_encode(msg, 9) == 0x772B);
+    uint8_t a1[] = "A";
+    EXPECT(m17_crc_array_encode(a1, 1) == 0x206E);
+    EXPECT(m17_golay_encode(0xABC) == 0xABC23C && m17_golay_encode(0x001) == 0x0018EB);
+    uint12_t od = 0;
+    EXPECT(m_17_golay_decode(0xABC23C ^ 0x111000, od) == 3 && od == 0xABC);
+    EXPECT(m_17_golay_decode(0xABC23C ^ 0x00F000, od) == 4 && od == 0x0F3);
+    uint8_t bits8[8] = {1, 0, 1, 1, 0, 0, 1, 0}, coded[64];
+    EXPECT(m17_conv_encode_1(bits8, coded, 8) == 24);
+    const char *kat = "110110001111101001101100";
+    for (int i = 0; i < 24; i++) EXPECT(coded[i] == kat[i] - '0');
+    float zeros[296] = {0}; uint8_t vb[148];
+    EXPECT(m17_viterbi_decode(zeros, vb, 296) == 148);
+    int ones = 0; for (int i = 0; i < 148; i++) ones += vb[i];
+    EXPECT(ones == 144 && vb[0] == 0 && vb[1] == 1 && vb[147] == 0);
+    uint8_t perm[368], back[368], src[368];
+    for (int i = 0; i < 368; i++) src[i] = (uint8_t)(i * 7);
+    m17_interleave(src, perm, 368); m17_interleave(perm, back, 368);
+    for (int i = 0; i < 368; i++) EXPECT(back[i] == src[i]);                 // QPP is an involution
+    uint8_t prbs[16]; m17_prbs9_tx_reset(); m17_prbs9_tx_load(prbs, 16);
+    const char *pk = "0000100011000010";
+    for (int i = 0; i < 16; i++) EXPECT(prbs[i] == pk[i] - '0');
+
+    // ---- one over, looped back
+    const int F = 14;
+    uint8_t meta[14] = {0}, payload[F][16];
+    M17Type ty = {1, 2, 0, 0, 0, 0};                                         // stream, voice -> TYPE 0x0005
+    EXPECT(m17_pack_type(ty) == 0x0005);
+    m17_send_carrier(); m17_send_preamble(); m17_send_preamble();
+    m17_send_link_setup_frame(0xFFFFFFFFFFFFull, 0x0000025EA29Full, ty, meta);
+    for (int f = 0; f < F; f++) { for (int i = 0; i < 16; i++) payload[f][i] = (uint8_t)(f * 16 + i); m17_send_stream_frame(payload[f]); }
+    m17_send_eot(); m17_send_carrier(); m17_send_carrier();
+    EXPECT(g_iq.size() == (size_t)(F + 7) * 1920);
+    for (size_t b = 0; b + 1920 <= g_iq.size(); b += 1920) m17_dsp_rx(&g_iq[b], 1920);
+    int stream = 0, delivered = 0, exact = 0, lsf_ok = 0;
+    for (auto &r : g_frames) {
+        if (r.type == M17B_T_LSF && r.crc == 0) lsf_ok++;
+        if (r.type != M17B_T_STREAM) continue;
+        stream++;
+        if (!(r.flags & M17B_F_DELIVERED)) continue;
+        delivered++;
+        int fn = (r.data[0] << 8) | r.data[1];
+        if (fn < F && !memcmp(r.data + 2, payload[fn], 16)) exact++;
+    }
+    EXPECT(g_aos == 1 && g_los == 1 && !m17_rx_lock());
+    EXPECT(lsf_ok == 1 && stream == F && delivered >= F - 6 && exact == delivered);
+    printf("{\"shim_loopback\": \"%s\", \"frames\": %zu, \"stream\": %d, \"delivered\": %d, \"exact\": %d, \"aos\": %d, \"los\": %d, \"err\": %d}\n",
+           g_fail ? "FAIL" : "PASS", g_frames.size(), stream, delivered, exact, g_aos, g_los, m17b_shim_last_error());
+    return g_fail || m17b_shim_last_error() ? 1 : 0;
+}

@@ -150,7 +150,7 @@ def test_full_size_properties(ctx):
         assert len(dl) >= 220, (c, len(dl))      # 244 sent; delivery starts once six LICH chunks have arrived
         late = np.nonzero(fn >= 12)[0]                       # the timing loop is still converging during the first frames
         assert all(np.array_equal(dl["data"][i, 2:18], pl[c, fn[i]]) for i in late), c
-        assert int((f["flags"] & 4 != 0).sum()) == 1 and f[-1]["type"] == 5          # one LOS, on the EOT frame
+        assert f[-1]["type"] == 5 and (f[-1]["flags"] & 4)                            # the over ends with LOS on the EOT frame
     rx.reset()
     rx.m17_dsp_rx(iq)
     b = rx.results()
@@ -173,3 +173,15 @@ def test_full_size_properties(ctx):
     for c in range(0, C, 53):
         assert np.array_equal(fh[c, : nh[c]].view(np.uint8), a["frames"][c, : a["nframes"][c]].view(np.uint8))
     rx.close()
+
+
+def test_cpp_host_programs():
+    """C++ host code above the C ABI (no Python in the loop): the batched loopback driver and the batch-1 shim that
+    carries the reference's original function names."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["bash", os.path.join(root, "tests", "cpp", "build.sh")], check=True)
+    out = subprocess.run([os.path.join(root, "tests", "cpp", "bin", "shim_loopback")], capture_output=True, text=True)
+    assert out.returncode == 0 and '"PASS"' in out.stdout, out.stdout + out.stderr
+    out = subprocess.run([os.path.join(root, "tests", "cpp", "bin", "rx_loopback"), "96", "30", "1"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
