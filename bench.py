@@ -207,7 +207,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    S = max(cores, 16)
+    S = min(512, 16 * cores)          # about 0.25 s of all-core work per step
     T = BLOCKS
     X = reference_input(S, T, 1234)
     ref_bin = os.path.join(ROOT, "oracle", "_ref", "m17ref_bench")

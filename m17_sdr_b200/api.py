@@ -415,3 +415,30 @@ class Equalizer:
         out = torch.empty((self.nchan, nsym), dtype=torch.float32, device=pairs.device)
         _l.check(self.L.m17b_eq_train(self.h, _ptr(pairs), _ptr(train), nsym, _ptr(out), _stream()))
         return out
+
+
+def reassemble_packets(ctx, frames, nframes):
+    """Packet-mode application layer done right (the reference's parse_packet cannot validate multi-frame packets,
+    SURVEY D4): walk one channel's records in order, concatenate the 25-byte chunks of non-final packet frames and the
+    `count` bytes of the EOF frame, and check the trailing CRC-16 with the GPU primitive.
+    frames: numpy structured array [cap] of one channel, nframes: its record count.
+    Returns a list of (payload_bytes_without_crc, crc_ok)."""
+    out, cur, done = [], b"", []
+    for r in frames[:nframes]:
+        if r["type"] != 3 or not (r["flags"] & 0x02):
+            continue
+        meta = int(r["data"][25])
+        if meta & 0x80:
+            cur += bytes(r["data"][: (meta >> 2) & 0x1F])
+            done.append(cur)
+            cur = b""
+        else:
+            cur += bytes(r["data"][:25])
+    for pkt in done:
+        if len(pkt) < 2:
+            out.append((pkt, False))
+            continue
+        t = torch.frombuffer(bytearray(pkt), dtype=torch.uint8).reshape(1, -1).to(ctx.device)
+        crc = int(ctx.m17_crc_array_encode(t).view(torch.int16).to(torch.int32).item()) & 0xFFFF
+        out.append((pkt[:-2], crc == 0))
+    return out

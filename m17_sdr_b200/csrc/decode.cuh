@@ -282,7 +282,8 @@ __global__ void k_set_i32(int32_t *p, int32_t v) { *p = v; }
 template <int NT, bool STREAM> static size_t decode_smem() { return (size_t)NT * 193 * 4 + (size_t)(STREAM ? 148 : 244) * NT * 2; }
 
 static int launch_decode(m17b_ctx *ctx, const float *syms, int64_t sym_pitch, int sym_carry, const int32_t *sym_base,
-                         m17b_frame_rec *frames, int64_t fcap, const int32_t *nframes, int64_t nchan, float *soft_out, cudaStream_t st) {
+                         m17b_frame_rec *frames, int64_t fcap, const int32_t *nframes, int64_t nchan, float *soft_out, cudaStream_t st,
+                         cudaStream_t aux = nullptr, cudaEvent_t ev_fork = nullptr, cudaEvent_t ev_join = nullptr) {
     const int tiles = (int)((fcap + DECODE_NT - 1) / DECODE_NT);
     static bool attr_set = false;
     if (!attr_set) {
@@ -292,11 +293,15 @@ static int launch_decode(m17b_ctx *ctx, const float *syms, int64_t sym_pitch, in
     }
     if ((int64_t)tiles * nchan > 0x7fffffffLL) return M17B_E_ARG;
     const unsigned grid = (unsigned)(tiles * nchan);
+    // the two kernels touch disjoint records: run the (rare, long, sparse) LSF/packet one beside the stream-frame one
+    cudaStream_t st2 = st;
+    if (aux) { CUDA_TRY(cudaEventRecord(ev_fork, st)); CUDA_TRY(cudaStreamWaitEvent(aux, ev_fork, 0)); st2 = aux; }
+    k_decode_frames<DECODE_NT, false><<<grid, DECODE_NT, decode_smem<DECODE_NT, false>(), st2>>>(syms, sym_pitch, sym_carry, sym_base, frames, fcap, nframes,
+                                                                                            tiles, soft_out, ctx->d_crc, ctx->d_genc, ctx->d_gerr);
     k_decode_frames<DECODE_NT, true><<<grid, DECODE_NT, decode_smem<DECODE_NT, true>(), st>>>(syms, sym_pitch, sym_carry, sym_base, frames, fcap, nframes,
                                                                                           tiles, soft_out, ctx->d_crc, ctx->d_genc, ctx->d_gerr);
-    k_decode_frames<DECODE_NT, false><<<grid, DECODE_NT, decode_smem<DECODE_NT, false>(), st>>>(syms, sym_pitch, sym_carry, sym_base, frames, fcap, nframes,
-                                                                                           tiles, soft_out, ctx->d_crc, ctx->d_genc, ctx->d_gerr);
     KERNEL_CHECK();
+    if (aux) { CUDA_TRY(cudaEventRecord(ev_join, aux)); CUDA_TRY(cudaStreamWaitEvent(st, ev_join, 0)); }
     return M17B_OK;
 }
 

@@ -24,7 +24,8 @@ struct m17b_rx {
     unsigned long long *d_stats;
     int16_t *d_iq_stage[2];           // staging for the _host entry point (double buffered over channel chunks)
     int64_t stage_chunk;
-    cudaStream_t copy_stream;
+    cudaStream_t copy_stream, aux_stream;   // aux: LSF/packet/BERT frame decode runs beside the stream-frame decode
+    cudaEvent_t ev_fork, ev_join;
     cudaEvent_t ev_h2d[2], ev_done[2];
     int afc, last_launches, seam_last;
     int timing;                       // record cudaEvents around each stage of the next calls (bench only)
@@ -141,6 +142,9 @@ extern "C" int m17b_rx_destroy(m17b_rx *rx) {
         if (rx->ev_done[i]) cudaEventDestroy(rx->ev_done[i]);
     }
     if (rx->copy_stream) cudaStreamDestroy(rx->copy_stream);
+    if (rx->aux_stream) cudaStreamDestroy(rx->aux_stream);
+    if (rx->ev_fork) cudaEventDestroy(rx->ev_fork);
+    if (rx->ev_join) cudaEventDestroy(rx->ev_join);
     for (int r = 0; r < M17B_TIMING_RING; r++) for (int i = 0; i < 5; i++) if (rx->ev_stage[r][i]) cudaEventDestroy(rx->ev_stage[r][i]);
     free(rx);
     return M17B_OK;
@@ -182,6 +186,9 @@ extern "C" int m17b_rx_create(m17b_ctx *ctx, int64_t nchan, int64_t max_blocks, 
     A((void **)&rx->d_events, sizeof(m17b_event_rec) * nchan * rx->ecap);
     A((void **)&rx->d_stats, sizeof(unsigned long long) * nchan * 8);
     if (e != cudaSuccess) { m17b_set_cuda_error(e, __FILE__, __LINE__); m17b_rx_destroy(rx); return e == cudaErrorMemoryAllocation ? M17B_E_NOMEM : M17B_E_CUDA; }
+    CUDA_TRY(cudaStreamCreateWithFlags(&rx->aux_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&rx->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&rx->ev_join, cudaEventDisableTiming));
     int rc = m17b_rx_reset(rx, nullptr);
     if (rc) { m17b_rx_destroy(rx); return rc; }
     CUDA_TRY(cudaStreamSynchronize(nullptr));
@@ -215,13 +222,14 @@ static int rx_back_half(m17b_rx *rx, int64_t c0, int64_t nc, const float *disc, 
                                                         rx->d_events + c0 * rx->ecap, rx->ecap, rx->d_nevents + c0, rx->d_stats + c0 * 8, commit_fe);
     KERNEL_CHECK();
     STAGE_MARK(2);
-    int rc = launch_decode(ctx, syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0, nc, nullptr, st);
+    int rc = launch_decode(ctx, syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0, nc, nullptr, st,
+                           rx->aux_stream, rx->ev_fork, rx->ev_join);
     if (rc) return rc;
     STAGE_MARK(3);
     k_post<<<grid_for(nc, POST_WARPS), POST_WARPS * 32, 0, st>>>(frames, rx->fcap, rx->d_nframes + c0, nc, rx->d_state + c0, ctx->d_crc, rx->d_stats + c0 * 8);
     KERNEL_CHECK();
     STAGE_MARK(4);
-    rx->last_launches += 3;
+    rx->last_launches += 4;       // sync/framer, two decode kernels, post
     return M17B_OK;
 }
 

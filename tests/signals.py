@@ -60,3 +60,46 @@ def baseband_channels(port, nchan, nframes, seed, ebn0_db):
     for c in range(nchan):
         D[c, : len(out[c])] = out[c]
     return D, pl
+
+
+def packet_frames(port, data):
+    """m17_send_packet_frames semantics (m17_tx_routines.cpp:323-353): append CRC-16, split in 25-byte chunks,
+    non-final frames carry their index, the final frame EOF + the number of bytes used (25 if the split is exact)."""
+    crc = port.crc(bytes(data))
+    buf = bytes(data) + bytes([crc >> 8, crc & 0xFF])
+    frames, left = len(buf) // 25, len(buf) % 25
+    out = []
+    if left == 0:
+        for i in range(frames - 1):
+            out.append(port.fmt_packet(buf[i * 25:(i + 1) * 25], 0, i))
+        out.append(port.fmt_packet(buf[(frames - 1) * 25:], 1, 25))
+    else:
+        for i in range(frames):
+            out.append(port.fmt_packet(buf[i * 25:(i + 1) * 25], 0, i))
+        out.append(port.fmt_packet(buf[frames * 25:], 1, left))
+    return out
+
+
+def packet_channels(port, nchan, seed, ebn0=None, f0_max=1000.0, max_len=200):
+    """Config-3 style: preamble x2, LSF (TYPE 0x0002 packet/data), one packet of 1..max_len bytes, EOT; carrier
+    offset; fractional timing offset by modulating at os=80 and decimating by 8 from a random phase; integer delay.
+    Returns (iq int16 [C][T*1920][2], list of packet payloads)."""
+    rng = np.random.default_rng(seed)
+    chans, packets = [], []
+    for c in range(nchan):
+        data = bytes(rng.integers(0, 256, int(rng.integers(1, max_len + 1)), dtype=np.uint8))
+        packets.append(data)
+        lsf = port.build_lsf(0xFFFFFFFFFFFF, port.encode_call("G4GUO    "), 0x0002)
+        script = np.concatenate([np.full(192, 4, np.uint8), port.fmt_preamble(), port.fmt_preamble(), port.fmt_lsf(lsf)] +
+                                packet_frames(port, data) + [port.fmt_eot(), np.full(384, 4, np.uint8)])
+        iq80 = port.mod(script, 80)
+        chans.append(iq80[int(rng.integers(0, 8))::8][: len(script) * 10])
+    n = max(len(x) for x in chans)
+    T = (n + BLOCK - 1) // BLOCK + 2
+    X = np.zeros((nchan, T * BLOCK, 2), np.int16)
+    for c in range(nchan):
+        x = delay_iq(chans[c], int(rng.integers(0, BLOCK)), T * BLOCK)
+        e = ebn0[c] if isinstance(ebn0, (list, tuple, np.ndarray)) else ebn0
+        x = add_iq_noise(x, e, rng)
+        X[c] = rotate_iq(x, float(rng.uniform(-f0_max, f0_max)))
+    return X, packets

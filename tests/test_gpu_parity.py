@@ -45,6 +45,10 @@ def test_rx_chain_state_carry_across_calls(ctx, port):
     gc.check_rx_baseband(ctx, port, nchan=6, seed=24, split=[3, 1, 1, 9])
 
 
+def test_rx_packet_mode_offsets(ctx, port):
+    gc.check_rx_packet(ctx, port)
+
+
 def test_tx(ctx, port):
     gc.check_tx(ctx, port)
     gc.check_tx(ctx, port, nchan=2, F=4, os_=80)
