@@ -47,6 +47,7 @@ struct __align__(16) GatherMaps {
 };
 // TX-side maps: for final (interleaved, randomised) bit i of a frame -> which type-3 bit feeds it
 // (QPP is an involution) and, per type-3 bit, which coded (pre-puncture) position it is.
+struct __align__(16) PunctSteps { uint8_t keep[3][244]; };   // per trellis step: bit0/bit1 = first/second coded bit survives P1/P2/P3
 struct __align__(16) TxMaps {
     uint16_t qpp[368];   // pi(i) = (45 i + 92 i^2) mod 368          m17_interleave.cpp:5
     uint8_t  rnd[368];   // randomiser bits, MSB first               m17_correlate.cpp:35-42

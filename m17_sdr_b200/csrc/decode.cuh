@@ -34,26 +34,28 @@ __device__ __forceinline__ float acs_select(float a, float b, unsigned &dec, uns
     return r;
 }
 template <int V> struct Acs {
-    __device__ __forceinline__ static void run(const float (&acm)[16], float (&tm)[16], float m0, float m1, float m2, float m3, unsigned &dec) {
+    // the decision bits are collected in four independent accumulators (V & 3) so that the predicated ORs do not form
+    // one 16-long dependency chain per step
+    __device__ __forceinline__ static void run(const float (&acm)[16], float (&tm)[16], float m0, float m1, float m2, float m3, unsigned (&dec)[4]) {
         constexpr int w = (2 * V) & 15, y = w + 1, hi = (V >> 3) << 4;
         constexpr int x = conv_sym(hi | w), z = conv_sym(hi | y);
         const float a = acm[w] + pick4<x>(m0, m1, m2, m3);
         const float b = acm[y] + pick4<z>(m0, m1, m2, m3);
-        tm[V] = acs_select(a, b, dec, 1u << V);
+        tm[V] = acs_select(a, b, dec[V & 3], 1u << V);
         Acs<V + 1>::run(acm, tm, m0, m1, m2, m3, dec);
     }
 };
 template <> struct Acs<16> {
-    __device__ __forceinline__ static void run(const float (&)[16], float (&)[16], float, float, float, float, unsigned &) {}
+    __device__ __forceinline__ static void run(const float (&)[16], float (&)[16], float, float, float, float, unsigned (&)[4]) {}
 };
 // one trellis step from metrics `from` into `to` (ping-pong, so no register copies); returns the 16 decisions
 __device__ __forceinline__ unsigned viterbi_step_pp(const float (&from)[16], float (&to)[16], float s1, float s2) {
     // branch metrics: correlation of (+-s1, +-s2) with the expected pair, each a single rounded add
     const float n1 = -s1, n2 = -s2;
     const float m0 = n1 + n2, m1 = n1 + s2, m2 = s1 + n2, m3 = s1 + s2;
-    unsigned dec = 0;
+    unsigned dec[4] = {0, 0, 0, 0};
     Acs<0>::run(from, to, m0, m1, m2, m3, dec);
-    return dec;
+    return (dec[0] | dec[1]) | (dec[2] | dec[3]);
 }
 __device__ __forceinline__ unsigned viterbi_step(float (&acm)[16], float s1, float s2) {
     float tm[16];
@@ -137,22 +139,36 @@ __device__ __forceinline__ void decode_conv(const float *row, uint16_t *dec, int
     float ma[16], mb[16];
     viterbi_init(ma);
     static_assert(F::STEPS % 2 == 0, "two steps per iteration");
+    // software pipeline: the four soft values of the NEXT two steps are gathered (constant-memory map -> smem -> demap)
+    // while the 32 butterflies of the current two steps issue
+    uint2 e = *(const uint2 *)map;                                          // four uint16 entries, warp-uniform
+    float s1 = gather_soft(row, e.x & 0xFFFFu), s2 = gather_soft(row, e.x >> 16);
+    float s3 = gather_soft(row, e.y & 0xFFFFu), s4 = gather_soft(row, e.y >> 16);
     for (int t = 0; t < F::STEPS; t += 2) {
-        const uint2 e = *(const uint2 *)(map + 2 * t);                      // four uint16 entries, warp-uniform
-        const float s1 = gather_soft(row, e.x & 0xFFFFu), s2 = gather_soft(row, e.x >> 16);
-        const float s3 = gather_soft(row, e.y & 0xFFFFu), s4 = gather_soft(row, e.y >> 16);
+        float n1 = 0.f, n2 = 0.f, n3 = 0.f, n4 = 0.f;
+        if (t + 2 < F::STEPS) {
+            e = *(const uint2 *)(map + 2 * t + 4);
+            n1 = gather_soft(row, e.x & 0xFFFFu); n2 = gather_soft(row, e.x >> 16);
+            n3 = gather_soft(row, e.y & 0xFFFFu); n4 = gather_soft(row, e.y >> 16);
+        }
         dec[t * NT + tid] = (uint16_t)viterbi_step_pp(ma, mb, s1, s2);
         dec[(t + 1) * NT + tid] = (uint16_t)viterbi_step_pp(mb, ma, s3, s4);
+        s1 = n1; s2 = n2; s3 = n3; s4 = n4;
     }
     // traceback from state 0; out[t] = MSB of the state at step t = input bit t-1.  Callers discard out[0] and pack
     // out[1..8*NBYTES] MSB first (pack_1_to_8(&bits[1],...), m17_rx_parse.cpp:97,142,171).
-    unsigned s = 0, acc = 0;
-    for (int t = F::STEPS - 1; t >= 1; t--) {
-        s = trace_prev(s, dec[t * NT + tid]);
-        if (t <= 8 * F::NBYTES) {
-            acc |= ((s >> 3) & 1u) << ((8 - t) & 7);                        // t = 8j+8 is bit 0 of byte j ... t = 8j+1 is bit 7
-            if ((t & 7) == 1) { obytes[(t - 1) >> 3] = (uint8_t)acc; acc = 0; }
-        }
+    // The survivor words do not depend on the state, so they are fetched eight steps at a time; only the 3-op state
+    // update is serial.
+    unsigned s = 0;
+    static_assert(F::STEPS - 1 >= 8 * F::NBYTES && (F::STEPS - 1 - 8 * F::NBYTES) < 8, "tail shorter than a byte");
+    for (int t = F::STEPS - 1; t > 8 * F::NBYTES; t--) s = trace_prev(s, dec[t * NT + tid]);   // tail bits, discarded
+    for (int j = F::NBYTES - 1; j >= 0; j--) {
+        unsigned d[8], acc = 0;
+#pragma unroll
+        for (int b = 0; b < 8; b++) d[b] = dec[(8 * j + 8 - b) * NT + tid];                      // t = 8j+8 ... 8j+1
+#pragma unroll
+        for (int b = 0; b < 8; b++) { s = trace_prev(s, d[b]); acc |= ((s >> 3) & 1u) << b; }   // t = 8j+8 is bit 0 ... t = 8j+1 is bit 7
+        obytes[j] = (uint8_t)acc;
     }
 }
 
@@ -336,26 +352,40 @@ __global__ void __launch_bounds__(NT) k_viterbi_punct(const float *__restrict__ 
     __syncwarp();
     if (f >= n) return;
     const float *row = &rows[tid * PITCH];
-    float acm[16];
-    viterbi_init(acm);
+    float ma[16], mb[16];
+    viterbi_init(ma);
     int k = 0;
-    for (int t = 0; t < F::STEPS; t++) {
-        float s1 = d_punct_keeps(PAT, 2 * t) ? row[k++] : 0.0f;
-        float s2 = d_punct_keeps(PAT, 2 * t + 1) ? row[k++] : 0.0f;
-        dec[t * NT + tid] = (uint16_t)viterbi_step(acm, s1, s2);
+    static_assert(F::STEPS % 2 == 0, "two steps per iteration");
+    auto fetch = [&](int t, float &a1, float &a2, float &a3, float &a4) {
+        const unsigned k0 = c_punct.keep[PAT - 1][t], k1 = c_punct.keep[PAT - 1][t + 1];      // warp-uniform
+        a1 = (k0 & 1) ? row[k++] : 0.0f;
+        a2 = (k0 & 2) ? row[k++] : 0.0f;
+        a3 = (k1 & 1) ? row[k++] : 0.0f;
+        a4 = (k1 & 2) ? row[k++] : 0.0f;
+    };
+    float s1, s2, s3, s4;
+    fetch(0, s1, s2, s3, s4);
+    for (int t = 0; t < F::STEPS; t += 2) {                                 // next two steps' inputs load behind this pair's ACS
+        float n1 = 0.f, n2 = 0.f, n3 = 0.f, n4 = 0.f;
+        if (t + 2 < F::STEPS) fetch(t + 2, n1, n2, n3, n4);
+        dec[t * NT + tid] = (uint16_t)viterbi_step_pp(ma, mb, s1, s2);
+        dec[(t + 1) * NT + tid] = (uint16_t)viterbi_step_pp(mb, ma, s3, s4);
+        s1 = n1; s2 = n2; s3 = n3; s4 = n4;
     }
-    unsigned s = 0, acc = 0;
+    unsigned s = 0;
     uint8_t *o = bytes + f * F::NBYTES;
-    for (int t = F::STEPS - 1; t >= 1; t--) {
-        s = trace_prev(s, dec[t * NT + tid]);
-        if (t <= 8 * F::NBYTES) {
-            acc |= ((s >> 3) & 1u) << ((8 - t) & 7);
-            if ((t & 7) == 1) { o[(t - 1) >> 3] = (uint8_t)acc; acc = 0; }
-        }
+    for (int t = F::STEPS - 1; t > 8 * F::NBYTES; t--) s = trace_prev(s, dec[t * NT + tid]);
+    for (int j = F::NBYTES - 1; j >= 0; j--) {
+        unsigned d[8], acc = 0;
+#pragma unroll
+        for (int b = 0; b < 8; b++) d[b] = dec[(8 * j + 8 - b) * NT + tid];
+#pragma unroll
+        for (int b = 0; b < 8; b++) { s = trace_prev(s, d[b]); acc |= ((s >> 3) & 1u) << b; }
+        o[j] = (uint8_t)acc;
     }
 }
 template <class F, int PAT, int NIN> static int launch_vp(const float *d_soft, int64_t n, uint8_t *d_bytes, cudaStream_t st) {
-    constexpr int NT = 64;
+    constexpr int NT = 32;      // one warp per CTA: the smem-limited number of resident warps is highest this way
     size_t smem = (((size_t)NT * (NIN + 1) * 4 + 15) & ~(size_t)15) + (size_t)F::STEPS * NT * 2;
     CUDA_TRY(cudaFuncSetAttribute(k_viterbi_punct<F, PAT, NIN, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_viterbi_punct<F, PAT, NIN, NT><<<grid_for(n, NT), NT, smem, st>>>(d_soft, n, d_bytes);

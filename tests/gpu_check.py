@@ -312,7 +312,7 @@ def check_rx_packet(ctx, P, nchan=12, seed=25, verbose=False):
             if r["type"] == 3 and r["flags"] & 2:
                 m = int(r["data"][25])
                 if m & 0x80:
-                    buf += bytes(r["data"][: (m >> 2) & 31]); exp.append((buf[:-2], len(buf) >= 2 and P.crc(buf) == 0)); buf = b""
+                    buf += bytes(r["data"][: (m >> 2) & 31]); exp.append((buf[:-2], P.crc(buf) == 0) if len(buf) >= 2 else (buf, False)); buf = b""
                 else:
                     buf += bytes(r["data"][:25])
         assert got == exp, (c, got, exp)
