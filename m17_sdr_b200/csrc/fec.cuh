@@ -256,7 +256,18 @@ extern "C" int m17b_demap_frame(m17b_ctx *ctx, const float *d_sym, int64_t n, fl
 
 // ---------------------------------------------------------------- sync-word correlator (m17_rx_frame.cpp:22-81)
 struct SyncResult { int type, votes; float variance; };
-__device__ __forceinline__ float tpl_mul(float v, unsigned mask, int i) { return ((mask >> i) & 1u) ? -v : v; }   // v * (+-1.0f), exact
+// sync templates as sign masks, bit i set = template[i] is -1 (m17_rx_frame.cpp:5-12): preamble, LSF 0x55F7, stream 0xFF5D,
+// packet 0x75FF, BERT 0xDF55, EOT 0x555D.  Compile-time so the six correlations are plain add/subtract chains.
+__host__ __device__ constexpr unsigned sync_neg_mask(int t) {
+    return t == 0 ? 0xAAu : t == 1 ? 0xB0u : t == 2 ? 0x4Fu : t == 3 ? 0xF2u : t == 4 ? 0x0Du : 0x40u;
+}
+template <int T_> __device__ __forceinline__ float sync_corr(const float *v) {
+    constexpr unsigned m = sync_neg_mask(T_);
+    float s = (m & 1u) ? -v[0] : v[0];                                       // vect[0]*sframe[t][0], exact
+#pragma unroll
+    for (int i = 1; i < 8; i++) s = ((m >> i) & 1u) ? s - v[i] : s + v[i];   // sums[t] += vect[i]*sframe[t][i]  (a + (-b) == a - b)
+    return s;
+}
 __device__ __forceinline__ SyncResult sync_check8(const float *v) {
     SyncResult r;
     // find_variance: the 'else' means a sample that raises the max is never tested against the min
@@ -269,19 +280,18 @@ __device__ __forceinline__ SyncResult sync_check8(const float *v) {
     // six 8-term correlations, sequential adds; arg-max with strict '>' starting from (0, type 0)
     float best = 0;
     int type = 0;
-#pragma unroll
-    for (int t = 0; t < 6; t++) {
-        unsigned m = c_sync_neg[t];
-        float s = tpl_mul(v[0], m, 0);
-#pragma unroll
-        for (int i = 1; i < 8; i++) s += tpl_mul(v[i], m, i);
-        if (s > best) { best = s; type = t; }
-    }
+    { const float s = sync_corr<0>(v); if (s > best) { best = s; type = 0; } }
+    { const float s = sync_corr<1>(v); if (s > best) { best = s; type = 1; } }
+    { const float s = sync_corr<2>(v); if (s > best) { best = s; type = 2; } }
+    { const float s = sync_corr<3>(v); if (s > best) { best = s; type = 3; } }
+    { const float s = sync_corr<4>(v); if (s > best) { best = s; type = 4; } }
+    { const float s = sync_corr<5>(v); if (s > best) { best = s; type = 5; } }
     r.type = type;
-    unsigned m = c_sync_neg[type];
+    // votes: vect[i]*sframe[type][i] < 0  <=>  v[i] < 0 where the template is +1, v[i] > 0 where it is -1
+    const unsigned m = (unsigned)((0x400DF24FB0AAull >> (8 * type)) & 0xFFu);
     int votes = 0;
 #pragma unroll
-    for (int i = 0; i < 8; i++) votes += (tpl_mul(v[i], m, i) < 0) ? 1 : 0;
+    for (int i = 0; i < 8; i++) votes += (((m >> i) & 1u) ? (v[i] > 0) : (v[i] < 0)) ? 1 : 0;
     r.votes = votes;
     return r;
 }

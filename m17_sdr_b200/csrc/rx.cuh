@@ -8,7 +8,7 @@
 //   k_decode_frames (thread per frame)                            -> decoded bytes, Golay, CRC into the records
 //   k_post          (thread per channel, frames in order)         -> LICH cache, delivery / LSF-event flags, stats
 #pragma once
-#include "sync.cuh"
+#include "sync_cta.cuh"
 
 #define M17B_TIMING_RING 64
 struct m17b_rx {
@@ -28,6 +28,7 @@ struct m17b_rx {
     cudaEvent_t ev_fork, ev_join;
     cudaEvent_t ev_h2d[2], ev_done[2];
     int afc, last_launches, seam_last;
+    int sync_impl;                    // -1 auto; 0: warp per channel (sync.cuh); 2 / 4: CTA of that many warps per channel (sync_cta.cuh)
     int timing;                       // record cudaEvents around each stage of the next calls (bench only)
     cudaEvent_t ev_stage[M17B_TIMING_RING][5];
     int64_t tcount;                   // calls made since timing was enabled
@@ -169,6 +170,8 @@ extern "C" int m17b_rx_create(m17b_ctx *ctx, int64_t nchan, int64_t max_blocks, 
     m17b_rx *rx = (m17b_rx *)calloc(1, sizeof(m17b_rx));
     if (!rx) return M17B_E_NOMEM;
     rx->ctx = ctx; rx->nchan = nchan; rx->max_blocks = max_blocks;
+    rx->sync_impl = -1;                // auto: few channels per launch -> 4 warps per channel (latency), many -> 1 warp per channel (fewest instructions)
+    if (const char *e = getenv("M17B_SYNC_IMPL")) rx->sync_impl = atoi(e);     // tuning knob: 0 = one warp per channel, 2 / 4 = warps per channel
     rx->sym_pitch = (M17B_SYM_CARRY + max_blocks * M17B_SYM_CAP_PER_BLOCK + 3) & ~(int64_t)3;
     rx->fcap = max_blocks + max_blocks / 64 + 4;
     rx->ecap = 2 * rx->fcap + 4;
@@ -209,17 +212,23 @@ extern "C" int m17b_rx_set_afc(m17b_rx *rx, int on) {
 static int rx_back_half(m17b_rx *rx, int64_t c0, int64_t nc, const float *disc, const float *mean, int64_t T, int commit_fe, cudaStream_t st) {
     m17b_ctx *ctx = rx->ctx;
     STAGE_MARK(1);
-    const unsigned g = grid_for(nc, SY_WARPS);
     float *syms = rx->d_syms + c0 * rx->sym_pitch;
     m17b_frame_rec *frames = rx->d_frames + c0 * rx->fcap;
-    if (mean)
-        k_sync_frame<true><<<g, SY_WARPS * 32, 0, st>>>(disc, mean, nc, T, rx->d_state + c0, ctx->d_mf, ctx->d_md, syms, rx->sym_pitch,
-                                                       rx->d_nsym + c0 * T, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0,
-                                                       rx->d_events + c0 * rx->ecap, rx->ecap, rx->d_nevents + c0, rx->d_stats + c0 * 8, commit_fe);
-    else
-        k_sync_frame<false><<<g, SY_WARPS * 32, 0, st>>>(disc, nullptr, nc, T, rx->d_state + c0, ctx->d_mf, ctx->d_md, syms, rx->sym_pitch,
-                                                        rx->d_nsym + c0 * T, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0,
-                                                        rx->d_events + c0 * rx->ecap, rx->ecap, rx->d_nevents + c0, rx->d_stats + c0 * 8, commit_fe);
+#define SYNC_ARGS disc, mean, nc, T, rx->d_state + c0, ctx->d_mf, ctx->d_md, syms, rx->sym_pitch, rx->d_nsym + c0 * T, rx->d_sym_base + c0, frames, rx->fcap, \
+                  rx->d_nframes + c0, rx->d_events + c0 * rx->ecap, rx->ecap, rx->d_nevents + c0, rx->d_stats + c0 * 8, commit_fe
+    const int impl = rx->sync_impl >= 0 ? rx->sync_impl : (nc <= 256 ? 4 : 0);
+    if (impl == 4) {
+        if (mean) k_sync_frame_cta<4, true><<<(unsigned)nc, 128, 0, st>>>(SYNC_ARGS);
+        else      k_sync_frame_cta<4, false><<<(unsigned)nc, 128, 0, st>>>(SYNC_ARGS);
+    } else if (impl == 2) {
+        if (mean) k_sync_frame_cta<2, true><<<(unsigned)nc, 64, 0, st>>>(SYNC_ARGS);
+        else      k_sync_frame_cta<2, false><<<(unsigned)nc, 64, 0, st>>>(SYNC_ARGS);
+    } else {
+        const unsigned g = grid_for(nc, SY_WARPS);
+        if (mean) k_sync_frame<true><<<g, SY_WARPS * 32, 0, st>>>(SYNC_ARGS);
+        else      k_sync_frame<false><<<g, SY_WARPS * 32, 0, st>>>(SYNC_ARGS);
+    }
+#undef SYNC_ARGS
     KERNEL_CHECK();
     STAGE_MARK(2);
     int rc = launch_decode(ctx, syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0, nc, nullptr, st,
