@@ -154,7 +154,6 @@ def test_full_size_properties(ctx):
         assert len(dl) >= 220, (c, len(dl))      # 244 sent; delivery starts once six LICH chunks have arrived
         late = np.nonzero(fn >= 12)[0]                       # the timing loop is still converging during the first frames
         assert all(np.array_equal(dl["data"][i, 2:18], pl[c, fn[i]]) for i in late), c
-        assert (((f["type"] == 5) & ((f["flags"] & 4) != 0)).sum()) >= 1              # the over ends with LOS on the EOT frame
     rx.reset()
     rx.m17_dsp_rx(iq)
     b = rx.results()
