@@ -8,7 +8,7 @@
 // crosses a block boundary, so every (channel, block) item is independent.  The only serial work inside an
 // item is the fp32 running sum, whose order must be kept for bit-exactness, hence:
 //   mapping: one LANE per item, one warp per 32 items.  Each lane streams its own 7680-byte row with 16-byte
-//   loads (software-pipelined one 20-sample chunk ahead; the 32-byte sectors are fully consumed through L1), and
+//   loads (two alternating register buffers, one 20-sample chunk ahead; 32-byte sectors fully consumed through L1), and
 //   walks it sequentially with the discriminator history in registers.  Because 20 = lcm(4 samples per load,
 //   5 = decimation), the kept sample of every group of five sits at a lane-constant position: no counters.
 //   Kept outputs collect in a [32][33] shared tile that is flushed with coalesced 128-byte row stores every
@@ -42,10 +42,9 @@ __device__ __forceinline__ LimSample fe_limit_ieee(uint32_t raw, float *mo = nul
 }
 
 __device__ __forceinline__ LimSample fe_limit(uint32_t raw, float *mo = nullptr, float *go = nullptr) {
-    // int16 -> float without the conversion pipe: (x + 32768) planted in the mantissa of 2^23
-    const float bias = 8388608.0f + 32768.0f;
-    const float xr = __uint_as_float(((raw & 0xFFFFu) ^ 0x8000u) | 0x4B000000u) - bias;
-    const float xi = __uint_as_float(((raw >> 16) ^ 0x8000u) | 0x4B000000u) - bias;
+    // int16 -> float: one I2F.S16 per component, reading the half-register directly (exact)
+    const float xr = (float)(short)(raw & 0xFFFFu);
+    const float xi = (float)(short)(raw >> 16);
     constexpr float c_hi = 0.00003f;
     constexpr float c_lo = (float)(0.00003 - (double)0.00003f);
     const float re = __fmaf_rn(xr, c_hi, xr * c_lo);
@@ -103,35 +102,41 @@ __global__ void __launch_bounds__(FE_WARPS * 32) k_frontend(const uint32_t *__re
     }
     const int keep = 4 - count0;                                 // count = (count+1)%5 hits 0 at samples = keep (mod 5)
     float acc = 0.0f;                                            // sum of u; sum of u*0.5 == 0.5*sum (exact power-of-two scaling)
-    uint4 cur[5], nxt[5];
+    // 20 samples (five 16-byte loads) per chunk; two register buffers alternate so the next chunk's loads are in flight
+    // while the current one is processed, without register copies
+    auto process20 = [&](const uint4 (&w)[5], int slot) {
+        float u[20];
 #pragma unroll
-    for (int q = 0; q < 5; q++) cur[q] = __ldg(row + q);
+        for (int s = 0; s < 20; s++) {
+            const uint4 q = w[s >> 2];
+            const uint32_t raw = (s & 3) == 0 ? q.x : (s & 3) == 1 ? q.y : (s & 3) == 2 ? q.z : q.w;
+            const LimSample x = fe_limit(raw);
+            // dsp_arctan_disc2 (m17_dsp.cpp:203-212)
+            const float a = z0im * (x.re - z1re);
+            const float b = z0re * (x.im - z1im);
+            u[s] = b - a;
+            z1re = z0re; z1im = z0im; z0re = x.re; z0im = x.im;
+            acc += u[s];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            tout[wid][lane][slot * 4 + j] = sel5(u[5 * j], u[5 * j + 1], u[5 * j + 2], u[5 * j + 3], u[5 * j + 4], keep) * 0.5f;
+    };
+    uint4 bufa[5], bufb[5];
+#pragma unroll
+    for (int q = 0; q < 5; q++) bufa[q] = __ldg(row + q);
     for (int grp = 0; grp < 12; grp++) {
 #pragma unroll 1
-        for (int chk = 0; chk < 8; chk++) {
+        for (int chk = 0; chk < 8; chk += 2) {
             const int c20 = grp * 8 + chk;
-            if (c20 < 95) {
 #pragma unroll
-                for (int q = 0; q < 5; q++) nxt[q] = __ldg(row + (c20 + 1) * 5 + q);
+            for (int q = 0; q < 5; q++) bufb[q] = __ldg(row + (c20 + 1) * 5 + q);
+            process20(bufa, chk);
+            if (c20 + 2 < 96) {
+#pragma unroll
+                for (int q = 0; q < 5; q++) bufa[q] = __ldg(row + (c20 + 2) * 5 + q);
             }
-            float u[20];
-#pragma unroll
-            for (int s = 0; s < 20; s++) {
-                const uint4 w = cur[s >> 2];
-                const uint32_t raw = (s & 3) == 0 ? w.x : (s & 3) == 1 ? w.y : (s & 3) == 2 ? w.z : w.w;
-                const LimSample x = fe_limit(raw);
-                // dsp_arctan_disc2 (m17_dsp.cpp:203-212)
-                const float a = z0im * (x.re - z1re);
-                const float b = z0re * (x.im - z1im);
-                u[s] = b - a;
-                z1re = z0re; z1im = z0im; z0re = x.re; z0im = x.im;
-                acc += u[s];
-            }
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                tout[wid][lane][chk * 4 + j] = sel5(u[5 * j], u[5 * j + 1], u[5 * j + 2], u[5 * j + 3], u[5 * j + 4], keep) * 0.5f;
-#pragma unroll
-            for (int q = 0; q < 5; q++) cur[q] = nxt[q];
+            process20(bufb, chk + 1);
         }
         __syncwarp();
 #pragma unroll 4
