@@ -65,7 +65,7 @@ class ClockSampler:
         if under_profiler():
             return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=clean_env())
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -355,6 +355,14 @@ def run_cuda(args):
     stages = {k: {"ms": round(v, 4), "alg_bytes_per_frame": STAGE_BYTES[k], "gbs": round(STAGE_BYTES[k] * C * T / (v * 1e-3) / 1e9, 1) if v > 0 else None}
               for k, v in stage.items()}
     achieved = STAGE_BYTES[dom] * C * T / (stage[dom] * 1e-3) / 1e9
+    kname = {"frontend": "k_frontend", "sync_frame": "k_sync_frame", "decode": "k_decode_frames", "post": "k_post"}
+    traffic = None
+    try:                                       # dram__bytes_read+write per launch from the ncu --set full capture (profiles/)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if (C, T) == (CHANNELS_PER_GPU, BLOCKS):
+            traffic = tj.get(kname[dom])
+    except (OSError, ValueError):
+        pass
     # bounded CPU baseline on the same IQ (rank 0 only)
     S = min(C, max(2 * (os.cpu_count() or 1), 16))
     cb = cpu_baseline(iq_host[:S].numpy(), T) if not under_profiler() else {"value": None, "unit": UNIT, "cores": 0, "kind": "skipped under profiler", "sample": ""}
@@ -373,8 +381,10 @@ def run_cuda(args):
                 "d2h_bytes_per_step": int(C * rx.frame_cap * 64 + 4 * C), "records_equal_device_path": e2e_same},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": {"frontend": "k_frontend", "sync_frame": "k_sync_frame", "decode": "k_decode_frames", "post": "k_post"}[dom],
-                     "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": None,
+        "roofline": {"bound": "hbm", "kernel": kname[dom],
+                     "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": traffic,
+                     "note": "dominant kernel by device time; k_sync_frame (matched filter + timing loop) is issue/latency-bound, not HBM-bound "
+                             "(DESIGN.md 4) -- the HBM-bound stage is k_frontend, see stages",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 (B200_PROFILING.md)",
                      "whole_chain_gbs": round(FRAME_BYTES_FUSED * C * T / (ms_step * 1e-3) / 1e9, 1), "stages": stages},
         "cpu_baseline": cb,
