@@ -93,6 +93,16 @@ struct RxChanState {
     uint8_t packet[800];     // m_packet
 };
 
+// ---------------------------------------------------------------- packed fp32 pairs (sm_100 FMUL2 / FADD2 / FFMA2)
+// Each half is an independent IEEE round-to-nearest operation, so results are bit-identical to the scalar forms; they
+// only halve the instruction count.  NOTE: ptxas contracts mul.rn.f32x2 followed by add.rn.f32x2 into FFMA2 even
+// with --fmad=false, so a packed product must never feed a packed add directly -- products are consumed by scalar adds.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
 // ---------------------------------------------------------------- small device helpers
 __device__ __forceinline__ uint16_t crc16_step(uint16_t crc, uint8_t byte, const uint16_t *tab) {
     // m17_crc.cpp:30-33

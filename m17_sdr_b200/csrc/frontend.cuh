@@ -42,14 +42,15 @@ __device__ __forceinline__ LimSample fe_limit_ieee(uint32_t raw, float *mo = nul
 }
 
 __device__ __forceinline__ LimSample fe_limit(uint32_t raw, float *mo = nullptr, float *go = nullptr) {
-    // int16 -> float: one I2F.S16 per component, reading the half-register directly (exact)
-    const float xr = (float)(short)(raw & 0xFFFFu);
-    const float xi = (float)(short)(raw >> 16);
+    // int16 -> float: one I2F.S16 per component, reading the half-register directly (exact); from here (re, im) travel as
+    // one packed pair: FMUL2 / FFMA2 do the two-float scaling, the squares and the final limiter scaling in one issue slot each
+    const f32x2 x = pack2((float)(short)(raw & 0xFFFFu), (float)(short)(raw >> 16));
     constexpr float c_hi = 0.00003f;
     constexpr float c_lo = (float)(0.00003 - (double)0.00003f);
-    const float re = __fmaf_rn(xr, c_hi, xr * c_lo);
-    const float im = __fmaf_rn(xi, c_hi, xi * c_lo);
-    const float s = re * re + im * im;                        // two rounded products, one rounded sum (no contraction)
+    const f32x2 v = fma2(x, pack2(c_hi, c_hi), mul2(x, pack2(c_lo, c_lo)));      // (re, im) = fmaf(x, c_hi, x * c_lo)
+    float q0, q1;
+    unpack2(mul2(v, v), q0, q1);
+    const float s = q0 + q1;                                   // two rounded products, one rounded (scalar) sum: no contraction
     float y;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(s));
     // m = RN(sqrt(s)): Newton step on the residual
@@ -66,8 +67,7 @@ __device__ __forceinline__ LimSample fe_limit(uint32_t raw, float *mo = nullptr,
     if (((mb + 1u) & 0x7FFFFFu) == 0u) g = __uint_as_float(0x7F000000u - mb);
     if (mo) { *mo = m; *go = g; }
     LimSample o;
-    o.re = re * g;
-    o.im = im * g;
+    unpack2(mul2(v, pack2(g, g)), o.re, o.im);
     return o;
 }
 

@@ -50,17 +50,21 @@ __device__ __forceinline__ void sync_adjust(int TH, int &thr, int &index, int &c
 // Two consecutive symbols for one lane: windows xs[n0 .. n0+30] and xs[n0+2 .. n0+32], n0 = i + 4*lane.  R = i & 3 is
 // warp-uniform, so array / offset of every tap are compile-time and the 32 lanes read consecutive words.
 template <int R>
-__device__ __forceinline__ void dot2(const float (*X)[SY_XQ], int base, const float (&cmf)[M17B_FN], const float (&cmd)[M17B_FN],
-                                     float &sa, float &da, float &sb, float &db) {
+__device__ __forceinline__ void dot2(const float (*X)[SY_XQ], int base, const f32x2 (&tp)[M17B_FN], float &sa, float &da, float &sb, float &db) {
     float x[M17B_FN + 2];
 #pragma unroll
     for (int k = 0; k < M17B_FN + 2; k++) x[k] = X[(R + k) & 3][base + ((R + k) >> 2)];
-    sa = x[0] * cmf[0]; da = x[0] * cmd[0];                  // sum = in[0]*c[0]; sum += in[i]*c[i]   (m17_rx_sync.cpp:25-31)
-    sb = x[2] * cmf[0]; db = x[2] * cmd[0];
+    // tp[k] = (matched tap k, derivative tap k): one FMUL2 with the sample broadcast gives both rounded products; the running
+    // sums stay scalar adds in the reference's order (sum = in[0]*c[0]; sum += in[i]*c[i], m17_rx_sync.cpp:25-31)
+    unpack2(mul2(tp[0], pack2(x[0], x[0])), sa, da);
+    unpack2(mul2(tp[0], pack2(x[2], x[2])), sb, db);
 #pragma unroll
     for (int k = 1; k < M17B_FN; k++) {
-        sa += x[k] * cmf[k]; da += x[k] * cmd[k];
-        sb += x[k + 2] * cmf[k]; db += x[k + 2] * cmd[k];
+        float pa, qa, pb, qb;
+        unpack2(mul2(tp[k], pack2(x[k], x[k])), pa, qa);
+        unpack2(mul2(tp[k], pack2(x[k + 2], x[k + 2])), pb, qb);
+        sa += pa; da += qa;
+        sb += pb; db += qb;
     }
 }
 
@@ -100,7 +104,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32) k_sync_frame(const float *__res
     }
     if (lane == 0) sym_base[c] = base_g;
     int nfr = 0, nev = 0, n_aos = 0, n_los = 0;
-    float cmf[M17B_FN], cmd[M17B_FN];
+    f32x2 tp[M17B_FN];                      // (matched, derivative) tap pairs of the current polyphase branch
     int tap_index = -1;
     __syncwarp();
     // the block's samples are fetched one block ahead (registers), so the DRAM latency hides behind the timing loop
@@ -142,7 +146,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32) k_sync_frame(const float *__res
             }
             if (index != tap_index) {
 #pragma unroll
-                for (int k = 0; k < M17B_FN; k++) { cmf[k] = __ldg(g_mf + index * M17B_FN + k); cmd[k] = __ldg(g_md + index * M17B_FN + k); }
+                for (int k = 0; k < M17B_FN; k++) tp[k] = pack2(__ldg(g_mf + index * M17B_FN + k), __ldg(g_md + index * M17B_FN + k));
                 tap_index = index;
             }
             // speculate: lane l computes the symbols at samples ja = i + 4l and jb = ja + 2
@@ -152,10 +156,10 @@ __global__ void __launch_bounds__(SY_WARPS * 32) k_sync_frame(const float *__res
             if (valid_a) {
                 const int base = (i >> 2) + lane;
                 switch (i & 3) {
-                    case 0: dot2<0>(sm.x, base, cmf, cmd, sa, da, sb, db); break;
-                    case 1: dot2<1>(sm.x, base, cmf, cmd, sa, da, sb, db); break;
-                    case 2: dot2<2>(sm.x, base, cmf, cmd, sa, da, sb, db); break;
-                    default: dot2<3>(sm.x, base, cmf, cmd, sa, da, sb, db); break;
+                    case 0: dot2<0>(sm.x, base, tp, sa, da, sb, db); break;
+                    case 1: dot2<1>(sm.x, base, tp, sa, da, sb, db); break;
+                    case 2: dot2<2>(sm.x, base, tp, sa, da, sb, db); break;
+                    default: dot2<3>(sm.x, base, tp, sa, da, sb, db); break;
                 }
             }
             // votes happen on the sample after each symbol (sync_update, m17_rx_sync.cpp:38-42) if it is in this block
