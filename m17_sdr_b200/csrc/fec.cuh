@@ -289,10 +289,10 @@ __device__ __forceinline__ SyncResult sync_check8(const float *v) {
     r.type = type;
     // votes: vect[i]*sframe[type][i] < 0  <=>  v[i] < 0 where the template is +1, v[i] > 0 where it is -1
     const unsigned m = (unsigned)((0x400DF24FB0AAull >> (8 * type)) & 0xFFu);
-    int votes = 0;
+    unsigned negm = 0, posm = 0;                                             // bit i: v[i] < 0 / v[i] > 0 (both clear for 0 and NaN)
 #pragma unroll
-    for (int i = 0; i < 8; i++) votes += (((m >> i) & 1u) ? (v[i] > 0) : (v[i] < 0)) ? 1 : 0;
-    r.votes = votes;
+    for (int i = 0; i < 8; i++) { negm |= (v[i] < 0) ? (1u << i) : 0u; posm |= (v[i] > 0) ? (1u << i) : 0u; }
+    r.votes = __popc((negm & ~m & 0xFFu) | (posm & m));
     return r;
 }
 // m17_unlocked_sync_check / m17_locked_sync_check (m17_rx_frame.cpp:82-103); variance compared as double

@@ -25,6 +25,7 @@ struct SyncWarpSmem {
                                         // stride-4 windows of the 32 lanes (two symbols per lane) hit 32 different banks
     float hist[SY_HIST];                // [0,8): sliding sync window carried in; [8, 8+n): symbols emitted in this block
     float head[8];                      // m_f_sym[0..7] of the frame being collected
+    float pre[2][384 + 4];              // cp.async landing zone for the NEXT block's raw samples (+ its mean), double buffered
 };
 
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
@@ -107,27 +108,39 @@ __global__ void __launch_bounds__(SY_WARPS * 32) k_sync_frame(const float *__res
     f32x2 tp[M17B_FN];                      // (matched, derivative) tap pairs of the current polyphase branch
     int tap_index = -1;
     __syncwarp();
-    // the block's samples are fetched one block ahead (registers), so the DRAM latency hides behind the timing loop
-    float pf[12], pmu = 0.0f;
+    // The block's samples are fetched one block ahead with cp.async straight into shared memory: completion is tracked by
+    // the async-copy group, not by a register scoreboard, so nothing in the timing loop ever waits on the DRAM latency.
+    auto prefetch = [&](int64_t tt, int buf) {
+        const float *src = disc + (c * T + tt) * 384;
 #pragma unroll
-    for (int q = 0; q < 12; q++) pf[q] = __ldg(disc + (c * T) * 384 + lane + 32 * q);
-    if (HAS_MEAN) pmu = mean[c * T];
+        for (int q = 0; q < 12; q++) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.pre[buf][lane + 32 * q]);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src + lane + 32 * q));
+        }
+        if (HAS_MEAN && lane == 0) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.pre[buf][384]);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(mean + c * T + tt));
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    prefetch(0, 0);
 
     for (int64_t t = 0; t < T; t++) {
         // ---- stage the block's 384 discriminator samples behind the 30 of history
+        const int buf = (int)(t & 1);
+        asm volatile("cp.async.wait_group 0;");
+        __syncwarp();
+        {
+            const float pmu = HAS_MEAN ? sm.pre[buf][384] : 0.0f;
 #pragma unroll
-        for (int q = 0; q < 12; q++) {
-            float v = pf[q];
-            if (HAS_MEAN) v = v - pmu;                                      // m17_dsp.cpp:217-219
-            const int n = 30 + lane + 32 * q;
-            sm.x[n & 3][n >> 2] = v;
+            for (int q = 0; q < 12; q++) {
+                float v = sm.pre[buf][lane + 32 * q];
+                if (HAS_MEAN) v = v - pmu;                                  // m17_dsp.cpp:217-219
+                const int n = 30 + lane + 32 * q;
+                sm.x[n & 3][n >> 2] = v;
+            }
         }
-        if (t + 1 < T) {
-            const float *src = disc + (c * T + t + 1) * 384;
-#pragma unroll
-            for (int q = 0; q < 12; q++) pf[q] = __ldg(src + lane + 32 * q);
-            if (HAS_MEAN) pmu = mean[c * T + t + 1];
-        }
+        if (t + 1 < T) prefetch(t + 1, buf ^ 1);
         __syncwarp();
 
         // ---- timing loop (m17_rx_sync.cpp:77-99); m17_rx_lock() is constant inside a block
