@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(NW * 32) k_sync_frame_cta(const float *__restr
     }
     if (tid == 0) sym_base[c] = base_g;
     int nfr = 0, nev = 0, n_aos = 0, n_los = 0;
-    float cmf[M17B_FN], cmd[M17B_FN];
+    f32x2 tp[M17B_FN];                      // (matched, derivative) tap pairs of the current polyphase branch
     int tap_index = -1;
     // the block's samples are fetched one block ahead
     float pf[NQ], pmu = 0.0f;
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(NW * 32) k_sync_frame_cta(const float *__restr
             }
             if (index != tap_index) {
 #pragma unroll
-                for (int k = 0; k < M17B_FN; k++) { cmf[k] = __ldg(g_mf + index * M17B_FN + k); cmd[k] = __ldg(g_md + index * M17B_FN + k); }
+                for (int k = 0; k < M17B_FN; k++) tp[k] = pack2(__ldg(g_mf + index * M17B_FN + k), __ldg(g_md + index * M17B_FN + k));
                 tap_index = index;
             }
             // speculate: thread k computes the symbol at sample j = i + 2k
@@ -113,13 +113,14 @@ __global__ void __launch_bounds__(NW * 32) k_sync_frame_cta(const float *__restr
                 const float *B = (i & 1) ? sm.xe : sm.xo;
                 const int h = (i >> 1) + tid, ob = i & 1;
                 float x = A[h];
-                s = x * cmf[0];                                                // sum = in[0]*c[0]; sum += in[i]*c[i]  (m17_rx_sync.cpp:25-31)
-                d = x * cmd[0];
+                unpack2(mul2(tp[0], pack2(x, x)), s, d);                      // sum = in[0]*c[0]; sum += in[i]*c[i]  (m17_rx_sync.cpp:25-31)
 #pragma unroll
                 for (int k = 1; k < M17B_FN; k++) {
                     x = (k & 1) ? B[h + (k >> 1) + ob] : A[h + (k >> 1)];
-                    s += x * cmf[k];
-                    d += x * cmd[k];
+                    float ps, pd;
+                    unpack2(mul2(tp[k], pack2(x, x)), ps, pd);                  // one FMUL2: both rounded products
+                    s += ps;
+                    d += pd;
                 }
             }
             const bool has_vote = valid && (j + 1 < 384);

@@ -7,7 +7,6 @@
 __constant__ GatherMaps c_maps;
 __constant__ TxMaps     c_tx;
 __constant__ PunctSteps c_punct;
-__constant__ uint8_t    c_sync_neg[6];     // sync templates as sign masks (bit i set = -1), m17_rx_frame.cpp:5-12
 
 // M17 randomiser sequence (protocol constant, m17_correlate.cpp:3-7)
 static const uint8_t kRandSeq[46] = {
@@ -154,7 +153,6 @@ extern "C" int m17b_ctx_create(int device, m17b_ctx **out) {
     build_sync_banks(ctx->h_mf, ctx->h_md);
     GatherMaps gm; TxMaps tm;
     build_gather_maps(&gm, &tm);
-    const uint8_t sync_neg[6] = {0xAA, 0xB0, 0x4F, 0xF2, 0x0D, 0x40};
     PunctSteps ps;
     for (int pat = 1; pat <= 3; pat++)
         for (int t = 0; t < 244; t++) ps.keep[pat - 1][t] = (uint8_t)((punct_keeps(pat, 2 * t) ? 1 : 0) | (punct_keeps(pat, 2 * t + 1) ? 2 : 0));
@@ -165,7 +163,6 @@ extern "C" int m17b_ctx_create(int device, m17b_ctx **out) {
     free(genc); free(gerr);
     CUDA_TRY(cudaMemcpyToSymbol(c_maps, &gm, sizeof(gm)));
     CUDA_TRY(cudaMemcpyToSymbol(c_tx, &tm, sizeof(tm)));
-    CUDA_TRY(cudaMemcpyToSymbol(c_sync_neg, sync_neg, sizeof(sync_neg)));
     CUDA_TRY(cudaMemcpyToSymbol(c_punct, &ps, sizeof(ps)));
 
     // contraction self-test: (1+2^-12)*(1+2^-12) - 1 : separate rounding gives 2^-11, an FMA gives 2^-11 + 2^-24

@@ -409,6 +409,48 @@ long m17o_mod(m17o_tx *t, const uint8_t *syms, long nsym, int16_t *iq, float *fr
     return n;
 }
 
+/* ================================================================== Pluto /8 decimator (radio.cpp:18-51,157-177) */
+void m17o_lpf_design(float *taps, float bw, int ntaps) {
+    /* m17_dsp.cpp:347-360: rectangular-window sinc, double math, first tap time by integer division */
+    double B = bw, t = -(ntaps - 1) / 2;
+    for (int i = 0; i < ntaps; i++) {
+        double a = (t == 0) ? 2.0 * B : 2.0 * B * sin(M_PI * t * B) / (M_PI * t * B);
+        taps[i] = (float)a;
+        t = t + 1.0;
+    }
+}
+void m17o_dec_open(m17o_dec *d) {
+    float f[31];
+    memset(d, 0, sizeof(*d));
+    m17o_lpf_design(f, 0.125f, 31);
+    m17o_set_gain(f, 0.9, 1, 31);                                /* radio.cpp:48: gain literal 0.9 (double) narrowed to the float parameter */
+    for (int i = 0; i < 31; i++) d->taps[i] = (int16_t)(f[i] * 0x7FFF);     /* m17_dsp_float_to_short, m17_dsp.cpp:382-386 */
+}
+void m17o_dec_run(m17o_dec *d, const int16_t *in, long nout, int16_t *out) {
+    /* streaming form of rx_decimate_filter over m_rx_buff: output k uses inputs 8k-31 .. 8k-1 (the 31-sample history
+       carried at the head of the buffer, radio.cpp:167), symmetric taps folded, int32 accumulate, arithmetic >> 15 */
+    for (long k = 0; k < nout; k++) {
+        int32_t re, im, w[31][2];
+        for (int j = 0; j < 31; j++) {
+            long n = 8 * k - 31 + j;
+            if (n >= 0) { w[j][0] = in[2 * n]; w[j][1] = in[2 * n + 1]; }
+            else        { w[j][0] = d->hist[31 + n][0]; w[j][1] = d->hist[31 + n][1]; }
+        }
+        re = w[15][0] * d->taps[15];
+        im = w[15][1] * d->taps[15];
+        for (int i = 0; i < 15; i++) { re += d->taps[i] * (w[i][0] + w[30 - i][0]); im += d->taps[i] * (w[i][1] + w[30 - i][1]); }
+        out[2 * k] = (int16_t)(re >> 15);
+        out[2 * k + 1] = (int16_t)(im >> 15);
+    }
+    /* new history = last 31 inputs */
+    int16_t nh[31][2];
+    for (int j = 0; j < 31; j++) {
+        long n = 8 * nout - 31 + j;
+        if (n >= 0) { nh[j][0] = in[2 * n]; nh[j][1] = in[2 * n + 1]; } else { nh[j][0] = d->hist[31 + n][0]; nh[j][1] = d->hist[31 + n][1]; }
+    }
+    memcpy(d->hist, nh, sizeof(nh));
+}
+
 /* ================================================================== RX */
 struct m17o_rx {
     /* front end */

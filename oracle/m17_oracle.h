@@ -86,6 +86,12 @@ int  m17o_fmt_bert(m17o_tx *t, uint8_t *dibits);                             /* 
    frequency samples m_sum when freq != NULL); returns samples written.  m17_modulate.cpp:22-61,79-92 */
 long m17o_mod(m17o_tx *t, const uint8_t *syms, long nsym, int16_t *iq, float *freq);
 
+/* ---- Pluto front-end decimator: int16 31-tap symmetric low-pass, decimate by 8, 384 kS/s -> 48 kS/s */
+typedef struct { int16_t taps[31]; int16_t hist[31][2]; } m17o_dec;
+void m17o_lpf_design(float *taps, float bw, int ntaps);                      /* m17_dsp.cpp:347-360 */
+void m17o_dec_open(m17o_dec *d);                                             /* build_pluto_rx_dec_filter, radio.cpp:44-51 */
+void m17o_dec_run(m17o_dec *d, const int16_t *in, long nout, int16_t *out);  /* radio.cpp:18-40,157-177: in [8*nout][2] -> out [nout][2] */
+
 /* ---- RX */
 typedef struct m17o_rx m17o_rx;
 m17o_rx *m17o_rx_new(void);

@@ -106,6 +106,7 @@ void gui_save_dest_address(uint48_t) {}
 void gui_save_src_address(uint48_t) { if (g_cur) g_cur->flags |= M17R_F_LSF_EVENT; }
 bool m17_net_new_rx_data(uint16_t, uint8_t *, uint16_t, uint8_t *) { if (g_cur) g_cur->flags |= M17R_F_DELIVERED; return true; }
 void m17_txrx_spkr_audio(uint8_t *) {}
+#ifndef REF_WITH_RADIO
 void radio_afc(float mean) { if (g_afc && m17_db_in_frame()) g_afc_delta -= mean * 0.1; }
 float radio_get_afc_delta(void) { if (g_afc && m17_db_in_frame()) return g_afc_delta; g_afc_delta = 0; return 0; }
 bool radio_get_afc_status(void) { return g_afc; }
@@ -118,6 +119,59 @@ int  radio_transmit_samples(scmplx *s, uint32_t n) {
     }
     return (int)n;
 }
+#else
+/*
+ * REF_WITH_RADIO build (oracle/_ref/libm17ref_radio.so): the reference's own radio.cpp is linked in place of the five
+ * radio_* stubs above, and the SDR driver entry points it calls are stubbed instead.  Only the Pluto receive path is
+ * exercised: radio_receive_samples() pulls eight 1920-sample chunks at 384 kS/s through pluto_rx_samples() and runs the
+ * int16 31-tap /8 decimator (radio.cpp:18-40,157-177).
+ */
+static const int16_t *g_pl_src = 0; static long g_pl_left = 0;
+uint32_t pluto_rx_samples(scmplx *s) {
+    long n = g_pl_left < 1920 ? g_pl_left : 1920;
+    memset(s, 0, sizeof(scmplx) * 1920);
+    if (n > 0) { memcpy(s, g_pl_src, sizeof(scmplx) * n); g_pl_src += 2 * n; g_pl_left -= n; }
+    return 1920;
+}
+int  pluto_open(uint32_t) { return 0; }
+void pluto_close(void) {}
+void pluto_set_rx_sample_rate(long int) {}
+void pluto_set_tx_sample_rate(long int) {}
+void pluto_configure_x8_int_dec(long long int) {}
+void pluto_set_rx_freq(long long int) {}
+void pluto_set_tx_freq(long long int) {}
+void pluto_set_tx_level(double) {}
+void pluto_read_rssi_value(long long int *r) { *r = 60; }
+void pluto_stop_rx_stream(void) {}
+void pluto_stop_tx_stream(void) {}
+int  pluto_start_rx_stream(void) { return 0; }
+int  pluto_start_tx_stream(void) { return 0; }
+void pluto_tx_samples(scmplx *, int) {}
+int  lime_open(void) { return 0; }
+void lime_close(void) {}
+void lime_ptt_rx(void) {}
+void lime_ptt_tx(void) {}
+bool lime_read_ptt(void) { return false; }
+uint32_t lime_read_rssi(void) { return 4000; }
+double lime_get_rx_gain(void) { return 1.0; }
+void lime_set_rx_gain(double) {}
+void lime_set_tx_gain(float) {}
+void lime_set_rx_freq(uint64_t) {}
+void lime_set_tx_freq(uint64_t) {}
+void lime_got_to_duplex(void) {}
+void lime_got_to_receive(void) {}
+void lime_got_to_transmit(void) {}
+int  lime_receive_samples(int16_t *, int n) { return n; }
+int  lime_transmit_samples(int16_t *, int n) { return n; }
+int  rpi_gpio_open(void) { return 0; }
+void rpi_gpio_close(void) {}
+void rpi_rx(void) {}
+void rpi_tx(void) {}
+void gui_dp(void) {}
+void gui_rx(void) {}
+void gui_tx(void) {}
+void gui_bar(double) {}
+#endif
 int udp_send(uint8_t *, int len) { return len; }
 
 /* ------------------------------------------------------------------ --wrap interposers */
@@ -435,6 +489,17 @@ int ref_tx_dibits_run(long C, int nproc, const uint8_t *script, long nsym, int16
     });
 }
 
+#ifdef REF_WITH_RADIO
+/* Pluto front-end decimator: in = int16 [C][nblk*8*1920][2] at 384 kS/s, out (MAP_SHARED) = int16 [C][nblk*1920][2] at 48 kS/s;
+   one pristine process per channel (m_rx_buff is a file static, radio.cpp:15) */
+int ref_pluto_run(const int16_t *in, long C, long nblk, int nproc, int16_t *out) {
+    return fork_each(C, nproc, [&](long c) {
+        radio_open(RADIO_TYPE_PLUTO);
+        g_pl_src = in + c * nblk * 8 * 1920 * 2; g_pl_left = nblk * 8 * 1920;
+        for (long b = 0; b < nblk; b++) radio_receive_samples((scmplx *)(out + (c * nblk + b) * 1920 * 2), 1920);
+    });
+}
+#endif
 void *ref_shared_alloc(long bytes) {
     void *p = mmap(0, bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
     return p == MAP_FAILED ? 0 : p;
