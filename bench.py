@@ -282,9 +282,10 @@ def run_cuda(args):
             torch.cuda.synchronize()
 
     # ---- device-resident throughput ("value")
+    if args.slice_blocks is not None:
+        rx.set_slice_blocks(args.slice_blocks)
     for _ in range(args.warmup):
         step()
-    rx.set_timing(True)
     sync_all()
     sampler = ClockSampler(local)
     sampler.start()
@@ -303,15 +304,29 @@ def run_cuda(args):
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms_step = float(tms.item()) / args.steps
-    launches = (rx.launches() + 1) * args.steps          # 4 chain kernels + the state-reset kernel per step
+    launches = (rx.launches() + 1) * args.steps          # chain kernels of every pipeline slice + the state-reset kernel per step
+    res = rx.results()
+    # ---- per-stage device times: the same step with the stages strictly in sequence (stage timing switches the time-sliced
+    #      pipeline off), CUDA events recorded by the library on the launching stream around each stage
     stage = {k: 0.0 for k in ("frontend", "sync_frame", "decode", "post")}
-    nst = min(args.steps, 64)
-    for i in range(args.steps - nst, args.steps):
+    nst = min(args.steps, 16)
+    rx.set_timing(True)
+    es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    step(); torch.cuda.synchronize()
+    rx.set_timing(True)                      # restart the call counter after the warm-up step
+    es0.record()
+    for _ in range(nst):
+        step()
+    es1.record()
+    torch.cuda.synchronize()
+    ms_step_serial = es0.elapsed_time(es1) / nst
+    for i in range(nst):
         s = rx.stage_ms(i)
         for k in stage:
             stage[k] += s[k] / nst
     rx.set_timing(False)
-    res = rx.results()
+    res_serial = rx.results()
+    same_serial = bool(np.array_equal(res_serial["frames"].view(np.uint8), res["frames"].view(np.uint8)) and np.array_equal(res_serial["nsym"], res["nsym"]))
     nfr = res["nframes"]
     ok, tot = payload_check(torch, res["frames"], nfr, payload)
     stats = res["stats"].sum(0)
@@ -376,7 +391,7 @@ def run_cuda(args):
         "config": {"workload": f"configs[1]: {C} concurrent stream-mode channels per GPU x {T} blocks (10 s each), full m17_dsp_rx chain from int16 IQ "
                                f"(limiter, discriminator, RRC matched filter + timing loop, sync/framer, demap+gather, Viterbi, Golay, CRC, LICH), "
                                f"AWGN on IQ Eb/N0 {{22,24,26,30,inf}} dB, f0 +-1 kHz, random start delay",
-                   "channels_per_gpu": C, "blocks": T, "l2": "input 1.97 GB per GPU >> 126 MB L2 (no flush needed)", "parallelism": f"channels sharded x{world}, no data-path collective"},
+                   "channels_per_gpu": C, "blocks": T, "pipeline_slice_blocks": args.slice_blocks or 0, "l2": "input 1.97 GB per GPU >> 126 MB L2 (no flush needed)", "parallelism": f"channels sharded x{world}, no data-path collective"},
         "e2e": {"value": frames_step / (e2e_ms / 1e3) / 25.0, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(C * T * 7680),
                 "d2h_bytes_per_step": int(C * rx.frame_cap * 64 + 4 * C), "records_equal_device_path": e2e_same},
         "gpu_launches": int(launches),
@@ -386,7 +401,9 @@ def run_cuda(args):
                      "note": "dominant kernel by device time; k_sync_frame (matched filter + timing loop) is issue/latency-bound, not HBM-bound "
                              "(DESIGN.md 4) -- the HBM-bound stage is k_frontend, see stages",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 (B200_PROFILING.md)",
-                     "whole_chain_gbs": round(FRAME_BYTES_FUSED * C * T / (ms_step * 1e-3) / 1e9, 1), "stages": stages},
+                     "whole_chain_gbs": round(FRAME_BYTES_FUSED * C * T / (ms_step * 1e-3) / 1e9, 1),
+                     "stages_measured": "stages strictly in sequence (no time slicing), CUDA events on the launching stream",
+                     "ms_per_step_in_sequence": round(ms_step_serial, 4), "records_equal_pipelined": same_serial, "stages": stages},
         "cpu_baseline": cb,
         "check": {"delivered_payloads_exact": f"{ok}/{tot}", "frames": int(stats[0]), "stream_frames": int(stats[1]), "delivered": int(stats[3]),
                   "golay_errors": int(stats[2]), "aos": int(stats[4]), "los": int(stats[5])},
@@ -405,6 +422,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--channels", type=int, default=CHANNELS_PER_GPU)
     ap.add_argument("--blocks", type=int, default=BLOCKS)
+    ap.add_argument("--slice-blocks", type=int, default=None, help="blocks per pipeline slice (0 = stages in sequence); default: library default")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
     if args.impl == "reference":

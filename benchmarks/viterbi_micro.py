@@ -19,6 +19,10 @@ def make_frames(ctx, pattern, n, ebn0_db, seed=3):
     nb, full, _ = CFG[pattern]
     g = torch.Generator(device=ctx.device); g.manual_seed(seed)
     data = torch.randint(0, 256, (n, nb), generator=g, device=ctx.device, dtype=torch.int32).to(torch.uint8)
+    if pattern == 3:
+        # packet frames carry eof<<7 | n<<2 in the last byte (m17_tx_routines.cpp:210): its two low bits are 0, which is what lets
+        # the reference cut the coded frame at 420 bits (2 of the 4 tail steps) and still trace back from state 0
+        data[:, -1] &= 0xFC
     coded = ctx.m17_conv_encode_8(data)[:, :full].contiguous()
     kept = ctx.m17_punc(pattern, coded).float() * 2 - 1
     if ebn0_db is not None:

@@ -166,6 +166,10 @@ int m17b_dsp_rx_host(m17b_rx *rx, const int16_t *h_iq, int64_t nblocks, m17b_fra
    (0-based, counted since timing was switched on; the last 64 calls are kept).  Not recorded by the _host entry point. */
 int m17b_rx_set_timing(m17b_rx *rx, int on);
 int m17b_rx_stage_ms(m17b_rx *rx, int64_t call_index, float *h_out4);
+/* Time-sliced pipelining of m17b_dsp_rx / m17b_rx_baseband: the call is cut into slices of `blocks` 40-ms blocks and the
+   front end of slice k+1, the timing loop + framer of slice k and the frame decode of slice k-1 run concurrently on
+   internal streams (results are identical).  0 = no slicing (stages strictly in sequence), the default. */
+int m17b_rx_set_slice_blocks(m17b_rx *rx, int blocks);
 /* number of kernels the last m17b_dsp_rx / m17b_rx_baseband call launched */
 int m17b_rx_last_launches(const m17b_rx *rx);
 

@@ -272,6 +272,10 @@ class Rx:
         _l.check(self.L.m17b_dsp_rx_host(self.h, _ptr(iq_host), nblocks, _ptr(frames_host), _ptr(nframes_host), _stream()))
         return frames_host, nframes_host
 
+    def set_slice_blocks(self, blocks):
+        """Blocks per pipeline slice (0 = run the stages strictly in sequence); results do not depend on it."""
+        _l.check(self.L.m17b_rx_set_slice_blocks(self.h, int(blocks)))
+
     def set_timing(self, on=True):
         _l.check(self.L.m17b_rx_set_timing(self.h, int(on)))
 

@@ -179,7 +179,7 @@ __device__ __forceinline__ void decode_conv(const float *row, uint16_t *dec, int
 template <int NT, bool STREAM>
 __global__ void __launch_bounds__(NT) k_decode_frames(const float *__restrict__ syms, int64_t sym_pitch, int sym_carry,
                                                       const int32_t *__restrict__ sym_base, m17b_frame_rec *frames, int64_t fcap,
-                                                      const int32_t *__restrict__ nframes, int tiles_per_chan, float *soft_out,
+                                                      const int32_t *__restrict__ nframes, const int2 *__restrict__ frame_rng, int tiles_per_chan, float *soft_out,
                                                       const uint16_t *__restrict__ g_crc, const uint16_t *__restrict__ genc,
                                                       const uint16_t *__restrict__ gerr) {
     extern __shared__ unsigned char smem_raw[];
@@ -190,8 +190,11 @@ __global__ void __launch_bounds__(NT) k_decode_frames(const float *__restrict__ 
     const int tid = threadIdx.x, lane = tid & 31, wbase = tid & ~31;
     const int64_t c = blockIdx.x / tiles_per_chan;
     const int tile = blockIdx.x % tiles_per_chan;
-    const int nfr = min((int64_t)nframes[c], fcap);
-    const int slot = tile * NT + tid;
+    // records [lo, nfr) of the channel: the whole call, or the slice a pipelined sync kernel just completed
+    int lo = 0, nfr;
+    if (frame_rng) { const int2 r = frame_rng[c]; lo = r.x; nfr = r.y; }
+    else nfr = min((int64_t)nframes[c], fcap);
+    const int slot = lo + tile * NT + tid;
     m17b_frame_rec *rec = frames + c * fcap + slot;
     int type = -1, flags = 0;
     uint32_t w0 = 0;
@@ -297,10 +300,12 @@ __global__ void k_set_i32(int32_t *p, int32_t v) { *p = v; }
 #define DECODE_NT 32
 template <int NT, bool STREAM> static size_t decode_smem() { return (size_t)NT * 193 * 4 + (size_t)(STREAM ? 148 : 244) * NT * 2; }
 
+// frame_rng / max_frames: decode only the records [rng.x, rng.y) of each channel (at most max_frames of them)
 static int launch_decode(m17b_ctx *ctx, const float *syms, int64_t sym_pitch, int sym_carry, const int32_t *sym_base,
                          m17b_frame_rec *frames, int64_t fcap, const int32_t *nframes, int64_t nchan, float *soft_out, cudaStream_t st,
-                         cudaStream_t aux = nullptr, cudaEvent_t ev_fork = nullptr, cudaEvent_t ev_join = nullptr) {
-    const int tiles = (int)((fcap + DECODE_NT - 1) / DECODE_NT);
+                         cudaStream_t aux = nullptr, cudaEvent_t ev_fork = nullptr, cudaEvent_t ev_join = nullptr,
+                         const int2 *frame_rng = nullptr, int64_t max_frames = 0) {
+    const int tiles = (int)(((frame_rng ? max_frames : fcap) + DECODE_NT - 1) / DECODE_NT);
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(k_decode_frames<DECODE_NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_smem<DECODE_NT, true>()));
@@ -313,9 +318,9 @@ static int launch_decode(m17b_ctx *ctx, const float *syms, int64_t sym_pitch, in
     cudaStream_t st2 = st;
     if (aux) { CUDA_TRY(cudaEventRecord(ev_fork, st)); CUDA_TRY(cudaStreamWaitEvent(aux, ev_fork, 0)); st2 = aux; }
     k_decode_frames<DECODE_NT, false><<<grid, DECODE_NT, decode_smem<DECODE_NT, false>(), st2>>>(syms, sym_pitch, sym_carry, sym_base, frames, fcap, nframes,
-                                                                                            tiles, soft_out, ctx->d_crc, ctx->d_genc, ctx->d_gerr);
+                                                                                            frame_rng, tiles, soft_out, ctx->d_crc, ctx->d_genc, ctx->d_gerr);
     k_decode_frames<DECODE_NT, true><<<grid, DECODE_NT, decode_smem<DECODE_NT, true>(), st>>>(syms, sym_pitch, sym_carry, sym_base, frames, fcap, nframes,
-                                                                                          tiles, soft_out, ctx->d_crc, ctx->d_genc, ctx->d_gerr);
+                                                                                          frame_rng, tiles, soft_out, ctx->d_crc, ctx->d_genc, ctx->d_gerr);
     KERNEL_CHECK();
     if (aux) { CUDA_TRY(cudaEventRecord(ev_join, aux)); CUDA_TRY(cudaStreamWaitEvent(st, ev_join, 0)); }
     return M17B_OK;

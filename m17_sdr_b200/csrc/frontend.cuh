@@ -79,24 +79,30 @@ __device__ __forceinline__ float sel5(float a0, float a1, float a2, float a3, fl
     return (k == 4) ? a4 : r;
 }
 
-__global__ void __launch_bounds__(FE_WARPS * 32) k_frontend(const uint32_t *__restrict__ iq, int64_t nchan, int64_t T, RxChanState *st,
-                                                            float *__restrict__ disc, float *__restrict__ mean) {
+// Items are the (channel, block) pairs of blocks [t0, t0+Tc) of a call of T blocks per channel (T is the row pitch of iq,
+// disc and mean); the whole call is t0 = 0, Tc = T.  Sub-ranges let the host pipeline the front end of one time slice with
+// the timing loop of the previous one (rx.cuh).
+__global__ void __launch_bounds__(FE_WARPS * 32) k_frontend(const uint32_t *__restrict__ iq, int64_t nchan, int64_t T, int64_t t0, int64_t Tc,
+                                                            RxChanState *st, float *__restrict__ disc, float *__restrict__ mean) {
     __shared__ float tout[FE_WARPS][32][33];
+    __shared__ int64_t gsl[FE_WARPS][32];                        // global (channel, block) index of each lane's item
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t nitems = nchan * T;
+    const int64_t nitems = nchan * Tc;
     const int64_t item0 = ((int64_t)blockIdx.x * FE_WARPS + wid) * 32;
     if (item0 >= nitems) return;
     const bool live = item0 + lane < nitems;
     const int64_t item = live ? item0 + lane : nitems - 1;       // dead lanes shadow the last item (results discarded)
-    const int64_t ch = item / T, t = item % T;
-    const uint4 *row = (const uint4 *)(iq + item * 1920);
+    const int64_t ch = item / Tc, t = t0 + item % Tc;
+    const int64_t g = ch * T + t;
+    gsl[wid][lane] = g;
+    const uint4 *row = (const uint4 *)(iq + g * 1920);
 
     // carried discriminator state: z[0], z[1] are the two previous LIMITED samples (m17_dsp.cpp:196,205-206)
     float z0re, z0im, z1re, z1im;
     const int count0 = st[ch].disc_count;                        // 1920 % 5 == 0: the /5 phase is the same in every block
     if (t == 0) { z0re = st[ch].z0re; z0im = st[ch].z0im; z1re = st[ch].z1re; z1im = st[ch].z1im; }
     else {
-        const uint32_t *prev = iq + item * 1920;
+        const uint32_t *prev = iq + g * 1920;
         LimSample a = fe_limit(__ldg(prev - 1)), b = fe_limit(__ldg(prev - 2));
         z0re = a.re; z0im = a.im; z1re = b.re; z1im = b.im;
     }
@@ -141,11 +147,11 @@ __global__ void __launch_bounds__(FE_WARPS * 32) k_frontend(const uint32_t *__re
         __syncwarp();
 #pragma unroll 4
         for (int r = 0; r < 32; r++)
-            if (item0 + r < nitems) disc[(item0 + r) * 384 + grp * 32 + lane] = tout[wid][r][lane];
+            if (item0 + r < nitems) disc[gsl[wid][r] * 384 + grp * 32 + lane] = tout[wid][r][lane];
         __syncwarp();
     }
     if (live) {
-        mean[item] = (acc * 0.5f) / 1920.0f;                     // offset/len (m17_dsp.cpp:214)
+        mean[g] = (acc * 0.5f) / 1920.0f;                     // offset/len (m17_dsp.cpp:214)
         if (t == T - 1) { st[ch].nz0re = z0re; st[ch].nz0im = z0im; st[ch].nz1re = z1re; st[ch].nz1im = z1im; }
     }
 }

@@ -11,6 +11,7 @@
 #include "sync_cta.cuh"
 
 #define M17B_TIMING_RING 64
+#define M17B_MAX_SLICES 16
 struct m17b_rx {
     m17b_ctx *ctx;
     int64_t nchan, max_blocks, last_blocks;
@@ -28,6 +29,11 @@ struct m17b_rx {
     cudaEvent_t ev_fork, ev_join;
     cudaEvent_t ev_h2d[2], ev_done[2];
     int afc, last_launches, seam_last;
+    // time-sliced pipeline (see rx_pipeline): front end of slice k+1 | timing loop + framer of slice k | frame decode of slice k-1
+    int slice_blocks;                 // blocks per slice; 0 = one slice (stages strictly in sequence)
+    cudaStream_t s_fe, s_sync, s_dec;
+    cudaEvent_t ev_start, ev_fe[M17B_MAX_SLICES], ev_sy[M17B_MAX_SLICES], ev_end;
+    int2 *d_frame_rng;                // [M17B_MAX_SLICES][nchan] records completed by each slice
     int sync_impl;                    // -1 auto; 0: warp per channel (sync.cuh); 2 / 4: CTA of that many warps per channel (sync_cta.cuh)
     int timing;                       // record cudaEvents around each stage of the next calls (bench only)
     cudaEvent_t ev_stage[M17B_TIMING_RING][5];
@@ -142,6 +148,13 @@ extern "C" int m17b_rx_destroy(m17b_rx *rx) {
         if (rx->ev_h2d[i]) cudaEventDestroy(rx->ev_h2d[i]);
         if (rx->ev_done[i]) cudaEventDestroy(rx->ev_done[i]);
     }
+    cudaFree(rx->d_frame_rng);
+    if (rx->s_fe) cudaStreamDestroy(rx->s_fe);
+    if (rx->s_sync) cudaStreamDestroy(rx->s_sync);
+    if (rx->s_dec) cudaStreamDestroy(rx->s_dec);
+    if (rx->ev_start) cudaEventDestroy(rx->ev_start);
+    if (rx->ev_end) cudaEventDestroy(rx->ev_end);
+    for (int i = 0; i < M17B_MAX_SLICES; i++) { if (rx->ev_fe[i]) cudaEventDestroy(rx->ev_fe[i]); if (rx->ev_sy[i]) cudaEventDestroy(rx->ev_sy[i]); }
     if (rx->copy_stream) cudaStreamDestroy(rx->copy_stream);
     if (rx->aux_stream) cudaStreamDestroy(rx->aux_stream);
     if (rx->ev_fork) cudaEventDestroy(rx->ev_fork);
@@ -188,10 +201,26 @@ extern "C" int m17b_rx_create(m17b_ctx *ctx, int64_t nchan, int64_t max_blocks, 
     A((void **)&rx->d_frames, sizeof(m17b_frame_rec) * nchan * rx->fcap);
     A((void **)&rx->d_events, sizeof(m17b_event_rec) * nchan * rx->ecap);
     A((void **)&rx->d_stats, sizeof(unsigned long long) * nchan * 8);
+    A((void **)&rx->d_frame_rng, sizeof(int2) * nchan * M17B_MAX_SLICES);
     if (e != cudaSuccess) { m17b_set_cuda_error(e, __FILE__, __LINE__); m17b_rx_destroy(rx); return e == cudaErrorMemoryAllocation ? M17B_E_NOMEM : M17B_E_CUDA; }
     CUDA_TRY(cudaStreamCreateWithFlags(&rx->aux_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&rx->ev_fork, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&rx->ev_join, cudaEventDisableTiming));
+    {   // the serial chain of the timing loop is the critical path of the pipeline: it gets the highest priority
+        int lo = 0, hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&rx->s_sync, cudaStreamNonBlocking, hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&rx->s_dec, cudaStreamNonBlocking, hi < lo ? hi + 1 : lo));
+        CUDA_TRY(cudaStreamCreateWithPriority(&rx->s_fe, cudaStreamNonBlocking, lo));
+        CUDA_TRY(cudaEventCreateWithFlags(&rx->ev_start, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&rx->ev_end, cudaEventDisableTiming));
+        for (int i = 0; i < M17B_MAX_SLICES; i++) {
+            CUDA_TRY(cudaEventCreateWithFlags(&rx->ev_fe[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&rx->ev_sy[i], cudaEventDisableTiming));
+        }
+    }
+    rx->slice_blocks = 0;          // measured on B200: slicing gives no gain at 1024 channels (the kernels contend for issue slots), see DESIGN.md 4
+    if (const char *e2 = getenv("M17B_SLICE_BLOCKS")) rx->slice_blocks = atoi(e2);
     int rc = m17b_rx_reset(rx, nullptr);
     if (rc) { m17b_rx_destroy(rx); return rc; }
     CUDA_TRY(cudaStreamSynchronize(nullptr));
@@ -207,15 +236,15 @@ extern "C" int m17b_rx_set_afc(m17b_rx *rx, int on) {
     return M17B_OK;
 }
 
-// stages 2..4 for channels [c0, c0+nc)
 #define STAGE_MARK(i) do { if (rx->timing) CUDA_TRY(cudaEventRecord(rx->ev_stage[rx->tcount % M17B_TIMING_RING][i], st)); } while (0)
-static int rx_back_half(m17b_rx *rx, int64_t c0, int64_t nc, const float *disc, const float *mean, int64_t T, int commit_fe, cudaStream_t st) {
+
+// matched filter + timing loop + framer over blocks [t0, t1) of channels [c0, c0+nc)
+static int launch_sync(m17b_rx *rx, int64_t c0, int64_t nc, const float *disc, const float *mean, int64_t T, int t0, int t1, int2 *rng, int commit_fe,
+                       cudaStream_t st) {
     m17b_ctx *ctx = rx->ctx;
-    STAGE_MARK(1);
-    float *syms = rx->d_syms + c0 * rx->sym_pitch;
-    m17b_frame_rec *frames = rx->d_frames + c0 * rx->fcap;
-#define SYNC_ARGS disc, mean, nc, T, rx->d_state + c0, ctx->d_mf, ctx->d_md, syms, rx->sym_pitch, rx->d_nsym + c0 * T, rx->d_sym_base + c0, frames, rx->fcap, \
-                  rx->d_nframes + c0, rx->d_events + c0 * rx->ecap, rx->ecap, rx->d_nevents + c0, rx->d_stats + c0 * 8, commit_fe
+#define SYNC_ARGS disc, mean, nc, T, t0, t1, rng, rx->d_state + c0, ctx->d_mf, ctx->d_md, rx->d_syms + c0 * rx->sym_pitch, rx->sym_pitch, rx->d_nsym + c0 * T, \
+                  rx->d_sym_base + c0, rx->d_frames + c0 * rx->fcap, rx->fcap, rx->d_nframes + c0, rx->d_events + c0 * rx->ecap, rx->ecap, rx->d_nevents + c0, \
+                  rx->d_stats + c0 * 8, commit_fe
     const int impl = rx->sync_impl >= 0 ? rx->sync_impl : (nc <= 256 ? 4 : 0);
     if (impl == 4) {
         if (mean) k_sync_frame_cta<4, true><<<(unsigned)nc, 128, 0, st>>>(SYNC_ARGS);
@@ -230,33 +259,89 @@ static int rx_back_half(m17b_rx *rx, int64_t c0, int64_t nc, const float *disc, 
     }
 #undef SYNC_ARGS
     KERNEL_CHECK();
-    STAGE_MARK(2);
-    int rc = launch_decode(ctx, syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0, nc, nullptr, st,
-                           rx->aux_stream, rx->ev_fork, rx->ev_join);
-    if (rc) return rc;
-    STAGE_MARK(3);
-    k_post<<<grid_for(nc, POST_WARPS), POST_WARPS * 32, 0, st>>>(frames, rx->fcap, rx->d_nframes + c0, nc, rx->d_state + c0, ctx->d_crc, rx->d_stats + c0 * 8);
-    KERNEL_CHECK();
-    STAGE_MARK(4);
-    rx->last_launches += 4;       // sync/framer, two decode kernels, post
     return M17B_OK;
 }
 
-static int rx_chain(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t *d_iq, int64_t T, cudaStream_t st) {
-    float *disc = rx->d_disc + c0 * T * 384, *mean = rx->d_mean + c0 * T;
-    STAGE_MARK(0);
-    k_frontend<<<grid_for(nc * T, FE_WARPS * 32), FE_WARPS * 32, 0, st>>>((const uint32_t *)d_iq, nc, T, rx->d_state + c0, disc, mean);
+// The chain for channels [c0, c0+nc) over T blocks.  d_iq == NULL: the chain starts at the discriminator seam.
+//
+// One slice (rx->slice_blocks == 0, short calls, or stage timing on): front end -> sync/framer -> decode -> post in sequence on st.
+// Several slices: the call is cut into time slices of slice_blocks blocks.  The front end of slice k+1 (block-parallel, HBM /
+// issue bound), the timing loop + framer of slice k (one serial chain per channel: latency-bound, leaves most issue slots
+// idle) and the frame decode of slice k-1 (ALU-bound) run on three streams and share the SMs; events carry the only true
+// dependencies (FE(k) -> SYNC(k), SYNC(k-1) -> SYNC(k) by stream order, SYNC(k) -> DECODE(k)).  Results are identical
+// to the single-slice order: every kernel reads and writes exactly what it would have.
+static int rx_pipeline(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t *d_iq, const float *disc_in, int64_t T, cudaStream_t st, bool allow_slices = true) {
+    m17b_ctx *ctx = rx->ctx;
+    float *disc_w = rx->d_disc + c0 * T * 384, *mean_w = rx->d_mean + c0 * T;
+    const float *disc = d_iq ? disc_w : disc_in, *mean = d_iq ? mean_w : nullptr;
+    const int commit_fe = d_iq ? 1 : 0;
+    m17b_frame_rec *frames = rx->d_frames + c0 * rx->fcap;
+    float *syms = rx->d_syms + c0 * rx->sym_pitch;
+    int64_t sb = rx->slice_blocks;
+    int nsl = (sb > 0 && !rx->timing && allow_slices) ? (int)((T + sb - 1) / sb) : 1;
+    if (nsl > M17B_MAX_SLICES) { nsl = M17B_MAX_SLICES; }
+    if (nsl < 2) {
+        STAGE_MARK(0);
+        if (d_iq) {
+            k_frontend<<<grid_for(nc * T, FE_WARPS * 32), FE_WARPS * 32, 0, st>>>((const uint32_t *)d_iq, nc, T, 0, T, rx->d_state + c0, disc_w, mean_w);
+            KERNEL_CHECK();
+            rx->last_launches += 1;
+        }
+        STAGE_MARK(1);
+        int rc = launch_sync(rx, c0, nc, disc, mean, T, 0, (int)T, nullptr, commit_fe, st);
+        if (rc) return rc;
+        STAGE_MARK(2);
+        rc = launch_decode(ctx, syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0, nc, nullptr, st,
+                           rx->aux_stream, rx->ev_fork, rx->ev_join);
+        if (rc) return rc;
+        STAGE_MARK(3);
+        k_post<<<grid_for(nc, POST_WARPS), POST_WARPS * 32, 0, st>>>(frames, rx->fcap, rx->d_nframes + c0, nc, rx->d_state + c0, ctx->d_crc, rx->d_stats + c0 * 8);
+        KERNEL_CHECK();
+        STAGE_MARK(4);
+        rx->last_launches += 4;       // sync/framer, two decode kernels, post
+        return M17B_OK;
+    }
+    sb = (T + nsl - 1) / nsl;
+    CUDA_TRY(cudaEventRecord(rx->ev_start, st));
+    CUDA_TRY(cudaStreamWaitEvent(rx->s_fe, rx->ev_start, 0));
+    CUDA_TRY(cudaStreamWaitEvent(rx->s_sync, rx->ev_start, 0));
+    CUDA_TRY(cudaStreamWaitEvent(rx->s_dec, rx->ev_start, 0));
+    for (int k = 0; k < nsl; k++) {
+        const int64_t t0 = k * sb, t1 = (t0 + sb < T) ? t0 + sb : T;
+        if (t0 >= t1) break;
+        int2 *rng = rx->d_frame_rng + (int64_t)k * rx->nchan + c0;
+        if (d_iq) {
+            k_frontend<<<grid_for(nc * (t1 - t0), FE_WARPS * 32), FE_WARPS * 32, 0, rx->s_fe>>>((const uint32_t *)d_iq, nc, T, t0, t1 - t0, rx->d_state + c0, disc_w, mean_w);
+            KERNEL_CHECK();
+            CUDA_TRY(cudaEventRecord(rx->ev_fe[k], rx->s_fe));
+            CUDA_TRY(cudaStreamWaitEvent(rx->s_sync, rx->ev_fe[k], 0));
+            rx->last_launches += 1;
+        }
+        int rc = launch_sync(rx, c0, nc, disc, mean, T, (int)t0, (int)t1, rng, commit_fe, rx->s_sync);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(rx->ev_sy[k], rx->s_sync));
+        CUDA_TRY(cudaStreamWaitEvent(rx->s_dec, rx->ev_sy[k], 0));
+        const int64_t span = t1 - t0;
+        rc = launch_decode(ctx, syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0, nc, nullptr, rx->s_dec,
+                           rx->aux_stream, rx->ev_fork, rx->ev_join, rng, span + span / 64 + 4);
+        if (rc) return rc;
+        rx->last_launches += 3;
+    }
+    k_post<<<grid_for(nc, POST_WARPS), POST_WARPS * 32, 0, rx->s_dec>>>(frames, rx->fcap, rx->d_nframes + c0, nc, rx->d_state + c0, ctx->d_crc, rx->d_stats + c0 * 8);
     KERNEL_CHECK();
     rx->last_launches += 1;
-    return rx_back_half(rx, c0, nc, disc, mean, T, 1, st);
+    CUDA_TRY(cudaEventRecord(rx->ev_end, rx->s_dec));
+    CUDA_TRY(cudaStreamWaitEvent(st, rx->ev_end, 0));
+    return M17B_OK;
 }
+
 
 extern "C" int m17b_dsp_rx(m17b_rx *rx, const int16_t *d_iq, int64_t nblocks, void *stream) {
     if (!rx || !d_iq || nblocks <= 0) return M17B_E_ARG;
     if (nblocks > rx->max_blocks) return M17B_E_CAPACITY;
     if (rx->afc) return M17B_E_UNSUPPORTED;
     rx->last_launches = 0; rx->last_blocks = nblocks; rx->seam_last = 0;
-    int rc = rx_chain(rx, 0, rx->nchan, d_iq, nblocks, as_stream(stream));
+    int rc = rx_pipeline(rx, 0, rx->nchan, d_iq, nullptr, nblocks, as_stream(stream));
     if (rx->timing) rx->tcount++;
     return rc;
 }
@@ -265,7 +350,7 @@ extern "C" int m17b_rx_baseband(m17b_rx *rx, const float *d_disc, int64_t nblock
     if (!rx || !d_disc || nblocks <= 0) return M17B_E_ARG;
     if (nblocks > rx->max_blocks) return M17B_E_CAPACITY;
     rx->last_launches = 0; rx->last_blocks = nblocks; rx->seam_last = 1;
-    int rc = rx_back_half(rx, 0, rx->nchan, d_disc, nullptr, nblocks, 0, as_stream(stream));
+    int rc = rx_pipeline(rx, 0, rx->nchan, nullptr, d_disc, nblocks, as_stream(stream));
     if (rx->timing) rx->tcount++;
     return rc;
 }
@@ -300,6 +385,12 @@ extern "C" int m17b_rx_stage_ms(m17b_rx *rx, int64_t call_index, float *out4) {
         if (i == 0 && rx->seam_last) continue;
         CUDA_TRY(cudaEventElapsedTime(&out4[i], ev[i], ev[i + 1]));
     }
+    return M17B_OK;
+}
+// blocks per pipeline slice (0 = no slicing: the stages run strictly one after the other)
+extern "C" int m17b_rx_set_slice_blocks(m17b_rx *rx, int blocks) {
+    if (!rx || blocks < 0) return M17B_E_ARG;
+    rx->slice_blocks = blocks;
     return M17B_OK;
 }
 extern "C" int64_t m17b_rx_frame_cap(const m17b_rx *rx) { return rx ? rx->fcap : 0; }
@@ -338,7 +429,8 @@ extern "C" int m17b_dsp_rx_host(m17b_rx *rx, const int16_t *h_iq, int64_t nblock
         CUDA_TRY(cudaEventRecord(rx->ev_h2d[k], rx->copy_stream));
         CUDA_TRY(cudaStreamWaitEvent(st, rx->ev_h2d[k], 0));
         // note: the per-chunk front-end output lands at the chunk's own offset of d_disc (laid out for T = nblocks)
-        int rc = rx_chain(rx, c0, nc, rx->d_iq_stage[k], T, st);
+        // (the channel chunks already overlap copy and compute; no time slicing inside a chunk)
+        int rc = rx_pipeline(rx, c0, nc, rx->d_iq_stage[k], nullptr, T, st, false);
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(rx->ev_done[k], st));
         CUDA_TRY(cudaMemcpyAsync(h_frames + c0 * rx->fcap, rx->d_frames + c0 * rx->fcap, sizeof(m17b_frame_rec) * nc * rx->fcap, cudaMemcpyDeviceToHost, st));

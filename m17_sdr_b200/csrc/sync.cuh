@@ -71,7 +71,7 @@ __device__ __forceinline__ void dot2(const float (*X)[SY_XQ], int base, const f3
 
 template <bool HAS_MEAN>
 __global__ void __launch_bounds__(SY_WARPS * 32) k_sync_frame(const float *__restrict__ disc, const float *__restrict__ mean, int64_t nchan, int64_t T,
-                                                              RxChanState *st, const float *__restrict__ g_mf, const float *__restrict__ g_md,
+                                                              int t0, int t1, int2 *frame_rng, RxChanState *st, const float *__restrict__ g_mf, const float *__restrict__ g_md,
                                                               float *syms, int64_t sym_pitch, int32_t *__restrict__ nsym, int32_t *__restrict__ sym_base,
                                                               m17b_frame_rec *frames, int64_t fcap, int32_t *__restrict__ nframes,
                                                               m17b_event_rec *events, int64_t ecap, int32_t *__restrict__ nevents,
@@ -85,16 +85,19 @@ __global__ void __launch_bounds__(SY_WARPS * 32) k_sync_frame(const float *__res
     float *out = sm.hist + 8;
 
     // ---- load state (uniform loads)
-    if (commit_fe && lane == 0) { S->z0re = S->nz0re; S->z0im = S->nz0im; S->z1re = S->nz1re; S->z1im = S->nz1im; }
+    // blocks [t0, t1) of a call of T blocks: t0 = 0 starts the call (symbol carry, record / event counts from zero),
+    // t0 > 0 appends to what the earlier slices of the same call produced
+    if (commit_fe && lane == 0 && t1 == T) { S->z0re = S->nz0re; S->z0im = S->nz0im; S->z1re = S->nz1re; S->z1im = S->nz1im; }
     int clk = S->clk, thr = S->thr, index = S->index;
     float sumc = S->sum, difc = S->dif;
     int flock = S->flock, fclk = S->fclk, ferr = S->ferr, frame_start = S->frame_start, sym_total = S->sym_total;
-    const int base_g = sym_total;
+    const int base_g = t0 == 0 ? sym_total : sym_base[c];
+    const int sym_entry = sym_total;
     if (lane < 30) sm.x[lane & 3][lane >> 2] = S->tail[lane];
     if (lane < 8) { sm.hist[lane] = S->win[lane]; sm.head[lane] = S->head[lane]; }
     // carry: the last 192 symbols of the previous call move in front of the new ones
     float *sbuf = syms + c * sym_pitch;
-    {
+    if (t0 == 0) {
         const int prev_n = S->prev_n;
         float tmp[6];
 #pragma unroll
@@ -103,8 +106,9 @@ __global__ void __launch_bounds__(SY_WARPS * 32) k_sync_frame(const float *__res
 #pragma unroll
         for (int k = 0; k < 6; k++) sbuf[lane + 32 * k] = tmp[k];
     }
-    if (lane == 0) sym_base[c] = base_g;
-    int nfr = 0, nev = 0, n_aos = 0, n_los = 0;
+    if (lane == 0 && t0 == 0) sym_base[c] = base_g;
+    int nfr = t0 == 0 ? 0 : nframes[c], nev = t0 == 0 ? 0 : nevents[c], n_aos = 0, n_los = 0;
+    const int nfr_entry = nfr;
     f32x2 tp[M17B_FN];                      // (matched, derivative) tap pairs of the current polyphase branch
     int tap_index = -1;
     __syncwarp();
@@ -123,11 +127,11 @@ __global__ void __launch_bounds__(SY_WARPS * 32) k_sync_frame(const float *__res
         }
         asm volatile("cp.async.commit_group;");
     };
-    prefetch(0, 0);
+    prefetch(t0, 0);
 
-    for (int64_t t = 0; t < T; t++) {
+    for (int64_t t = t0; t < t1; t++) {
         // ---- stage the block's 384 discriminator samples behind the 30 of history
-        const int buf = (int)(t & 1);
+        const int buf = (int)((t - t0) & 1);
         asm volatile("cp.async.wait_group 0;");
         __syncwarp();
         {
@@ -140,7 +144,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32) k_sync_frame(const float *__res
                 sm.x[n & 3][n >> 2] = v;
             }
         }
-        if (t + 1 < T) prefetch(t + 1, buf ^ 1);
+        if (t + 1 < t1) prefetch(t + 1, buf ^ 1);
         __syncwarp();
 
         // ---- timing loop (m17_rx_sync.cpp:77-99); m17_rx_lock() is constant inside a block
@@ -204,10 +208,10 @@ __global__ void __launch_bounds__(SY_WARPS * 32) k_sync_frame(const float *__res
                 if (2 * lane <= P && m_idx + 2 * lane >= 0) out[m_idx + 2 * lane] = sa;
                 if (2 * lane + 1 <= P && m_idx + 2 * lane + 1 >= 0) out[m_idx + 2 * lane + 1] = sb;
                 m_idx += P + 1;
-                const int t0 = __shfl_sync(0xffffffffu, th_a, L), t1 = __shfl_sync(0xffffffffu, th_b, L);
+                const int thr0 = __shfl_sync(0xffffffffu, th_a, L), thr1 = __shfl_sync(0xffffffffu, th_b, L);
                 const float s0 = __shfl_sync(0xffffffffu, sa, L), s1 = __shfl_sync(0xffffffffu, sb, L);
                 const float d0 = __shfl_sync(0xffffffffu, da, L), d1 = __shfl_sync(0xffffffffu, db, L);
-                thr = (P & 1) ? t1 : t0;
+                thr = (P & 1) ? thr1 : thr0;
                 sumc = (P & 1) ? s1 : s0;
                 difc = (P & 1) ? d1 : d0;
                 clk = 0;
@@ -314,8 +318,9 @@ __global__ void __launch_bounds__(SY_WARPS * 32) k_sync_frame(const float *__res
         S->prev_n = sym_total - base_g;
         nframes[c] = nfr < fcap ? nfr : (int)fcap;
         nevents[c] = nev < ecap ? nev : (int)ecap;
+        if (frame_rng) frame_rng[c] = make_int2(nfr_entry, nfr < fcap ? nfr : (int)fcap);   // records completed by this slice
         unsigned long long *q = stats + c * 8;
-        q[0] += (unsigned long long)nfr; q[4] += (unsigned long long)n_aos; q[5] += (unsigned long long)n_los;
-        q[7] += (unsigned long long)(sym_total - base_g);
+        q[0] += (unsigned long long)(nfr - nfr_entry); q[4] += (unsigned long long)n_aos; q[5] += (unsigned long long)n_los;
+        q[7] += (unsigned long long)(sym_total - sym_entry);
     }
 }

@@ -25,7 +25,7 @@ struct SyncCtaSmem {
 
 template <int NW, bool HAS_MEAN>
 __global__ void __launch_bounds__(NW * 32) k_sync_frame_cta(const float *__restrict__ disc, const float *__restrict__ mean, int64_t nchan, int64_t T,
-                                                            RxChanState *st, const float *__restrict__ g_mf, const float *__restrict__ g_md,
+                                                            int t0, int t1, int2 *frame_rng, RxChanState *st, const float *__restrict__ g_mf, const float *__restrict__ g_md,
                                                             float *syms, int64_t sym_pitch, int32_t *__restrict__ nsym, int32_t *__restrict__ sym_base,
                                                             m17b_frame_rec *frames, int64_t fcap, int32_t *__restrict__ nframes,
                                                             m17b_event_rec *events, int64_t ecap, int32_t *__restrict__ nevents,
@@ -40,15 +40,16 @@ __global__ void __launch_bounds__(NW * 32) k_sync_frame_cta(const float *__restr
     float *out = sm.hist + 8;
 
     // ---- load state: scalars are replicated in every thread (uniform loads), framer state is only used by warp 0
-    if (commit_fe && tid == 0) { S->z0re = S->nz0re; S->z0im = S->nz0im; S->z1re = S->nz1re; S->z1im = S->nz1im; }
+    if (commit_fe && tid == 0 && t1 == T) { S->z0re = S->nz0re; S->z0im = S->nz0im; S->z1re = S->nz1re; S->z1im = S->nz1im; }
     int clk = S->clk, thr = S->thr, index = S->index;
     float sumc = S->sum, difc = S->dif;
     int flock = S->flock, fclk = S->fclk, ferr = S->ferr, frame_start = S->frame_start, sym_total = S->sym_total;
-    const int base_g = sym_total;
+    const int base_g = t0 == 0 ? sym_total : sym_base[c];     // blocks [t0, t1) of the call: see sync.cuh
+    const int sym_entry = sym_total;
     if (tid < 30) ((tid & 1) ? sm.xo : sm.xe)[tid >> 1] = S->tail[tid];
     if (tid < 8) { sm.hist[tid] = S->win[tid]; sm.head[tid] = S->head[tid]; }
     float *sbuf = syms + c * sym_pitch;
-    {   // carry: the last 192 symbols of the previous call move in front of the new ones
+    if (t0 == 0) {   // carry: the last 192 symbols of the previous call move in front of the new ones
         const int prev_n = S->prev_n;
         float tmp[(192 + NT - 1) / NT];
 #pragma unroll
@@ -57,27 +58,28 @@ __global__ void __launch_bounds__(NW * 32) k_sync_frame_cta(const float *__restr
 #pragma unroll
         for (int k = 0; k < (192 + NT - 1) / NT; k++) { const int idx = tid + NT * k; if (idx < 192) sbuf[idx] = tmp[k]; }
     }
-    if (tid == 0) sym_base[c] = base_g;
-    int nfr = 0, nev = 0, n_aos = 0, n_los = 0;
+    if (tid == 0 && t0 == 0) sym_base[c] = base_g;
+    int nfr = t0 == 0 ? 0 : nframes[c], nev = t0 == 0 ? 0 : nevents[c], n_aos = 0, n_los = 0;
+    const int nfr_entry = nfr;
     f32x2 tp[M17B_FN];                      // (matched, derivative) tap pairs of the current polyphase branch
     int tap_index = -1;
     // the block's samples are fetched one block ahead
     float pf[NQ], pmu = 0.0f;
 #pragma unroll
-    for (int q = 0; q < NQ; q++) { const int j = tid + NT * q; pf[q] = j < 384 ? __ldg(disc + (c * T) * 384 + j) : 0.0f; }
-    if (HAS_MEAN) pmu = mean[c * T];
+    for (int q = 0; q < NQ; q++) { const int j = tid + NT * q; pf[q] = j < 384 ? __ldg(disc + (c * T + t0) * 384 + j) : 0.0f; }
+    if (HAS_MEAN) pmu = mean[c * T + t0];
     // staging slot of this thread: sample j = tid + NT*q lives at n = 30 + j; 30 and NT are even, so the parity is tid & 1
     float *stg = ((tid & 1) ? sm.xo : sm.xe) + ((30 + tid) >> 1);
     __syncthreads();
 
-    for (int64_t t = 0; t < T; t++) {
+    for (int64_t t = t0; t < t1; t++) {
 #pragma unroll
         for (int q = 0; q < NQ; q++) {
             float v = pf[q];
             if (HAS_MEAN) v = v - pmu;                                          // m17_dsp.cpp:217-219
             if (tid + NT * q < 384) stg[(NT / 2) * q] = v;
         }
-        if (t + 1 < T) {
+        if (t + 1 < t1) {
             const float *src = disc + (c * T + t + 1) * 384;
 #pragma unroll
             for (int q = 0; q < NQ; q++) { const int j = tid + NT * q; pf[q] = j < 384 ? __ldg(src + j) : 0.0f; }
@@ -265,8 +267,9 @@ __global__ void __launch_bounds__(NW * 32) k_sync_frame_cta(const float *__restr
         S->prev_n = sym_total - base_g;
         nframes[c] = nfr < fcap ? nfr : (int)fcap;
         nevents[c] = nev < ecap ? nev : (int)ecap;
+        if (frame_rng) frame_rng[c] = make_int2(nfr_entry, nfr < fcap ? nfr : (int)fcap);
         unsigned long long *q = stats + c * 8;
-        q[0] += (unsigned long long)nfr; q[4] += (unsigned long long)n_aos; q[5] += (unsigned long long)n_los;
-        q[7] += (unsigned long long)(sym_total - base_g);
+        q[0] += (unsigned long long)(nfr - nfr_entry); q[4] += (unsigned long long)n_aos; q[5] += (unsigned long long)n_los;
+        q[7] += (unsigned long long)(sym_total - sym_entry);
     }
 }

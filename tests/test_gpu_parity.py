@@ -9,7 +9,7 @@ import pytest
 import torch
 
 import gpu_check as gc
-from m17_oracles import REC_DTYPE
+from m17_oracles import REC_DTYPE, Port
 
 pytestmark = pytest.mark.gpu
 G = np.load(os.path.join(os.path.dirname(__file__), "golden", "m17_golden.npz"))
@@ -146,18 +146,38 @@ def test_full_size_properties(ctx):
     rx.m17_dsp_rx(iq)
     a = rx.results()
     pl = payload.cpu().numpy()
-    # every noise-free channel (sweep index 4) delivers frames 5..243 and every delivered payload is exact
-    for c in range(4, C, 5 * 8):
+    # loopback property: the noise-free channels (sweep index 4) deliver most of the 244 frames, and nearly all delivered
+    # payloads are what was sent.  (Not "all": with a +-1 kHz carrier offset the reference's own timing loop occasionally
+    # slips and costs a frame -- the oracle loses exactly the same frames, which is what the bit-exact comparison below pins.)
+    n_exact = n_late = 0
+    for c in range(4, C, 5):
         f = a["frames"][c, : a["nframes"][c]]
         dl = f[(f["type"] == 2) & ((f["flags"] & 8) != 0)]
         fn = (dl["data"][:, 0].astype(int) << 8) | dl["data"][:, 1]
-        assert len(dl) >= 220, (c, len(dl))      # 244 sent; delivery starts once six LICH chunks have arrived
-        late = np.nonzero(fn >= 12)[0]                       # the timing loop is still converging during the first frames
-        assert all(np.array_equal(dl["data"][i, 2:18], pl[c, fn[i]]) for i in late), c
+        assert len(dl) >= 190, (c, len(dl))      # 244 sent; delivery starts once six LICH chunks have arrived
+        late = np.nonzero((fn >= 12) & (fn < pl.shape[1]))[0]     # the timing loop is still converging during the first frames
+        n_late += len(late)
+        n_exact += sum(np.array_equal(dl["data"][i, 2:18], pl[c, fn[i]]) for i in late)
+    assert n_exact >= 0.995 * n_late, (n_exact, n_late)
+    # full-size parity: every 8th channel (all five noise levels), all 250 blocks, bit-exact against the oracle --
+    # discriminator samples, symbol stream, records, events
+    idx = np.arange(0, C, 8)
+    o = Port().rx_run(iq[torch.from_numpy(idx).cuda()].cpu().numpy(), seam=0)
+    sub = {k: (v[idx] if isinstance(v, np.ndarray) and v.shape[:1] == (C,) else v) for k, v in a.items()}
+    gc.compare_chain(sub, o, 0, len(idx))
     rx.reset()
     rx.m17_dsp_rx(iq)
     b = rx.results()
     assert np.array_equal(a["frames"].view(np.uint8), b["frames"].view(np.uint8)) and np.array_equal(a["nsym"], b["nsym"])   # idempotent
+    # the time-sliced pipeline (front end | timing loop | decode on three streams) must not change a single byte
+    for sb in (0, 7, 100):
+        rx.set_slice_blocks(sb)
+        rx.reset()
+        rx.m17_dsp_rx(iq)
+        b = rx.results()
+        assert np.array_equal(a["frames"].view(np.uint8), b["frames"].view(np.uint8)) and np.array_equal(a["nsym"], b["nsym"]), sb
+        assert np.array_equal(a["stats"], b["stats"]) and np.array_equal(a["events"], b["events"]) and gc.bits_eq(a["syms"], b["syms"]), sb
+    rx.set_slice_blocks(0)
     rx.reset()
     parts = [25] * 10
     nf = np.zeros(C, np.int64)
