@@ -32,7 +32,7 @@ extern "C" {
 #define M17B_E_ARG        -1   /* bad argument                                   */
 #define M17B_E_CUDA       -2   /* CUDA runtime error (see m17b_last_cuda_error)  */
 #define M17B_E_NOMEM      -3
-#define M17B_E_UNSUPPORTED -4  /* e.g. AFC on the block-parallel front end       */
+#define M17B_E_UNSUPPORTED -4  /* feature not available in this build             */
 #define M17B_E_CAPACITY   -5   /* nblocks exceeds the capacity given at create   */
 
 #define M17B_BLOCK_SAMPLES 1920   /* N_SAMPLES         m17defines.h:17 */
@@ -140,7 +140,9 @@ int m17b_rx_create(m17b_ctx *ctx, int64_t nchan, int64_t max_blocks, m17b_rx **o
 int m17b_rx_destroy(m17b_rx *rx);
 /* m17_rx_init + m17_rx_sync_init initial state for every channel (m17_rx_frame.cpp:183-186, m17_rx_sync.cpp:124-127) */
 int m17b_rx_reset(m17b_rx *rx, void *stream);
-/* radio_set_afc_on/off: only 'off' is supported by the block-parallel front end (returns M17B_E_UNSUPPORTED otherwise) */
+/* radio_set_afc_on / radio_set_afc_off (radio.cpp:146-152): with AFC on, m17b_dsp_rx runs dsp_nco_mixer + radio_afc
+   (m17_dsp.cpp:390-408, radio.cpp:196-208) and processes the blocks of a call one at a time (the loop is closed through the
+   framer); off (the reference default) uses the block-parallel front end.  No effect on m17b_rx_baseband. */
 int m17b_rx_set_afc(m17b_rx *rx, int on);
 /* m17_dsp_rx (m17_dsp.cpp:461-476) for nchan channels x nblocks blocks: d_iq = int16 [nchan][nblocks*1920][2] */
 int m17b_dsp_rx(m17b_rx *rx, const int16_t *d_iq, int64_t nblocks, void *stream);

@@ -46,6 +46,7 @@ void m17_dsp_rx(scmplx *in, int len);
 int  m17_rx_sync_samples(float *in, float *out, int len);
 void m17_rx_symbols(float *sym, int len);
 void m17_rx_init(void); void m17_rx_lost(void); bool m17_rx_lock(void);
+void radio_set_afc_on(void); void radio_set_afc_off(void); bool radio_get_afc_status(void);   // radio.cpp:146-155
 void m17_dsp_demap_frame(float *in, float *out);
 // FEC primitives
 int m17_punc_p1(uint8_t *in, uint8_t *out, int len); int m17_punc_p2(uint8_t *in, uint8_t *out, int len); int m17_punc_p3(uint8_t *in, uint8_t *out, int len);
@@ -97,6 +98,7 @@ struct State {
         return true;
     }
     bool ensure_tx() { if (!ensure()) return false; if (!tx && chk(m17b_tx_create(ctx, 1, os, &tx))) return false; return true; }
+    bool afc = false;
     bool scratch(size_t bytes) {
         if (bytes <= cap) return true;
         cudaFree(dA); cudaFree(dB); cudaFree(dC);
@@ -165,6 +167,9 @@ void m17_mod_init(void) { m17b_shim::S().ensure_tx(); }
 void m17_rx_init(void) { m17_rx_sync_init(); }
 void m17_rx_lost(void) { m17_rx_sync_init(); }
 bool m17_rx_lock(void) { return m17b_shim::S().lock; }
+void radio_set_afc_on(void) { auto &s = m17b_shim::S(); if (s.ensure() && !s.chk(m17b_rx_set_afc(s.rx, 1))) s.afc = true; }
+void radio_set_afc_off(void) { auto &s = m17b_shim::S(); if (s.ensure() && !s.chk(m17b_rx_set_afc(s.rx, 0))) s.afc = false; }
+bool radio_get_afc_status(void) { return m17b_shim::S().afc; }
 
 void m17_dsp_build_rrc_filter(float *f, float rolloff, int ntaps, int sps) { m17b_build_rrc_filter(f, rolloff, ntaps, sps); }
 void m17_dsp_set_filter_gain(float *f, float gain, int stride, int ntaps) { m17b_set_filter_gain(f, gain, stride, ntaps); }

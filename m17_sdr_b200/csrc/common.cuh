@@ -71,6 +71,10 @@ struct m17b_ctx {
 // ---------------------------------------------------------------- per-channel persistent RX state
 // Everything the reference keeps in file statics for one channel (SURVEY 8b "persistent state").
 struct RxChanState {
+    // AFC: NCO phase (dsp_nco_mixer's static acc, m17_dsp.cpp:391) and loop state m_afc_delta (radio.cpp:9); afc.cuh
+    double nco_acc;
+    float afc_delta;
+    int   afc_pad;
     // front end: dsp_arctan_disc2 statics (m17_dsp.cpp:195-196)
     float z0re, z0im, z1re, z1im;
     float nz0re, nz0im, nz1re, nz1im;   // written by the front-end kernel, committed by the sync kernel (no read/write race

@@ -8,7 +8,7 @@
 //   k_decode_frames (thread per frame)                            -> decoded bytes, Golay, CRC into the records
 //   k_post          (thread per channel, frames in order)         -> LICH cache, delivery / LSF-event flags, stats
 #pragma once
-#include "sync_cta.cuh"
+#include "afc.cuh"
 
 #define M17B_TIMING_RING 64
 #define M17B_MAX_SLICES 16
@@ -228,11 +228,16 @@ extern "C" int m17b_rx_create(m17b_ctx *ctx, int64_t nchan, int64_t max_blocks, 
     return M17B_OK;
 }
 
+// radio_set_afc_on / radio_set_afc_off (radio.cpp:146-152).  With AFC on, m17b_dsp_rx alternates the AFC front end
+// (afc.cuh) and the sync/framer kernel one block at a time, because the NCO step of a block depends on the framer state and
+// the discriminator mean of the block before it.
 extern "C" int m17b_rx_set_afc(m17b_rx *rx, int on) {
     if (!rx) return M17B_E_ARG;
-    // dsp_nco_mixer + radio_afc (m17_dsp.cpp:390-408, radio.cpp:196-208) make the front end block-serial; not built yet
-    if (on) return M17B_E_UNSUPPORTED;
-    rx->afc = 0;
+    if (!on && rx->afc) {
+        k_afc_off<<<grid_for(rx->nchan, 128), 128>>>(rx->d_state, rx->nchan);
+        KERNEL_CHECK();
+    }
+    rx->afc = on != 0;
     return M17B_OK;
 }
 
@@ -280,6 +285,27 @@ static int rx_pipeline(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t *d_iq,
     int64_t sb = rx->slice_blocks;
     int nsl = (sb > 0 && !rx->timing && allow_slices) ? (int)((T + sb - 1) / sb) : 1;
     if (nsl > M17B_MAX_SLICES) { nsl = M17B_MAX_SLICES; }
+    if (rx->afc && d_iq) {
+        // block-serial loop: AFC front end of block t, then timing loop + framer of block t (which decides in_frame for t+1)
+        STAGE_MARK(0);
+        STAGE_MARK(1);
+        for (int64_t t = 0; t < T; t++) {
+            k_frontend_afc<<<grid_for(nc, AFC_WARPS), AFC_WARPS * 32, AFC_WARPS * sizeof(AfcWarpSmem), st>>>((const uint32_t *)d_iq, nc, T, t, rx->d_state + c0, disc_w, mean_w);
+            KERNEL_CHECK();
+            int rc = launch_sync(rx, c0, nc, disc, mean, T, (int)t, (int)t + 1, nullptr, 0, st);
+            if (rc) return rc;
+        }
+        STAGE_MARK(2);
+        int rc = launch_decode(ctx, syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0, nc, nullptr, st,
+                               rx->aux_stream, rx->ev_fork, rx->ev_join);
+        if (rc) return rc;
+        STAGE_MARK(3);
+        k_post<<<grid_for(nc, POST_WARPS), POST_WARPS * 32, 0, st>>>(frames, rx->fcap, rx->d_nframes + c0, nc, rx->d_state + c0, ctx->d_crc, rx->d_stats + c0 * 8);
+        KERNEL_CHECK();
+        STAGE_MARK(4);
+        rx->last_launches += (int)(2 * T) + 3;
+        return M17B_OK;
+    }
     if (nsl < 2) {
         STAGE_MARK(0);
         if (d_iq) {
@@ -339,7 +365,6 @@ static int rx_pipeline(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t *d_iq,
 extern "C" int m17b_dsp_rx(m17b_rx *rx, const int16_t *d_iq, int64_t nblocks, void *stream) {
     if (!rx || !d_iq || nblocks <= 0) return M17B_E_ARG;
     if (nblocks > rx->max_blocks) return M17B_E_CAPACITY;
-    if (rx->afc) return M17B_E_UNSUPPORTED;
     rx->last_launches = 0; rx->last_blocks = nblocks; rx->seam_last = 0;
     int rc = rx_pipeline(rx, 0, rx->nchan, d_iq, nullptr, nblocks, as_stream(stream));
     if (rx->timing) rx->tcount++;
@@ -401,7 +426,6 @@ extern "C" int m17b_rx_last_launches(const m17b_rx *rx) { return rx ? rx->last_l
 extern "C" int m17b_dsp_rx_host(m17b_rx *rx, const int16_t *h_iq, int64_t nblocks, m17b_frame_rec *h_frames, int32_t *h_nframes, void *stream) {
     if (!rx || !h_iq || !h_frames || !h_nframes || nblocks <= 0) return M17B_E_ARG;
     if (nblocks > rx->max_blocks) return M17B_E_CAPACITY;
-    if (rx->afc) return M17B_E_UNSUPPORTED;
     cudaStream_t st = as_stream(stream);
     const int64_t T = nblocks;
     if (!rx->copy_stream) {

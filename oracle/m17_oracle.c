@@ -703,7 +703,8 @@ static void *job_main(void *p) {
         m17o_rx_trace(r, j->disc ? j->disc + c * j->T * 384 : 0, j->nsym ? j->nsym + c * j->T : 0,
                       j->syms ? j->syms + c * j->symcap : 0, j->symcap, j->frames ? j->frames + c * j->fcap : 0, j->fcap,
                       j->soft ? j->soft + c * j->fcap * 368 : 0, j->events ? j->events + c * j->ecap : 0, j->ecap);
-        if (j->seam == 0) { const int16_t *iq = (const int16_t *)j->in + c * j->T * 3840; for (long t = 0; t < j->T; t++) m17o_dsp_rx(r, iq + t * 3840, 1920); }
+        if (j->seam & 16) m17o_rx_set_afc(r, 1);          /* seam flag 16: AFC on (radio_set_afc_on, radio.cpp:146-148) */
+        if ((j->seam & 15) == 0) { const int16_t *iq = (const int16_t *)j->in + c * j->T * 3840; for (long t = 0; t < j->T; t++) m17o_dsp_rx(r, iq + t * 3840, 1920); }
         else { const float *d = (const float *)j->in + c * j->T * 384; for (long t = 0; t < j->T; t++) m17o_rx_baseband(r, d + t * 384, 384); }
         if (j->counts) m17o_rx_counts(r, j->counts + c * 4);
         m17o_rx_free(r);

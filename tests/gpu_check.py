@@ -227,7 +227,34 @@ def compare_chain(res, o, seam, Cn, verbose=False):
     assert not msgs, msgs[:4]
 
 
-def run_chain(ctx, X, seam=0, split=None):
+def check_rx_afc(ctx, P, seed=31, nchan=12, nframes=30):
+    """AFC on (dsp_nco_mixer + radio_afc): records and events exact; discriminator samples / symbols bit-identical unless a
+    double sincos result fell on a float rounding boundary (CUDA libm vs glibc), then within 1e-5 relative RMS."""
+    X, _ = signals.stream_channels(P, nchan, nframes, seed, ebn0=[None, 30, 26, 24, None, 28] * 2, f0_max=1800.0)
+    o = P.rx_run(X, seam=0, afc=True)
+    for split in (None, [7, 1, 13]):
+        res = run_chain(ctx, X, 0, split, afc=True)
+        disc = res["disc_raw"] - res["mean"][:, :, None]
+        exact = bits_eq(disc, o.disc)
+        rel = float(np.sqrt(np.mean((disc.astype(np.float64) - o.disc) ** 2) / np.mean(o.disc.astype(np.float64) ** 2)))
+        assert rel < 1e-5, ("afc disc rms", rel)
+        if exact:
+            compare_chain(res, o, 0, nchan)
+        else:                                   # one-ulp sincos difference somewhere: decisions must still agree
+            assert np.array_equal(res["nsym"], o.nsym)
+            for c in range(nchan):
+                nf = int(o.counts[c, 2]); ns = int(o.counts[c, 1])
+                assert int(res["nframes"][c]) == nf
+                for name in ("sym_off", "type", "flags", "golay_err", "nbytes", "lich", "data", "crc", "votes", "frame_errors"):
+                    assert bits_eq(res["frames"][c, :nf][name], o.frames[c, :nf][name]), (name, c)
+                a, b = res["syms"][c, :ns].astype(np.float64), o.syms[c, :ns].astype(np.float64)
+                assert np.sqrt(np.mean((a - b) ** 2) / max(np.mean(b ** 2), 1e-30)) < 1e-5
+    off = run_chain(ctx, X, 0)
+    assert not bits_eq(off["disc_raw"], res["disc_raw"])       # the loop really acted
+    return "rx afc ok (%d ch, bit-identical=%s, rel rms %.1e, %d frames)" % (nchan, exact, rel, int(o.counts[:, 2].sum()))
+
+
+def run_chain(ctx, X, seam=0, split=None, afc=False):
     """Run the CUDA chain over X; split = list of block counts to process in successive calls (state carry)."""
     import m17_sdr_b200 as m
     Cn = X.shape[0]
@@ -238,6 +265,8 @@ def run_chain(ctx, X, seam=0, split=None):
     if sum(parts) < T:
         parts.append(T - sum(parts))
     rx = m.Rx(ctx, Cn, max(parts))
+    if afc:
+        rx.set_afc(True)
     out = []
     t0 = 0
     for nb in parts:
@@ -420,6 +449,7 @@ CHECKS = [
     ("rx_chain", lambda c, P: check_rx_chain(c, P, verbose=True)),
     ("rx_chain_split", lambda c, P: check_rx_chain(c, P, nchan=6, seed=23, verbose=True, split=[1, 7, 2, 1, 13])),
     ("rx_packet", lambda c, P: check_rx_packet(c, P, verbose=True)),
+    ("rx_afc", lambda c, P: check_rx_afc(c, P)),
     ("tx", lambda c, P: check_tx(c, P)),
     ("tx_os80", lambda c, P: check_tx(c, P, nchan=2, F=3, os_=80)),
     ("equalizer", lambda c, P: check_equalizer(c, P)),

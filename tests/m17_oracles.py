@@ -328,7 +328,7 @@ class Port:
         return (iq, freq) if want_freq else iq
 
     # ---- RX
-    def rx_run(self, x, seam=0, nthreads=None, want_disc=True, want_soft=False):
+    def rx_run(self, x, seam=0, nthreads=None, want_disc=True, want_soft=False, afc=False):
         x = np.ascontiguousarray(x)
         if seam == 0:
             assert x.dtype == np.int16 and x.ndim == 3 and x.shape[2] == 2 and x.shape[1] % BLOCK == 0
@@ -338,7 +338,7 @@ class Port:
             Cn, T = x.shape[0], x.shape[1] // DISC_PER_BLOCK
         o = _alloc_rx_out(Cn, T, want_disc, want_soft, np.zeros)
         nthreads = nthreads or min(os.cpu_count() or 1, Cn)
-        self.L.m17o_rx_run(_p(x), seam, Cn, T, nthreads, _p(o.disc), _p(o.nsym), _p(o.syms), o.symcap, _p(o.frames), o.fcap,
+        self.L.m17o_rx_run(_p(x), seam | (16 if afc else 0), Cn, T, nthreads, _p(o.disc), _p(o.nsym), _p(o.syms), o.symcap, _p(o.frames), o.fcap,
                            _p(o.soft), _p(o.events), o.ecap, _p(o.counts))
         return o
 
@@ -574,8 +574,9 @@ class Ref:
         n = int(nout.min())
         return np.array(iq[:, :n])
 
-    def rx_run(self, x, seam=0, nproc=None, want_disc=True, want_soft=False):
+    def rx_run(self, x, seam=0, nproc=None, want_disc=True, want_soft=False, afc=False):
         x = np.ascontiguousarray(x)
+        self.L.ref_set_afc(1 if afc else 0)           # inherited by the per-channel child processes
         if seam == 0:
             Cn, T = x.shape[0], x.shape[1] // BLOCK
         else:
@@ -583,6 +584,7 @@ class Ref:
         o = _alloc_rx_out(Cn, T, want_disc, want_soft, shared_array)
         fails = self.L.ref_rx_run(_p(x), seam, Cn, T, nproc or os.cpu_count(), _p(o.disc), _p(o.nsym), _p(o.syms), o.symcap,
                                   _p(o.frames), o.fcap, _p(o.soft), _p(o.events), o.ecap, _p(o.counts))
+        self.L.ref_set_afc(0)
         assert fails == 0, "a reference child process crashed"
         return o
 

@@ -130,9 +130,12 @@ def test_edge_cases(ctx, port):
     rx = m.Rx(ctx, 2, 2)
     with pytest.raises(m.M17Error):
         rx.m17_dsp_rx(torch.zeros((2, 3 * 1920, 2), dtype=torch.int16, device="cuda"))
-    with pytest.raises(m.M17Error):
-        rx.set_afc(True)
     rx.close()
+
+
+def test_rx_chain_afc(ctx, port):
+    """m17_dsp_rx with radio_set_afc_on(): NCO mixer + AFC loop closed through the framer, block-serial path."""
+    print(gc.check_rx_afc(ctx, port))
 
 
 def test_full_size_properties(ctx):

@@ -53,3 +53,14 @@ def test_rx_chain_random(port, ref):
 def test_rx_baseband_sweep(port, ref):
     D, _ = signals.baseband_channels(port, 8, 16, 104, [None, 12, 10, 8, 6, 4, 2, 0])
     compare_rx(port.rx_run(D, seam=1), ref.rx_run(D, seam=1))
+
+
+def test_rx_chain_afc(port, ref):
+    """AFC on (dsp_nco_mixer + radio_afc, m17_dsp.cpp:390-408, radio.cpp:196-208): the restatement follows the reference's
+    NCO phase, delta updates gated by in_frame, and everything downstream bit for bit."""
+    X, _ = signals.stream_channels(port, 8, 24, 105, ebn0=[None, 30, 26, 24, None, 28, 24, 22], f0_max=1800.0)
+    a, b = port.rx_run(X, afc=True), ref.rx_run(X, afc=True)
+    assert feq(a.disc, b.disc)
+    compare_rx(a, b)
+    off = port.rx_run(X)
+    assert not feq(a.disc, off.disc)          # the NCO really moved the spectrum once a frame was acquired
