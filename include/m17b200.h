@@ -205,6 +205,37 @@ int m17b_fmt_bert_frames(m17b_tx *tx, int64_t F, uint8_t *d_dibits, void *stream
    -> d_iq int16 [nchan][nsym*os][2]; d_freq (optional) float [nchan][nsym*os] = the filtered deviation m_sum */
 int m17b_mod_dibits(m17b_tx *tx, const uint8_t *d_syms, int64_t nsym, int16_t *d_iq, float *d_freq, void *stream);
 
+/* ------------------------------------------------------------------ Pluto front-end decimator */
+typedef struct m17b_dec m17b_dec;   /* per-batch decimator state: the 31-sample history m_rx_buff carries (radio.cpp:15,167) */
+/* m17_dsp_build_lpf_filter (m17_dsp.cpp:347-360) and m17_dsp_float_to_short (m17_dsp.cpp:382-386), host side */
+int m17b_build_lpf_filter(float *h_taps, float bw, int ntaps);
+int m17b_float_to_short(const float *h_in, int16_t *h_out, int len);
+/* build_pluto_rx_dec_filter (radio.cpp:44-51) + zeroed m_rx_buff */
+int m17b_dec_create(m17b_ctx *ctx, int64_t nchan, m17b_dec **out);
+int m17b_dec_destroy(m17b_dec *dec);
+int m17b_dec_reset(m17b_dec *dec, void *stream);
+int m17b_dec_get_taps(const m17b_dec *dec, int16_t *h_taps31);
+/* radio_receive_samples, Pluto branch: rx_decimate_filter / sub_filter (radio.cpp:18-40,157-177) for nchan channels.
+   d_in int16 [nchan][8*nout][2] at 384 kS/s -> d_out int16 [nchan][nout][2] at 48 kS/s (nout a multiple of 4; the
+   reference produces 240 per 1920-sample chunk); the 31-sample filter history carries over from call to call */
+int m17b_dec_run(m17b_dec *dec, const int16_t *d_in, int64_t nout, int16_t *d_out, void *stream);
+
+/* ------------------------------------------------------------------ M17-over-UDP reflector frame */
+#define M17B_NET_FRAME_BYTES 54
+/* net_add_magic/_stream_id/_lich/_fn/_payload/_crc (m17_net.cpp:25-49), build_lich_to_net + m17_send_stream_frame_to_net
+   (m17_tx_routines.cpp:54-70,298-306): n frames.  d_lsf: LSF bytes (>= 28 used) lsf_stride apart; have_dst != 0 replaces the
+   destination call with dst (the gateway's "<reflector> <module>" address, m17_net.cpp:56-61).  d_out [n][54] */
+int m17b_net_pack(m17b_ctx *ctx, const uint16_t *d_sid, const uint8_t *d_lsf, int64_t lsf_stride, int have_dst, uint64_t dst,
+                  const uint16_t *d_fn, const uint8_t *d_payload, int64_t n, uint8_t *d_out, void *stream);
+/* m17_parse_m17_data (m17_net.cpp:203-238) + build_lich_from_net (m17_tx_routines.cpp:71-86): d_in [n][54] -> d_ok [n]
+   (magic and CRC over all 54 bytes), stream id, the 30-byte LSF the TX side uses (bytes 6..33 + fresh CRC), FN, payload [n][16] */
+int m17b_net_parse(m17b_ctx *ctx, const uint8_t *d_in, int64_t n, uint8_t *d_ok, uint16_t *d_sid, uint8_t *d_lsf30, uint16_t *d_fn,
+                   uint8_t *d_payload, void *stream);
+/* m17_net_new_rx_data for the last m17b_dsp_rx / m17b_rx_baseband call (m17_rx_parse.cpp:148-154): every DELIVERED stream
+   record of channel c becomes one datagram with the link-setup data that was valid when it was parsed, stream id d_sid[c].
+   d_out [nchan][frame_cap][54] (datagrams of a channel packed from slot 0 in record order), d_count [nchan] */
+int m17b_rx_net_frames(m17b_rx *rx, const uint16_t *d_sid, int have_dst, uint64_t dst, uint8_t *d_out, int32_t *d_count, void *stream);
+
 /* ------------------------------------------------------------------ equaliser (m17_equalize.cpp) */
 int m17b_eq_create(m17b_ctx *ctx, int64_t nchan, m17b_eq **out);   /* eq_open  :217-224 */
 int m17b_eq_destroy(m17b_eq *eq);

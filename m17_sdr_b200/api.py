@@ -86,6 +86,25 @@ class Context:
         _l.check(self.L.m17b_get_sync_taps(self.h, mf.ctypes.data_as(C.c_void_p), md.ctypes.data_as(C.c_void_p)))
         return mf, md
 
+    # ---- M17-over-UDP reflector frames (m17_net.cpp:25-74,203-238; m17_tx_routines.cpp:54-86,298-306)
+    def net_pack(self, sid, lsf, fn, payload, dst=None):
+        """sid uint16 [n], lsf uint8 [n][>=28], fn uint16 [n], payload uint8 [n][16] -> uint8 [n][54] datagrams."""
+        _chk_dev(sid, torch.uint16, "sid"); _chk_dev(lsf, torch.uint8, "lsf"); _chk_dev(fn, torch.uint16, "fn"); _chk_dev(payload, torch.uint8, "payload")
+        n = sid.shape[0]
+        out = self._new((n, 54), torch.uint8)
+        _l.check(self.L.m17b_net_pack(self.h, _ptr(sid), _ptr(lsf), lsf.shape[1], 0 if dst is None else 1, int(dst or 0), _ptr(fn), _ptr(payload), n,
+                                      _ptr(out), _stream()))
+        return out
+
+    def net_parse(self, frames):
+        """uint8 [n][54] -> (ok uint8 [n], sid uint16 [n], lsf uint8 [n][30], fn uint16 [n], payload uint8 [n][16])."""
+        _chk_dev(frames, torch.uint8, "frames")
+        n = frames.shape[0]
+        ok, sid, lsf = self._new((n,), torch.uint8), self._new((n,), torch.uint16), self._new((n, 30), torch.uint8)
+        fn, pld = self._new((n,), torch.uint16), self._new((n, 16), torch.uint8)
+        _l.check(self.L.m17b_net_parse(self.h, _ptr(frames), n, _ptr(ok), _ptr(sid), _ptr(lsf), _ptr(fn), _ptr(pld), _stream()))
+        return ok, sid, lsf, fn, pld
+
     # ---- bit-domain primitives (CUDA tensors in, CUDA tensors out)
     def m17_crc_array_encode(self, data):
         _chk_dev(data, torch.uint8, "data")
@@ -272,6 +291,15 @@ class Rx:
         _l.check(self.L.m17b_dsp_rx_host(self.h, _ptr(iq_host), nblocks, _ptr(frames_host), _ptr(nframes_host), _stream()))
         return frames_host, nframes_host
 
+    def m17_net_new_rx_data(self, sid, dst=None):
+        """Gateway output of the last call: every delivered stream frame as a 54-byte M17-over-UDP datagram.
+        sid uint16 [nchan] -> (uint8 [nchan][frame_cap][54], count int32 [nchan])."""
+        _chk_dev(sid, torch.uint16, "sid")
+        out = torch.empty((self.nchan, self.frame_cap, 54), dtype=torch.uint8, device=sid.device)
+        cnt = torch.empty((self.nchan,), dtype=torch.int32, device=sid.device)
+        _l.check(self.L.m17b_rx_net_frames(self.h, _ptr(sid), 0 if dst is None else 1, int(dst or 0), _ptr(out), _ptr(cnt), _stream()))
+        return out, cnt
+
     def set_slice_blocks(self, blocks):
         """Blocks per pipeline slice (0 = run the stages strictly in sequence); results do not depend on it."""
         _l.check(self.L.m17b_rx_set_slice_blocks(self.h, int(blocks)))
@@ -394,6 +422,38 @@ class Tx:
         freq = torch.empty((self.nchan, nsym * self.os), dtype=torch.float32, device=syms.device) if want_freq else None
         _l.check(self.L.m17b_mod_dibits(self.h, _ptr(syms), nsym, _ptr(iq), _ptr(freq), _stream()))
         return (iq, freq) if want_freq else iq
+
+
+class Decimator:
+    """Batched Pluto front-end decimator: radio_receive_samples' /8 int16 FIR (radio.cpp:18-51,157-177)."""
+
+    def __init__(self, ctx, nchan):
+        self.ctx, self.L, self.nchan = ctx, ctx.L, nchan
+        h = C.c_void_p()
+        _l.check(self.L.m17b_dec_create(ctx.h, nchan, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.L.m17b_dec_destroy(self.h)
+            self.h = None
+
+    def reset(self):
+        _l.check(self.L.m17b_dec_reset(self.h, _stream()))
+
+    def taps(self):
+        t = np.zeros(31, np.int16)
+        _l.check(self.L.m17b_dec_get_taps(self.h, t.ctypes.data_as(C.c_void_p)))
+        return t
+
+    def radio_receive_samples(self, iq384):
+        """iq384: int16 CUDA tensor [nchan][8*nout][2] at 384 kS/s -> int16 [nchan][nout][2] at 48 kS/s."""
+        _chk_dev(iq384, torch.int16, "iq384")
+        assert iq384.shape[0] == self.nchan and iq384.shape[1] % 32 == 0 and iq384.shape[2] == 2
+        nout = iq384.shape[1] // 8
+        out = torch.empty((self.nchan, nout, 2), dtype=torch.int16, device=iq384.device)
+        _l.check(self.L.m17b_dec_run(self.h, _ptr(iq384), nout, _ptr(out), _stream()))
+        return out
 
 
 class Equalizer:

@@ -8,7 +8,7 @@
 //   k_decode_frames (thread per frame)                            -> decoded bytes, Golay, CRC into the records
 //   k_post          (thread per channel, frames in order)         -> LICH cache, delivery / LSF-event flags, stats
 #pragma once
-#include "afc.cuh"
+#include "dec.cuh"
 
 #define M17B_TIMING_RING 64
 #define M17B_MAX_SLICES 16
@@ -23,6 +23,8 @@ struct m17b_rx {
     m17b_frame_rec *d_frames;
     m17b_event_rec *d_events;
     unsigned long long *d_stats;
+    uint8_t *d_lsf_snap, *d_lsf_ver;  // [nchan][nsnap][32] link-setup data as it stood (version 0 = at the start of the call), [nchan][fcap] version per record
+    int nsnap;
     int16_t *d_iq_stage[2];           // staging for the _host entry point (double buffered over channel chunks)
     int64_t stage_chunk;
     cudaStream_t copy_stream, aux_stream;   // aux: LSF/packet/BERT frame decode runs beside the stream-frame decode
@@ -57,9 +59,13 @@ __global__ void k_rx_reset(RxChanState *st, int64_t nchan) {
 // actually changes the cache -- while a stream runs the same six chunks repeat, so the cached verdict is reused
 // (identical result: the CRC is a pure function of the 30 bytes).
 #define POST_WARPS 4
-struct PostWarpSmem { uint4 hdr[32]; uint8_t lsf0[32], lsf1[32]; };
+// For the M17-over-UDP gateway output (net.cuh) the kernel also keeps the history of the validated link-setup data m_lsf[1]
+// over the call: snapshot 0 is the cache as the call found it, a new snapshot is taken whenever copy_lich() changes it, and
+// every record gets the number of the snapshot that was current when it was parsed.
+struct PostWarpSmem { uint4 hdr[32]; uint8_t lsf0[32], lsf1[32], ver[32]; };
 __global__ void __launch_bounds__(POST_WARPS * 32) k_post(m17b_frame_rec *frames, int64_t fcap, const int32_t *__restrict__ nframes, int64_t nchan,
-                                                          RxChanState *st, const uint16_t *__restrict__ g_crc, unsigned long long *stats) {
+                                                          RxChanState *st, const uint16_t *__restrict__ g_crc, unsigned long long *stats,
+                                                          uint8_t *__restrict__ lsf_snap, int nsnap, uint8_t *__restrict__ lsf_ver) {
     __shared__ uint16_t tab[256];
     __shared__ PostWarpSmem sm_all[POST_WARPS];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = g_crc[i];
@@ -75,6 +81,10 @@ __global__ void __launch_bounds__(POST_WARPS * 32) k_post(m17b_frame_rec *frames
     auto crc30 = [&](const uint8_t *p) { uint16_t k = 0xFFFF; for (int i = 0; i < 30; i++) k = crc16_step(k, p[i], tab); return k; };
     bool lsf0_ok = false, lsf1_ok = false;
     if (lane == 0) { lsf0_ok = crc30(sm.lsf0) == 0; lsf1_ok = crc30(sm.lsf1) == 0; }
+    uint8_t *snap = lsf_snap + c * (int64_t)nsnap * 32;
+    snap[lane] = sm.lsf1[lane];                                               // snapshot 0
+    bool dirty = __any_sync(0xffffffffu, lane < 30 && sm.lsf0[lane] != sm.lsf1[lane]);
+    int ver = 0;
     unsigned long long n_stream = 0, n_gerr = 0, n_deliv = 0, n_lsf = 0;
     const int n = nframes[c];
     m17b_frame_rec *base = frames + c * fcap;
@@ -103,10 +113,15 @@ __global__ void __launch_bounds__(POST_WARPS * 32) k_post(m17b_frame_rec *frames
                     if (seq < 6) {
                         bool changed = false;
                         for (int i = 0; i < 5; i++) { changed |= sm.lsf0[seq * 5 + i] != l[i]; sm.lsf0[seq * 5 + i] = l[i]; }
-                        if (changed) lsf0_ok = crc30(sm.lsf0) == 0;
+                        if (changed) { lsf0_ok = crc30(sm.lsf0) == 0; dirty = true; }
                         if (lsf0_ok) {
                             for (int i = 0; i < 30; i++) sm.lsf1[i] = sm.lsf0[i];       // copy_lich
                             lsf1_ok = true;
+                            if (dirty) {
+                                if (ver < nsnap - 1) ver++;
+                                for (int i = 0; i < 32; i++) snap[ver * 32 + i] = i < 30 ? sm.lsf0[i] : 0;
+                                dirty = false;
+                            }
                             flags |= M17B_F_LSF_EVENT; n_lsf++;
                         }
                     }
@@ -125,10 +140,15 @@ __global__ void __launch_bounds__(POST_WARPS * 32) k_post(m17b_frame_rec *frames
                     }
                 }
                 sm.hdr[j].y = (q.y & 0xFFFF00FFu) | ((uint32_t)flags << 8);
+                sm.ver[j] = (uint8_t)ver;
             }
         }
         __syncwarp();
-        if (k < n) { const uint32_t y = sm.hdr[lane].y; if (y != h.y) ((uint8_t *)(base + k))[5] = (uint8_t)(y >> 8); }
+        if (k < n) {
+            const uint32_t y = sm.hdr[lane].y;
+            if (y != h.y) ((uint8_t *)(base + k))[5] = (uint8_t)(y >> 8);
+            lsf_ver[c * fcap + k] = (y >> 8) & M17B_F_PARSED ? sm.ver[lane] : 0;
+        }
         __syncwarp();
     }
     S->lsf[0][lane] = sm.lsf0[lane];
@@ -148,7 +168,7 @@ extern "C" int m17b_rx_destroy(m17b_rx *rx) {
         if (rx->ev_h2d[i]) cudaEventDestroy(rx->ev_h2d[i]);
         if (rx->ev_done[i]) cudaEventDestroy(rx->ev_done[i]);
     }
-    cudaFree(rx->d_frame_rng);
+    cudaFree(rx->d_frame_rng); cudaFree(rx->d_lsf_snap); cudaFree(rx->d_lsf_ver);
     if (rx->s_fe) cudaStreamDestroy(rx->s_fe);
     if (rx->s_sync) cudaStreamDestroy(rx->s_sync);
     if (rx->s_dec) cudaStreamDestroy(rx->s_dec);
@@ -202,6 +222,10 @@ extern "C" int m17b_rx_create(m17b_ctx *ctx, int64_t nchan, int64_t max_blocks, 
     A((void **)&rx->d_events, sizeof(m17b_event_rec) * nchan * rx->ecap);
     A((void **)&rx->d_stats, sizeof(unsigned long long) * nchan * 8);
     A((void **)&rx->d_frame_rng, sizeof(int2) * nchan * M17B_MAX_SLICES);
+    rx->nsnap = (int)(max_blocks / 6 + 2);        // a new LSF needs six LICH chunks = six frames
+    if (rx->nsnap > 255) rx->nsnap = 255;
+    A((void **)&rx->d_lsf_snap, (size_t)nchan * rx->nsnap * 32);
+    A((void **)&rx->d_lsf_ver, (size_t)nchan * rx->fcap);
     if (e != cudaSuccess) { m17b_set_cuda_error(e, __FILE__, __LINE__); m17b_rx_destroy(rx); return e == cudaErrorMemoryAllocation ? M17B_E_NOMEM : M17B_E_CUDA; }
     CUDA_TRY(cudaStreamCreateWithFlags(&rx->aux_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&rx->ev_fork, cudaEventDisableTiming));
@@ -300,7 +324,8 @@ static int rx_pipeline(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t *d_iq,
                                rx->aux_stream, rx->ev_fork, rx->ev_join);
         if (rc) return rc;
         STAGE_MARK(3);
-        k_post<<<grid_for(nc, POST_WARPS), POST_WARPS * 32, 0, st>>>(frames, rx->fcap, rx->d_nframes + c0, nc, rx->d_state + c0, ctx->d_crc, rx->d_stats + c0 * 8);
+        k_post<<<grid_for(nc, POST_WARPS), POST_WARPS * 32, 0, st>>>(frames, rx->fcap, rx->d_nframes + c0, nc, rx->d_state + c0, ctx->d_crc, rx->d_stats + c0 * 8,
+                                                                  rx->d_lsf_snap + c0 * rx->nsnap * 32, rx->nsnap, rx->d_lsf_ver + c0 * rx->fcap);
         KERNEL_CHECK();
         STAGE_MARK(4);
         rx->last_launches += (int)(2 * T) + 3;
@@ -321,7 +346,8 @@ static int rx_pipeline(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t *d_iq,
                            rx->aux_stream, rx->ev_fork, rx->ev_join);
         if (rc) return rc;
         STAGE_MARK(3);
-        k_post<<<grid_for(nc, POST_WARPS), POST_WARPS * 32, 0, st>>>(frames, rx->fcap, rx->d_nframes + c0, nc, rx->d_state + c0, ctx->d_crc, rx->d_stats + c0 * 8);
+        k_post<<<grid_for(nc, POST_WARPS), POST_WARPS * 32, 0, st>>>(frames, rx->fcap, rx->d_nframes + c0, nc, rx->d_state + c0, ctx->d_crc, rx->d_stats + c0 * 8,
+                                                                  rx->d_lsf_snap + c0 * rx->nsnap * 32, rx->nsnap, rx->d_lsf_ver + c0 * rx->fcap);
         KERNEL_CHECK();
         STAGE_MARK(4);
         rx->last_launches += 4;       // sync/framer, two decode kernels, post
@@ -353,7 +379,8 @@ static int rx_pipeline(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t *d_iq,
         if (rc) return rc;
         rx->last_launches += 3;
     }
-    k_post<<<grid_for(nc, POST_WARPS), POST_WARPS * 32, 0, rx->s_dec>>>(frames, rx->fcap, rx->d_nframes + c0, nc, rx->d_state + c0, ctx->d_crc, rx->d_stats + c0 * 8);
+    k_post<<<grid_for(nc, POST_WARPS), POST_WARPS * 32, 0, rx->s_dec>>>(frames, rx->fcap, rx->d_nframes + c0, nc, rx->d_state + c0, ctx->d_crc, rx->d_stats + c0 * 8,
+                                                                  rx->d_lsf_snap + c0 * rx->nsnap * 32, rx->nsnap, rx->d_lsf_ver + c0 * rx->fcap);
     KERNEL_CHECK();
     rx->last_launches += 1;
     CUDA_TRY(cudaEventRecord(rx->ev_end, rx->s_dec));

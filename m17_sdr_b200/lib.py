@@ -68,6 +68,16 @@ _SIGS = {
     "m17b_fmt_packet_frames": ([_vp, _vp, _vp, _i64, _vp, _vp], _i32),
     "m17b_fmt_bert_frames": ([_vp, _i64, _vp, _vp], _i32),
     "m17b_mod_dibits": ([_vp, _vp, _i64, _vp, _vp, _vp], _i32),
+    "m17b_build_lpf_filter": ([_vp, C.c_float, _i32], _i32),
+    "m17b_float_to_short": ([_vp, _vp, _i32], _i32),
+    "m17b_dec_create": ([_vp, _i64, C.POINTER(_vp)], _i32),
+    "m17b_dec_destroy": ([_vp], _i32),
+    "m17b_dec_reset": ([_vp, _vp], _i32),
+    "m17b_dec_get_taps": ([_vp, _vp], _i32),
+    "m17b_dec_run": ([_vp, _vp, _i64, _vp, _vp], _i32),
+    "m17b_net_pack": ([_vp, _vp, _vp, _i64, _i32, _u64, _vp, _vp, _i64, _vp, _vp], _i32),
+    "m17b_net_parse": ([_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp], _i32),
+    "m17b_rx_net_frames": ([_vp, _vp, _i32, _u64, _vp, _vp, _vp], _i32),
     "m17b_eq_create": ([_vp, _i64, C.POINTER(_vp)], _i32),
     "m17b_eq_destroy": ([_vp], _i32),
     "m17b_eq_reset": ([_vp, _vp], _i32),

@@ -409,6 +409,32 @@ long m17o_mod(m17o_tx *t, const uint8_t *syms, long nsym, int16_t *iq, float *fr
     return n;
 }
 
+/* ================================================================== M17-over-UDP reflector frame */
+/* m17_net_new_rx_data / net_add_* (m17_net.cpp:25-74), m17_send_stream_frame_to_net (m17_tx_routines.cpp:298-306):
+   "M17 " | stream id (2, BE) | LSF bytes 0..27 (dst6 src6 type2 meta14) | FN (2, BE) | payload 16 | CRC-16 over the first 52.
+   have_dst: the RX gateway path overwrites the destination call with the reflector's (m17_net.cpp:56-61) */
+void m17o_net_pack(uint16_t sid, const uint8_t *lsf28, int have_dst, uint64_t dst, uint16_t fn, const uint8_t *pld16, uint8_t *o) {
+    o[0] = 0x4D; o[1] = 0x31; o[2] = 0x37; o[3] = 0x20;
+    o[4] = (uint8_t)(sid >> 8); o[5] = (uint8_t)sid;
+    memcpy(o + 6, lsf28, 28);
+    if (have_dst) for (int i = 0; i < 6; i++) o[6 + i] = (uint8_t)(dst >> (40 - 8 * i));
+    o[34] = (uint8_t)(fn >> 8); o[35] = (uint8_t)fn;
+    memcpy(o + 36, pld16, 16);
+    uint16_t crc = m17o_crc(o, 52);
+    o[52] = (uint8_t)(crc >> 8); o[53] = (uint8_t)crc;
+}
+/* m17_parse_m17_data (m17_net.cpp:203-238) + build_lich_from_net (m17_tx_routines.cpp:71-86): accept iff the CRC over all 54
+   bytes is 0; the TX side's LSF is bytes 6..33 (the TYPE word survives m17_upack_type/m17_pack_type unchanged) + a fresh CRC */
+int m17o_net_parse(const uint8_t *b, uint16_t *sid, uint8_t *lsf30, uint16_t *fn, uint8_t *pld16) {
+    *sid = (uint16_t)((b[4] << 8) | b[5]);
+    memcpy(lsf30, b + 6, 28);
+    uint16_t crc = m17o_crc(lsf30, 28);
+    lsf30[28] = (uint8_t)(crc >> 8); lsf30[29] = (uint8_t)crc;
+    *fn = (uint16_t)((b[34] << 8) | b[35]);
+    memcpy(pld16, b + 36, 16);
+    return m17o_crc(b, 54) == 0;
+}
+
 /* ================================================================== Pluto /8 decimator (radio.cpp:18-51,157-177) */
 void m17o_lpf_design(float *taps, float bw, int ntaps) {
     /* m17_dsp.cpp:347-360: rectangular-window sinc, double math, first tap time by integer division */

@@ -86,6 +86,10 @@ int  m17o_fmt_bert(m17o_tx *t, uint8_t *dibits);                             /* 
    frequency samples m_sum when freq != NULL); returns samples written.  m17_modulate.cpp:22-61,79-92 */
 long m17o_mod(m17o_tx *t, const uint8_t *syms, long nsym, int16_t *iq, float *freq);
 
+/* ---- M17-over-UDP reflector frame, 54 bytes */
+void m17o_net_pack(uint16_t sid, const uint8_t *lsf28, int have_dst, uint64_t dst, uint16_t fn, const uint8_t *pld16, uint8_t *out54);   /* m17_net.cpp:25-74 */
+int  m17o_net_parse(const uint8_t *b54, uint16_t *sid, uint8_t *lsf30, uint16_t *fn, uint8_t *pld16);   /* m17_net.cpp:203-238, m17_tx_routines.cpp:71-86 */
+
 /* ---- Pluto front-end decimator: int16 31-tap symmetric low-pass, decimate by 8, 384 kS/s -> 48 kS/s */
 typedef struct { int16_t taps[31]; int16_t hist[31][2]; } m17o_dec;
 void m17o_lpf_design(float *taps, float bw, int ntaps);                      /* m17_dsp.cpp:347-360 */

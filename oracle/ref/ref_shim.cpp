@@ -36,6 +36,7 @@ int  m17_fmt_add_stream_frame(uint8_t *dibits, uint8_t *payload);
 int  m17_fmt_add_eot(uint8_t *dibits);
 int  m17_fmt_add_link_setup_frame(uint8_t *dibits, uint48_t dest, uint48_t src, M17Type type, uint8_t *meta);
 extern uint8_t  m_lich[30];
+int build_lich_from_net(uint8_t *net);
 extern uint8_t  m_lich_count;
 extern uint16_t m_fn;
 extern uint16_t g_errtab[0x1000];
@@ -104,9 +105,10 @@ void gui_los(void) {
 void gui_update(void) {}
 void gui_save_dest_address(uint48_t) {}
 void gui_save_src_address(uint48_t) { if (g_cur) g_cur->flags |= M17R_F_LSF_EVENT; }
-bool m17_net_new_rx_data(uint16_t, uint8_t *, uint16_t, uint8_t *) { if (g_cur) g_cur->flags |= M17R_F_DELIVERED; return true; }
 void m17_txrx_spkr_audio(uint8_t *) {}
 #ifndef REF_WITH_RADIO
+bool m17_net_new_rx_data(uint16_t, uint8_t *, uint16_t, uint8_t *) { if (g_cur) g_cur->flags |= M17R_F_DELIVERED; return true; }
+int udp_send(uint8_t *, int len) { return len; }
 void radio_afc(float mean) { if (g_afc && m17_db_in_frame()) g_afc_delta -= mean * 0.1; }
 float radio_get_afc_delta(void) { if (g_afc && m17_db_in_frame()) return g_afc_delta; g_afc_delta = 0; return 0; }
 bool radio_get_afc_status(void) { return g_afc; }
@@ -171,8 +173,43 @@ void gui_dp(void) {}
 void gui_rx(void) {}
 void gui_tx(void) {}
 void gui_bar(double) {}
+/* the reference's own m17_net.cpp is linked too (M17-over-UDP frame format): its datagrams are captured at
+   sendto() (ld --wrap=sendto), its buffer pool and GUI hooks are stubbed */
+#include <sys/socket.h>
+static uint8_t g_udp_last[64]; static int g_udp_len = 0;
+extern "C" ssize_t __wrap_sendto(int, const void *b, size_t len, int, const struct sockaddr *, socklen_t) {
+    if (g_cur) g_cur->flags |= M17R_F_DELIVERED;
+    g_udp_len = (int)len; memcpy(g_udp_last, b, len < 64 ? len : 64);
+    return (ssize_t)len;
+}
+static uint8_t g_pool[64], g_posted[64]; static int g_nposted = 0;
+uint8_t *buff_alloc(void) { return g_pool; }
+void buff_rel(uint8_t *) {}
+void buff_post(uint8_t *b) { memcpy(g_posted, b, 54); g_nposted++; }
+void gui_cmd_resp(const char *) {}
+void m17_net_parse_msg(uint8_t *b, int len);
+void m17_parse_m17_data(uint8_t *b);
+/* m17_net_new_rx_data (m17_net.cpp:53-74) after the reflector acknowledged the connection: 54-byte datagram out */
+extern "C" int ref_net_rx_data(int frame_id, const uint8_t *lsf30, int fn, const uint8_t *pld16, uint8_t *out54) {
+    uint8_t ack[8] = {'A', 'C', 'K', 'N'}, lich[64] = {0}, pl[16];
+    m17_net_parse_msg(ack, 4);
+    memcpy(lich, lsf30, 30); memcpy(pl, pld16, 16);
+    g_udp_len = 0;
+    m17_net_new_rx_data((uint16_t)frame_id, lich, (uint16_t)fn, pl);
+    memcpy(out54, g_udp_last, 54);
+    return g_udp_len;
+}
+/* m17_parse_m17_data (m17_net.cpp:203-238) in gateway mode: returns 1 and the frame handed to the radio side if its CRC passed */
+extern "C" int ref_net_parse(const uint8_t *b54, uint8_t *posted54) {
+    uint8_t b[64]; memcpy(b, b54, 54);
+    m17_db_set_chan_type(DRTODN);
+    const int before = g_nposted;
+    m17_parse_m17_data(b);
+    if (g_nposted == before) return 0;
+    memcpy(posted54, g_posted, 54);
+    return 1;
+}
 #endif
-int udp_send(uint8_t *, int len) { return len; }
 
 /* ------------------------------------------------------------------ --wrap interposers */
 extern "C" {
@@ -500,6 +537,12 @@ int ref_pluto_run(const int16_t *in, long C, long nblk, int nproc, int16_t *out)
     });
 }
 #endif
+/* build_lich_from_net (m17_tx_routines.cpp:71-86): the 30-byte LSF (with CRC) the TX side derives from a network frame */
+extern "C" void ref_lich_from_net(const uint8_t *net54, uint8_t *out30) {
+    uint8_t b[64]; memcpy(b, net54, 54);
+    build_lich_from_net(b);
+    memcpy(out30, m_lich, 30);
+}
 void *ref_shared_alloc(long bytes) {
     void *p = mmap(0, bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
     return p == MAP_FAILED ? 0 : p;

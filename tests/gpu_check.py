@@ -227,6 +227,123 @@ def compare_chain(res, o, seam, Cn, verbose=False):
     assert not msgs, msgs[:4]
 
 
+def check_decimator(ctx, P, seed=41):
+    """Pluto /8 decimator (radio.cpp:18-51,157-177): random and extreme int16 input, ragged call sizes with the history
+    carried between calls, bit-exact against the oracle; then decimator -> m17_dsp_rx on an 8x oversampled M17 signal."""
+    import m17_sdr_b200 as m
+    rng = np.random.default_rng(seed)
+    Cn, nout = 5, 3 * 1920
+    X = rng.integers(-32768, 32768, (Cn, 8 * nout, 2)).astype(np.int16)
+    X[1] = 32767
+    X[2, ::2] = -32768
+    X[3] = -32768
+    exp = P.dec_run(X)
+    dec = m.Decimator(ctx, Cn)
+    assert np.array_equal(dec.taps(), P.dec_taps()), "decimator taps"
+    got = dec.radio_receive_samples(dev(X)).cpu().numpy()
+    assert np.array_equal(got, exp), ("decimate one call", first_diff(got.view(np.uint32), exp.view(np.uint32)))
+    dec.reset()
+    o = 0
+    for n in (4, 236, 1920, 512, 516, 2572):
+        got = dec.radio_receive_samples(dev(X[:, 8 * o:8 * (o + n)])).cpu().numpy()
+        assert np.array_equal(got, exp[:, o:o + n]), ("decimate split", o, n)
+        o += n
+    assert o == nout
+    dec.close()
+    # a Pluto-rate capture: TX at oversample 80 (384 kS/s), decimator, then the RX chain; everything against the oracle
+    lsf = lsf_for(P)
+    pl = rng.integers(0, 256, (2, 6, 16), dtype=np.uint8)
+    chans = []
+    for c in range(2):
+        iq, _, _ = P.tx_stream_over(lsf, pl[c], os_=80)
+        chans.append(iq)
+    n = max(len(x) for x in chans)
+    T = n // (8 * 1920) + 2
+    Y = np.zeros((2, T * 8 * 1920, 2), np.int16)
+    for c in range(2):
+        d = int(rng.integers(0, 8 * 1920))
+        Y[c, d:d + len(chans[c])] = chans[c][: Y.shape[1] - d]
+        Y[c, :d] = chans[c][0]; Y[c, d + len(chans[c]):] = chans[c][-1]
+    Y = signals.add_iq_noise(Y, 30.0, rng)
+    dec = m.Decimator(ctx, 2)
+    x48 = dec.radio_receive_samples(dev(Y))
+    e48 = P.dec_run(Y)
+    assert np.array_equal(x48.cpu().numpy(), e48), "decimate M17 capture"
+    dec.close()
+    z = (e48[..., 0] == 0) & (e48[..., 1] == 0)       # the zero filter history gives (0,0) at the very start: the limiter divides by |z| (SURVEY D7)
+    e48[z, 0] = 1
+    res = run_chain(ctx, e48, 0)
+    ora = P.rx_run(e48, seam=0)
+    compare_chain(res, ora, 0, 2)
+    ndel = int(sum(((res["frames"][c, :res["nframes"][c]]["flags"] & F_DELIVERED) != 0).sum() for c in range(2)))
+    return "decimator ok (%d outputs x %d ch exact, split calls exact, 384 kS/s capture -> %d frames, %d delivered)" % (nout, Cn, int(res["nframes"].sum()), ndel)
+
+
+def check_udp_frames(ctx, P, seed=43):
+    """M17-over-UDP frames: pack / parse primitives against the oracle, and the gateway output of a decoded
+    RX call -- one datagram per delivered stream frame carrying the LSF recovered from the LICH -- against datagrams the oracle
+    builds from the oracle's own records; finally datagrams -> TX formatter -> RX again (gateway loop)."""
+    import m17_sdr_b200 as m
+    rng = np.random.default_rng(seed)
+    n = 300
+    lsf = np.stack([P.build_lsf(int(rng.integers(0, 1 << 48)), int(rng.integers(0, 1 << 48)), int(rng.integers(0, 1 << 16)),
+                                rng.integers(0, 256, 14, dtype=np.uint8)) for _ in range(n)])
+    sid = rng.integers(0, 1 << 16, n).astype(np.uint16); fn = rng.integers(0, 1 << 16, n).astype(np.uint16)
+    pld = rng.integers(0, 256, (n, 16), dtype=np.uint8)
+    dst = P.encode_call("M17-M17 C")
+    for d in (None, dst):
+        got = ctx.net_pack(dev(sid), dev(lsf), dev(fn), dev(pld), dst=d).cpu().numpy()
+        exp = np.stack([P.net_pack(int(sid[i]), lsf[i], int(fn[i]), pld[i], dst=d) for i in range(n)])
+        assert np.array_equal(got, exp), ("net_pack", d)
+    bad = exp.copy()
+    bad[::3, rng.integers(0, 54)] ^= 0x10
+    ok, s2, l2, f2, p2 = [t.cpu().numpy() for t in ctx.net_parse(dev(bad))]
+    for i in range(n):
+        eok, esid, elsf, efn, epld = P.net_parse(bad[i])
+        assert bool(ok[i]) == eok and s2[i] == esid and f2[i] == efn and np.array_equal(l2[i], elsf) and np.array_equal(p2[i], epld), ("net_parse", i)
+    # gateway output of an RX call: two transmissions with different LSFs on every channel, so the LSF cache changes mid-call
+    Cn, F = 6, 9
+    X = []
+    plA, plB = rng.integers(0, 256, (Cn, F, 16), dtype=np.uint8), rng.integers(0, 256, (Cn, F, 16), dtype=np.uint8)
+    for c in range(Cn):
+        a, _, _ = P.tx_stream_over(lsf_for(P, src="G4GUO    "), plA[c])
+        b, _, _ = P.tx_stream_over(lsf_for(P, src="AB%dCD    " % c, typeword=0x0085), plB[c])
+        X.append(np.concatenate([a, b]))
+    T = max(len(x) for x in X) // 1920 + 2
+    Y = np.zeros((Cn, T * 1920, 2), np.int16)
+    for c in range(Cn):
+        Y[c, :len(X[c])] = X[c]; Y[c, len(X[c]):] = X[c][-1]
+    Y = signals.add_iq_noise(Y, 28.0, rng)
+    rx = m.Rx(ctx, Cn, T)
+    rx.m17_dsp_rx(dev(Y))
+    res = rx.results()
+    sidc = (np.arange(Cn) * 257 + 5).astype(np.uint16)
+    out, cnt = rx.m17_net_new_rx_data(dev(sidc), dst=dst)
+    out, cnt = out.cpu().numpy(), cnt.cpu().numpy()
+    o = P.rx_run(Y, seam=0)
+    ntot = 0
+    for c in range(Cn):
+        # oracle: walk the oracle's records, keeping m_lsf[1] as update_lich would (m17_rx_parse.cpp:71-85)
+        lsf0, lsf1, exp = np.zeros(30, np.uint8), np.zeros(30, np.uint8), []
+        for r in o.frames[c, : int(o.counts[c, 2])]:
+            if r["type"] != 2 or not (r["flags"] & 2):
+                continue
+            seq = int(r["lich"][5]) >> 5
+            if seq < 6:
+                lsf0[5 * seq:5 * seq + 5] = r["lich"][:5]
+                if P.crc(bytes(lsf0)) == 0:
+                    lsf1 = lsf0.copy()
+            if r["flags"] & F_DELIVERED:
+                exp.append(P.net_pack(int(sidc[c]), lsf1, (int(r["data"][0]) << 8) | int(r["data"][1]), r["data"][2:18], dst=dst))
+        assert cnt[c] == len(exp), ("datagram count", c, cnt[c], len(exp))
+        assert np.array_equal(out[c, :cnt[c]], np.stack(exp)), ("datagrams", c)
+        srcs = {bytes(e[12:18]) for e in exp}
+        assert len(srcs) == 2, "both transmissions' LSFs must appear"
+        ntot += len(exp)
+    rx.close()
+    return "udp frames ok (%d packed/parsed exact, %d gateway datagrams over %d channels with an LSF change mid-call)" % (n, ntot, Cn)
+
+
 def check_rx_afc(ctx, P, seed=31, nchan=12, nframes=30):
     """AFC on (dsp_nco_mixer + radio_afc): records and events exact; discriminator samples / symbols bit-identical unless a
     double sincos result fell on a float rounding boundary (CUDA libm vs glibc), then within 1e-5 relative RMS."""
@@ -450,6 +567,8 @@ CHECKS = [
     ("rx_chain_split", lambda c, P: check_rx_chain(c, P, nchan=6, seed=23, verbose=True, split=[1, 7, 2, 1, 13])),
     ("rx_packet", lambda c, P: check_rx_packet(c, P, verbose=True)),
     ("rx_afc", lambda c, P: check_rx_afc(c, P)),
+    ("decimator", lambda c, P: check_decimator(c, P)),
+    ("udp_frames", lambda c, P: check_udp_frames(c, P)),
     ("tx", lambda c, P: check_tx(c, P)),
     ("tx_os80", lambda c, P: check_tx(c, P, nchan=2, F=3, os_=80)),
     ("equalizer", lambda c, P: check_equalizer(c, P)),

@@ -100,6 +100,43 @@ class Port:
         L.m17o_rrc_design.argtypes = [_vp, C.c_float, C.c_int, C.c_int]
         L.m17o_set_gain.argtypes = [_vp, C.c_float, C.c_int, C.c_int]
 
+    # ---- M17-over-UDP frame (m17_net.cpp:25-74,203-238)
+    def net_pack(self, sid, lsf, fn, pld, dst=None):
+        out = np.zeros(54, np.uint8)
+        self.L.m17o_net_pack(C.c_uint16(sid), _p(np.ascontiguousarray(lsf[:28], np.uint8)), 0 if dst is None else 1, C.c_uint64(dst or 0), C.c_uint16(fn),
+                             _p(np.ascontiguousarray(pld, np.uint8)), _p(out))
+        return out
+
+    def net_parse(self, b54):
+        sid, fn = C.c_uint16(), C.c_uint16()
+        lsf, pld = np.zeros(30, np.uint8), np.zeros(16, np.uint8)
+        ok = self.L.m17o_net_parse(_p(np.ascontiguousarray(b54, np.uint8)), C.byref(sid), _p(lsf), C.byref(fn), _p(pld))
+        return bool(ok), sid.value, lsf, fn.value, pld
+
+    # ---- Pluto /8 front-end decimator (radio.cpp:18-51,157-177)
+    def dec_taps(self):
+        st = np.zeros(256, np.uint8)
+        self.L.m17o_dec_open(_p(st))
+        return st[:62].view(np.int16).copy()
+
+    def dec_run(self, x, parts=None):
+        """x: int16 [C][8*nout][2] at 384 kS/s -> int16 [C][nout][2]; parts = successive call sizes in outputs (state carry)."""
+        x = np.ascontiguousarray(x, np.int16)
+        Cn, nout = x.shape[0], x.shape[1] // 8
+        out = np.zeros((Cn, nout, 2), np.int16)
+        parts = list(parts or [nout])
+        assert sum(parts) == nout
+        for c in range(Cn):
+            st = np.zeros(256, np.uint8)
+            self.L.m17o_dec_open(_p(st))
+            o = 0
+            for n in parts:
+                xin = np.ascontiguousarray(x[c, 8 * o:8 * (o + n)]); y = np.zeros((n, 2), np.int16)
+                self.L.m17o_dec_run(_p(st), _p(xin), C.c_long(n), _p(y))
+                out[c, o:o + n] = y
+                o += n
+        return out
+
     # ---- primitives
     def crc(self, b):
         a = np.frombuffer(bytes(b), np.uint8) if len(b) else np.zeros(1, np.uint8)
@@ -595,6 +632,45 @@ class Ref:
         nfr = shared_array((nproc,), np.int64)
         self.L.ref_rx_time(_p(iq), Cn, T, nproc, _p(secs), _p(nfr))
         return float(secs.max())
+
+
+class RefRadio:
+    """The reference's radio.cpp (Pluto /8 decimator) linked with the hot-path objects and SDR driver stubs."""
+
+    PATH = os.path.join(ORACLE_DIR, "_ref", "libm17ref_radio.so")
+
+    @staticmethod
+    def available():
+        return os.path.exists(RefRadio.PATH)
+
+    def __init__(self):
+        self.L = C.CDLL(RefRadio.PATH)
+        self.L.ref_init(10)                       # the reference's init chain (CRC table etc., main.cpp:108-126)
+
+    def net_rx_data(self, frame_id, lsf30, fn, pld):
+        out = np.zeros(54, np.uint8)
+        n = self.L.ref_net_rx_data(int(frame_id), _p(np.ascontiguousarray(lsf30, np.uint8)), int(fn), _p(np.ascontiguousarray(pld, np.uint8)), _p(out))
+        assert n == 54, n
+        return out
+
+    def net_parse(self, b54):
+        posted = np.zeros(54, np.uint8)
+        ok = self.L.ref_net_parse(_p(np.ascontiguousarray(b54, np.uint8)), _p(posted))
+        return bool(ok), posted
+
+    def lich_from_net(self, b54):
+        out = np.zeros(30, np.uint8)
+        self.L.ref_lich_from_net(_p(np.ascontiguousarray(b54, np.uint8)), _p(out))
+        return out
+
+    def pluto_run(self, x, nproc=None):
+        """x: int16 [C][nblk*8*1920][2] -> radio_receive_samples() output int16 [C][nblk*1920][2]."""
+        x = np.ascontiguousarray(x, np.int16)
+        Cn, nblk = x.shape[0], x.shape[1] // (8 * BLOCK)
+        out = shared_array((Cn, nblk * BLOCK, 2), np.int16)
+        fails = self.L.ref_pluto_run(_p(x), C.c_long(Cn), C.c_long(nblk), nproc or os.cpu_count(), _p(out))
+        assert fails == 0
+        return np.array(out)
 
 
 # ---------------------------------------------------------------------------- synthetic channels

@@ -133,6 +133,16 @@ def test_edge_cases(ctx, port):
     rx.close()
 
 
+def test_pluto_decimator(ctx, port):
+    """radio_receive_samples' /8 decimator ahead of m17_dsp_rx."""
+    print(gc.check_decimator(ctx, port))
+
+
+def test_udp_frames(ctx, port):
+    """M17-over-UDP reflector frame format either side of the path."""
+    print(gc.check_udp_frames(ctx, port))
+
+
 def test_rx_chain_afc(ctx, port):
     """m17_dsp_rx with radio_set_afc_on(): NCO mixer + AFC loop closed through the framer, block-serial path."""
     print(gc.check_rx_afc(ctx, port))

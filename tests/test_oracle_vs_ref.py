@@ -64,3 +64,45 @@ def test_rx_chain_afc(port, ref):
     compare_rx(a, b)
     off = port.rx_run(X)
     assert not feq(a.disc, off.disc)          # the NCO really moved the spectrum once a frame was acquired
+
+
+def test_pluto_decimator(port):
+    """the int16 31-tap /8 decimator of the Pluto receive path (radio.cpp:18-51,157-177), restatement
+    against the reference's own radio.cpp, including the 31-sample history across 1920-sample chunks and int16 extremes."""
+    import pytest
+    from m17_oracles import RefRadio
+    if not RefRadio.available():
+        pytest.skip("oracle/_ref/libm17ref_radio.so not built")
+    rng = np.random.default_rng(106)
+    X = rng.integers(-32768, 32768, (4, 3 * 8 * 1920, 2)).astype(np.int16)
+    X[1] = 32767
+    X[2, ::2] = -32768
+    r = RefRadio().pluto_run(X)
+    assert np.array_equal(port.dec_run(X), r)
+    assert np.array_equal(port.dec_run(X, parts=[1, 239, 1920, 3600]), r)
+
+
+def test_udp_frame_format(port):
+    """the 54-byte M17-over-UDP frame, restatement against the reference's m17_net.cpp / m17_tx_routines.cpp
+    (datagrams captured at sendto)."""
+    import pytest
+    from m17_oracles import RefRadio
+    if not RefRadio.available():
+        pytest.skip("oracle/_ref/libm17ref_radio.so not built")
+    R = RefRadio()
+    rng = np.random.default_rng(107)
+    blank = port.encode_call(" ")                # no reflector connected: the gateway's destination is "<name> <module>" = " "
+    for k in range(40):
+        lsf = port.build_lsf(int(rng.integers(0, 1 << 48)), int(rng.integers(0, 1 << 48)), int(rng.integers(0, 1 << 16)), rng.integers(0, 256, 14, dtype=np.uint8))
+        pld = rng.integers(0, 256, 16, dtype=np.uint8)
+        sid, fn = int(rng.integers(0, 1 << 16)), int(rng.integers(0, 1 << 16))
+        want = R.net_rx_data(sid, lsf, fn, pld)
+        got = port.net_pack(sid, lsf, fn, pld, dst=blank)
+        assert np.array_equal(got, want), k
+        ok, psid, plsf, pfn, ppld = port.net_parse(want)
+        rok, posted = R.net_parse(want)
+        assert ok and rok and np.array_equal(posted, want)
+        assert (psid, pfn) == (sid, fn) and np.array_equal(ppld, pld)
+        assert np.array_equal(plsf, R.lich_from_net(want))
+        bad = want.copy(); bad[int(rng.integers(0, 54))] ^= 1 << int(rng.integers(0, 8))
+        assert port.net_parse(bad)[0] is False and R.net_parse(bad)[0] is False
