@@ -5,7 +5,7 @@ import subprocess
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
-LIB = os.path.join(PKG, "libm17b200.so")
+LIB = os.environ.get("M17B_LIB") or os.path.join(PKG, "libm17b200.so")      # M17B_LIB: kernel-tuning variants built side by side
 SRC = os.path.join(PKG, "csrc", "m17b200.cu")
 
 NVCC_FLAGS = [
@@ -30,7 +30,7 @@ def build(force=False, verbose=False):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: libm17b200.so cannot be built (there is no CPU fallback)")
-    cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-o", LIB, SRC]
+    cmd = [nvcc] + NVCC_FLAGS + os.environ.get("M17B_NVCC_EXTRA", "").split() + ["-I", os.path.join(ROOT, "include"), "-o", LIB, SRC]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.run(cmd, check=True)

@@ -7,9 +7,9 @@
 // With AFC off (the reference default, radio.cpp:146-155) nothing but two input samples and the /5 phase
 // crosses a block boundary, so every (channel, block) item is independent.  The only serial work inside an
 // item is the fp32 running sum, whose order must be kept for bit-exactness, hence:
-//   mapping: one LANE per item, one warp per 32 items.  Each lane streams its own 7680-byte row with 16-byte
-//   loads (two alternating register buffers, one 20-sample chunk ahead; 32-byte sectors fully consumed through L1), and
-//   walks it sequentially with the discriminator history in registers.  Because 20 = lcm(4 samples per load,
+//   mapping: one LANE per item, one warp per 32 items.  The warp fetches the rows cooperatively in 20-sample chunks
+//   (coalesced 16-byte pieces, two chunks ahead, through a small shared-memory tile), and every lane walks its own row
+//   sequentially with the discriminator history in registers.  Because 20 = lcm(4 samples per load,
 //   5 = decimation), the kept sample of every group of five sits at a lane-constant position: no counters.
 //   Kept outputs collect in a [32][33] shared tile that is flushed with coalesced 128-byte row stores every
 //   160 samples.  HBM traffic per item: 7680 B in, 1536 + 4 B out (the algorithmic minimum of the staged design).
@@ -41,50 +41,69 @@ __device__ __forceinline__ LimSample fe_limit_ieee(uint32_t raw, float *mo = nul
     return s;
 }
 
-__device__ __forceinline__ LimSample fe_limit(uint32_t raw, float *mo = nullptr, float *go = nullptr) {
-    // int16 -> float: one I2F.S16 per component, reading the half-register directly (exact); from here (re, im) travel as
-    // one packed pair: FMUL2 / FFMA2 do the two-float scaling, the squares and the final limiter scaling in one issue slot each
-    const f32x2 x = pack2((float)(short)(raw & 0xFFFFu), (float)(short)(raw >> 16));
+// Two samples at a time.  (re, im) of each sample travel as one packed pair through the scaling, the squares and the final
+// limiter scaling; the Newton / Markstein residual steps for sqrt and reciprocal are packed ACROSS the two samples
+// (one FMUL2 / FFMA2 serves both), with the negated operands the residuals need produced by packed multiplies by -1 (exact).
+// Every half of every packed operation is an independent IEEE round-to-nearest operation, so the results are those of the
+// scalar formulation, which m17b_selftest_frontend compares with fe_limit_ieee over all 2^32 raw words.
+__device__ __forceinline__ void fe_limit2(uint32_t raw_a, uint32_t raw_b, LimSample &oa, LimSample &ob, float *mo = nullptr, float *go = nullptr) {
+    // int16 -> float: one I2F.S16 per component, reading the half-register directly (exact)
+    const f32x2 xa = pack2((float)(short)(raw_a & 0xFFFFu), (float)(short)(raw_a >> 16));
+    const f32x2 xb = pack2((float)(short)(raw_b & 0xFFFFu), (float)(short)(raw_b >> 16));
     constexpr float c_hi = 0.00003f;
     constexpr float c_lo = (float)(0.00003 - (double)0.00003f);
-    const f32x2 v = fma2(x, pack2(c_hi, c_hi), mul2(x, pack2(c_lo, c_lo)));      // (re, im) = fmaf(x, c_hi, x * c_lo)
-    float q0, q1;
-    unpack2(mul2(v, v), q0, q1);
-    const float s = q0 + q1;                                   // two rounded products, one rounded (scalar) sum: no contraction
-    float y;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(s));
-    // m = RN(sqrt(s)): Newton step on the residual
-    float m = s * y;
-    const float h = 0.5f * y;
-    m = __fmaf_rn(__fmaf_rn(-m, m, s), h, m);
-    // g = RN(1/m): two residual corrections starting from y ~ 1/m (Markstein).  The one input class this cannot round
-    // correctly is a divisor whose significand is all ones: the Newton iterate then lands exactly on a rounding midpoint
-    // while the true quotient 2^-(e+1) (1 + 2^-24 + 2^-48 + ..) lies just above it; its correctly rounded value is known in
-    // closed form, 2^-(e+1) (1 + 2^-23), whose bit pattern is 0x7F000000 - bits(m).
-    float g = __fmaf_rn(__fmaf_rn(-m, y, 1.0f), y, y);
-    g = __fmaf_rn(__fmaf_rn(-m, g, 1.0f), g, g);
-    const uint32_t mb = __float_as_uint(m);
-    if (((mb + 1u) & 0x7FFFFFu) == 0u) g = __uint_as_float(0x7F000000u - mb);
-    if (mo) { *mo = m; *go = g; }
-    LimSample o;
-    unpack2(mul2(v, pack2(g, g)), o.re, o.im);
-    return o;
+    const f32x2 CH = pack2(c_hi, c_hi), CL = pack2(c_lo, c_lo);
+    const f32x2 va = fma2(xa, CH, mul2(xa, CL));               // (re, im) = fmaf(x, c_hi, x * c_lo) == (float)((double)x * 0.00003)
+    const f32x2 vb = fma2(xb, CH, mul2(xb, CL));
+    float qa0, qa1, qb0, qb1;
+    unpack2(mul2(va, va), qa0, qa1);
+    unpack2(mul2(vb, vb), qb0, qb1);
+    const float sa = qa0 + qa1, sb = qb0 + qb1;                // two rounded products, one rounded (scalar) sum: no contraction
+    float ya, yb;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(ya) : "f"(sa));
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(yb) : "f"(sb));
+    const f32x2 S = pack2(sa, sb), Y = pack2(ya, yb);
+    const f32x2 NEG1 = pack2(-1.0f, -1.0f), HALF = pack2(0.5f, 0.5f), ONE = pack2(1.0f, 1.0f);
+    // m = RN(sqrt(s)): Newton step on the residual s - m*m
+    f32x2 M = mul2(S, Y);
+    const f32x2 H = mul2(Y, HALF);
+    M = fma2(fma2(mul2(M, NEG1), M, S), H, M);
+    // g = RN(1/m): two residual corrections starting from y ~ 1/m (Markstein); t = m*g - 1 = -(1 - m*g) exactly, so
+    // g + (1 - m*g)*g = fma(t, -g, g).  The one input class this cannot round correctly is a divisor whose significand is all
+    // ones: the Newton iterate then lands exactly on a rounding midpoint while the true quotient 2^-(e+1) (1 + 2^-24 + ..)
+    // lies just above it; its correctly rounded value is known in closed form, 2^-(e+1) (1 + 2^-23) = bits 0x7F000000 - bits(m).
+    f32x2 G = fma2(fma2(M, Y, NEG1), mul2(Y, NEG1), Y);
+    G = fma2(fma2(M, G, NEG1), mul2(G, NEG1), G);
+    float ma, mb, ga, gb;
+    unpack2(M, ma, mb);
+    unpack2(G, ga, gb);
+    const uint32_t mab = __float_as_uint(ma), mbb = __float_as_uint(mb);
+    if ((mab | 0xFF800000u) == 0xFFFFFFFFu) ga = __uint_as_float(0x7F000000u - mab);
+    if ((mbb | 0xFF800000u) == 0xFFFFFFFFu) gb = __uint_as_float(0x7F000000u - mbb);
+    if (mo) { mo[0] = ma; mo[1] = mb; go[0] = ga; go[1] = gb; }
+    unpack2(mul2(va, pack2(ga, ga)), oa.re, oa.im);
+    unpack2(mul2(vb, pack2(gb, gb)), ob.re, ob.im);
+}
+__device__ __forceinline__ LimSample fe_limit(uint32_t raw, float *mo = nullptr, float *go = nullptr) {
+    LimSample a, b;
+    float m2[2], g2[2];
+    fe_limit2(raw, raw, a, b, mo ? m2 : nullptr, mo ? g2 : nullptr);
+    if (mo) { *mo = m2[0]; *go = g2[0]; }
+    return a;
 }
 
-// 5-way select by a lane-constant position
-__device__ __forceinline__ float sel5(float a0, float a1, float a2, float a3, float a4, int k) {
-    float lo = (k == 0) ? a0 : a1;
-    float hi = (k == 2) ? a2 : a3;
-    float r = (k < 2) ? lo : hi;
-    return (k == 4) ? a4 : r;
-}
+// The /5 decimation phase: dsp_arctan_disc2 keeps the sample at which count = (count+1)%5 reaches 0 (m17_dsp.cpp:207-211).
+// The reference only ever feeds whole 1920-sample blocks (m17_dsp_rx, m17_tx_rx.cpp), as does this ABI, and 1920 % 5 == 0, so
+// `count` is 0 at every block boundary and the kept samples are those at positions 4 (mod 5): a compile-time pattern.
+#define FE_KEEP 4
 
 // Items are the (channel, block) pairs of blocks [t0, t0+Tc) of a call of T blocks per channel (T is the row pitch of iq,
 // disc and mean); the whole call is t0 = 0, Tc = T.  Sub-ranges let the host pipeline the front end of one time slice with
 // the timing loop of the previous one (rx.cuh).
-__global__ void __launch_bounds__(FE_WARPS * 32) k_frontend(const uint32_t *__restrict__ iq, int64_t nchan, int64_t T, int64_t t0, int64_t Tc,
+__global__ void __launch_bounds__(FE_WARPS * 32, 7) k_frontend(const uint32_t *__restrict__ iq, int64_t nchan, int64_t T, int64_t t0, int64_t Tc,
                                                             RxChanState *st, float *__restrict__ disc, float *__restrict__ mean) {
-    __shared__ float tout[FE_WARPS][32][33];
+    __shared__ float tout[FE_WARPS][32][17];
+    __shared__ __align__(16) uint4 stage[FE_WARPS][160];         // one 20-sample chunk of the warp's 32 rows
     __shared__ int64_t gsl[FE_WARPS][32];                        // global (channel, block) index of each lane's item
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t nitems = nchan * Tc;
@@ -95,60 +114,204 @@ __global__ void __launch_bounds__(FE_WARPS * 32) k_frontend(const uint32_t *__re
     const int64_t ch = item / Tc, t = t0 + item % Tc;
     const int64_t g = ch * T + t;
     gsl[wid][lane] = g;
-    const uint4 *row = (const uint4 *)(iq + g * 1920);
 
     // carried discriminator state: z[0], z[1] are the two previous LIMITED samples (m17_dsp.cpp:196,205-206)
     float z0re, z0im, z1re, z1im;
-    const int count0 = st[ch].disc_count;                        // 1920 % 5 == 0: the /5 phase is the same in every block
     if (t == 0) { z0re = st[ch].z0re; z0im = st[ch].z0im; z1re = st[ch].z1re; z1im = st[ch].z1im; }
     else {
         const uint32_t *prev = iq + g * 1920;
         LimSample a = fe_limit(__ldg(prev - 1)), b = fe_limit(__ldg(prev - 2));
         z0re = a.re; z0im = a.im; z1re = b.re; z1im = b.im;
     }
-    const int keep = 4 - count0;                                 // count = (count+1)%5 hits 0 at samples = keep (mod 5)
     float acc = 0.0f;                                            // sum of u; sum of u*0.5 == 0.5*sum (exact power-of-two scaling)
-    // 20 samples (five 16-byte loads) per chunk; two register buffers alternate so the next chunk's loads are in flight
-    // while the current one is processed, without register copies
     auto process20 = [&](const uint4 (&w)[5], int slot) {
-        float u[20];
 #pragma unroll
-        for (int s = 0; s < 20; s++) {
+        for (int s = 0; s < 20; s += 2) {
             const uint4 q = w[s >> 2];
-            const uint32_t raw = (s & 3) == 0 ? q.x : (s & 3) == 1 ? q.y : (s & 3) == 2 ? q.z : q.w;
-            const LimSample x = fe_limit(raw);
-            // dsp_arctan_disc2 (m17_dsp.cpp:203-212)
-            const float a = z0im * (x.re - z1re);
-            const float b = z0re * (x.im - z1im);
-            u[s] = b - a;
-            z1re = z0re; z1im = z0im; z0re = x.re; z0im = x.im;
-            acc += u[s];
+            const uint32_t raw0 = (s & 3) == 0 ? q.x : q.z, raw1 = (s & 3) == 0 ? q.y : q.w;
+            LimSample x0, x1;
+            fe_limit2(raw0, raw1, x0, x1);
+            // dsp_arctan_disc2 (m17_dsp.cpp:203-212), two samples
+            const float a0 = z0im * (x0.re - z1re);
+            const float b0 = z0re * (x0.im - z1im);
+            const float u0 = b0 - a0;
+            acc += u0;
+            const float a1 = x0.im * (x1.re - z0re);
+            const float b1 = x0.re * (x1.im - z0im);
+            const float u1 = b1 - a1;
+            acc += u1;
+            if (s % 5 == FE_KEEP) tout[wid][lane][slot * 4 + s / 5] = u0 * 0.5f;
+            if ((s + 1) % 5 == FE_KEEP) tout[wid][lane][slot * 4 + (s + 1) / 5] = u1 * 0.5f;
+            z1re = x0.re; z1im = x0.im; z0re = x1.re; z0im = x1.im;
         }
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-            tout[wid][lane][slot * 4 + j] = sel5(u[5 * j], u[5 * j + 1], u[5 * j + 2], u[5 * j + 3], u[5 * j + 4], keep) * 0.5f;
     };
-    uint4 bufa[5], bufb[5];
+    // Loads.  A warp-wide LDG.128 whose lanes each walk their own row (7680 B apart) costs 32 L1 tag wavefronts for 512 B, so
+    // the warp fetches each 20-sample chunk of its 32 rows COOPERATIVELY instead: the chunk is 160 16-byte pieces (5 per row);
+    // piece p = lane + 32 k is loaded by `lane`, so one load instruction covers 6.4 rows x 80 contiguous bytes (about 8
+    // wavefronts).  The pieces wait in registers while the previous chunk is processed, are then parked in a shared-memory
+    // tile (piece p at byte 16 p: the rows come out contiguous at an 80-byte pitch = 4 x 5 words, conflict-free for 16-byte
+    // row reads), and each lane reads its own row back.  Everything is sized for 28 resident warps per SM (<= 72 registers,
+    // 5 KB of shared memory per warp): 8000 warp-units of the 1024 x 250 workload then fit in two full waves of 148 x 28.
+    uint32_t off[5];                                               // piece offsets (in 16-byte units) relative to the warp's first row
+    const uint4 *base = (const uint4 *)(iq + gsl[wid][0] * 1920);
 #pragma unroll
-    for (int q = 0; q < 5; q++) bufa[q] = __ldg(row + q);
-    for (int grp = 0; grp < 12; grp++) {
+    for (int k = 0; k < 5; k++) {
+        const int p = lane + 32 * k, r = p / 5;
+        int64_t it = item0 + r;
+        if (it >= nitems) it = nitems - 1;
+        const int64_t gr = (it / Tc) * T + t0 + it % Tc;
+        off[k] = (uint32_t)((gr - gsl[wid][0]) * 480 + (p - 5 * r));
+    }
+    uint4 *tile = stage[wid];                                      // 160 pieces = one 20-sample chunk of the warp's 32 rows
+#pragma unroll
+    for (int k = 0; k < 5; k++) tile[lane + 32 * k] = __ldg(base + off[k]);
+    __syncwarp();
+    for (int seg = 0; seg < 24; seg++) {                           // 24 segments of 4 chunks = 80 samples -> 16 kept values per row
 #pragma unroll 1
-        for (int chk = 0; chk < 8; chk += 2) {
-            const int c20 = grp * 8 + chk;
+        for (int chk = 0; chk < 4; chk++) {
+            const int c20 = seg * 4 + chk;
+            uint4 nx[5];
+            if (c20 + 1 < 96) {
 #pragma unroll
-            for (int q = 0; q < 5; q++) bufb[q] = __ldg(row + (c20 + 1) * 5 + q);
-            process20(bufa, chk);
-            if (c20 + 2 < 96) {
-#pragma unroll
-                for (int q = 0; q < 5; q++) bufa[q] = __ldg(row + (c20 + 2) * 5 + q);
+                for (int k = 0; k < 5; k++) nx[k] = __ldg(base + off[k] + (c20 + 1) * 5);
             }
-            process20(bufb, chk + 1);
+            uint4 w[5];
+#pragma unroll
+            for (int q = 0; q < 5; q++) w[q] = tile[lane * 5 + q];
+            __syncwarp();                                          // every lane has its row: the tile may be refilled
+            process20(w, chk);
+            if (c20 + 1 < 96) {
+#pragma unroll
+                for (int k = 0; k < 5; k++) tile[lane + 32 * k] = nx[k];
+            }
+            __syncwarp();
+        }
+        // flush: 16 kept values per row, half a 128-byte line per row and store
+        {
+            const int r0 = lane >> 4, col = lane & 15;
+#pragma unroll 4
+            for (int r = 0; r < 32; r += 2)
+                if (item0 + r + r0 < nitems) disc[gsl[wid][r + r0] * 384 + seg * 16 + col] = tout[wid][r + r0][col];
         }
         __syncwarp();
+    }
+    if (live) {
+        mean[g] = (acc * 0.5f) / 1920.0f;                     // offset/len (m17_dsp.cpp:214)
+        if (t == T - 1) { st[ch].nz0re = z0re; st[ch].nz0im = z0im; st[ch].nz1re = z1re; st[ch].nz1im = z1im; }
+    }
+}
+
+// ---------------------------------------------------------------- TMA-staged variant
+// Same mapping (one lane per (channel, block) item, 32 items per warp) and the same arithmetic, but the rows no longer come
+// through per-lane 16-byte loads: a warp-wide LDG.128 whose 32 lanes sit 7680 B apart costs 32 L1 tag wavefronts, and that
+// -- not HBM, not issue slots -- is what bounded k_frontend (it ran at the same speed with 10 % fewer instructions).
+// Here every lane streams its row with 1-D bulk copies (cp.async.bulk, the TMA unit: no LSU / L1 involvement, no staging
+// registers) of 240 B = 60 samples into its own slot of a shared-memory ring, FE2_NST stages deep, each copy completing on
+// the lane's own mbarrier.  The lane then reads its slot with 16-byte LDS (slot pitch 60 words = 4 x odd: the 8 lanes of a
+// quarter-warp hit disjoint bank groups).  60 = lcm(4, 5) x 3 keeps both the word alignment and the /5 pattern compile-time.
+// Kept outputs collect in a [32][49] tile flushed with coalesced row stores every 4 stages (240 samples -> 48 values).
+#define FE2_CH 60
+#ifndef FE2_NST
+#define FE2_NST 4
+#endif
+#define FE2_STAGES (M17B_BLOCK_SAMPLES / FE2_CH)      // 32
+struct Fe2WarpSmem {
+    uint32_t ring[FE2_NST][32][FE2_CH];
+    float tout[32][49];
+    unsigned long long mbar[FE2_NST][32];
+    int64_t g[32];
+};
+
+__device__ __forceinline__ void fe2_issue(Fe2WarpSmem &sm, const uint32_t *row, int k, int lane) {
+    const int st = k % FE2_NST;
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&sm.mbar[st][lane]);
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.ring[st][lane][0]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(FE2_CH * 4) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(row + k * FE2_CH), "r"(FE2_CH * 4), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fe2_wait(Fe2WarpSmem &sm, int k, int lane) {
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&sm.mbar[k % FE2_NST][lane]);
+    const unsigned parity = (unsigned)((k / FE2_NST) & 1);
+    asm volatile("{\n\t.reg .pred p;\n\tFE2_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra FE2_DONE;\n\tbra FE2_WAIT;\n\tFE2_DONE:\n\t}"
+                 ::"r"(bar), "r"(parity) : "memory");
+}
+
+__global__ void __launch_bounds__(32) k_frontend_tma(const uint32_t *__restrict__ iq, int64_t nchan, int64_t T, int64_t t0, int64_t Tc,
+                                                     RxChanState *st, float *__restrict__ disc, float *__restrict__ mean) {
+    extern __shared__ __align__(16) unsigned char fe2_smem_raw[];
+    Fe2WarpSmem &sm = *(Fe2WarpSmem *)fe2_smem_raw;
+    const int lane = threadIdx.x;
+    const int64_t nitems = nchan * Tc;
+    const int64_t item0 = (int64_t)blockIdx.x * 32;
+    const bool live = item0 + lane < nitems;
+    const int64_t item = live ? item0 + lane : nitems - 1;       // dead lanes shadow the last item (results discarded)
+    const int64_t ch = item / Tc, t = t0 + item % Tc;
+    const int64_t g = ch * T + t;
+    sm.g[lane] = g;
+    const uint32_t *row = iq + g * M17B_BLOCK_SAMPLES;
+#pragma unroll
+    for (int s = 0; s < FE2_NST; s++) {
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(&sm.mbar[s][lane]);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#pragma unroll
+    for (int k = 0; k < FE2_NST - 1; k++) fe2_issue(sm, row, k, lane);
+
+    float z0re, z0im, z1re, z1im;
+    if (t == 0) { z0re = st[ch].z0re; z0im = st[ch].z0im; z1re = st[ch].z1re; z1im = st[ch].z1im; }
+    else {
+        LimSample a, b;
+        fe_limit2(__ldg(row - 1), __ldg(row - 2), a, b);
+        z0re = a.re; z0im = a.im; z1re = b.re; z1im = b.im;
+    }
+    float acc = 0.0f;
+    for (int k = 0; k < FE2_STAGES; k++) {
+        // the slot of stage k-1 was read completely (its values are in registers / consumed) before this point in program order
+        if (k + FE2_NST - 1 < FE2_STAGES) fe2_issue(sm, row, k + FE2_NST - 1, lane);
+        fe2_wait(sm, k, lane);
+        const uint4 *slot = (const uint4 *)&sm.ring[k % FE2_NST][lane][0];
+        float *trow = &sm.tout[lane][(k & 3) * 12];
+#pragma unroll
+        for (int c3 = 0; c3 < 3; c3++) {
+            uint4 w[5];
+#pragma unroll
+            for (int q = 0; q < 5; q++) w[q] = slot[c3 * 5 + q];
+#pragma unroll
+            for (int s = 0; s < 20; s += 2) {
+                const uint4 q = w[s >> 2];
+                const uint32_t raw0 = (s & 3) == 0 ? q.x : q.z, raw1 = (s & 3) == 0 ? q.y : q.w;
+                LimSample x0, x1;
+                fe_limit2(raw0, raw1, x0, x1);
+                // dsp_arctan_disc2 (m17_dsp.cpp:203-212), two samples
+                const float a0 = z0im * (x0.re - z1re);
+                const float b0 = z0re * (x0.im - z1im);
+                const float u0 = b0 - a0;
+                acc += u0;
+                const float a1 = x0.im * (x1.re - z0re);
+                const float b1 = x0.re * (x1.im - z0im);
+                const float u1 = b1 - a1;
+                acc += u1;
+                if (s % 5 == FE_KEEP) trow[c3 * 4 + s / 5] = u0 * 0.5f;
+                if ((s + 1) % 5 == FE_KEEP) trow[c3 * 4 + (s + 1) / 5] = u1 * 0.5f;
+                z1re = x0.re; z1im = x0.im; z0re = x1.re; z0im = x1.im;
+            }
+        }
+        if ((k & 3) == 3) {
+            __syncwarp();
+            const int o = (k >> 2) * 48;
 #pragma unroll 4
-        for (int r = 0; r < 32; r++)
-            if (item0 + r < nitems) disc[gsl[wid][r] * 384 + grp * 32 + lane] = tout[wid][r][lane];
-        __syncwarp();
+            for (int r = 0; r < 32; r++) {
+                if (item0 + r < nitems) {
+                    float *d = disc + sm.g[r] * 384 + o;
+                    d[lane] = sm.tout[r][lane];
+                    if (lane < 16) d[32 + lane] = sm.tout[r][32 + lane];
+                }
+            }
+            __syncwarp();
+        }
     }
     if (live) {
         mean[g] = (acc * 0.5f) / 1920.0f;                     // offset/len (m17_dsp.cpp:214)

@@ -36,7 +36,7 @@ struct m17b_rx {
     cudaStream_t s_fe, s_sync, s_dec;
     cudaEvent_t ev_start, ev_fe[M17B_MAX_SLICES], ev_sy[M17B_MAX_SLICES], ev_end;
     int2 *d_frame_rng;                // [M17B_MAX_SLICES][nchan] records completed by each slice
-    int sync_impl;                    // -1 auto; 0: warp per channel (sync.cuh); 2 / 4: CTA of that many warps per channel (sync_cta.cuh)
+    int sync_impl;                    // -1 auto; 0: warp per channel (sync.cuh); 2 / 4: CTA of that many warps per channel (sync_cta.cuh); 8 / 16 / 32: lanes per channel (sync_g.cuh)
     int timing;                       // record cudaEvents around each stage of the next calls (bench only)
     cudaEvent_t ev_stage[M17B_TIMING_RING][5];
     int64_t tcount;                   // calls made since timing was enabled
@@ -265,6 +265,22 @@ extern "C" int m17b_rx_set_afc(m17b_rx *rx, int on) {
     return M17B_OK;
 }
 
+// front end over blocks [t0, t0+Tc): the per-lane-load kernel; M17B_FE_IMPL=1 selects the TMA-staged variant (measured slower:
+// its 23-38 KB of ring per warp leaves 5-9 warps per SM, too few to cover the limiter's dependency chains)
+static int launch_frontend(const int16_t *d_iq, int64_t nc, int64_t T, int64_t t0, int64_t Tc, RxChanState *state, float *disc, float *mean, cudaStream_t st) {
+    static int impl = -1;
+    if (impl < 0) {
+        const char *e = getenv("M17B_FE_IMPL");
+        impl = e ? atoi(e) : 0;
+        CUDA_TRY(cudaFuncSetAttribute(k_frontend_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Fe2WarpSmem)));
+        if (const char *cv = getenv("M17B_FE_CARVEOUT")) CUDA_TRY(cudaFuncSetAttribute(k_frontend, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
+    }
+    if (impl == 1) k_frontend_tma<<<grid_for(nc * Tc, 32), 32, sizeof(Fe2WarpSmem), st>>>((const uint32_t *)d_iq, nc, T, t0, Tc, state, disc, mean);
+    else k_frontend<<<grid_for(nc * Tc, FE_WARPS * 32), FE_WARPS * 32, 0, st>>>((const uint32_t *)d_iq, nc, T, t0, Tc, state, disc, mean);
+    KERNEL_CHECK();
+    return M17B_OK;
+}
+
 #define STAGE_MARK(i) do { if (rx->timing) CUDA_TRY(cudaEventRecord(rx->ev_stage[rx->tcount % M17B_TIMING_RING][i], st)); } while (0)
 
 // matched filter + timing loop + framer over blocks [t0, t1) of channels [c0, c0+nc)
@@ -274,8 +290,27 @@ static int launch_sync(m17b_rx *rx, int64_t c0, int64_t nc, const float *disc, c
 #define SYNC_ARGS disc, mean, nc, T, t0, t1, rng, rx->d_state + c0, ctx->d_mf, ctx->d_md, rx->d_syms + c0 * rx->sym_pitch, rx->sym_pitch, rx->d_nsym + c0 * T, \
                   rx->d_sym_base + c0, rx->d_frames + c0 * rx->fcap, rx->fcap, rx->d_nframes + c0, rx->d_events + c0 * rx->ecap, rx->ecap, rx->d_nevents + c0, \
                   rx->d_stats + c0 * 8, commit_fe
+    // auto policy (measured on B200): one warp per channel has the fewest instructions and wins from ~512 channels
+    // up; below that a channel's serial chain is the whole story and four warps per channel shorten it
     const int impl = rx->sync_impl >= 0 ? rx->sync_impl : (nc <= 256 ? 4 : 0);
-    if (impl == 4) {
+    if (impl == 64) {
+        // two warps per channel, producer (timing loop) / consumer (framer): sync_pc.cuh
+        const unsigned g = grid_for(nc, PC_CH);
+        if (mean) k_sync_frame_pc<true><<<g, PC_CH * 64, 0, st>>>(SYNC_ARGS);
+        else      k_sync_frame_pc<false><<<g, PC_CH * 64, 0, st>>>(SYNC_ARGS);
+    } else if (impl == 8 || impl == 16 || impl == 32) {
+        // G lanes per channel (sync_g.cuh): 32 / G channels share a warp's instruction stream
+#define SYNC_G(GG) do { \
+            const size_t smem = sizeof(SyncGroupSmem) * SY_WARPS * (32 / GG); \
+            static bool attr = false; \
+            if (!attr) { CUDA_TRY(cudaFuncSetAttribute(k_sync_frame_g<true, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                         CUDA_TRY(cudaFuncSetAttribute(k_sync_frame_g<false, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; } \
+            const unsigned g = grid_for(nc, SY_WARPS * (32 / GG)); \
+            if (mean) k_sync_frame_g<true, GG><<<g, SY_WARPS * 32, smem, st>>>(SYNC_ARGS); \
+            else      k_sync_frame_g<false, GG><<<g, SY_WARPS * 32, smem, st>>>(SYNC_ARGS); } while (0)
+        if (impl == 8) SYNC_G(8); else if (impl == 16) SYNC_G(16); else SYNC_G(32);
+#undef SYNC_G
+    } else if (impl == 4) {
         if (mean) k_sync_frame_cta<4, true><<<(unsigned)nc, 128, 0, st>>>(SYNC_ARGS);
         else      k_sync_frame_cta<4, false><<<(unsigned)nc, 128, 0, st>>>(SYNC_ARGS);
     } else if (impl == 2) {
@@ -334,8 +369,8 @@ static int rx_pipeline(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t *d_iq,
     if (nsl < 2) {
         STAGE_MARK(0);
         if (d_iq) {
-            k_frontend<<<grid_for(nc * T, FE_WARPS * 32), FE_WARPS * 32, 0, st>>>((const uint32_t *)d_iq, nc, T, 0, T, rx->d_state + c0, disc_w, mean_w);
-            KERNEL_CHECK();
+            int rcf = launch_frontend(d_iq, nc, T, 0, T, rx->d_state + c0, disc_w, mean_w, st);
+            if (rcf) return rcf;
             rx->last_launches += 1;
         }
         STAGE_MARK(1);
@@ -363,8 +398,8 @@ static int rx_pipeline(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t *d_iq,
         if (t0 >= t1) break;
         int2 *rng = rx->d_frame_rng + (int64_t)k * rx->nchan + c0;
         if (d_iq) {
-            k_frontend<<<grid_for(nc * (t1 - t0), FE_WARPS * 32), FE_WARPS * 32, 0, rx->s_fe>>>((const uint32_t *)d_iq, nc, T, t0, t1 - t0, rx->d_state + c0, disc_w, mean_w);
-            KERNEL_CHECK();
+            int rcf = launch_frontend(d_iq, nc, T, t0, t1 - t0, rx->d_state + c0, disc_w, mean_w, rx->s_fe);
+            if (rcf) return rcf;
             CUDA_TRY(cudaEventRecord(rx->ev_fe[k], rx->s_fe));
             CUDA_TRY(cudaStreamWaitEvent(rx->s_sync, rx->ev_fe[k], 0));
             rx->last_launches += 1;

@@ -69,8 +69,29 @@ __device__ __forceinline__ void dot2(const float (*X)[SY_XQ], int base, const f3
     }
 }
 
+// Six consecutive symbols for one lane (a whole 40-ms block in one warp round): windows xs[n0 + 2m .. n0 + 2m + 30], m = 0..5,
+// n0 = i + 12*lane, so the lane loads 41 samples once.  With the residue-split layout consecutive lanes (stride 12 samples =
+// 3 words per residue array) read 32 different banks.
+template <int R>
+__device__ __forceinline__ void dot6(const float (*X)[SY_XQ], int base, const f32x2 (&tp)[M17B_FN], float (&s)[6], float (&d)[6]) {
+    float x[M17B_FN + 10];
+#pragma unroll
+    for (int k = 0; k < M17B_FN + 10; k++) x[k] = X[(R + k) & 3][base + ((R + k) >> 2)];
+#pragma unroll
+    for (int m = 0; m < 6; m++) unpack2(mul2(tp[0], pack2(x[2 * m], x[2 * m])), s[m], d[m]);
+#pragma unroll
+    for (int k = 1; k < M17B_FN; k++) {
+#pragma unroll
+        for (int m = 0; m < 6; m++) {
+            float p, q;
+            unpack2(mul2(tp[k], pack2(x[2 * m + k], x[2 * m + k])), p, q);
+            s[m] += p; d[m] += q;
+        }
+    }
+}
+
 template <bool HAS_MEAN>
-__global__ void __launch_bounds__(SY_WARPS * 32) k_sync_frame(const float *__restrict__ disc, const float *__restrict__ mean, int64_t nchan, int64_t T,
+__global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__restrict__ disc, const float *__restrict__ mean, int64_t nchan, int64_t T,
                                                               int t0, int t1, int2 *frame_rng, RxChanState *st, const float *__restrict__ g_mf, const float *__restrict__ g_md,
                                                               float *syms, int64_t sym_pitch, int32_t *__restrict__ nsym, int32_t *__restrict__ sym_base,
                                                               m17b_frame_rec *frames, int64_t fcap, int32_t *__restrict__ nframes,
@@ -165,6 +186,58 @@ __global__ void __launch_bounds__(SY_WARPS * 32) k_sync_frame(const float *__res
 #pragma unroll
                 for (int k = 0; k < M17B_FN; k++) tp[k] = pack2(__ldg(g_mf + index * M17B_FN + k), __ldg(g_md + index * M17B_FN + k));
                 tap_index = index;
+            }
+            if (flock && i <= 1) {
+                // Locked, at the start of a block: the threshold is 80, so a trip inside the block is rare -- speculate the
+                // whole block in ONE round, six consecutive symbols per lane (192 symbols, all inside the block for i <= 1).
+                float s6[6], d6[6];
+                if (i == 0) dot6<0>(sm.x, 3 * lane, tp, s6, d6); else dot6<1>(sm.x, 3 * lane, tp, s6, d6);
+                int th6[6], run = 0;
+#pragma unroll
+                for (int m = 0; m < 6; m++) {
+                    const int j = i + 2 * (6 * lane + m);
+                    float dd = (s6[m] < 0) ? -d6[m] : d6[m];
+                    if (j + 1 < 384) run += (dd > 0) - (dd < 0);           // the vote happens on the next sample, if it is in this block
+                    th6[m] = run;
+                }
+                const int incl = warp_incl_scan(run, lane);
+                const int off = thr + incl - run;
+                int fm = 6;                                                    // first symbol of this lane whose vote trips
+#pragma unroll
+                for (int m = 5; m >= 0; m--) {
+                    th6[m] += off;
+                    const int j = i + 2 * (6 * lane + m);
+                    if ((j + 1 < 384) && (th6[m] > TH || th6[m] < -TH)) fm = m;
+                }
+                const unsigned trip = __ballot_sync(0xffffffffu, fm < 6);
+                if (!trip) {
+#pragma unroll
+                    for (int m = 0; m < 6; m++) if (m_idx + 6 * lane + m >= 0) out[m_idx + 6 * lane + m] = s6[m];
+                    m_idx += 192;
+                    thr = __shfl_sync(0xffffffffu, th6[5], 31);
+                    sumc = __shfl_sync(0xffffffffu, s6[5], 31);
+                    difc = __shfl_sync(0xffffffffu, d6[5], 31);
+                    if (i == 0) clk = 0; else clk = 1;                         // last symbol at sample 382 (vote at 383) / 383 (vote in the next block)
+                    i = 384;
+                } else {
+                    const int L = __ffs(trip) - 1;
+                    const int fmL = __shfl_sync(0xffffffffu, fm, L);
+                    const int P = 6 * L + fmL;
+#pragma unroll
+                    for (int m = 0; m < 6; m++) if (6 * lane + m <= P && m_idx + 6 * lane + m >= 0) out[m_idx + 6 * lane + m] = s6[m];
+                    m_idx += P + 1;
+                    int tsel = th6[0]; float ssel = s6[0], dsel = d6[0];
+#pragma unroll
+                    for (int m = 1; m < 6; m++) if (fmL == m) { tsel = th6[m]; ssel = s6[m]; dsel = d6[m]; }
+                    thr = __shfl_sync(0xffffffffu, tsel, L);
+                    sumc = __shfl_sync(0xffffffffu, ssel, L);
+                    difc = __shfl_sync(0xffffffffu, dsel, L);
+                    clk = 0;
+                    __syncwarp();
+                    sync_adjust(TH, thr, index, clk, m_idx, out, lane);
+                    i = i + 2 * P + 2;
+                }
+                continue;
             }
             // speculate: lane l computes the symbols at samples ja = i + 4l and jb = ja + 2
             const int ja = i + 4 * lane, jb = ja + 2;

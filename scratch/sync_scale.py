@@ -1,0 +1,19 @@
+import os, sys, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench, m17_sdr_b200 as m
+ctx = m.Context(0)
+bench.EBN0_SWEEP = (None,)
+for C, T in ((128, 250), (512, 250), (1024, 250), (2048, 250), (4096, 250), (1024, 60)):
+    iq, payload = bench.make_workload(ctx, m, torch, C, T, seed=1000)
+    rx = m.Rx(ctx, C, T)
+    for _ in range(2): rx.reset(); rx.m17_dsp_rx(iq)
+    rx.set_timing(True)
+    for _ in range(5): rx.reset(); rx.m17_dsp_rx(iq)
+    torch.cuda.synchronize()
+    st = {}
+    for i in range(5):
+        s = rx.stage_ms(i)
+        for k in s: st[k] = st.get(k, 0) + s[k] / 5
+    print(os.environ.get("M17B_SYNC_IMPL", "default"), C, T, {k: round(v, 4) for k, v in st.items()}, flush=True)
+    rx.close(); del iq
