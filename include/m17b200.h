@@ -144,6 +144,14 @@ int m17b_rx_reset(m17b_rx *rx, void *stream);
    (m17_dsp.cpp:390-408, radio.cpp:196-208) and processes the blocks of a call one at a time (the loop is closed through the
    framer); off (the reference default) uses the block-parallel front end.  No effect on m17b_rx_baseband. */
 int m17b_rx_set_afc(m17b_rx *rx, int on);
+/* BERT receive.  The reference sends BERT frames (m17_fmt_add_bert_frame) but its decode_bert_frame is empty
+   (m17_rx_parse.cpp:178-180) and m17_prbs9_rx_check (m17_prbs9.cpp:40-64) is never called.  With on != 0, BERT frames are
+   de-punctured (P2, 402 coded bits), Viterbi-decoded (201 steps) into data[0..25) and their 197 PRBS9 bits go through the
+   reference's checker.  Off (the default) reproduces upstream: BERT records carry no data. */
+int m17b_rx_set_bert(m17b_rx *rx, int on);
+/* checker state per channel, d_out uint32 [nchan][8]: m_rx_state, m_rx_idx, m_rx_bad, m_rx_good, m_rx_eq_cnt, m_rx_dif_cnt
+   (m17_prbs9.cpp:7-12), then two running totals: bits checked while in sync, bit errors among them */
+int m17b_rx_get_bert(m17b_rx *rx, uint32_t *d_out, void *stream);
 /* m17_dsp_rx (m17_dsp.cpp:461-476) for nchan channels x nblocks blocks: d_iq = int16 [nchan][nblocks*1920][2] */
 int m17b_dsp_rx(m17b_rx *rx, const int16_t *d_iq, int64_t nblocks, void *stream);
 /* baseband seam (m17_test.cpp:49-51): m17_rx_sync_samples + m17_rx_symbols on d_disc = float [nchan][nblocks*384] */

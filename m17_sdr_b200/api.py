@@ -267,6 +267,16 @@ class Rx:
     def set_afc(self, on):
         _l.check(self.L.m17b_rx_set_afc(self.h, int(bool(on))))
 
+    def set_bert(self, on):
+        """BERT receive extension: decode BERT frames and run m17_prbs9_rx_check on their bits (off = upstream behaviour)."""
+        _l.check(self.L.m17b_rx_set_bert(self.h, int(bool(on))))
+
+    def bert(self):
+        """uint32 [nchan][8]: state, idx, bad, good, eq_cnt, dif_cnt (m17_prbs9.cpp:7-12), bits checked in sync, bit errors."""
+        out = torch.empty((self.nchan, 8), dtype=torch.int32, device=self.ctx.device)
+        _l.check(self.L.m17b_rx_get_bert(self.h, _ptr(out), _stream()))
+        return out
+
     def m17_dsp_rx(self, iq):
         """iq: int16 CUDA tensor [nchan][nblocks*1920][2]."""
         _chk_dev(iq, torch.int16, "iq")

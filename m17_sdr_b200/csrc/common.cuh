@@ -44,6 +44,7 @@ struct __align__(16) GatherMaps {
     uint16_t p2[296];    // stream : 148 steps (type-3 bits 96..367)
     uint16_t p3[420];    // packet : 210 steps
     uint16_t lich[96];   // stream : 4 x 24 Golay bits
+    uint16_t bert[402];  // BERT   : 201 steps (197 PRBS9 bits + 4 tail); the 369th kept bit is never sent -> erasure
 };
 // TX-side maps: for final (interleaved, randomised) bit i of a frame -> which type-3 bit feeds it
 // (QPP is an involution) and, per type-3 bit, which coded (pre-puncture) position it is.
@@ -95,6 +96,11 @@ struct RxChanState {
     int   packet_idx;
     uint8_t lsf[2][32];      // m_lsf[2][30] padded
     uint8_t packet[800];     // m_packet
+    // BERT receive: PRBS9 checker statics m_rx_idx, m_rx_state, m_rx_bad, m_rx_good, m_rx_eq_cnt, m_rx_dif_cnt
+    // (m17_prbs9.cpp:7-12) and two running totals (bits checked while in sync, bit errors among them)
+    uint16_t prbs_idx, prbs_bad, prbs_good, prbs_eq, prbs_dif, prbs_pad;
+    int      prbs_state;
+    uint32_t bert_bits, bert_errs;
 };
 
 // ---------------------------------------------------------------- packed fp32 pairs (sm_100 FMUL2 / FADD2 / FFMA2)

@@ -122,6 +122,7 @@ extern "C" int m17b_viterbi_decode(m17b_ctx *ctx, const float *d_soft, int len, 
 struct FrameLsf    { static constexpr int STEPS = 244, NBYTES = 30; __device__ static const uint16_t *map() { return c_maps.p1; } };
 struct FrameStream { static constexpr int STEPS = 148, NBYTES = 18; __device__ static const uint16_t *map() { return c_maps.p2; } };
 struct FramePacket { static constexpr int STEPS = 210, NBYTES = 26; __device__ static const uint16_t *map() { return c_maps.p3; } };
+struct FrameBert   { static constexpr int STEPS = 201, NBYTES = 25; __device__ static const uint16_t *map() { return c_maps.bert; } };
 
 // soft value for one gather-map entry; the row already holds m = sym * cor (m17_dsp.cpp:38) for the payload symbols
 __device__ __forceinline__ float gather_soft(const float *row, unsigned e) {
@@ -138,23 +139,27 @@ __device__ __forceinline__ void decode_conv(const float *row, uint16_t *dec, int
     const uint16_t *map = F::map();
     float ma[16], mb[16];
     viterbi_init(ma);
-    static_assert(F::STEPS % 2 == 0, "two steps per iteration");
     // software pipeline: the four soft values of the NEXT two steps are gathered (constant-memory map -> smem -> demap)
-    // while the 32 butterflies of the current two steps issue
+    // while the 32 butterflies of the current two steps issue.  An odd step count (BERT: 201) ends with one single step.
+    constexpr int PAIRS = F::STEPS & ~1;
     uint2 e = *(const uint2 *)map;                                          // four uint16 entries, warp-uniform
     float s1 = gather_soft(row, e.x & 0xFFFFu), s2 = gather_soft(row, e.x >> 16);
     float s3 = gather_soft(row, e.y & 0xFFFFu), s4 = gather_soft(row, e.y >> 16);
-    for (int t = 0; t < F::STEPS; t += 2) {
+    for (int t = 0; t < PAIRS; t += 2) {
         float n1 = 0.f, n2 = 0.f, n3 = 0.f, n4 = 0.f;
-        if (t + 2 < F::STEPS) {
+        if (t + 2 < PAIRS) {
             e = *(const uint2 *)(map + 2 * t + 4);
             n1 = gather_soft(row, e.x & 0xFFFFu); n2 = gather_soft(row, e.x >> 16);
             n3 = gather_soft(row, e.y & 0xFFFFu); n4 = gather_soft(row, e.y >> 16);
+        } else if (F::STEPS & 1) {
+            const unsigned ee = *(const unsigned *)(map + 2 * t + 4);
+            n1 = gather_soft(row, ee & 0xFFFFu); n2 = gather_soft(row, ee >> 16);
         }
         dec[t * NT + tid] = (uint16_t)viterbi_step_pp(ma, mb, s1, s2);
         dec[(t + 1) * NT + tid] = (uint16_t)viterbi_step_pp(mb, ma, s3, s4);
         s1 = n1; s2 = n2; s3 = n3; s4 = n4;
     }
+    if (F::STEPS & 1) dec[(F::STEPS - 1) * NT + tid] = (uint16_t)viterbi_step_pp(ma, mb, s1, s2);
     // traceback from state 0; out[t] = MSB of the state at step t = input bit t-1.  Callers discard out[0] and pack
     // out[1..8*NBYTES] MSB first (pack_1_to_8(&bits[1],...), m17_rx_parse.cpp:97,142,171).
     // The survivor words do not depend on the state, so they are fetched eight steps at a time; only the 3-op state
@@ -181,7 +186,7 @@ __global__ void __launch_bounds__(NT) k_decode_frames(const float *__restrict__ 
                                                       const int32_t *__restrict__ sym_base, m17b_frame_rec *frames, int64_t fcap,
                                                       const int32_t *__restrict__ nframes, const int2 *__restrict__ frame_rng, int tiles_per_chan, float *soft_out,
                                                       const uint16_t *__restrict__ g_crc, const uint16_t *__restrict__ genc,
-                                                      const uint16_t *__restrict__ gerr) {
+                                                      const uint16_t *__restrict__ gerr, int bert_on) {
     extern __shared__ unsigned char smem_raw[];
     constexpr int PITCH = 193;
     float *rows = (float *)smem_raw;                                        // [NT][193]
@@ -256,6 +261,11 @@ __global__ void __launch_bounds__(NT) k_decode_frames(const float *__restrict__ 
     } else if (type == M17B_T_PACKET) {
         decode_conv<FramePacket, NT>(row, dec, tid, ob);
         nbytes = FramePacket::NBYTES;
+    } else if (type == M17B_T_BERT && bert_on) {
+        // decode_bert_frame is empty upstream (m17_rx_parse.cpp:178-180: demap only); with the BERT receive extension on
+        // (m17b_rx_set_bert): inverse of m17_fmt_add_bert_frame (m17_tx_routines.cpp:226-238): 197 PRBS9 bits + 3 of the 4 tail bits -> 25 bytes
+        decode_conv<FrameBert, NT>(row, dec, tid, ob);
+        nbytes = FrameBert::NBYTES;
     }
     uint32_t crc = 0;
     if (nbytes) {
@@ -304,7 +314,7 @@ template <int NT, bool STREAM> static size_t decode_smem() { return (size_t)NT *
 static int launch_decode(m17b_ctx *ctx, const float *syms, int64_t sym_pitch, int sym_carry, const int32_t *sym_base,
                          m17b_frame_rec *frames, int64_t fcap, const int32_t *nframes, int64_t nchan, float *soft_out, cudaStream_t st,
                          cudaStream_t aux = nullptr, cudaEvent_t ev_fork = nullptr, cudaEvent_t ev_join = nullptr,
-                         const int2 *frame_rng = nullptr, int64_t max_frames = 0) {
+                         const int2 *frame_rng = nullptr, int64_t max_frames = 0, int bert_on = 0) {
     const int tiles = (int)(((frame_rng ? max_frames : fcap) + DECODE_NT - 1) / DECODE_NT);
     static bool attr_set = false;
     if (!attr_set) {
@@ -318,9 +328,9 @@ static int launch_decode(m17b_ctx *ctx, const float *syms, int64_t sym_pitch, in
     cudaStream_t st2 = st;
     if (aux) { CUDA_TRY(cudaEventRecord(ev_fork, st)); CUDA_TRY(cudaStreamWaitEvent(aux, ev_fork, 0)); st2 = aux; }
     k_decode_frames<DECODE_NT, false><<<grid, DECODE_NT, decode_smem<DECODE_NT, false>(), st2>>>(syms, sym_pitch, sym_carry, sym_base, frames, fcap, nframes,
-                                                                                            frame_rng, tiles, soft_out, ctx->d_crc, ctx->d_genc, ctx->d_gerr);
+                                                                                            frame_rng, tiles, soft_out, ctx->d_crc, ctx->d_genc, ctx->d_gerr, bert_on);
     k_decode_frames<DECODE_NT, true><<<grid, DECODE_NT, decode_smem<DECODE_NT, true>(), st>>>(syms, sym_pitch, sym_carry, sym_base, frames, fcap, nframes,
-                                                                                          frame_rng, tiles, soft_out, ctx->d_crc, ctx->d_genc, ctx->d_gerr);
+                                                                                          frame_rng, tiles, soft_out, ctx->d_crc, ctx->d_genc, ctx->d_gerr, bert_on);
     KERNEL_CHECK();
     if (aux) { CUDA_TRY(cudaEventRecord(ev_join, aux)); CUDA_TRY(cudaStreamWaitEvent(st, ev_join, 0)); }
     return M17B_OK;

@@ -30,7 +30,7 @@ struct m17b_rx {
     cudaStream_t copy_stream, aux_stream;   // aux: LSF/packet/BERT frame decode runs beside the stream-frame decode
     cudaEvent_t ev_fork, ev_join;
     cudaEvent_t ev_h2d[2], ev_done[2];
-    int afc, last_launches, seam_last;
+    int afc, bert, last_launches, seam_last;
     // time-sliced pipeline (see rx_pipeline): front end of slice k+1 | timing loop + framer of slice k | frame decode of slice k-1
     int slice_blocks;                 // blocks per slice; 0 = one slice (stages strictly in sequence)
     cudaStream_t s_fe, s_sync, s_dec;
@@ -65,7 +65,8 @@ __global__ void k_rx_reset(RxChanState *st, int64_t nchan) {
 struct PostWarpSmem { uint4 hdr[32]; uint8_t lsf0[32], lsf1[32], ver[32]; };
 __global__ void __launch_bounds__(POST_WARPS * 32) k_post(m17b_frame_rec *frames, int64_t fcap, const int32_t *__restrict__ nframes, int64_t nchan,
                                                           RxChanState *st, const uint16_t *__restrict__ g_crc, unsigned long long *stats,
-                                                          uint8_t *__restrict__ lsf_snap, int nsnap, uint8_t *__restrict__ lsf_ver) {
+                                                          uint8_t *__restrict__ lsf_snap, int nsnap, uint8_t *__restrict__ lsf_ver,
+                                                          const uint8_t *__restrict__ g_prbs, int bert_on) {
     __shared__ uint16_t tab[256];
     __shared__ PostWarpSmem sm_all[POST_WARPS];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = g_crc[i];
@@ -126,6 +127,31 @@ __global__ void __launch_bounds__(POST_WARPS * 32) k_post(m17b_frame_rec *frames
                         }
                     }
                     if (lsf1_ok) { flags |= M17B_F_DELIVERED; n_deliv++; }              // :148-158
+                } else if (type == M17B_T_BERT && bert_on) {
+                    // the decode_bert_frame the reference left empty (m17_rx_parse.cpp:178-180): the frame's 197 PRBS9 bits go
+                    // through m17_prbs9_rx_check (m17_prbs9.cpp:40-64), bit by bit, in order
+                    const m17b_frame_rec *r = base + k0 + j;
+                    int idx = S->prbs_idx, state = S->prbs_state;
+                    unsigned bad = S->prbs_bad, good = S->prbs_good, eq = S->prbs_eq, dif = S->prbs_dif, nb = 0, ne = 0;
+                    for (int b = 0; b < 197; b++) {
+                        const unsigned bit = (r->data[b >> 3] >> (7 - (b & 7))) & 1u;
+                        const unsigned d = bit ^ g_prbs[idx];
+                        if (d) { dif = (dif + 1) & 0xFFFF; eq = 0; } else { eq = (eq + 1) & 0xFFFF; dif = 0; }
+                        idx = idx + 1 == 511 ? 0 : idx + 1;
+                        if (state == 0) {
+                            bad = 0; good = 0;
+                            if (eq >= 18) state = 1;
+                            if (d) { idx = 0; state = 0; }                              // m17_prbs9_rx_reset
+                        } else {
+                            nb++; ne += d;
+                            if (dif >= 18) state = 0;
+                            if (d) bad = (bad + 1) & 0xFFFF;
+                            // `if(d == 9) m_rx_good++` (m17_prbs9.cpp:61) can never fire: m_rx_good stays 0
+                        }
+                    }
+                    S->prbs_idx = (uint16_t)idx; S->prbs_state = state;
+                    S->prbs_bad = (uint16_t)bad; S->prbs_good = (uint16_t)good; S->prbs_eq = (uint16_t)eq; S->prbs_dif = (uint16_t)dif;
+                    S->bert_bits += nb; S->bert_errs += ne;
                 } else if (type == M17B_T_PACKET) {
                     // parse_packet (m17_rx_parse.cpp:34-51) including its index bug; the copy is clamped to the buffer
                     const m17b_frame_rec *r = base + k0 + j;
@@ -356,11 +382,12 @@ static int rx_pipeline(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t *d_iq,
         }
         STAGE_MARK(2);
         int rc = launch_decode(ctx, syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0, nc, nullptr, st,
-                               rx->aux_stream, rx->ev_fork, rx->ev_join);
+                               rx->aux_stream, rx->ev_fork, rx->ev_join, nullptr, 0, rx->bert);
         if (rc) return rc;
         STAGE_MARK(3);
         k_post<<<grid_for(nc, POST_WARPS), POST_WARPS * 32, 0, st>>>(frames, rx->fcap, rx->d_nframes + c0, nc, rx->d_state + c0, ctx->d_crc, rx->d_stats + c0 * 8,
-                                                                  rx->d_lsf_snap + c0 * rx->nsnap * 32, rx->nsnap, rx->d_lsf_ver + c0 * rx->fcap);
+                                                                  rx->d_lsf_snap + c0 * rx->nsnap * 32, rx->nsnap, rx->d_lsf_ver + c0 * rx->fcap,
+                                                                  ctx->d_prbs, rx->bert);
         KERNEL_CHECK();
         STAGE_MARK(4);
         rx->last_launches += (int)(2 * T) + 3;
@@ -378,11 +405,12 @@ static int rx_pipeline(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t *d_iq,
         if (rc) return rc;
         STAGE_MARK(2);
         rc = launch_decode(ctx, syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0, nc, nullptr, st,
-                           rx->aux_stream, rx->ev_fork, rx->ev_join);
+                           rx->aux_stream, rx->ev_fork, rx->ev_join, nullptr, 0, rx->bert);
         if (rc) return rc;
         STAGE_MARK(3);
         k_post<<<grid_for(nc, POST_WARPS), POST_WARPS * 32, 0, st>>>(frames, rx->fcap, rx->d_nframes + c0, nc, rx->d_state + c0, ctx->d_crc, rx->d_stats + c0 * 8,
-                                                                  rx->d_lsf_snap + c0 * rx->nsnap * 32, rx->nsnap, rx->d_lsf_ver + c0 * rx->fcap);
+                                                                  rx->d_lsf_snap + c0 * rx->nsnap * 32, rx->nsnap, rx->d_lsf_ver + c0 * rx->fcap,
+                                                                  ctx->d_prbs, rx->bert);
         KERNEL_CHECK();
         STAGE_MARK(4);
         rx->last_launches += 4;       // sync/framer, two decode kernels, post
@@ -410,12 +438,13 @@ static int rx_pipeline(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t *d_iq,
         CUDA_TRY(cudaStreamWaitEvent(rx->s_dec, rx->ev_sy[k], 0));
         const int64_t span = t1 - t0;
         rc = launch_decode(ctx, syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0, nc, nullptr, rx->s_dec,
-                           rx->aux_stream, rx->ev_fork, rx->ev_join, rng, span + span / 64 + 4);
+                           rx->aux_stream, rx->ev_fork, rx->ev_join, rng, span + span / 64 + 4, rx->bert);
         if (rc) return rc;
         rx->last_launches += 3;
     }
     k_post<<<grid_for(nc, POST_WARPS), POST_WARPS * 32, 0, rx->s_dec>>>(frames, rx->fcap, rx->d_nframes + c0, nc, rx->d_state + c0, ctx->d_crc, rx->d_stats + c0 * 8,
-                                                                  rx->d_lsf_snap + c0 * rx->nsnap * 32, rx->nsnap, rx->d_lsf_ver + c0 * rx->fcap);
+                                                                  rx->d_lsf_snap + c0 * rx->nsnap * 32, rx->nsnap, rx->d_lsf_ver + c0 * rx->fcap,
+                                                                  ctx->d_prbs, rx->bert);
     KERNEL_CHECK();
     rx->last_launches += 1;
     CUDA_TRY(cudaEventRecord(rx->ev_end, rx->s_dec));
@@ -440,6 +469,28 @@ extern "C" int m17b_rx_baseband(m17b_rx *rx, const float *d_disc, int64_t nblock
     int rc = rx_pipeline(rx, 0, rx->nchan, nullptr, d_disc, nblocks, as_stream(stream));
     if (rx->timing) rx->tcount++;
     return rc;
+}
+
+// BERT receive.  Upstream decodes nothing for BERT frames (decode_bert_frame is empty); with this switched
+// on they are de-punctured / Viterbi-decoded like any other frame and their PRBS9 bits run through m17_prbs9_rx_check.
+extern "C" int m17b_rx_set_bert(m17b_rx *rx, int on) {
+    if (!rx) return M17B_E_ARG;
+    rx->bert = on != 0;
+    return M17B_OK;
+}
+__global__ void k_get_bert(const RxChanState *st, int64_t nchan, uint32_t *out) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchan) return;
+    const RxChanState &S = st[c];
+    uint32_t *o = out + c * 8;
+    o[0] = (uint32_t)S.prbs_state; o[1] = S.prbs_idx; o[2] = S.prbs_bad; o[3] = S.prbs_good; o[4] = S.prbs_eq; o[5] = S.prbs_dif;
+    o[6] = S.bert_bits; o[7] = S.bert_errs;
+}
+extern "C" int m17b_rx_get_bert(m17b_rx *rx, uint32_t *d_out, void *stream) {
+    if (!rx || !d_out) return M17B_E_ARG;
+    k_get_bert<<<grid_for(rx->nchan, 128), 128, 0, as_stream(stream)>>>(rx->d_state, rx->nchan, d_out);
+    KERNEL_CHECK();
+    return M17B_OK;
 }
 
 extern "C" int m17b_rx_get_view(m17b_rx *rx, m17b_rx_view *v) {

@@ -89,6 +89,8 @@ static void build_gather_maps(GatherMaps *g, TxMaps *tx) {
     k = 0;
     for (int p = 0; p < 420; p++) g->p3[p] = punct_keeps(3, p) ? entry(k++) : (uint16_t)MAP_ERASE;
     for (int j = 0; j < 96; j++) g->lich[j] = entry(j);
+    k = 0;
+    for (int p = 0; p < 402; p++) g->bert[p] = (punct_keeps(2, p) && k < 368) ? entry(k++) : (uint16_t)MAP_ERASE;
 
     for (int i = 0; i < 368; i++) { tx->qpp[i] = (uint16_t)qpp_perm(i); tx->rnd[i] = (uint8_t)rand_bit(i); }
     for (int pat = 1; pat <= 3; pat++) {

@@ -47,6 +47,8 @@ _SIGS = {
     "m17b_rx_destroy": ([_vp], _i32),
     "m17b_rx_reset": ([_vp, _vp], _i32),
     "m17b_rx_set_afc": ([_vp, _i32], _i32),
+    "m17b_rx_set_bert": ([_vp, _i32], _i32),
+    "m17b_rx_get_bert": ([_vp, _vp, _vp], _i32),
     "m17b_dsp_rx": ([_vp, _vp, _i64, _vp], _i32),
     "m17b_rx_baseband": ([_vp, _vp, _i64, _vp], _i32),
     "m17b_rx_get_view": ([_vp, C.POINTER(RxView)], _i32),

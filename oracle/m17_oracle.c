@@ -490,6 +490,10 @@ struct m17o_rx {
     /* parser */
     uint8_t lsf[2][30], packet[800]; int packet_idx;     /* m17_rx_parse.cpp:5-7 */
     int in_frame; uint32_t g_errors, n_frames;           /* m17defines.h:104-107 */
+    /* BERT receive (extension: the reference's decode_bert_frame is empty, m17_rx_parse.cpp:178-180): PRBS9 checker statics
+       m_rx_idx, m_rx_state, m_rx_bad, m_rx_good, m_rx_eq_cnt, m_rx_dif_cnt (m17_prbs9.cpp:7-12) + two running totals */
+    int bert_on; uint16_t prbs_idx; int prbs_state; uint16_t prbs_bad, prbs_good, prbs_eq, prbs_dif;
+    uint32_t bert_bits, bert_errs;
     /* trace */
     float *t_disc; int32_t *t_nsym; float *t_syms; long symcap;
     m17_frame_rec *t_frames; long fcap; float *t_soft; m17_event_rec *t_events; long ecap;
@@ -504,6 +508,28 @@ m17o_rx *m17o_rx_new(void) {
 }
 void m17o_rx_free(m17o_rx *r) { free(r); }
 void m17o_rx_set_afc(m17o_rx *r, int on) { r->afc_on = on; }
+void m17o_rx_set_bert(m17o_rx *r, int on) { r->bert_on = on; }
+void m17o_rx_get_bert(const m17o_rx *r, uint32_t *o) {
+    o[0] = (uint32_t)r->prbs_state; o[1] = r->prbs_idx; o[2] = r->prbs_bad; o[3] = r->prbs_good; o[4] = r->prbs_eq; o[5] = r->prbs_dif;
+    o[6] = r->bert_bits; o[7] = r->bert_errs;
+}
+/* m17_prbs9_rx_check (m17_prbs9.cpp:40-64), literally: hunting restarts the local sequence on every mismatch, 18 matches in a
+   row give sync, 18 mismatches in a row lose it; `if(d == 9) m_rx_good++` can never fire (d is 0 or 1) and is kept as is */
+void m17o_prbs9_rx_check(m17o_rx *r, uint8_t bit) {
+    uint8_t d = bit ^ t_prbs[r->prbs_idx];
+    if (d) { r->prbs_dif++; r->prbs_eq = 0; } else { r->prbs_eq++; r->prbs_dif = 0; }
+    r->prbs_idx = (uint16_t)((r->prbs_idx + 1) % 511);
+    if (r->prbs_state == 0) {
+        r->prbs_bad = 0; r->prbs_good = 0;
+        if (r->prbs_eq >= 18) r->prbs_state = 1;
+        if (d) { r->prbs_idx = 0; r->prbs_state = 0; }           /* m17_prbs9_rx_reset */
+    } else {
+        r->bert_bits++; if (d) r->bert_errs++;                   /* running totals (ours) */
+        if (r->prbs_dif >= 18) r->prbs_state = 0;
+        if (d) r->prbs_bad++;
+        if (d == 9) r->prbs_good++;
+    }
+}
 void m17o_rx_trace(m17o_rx *r, float *disc, int32_t *nsym, float *syms, long symcap, m17_frame_rec *frames, long fcap,
                    float *soft, m17_event_rec *events, long ecap) {
     r->t_disc = disc; r->t_nsym = nsym; r->t_syms = syms; r->symcap = symcap; r->t_frames = frames; r->fcap = fcap;
@@ -606,9 +632,21 @@ static void rx_parse(m17o_rx *r, const float *s, int type, m17_frame_rec *f) {
     m17o_demap_frame(s, sb);
     { float sum = 0; for (int i = 0; i < 8; i++) sum += fabsf(s[i]); f->cor = (float)(8.0 / sum); }
     if (r->t_soft && r->n_rec < r->fcap) memcpy(&r->t_soft[r->n_rec * 368], sb, sizeof(sb));
-    if (type == 4) return;                                       /* decode_bert_frame is empty (:178-180) */
+    if (type == 4 && !r->bert_on) return;                        /* decode_bert_frame is empty (:178-180) */
     m17o_derand_soft(sb, sb, 368);
     m17o_deinterleave(sb, so, 368);
+    if (type == 4) {
+        /* what decode_bert_frame was meant to be (inverse of m17_fmt_add_bert_frame, m17_tx_routines.cpp:226-238): de-puncture P2
+           to 402 coded bits (the 369th kept bit was never sent: an erasure), Viterbi over 201 steps, 197 PRBS9 bits to the checker */
+        float sp[369];
+        memcpy(sp, so, sizeof(so)); sp[368] = 0.0f;
+        m17o_depunc(2, sp, dp, 402);
+        m17o_viterbi(dp, bits, 402);
+        pack_bits(bits + 1, f->data, 200); f->nbytes = 25;
+        for (int i = 1; i <= 197; i++) m17o_prbs9_rx_check(r, bits[i]);
+        f->crc = m17o_crc(f->data, f->nbytes);
+        return;
+    }
     if (type == 1) {                                             /* decode_link_frame :86-101 */
         m17o_depunc(1, so, dp, 488);
         m17o_viterbi(dp, bits, 488);
@@ -720,6 +758,8 @@ typedef struct {
     float *disc; int32_t *nsym; float *syms; long symcap; m17_frame_rec *frames; long fcap; float *soft;
     m17_event_rec *events; long ecap; int64_t *counts; double secs;
 } job_t;
+static uint32_t *g_bert_out = 0;                                /* optional [C][8] sink for the BERT checker state of a batch run */
+void m17o_set_bert_out(uint32_t *p) { g_bert_out = p; }
 static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 static void *job_main(void *p) {
     job_t *j = (job_t *)p;
@@ -729,10 +769,12 @@ static void *job_main(void *p) {
         m17o_rx_trace(r, j->disc ? j->disc + c * j->T * 384 : 0, j->nsym ? j->nsym + c * j->T : 0,
                       j->syms ? j->syms + c * j->symcap : 0, j->symcap, j->frames ? j->frames + c * j->fcap : 0, j->fcap,
                       j->soft ? j->soft + c * j->fcap * 368 : 0, j->events ? j->events + c * j->ecap : 0, j->ecap);
+        if (j->seam & 32) m17o_rx_set_bert(r, 1);         /* seam flag 32: BERT receive extension on */
         if (j->seam & 16) m17o_rx_set_afc(r, 1);          /* seam flag 16: AFC on (radio_set_afc_on, radio.cpp:146-148) */
         if ((j->seam & 15) == 0) { const int16_t *iq = (const int16_t *)j->in + c * j->T * 3840; for (long t = 0; t < j->T; t++) m17o_dsp_rx(r, iq + t * 3840, 1920); }
         else { const float *d = (const float *)j->in + c * j->T * 384; for (long t = 0; t < j->T; t++) m17o_rx_baseband(r, d + t * 384, 384); }
         if (j->counts) m17o_rx_counts(r, j->counts + c * 4);
+        if (g_bert_out) m17o_rx_get_bert(r, g_bert_out + c * 8);
         m17o_rx_free(r);
     }
     j->secs = now_s() - t0;

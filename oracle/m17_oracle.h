@@ -101,6 +101,10 @@ typedef struct m17o_rx m17o_rx;
 m17o_rx *m17o_rx_new(void);
 void     m17o_rx_free(m17o_rx *r);
 void     m17o_rx_set_afc(m17o_rx *r, int on);
+void     m17o_rx_set_bert(m17o_rx *r, int on);                               /* BERT receive extension (decode_bert_frame is empty upstream) */
+void     m17o_rx_get_bert(const m17o_rx *r, uint32_t *out8);                 /* state, idx, bad, good, eq, dif (m17_prbs9.cpp:7-12), bits, errs */
+void     m17o_prbs9_rx_check(m17o_rx *r, uint8_t bit);                       /* m17_prbs9.cpp:40-64 */
+void     m17o_set_bert_out(uint32_t *p);
 void     m17o_rx_trace(m17o_rx *r, float *disc, int32_t *nsym, float *syms, long symcap,
                        m17_frame_rec *frames, long fcap, float *soft, m17_event_rec *events, long ecap);
 void     m17o_rx_counts(const m17o_rx *r, int64_t *out4);     /* blocks, syms, frames, events */

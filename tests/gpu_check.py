@@ -344,6 +344,51 @@ def check_udp_frames(ctx, P, seed=43):
     return "udp frames ok (%d packed/parsed exact, %d gateway datagrams over %d channels with an LSF change mid-call)" % (n, ntot, Cn)
 
 
+def check_rx_bert(ctx, P, seed=47, nchan=8, F=14):
+    """BERT receive: carrier, preambles, F BERT frames (m17_fmt_add_bert_frame), EOT at several noise levels.
+    With the extension on, records (decoded PRBS bytes) and the m17_prbs9_rx_check state must equal the oracle's; with it off
+    (upstream behaviour) BERT records carry no data."""
+    import m17_sdr_b200 as m
+    rng = np.random.default_rng(seed)
+    pre, eot = np.full(192, 0, np.uint8), np.zeros(192, np.uint8)
+    P.L.m17o_fmt_preamble(pre.ctypes.data_as(__import__("ctypes").c_void_p)); P.L.m17o_fmt_eot(eot.ctypes.data_as(__import__("ctypes").c_void_p))
+    script = np.concatenate([np.full(192, 4, np.uint8), pre, pre] + list(P.fmt_bert(F)) + [eot, np.full(2 * 192, 4, np.uint8)])
+    iq = P.mod(script)
+    T = len(iq) // 1920 + 2
+    X = np.zeros((nchan, T * 1920, 2), np.int16)
+    for c in range(nchan):
+        d = int(rng.integers(0, 1920))
+        X[c, d:d + len(iq)] = iq[: X.shape[1] - d]; X[c, :d] = iq[0]; X[c, d + len(iq):] = iq[-1]
+    X = np.stack([signals.add_iq_noise(X[c], [None, 30.0, 26.0, 24.0, 23.0, 22.0, 21.5, 21.0][c % 8], rng) for c in range(nchan)])
+    o = P.rx_run(X, seam=0, bert=True)
+    rx = m.Rx(ctx, nchan, T)
+    rx.set_bert(True)
+    for split in (None, [3, 5]):
+        rx.reset()
+        t0 = 0
+        outs = []
+        for nb in (split or []) + [T - sum(split or [])]:
+            rx.m17_dsp_rx(dev(X[:, t0 * 1920:(t0 + nb) * 1920])); outs.append(rx.results()); t0 += nb
+        got = rx.bert().cpu().numpy().view(np.uint32)
+        assert np.array_equal(got, o["bert"]), ("bert checker state", got[:3], o["bert"][:3])
+        for c in range(nchan):
+            fr = np.concatenate([r["frames"][c, :r["nframes"][c]] for r in outs])
+            nf = int(o.counts[c, 2])
+            assert len(fr) == nf, ("nframes", c)
+            for name in ("type", "flags", "nbytes", "data", "crc"):
+                assert bits_eq(fr[name], o.frames[c, :nf][name]), ("bert rec." + name, c)
+    nb = int((o.frames["type"] == 4).sum())
+    best = int(np.argmax(o["bert"][:, 6].astype(np.int64) - 1000 * o["bert"][:, 7].astype(np.int64)))
+    assert int(o["bert"][best, 6]) > 150 * (F - 2) and int(o["bert"][best, 7]) == 0, "a high-SNR channel must sync with no bit errors"
+    rx.set_bert(False)
+    rx.reset(); rx.m17_dsp_rx(dev(X)); off = rx.results()
+    gc_off = P.rx_run(X, seam=0)
+    compare_chain(off, gc_off, 0, nchan)
+    rx.close()
+    return "rx bert ok (%d BERT frames, checker states exact; best channel %d bits / %d errors, noisiest %d / %d)" % (
+        nb, o["bert"][best, 6], o["bert"][best, 7], o["bert"][nchan - 1, 6], o["bert"][nchan - 1, 7])
+
+
 def check_rx_afc(ctx, P, seed=31, nchan=12, nframes=30):
     """AFC on (dsp_nco_mixer + radio_afc): records and events exact; discriminator samples / symbols bit-identical unless a
     double sincos result fell on a float rounding boundary (CUDA libm vs glibc), then within 1e-5 relative RMS."""
@@ -567,6 +612,7 @@ CHECKS = [
     ("rx_chain_split", lambda c, P: check_rx_chain(c, P, nchan=6, seed=23, verbose=True, split=[1, 7, 2, 1, 13])),
     ("rx_packet", lambda c, P: check_rx_packet(c, P, verbose=True)),
     ("rx_afc", lambda c, P: check_rx_afc(c, P)),
+    ("rx_bert", lambda c, P: check_rx_bert(c, P)),
     ("decimator", lambda c, P: check_decimator(c, P)),
     ("udp_frames", lambda c, P: check_udp_frames(c, P)),
     ("tx", lambda c, P: check_tx(c, P)),

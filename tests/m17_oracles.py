@@ -365,7 +365,19 @@ class Port:
         return (iq, freq) if want_freq else iq
 
     # ---- RX
-    def rx_run(self, x, seam=0, nthreads=None, want_disc=True, want_soft=False, afc=False):
+    def prbs_check(self, bits):
+        """m17_prbs9_rx_check over a bit sequence from a fresh checker -> [state, idx, bad, good, eq, dif, bits, errs]."""
+        self.L.m17o_rx_new.restype = _vp
+        r = self.L.m17o_rx_new()
+        b = np.ascontiguousarray(bits, np.uint8)
+        for v in b:
+            self.L.m17o_prbs9_rx_check(_vp(r), int(v))
+        out = np.zeros(8, np.uint32)
+        self.L.m17o_rx_get_bert(_vp(r), _p(out))
+        self.L.m17o_rx_free(_vp(r))
+        return out
+
+    def rx_run(self, x, seam=0, nthreads=None, want_disc=True, want_soft=False, afc=False, bert=False):
         x = np.ascontiguousarray(x)
         if seam == 0:
             assert x.dtype == np.int16 and x.ndim == 3 and x.shape[2] == 2 and x.shape[1] % BLOCK == 0
@@ -375,8 +387,13 @@ class Port:
             Cn, T = x.shape[0], x.shape[1] // DISC_PER_BLOCK
         o = _alloc_rx_out(Cn, T, want_disc, want_soft, np.zeros)
         nthreads = nthreads or min(os.cpu_count() or 1, Cn)
-        self.L.m17o_rx_run(_p(x), seam | (16 if afc else 0), Cn, T, nthreads, _p(o.disc), _p(o.nsym), _p(o.syms), o.symcap, _p(o.frames), o.fcap,
+        if bert:
+            o["bert"] = np.zeros((Cn, 8), np.uint32)
+            self.L.m17o_set_bert_out(_p(o["bert"]))
+        seam_flags = seam | (16 if afc else 0) | (32 if bert else 0)
+        self.L.m17o_rx_run(_p(x), seam_flags, Cn, T, nthreads, _p(o.disc), _p(o.nsym), _p(o.syms), o.symcap, _p(o.frames), o.fcap,
                            _p(o.soft), _p(o.events), o.ecap, _p(o.counts))
+        self.L.m17o_set_bert_out(None)
         return o
 
     def rx_time(self, iq, nthreads):

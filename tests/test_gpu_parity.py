@@ -143,6 +143,11 @@ def test_udp_frames(ctx, port):
     print(gc.check_udp_frames(ctx, port))
 
 
+def test_rx_bert(ctx, port):
+    """BERT receive (decode + m17_prbs9_rx_check), off by default as upstream."""
+    print(gc.check_rx_bert(ctx, port))
+
+
 def test_rx_chain_afc(ctx, port):
     """m17_dsp_rx with radio_set_afc_on(): NCO mixer + AFC loop closed through the framer, block-serial path."""
     print(gc.check_rx_afc(ctx, port))

@@ -106,3 +106,28 @@ def test_udp_frame_format(port):
         assert np.array_equal(plsf, R.lich_from_net(want))
         bad = want.copy(); bad[int(rng.integers(0, 54))] ^= 1 << int(rng.integers(0, 8))
         assert port.net_parse(bad)[0] is False and R.net_parse(bad)[0] is False
+
+
+def test_prbs9_rx_checker(port):
+    """m17_prbs9_rx_check (m17_prbs9.cpp:40-64): the restatement against the reference source itself (its verdict lives in file
+    statics, exported by oracle/ref/prbs_shim.cpp): clean sequence, errors while in sync, loss of sync, re-acquisition."""
+    import ctypes as C
+    import os
+    import pytest
+    from m17_oracles import ORACLE_DIR, _p
+    path = os.path.join(ORACLE_DIR, "_ref", "libm17ref_prbs.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libm17ref_prbs.so not built")
+    rng = np.random.default_rng(108)
+    seq = np.tile(port.prbs9(), 6)
+    cases = [seq[:1500].copy(), seq[3:1200].copy(), rng.integers(0, 2, 900).astype(np.uint8)]
+    e = seq[:2500].copy(); e[rng.integers(100, 2500, 40)] ^= 1; cases.append(e)
+    b = seq[:3000].copy(); b[700:760] ^= 1; b[1500:1530] = rng.integers(0, 2, 30); cases.append(b)
+    L = C.CDLL(path)
+    L.refp_init()                                   # once: the reference never clears its counters again
+    for k, bits in enumerate(cases):
+        L.refp_check(_p(bits), C.c_long(len(bits)))
+        st = np.zeros(6, np.uint32)
+        L.refp_state(_p(st))
+        got = port.prbs_check(np.concatenate(cases[:k + 1]))      # a fresh restatement fed the same history
+        assert np.array_equal(got[:6], st), (k, got, st)
