@@ -163,3 +163,29 @@ def test_rx_edge_cases(port):
     noise[(noise[..., 0] == 0) & (noise[..., 1] == 0)] = 1
     o = port.rx_run(noise, seam=0)
     assert o.counts[0, 0] == 6 and 6 * 190 <= o.counts[0, 1] <= 6 * 194 and T > 1
+
+
+def test_golden_ext(port):
+    """Fixtures made by the unmodified reference for the pieces around the hot path (tests/golden/make_golden_ext.py): AFC loop,
+    Pluto /8 decimator, M17-over-UDP frames, PRBS9 receive checker."""
+    import os
+    from m17_oracles import compare_rx  # noqa: F401
+    here = os.path.dirname(os.path.abspath(__file__))
+    G = np.load(os.path.join(here, "golden", "m17_golden.npz"))
+    E = np.load(os.path.join(here, "golden", "m17_golden_ext.npz"))
+    o = port.rx_run(np.ascontiguousarray(G["rx_iq"]), seam=0, afc=True)
+    assert np.array_equal(o.nsym, E["afc_nsym"]) and np.array_equal(o.counts, E["afc_counts"])
+    for c in range(o.nsym.shape[0]):
+        ns, nf, ne = (int(x) for x in E["afc_counts"][c, 1:4])
+        assert np.array_equal(o.syms[c, :ns].view(np.uint32), E["afc_syms"][c, :ns].view(np.uint32)), c
+        assert np.array_equal(o.frames[c, :nf].view(np.uint8).reshape(nf, 64)[:, :56], E["afc_frames"][c, :nf, :56]), c
+        assert np.array_equal(o.events[c, :ne].view(np.int32).reshape(ne, 2), E["afc_events"][c, :ne]), c
+    assert np.array_equal(o.disc[1].view(np.uint32), E["afc_disc_c1"].view(np.uint32))
+    assert np.array_equal(port.dec_run(E["dec_in"]), E["dec_out"])
+    assert np.array_equal(port.dec_run(E["dec_in"], parts=[4, 1916, 1920]), E["dec_out"])
+    blank = port.encode_call(" ")
+    for i in range(len(E["udp_sid"])):
+        assert np.array_equal(port.net_pack(int(E["udp_sid"][i]), E["udp_lsf"][i], int(E["udp_fn"][i]), E["udp_pld"][i], dst=blank), E["udp_frames"][i])
+        ok, sid, lsf, fn, pld = port.net_parse(E["udp_frames"][i])
+        assert ok and sid == E["udp_sid"][i] and fn == E["udp_fn"][i] and np.array_equal(pld, E["udp_pld"][i]) and np.array_equal(lsf, E["udp_lich"][i])
+    assert np.array_equal(port.prbs_check(E["prbs_bits"])[:6], E["prbs_state"])
