@@ -31,6 +31,7 @@ BLOCKS = 250                      # 10 s per channel
 EBN0_SWEEP = (22.0, 24.0, 26.0, 30.0, None)
 FRAME_BYTES_FUSED = 7744          # 7680 B IQ in + 64 B record out
 STAGE_BYTES = {"frontend": 9216, "sync_frame": 2304, "decode": 768 + 64, "post": 64}   # algorithmic bytes per channel-frame
+DECIMATOR_BYTES = 8 * 7680 + 7680   # Pluto /8 front-end decimator: 61 440 B in + 7 680 B out per channel-frame
 METRIC = "M17 channel-seconds decoded per second"
 UNIT = "channel-s/s"
 
@@ -331,6 +332,22 @@ def run_cuda(args):
     ok, tot = payload_check(torch, res["frames"], nfr, payload)
     stats = res["stats"].sum(0)
 
+    # ---- the stage ahead of the path: Pluto /8 decimator on its own 384 kS/s input (outside the step above)
+    dec_blocks = 32
+    dec_in = torch.randint(-20000, 20000, (C, dec_blocks * 8 * 1920, 2), device=ctx.device, dtype=torch.int16)
+    dec = m.Decimator(ctx, C)
+    for _ in range(3):
+        dec.radio_receive_samples(dec_in)
+    ed0, ed1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ed0.record()
+    for _ in range(10):
+        dec.radio_receive_samples(dec_in)
+    ed1.record()
+    torch.cuda.synchronize()
+    dec_ms = ed0.elapsed_time(ed1) / 10
+    dec.close()
+    del dec_in
+
     # ---- end-to-end through the C ABI with HOST buffers ("e2e")
     iq_host = torch.empty(iq.shape, dtype=torch.int16).pin_memory()
     iq_host.copy_(iq)
@@ -369,6 +386,9 @@ def run_cuda(args):
     dom = max(stage, key=stage.get)
     stages = {k: {"ms": round(v, 4), "alg_bytes_per_frame": STAGE_BYTES[k], "gbs": round(STAGE_BYTES[k] * C * T / (v * 1e-3) / 1e9, 1) if v > 0 else None}
               for k, v in stage.items()}
+    stages["decimator_x8 (ahead of the path, measured separately)"] = {
+        "ms": round(dec_ms, 4), "alg_bytes_per_frame": DECIMATOR_BYTES, "channel_frames": C * dec_blocks,
+        "gbs": round(DECIMATOR_BYTES * C * dec_blocks / (dec_ms * 1e-3) / 1e9, 1)}
     achieved = STAGE_BYTES[dom] * C * T / (stage[dom] * 1e-3) / 1e9
     kname = {"frontend": "k_frontend", "sync_frame": "k_sync_frame", "decode": "k_decode_frames", "post": "k_post"}
     traffic = None

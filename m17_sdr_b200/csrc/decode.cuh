@@ -135,7 +135,17 @@ __device__ __forceinline__ float gather_soft(const float *row, unsigned e) {
 // Viterbi + traceback + pack for one frame; row = this thread's scaled symbols in smem (reused as byte scratch
 // afterwards), dec = this thread's decision column.  Writes NBYTES decoded bytes to obytes (smem).
 template <class F, int NT>
-__device__ __forceinline__ void decode_conv(const float *row, uint16_t *dec, int tid, uint8_t *obytes) {
+__device__ __forceinline__ void decode_conv(const float *row, uint16_t *dec_smem, int tid, uint8_t *obytes) {
+#ifndef M17B_DEC_SMEM
+    // survivor words in per-thread LOCAL memory (interleaved per thread by the hardware, so the accesses coalesce) instead of
+    // shared memory: frees 9.5 / 15.6 KB of shared memory per warp for occupancy
+    uint16_t decl[F::STEPS];
+    uint16_t *dec = decl;
+#define DIDX(t) (t)
+#else
+    uint16_t *dec = dec_smem;
+#define DIDX(t) ((t) * NT + tid)
+#endif
     const uint16_t *map = F::map();
     float ma[16], mb[16];
     viterbi_init(ma);
@@ -155,26 +165,27 @@ __device__ __forceinline__ void decode_conv(const float *row, uint16_t *dec, int
             const unsigned ee = *(const unsigned *)(map + 2 * t + 4);
             n1 = gather_soft(row, ee & 0xFFFFu); n2 = gather_soft(row, ee >> 16);
         }
-        dec[t * NT + tid] = (uint16_t)viterbi_step_pp(ma, mb, s1, s2);
-        dec[(t + 1) * NT + tid] = (uint16_t)viterbi_step_pp(mb, ma, s3, s4);
+        dec[DIDX(t)] = (uint16_t)viterbi_step_pp(ma, mb, s1, s2);
+        dec[DIDX(t + 1)] = (uint16_t)viterbi_step_pp(mb, ma, s3, s4);
         s1 = n1; s2 = n2; s3 = n3; s4 = n4;
     }
-    if (F::STEPS & 1) dec[(F::STEPS - 1) * NT + tid] = (uint16_t)viterbi_step_pp(ma, mb, s1, s2);
+    if (F::STEPS & 1) dec[DIDX(F::STEPS - 1)] = (uint16_t)viterbi_step_pp(ma, mb, s1, s2);
     // traceback from state 0; out[t] = MSB of the state at step t = input bit t-1.  Callers discard out[0] and pack
     // out[1..8*NBYTES] MSB first (pack_1_to_8(&bits[1],...), m17_rx_parse.cpp:97,142,171).
     // The survivor words do not depend on the state, so they are fetched eight steps at a time; only the 3-op state
     // update is serial.
     unsigned s = 0;
     static_assert(F::STEPS - 1 >= 8 * F::NBYTES && (F::STEPS - 1 - 8 * F::NBYTES) < 8, "tail shorter than a byte");
-    for (int t = F::STEPS - 1; t > 8 * F::NBYTES; t--) s = trace_prev(s, dec[t * NT + tid]);   // tail bits, discarded
+    for (int t = F::STEPS - 1; t > 8 * F::NBYTES; t--) s = trace_prev(s, dec[DIDX(t)]);   // tail bits, discarded
     for (int j = F::NBYTES - 1; j >= 0; j--) {
         unsigned d[8], acc = 0;
 #pragma unroll
-        for (int b = 0; b < 8; b++) d[b] = dec[(8 * j + 8 - b) * NT + tid];                      // t = 8j+8 ... 8j+1
+        for (int b = 0; b < 8; b++) d[b] = dec[DIDX(8 * j + 8 - b)];                             // t = 8j+8 ... 8j+1
 #pragma unroll
         for (int b = 0; b < 8; b++) { s = trace_prev(s, d[b]); acc |= ((s >> 3) & 1u) << b; }   // t = 8j+8 is bit 0 ... t = 8j+1 is bit 7
         obytes[j] = (uint8_t)acc;
     }
+#undef DIDX
 }
 
 // frames: records pre-filled with sym_off/type/flags by the framer (or by k_parse_init); the symbols of record r
@@ -308,7 +319,11 @@ __global__ void k_parse_init(const uint8_t *type, int64_t n, m17b_frame_rec *rec
 __global__ void k_set_i32(int32_t *p, int32_t v) { *p = v; }
 
 #define DECODE_NT 32
+#ifndef M17B_DEC_SMEM
+template <int NT, bool STREAM> static size_t decode_smem() { return (size_t)NT * 193 * 4; }
+#else
 template <int NT, bool STREAM> static size_t decode_smem() { return (size_t)NT * 193 * 4 + (size_t)(STREAM ? 148 : 244) * NT * 2; }
+#endif
 
 // frame_rng / max_frames: decode only the records [rng.x, rng.y) of each channel (at most max_frames of them)
 static int launch_decode(m17b_ctx *ctx, const float *syms, int64_t sym_pitch, int sym_carry, const int32_t *sym_base,
