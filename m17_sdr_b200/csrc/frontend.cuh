@@ -103,7 +103,7 @@ __device__ __forceinline__ LimSample fe_limit(uint32_t raw, float *mo = nullptr,
 __global__ void __launch_bounds__(FE_WARPS * 32, 7) k_frontend(const uint32_t *__restrict__ iq, int64_t nchan, int64_t T, int64_t t0, int64_t Tc,
                                                             RxChanState *st, float *__restrict__ disc, float *__restrict__ mean) {
     __shared__ float tout[FE_WARPS][32][17];
-    __shared__ __align__(16) uint4 stage[FE_WARPS][160];         // one 20-sample chunk of the warp's 32 rows
+    __shared__ __align__(16) uint4 stage[FE_WARPS][2][160];      // two 20-sample chunks of the warp's 32 rows
     __shared__ int64_t gsl[FE_WARPS][32];                        // global (channel, block) index of each lane's item
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t nitems = nchan * Tc;
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 7) k_frontend(const uint32_t *_
         z0re = a.re; z0im = a.im; z1re = b.re; z1im = b.im;
     }
     float acc = 0.0f;                                            // sum of u; sum of u*0.5 == 0.5*sum (exact power-of-two scaling)
-    auto process20 = [&](const uint4 (&w)[5], int slot) {
+    auto process20 = [&](const uint4 *w, int slot) {              // w: the lane's five 16-byte pieces (registers or shared memory)
 #pragma unroll
         for (int s = 0; s < 20; s += 2) {
             const uint4 q = w[s >> 2];
@@ -148,10 +148,10 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 7) k_frontend(const uint32_t *_
     // Loads.  A warp-wide LDG.128 whose lanes each walk their own row (7680 B apart) costs 32 L1 tag wavefronts for 512 B, so
     // the warp fetches each 20-sample chunk of its 32 rows COOPERATIVELY instead: the chunk is 160 16-byte pieces (5 per row);
     // piece p = lane + 32 k is loaded by `lane`, so one load instruction covers 6.4 rows x 80 contiguous bytes (about 8
-    // wavefronts).  The pieces wait in registers while the previous chunk is processed, are then parked in a shared-memory
-    // tile (piece p at byte 16 p: the rows come out contiguous at an 80-byte pitch = 4 x 5 words, conflict-free for 16-byte
-    // row reads), and each lane reads its own row back.  Everything is sized for 28 resident warps per SM (<= 72 registers,
-    // 5 KB of shared memory per warp): 8000 warp-units of the 1024 x 250 workload then fit in two full waves of 148 x 28.
+    // wavefronts).  The pieces land in a shared-memory tile (piece p at byte 16 p: the rows come out contiguous at an 80-byte
+    // pitch = 4 x 5 words, conflict-free for 16-byte row reads), and each lane reads its own row back.  Everything is sized
+    // for 28 resident warps per SM (<= 72 registers, 7.5 KB of shared memory per warp): the 8000 warp-units of the 1024 x 250
+    // workload then fit in two full waves of 148 x 28.
     uint32_t off[5];                                               // piece offsets (in 16-byte units) relative to the warp's first row
     const uint4 *base = (const uint4 *)(iq + gsl[wid][0] * 1920);
 #pragma unroll
@@ -162,29 +162,32 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 7) k_frontend(const uint32_t *_
         const int64_t gr = (it / Tc) * T + t0 + it % Tc;
         off[k] = (uint32_t)((gr - gsl[wid][0]) * 480 + (p - 5 * r));
     }
-    uint4 *tile = stage[wid];                                      // 160 pieces = one 20-sample chunk of the warp's 32 rows
+    // two tiles of 160 pieces (one 20-sample chunk of the warp's 32 rows each), filled two chunks ahead with 16-byte cp.async:
+    // completion is tracked by the async-copy group, NOT by a register scoreboard -- with plain loads into registers the
+    // compiler's scoreboard sharing made the first arithmetic instruction of every chunk wait for that chunk's own prefetch
+    // (17 % of all stall samples, profiles/r01b_ncu_hotspots.txt)
+    auto fetch = [&](int c20) {
+        if (c20 < 96) {
+            uint4 *tl = stage[wid][c20 & 1];
 #pragma unroll
-    for (int k = 0; k < 5; k++) tile[lane + 32 * k] = __ldg(base + off[k]);
-    __syncwarp();
+            for (int k = 0; k < 5; k++) {
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(tl + lane + 32 * k);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(base + off[k] + c20 * 5));
+            }
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    fetch(0);
+    fetch(1);
     for (int seg = 0; seg < 24; seg++) {                           // 24 segments of 4 chunks = 80 samples -> 16 kept values per row
 #pragma unroll 1
         for (int chk = 0; chk < 4; chk++) {
             const int c20 = seg * 4 + chk;
-            uint4 nx[5];
-            if (c20 + 1 < 96) {
-#pragma unroll
-                for (int k = 0; k < 5; k++) nx[k] = __ldg(base + off[k] + (c20 + 1) * 5);
-            }
-            uint4 w[5];
-#pragma unroll
-            for (int q = 0; q < 5; q++) w[q] = tile[lane * 5 + q];
-            __syncwarp();                                          // every lane has its row: the tile may be refilled
-            process20(w, chk);
-            if (c20 + 1 < 96) {
-#pragma unroll
-                for (int k = 0; k < 5; k++) tile[lane + 32 * k] = nx[k];
-            }
+            asm volatile("cp.async.wait_group 1;");                // chunk c20 has landed (chunk c20 + 1 may still be in flight)
             __syncwarp();
+            process20(stage[wid][c20 & 1] + lane * 5, chk);        // row pieces are read from the tile as they are needed
+            __syncwarp();                                          // every lane is done with its row: the tile may be refilled
+            fetch(c20 + 2);
         }
         // flush: 16 kept values per row, half a 128-byte line per row and store
         {
