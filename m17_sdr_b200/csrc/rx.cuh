@@ -36,7 +36,7 @@ struct m17b_rx {
     cudaStream_t s_fe, s_sync, s_dec;
     cudaEvent_t ev_start, ev_fe[M17B_MAX_SLICES], ev_sy[M17B_MAX_SLICES], ev_end;
     int2 *d_frame_rng;                // [M17B_MAX_SLICES][nchan] records completed by each slice
-    int sync_impl;                    // -1 auto; 0: warp per channel (sync.cuh); 2 / 4: CTA of that many warps per channel (sync_cta.cuh); 8 / 16 / 32: lanes per channel (sync_g.cuh)
+    int sync_impl;                    // -1 auto; 0: warp per channel (sync.cuh); 2 / 4: CTA of that many warps per channel (sync_cta.cuh); 8 / 16 / 32: lanes per channel (sync_g.cuh); 33: 32 lanes with taps in smem; 64: producer/consumer warp pair (sync_pc.cuh)
     int timing;                       // record cudaEvents around each stage of the next calls (bench only)
     cudaEvent_t ev_stage[M17B_TIMING_RING][5];
     int64_t tcount;                   // calls made since timing was enabled
@@ -318,8 +318,16 @@ static int launch_sync(m17b_rx *rx, int64_t c0, int64_t nc, const float *disc, c
                   rx->d_stats + c0 * 8, commit_fe
     // auto policy (measured on B200): one warp per channel has the fewest instructions and wins from ~512 channels
     // up; below that a channel's serial chain is the whole story and four warps per channel shorten it
-    const int impl = rx->sync_impl >= 0 ? rx->sync_impl : (nc <= 256 ? 4 : 0);
-    if (impl == 64) {
+    // Beyond one resident wave (8 channels per SM at 178 registers = 1184 on a B200) the tap-pairs-in-shared-memory variant
+    // (108 registers, 16 warps per SM) is 15-23 % faster: 2048 ch 1.64 -> 1.33 ms, 4096 ch 3.26 -> 2.52 ms.
+    const int impl = rx->sync_impl >= 0 ? rx->sync_impl : (nc <= 256 ? 4 : nc <= 8 * 148 ? 0 : 33);
+    if (impl == 33) {
+        // one warp per channel, tap pairs in shared memory: 16 resident warps per SM, for batches that do not fit one wave
+        const size_t smem = sizeof(SyncGroupSmem) * SY_WARPS;
+        const unsigned g = grid_for(nc, SY_WARPS);
+        if (mean) k_sync_frame_g<true, 32, true><<<g, SY_WARPS * 32, smem, st>>>(SYNC_ARGS);
+        else      k_sync_frame_g<false, 32, true><<<g, SY_WARPS * 32, smem, st>>>(SYNC_ARGS);
+    } else if (impl == 64) {
         // two warps per channel, producer (timing loop) / consumer (framer): sync_pc.cuh
         const unsigned g = grid_for(nc, PC_CH);
         if (mean) k_sync_frame_pc<true><<<g, PC_CH * 64, 0, st>>>(SYNC_ARGS);

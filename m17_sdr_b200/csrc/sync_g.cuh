@@ -22,6 +22,7 @@ struct SyncGroupSmem {
     float hist[SY_HIST];                // [0,8): sliding sync window carried in; [8, 8+n): symbols emitted in this block
     float head[8];                      // m_f_sym[0..7] of the frame being collected
     float pre[2][384 + 4];              // cp.async landing zone for the NEXT block's raw samples (+ its mean), double buffered
+    f32x2 taps[M17B_FN + 1];            // TAPS_SMEM variants: (matched, derivative) tap pairs of the current polyphase branch
 };
 
 template <int G>
@@ -142,8 +143,11 @@ __device__ __forceinline__ void sync_round(unsigned gmask, int gl, int gshift, c
     }
 }
 
-template <bool HAS_MEAN, int G>
-__global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame_g(const float *__restrict__ disc, const float *__restrict__ mean, int64_t nchan, int64_t T,
+// TAPS_SMEM: the 31 tap pairs are read from shared memory (broadcast) instead of living in 62 registers: ~110 registers instead
+// of ~170, i.e. 16 instead of 8 resident warps per SM.  No help while every channel is resident anyway (<= 1184 channels per
+// GPU: the chain's latency rules), but above that the kernel runs in waves and twice the warps hide twice the latency.
+template <bool HAS_MEAN, int G, bool TAPS_SMEM = false>
+__global__ void __launch_bounds__(SY_WARPS * 32, TAPS_SMEM ? 4 : 2) k_sync_frame_g(const float *__restrict__ disc, const float *__restrict__ mean, int64_t nchan, int64_t T,
                                                                    int t0, int t1, int2 *frame_rng, RxChanState *st, const float *__restrict__ g_mf,
                                                                    const float *__restrict__ g_md, float *syms, int64_t sym_pitch,
                                                                    int32_t *__restrict__ nsym, int32_t *__restrict__ sym_base, m17b_frame_rec *frames,
@@ -190,7 +194,8 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame_g(const float *
     if (gl == 0 && t0 == 0) sym_base[c] = base_g;
     int nfr = t0 == 0 ? 0 : nframes[c], nev = t0 == 0 ? 0 : nevents[c], n_aos = 0, n_los = 0;
     const int nfr_entry = nfr;
-    f32x2 tp[M17B_FN];                      // (matched, derivative) tap pairs of the current polyphase branch
+    f32x2 tp_reg[TAPS_SMEM ? 1 : M17B_FN];  // (matched, derivative) tap pairs of the current polyphase branch
+    const f32x2 *tp = TAPS_SMEM ? sm.taps : tp_reg;
     int tap_index = -1;
     __syncwarp(gmask);
     // The block's samples are fetched one block ahead with cp.async straight into shared memory: completion is tracked by
@@ -243,8 +248,13 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame_g(const float *
             }
             if (i >= 384) break;
             if (index != tap_index) {
+                if (TAPS_SMEM) {
+                    for (int k = gl; k < M17B_FN; k += G) sm.taps[k] = pack2(__ldg(g_mf + index * M17B_FN + k), __ldg(g_md + index * M17B_FN + k));
+                    __syncwarp(gmask);
+                } else {
 #pragma unroll
-                for (int k = 0; k < M17B_FN; k++) tp[k] = pack2(__ldg(g_mf + index * M17B_FN + k), __ldg(g_md + index * M17B_FN + k));
+                    for (int k = 0; k < M17B_FN; k++) tp_reg[k] = pack2(__ldg(g_mf + index * M17B_FN + k), __ldg(g_md + index * M17B_FN + k));
+                }
                 tap_index = index;
             }
             if (flock) sync_round<G, NSL_LOCKED>(gmask, gl, gshift, sm.x, out, tp, TH, i, m_idx, thr, index, clk, sumc, difc);

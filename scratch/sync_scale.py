@@ -4,7 +4,7 @@ sys.path.insert(0, ROOT)
 import bench, m17_sdr_b200 as m
 ctx = m.Context(0)
 bench.EBN0_SWEEP = (None,)
-for C, T in ((128, 250), (512, 250), (1024, 250), (2048, 250), (4096, 250), (1024, 60)):
+for C, T in ((1024, 250), (2048, 250), (4096, 250), (8192, 125)):
     iq, payload = bench.make_workload(ctx, m, torch, C, T, seed=1000)
     rx = m.Rx(ctx, C, T)
     for _ in range(2): rx.reset(); rx.m17_dsp_rx(iq)
