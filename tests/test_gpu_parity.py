@@ -143,6 +143,26 @@ def test_udp_frames(ctx, port):
     print(gc.check_udp_frames(ctx, port))
 
 
+@pytest.mark.parametrize("impl", [2, 4, 8, 16, 32, 33, 64])
+def test_sync_kernel_variants(ctx, port, impl, monkeypatch):
+    """Every timing-loop / framer kernel variant (CTA per channel, G lanes per channel, taps in shared memory, producer /
+    consumer warp pair) is bit-exact against the oracle on the IQ chain with split calls and on the packet-mode set."""
+    monkeypatch.setenv("M17B_SYNC_IMPL", str(impl))
+    gc.check_rx_chain(ctx, port, nchan=6, seed=23, split=[1, 7, 2, 1, 13])
+    gc.check_rx_packet(ctx, port)
+
+
+def test_frontend_tma_variant(ctx, port, monkeypatch):
+    """The TMA-staged front end (cp.async.bulk ring + mbarriers) produces the same bits as the default kernel.
+    (The selector is read once per process, so this runs the variant in a child process.)"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, M17B_FE_IMPL="1")
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "gpu_check.py"), "rx_chain", "rx_chain_split"], capture_output=True, text=True, env=env)
+    assert out.returncode == 0 and "FAILS 0" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
 def test_rx_bert(ctx, port):
     """BERT receive (decode + m17_prbs9_rx_check), off by default as upstream."""
     print(gc.check_rx_bert(ctx, port))
