@@ -1,3 +1,6 @@
+// benchmarks/access_probe.cu -- build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o access_probe access_probe.cu
+// Result on B200 (round 1): 80-byte bursts 5.86 TB/s, 160 B 5.87, 320 B 5.70, 640 B 7.0, plain streaming read 6.29 TB/s:
+// the front end's cooperative row walk is not limited by its memory access pattern.
 // access-pattern probe: every warp owns 32 rows of 7680 B (consecutive rows), and walks them in steps of BURST bytes per row,
 // loading the 32 x BURST bytes of a step with coalesced 16-byte pieces (piece p = lane + 32 k -> row p / PPR, piece p % PPR).
 #include <cuda_runtime.h>

@@ -1,3 +1,5 @@
+"""Per-stage device times of the bench step (front end, sync/framer, decode, post) -- the library marks the stage boundaries with
+CUDA events.  Honours M17B_SYNC_IMPL / M17B_FE_IMPL / M17B_LIB for comparing kernel variants."""
 import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

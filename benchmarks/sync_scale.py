@@ -1,3 +1,5 @@
+"""Stage times against the number of channels per GPU (clean channels): shows the timing-loop kernel going from latency-bound
+(<= 1184 resident channels) to wave-bound, and the variants selected by M17B_SYNC_IMPL."""
 import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

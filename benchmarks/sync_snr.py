@@ -1,3 +1,5 @@
+"""Stage times against the noise level of the channels (all channels at one Eb/N0, then the bench mix): the timing-loop kernel's
+time is set by its slowest channel."""
 import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
