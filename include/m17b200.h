@@ -207,6 +207,12 @@ int m17b_fmt_link_setup_frame(m17b_ctx *ctx, const uint8_t *d_lsf, int64_t n, ui
 int m17b_fmt_stream_frames(m17b_tx *tx, const uint8_t *d_payload, int64_t F, uint8_t *d_dibits, void *stream);
 /* m17_fmt_add_packet (m17_tx_routines.cpp:201-222, safe buffers: D2): d_chunk [n][25], d_meta [n] (= eof<<7 | nf<<2) */
 int m17b_fmt_packet_frames(m17b_ctx *ctx, const uint8_t *d_chunk, const uint8_t *d_meta, int64_t n, uint8_t *d_dibits, void *stream);
+/* m17_send_packet_frames (m17_tx_routines.cpp:323-353) up to the dibits: n packets of d_len[i] bytes (stride apart) get their
+   CRC-16 appended and are cut into 25-byte chunks (non-final frames: frame number; final frame: EOF + bytes used, 25 when the
+   split is exact) -> d_dibits [n][max_frames][192], d_nframes [n]; slots past a packet's last frame hold blank-carrier
+   symbols (4).  max_frames <= 32 (the frame counter is 5 bits); packets longer than 25*max_frames-2 bytes are truncated. */
+int m17b_send_packet_frames(m17b_ctx *ctx, const uint8_t *d_packets, int64_t stride, const int32_t *d_len, int64_t n, int max_frames,
+                            uint8_t *d_dibits, int32_t *d_nframes, void *stream);
 /* m17_fmt_add_bert_frame (m17_tx_routines.cpp:226-238, intended behaviour: D5): F frames per channel */
 int m17b_fmt_bert_frames(m17b_tx *tx, int64_t F, uint8_t *d_dibits, void *stream);
 /* m17_mod_dibits / m17_mod_carrier (m17_modulate.cpp:42-61,79-92): d_syms [nchan][nsym] (0..3 dibit, 4 = carrier)

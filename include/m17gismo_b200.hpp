@@ -72,6 +72,7 @@ void m17_send_preamble(void);
 void m17_send_link_setup_frame(uint48_t dest, uint48_t src, M17Type type, uint8_t *meta);
 void m17_send_stream_frame(uint8_t *payload);
 void m17_send_bert_frame(void);
+void m17_send_packet_frames(uint8_t *packet, int len);     // writes the CRC into packet[len], packet[len+1] like the reference
 void m17_send_eot(void);
 void m17_send_carrier(void);
 
@@ -333,6 +334,21 @@ void m17_send_stream_frame(uint8_t *payload) {
     uint8_t d[192];
     s.down(d, s.dB, 192);
     m17_mod_dibits(d, 192);
+}
+void m17_send_packet_frames(uint8_t *packet, int len) {      // m17_tx_routines.cpp:323-353
+    auto &s = m17b_shim::S();
+    if (len < 0 || len > 798) { s.err = M17B_E_ARG; return; }
+    if (!s.ensure_tx() || !s.scratch(32 * 192 + 1024)) return;
+    uint16_t crc = m17_crc_array_encode(packet, len);
+    packet[len] = (uint8_t)(crc >> 8); packet[len + 1] = (uint8_t)crc;      // the caller's buffer must be 2 bytes longer (:325)
+    int32_t l32 = len, nf = 0;
+    s.up(s.dA, packet, (size_t)len);
+    s.up((uint8_t *)s.dC, &l32, 4);
+    if (s.chk(m17b_send_packet_frames(s.ctx, (const uint8_t *)s.dA, 0, (const int32_t *)s.dC, 1, 32, (uint8_t *)s.dB, (int32_t *)s.dC + 1, nullptr))) return;
+    s.down(&nf, (int32_t *)s.dC + 1, 4);
+    std::vector<uint8_t> d((size_t)nf * 192);
+    s.down(d.data(), s.dB, d.size());
+    for (int f = 0; f < nf; f++) m17_mod_dibits(&d[(size_t)f * 192], 192);
 }
 void m17_send_bert_frame(void) {
     auto &s = m17b_shim::S();

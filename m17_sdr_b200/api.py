@@ -419,6 +419,15 @@ class Tx:
         _l.check(self.L.m17b_fmt_packet_frames(self.ctx.h, _ptr(chunks), _ptr(meta), n, _ptr(out), _stream()))
         return out
 
+    def m17_send_packet_frames(self, packets, lengths, max_frames=32):
+        """packets uint8 [n][stride], lengths int32 [n] -> (dibits uint8 [n][max_frames][192], nframes int32 [n])."""
+        _chk_dev(packets, torch.uint8, "packets"); _chk_dev(lengths, torch.int32, "lengths")
+        n = packets.shape[0]
+        out = torch.empty((n, max_frames, 192), dtype=torch.uint8, device=packets.device)
+        nf = torch.empty((n,), dtype=torch.int32, device=packets.device)
+        _l.check(self.L.m17b_send_packet_frames(self.ctx.h, _ptr(packets), packets.shape[1], _ptr(lengths), n, max_frames, _ptr(out), _ptr(nf), _stream()))
+        return out, nf
+
     def m17_fmt_add_bert_frame(self, F):
         out = torch.empty((self.nchan, F, 192), dtype=torch.uint8, device=self.ctx.device)
         _l.check(self.L.m17b_fmt_bert_frames(self.h, F, _ptr(out), _stream()))

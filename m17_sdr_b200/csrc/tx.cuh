@@ -134,6 +134,56 @@ extern "C" int m17b_fmt_packet_frames(m17b_ctx *ctx, const uint8_t *d_chunk, con
     KERNEL_CHECK();
     return M17B_OK;
 }
+// m17_send_packet_frames (m17_tx_routines.cpp:323-353), batched: append the CRC-16 to each packet, cut it into 25-byte chunks,
+// non-final frames carry their index, the final frame EOF + the number of bytes used (25 when the split is exact).
+// One thread per packet prepares chunk / meta arrays for the frame formatter; slots past a packet's last frame are marked.
+__global__ void k_packet_split(const uint8_t *__restrict__ pk, int64_t stride, const int32_t *__restrict__ len, int64_t n, int max_frames,
+                               const uint16_t *__restrict__ g_crc, uint8_t *__restrict__ chunk, uint8_t *__restrict__ meta, int32_t *__restrict__ nframes) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t *p = pk + i * stride;
+    int L = len[i];
+    if (L < 0) L = 0;
+    if (L + 2 > 25 * max_frames) L = 25 * max_frames - 2;
+    uint16_t k = 0xFFFF;
+    for (int b = 0; b < L; b++) k = crc16_step(k, p[b], g_crc);
+    const int tot = L + 2, frames = tot / 25, left = tot % 25;
+    const int nf = left == 0 ? frames : frames + 1;
+    uint8_t *c = chunk + i * (int64_t)max_frames * 25;
+    for (int b = 0; b < max_frames * 25; b++) {
+        uint8_t v = 0;
+        if (b < L) v = p[b]; else if (b == L) v = (uint8_t)(k >> 8); else if (b == L + 1) v = (uint8_t)k;
+        c[b] = v;                                                  // m17_fmt_add_packet zero-pads the last chunk (:206-207)
+    }
+    for (int f = 0; f < max_frames; f++) {
+        uint8_t m = 0xFF;                                          // slot not used by this packet
+        if (f < nf - 1) m = (uint8_t)(f << 2);                     // eof = 0, frame number
+        else if (f == nf - 1) m = (uint8_t)(0x80 | ((left == 0 ? 25 : left) << 2));
+        meta[i * max_frames + f] = m;
+    }
+    nframes[i] = nf;
+}
+__global__ void k_packet_blank(const uint8_t *__restrict__ meta, int64_t nslots, uint8_t *__restrict__ dibits) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nslots * 192) return;
+    if (meta[t / 192] == 0xFF) dibits[t] = 4;                       // unused slot: blank carrier symbols (m17_mod_carrier)
+}
+extern "C" int m17b_send_packet_frames(m17b_ctx *ctx, const uint8_t *d_packets, int64_t stride, const int32_t *d_len, int64_t n, int max_frames,
+                                       uint8_t *d_dibits, int32_t *d_nframes, void *stream) {
+    if (!ctx || !d_packets || !d_len || !d_dibits || !d_nframes || n < 0 || max_frames < 1 || max_frames > 32 || stride < 0) return M17B_E_ARG;
+    if (n == 0) return M17B_OK;
+    cudaStream_t st = as_stream(stream);
+    uint8_t *chunk, *meta;
+    CUDA_TRY(cudaMallocAsync((void **)&chunk, (size_t)n * max_frames * 25, st));
+    CUDA_TRY(cudaMallocAsync((void **)&meta, (size_t)n * max_frames, st));
+    k_packet_split<<<grid_for(n, 128), 128, 0, st>>>(d_packets, stride, d_len, n, max_frames, ctx->d_crc, chunk, meta, d_nframes);
+    k_fmt<3><<<grid_for(n * max_frames * 192, 192), 192, 0, st>>>(chunk, meta, n * max_frames, 1, nullptr, d_dibits, ctx->d_genc, ctx->d_prbs);
+    k_packet_blank<<<grid_for(n * max_frames * 192, 256), 256, 0, st>>>(meta, n * max_frames, d_dibits);
+    KERNEL_CHECK();
+    CUDA_TRY(cudaFreeAsync(chunk, st));
+    CUDA_TRY(cudaFreeAsync(meta, st));
+    return M17B_OK;
+}
 extern "C" int m17b_fmt_stream_frames(m17b_tx *tx, const uint8_t *d_payload, int64_t F, uint8_t *d_dibits, void *stream) {
     if (!tx || !d_payload || !d_dibits || F < 0) return M17B_E_ARG;
     if (F == 0) return M17B_OK;

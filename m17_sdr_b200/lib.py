@@ -68,6 +68,7 @@ _SIGS = {
     "m17b_fmt_link_setup_frame": ([_vp, _vp, _i64, _vp, _vp], _i32),
     "m17b_fmt_stream_frames": ([_vp, _vp, _i64, _vp, _vp], _i32),
     "m17b_fmt_packet_frames": ([_vp, _vp, _vp, _i64, _vp, _vp], _i32),
+    "m17b_send_packet_frames": ([_vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp], _i32),
     "m17b_fmt_bert_frames": ([_vp, _i64, _vp, _vp], _i32),
     "m17b_mod_dibits": ([_vp, _vp, _i64, _vp, _vp, _vp], _i32),
     "m17b_build_lpf_filter": ([_vp, C.c_float, _i32], _i32),

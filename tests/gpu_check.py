@@ -522,6 +522,18 @@ def check_tx(ctx, P, nchan=6, F=12, seed=31, os_=10):
     assert np.array_equal(tx.fmt_preamble(), P.fmt_preamble()) and np.array_equal(tx.fmt_eot(), P.fmt_eot())
     got = tx.m17_fmt_add_link_setup_frame(dev(lsfs)).cpu().numpy()
     assert np.array_equal(got, np.stack([P.fmt_lsf(l) for l in lsfs])), "fmt lsf"
+    # m17_send_packet_frames: CRC + 25-byte chunking, including the exact-fit and single-frame cases
+    lens = [1, 22, 23, 24, 48, 73, 100, 200, 798]
+    pk = np.zeros((len(lens), 800), np.uint8)
+    for i, ln in enumerate(lens):
+        pk[i, :ln] = rng.integers(0, 256, ln, dtype=np.uint8)
+    dib, nfr = tx.m17_send_packet_frames(dev(pk), dev(np.array(lens, np.int32)))
+    dib, nfr = dib.cpu().numpy(), nfr.cpu().numpy()
+    for i, ln in enumerate(lens):
+        exp = signals.packet_frames(P, bytes(pk[i, :ln]))
+        assert nfr[i] == len(exp), ("packet frames", ln, nfr[i], len(exp))
+        assert np.array_equal(dib[i, :nfr[i]], np.stack(exp)), ("packet dibits", ln)
+        assert np.all(dib[i, nfr[i]:] == 4), "unused packet slots are blank carrier"
     tx.set_lsf(dev(lsfs))
     d1 = tx.m17_fmt_add_stream_frame(dev(pl[:, :F // 2])).cpu().numpy()
     d2 = tx.m17_fmt_add_stream_frame(dev(pl[:, F // 2:])).cpu().numpy()          # state carry: m_fn / m_lich_count
