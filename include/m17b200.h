@@ -123,6 +123,15 @@ int m17b_de_correlate_1_u8(m17b_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, i
 int m17b_de_correlate_1_f32(m17b_ctx *ctx, const float *d_in, float *d_out, int len, int64_t n, void *stream);
 /* m17_dsp_demap_frame (m17_dsp.cpp:82-95): n x 192 symbols -> n x 368 soft bits */
 int m17b_demap_frame(m17b_ctx *ctx, const float *d_sym, int64_t n, float *d_soft, void *stream);
+/* m17_dsp_demap_symbol (m17_dsp.cpp:35-42): n symbols, each with its own normaliser -> d_out [n][2] = {-m, |m| - 0.6666} */
+int m17b_demap_symbols(m17b_ctx *ctx, const float *d_in, const float *d_mag, int64_t n, float *d_out, void *stream);
+/* m17_dsp_decimating_filter (m17_dsp.cpp:438-449): n rows in_pitch floats apart, each len samples (+ flen-1 of look-ahead),
+   out[k] = sum_j in[k*stride+j]*coffs[j]; d_out [n][ceil(len/stride)]; the output length is returned through *out_len */
+int m17b_dsp_decimating_filter(m17b_ctx *ctx, const float *d_in, int64_t in_pitch, const float *d_coffs, int stride, int flen, int len, int64_t n,
+                               float *d_out, int *out_len, void *stream);
+/* m17_prbs9_rx_check (m17_prbs9.cpp:40-64) on n bit sequences (d_bits [n][nbits], one bit per byte) with persistent checker
+   state d_state uint32 [n][8] (layout of m17b_rx_get_bert; all zero = m17_prbs9_rx_reset in a fresh process) */
+int m17b_prbs9_rx_check(m17b_ctx *ctx, const uint8_t *d_bits, int nbits, int64_t n, uint32_t *d_state, void *stream);
 /* m17_sync_check (m17_rx_frame.cpp:47-81): n x 8 symbols -> type, votes, variance */
 int m17b_sync_check(m17b_ctx *ctx, const float *d_vec, int64_t n, uint8_t *d_type, uint8_t *d_votes, float *d_var, void *stream);
 /* m17_prbs9_tx_load (m17_prbs9.cpp:27-32): n sequences of len bits starting at phase start[i] (NULL = 0) */
@@ -254,6 +263,7 @@ int m17b_rx_net_frames(m17b_rx *rx, const uint16_t *d_sid, int have_dst, uint64_
 int m17b_eq_create(m17b_ctx *ctx, int64_t nchan, m17b_eq **out);   /* eq_open  :217-224 */
 int m17b_eq_destroy(m17b_eq *eq);
 int m17b_eq_reset(m17b_eq *eq, void *stream);                       /* eq_reset :137-141 */
+int m17b_eq_restart(m17b_eq *eq, void *stream);                     /* eq_restart :142-145 (U/D factors only) */
 /* eq_train_known / eq_train_unknown (:163-213) for nsym symbols per channel: d_in [nchan][nsym][2],
    d_train [nchan][nsym] or NULL (decision-directed) -> d_out [nchan][nsym] */
 int m17b_eq_train(m17b_eq *eq, const float *d_in, const float *d_train, int64_t nsym, float *d_out, void *stream);

@@ -63,8 +63,15 @@ uint24_t m17_golay_encode(uint12_t data);
 int m_17_golay_decode(uint24_t word, uint12_t &odata);
 uint16_t m17_crc_array_encode(uint8_t *in, int len);
 void m17_prbs9_tx_load(uint8_t *out, int len); void m17_prbs9_tx_reset(void);
+void m17_prbs9_rx_reset(void); int m17_prbs9_rx_check(uint8_t bit);          // m17_prbs9.cpp:36-64
+const uint32_t *m17b_shim_prbs9_state(void);   // {m_rx_state, m_rx_idx, m_rx_bad, m_rx_good, m_rx_eq_cnt, m_rx_dif_cnt, bits, errors}: file statics upstream
+void m17_dsp_demap_symbol(float in, float mag, float *out);
+void m17_dsp_build_lpf_filter(float *filter, float bw, int ntaps);
+void m17_dsp_float_to_short(float *in, int16_t *out, int len);
+int  m17_dsp_decimating_filter(float *in, float *out, float *coffs, int stride, int flen, int len);
+void m17_rx_parse(float *s, uint8_t type);     // one frame, record handed to the frame callback (no LICH state: see m17_dsp_rx)
 // equaliser
-void eq_open(void); void eq_reset(void); float eq_train_known(float *in, float train); float eq_train_unknown(float *in);
+void eq_open(void); void eq_reset(void); void eq_restart(void); float eq_train_known(float *in, float train); float eq_train_unknown(float *in);
 // TX
 uint16_t m17_pack_type(M17Type type);
 void m17_mod_dibits(uint8_t *dibits, int len); void m17_mod_carrier(void);
@@ -87,6 +94,7 @@ struct State {
     void *dA = nullptr, *dB = nullptr, *dC = nullptr; size_t cap = 0;
     m17b_shim_callbacks cb = {nullptr, nullptr, nullptr, nullptr};
     int os = 10, err = 0, prbs_idx = 0;
+    uint32_t prbs_rx[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     bool lock = false;
     std::vector<scmplx> txbuf;                 // m_tx_samples: flushed every 1920 samples (m17_modulate.cpp:30-33)
     std::vector<m17b_frame_rec> pend_fr; std::vector<m17b_event_rec> pend_ev;
@@ -287,6 +295,47 @@ void m17_prbs9_tx_load(uint8_t *out, int len) {
 }
 void eq_open(void) { auto &s = m17b_shim::S(); if (s.ensure()) { m17b_eq_destroy(s.eq); s.eq = nullptr; s.chk(m17b_eq_create(s.ctx, 1, &s.eq)); } }
 void eq_reset(void) { auto &s = m17b_shim::S(); if (s.ensure()) s.chk(m17b_eq_reset(s.eq, nullptr)); }
+void eq_restart(void) { auto &s = m17b_shim::S(); if (s.ensure()) s.chk(m17b_eq_restart(s.eq, nullptr)); }
+void m17_prbs9_rx_reset(void) { auto &s = m17b_shim::S(); s.prbs_rx[0] = 0; s.prbs_rx[1] = 0; }      // m_rx_idx = 0, NO_SYNC (:36-39)
+int m17_prbs9_rx_check(uint8_t bit) {
+    auto &s = m17b_shim::S();
+    if (!s.ensure() || !s.scratch(64)) return 0;
+    s.up(s.dA, &bit, 1);
+    s.up(s.dC, s.prbs_rx, 32);
+    if (s.chk(m17b_prbs9_rx_check(s.ctx, (const uint8_t *)s.dA, 1, 1, (uint32_t *)s.dC, nullptr))) return 0;
+    s.down(s.prbs_rx, s.dC, 32);
+    return 0;                                                                                          // as upstream (:63)
+}
+const uint32_t *m17b_shim_prbs9_state(void) { return m17b_shim::S().prbs_rx; }
+void m17_dsp_demap_symbol(float in, float mag, float *out) {
+    auto &s = m17b_shim::S();
+    if (!s.ensure() || !s.scratch(16)) return;
+    s.up(s.dA, &in, 4); s.up(s.dC, &mag, 4);
+    if (s.chk(m17b_demap_symbols(s.ctx, (const float *)s.dA, (const float *)s.dC, 1, (float *)s.dB, nullptr))) return;
+    s.down(out, s.dB, 8);
+}
+void m17_dsp_build_lpf_filter(float *filter, float bw, int ntaps) { m17b_build_lpf_filter(filter, bw, ntaps); }
+void m17_dsp_float_to_short(float *in, int16_t *out, int len) { m17b_float_to_short(in, out, len); }
+int m17_dsp_decimating_filter(float *in, float *out, float *coffs, int stride, int flen, int len) {
+    auto &s = m17b_shim::S();
+    const size_t nin = (size_t)len + flen;
+    if (len <= 0 || stride <= 0 || flen <= 0 || !s.ensure() || !s.scratch(nin * 4)) return 0;
+    int nout = 0;
+    s.up(s.dA, in, ((size_t)len + flen - 1) * 4);                 // upstream reads flen-1 samples past len
+    s.up(s.dC, coffs, (size_t)flen * 4);
+    if (s.chk(m17b_dsp_decimating_filter(s.ctx, (const float *)s.dA, (int64_t)nin, (const float *)s.dC, stride, flen, len, 1, (float *)s.dB, &nout, nullptr))) return 0;
+    s.down(out, s.dB, (size_t)nout * 4);
+    return nout;
+}
+void m17_rx_parse(float *sym, uint8_t type) {
+    auto &s = m17b_shim::S();
+    if (!s.ensure() || !s.scratch(192 * 4)) return;
+    s.up(s.dA, sym, 192 * 4); s.up(s.dC, &type, 1);
+    if (s.chk(m17b_rx_parse_frames(s.ctx, (const float *)s.dA, (const uint8_t *)s.dC, 1, (m17b_frame_rec *)s.dB, nullptr, nullptr))) return;
+    m17b_frame_rec r;
+    s.down(&r, s.dB, sizeof(r));
+    if (s.cb.frame) s.cb.frame(&r, s.cb.user);
+}
 static inline float m17b_shim_eq(float *in, const float *train) {
     auto &s = m17b_shim::S();
     float y = 0;

@@ -105,6 +105,30 @@ class Context:
         _l.check(self.L.m17b_net_parse(self.h, _ptr(frames), n, _ptr(ok), _ptr(sid), _ptr(lsf), _ptr(fn), _ptr(pld), _stream()))
         return ok, sid, lsf, fn, pld
 
+    def m17_dsp_demap_symbol(self, sym, mag):
+        _chk_dev(sym, torch.float32, "sym"); _chk_dev(mag, torch.float32, "mag")
+        out = self._new((sym.numel(), 2), torch.float32)
+        _l.check(self.L.m17b_demap_symbols(self.h, _ptr(sym), _ptr(mag), sym.numel(), _ptr(out), _stream()))
+        return out
+
+    def m17_dsp_decimating_filter(self, x, coffs, stride, length):
+        """x float32 [n][>= length + len(coffs) - 1] -> [n][ceil(length/stride)]."""
+        _chk_dev(x, torch.float32, "x"); _chk_dev(coffs, torch.float32, "coffs")
+        n, nout = x.shape[0], (length + stride - 1) // stride
+        out = self._new((n, nout), torch.float32)
+        ol = C.c_int()
+        _l.check(self.L.m17b_dsp_decimating_filter(self.h, _ptr(x), x.shape[1], _ptr(coffs), stride, coffs.numel(), length, n, _ptr(out), C.byref(ol), _stream()))
+        assert ol.value == nout
+        return out
+
+    def m17_prbs9_rx_check(self, bits, state=None):
+        """bits uint8 [n][nbits]; state int32 [n][8] (updated in place, zeros if None) -> state."""
+        _chk_dev(bits, torch.uint8, "bits")
+        if state is None:
+            state = torch.zeros((bits.shape[0], 8), dtype=torch.int32, device=bits.device)
+        _l.check(self.L.m17b_prbs9_rx_check(self.h, _ptr(bits), bits.shape[1], bits.shape[0], _ptr(state), _stream()))
+        return state
+
     # ---- bit-domain primitives (CUDA tensors in, CUDA tensors out)
     def m17_crc_array_encode(self, data):
         _chk_dev(data, torch.uint8, "data")
@@ -491,6 +515,9 @@ class Equalizer:
 
     def eq_reset(self):
         _l.check(self.L.m17b_eq_reset(self.h, _stream()))
+
+    def eq_restart(self):
+        _l.check(self.L.m17b_eq_restart(self.h, _stream()))
 
     def eq_train(self, pairs, train=None):
         _chk_dev(pairs, torch.float32, "pairs")

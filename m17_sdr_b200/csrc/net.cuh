@@ -118,3 +118,86 @@ extern "C" int m17b_rx_net_frames(m17b_rx *rx, const uint16_t *d_sid, int have_d
     KERNEL_CHECK();
     return M17B_OK;
 }
+
+// ================================================================ remaining small m17defines.h entry points, batched
+// m17_dsp_demap_symbol (m17_dsp.cpp:35-42): n symbols with their own normaliser -> n x {MSB soft, LSB soft}
+__global__ void k_demap_symbols(const float *__restrict__ in, const float *__restrict__ mag, int64_t n, float *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[2 * i] = demap_soft(in[i], mag[i], false);
+    out[2 * i + 1] = demap_soft(in[i], mag[i], true);
+}
+extern "C" int m17b_demap_symbols(m17b_ctx *ctx, const float *d_in, const float *d_mag, int64_t n, float *d_out, void *stream) {
+    if (!ctx || !d_in || !d_mag || !d_out || n < 0) return M17B_E_ARG;
+    if (n == 0) return M17B_OK;
+    k_demap_symbols<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(d_in, d_mag, n, d_out);
+    KERNEL_CHECK();
+    return M17B_OK;
+}
+// m17_dsp_decimating_filter (m17_dsp.cpp:438-449): out[k] = sum_j in[k*stride + j] * coffs[j], the sum started at 0 and added in
+// order (no contraction); n rows of `len` samples (+ flen - 1 of look-ahead, as upstream reads them), in_pitch apart
+__global__ void k_decimating_filter(const float *__restrict__ in, int64_t in_pitch, const float *__restrict__ coffs, int stride, int flen, int nout,
+                                    int64_t n, float *__restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * nout) return;
+    const int64_t r = t / nout; const int k = (int)(t % nout);
+    const float *s = in + r * in_pitch + (int64_t)k * stride;
+    float sum = 0;
+    for (int j = 0; j < flen; j++) sum += s[j] * coffs[j];
+    out[t] = sum;
+}
+extern "C" int m17b_dsp_decimating_filter(m17b_ctx *ctx, const float *d_in, int64_t in_pitch, const float *d_coffs, int stride, int flen, int len, int64_t n,
+                                          float *d_out, int *out_len, void *stream) {
+    if (!ctx || !d_in || !d_coffs || !d_out || stride < 1 || flen < 1 || len < 0 || n < 0) return M17B_E_ARG;
+    const int nout = (len + stride - 1) / stride;                  // for (i = 0; i < len; i += stride)
+    if (out_len) *out_len = nout;
+    if (n == 0 || nout == 0) return M17B_OK;
+    k_decimating_filter<<<grid_for(n * nout, 256), 256, 0, as_stream(stream)>>>(d_in, in_pitch, d_coffs, stride, flen, nout, n, d_out);
+    KERNEL_CHECK();
+    return M17B_OK;
+}
+// m17_prbs9_rx_check (m17_prbs9.cpp:40-64) over n independent bit sequences with persistent checker state
+// d_state uint32 [n][8]: m_rx_state, m_rx_idx, m_rx_bad, m_rx_good, m_rx_eq_cnt, m_rx_dif_cnt, bits checked in sync, bit errors
+// (zeros = m17_prbs9_rx_reset on a fresh process)
+__global__ void k_prbs9_rx_check(const uint8_t *__restrict__ bits, int nbits, int64_t n, uint32_t *st, const uint8_t *__restrict__ g_prbs) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    uint32_t *o = st + r * 8;
+    int state = (int)o[0], idx = (int)o[1];
+    unsigned bad = o[2], good = o[3], eq = o[4], dif = o[5], nb = o[6], ne = o[7];
+    for (int b = 0; b < nbits; b++) {
+        const unsigned d = (bits[r * nbits + b] ^ g_prbs[idx]) & 1u;
+        if (d) { dif = (dif + 1) & 0xFFFF; eq = 0; } else { eq = (eq + 1) & 0xFFFF; dif = 0; }
+        idx = idx + 1 == 511 ? 0 : idx + 1;
+        if (state == 0) {
+            bad = 0; good = 0;
+            if (eq >= 18) state = 1;
+            if (d) { idx = 0; state = 0; }
+        } else {
+            nb++; ne += d;
+            if (dif >= 18) state = 0;
+            if (d) bad = (bad + 1) & 0xFFFF;
+        }
+    }
+    o[0] = (uint32_t)state; o[1] = (uint32_t)idx; o[2] = bad; o[3] = good; o[4] = eq; o[5] = dif; o[6] = nb; o[7] = ne;
+}
+extern "C" int m17b_prbs9_rx_check(m17b_ctx *ctx, const uint8_t *d_bits, int nbits, int64_t n, uint32_t *d_state, void *stream) {
+    if (!ctx || !d_bits || !d_state || nbits < 0 || n < 0) return M17B_E_ARG;
+    if (n == 0 || nbits == 0) return M17B_OK;
+    k_prbs9_rx_check<<<grid_for(n, 128), 128, 0, as_stream(stream)>>>(d_bits, nbits, n, d_state, ctx->d_prbs);
+    KERNEL_CHECK();
+    return M17B_OK;
+}
+// eq_restart (m17_equalize.cpp:142-145): the U/D factors start over, the tap weights stay
+__global__ void k_eq_restart(EqState *st, int64_t nchan) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchan) return;
+    EqState &e = st[c];
+    for (int j = 0; j < 5; j++) { for (int i = 0; i < j; i++) e.u[i][j] = 0.0f; e.d[j] = 0.1f; }   // eq_k_reset_ud :25-36
+}
+extern "C" int m17b_eq_restart(m17b_eq *eq, void *stream) {
+    if (!eq) return M17B_E_ARG;
+    k_eq_restart<<<grid_for(eq->nchan, 128), 128, 0, as_stream(stream)>>>(eq->d_state, eq->nchan);
+    KERNEL_CHECK();
+    return M17B_OK;
+}

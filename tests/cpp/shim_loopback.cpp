@@ -47,6 +47,26 @@ int main() {
     const char *pk = "0000100011000010";
     for (int i = 0; i < 16; i++) EXPECT(prbs[i] == pk[i] - '0');
 
+    // ---- the smaller entry points of m17defines.h
+    float so2[2];
+    m17_dsp_demap_symbol(0.5f, 2.0f, so2);                                   // m = 1: MSB soft -1, LSB soft 1 - 0.6666
+    EXPECT(so2[0] == -1.0f && so2[1] == (float)(1.0 - 0.6666));
+    float lpf[31]; int16_t lpq[31];
+    m17_dsp_build_lpf_filter(lpf, 0.125f, 31);
+    EXPECT(lpf[15] == 0.25f && lpf[14] == lpf[16] && lpf[0] == lpf[30]);
+    m17_dsp_float_to_short(lpf, lpq, 31);
+    EXPECT(lpq[15] == (int16_t)(0.25f * 0x7FFF));
+    float din[40], dco[4] = {1.0f, 2.0f, 3.0f, 4.0f}, dout[16];
+    for (int i = 0; i < 40; i++) din[i] = (float)i;
+    EXPECT(m17_dsp_decimating_filter(din, dout, dco, 4, 4, 32) == 8);
+    for (int k = 0; k < 8; k++) EXPECT(dout[k] == (float)(4 * k) + 2.0f * (4 * k + 1) + 3.0f * (4 * k + 2) + 4.0f * (4 * k + 3));
+    uint8_t pr[64]; m17_prbs9_tx_reset(); m17_prbs9_tx_load(pr, 64); m17_prbs9_rx_reset();
+    for (int i = 0; i < 64; i++) m17_prbs9_rx_check(pr[i]);
+    EXPECT(m17b_shim_prbs9_state()[0] == 1 && m17b_shim_prbs9_state()[1] == 64 && m17b_shim_prbs9_state()[7] == 0);   // in sync, no errors
+    m17_prbs9_tx_reset();
+    eq_open(); eq_restart(); eq_reset();
+    EXPECT(m17b_shim_last_error() == 0);
+
     // ---- one over, looped back
     const int F = 14;
     uint8_t meta[14] = {0}, payload[F][16];
