@@ -165,6 +165,10 @@ int m17b_rx_get_bert(m17b_rx *rx, uint32_t *d_out, void *stream);
 int m17b_dsp_rx(m17b_rx *rx, const int16_t *d_iq, int64_t nblocks, void *stream);
 /* baseband seam (m17_test.cpp:49-51): m17_rx_sync_samples + m17_rx_symbols on d_disc = float [nchan][nblocks*384] */
 int m17b_rx_baseband(m17b_rx *rx, const float *d_disc, int64_t nblocks, void *stream);
+/* symbol seam: m17_rx_symbols / m17_rx_sym (m17_rx_frame.cpp:126-177) on symbols supplied by the caller (another demodulator, an
+   equaliser in front of the framer): framer FSM, frame decode, LICH / packet post stage.  d_syms float [nchan][pitch],
+   d_nsym int32 [nchan] = symbols of each channel (<= max_blocks*200).  Results as for m17b_dsp_rx, reported as one block. */
+int m17b_rx_symbols(m17b_rx *rx, const float *d_syms, int64_t pitch, const int32_t *d_nsym, void *stream);
 /* device views of the last call's results (valid until the next call on this rx) */
 typedef struct {
     int64_t nchan, nblocks;

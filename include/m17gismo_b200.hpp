@@ -11,6 +11,7 @@
 //  * RX results arrive through m17b_shim_callbacks (frame records + AOS/LOS events) right after m17_dsp_rx /
 //    m17_rx_symbols returns; the reference's gui_*/m17_db_*/m17_net_new_rx_data up-calls are the caller's to make.
 //  * m17_rx_sync_samples runs the framer too (the kernel is fused); m17_rx_symbols then only dispatches the records.
+//    (Symbols from elsewhere go through the batched ABI's m17b_rx_symbols.)
 //  * blocks must be whole: m17_dsp_rx takes 1920 IQ samples, m17_rx_sync_samples 384 samples (as m17_dsp_rx feeds it).
 //  * TX IQ is handed to m17b_shim_callbacks::transmit in 1920-sample blocks (radio_transmit_samples, radio.cpp:178).
 #ifndef M17GISMO_B200_HPP

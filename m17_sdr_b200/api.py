@@ -315,6 +315,13 @@ class Rx:
         _l.check(self.L.m17b_rx_baseband(self.h, _ptr(disc), disc.shape[1] // DISC_PER_BLOCK, _stream()))
         return self
 
+    def m17_rx_symbols(self, syms, nsym):
+        """Symbol seam: syms float32 CUDA [nchan][pitch], nsym int32 CUDA [nchan] (framer + decode + post only)."""
+        _chk_dev(syms, torch.float32, "syms"); _chk_dev(nsym, torch.int32, "nsym")
+        assert syms.shape[0] == self.nchan
+        _l.check(self.L.m17b_rx_symbols(self.h, _ptr(syms), syms.shape[1], _ptr(nsym), _stream()))
+        return self
+
     def m17_dsp_rx_host(self, iq_host, frames_host=None, nframes_host=None):
         """End-to-end form: iq_host is a (preferably pinned) CPU int16 tensor; returns (records uint8 [nchan][cap][64], nframes)."""
         assert iq_host.dtype == torch.int16 and not iq_host.is_cuda and iq_host.is_contiguous()

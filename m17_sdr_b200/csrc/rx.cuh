@@ -479,6 +479,28 @@ extern "C" int m17b_rx_baseband(m17b_rx *rx, const float *d_disc, int64_t nblock
     return rc;
 }
 
+// Symbol seam: m17_rx_symbols (m17_rx_frame.cpp:173-177) on symbols supplied by the caller -- framer, frame decode, post.
+// d_syms float [nchan][pitch], d_nsym int32 [nchan] symbols per channel (<= max_blocks * 200); results as for m17b_dsp_rx,
+// reported as one "block" (view.nblocks = 1, view.d_nsym[c] = symbols taken).
+extern "C" int m17b_rx_symbols(m17b_rx *rx, const float *d_syms, int64_t pitch, const int32_t *d_nsym, void *stream) {
+    if (!rx || !d_syms || !d_nsym || pitch < 0) return M17B_E_ARG;
+    m17b_ctx *ctx = rx->ctx;
+    cudaStream_t st = as_stream(stream);
+    rx->last_launches = 0; rx->last_blocks = 1; rx->seam_last = 2;
+    const int64_t cap = rx->sym_pitch - M17B_SYM_CARRY;
+    k_framer<<<grid_for(rx->nchan, 4), 128, 0, st>>>(d_syms, pitch, d_nsym, rx->nchan, rx->d_state, rx->d_syms, rx->sym_pitch, cap, rx->d_nsym, rx->d_sym_base,
+                                                   rx->d_frames, rx->fcap, rx->d_nframes, rx->d_events, rx->ecap, rx->d_nevents, rx->d_stats);
+    KERNEL_CHECK();
+    int rc = launch_decode(ctx, rx->d_syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base, rx->d_frames, rx->fcap, rx->d_nframes, rx->nchan, nullptr, st,
+                           rx->aux_stream, rx->ev_fork, rx->ev_join, nullptr, 0, rx->bert);
+    if (rc) return rc;
+    k_post<<<grid_for(rx->nchan, POST_WARPS), POST_WARPS * 32, 0, st>>>(rx->d_frames, rx->fcap, rx->d_nframes, rx->nchan, rx->d_state, ctx->d_crc, rx->d_stats,
+                                                                      rx->d_lsf_snap, rx->nsnap, rx->d_lsf_ver, ctx->d_prbs, rx->bert);
+    KERNEL_CHECK();
+    rx->last_launches = 4;
+    return M17B_OK;
+}
+
 // BERT receive.  Upstream decodes nothing for BERT frames (decode_bert_frame is empty); with this switched
 // on they are de-punctured / Viterbi-decoded like any other frame and their PRBS9 bits run through m17_prbs9_rx_check.
 extern "C" int m17b_rx_set_bert(m17b_rx *rx, int on) {

@@ -51,6 +51,7 @@ _SIGS = {
     "m17b_rx_get_bert": ([_vp, _vp, _vp], _i32),
     "m17b_dsp_rx": ([_vp, _vp, _i64, _vp], _i32),
     "m17b_rx_baseband": ([_vp, _vp, _i64, _vp], _i32),
+    "m17b_rx_symbols": ([_vp, _vp, _i64, _vp, _vp], _i32),
     "m17b_rx_get_view": ([_vp, C.POINTER(RxView)], _i32),
     "m17b_rx_frame_cap": ([_vp], _i64),
     "m17b_dsp_rx_host": ([_vp, _vp, _i64, _vp, _vp, _vp], _i32),

@@ -364,6 +364,41 @@ def check_udp_frames(ctx, P, seed=43):
     return "udp frames ok (%d packed/parsed exact, %d gateway datagrams over %d channels with an LSF change mid-call)" % (n, ntot, Cn)
 
 
+def check_rx_symbols(ctx, P, seed=53):
+    """Symbol seam (m17_rx_symbols on caller-supplied symbols): the oracle's own symbol streams of a noisy baseband run go
+    through framer + decode + post in one call and in ragged pieces; records and events must equal the oracle's."""
+    import m17_sdr_b200 as m
+    D, _ = signals.baseband_channels(P, 7, 12, seed, [None, 12, 9, 7, 5, 3, 1])
+    o = P.rx_run(D, seam=1)
+    Cn = D.shape[0]
+    ns = o.counts[:, 1].astype(np.int64)
+    T = D.shape[1] // 384
+    rx = m.Rx(ctx, Cn, T)
+    for pieces in (1, 3):
+        rx.reset()
+        frames, events = [[] for _ in range(Cn)], [[] for _ in range(Cn)]
+        cuts = [np.round(np.linspace(0, n, pieces + 1) + (np.arange(pieces + 1) % 2) * 5 * (pieces > 1)).astype(np.int64).clip(0, n) for n in ns]
+        for k in range(pieces):
+            cnt = np.array([cuts[c][k + 1] - cuts[c][k] for c in range(Cn)], np.int32)
+            buf = np.zeros((Cn, max(int(cnt.max()), 1)), np.float32)
+            for c in range(Cn):
+                buf[c, :cnt[c]] = o.syms[c, cuts[c][k]:cuts[c][k + 1]]
+            rx.m17_rx_symbols(dev(buf), dev(cnt))
+            r = rx.results()
+            for c in range(Cn):
+                frames[c].append(r["frames"][c, :r["nframes"][c]]); events[c].append(r["events"][c, :r["nevents"][c]])
+        for c in range(Cn):
+            nf, ne = int(o.counts[c, 2]), int(o.counts[c, 3])
+            fa = np.concatenate(frames[c]); ea = np.concatenate(events[c])
+            assert len(fa) == nf and len(ea) == ne, ("symbol seam counts", c, len(fa), nf, len(ea), ne)
+            for name in REC_DTYPE.names:
+                if name != "rsvd":
+                    assert bits_eq(fa[name], o.frames[c, :nf][name]), ("symbol seam rec." + name, c, pieces)
+            assert np.array_equal(ea, o.events[c, :ne]), ("symbol seam events", c, pieces)
+    rx.close()
+    return "rx symbols ok (%d ch, %d frames, one call and 3 ragged pieces)" % (Cn, int(o.counts[:, 2].sum()))
+
+
 def check_rx_bert(ctx, P, seed=47, nchan=8, F=14):
     """BERT receive: carrier, preambles, F BERT frames (m17_fmt_add_bert_frame), EOT at several noise levels.
     With the extension on, records (decoded PRBS bytes) and the m17_prbs9_rx_check state must equal the oracle's; with it off
@@ -644,6 +679,7 @@ CHECKS = [
     ("rx_chain_split", lambda c, P: check_rx_chain(c, P, nchan=6, seed=23, verbose=True, split=[1, 7, 2, 1, 13])),
     ("rx_packet", lambda c, P: check_rx_packet(c, P, verbose=True)),
     ("rx_afc", lambda c, P: check_rx_afc(c, P)),
+    ("rx_symbols", lambda c, P: check_rx_symbols(c, P)),
     ("rx_bert", lambda c, P: check_rx_bert(c, P)),
     ("decimator", lambda c, P: check_decimator(c, P)),
     ("udp_frames", lambda c, P: check_udp_frames(c, P)),

@@ -163,6 +163,11 @@ def test_frontend_tma_variant(ctx, port, monkeypatch):
     assert out.returncode == 0 and "FAILS 0" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
+def test_rx_symbol_seam(ctx, port):
+    """m17_rx_symbols on caller-supplied symbols (framer + decode + post)."""
+    print(gc.check_rx_symbols(ctx, port))
+
+
 def test_rx_bert(ctx, port):
     """BERT receive (decode + m17_prbs9_rx_check), off by default as upstream."""
     print(gc.check_rx_bert(ctx, port))
