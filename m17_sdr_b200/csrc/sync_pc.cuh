@@ -41,7 +41,9 @@ __global__ void __launch_bounds__(PC_CH * 64, 4) k_sync_frame_pc(const float *__
                                                                  int32_t *__restrict__ nevents, unsigned long long *stats, int commit_fe) {
     __shared__ __align__(16) SyncPcSmem sm_all[PC_CH];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int slot = wid >> 1, role = wid & 1;                     // warps 2s, 2s+1 serve channel slot s: A, B
+    // warps 2s, 2s+1 serve channel slot s.  Warp w of a CTA runs on scheduler w % 4, so the heavy A role alternates between
+    // even and odd warps from one CTA to the next: every scheduler gets A and B warps instead of two schedulers getting all A's
+    const int slot = wid >> 1, role = (wid + blockIdx.x) & 1;
     const int64_t c = (int64_t)blockIdx.x * PC_CH + slot;
     if (c >= nchan) return;                                        // both warps of the pair leave together
     SyncPcSmem &sm = sm_all[slot];
