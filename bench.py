@@ -93,6 +93,40 @@ class ClockSampler:
                 "power_w_max": max(float(r[3]) for r in rows)}
 
 
+# ------------------------------------------------------------------------------------------------ NUMA placement
+def bind_to_gpu_numa_node(torch, local):
+    """Pin this rank's host threads (and therefore its first-touch pinned buffers) to the NUMA node its GPU hangs off, so that
+    the end-to-end path's H2D copies do not cross the socket interconnect when several ranks feed their GPUs at once."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        if all(hasattr(pr, a) for a in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+            addr = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        else:
+            out = subprocess.run(["nvidia-smi", f"--id={local}", "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True,
+                                 env=clean_env()).stdout.strip().lower()
+            if not out:
+                return None
+            addr = out[-12:] if out.count(":") == 2 else "0000:" + out
+        path = f"/sys/bus/pci/devices/{addr}/numa_node"
+        if not os.path.exists(path):
+            return None
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except (OSError, ValueError, subprocess.SubprocessError, AttributeError):
+        pass
+    return None
+
+
 # ------------------------------------------------------------------------------------------------ workload
 def make_workload(ctx, m, torch, C, T, seed):
     """Synthetic stream-mode channels generated ON THE GPU with the library's own TX path (outside any timed
@@ -257,6 +291,7 @@ def run_cuda(args):
     if not torch.cuda.is_available():
         raise m.M17Error("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(torch, local) if (world > 1 and not under_profiler()) else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     m.build()
@@ -411,7 +446,7 @@ def run_cuda(args):
         "config": {"workload": f"configs[1]: {C} concurrent stream-mode channels per GPU x {T} blocks (10 s each), full m17_dsp_rx chain from int16 IQ "
                                f"(limiter, discriminator, RRC matched filter + timing loop, sync/framer, demap+gather, Viterbi, Golay, CRC, LICH), "
                                f"AWGN on IQ Eb/N0 {{22,24,26,30,inf}} dB, f0 +-1 kHz, random start delay",
-                   "channels_per_gpu": C, "blocks": T, "pipeline_slice_blocks": args.slice_blocks or 0, "l2": "input 1.97 GB per GPU >> 126 MB L2 (no flush needed)", "parallelism": f"channels sharded x{world}, no data-path collective"},
+                   "channels_per_gpu": C, "blocks": T, "pipeline_slice_blocks": args.slice_blocks or 0, "l2": "input 1.97 GB per GPU >> 126 MB L2 (no flush needed)", "parallelism": f"channels sharded x{world}, no data-path collective", "host_numa_node_rank0": numa},
         "e2e": {"value": frames_step / (e2e_ms / 1e3) / 25.0, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(C * T * 7680),
                 "d2h_bytes_per_step": int(C * rx.frame_cap * 64 + 4 * C), "records_equal_device_path": e2e_same},
         "gpu_launches": int(launches),
