@@ -95,6 +95,48 @@ __global__ void __launch_bounds__(POST_WARPS * 32) k_post(m17b_frame_rec *frames
         if (k < n) h = *(const uint4 *)(base + k);                 // bytes 0..15: sym_off, type, flags, golay_err, nbytes, lich[6], data[0..1]
         sm.hdr[lane] = h;
         __syncwarp();
+        // Fast path.  While a stream runs the same six LICH chunks repeat, so a batch of 32 records usually changes nothing in
+        // the cache; then every record's flags follow from the cache state alone and the lanes set them in parallel.  Any
+        // record that would modify per-channel state (a new LICH chunk, an LSF / packet / BERT frame) sends the whole batch
+        // down the in-order walk below.
+        {
+            const int type = h.y & 0xFF, fl = (h.y >> 8) & 0xFF;
+            const bool parsed = (k < n) && (fl & M17B_F_PARSED);
+            const int seq = (int)((h.w >> 8) & 0xFF) >> 5;                       // lich[5] >> 5
+            bool simple = true;
+            if (parsed) {
+                if (type == M17B_T_STREAM) {
+                    if (seq < 6) {
+                        const uint8_t l[5] = {(uint8_t)h.z, (uint8_t)(h.z >> 8), (uint8_t)(h.z >> 16), (uint8_t)(h.z >> 24), (uint8_t)h.w};
+#pragma unroll
+                        for (int i = 0; i < 5; i++) simple &= sm.lsf0[seq * 5 + i] == l[i];
+                    }
+                } else if (type == M17B_T_LSF || type == M17B_T_PACKET || (type == M17B_T_BERT && bert_on)) simple = false;
+            }
+            const int st0 = __shfl_sync(0xffffffffu, (int)lsf0_ok | ((int)lsf1_ok << 1) | ((int)dirty << 2), 0);
+            const int ver0 = __shfl_sync(0xffffffffu, ver, 0);
+            if (__all_sync(0xffffffffu, simple) && !(st0 & 4)) {
+                const bool ok0 = st0 & 1, ok1 = st0 & 2;                         // cache unchanged and clean: lsf[1] == lsf[0]
+                const bool is_stream = parsed && type == M17B_T_STREAM;
+                const bool ev = is_stream && seq < 6 && ok0;                     // update_lich -> copy_lich -> parse_lsf
+                const bool dl = is_stream && (ok1 || ev);                        // :148-158
+                int ge = is_stream ? (int)((h.y >> 16) & 0xFF) : 0;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) ge += __shfl_xor_sync(0xffffffffu, ge, d);
+                const unsigned ms = __ballot_sync(0xffffffffu, is_stream), me = __ballot_sync(0xffffffffu, ev), md = __ballot_sync(0xffffffffu, dl);
+                if (lane == 0) {
+                    n_stream += __popc(ms); n_gerr += (unsigned)ge; n_lsf += __popc(me); n_deliv += __popc(md);
+                    if (me) lsf1_ok = true;
+                }
+                if (k < n) {
+                    const int nf = fl | (ev ? M17B_F_LSF_EVENT : 0) | (dl ? M17B_F_DELIVERED : 0);
+                    if (nf != fl) ((uint8_t *)(base + k))[5] = (uint8_t)nf;
+                    lsf_ver[c * fcap + k] = parsed ? (uint8_t)ver0 : 0;
+                }
+                __syncwarp();
+                continue;
+            }
+        }
         if (lane == 0) {
             const int m = (n - k0 < 32) ? n - k0 : 32;
             for (int j = 0; j < m; j++) {
