@@ -301,6 +301,20 @@ __device__ __forceinline__ bool sync_accept(const SyncResult &r, bool locked) {
     if (r.type < 1 || r.type > 4) return false;
     return (double)r.variance < (locked ? 0.5 : 0.3);
 }
+// m17_unlocked_sync_check on one window, with an exact early-out.  Acceptance needs votes == 0, type in 1..4 and variance < 0.3.
+// variance < 0.3 means every |v[i]| >= 0.7 max|v| > 0, so no element is zero; votes == 0 then means the sign pattern of the
+// window IS the winning template's (and a window whose signs equal a template's correlates with it at the maximum possible
+// sum |v|, so that template wins the arg-max).  Hence: unless the sign pattern is exactly one of the four frame sync words,
+// the window cannot be accepted and the six correlations / variance need not be computed.  (A NaN element makes every
+// correlation NaN -> type 0 -> rejected; it also fails the sign test.)
+__device__ __forceinline__ bool sync_unlocked_ok(const float *v) {
+    unsigned negm = 0, posm = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { negm |= (v[i] < 0) ? (1u << i) : 0u; posm |= (v[i] > 0) ? (1u << i) : 0u; }
+    if ((negm ^ posm) != 0xFFu) return false;
+    if (negm != sync_neg_mask(1) && negm != sync_neg_mask(2) && negm != sync_neg_mask(3) && negm != sync_neg_mask(4)) return false;
+    return sync_accept(sync_check8(v), false);
+}
 __global__ void k_sync_check(const float *vec, int64_t n, uint8_t *type, uint8_t *votes, float *var) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;

@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(NW * 32) k_sync_frame_cta(const float *__restr
                             float w[8];
 #pragma unroll
                             for (int k = 0; k < 8; k++) { int idx = q - 7 + k; w[k] = (idx >= reset_at) ? sm.hist[8 + idx] : 0.0f; }
-                            ok = sync_accept(sync_check8(w), false);
+                            ok = sync_unlocked_ok(w);
                         }
                         const unsigned m = __ballot_sync(0xffffffffu, ok);
                         if (m) found = q0 + __ffs(m) - 1;
