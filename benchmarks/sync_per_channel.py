@@ -1,0 +1,23 @@
+"""Per-channel cost of the timing-loop kernel on the bench workload: cycles and speculation rounds by noise class."""
+import os, sys, numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench, m17_sdr_b200 as m
+ctx = m.Context(0)
+C, T = 1024, 250
+iq, payload = bench.make_workload(ctx, m, torch, C, T, seed=1000)
+rx = m.Rx(ctx, C, T)
+for _ in range(2): rx.reset(); rx.m17_dsp_rx(iq)
+torch.cuda.synchronize()
+d = rx.debug_sync().cpu().numpy()
+res = rx.results()
+fr = res["stats"]
+for k, name in enumerate(("22 dB", "24 dB", "26 dB", "30 dB", "clean")):
+    cyc = d[k::5, 0] / 1e6; rnd = d[k::5, 1]
+    print(f"{name}: Mcycles min/med/max {cyc.min():.2f}/{np.median(cyc):.2f}/{cyc.max():.2f}  rounds med/max {int(np.median(rnd))}/{int(rnd.max())}  frames med {int(np.median(fr[k::5, 0]))} los max {int(fr[k::5, 5].max())}")
+if d[:, 2:7].sum() > 0:
+    tot = d[:, 0].astype(float)
+    for j, name in enumerate(("staging", "timing loop", "emission", "framer", "carry")):
+        print(f"phase {name}: median {np.median(d[:, 2 + j]) / T:.0f} cycles/block ({100 * np.median(d[:, 2 + j] / tot):.0f} %)")
+w = int(np.argmax(d[:, 0]))
+print("slowest channel", w, "class", w % 5, "Mcycles", d[w, 0] / 1e6, "rounds", d[w, 1], "frames", fr[w, 0], "aos", fr[w, 4], "los", fr[w, 5])

@@ -193,6 +193,10 @@ int m17b_rx_stage_ms(m17b_rx *rx, int64_t call_index, float *h_out4);
    front end of slice k+1, the timing loop + framer of slice k and the frame decode of slice k-1 run concurrently on
    internal streams (results are identical).  0 = no slicing (stages strictly in sequence), the default. */
 int m17b_rx_set_slice_blocks(m17b_rx *rx, int blocks);
+/* instrumentation: d_out uint64 [nchan][8] = {SM cycles, speculation rounds, cycles in staging / timing loop / emission / framer /
+   carry (only in builds with -DM17B_PHASE_CLOCKS), spare} the one-warp-per-channel timing-loop kernel spent on each channel in its
+   last launch (the kernel's time is that of its slowest channel) */
+int m17b_rx_debug_sync(m17b_rx *rx, uint64_t *d_out, void *stream);
 /* number of kernels the last m17b_dsp_rx / m17b_rx_baseband call launched */
 int m17b_rx_last_launches(const m17b_rx *rx);
 

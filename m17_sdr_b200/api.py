@@ -341,6 +341,12 @@ class Rx:
         _l.check(self.L.m17b_rx_net_frames(self.h, _ptr(sid), 0 if dst is None else 1, int(dst or 0), _ptr(out), _ptr(cnt), _stream()))
         return out, cnt
 
+    def debug_sync(self):
+        """int64 [nchan][8]: SM cycles, speculation rounds, per-phase cycles of the last timing-loop launch, per channel."""
+        out = torch.zeros((self.nchan, 8), dtype=torch.int64, device=self.ctx.device)
+        _l.check(self.L.m17b_rx_debug_sync(self.h, _ptr(out), _stream()))
+        return out
+
     def set_slice_blocks(self, blocks):
         """Blocks per pipeline slice (0 = run the stages strictly in sequence); results do not depend on it."""
         _l.check(self.L.m17b_rx_set_slice_blocks(self.h, int(blocks)))

@@ -101,6 +101,10 @@ struct RxChanState {
     uint16_t prbs_idx, prbs_bad, prbs_good, prbs_eq, prbs_dif, prbs_pad;
     int      prbs_state;
     uint32_t bert_bits, bert_errs;
+    // instrumentation: SM cycles the timing-loop kernel spent on this channel in its last launch, rounds it ran
+    unsigned long long dbg_cycles;
+    uint32_t dbg_rounds, dbg_pad;
+    unsigned long long dbg_phase[6];   // cycles in: staging, timing loop, emission, framer, carry, (spare)
 };
 
 // ---------------------------------------------------------------- packed fp32 pairs (sm_100 FMUL2 / FADD2 / FFMA2)

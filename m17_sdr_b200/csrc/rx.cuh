@@ -550,6 +550,18 @@ extern "C" int m17b_rx_set_bert(m17b_rx *rx, int on) {
     rx->bert = on != 0;
     return M17B_OK;
 }
+__global__ void k_get_dbg(const RxChanState *st, int64_t nchan, unsigned long long *out) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < nchan) { out[8 * c] = st[c].dbg_cycles; out[8 * c + 1] = st[c].dbg_rounds; for (int i = 0; i < 6; i++) out[8 * c + 2 + i] = st[c].dbg_phase[i]; }
+}
+// instrumentation: per channel {SM cycles, speculation rounds, cycles per phase x6 (builds with -DM17B_PHASE_CLOCKS)} of the last
+// one-warp-per-channel timing-loop launch
+extern "C" int m17b_rx_debug_sync(m17b_rx *rx, uint64_t *d_out, void *stream) {
+    if (!rx || !d_out) return M17B_E_ARG;
+    k_get_dbg<<<grid_for(rx->nchan, 128), 128, 0, as_stream(stream)>>>(rx->d_state, rx->nchan, (unsigned long long *)d_out);
+    KERNEL_CHECK();
+    return M17B_OK;
+}
 __global__ void k_get_bert(const RxChanState *st, int64_t nchan, uint32_t *out) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nchan) return;

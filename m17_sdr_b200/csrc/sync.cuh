@@ -104,6 +104,14 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
     SyncWarpSmem &sm = sm_all[wid];
     RxChanState *S = st + c;
     float *out = sm.hist + 8;
+    const long long clk_start = clock64();
+    unsigned dbg_rounds = 0;
+#ifdef M17B_PHASE_CLOCKS
+    long long ph[5] = {0, 0, 0, 0, 0}, pt = clk_start;
+#define PHASE(i) do { const long long now__ = clock64(); ph[i] += now__ - pt; pt = now__; } while (0)
+#else
+#define PHASE(i) do {} while (0)
+#endif
 
     // ---- load state (uniform loads)
     // blocks [t0, t1) of a call of T blocks: t0 = 0 starts the call (symbol carry, record / event counts from zero),
@@ -168,6 +176,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
         if (t + 1 < t1) prefetch(t + 1, buf ^ 1);
         __syncwarp();
 
+        PHASE(0);
         // ---- timing loop (m17_rx_sync.cpp:77-99); m17_rx_lock() is constant inside a block
         const int TH = flock ? 80 : 10;
         int i = 0, m_idx = 0;
@@ -187,6 +196,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
                 for (int k = 0; k < M17B_FN; k++) tp[k] = pack2(__ldg(g_mf + index * M17B_FN + k), __ldg(g_md + index * M17B_FN + k));
                 tap_index = index;
             }
+            dbg_rounds++;
             if (flock && i <= 1) {
                 // Locked, at the start of a block: the threshold is 80, so a trip inside the block is rare -- speculate the
                 // whole block in ONE round, six consecutive symbols per lane (192 symbols, all inside the block for i <= 1).
@@ -295,6 +305,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
         }
         const int n = m_idx < 0 ? 0 : m_idx;
         __syncwarp();
+        PHASE(1);
 
         // ---- emit the block's symbols to the channel's stream
         {
@@ -303,6 +314,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
             if (lane == 0) nsym[c * T + t] = n;
         }
 
+        PHASE(2);
         // ---- framer (m17_rx_frame.cpp:126-172)
         int p = 0, reset_at = -8;
         while (p < n) {
@@ -369,6 +381,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
                 }
             }
         }
+        PHASE(3);
         // ---- carry: sliding window = last 8 symbols (zeros before a reset), filter history = last 30 samples
         {
             float wv = 0.0f, a = 0.0f;
@@ -380,6 +393,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
         }
         sym_total += n;
         __syncwarp();
+        PHASE(4);
     }
 
     // ---- store state
@@ -389,6 +403,10 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
         S->clk = clk; S->thr = thr; S->index = index; S->sum = sumc; S->dif = difc;
         S->flock = flock; S->fclk = fclk; S->ferr = ferr; S->frame_start = frame_start; S->sym_total = sym_total;
         S->prev_n = sym_total - base_g;
+        S->dbg_cycles = (unsigned long long)(clock64() - clk_start); S->dbg_rounds = dbg_rounds;
+#ifdef M17B_PHASE_CLOCKS
+        for (int q5 = 0; q5 < 5; q5++) S->dbg_phase[q5] = (unsigned long long)ph[q5];
+#endif
         nframes[c] = nfr < fcap ? nfr : (int)fcap;
         nevents[c] = nev < ecap ? nev : (int)ecap;
         if (frame_rng) frame_rng[c] = make_int2(nfr_entry, nfr < fcap ? nfr : (int)fcap);   // records completed by this slice

@@ -56,6 +56,7 @@ _SIGS = {
     "m17b_rx_frame_cap": ([_vp], _i64),
     "m17b_dsp_rx_host": ([_vp, _vp, _i64, _vp, _vp, _vp], _i32),
     "m17b_rx_last_launches": ([_vp], _i32),
+    "m17b_rx_debug_sync": ([_vp, _vp, _vp], _i32),
     "m17b_rx_set_slice_blocks": ([_vp, _i32], _i32),
     "m17b_rx_set_timing": ([_vp, _i32], _i32),
     "m17b_rx_stage_ms": ([_vp, _i64, _vp], _i32),
