@@ -15,7 +15,10 @@ fr = res["stats"]
 for k, name in enumerate(("22 dB", "24 dB", "26 dB", "30 dB", "clean")):
     cyc = d[k::5, 0] / 1e6; rnd = d[k::5, 1]
     print(f"{name}: Mcycles min/med/max {cyc.min():.2f}/{np.median(cyc):.2f}/{cyc.max():.2f}  rounds med/max {int(np.median(rnd))}/{int(rnd.max())}  frames med {int(np.median(fr[k::5, 0]))} los max {int(fr[k::5, 5].max())}")
-if d[:, 2:7].sum() > 0:
+if os.environ.get("M17B_SYNC_IMPL") == "64" and d[:, 2:8].sum() > 0:
+    for j, name in enumerate(("A staging", "A timing loop", "A wait for B", "A carry+publish", "B wait for A", "B emission+framer")):
+        print(f"phase {name}: median {np.median(d[:, 2 + j]) / T:.0f} cycles/block")
+elif d[:, 2:7].sum() > 0:
     tot = d[:, 0].astype(float)
     for j, name in enumerate(("staging", "timing loop", "emission", "framer", "carry")):
         print(f"phase {name}: median {np.median(d[:, 2 + j]) / T:.0f} cycles/block ({100 * np.median(d[:, 2 + j] / tot):.0f} %)")

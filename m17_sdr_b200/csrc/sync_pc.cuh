@@ -30,7 +30,9 @@ struct SyncPcSmem {
 };
 
 __device__ __forceinline__ void pc_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-__device__ __forceinline__ void pc_bar_arrive(int id) { __threadfence_block(); asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+// (no __threadfence_block here: a memory fence would also wait for the warp's outstanding GLOBAL traffic -- A's cp.async prefetch,
+//  B's symbol / record stores -- once per block; the barrier itself orders the shared-memory accesses of its participants)
+__device__ __forceinline__ void pc_bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 
 template <bool HAS_MEAN>
 __global__ void __launch_bounds__(PC_CH * 64, 4) k_sync_frame_pc(const float *__restrict__ disc, const float *__restrict__ mean, int64_t nchan, int64_t T,
@@ -59,6 +61,12 @@ __global__ void __launch_bounds__(PC_CH * 64, 4) k_sync_frame_pc(const float *__
         if (lane < 30) sm.x[lane & 3][lane >> 2] = S->tail[lane];
         int tap_index = -1;
         __syncwarp();
+#ifdef M17B_PHASE_CLOCKS
+        long long ph[4] = {0, 0, 0, 0}, pt = clock64();
+#define PCPH(i) do { const long long now__ = clock64(); ph[i] += now__ - pt; pt = now__; } while (0)
+#else
+#define PCPH(i) do {} while (0)
+#endif
         auto prefetch = [&](int64_t tt, int buf) {
             const float *src = disc + (c * T + tt) * 384;
 #pragma unroll
@@ -89,6 +97,7 @@ __global__ void __launch_bounds__(PC_CH * 64, 4) k_sync_frame_pc(const float *__
             }
             if (t + 1 < t1) prefetch(t + 1, buf ^ 1);
             __syncwarp();
+            PCPH(0);
             float *out = sm.sym[buf] + 8;
             const int s_clk = clk, s_thr = thr, s_index = index;
             const float s_sum = sumc, s_dif = difc;
@@ -118,7 +127,9 @@ __global__ void __launch_bounds__(PC_CH * 64, 4) k_sync_frame_pc(const float *__
                 }
                 n = m_idx < 0 ? 0 : m_idx;
                 if (attempt == 0) {
-                    pc_bar_sync(BAR_DONE);                                  // B has finished the previous block
+                    PCPH(1);
+                    pc_bar_sync(BAR_DONE);
+                    PCPH(2);                                  // B has finished the previous block
                     const int fl = *(volatile int *)&sm.flock_pub;
                     if (fl == flock) break;                                 // the speculation held (almost always)
                     flock = fl;                                             // acquisition or loss in the previous block: run again
@@ -135,7 +146,11 @@ __global__ void __launch_bounds__(PC_CH * 64, 4) k_sync_frame_pc(const float *__
             }
             pc_bar_arrive(BAR_FULL);
             __syncwarp();
+            PCPH(3);
         }
+#ifdef M17B_PHASE_CLOCKS
+        if (lane == 0) for (int q4 = 0; q4 < 4; q4++) S->dbg_phase[q4] = (unsigned long long)ph[q4];
+#endif
         pc_bar_sync(BAR_DONE);                                              // pairs with B's last arrival
         if (lane < 30) S->tail[lane] = sm.x[lane & 3][lane >> 2];
         if (lane == 0) { S->clk = clk; S->thr = thr; S->index = index; S->sum = sumc; S->dif = difc; }
@@ -164,9 +179,15 @@ __global__ void __launch_bounds__(PC_CH * 64, 4) k_sync_frame_pc(const float *__
     if (lane == 0) sm.flock_pub = flock;
     __syncwarp();
     pc_bar_arrive(BAR_DONE);                                                // initial credit: A may publish its first block
+#ifdef M17B_PHASE_CLOCKS
+    long long phb[2] = {0, 0}, ptb = clock64();
+#endif
     for (int64_t t = t0; t < t1; t++) {
         const int buf = (int)((t - t0) & 1);
         pc_bar_sync(BAR_FULL);
+#ifdef M17B_PHASE_CLOCKS
+        { const long long now__ = clock64(); phb[0] += now__ - ptb; ptb = now__; }
+#endif
         float *hist = sm.sym[buf];
         const int n = *(volatile int *)&sm.n[buf];
         // ---- emit the block's symbols to the channel's stream
@@ -252,7 +273,13 @@ __global__ void __launch_bounds__(PC_CH * 64, 4) k_sync_frame_pc(const float *__
         if (lane == 0) sm.flock_pub = flock;
         __syncwarp();
         pc_bar_arrive(BAR_DONE);
+#ifdef M17B_PHASE_CLOCKS
+        { const long long now__ = clock64(); phb[1] += now__ - ptb; ptb = now__; }
+#endif
     }
+#ifdef M17B_PHASE_CLOCKS
+    if (lane == 0) { S->dbg_phase[4] = (unsigned long long)phb[0]; S->dbg_phase[5] = (unsigned long long)phb[1]; S->dbg_cycles = (unsigned long long)(phb[0] + phb[1]); }
+#endif
     // ---- store state
     {
         const int last = (int)((t1 - t0) & 1);                              // the window of the next block sits in this buffer
