@@ -16,7 +16,9 @@
 #pragma once
 #include "frontend.cuh"
 
+#ifndef SY_WARPS
 #define SY_WARPS 4
+#endif
 #define SY_XQ   106           // (30 + 384 + 2 + 8 pad) / 4 entries per residue class
 #define SY_HIST  (8 + 208)
 
