@@ -320,6 +320,8 @@ def run_cuda(args):
     # ---- device-resident throughput ("value")
     if args.slice_blocks is not None:
         rx.set_slice_blocks(args.slice_blocks)
+    if args.chan_groups is not None:
+        rx.set_chan_groups(args.chan_groups)
     for _ in range(args.warmup):
         step()
     sync_all()
@@ -446,7 +448,7 @@ def run_cuda(args):
         "config": {"workload": f"configs[1]: {C} concurrent stream-mode channels per GPU x {T} blocks (10 s each), full m17_dsp_rx chain from int16 IQ "
                                f"(limiter, discriminator, RRC matched filter + timing loop, sync/framer, demap+gather, Viterbi, Golay, CRC, LICH), "
                                f"AWGN on IQ Eb/N0 {{22,24,26,30,inf}} dB, f0 +-1 kHz, random start delay",
-                   "channels_per_gpu": C, "blocks": T, "pipeline_slice_blocks": args.slice_blocks or 0, "l2": "input 1.97 GB per GPU >> 126 MB L2 (no flush needed)", "parallelism": f"channels sharded x{world}, no data-path collective", "host_numa_node_rank0": numa},
+                   "channels_per_gpu": C, "blocks": T, "pipeline_slice_blocks": args.slice_blocks or 0, "channel_groups": "auto (3 independent channel-group chains on their own streams at 512..1184 channels)" if args.chan_groups is None else args.chan_groups, "l2": "input 1.97 GB per GPU >> 126 MB L2 (no flush needed)", "parallelism": f"channels sharded x{world}, no data-path collective", "host_numa_node_rank0": numa},
         "e2e": {"value": frames_step / (e2e_ms / 1e3) / 25.0, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(C * T * 7680),
                 "d2h_bytes_per_step": int(C * rx.frame_cap * 64 + 4 * C), "records_equal_device_path": e2e_same},
         "gpu_launches": int(launches),
@@ -477,6 +479,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--channels", type=int, default=CHANNELS_PER_GPU)
     ap.add_argument("--blocks", type=int, default=BLOCKS)
+    ap.add_argument("--chan-groups", type=int, default=None, help="independent channel-group chains per call (1 = one chain); default: library default (auto)")
     ap.add_argument("--slice-blocks", type=int, default=None, help="blocks per pipeline slice (0 = stages in sequence); default: library default")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup

@@ -18,6 +18,17 @@ for k, name in enumerate(("22 dB", "24 dB", "26 dB", "30 dB", "clean")):
 if os.environ.get("M17B_SYNC_IMPL") == "64" and d[:, 2:8].sum() > 0:
     for j, name in enumerate(("A staging", "A timing loop", "A wait for B", "A carry+publish", "B wait for A", "B emission+framer")):
         print(f"phase {name}: median {np.median(d[:, 2 + j]) / T:.0f} cycles/block")
+if os.environ.get("M17B_SYNC_IMPL") == "65":
+    rr = d[:, 1]
+    full, part, miss, unl = rr & 255, (rr >> 8) & 255, (rr >> 16) & 255, (rr >> 24) & 255
+    print("blocks of the reporting warp (every second block): predicted + no trip", int(full.sum()), " predicted + trip", int(part.sum()),
+          " mispredicted while locked", int(miss.sum()), " unlocked", int(unl.sum()))
+    for k, name in enumerate(("22 dB", "24 dB", "26 dB", "30 dB", "clean")):
+        print(f"  {name}: median per channel full/trip/miss/unlocked {int(np.median(full[k::5]))}/{int(np.median(part[k::5]))}/{int(np.median(miss[k::5]))}/{int(np.median(unl[k::5]))}")
+if os.environ.get("M17B_SYNC_IMPL") == "65" and d[:, 2:8].sum() > 0:
+    # the warp that ran the channel's last block reports its own clocks: it handled every second block
+    for j, name in enumerate(("staging", "speculative dot products + votes", "wait for the hand-off", "resolve: trip test / commit / fallback rounds", "emission + framer", "hand-off")):
+        print(f"phase {name}: median {np.median(d[:, 2 + j]) / (T / 2):.0f} cycles per own block")
 elif d[:, 2:7].sum() > 0:
     tot = d[:, 0].astype(float)
     for j, name in enumerate(("staging", "timing loop", "emission", "framer", "carry")):

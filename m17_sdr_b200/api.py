@@ -351,6 +351,10 @@ class Rx:
         """Blocks per pipeline slice (0 = run the stages strictly in sequence); results do not depend on it."""
         _l.check(self.L.m17b_rx_set_slice_blocks(self.h, int(blocks)))
 
+    def set_chan_groups(self, groups):
+        """Run the batch as `groups` independent channel groups on their own streams (0 / 1 = one chain); results do not depend on it."""
+        _l.check(self.L.m17b_rx_set_chan_groups(self.h, int(groups)))
+
     def set_timing(self, on=True):
         _l.check(self.L.m17b_rx_set_timing(self.h, int(on)))
 

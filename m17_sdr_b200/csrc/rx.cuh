@@ -12,6 +12,7 @@
 
 #define M17B_TIMING_RING 64
 #define M17B_MAX_SLICES 16
+#define M17B_MAX_GROUPS 8
 struct m17b_rx {
     m17b_ctx *ctx;
     int64_t nchan, max_blocks, last_blocks;
@@ -36,7 +37,13 @@ struct m17b_rx {
     cudaStream_t s_fe, s_sync, s_dec;
     cudaEvent_t ev_start, ev_fe[M17B_MAX_SLICES], ev_sy[M17B_MAX_SLICES], ev_end;
     int2 *d_frame_rng;                // [M17B_MAX_SLICES][nchan] records completed by each slice
-    int sync_impl;                    // -1 auto; 0: warp per channel (sync.cuh); 2 / 4: CTA of that many warps per channel (sync_cta.cuh); 8 / 16 / 32: lanes per channel (sync_g.cuh); 33: 32 lanes with taps in smem; 64: producer/consumer warp pair (sync_pc.cuh)
+    // channel-group pipeline (see m17b_dsp_rx): the channels are cut into chan_groups contiguous groups, each running its own
+    // front end -> sync -> decode -> post chain on its own stream, so that the latency-bound timing loop of one group shares the SMs
+    // with the throughput-bound front end / decode of another.  Channels are independent: results do not depend on it.
+    int chan_groups;                  // -1 = auto (3 groups for 512..1184 channels, measured on B200: 2.18 -> 2.04 ms at 1024 x 250), 0 / 1 = off
+    cudaStream_t s_grp[M17B_MAX_GROUPS], s_grp_aux[M17B_MAX_GROUPS];
+    cudaEvent_t ev_gfork, ev_gjoin[M17B_MAX_GROUPS], ev_gf[M17B_MAX_GROUPS], ev_gj[M17B_MAX_GROUPS];
+    int sync_impl;                    // -1 auto; 0: warp per channel (sync.cuh); 2 / 4: CTA of that many warps per channel (sync_cta.cuh); 8 / 16 / 32: lanes per channel (sync_g.cuh); 33: 32 lanes with taps in smem; 64: producer/consumer warp pair (sync_pc.cuh); 65: two warps alternating blocks (sync_xb.cuh)
     int timing;                       // record cudaEvents around each stage of the next calls (bench only)
     cudaEvent_t ev_stage[M17B_TIMING_RING][5];
     int64_t tcount;                   // calls made since timing was enabled
@@ -243,6 +250,14 @@ extern "C" int m17b_rx_destroy(m17b_rx *rx) {
     if (rx->ev_start) cudaEventDestroy(rx->ev_start);
     if (rx->ev_end) cudaEventDestroy(rx->ev_end);
     for (int i = 0; i < M17B_MAX_SLICES; i++) { if (rx->ev_fe[i]) cudaEventDestroy(rx->ev_fe[i]); if (rx->ev_sy[i]) cudaEventDestroy(rx->ev_sy[i]); }
+    for (int g = 0; g < M17B_MAX_GROUPS; g++) {
+        if (rx->s_grp[g]) cudaStreamDestroy(rx->s_grp[g]);
+        if (rx->s_grp_aux[g]) cudaStreamDestroy(rx->s_grp_aux[g]);
+        if (rx->ev_gjoin[g]) cudaEventDestroy(rx->ev_gjoin[g]);
+        if (rx->ev_gf[g]) cudaEventDestroy(rx->ev_gf[g]);
+        if (rx->ev_gj[g]) cudaEventDestroy(rx->ev_gj[g]);
+    }
+    if (rx->ev_gfork) cudaEventDestroy(rx->ev_gfork);
     if (rx->copy_stream) cudaStreamDestroy(rx->copy_stream);
     if (rx->aux_stream) cudaStreamDestroy(rx->aux_stream);
     if (rx->ev_fork) cudaEventDestroy(rx->ev_fork);
@@ -313,6 +328,8 @@ extern "C" int m17b_rx_create(m17b_ctx *ctx, int64_t nchan, int64_t max_blocks, 
     }
     rx->slice_blocks = 0;          // measured on B200: slicing gives no gain at 1024 channels (the kernels contend for issue slots), see DESIGN.md 4
     if (const char *e2 = getenv("M17B_SLICE_BLOCKS")) rx->slice_blocks = atoi(e2);
+    rx->chan_groups = -1;
+    if (const char *e3 = getenv("M17B_CHAN_GROUPS")) rx->chan_groups = atoi(e3);
     int rc = m17b_rx_reset(rx, nullptr);
     if (rc) { m17b_rx_destroy(rx); return rc; }
     CUDA_TRY(cudaStreamSynchronize(nullptr));
@@ -369,6 +386,11 @@ static int launch_sync(m17b_rx *rx, int64_t c0, int64_t nc, const float *disc, c
         const unsigned g = grid_for(nc, SY_WARPS);
         if (mean) k_sync_frame_g<true, 32, true><<<g, SY_WARPS * 32, smem, st>>>(SYNC_ARGS);
         else      k_sync_frame_g<false, 32, true><<<g, SY_WARPS * 32, smem, st>>>(SYNC_ARGS);
+    } else if (impl == 65) {
+        // two warps per channel alternating blocks: dot products + votes of block t+1 speculated while block t is resolved (sync_xb.cuh)
+        const unsigned g = grid_for(nc, XB_CH);
+        if (mean) k_sync_frame_xb<true><<<g, XB_CH * 64, 0, st>>>(SYNC_ARGS);
+        else      k_sync_frame_xb<false><<<g, XB_CH * 64, 0, st>>>(SYNC_ARGS);
     } else if (impl == 64) {
         // two warps per channel, producer (timing loop) / consumer (framer): sync_pc.cuh
         const unsigned g = grid_for(nc, PC_CH);
@@ -410,8 +432,12 @@ static int launch_sync(m17b_rx *rx, int64_t c0, int64_t nc, const float *disc, c
 // idle) and the frame decode of slice k-1 (ALU-bound) run on three streams and share the SMs; events carry the only true
 // dependencies (FE(k) -> SYNC(k), SYNC(k-1) -> SYNC(k) by stream order, SYNC(k) -> DECODE(k)).  Results are identical
 // to the single-slice order: every kernel reads and writes exactly what it would have.
-static int rx_pipeline(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t *d_iq, const float *disc_in, int64_t T, cudaStream_t st, bool allow_slices = true) {
+static int rx_pipeline(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t *d_iq, const float *disc_in, int64_t T, cudaStream_t st, bool allow_slices = true,
+                       int grp = -1) {
     m17b_ctx *ctx = rx->ctx;
+    // the stream / events of the side-by-side LSF/packet decode: the object's own, or the channel group's
+    cudaStream_t aux_stream = grp >= 0 ? rx->s_grp_aux[grp] : rx->aux_stream;
+    cudaEvent_t ev_fork = grp >= 0 ? rx->ev_gf[grp] : rx->ev_fork, ev_join = grp >= 0 ? rx->ev_gj[grp] : rx->ev_join;
     float *disc_w = rx->d_disc + c0 * T * 384, *mean_w = rx->d_mean + c0 * T;
     const float *disc = d_iq ? disc_w : disc_in, *mean = d_iq ? mean_w : nullptr;
     const int commit_fe = d_iq ? 1 : 0;
@@ -432,7 +458,7 @@ static int rx_pipeline(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t *d_iq,
         }
         STAGE_MARK(2);
         int rc = launch_decode(ctx, syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0, nc, nullptr, st,
-                               rx->aux_stream, rx->ev_fork, rx->ev_join, nullptr, 0, rx->bert);
+                               aux_stream, ev_fork, ev_join, nullptr, 0, rx->bert);
         if (rc) return rc;
         STAGE_MARK(3);
         k_post<<<grid_for(nc, POST_WARPS), POST_WARPS * 32, 0, st>>>(frames, rx->fcap, rx->d_nframes + c0, nc, rx->d_state + c0, ctx->d_crc, rx->d_stats + c0 * 8,
@@ -455,7 +481,7 @@ static int rx_pipeline(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t *d_iq,
         if (rc) return rc;
         STAGE_MARK(2);
         rc = launch_decode(ctx, syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0, nc, nullptr, st,
-                           rx->aux_stream, rx->ev_fork, rx->ev_join, nullptr, 0, rx->bert);
+                           aux_stream, ev_fork, ev_join, nullptr, 0, rx->bert);
         if (rc) return rc;
         STAGE_MARK(3);
         k_post<<<grid_for(nc, POST_WARPS), POST_WARPS * 32, 0, st>>>(frames, rx->fcap, rx->d_nframes + c0, nc, rx->d_state + c0, ctx->d_crc, rx->d_stats + c0 * 8,
@@ -488,7 +514,7 @@ static int rx_pipeline(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t *d_iq,
         CUDA_TRY(cudaStreamWaitEvent(rx->s_dec, rx->ev_sy[k], 0));
         const int64_t span = t1 - t0;
         rc = launch_decode(ctx, syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0, nc, nullptr, rx->s_dec,
-                           rx->aux_stream, rx->ev_fork, rx->ev_join, rng, span + span / 64 + 4, rx->bert);
+                           aux_stream, ev_fork, ev_join, rng, span + span / 64 + 4, rx->bert);
         if (rc) return rc;
         rx->last_launches += 3;
     }
@@ -503,11 +529,50 @@ static int rx_pipeline(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t *d_iq,
 }
 
 
+// The whole batch as chan_groups independent chains on their own streams (fork from / join into st).
+static int rx_grouped(m17b_rx *rx, const int16_t *d_iq, const float *d_disc, int64_t T, cudaStream_t st, int G) {
+    if (!rx->ev_gfork) {
+        int lo = 0, hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_TRY(cudaEventCreateWithFlags(&rx->ev_gfork, cudaEventDisableTiming));
+        for (int g = 0; g < M17B_MAX_GROUPS; g++) {
+            CUDA_TRY(cudaStreamCreateWithPriority(&rx->s_grp[g], cudaStreamNonBlocking, lo));
+            CUDA_TRY(cudaStreamCreateWithPriority(&rx->s_grp_aux[g], cudaStreamNonBlocking, lo));
+            CUDA_TRY(cudaEventCreateWithFlags(&rx->ev_gjoin[g], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&rx->ev_gf[g], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&rx->ev_gj[g], cudaEventDisableTiming));
+        }
+    }
+    CUDA_TRY(cudaEventRecord(rx->ev_gfork, st));
+    const int64_t per = (rx->nchan + G - 1) / G;
+    for (int g = 0; g < G; g++) {
+        const int64_t c0 = g * per, nc = (rx->nchan - c0 < per) ? rx->nchan - c0 : per;
+        if (nc <= 0) break;
+        CUDA_TRY(cudaStreamWaitEvent(rx->s_grp[g], rx->ev_gfork, 0));
+        int rc = rx_pipeline(rx, c0, nc, d_iq ? d_iq + c0 * T * 3840 : nullptr, d_disc ? d_disc + c0 * T * 384 : nullptr, T, rx->s_grp[g], false, g);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(rx->ev_gjoin[g], rx->s_grp[g]));
+        CUDA_TRY(cudaStreamWaitEvent(st, rx->ev_gjoin[g], 0));
+    }
+    return M17B_OK;
+}
+static int rx_groups_for(const m17b_rx *rx) {
+    int G = rx->chan_groups;
+    // auto: while every channel's timing loop is resident at once (<= 8 x 148 channels) the sync kernel ends with a tail of slow
+    // channels on mostly idle SMs; three staggered groups fill it with the next group's front end / decode.  Below 512 channels
+    // and above one wave nothing is gained (benchmarks/chan_groups.py).  More than 4 groups exceed the 8 hardware queues.
+    if (G < 0) G = (rx->nchan >= 512 && rx->nchan <= 8 * 148) ? 3 : 1;
+    if (G > M17B_MAX_GROUPS) G = M17B_MAX_GROUPS;
+    if (G < 2 || rx->timing || rx->afc || rx->nchan < 2 * G) return 1;
+    return G;
+}
+
 extern "C" int m17b_dsp_rx(m17b_rx *rx, const int16_t *d_iq, int64_t nblocks, void *stream) {
     if (!rx || !d_iq || nblocks <= 0) return M17B_E_ARG;
     if (nblocks > rx->max_blocks) return M17B_E_CAPACITY;
     rx->last_launches = 0; rx->last_blocks = nblocks; rx->seam_last = 0;
-    int rc = rx_pipeline(rx, 0, rx->nchan, d_iq, nullptr, nblocks, as_stream(stream));
+    const int G = rx_groups_for(rx);
+    int rc = G > 1 ? rx_grouped(rx, d_iq, nullptr, nblocks, as_stream(stream), G) : rx_pipeline(rx, 0, rx->nchan, d_iq, nullptr, nblocks, as_stream(stream));
     if (rx->timing) rx->tcount++;
     return rc;
 }
@@ -516,7 +581,8 @@ extern "C" int m17b_rx_baseband(m17b_rx *rx, const float *d_disc, int64_t nblock
     if (!rx || !d_disc || nblocks <= 0) return M17B_E_ARG;
     if (nblocks > rx->max_blocks) return M17B_E_CAPACITY;
     rx->last_launches = 0; rx->last_blocks = nblocks; rx->seam_last = 1;
-    int rc = rx_pipeline(rx, 0, rx->nchan, nullptr, d_disc, nblocks, as_stream(stream));
+    const int G = rx_groups_for(rx);
+    int rc = G > 1 ? rx_grouped(rx, nullptr, d_disc, nblocks, as_stream(stream), G) : rx_pipeline(rx, 0, rx->nchan, nullptr, d_disc, nblocks, as_stream(stream));
     if (rx->timing) rx->tcount++;
     return rc;
 }
@@ -607,6 +673,12 @@ extern "C" int m17b_rx_stage_ms(m17b_rx *rx, int64_t call_index, float *out4) {
         if (i == 0 && rx->seam_last) continue;
         CUDA_TRY(cudaEventElapsedTime(&out4[i], ev[i], ev[i + 1]));
     }
+    return M17B_OK;
+}
+// channel groups (0 / 1 = the whole batch as one chain)
+extern "C" int m17b_rx_set_chan_groups(m17b_rx *rx, int groups) {
+    if (!rx || groups < -1 || groups > M17B_MAX_GROUPS) return M17B_E_ARG;
+    rx->chan_groups = groups;
     return M17B_OK;
 }
 // blocks per pipeline slice (0 = no slicing: the stages run strictly one after the other)

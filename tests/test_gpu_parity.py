@@ -143,7 +143,7 @@ def test_udp_frames(ctx, port):
     print(gc.check_udp_frames(ctx, port))
 
 
-@pytest.mark.parametrize("impl", [2, 4, 8, 16, 32, 33, 64])
+@pytest.mark.parametrize("impl", [2, 4, 8, 16, 32, 33, 64, 65])
 def test_sync_kernel_variants(ctx, port, impl, monkeypatch):
     """Every timing-loop / framer kernel variant (CTA per channel, G lanes per channel, taps in shared memory, producer /
     consumer warp pair) is bit-exact against the oracle on the IQ chain with split calls and on the packet-mode set."""
@@ -221,6 +221,15 @@ def test_full_size_properties(ctx):
         assert np.array_equal(a["frames"].view(np.uint8), b["frames"].view(np.uint8)) and np.array_equal(a["nsym"], b["nsym"]), sb
         assert np.array_equal(a["stats"], b["stats"]) and np.array_equal(a["events"], b["events"]) and gc.bits_eq(a["syms"], b["syms"]), sb
     rx.set_slice_blocks(0)
+    # channel-group pipelining (independent chains on their own streams; the default at this size is 3 groups): same bytes
+    for G in (1, 2, 4, 7):
+        rx.set_chan_groups(G)
+        rx.reset()
+        rx.m17_dsp_rx(iq)
+        b = rx.results()
+        assert np.array_equal(a["frames"].view(np.uint8), b["frames"].view(np.uint8)) and np.array_equal(a["nsym"], b["nsym"]), G
+        assert np.array_equal(a["stats"], b["stats"]) and np.array_equal(a["events"], b["events"]) and gc.bits_eq(a["syms"], b["syms"]), G
+    rx.set_chan_groups(-1)
     rx.reset()
     parts = [25] * 10
     nf = np.zeros(C, np.int64)
