@@ -272,7 +272,8 @@ extern "C" int m17b_rx_reset(m17b_rx *rx, void *stream) {
     cudaStream_t st = as_stream(stream);
     k_rx_reset<<<grid_for(rx->nchan, 128), 128, 0, st>>>(rx->d_state, rx->nchan);
     KERNEL_CHECK();
-    CUDA_TRY(cudaMemsetAsync(rx->d_syms, 0, sizeof(float) * rx->nchan * rx->sym_pitch, st));
+    // only the carry region (the "last 192 symbols of the previous call") is ever read before it is written
+    CUDA_TRY(cudaMemset2DAsync(rx->d_syms, sizeof(float) * rx->sym_pitch, 0, sizeof(float) * M17B_SYM_CARRY, (size_t)rx->nchan, st));
     CUDA_TRY(cudaMemsetAsync(rx->d_stats, 0, sizeof(unsigned long long) * rx->nchan * 8, st));
     CUDA_TRY(cudaMemsetAsync(rx->d_nframes, 0, sizeof(int32_t) * rx->nchan, st));
     CUDA_TRY(cudaMemsetAsync(rx->d_nevents, 0, sizeof(int32_t) * rx->nchan, st));
@@ -330,6 +331,8 @@ extern "C" int m17b_rx_create(m17b_ctx *ctx, int64_t nchan, int64_t max_blocks, 
     if (const char *e2 = getenv("M17B_SLICE_BLOCKS")) rx->slice_blocks = atoi(e2);
     rx->chan_groups = -1;
     if (const char *e3 = getenv("M17B_CHAN_GROUPS")) rx->chan_groups = atoi(e3);
+    e = cudaMemset(rx->d_syms, 0, sizeof(float) * nchan * rx->sym_pitch);
+    if (e != cudaSuccess) { m17b_set_cuda_error(e, __FILE__, __LINE__); m17b_rx_destroy(rx); return M17B_E_CUDA; }
     int rc = m17b_rx_reset(rx, nullptr);
     if (rc) { m17b_rx_destroy(rx); return rc; }
     CUDA_TRY(cudaStreamSynchronize(nullptr));
