@@ -198,6 +198,15 @@ int m17b_rx_set_slice_blocks(m17b_rx *rx, int blocks);
    independent (m17_dsp_rx keeps all state per receiver), so results do not depend on it.  0 / 1 = one chain; -1 = automatic
    (the default: 3 groups for 512..1184 channels, one chain otherwise). */
 int m17b_rx_set_chan_groups(m17b_rx *rx, int groups);
+/* Experimental scheduling mode (off by default; results identical, tested): the front end and the timing loop + framer run as
+   two CO-RESIDENT kernels.  The front end walks the batch in time-major order on a capped grid-stride grid and counts finished
+   (channel, block) items per time slice of `slice_blocks` blocks (0 = keep, default 10); each timing-loop warp waits -- bounded,
+   an expired wait makes the next call fail loudly -- for a slice's counter before fetching the slice's first block.
+   Measured on B200 at 1024 x 250: the pair takes 1.64 ms side by side against 0.63 + 1.02 ms one after the other. */
+int m17b_rx_set_overlap(m17b_rx *rx, int on, int slice_blocks);
+/* instrumentation of the overlapped front end | timing loop mode (M17B_OVERLAP=1): h_out4 = %globaltimer ns of {front end first
+   start, front end last end, timing loop first start, timing loop last end} of the last such call.  Synchronises the device. */
+int m17b_rx_debug_overlap(m17b_rx *rx, uint64_t *h_out4);
 /* instrumentation: d_out uint64 [nchan][8] = {SM cycles, speculation rounds, cycles in staging / timing loop / emission / framer /
    carry (only in builds with -DM17B_PHASE_CLOCKS), spare} the one-warp-per-channel timing-loop kernel spent on each channel in its
    last launch (the kernel's time is that of its slowest channel) */

@@ -351,6 +351,16 @@ class Rx:
         """Blocks per pipeline slice (0 = run the stages strictly in sequence); results do not depend on it."""
         _l.check(self.L.m17b_rx_set_slice_blocks(self.h, int(blocks)))
 
+    def set_overlap(self, on, slice_blocks=0):
+        """Experimental: front end and timing loop as two co-resident kernels coupled by per-time-slice counters (results identical)."""
+        _l.check(self.L.m17b_rx_set_overlap(self.h, int(on), int(slice_blocks)))
+
+    def debug_overlap(self):
+        """ns (relative to the front end's first start) of {front end end, timing loop start, timing loop end} of the last overlapped call."""
+        out = (C.c_uint64 * 4)()
+        _l.check(self.L.m17b_rx_debug_overlap(self.h, out))
+        return {"fe_end": int(out[1]) - int(out[0]), "sync_start": int(out[2]) - int(out[0]), "sync_end": int(out[3]) - int(out[0])}
+
     def set_chan_groups(self, groups):
         """Run the batch as `groups` independent channel groups on their own streams (0 / 1 = one chain); results do not depend on it."""
         _l.check(self.L.m17b_rx_set_chan_groups(self.h, int(groups)))

@@ -100,20 +100,31 @@ __device__ __forceinline__ LimSample fe_limit(uint32_t raw, float *mo = nullptr,
 // Items are the (channel, block) pairs of blocks [t0, t0+Tc) of a call of T blocks per channel (T is the row pitch of iq,
 // disc and mean); the whole call is t0 = 0, Tc = T.  Sub-ranges let the host pipeline the front end of one time slice with
 // the timing loop of the previous one (rx.cuh).
+// fe_done != NULL (the front end running BESIDE the timing-loop kernel, rx.cuh): items are taken in TIME-major order (all channels
+// of block 0, then of block 1, ..) and every finished unit adds its item count to fe_done[slice] (slice = block / slice_blocks)
+// after a device-scope fence, so that the consumer can start on a time slice as soon as all of its rows are in memory.
+// OVL = false is the plain kernel (one unit per warp, channel-major order, no counters).
+template <bool OVL>
 __global__ void __launch_bounds__(FE_WARPS * 32, 7) k_frontend(const uint32_t *__restrict__ iq, int64_t nchan, int64_t T, int64_t t0, int64_t Tc,
-                                                            RxChanState *st, float *__restrict__ disc, float *__restrict__ mean) {
+                                                            RxChanState *st, float *__restrict__ disc, float *__restrict__ mean,
+                                                            int *fe_done, int slice_blocks) {
     __shared__ float tout[FE_WARPS][32][17];
     __shared__ __align__(16) uint4 stage[FE_WARPS][2][160];      // two 20-sample chunks of the warp's 32 rows
     __shared__ int64_t gsl[FE_WARPS][32];                        // global (channel, block) index of each lane's item
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t nitems = nchan * Tc;
-    const int64_t item0 = ((int64_t)blockIdx.x * FE_WARPS + wid) * 32;
-    if (item0 >= nitems) return;
+    unsigned long long *ovl_tm = (OVL && fe_done) ? (unsigned long long *)(fe_done + 1000) : nullptr;   // instrumentation: first start / last end
+    if (OVL && ovl_tm && threadIdx.x == 0) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); atomicMin(ovl_tm + 0, now); }
+    // a warp takes units of 32 items with a grid stride: one unit per warp when the grid covers the batch (the default), several
+    // when the host caps the grid to bound how many front-end CTAs sit on an SM beside the timing-loop kernel (rx.cuh)
+    for (int64_t item0 = ((int64_t)blockIdx.x * FE_WARPS + wid) * 32; item0 < nitems; item0 += OVL ? (int64_t)gridDim.x * FE_WARPS * 32 : nitems) {
     const bool live = item0 + lane < nitems;
     const int64_t item = live ? item0 + lane : nitems - 1;       // dead lanes shadow the last item (results discarded)
-    const int64_t ch = item / Tc, t = t0 + item % Tc;
+    const bool tmajor = OVL && fe_done != nullptr;
+    const int64_t ch = tmajor ? item % nchan : item / Tc, t = t0 + (tmajor ? item / nchan : item % Tc);
     const int64_t g = ch * T + t;
     gsl[wid][lane] = g;
+    __syncwarp();
 
     // carried discriminator state: z[0], z[1] are the two previous LIMITED samples (m17_dsp.cpp:196,205-206)
     float z0re, z0im, z1re, z1im;
@@ -152,15 +163,15 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 7) k_frontend(const uint32_t *_
     // pitch = 4 x 5 words, conflict-free for 16-byte row reads), and each lane reads its own row back.  Everything is sized
     // for 28 resident warps per SM (<= 72 registers, 7.5 KB of shared memory per warp): the 8000 warp-units of the 1024 x 250
     // workload then fit in two full waves of 148 x 28.
-    uint32_t off[5];                                               // piece offsets (in 16-byte units) relative to the warp's first row
+    int32_t off[5];                                                // piece offsets (in 16-byte units, signed) relative to the warp's first row
     const uint4 *base = (const uint4 *)(iq + gsl[wid][0] * 1920);
 #pragma unroll
     for (int k = 0; k < 5; k++) {
         const int p = lane + 32 * k, r = p / 5;
         int64_t it = item0 + r;
         if (it >= nitems) it = nitems - 1;
-        const int64_t gr = (it / Tc) * T + t0 + it % Tc;
-        off[k] = (uint32_t)((gr - gsl[wid][0]) * 480 + (p - 5 * r));
+        const int64_t gr = tmajor ? (it % nchan) * T + t0 + it / nchan : (it / Tc) * T + t0 + it % Tc;
+        off[k] = (int32_t)((gr - gsl[wid][0]) * 480 + (p - 5 * r));
     }
     // two tiles of 160 pieces (one 20-sample chunk of the warp's 32 rows each), filled two chunks ahead with 16-byte cp.async:
     // completion is tracked by the async-copy group, NOT by a register scoreboard -- with plain loads into registers the
@@ -202,6 +213,27 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 7) k_frontend(const uint32_t *_
         mean[g] = (acc * 0.5f) / 1920.0f;                     // offset/len (m17_dsp.cpp:214)
         if (t == T - 1) { st[ch].nz0re = z0re; st[ch].nz0im = z0im; st[ch].nz1re = z1re; st[ch].nz1im = z1im; }
     }
+    if (!OVL) return;
+    asm volatile("cp.async.wait_group 0;");                   // (only empty groups are left; keeps the group count per unit fixed)
+    if (fe_done) {
+        // publish: every lane's stores (discriminator rows, mean) become visible device-wide, then the unit is counted
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+            const int64_t last = (item0 + 31 < nitems ? item0 + 31 : nitems - 1);
+            const int64_t per_slice = nchan * slice_blocks;      // items per full slice (time-major order)
+            const int s_lo = (int)(item0 / per_slice), s_hi = (int)(last / per_slice);
+            if (s_lo == s_hi) atomicAdd(fe_done + s_lo, (int)(last - item0 + 1));
+            else {
+                const int64_t first_hi = (int64_t)s_hi * per_slice;
+                atomicAdd(fe_done + s_lo, (int)(first_hi - item0));
+                atomicAdd(fe_done + s_hi, (int)(last - first_hi + 1));
+            }
+        }
+    }
+    __syncwarp();
+    }
+    if (OVL && ovl_tm && lane == 0) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); atomicMax(ovl_tm + 1, now); }
 }
 
 // ---------------------------------------------------------------- TMA-staged variant

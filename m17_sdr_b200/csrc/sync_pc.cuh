@@ -40,7 +40,8 @@ __global__ void __launch_bounds__(PC_CH * 64, 4) k_sync_frame_pc(const float *__
                                                                  const float *__restrict__ g_md, float *syms, int64_t sym_pitch,
                                                                  int32_t *__restrict__ nsym, int32_t *__restrict__ sym_base, m17b_frame_rec *frames,
                                                                  int64_t fcap, int32_t *__restrict__ nframes, m17b_event_rec *events, int64_t ecap,
-                                                                 int32_t *__restrict__ nevents, unsigned long long *stats, int commit_fe) {
+                                                                 int32_t *__restrict__ nevents, unsigned long long *stats, int commit_fe,
+        const int * /*fe_done*/, int /*fe_slice*/, int * /*fe_err*/) {
     __shared__ __align__(16) SyncPcSmem sm_all[PC_CH];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // warps 2s, 2s+1 serve channel slot s.  Warp w of a CTA runs on scheduler w % 4, so the heavy A role alternates between

@@ -230,6 +230,15 @@ def test_full_size_properties(ctx):
         assert np.array_equal(a["frames"].view(np.uint8), b["frames"].view(np.uint8)) and np.array_equal(a["nsym"], b["nsym"]), G
         assert np.array_equal(a["stats"], b["stats"]) and np.array_equal(a["events"], b["events"]) and gc.bits_eq(a["syms"], b["syms"]), G
     rx.set_chan_groups(-1)
+    # overlapped mode (front end and timing loop as co-resident kernels coupled by per-slice counters): same bytes
+    for sl in (10, 7, 125):
+        rx.set_overlap(True, sl)
+        rx.reset()
+        rx.m17_dsp_rx(iq)
+        b = rx.results()
+        assert np.array_equal(a["frames"].view(np.uint8), b["frames"].view(np.uint8)) and np.array_equal(a["nsym"], b["nsym"]), sl
+        assert np.array_equal(a["stats"], b["stats"]) and np.array_equal(a["events"], b["events"]) and gc.bits_eq(a["syms"], b["syms"]), sl
+    rx.set_overlap(False)
     rx.reset()
     parts = [25] * 10
     nf = np.zeros(C, np.int64)
