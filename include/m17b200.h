@@ -163,7 +163,7 @@ int m17b_rx_set_bert(m17b_rx *rx, int on);
 int m17b_rx_get_bert(m17b_rx *rx, uint32_t *d_out, void *stream);
 /* m17_dsp_rx (m17_dsp.cpp:461-476) for nchan channels x nblocks blocks: d_iq = int16 [nchan][nblocks*1920][2] */
 int m17b_dsp_rx(m17b_rx *rx, const int16_t *d_iq, int64_t nblocks, void *stream);
-/* baseband seam (m17_test.cpp:49-51): m17_rx_sync_samples + m17_rx_symbols on d_disc = float [nchan][nblocks*384] */
+/* baseband seam (m17_test.cpp:49-51): m17_rx_sync_samples + m17_rx_symbols on d_disc = float [nchan][nblocks*384], 16-byte aligned */
 int m17b_rx_baseband(m17b_rx *rx, const float *d_disc, int64_t nblocks, void *stream);
 /* symbol seam: m17_rx_symbols / m17_rx_sym (m17_rx_frame.cpp:126-177) on symbols supplied by the caller (another demodulator, an
    equaliser in front of the framer): framer FSM, frame decode, LICH / packet post stage.  d_syms float [nchan][pitch],

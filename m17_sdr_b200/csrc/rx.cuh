@@ -672,7 +672,7 @@ extern "C" int m17b_dsp_rx(m17b_rx *rx, const int16_t *d_iq, int64_t nblocks, vo
 }
 
 extern "C" int m17b_rx_baseband(m17b_rx *rx, const float *d_disc, int64_t nblocks, void *stream) {
-    if (!rx || !d_disc || nblocks <= 0) return M17B_E_ARG;
+    if (!rx || !d_disc || nblocks <= 0 || ((uintptr_t)d_disc & 15)) return M17B_E_ARG;      // rows are fetched in 16-byte pieces
     if (nblocks > rx->max_blocks) return M17B_E_CAPACITY;
     rx->last_launches = 0; rx->last_blocks = nblocks; rx->seam_last = 1;
     const int G = rx_groups_for(rx);

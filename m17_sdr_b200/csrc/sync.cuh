@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
                                                               m17b_event_rec *events, int64_t ecap, int32_t *__restrict__ nevents,
                                                               unsigned long long *stats, int commit_fe,
                                                               const int *fe_done, int fe_slice, int *fe_err) {
-    __shared__ SyncWarpSmem sm_all[SY_WARPS];
+    __shared__ __align__(16) SyncWarpSmem sm_all[SY_WARPS];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t c = (int64_t)blockIdx.x * SY_WARPS + wid;
     if (c >= nchan) return;
@@ -168,9 +168,9 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
     auto prefetch = [&](int64_t tt, int buf) {
         const float *src = disc + (c * T + tt) * 384;
 #pragma unroll
-        for (int q = 0; q < 12; q++) {
-            const unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.pre[buf][lane + 32 * q]);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src + lane + 32 * q));
+        for (int q = 0; q < 3; q++) {                                          // 96 pieces of 16 bytes (rows are 1536-byte aligned)
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.pre[buf][4 * (lane + 32 * q)]);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + 4 * (lane + 32 * q)));
         }
         if (HAS_MEAN) {
             if (OVL && fe_done) {
@@ -195,11 +195,16 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
         {
             const float pmu = !HAS_MEAN ? 0.0f : (OVL && fe_done) ? pmu_pf : sm.pre[buf][384];
 #pragma unroll
-            for (int q = 0; q < 12; q++) {
-                float v = sm.pre[buf][lane + 32 * q];
-                if (HAS_MEAN) v = v - pmu;                                  // m17_dsp.cpp:217-219
-                const int n = 30 + lane + 32 * q;
-                sm.x[n & 3][n >> 2] = v;
+            for (int q = 0; q < 3; q++) {
+                // four consecutive samples 4m .. 4m+3 (m = lane + 32 q) land at n = 30 + 4m + j: residue (2 + j) & 3, slot
+                // 7 + m + ((2 + j) >> 2) -- every store has consecutive lanes on consecutive words of one residue array
+                const int mq = lane + 32 * q;
+                float4 v = *(const float4 *)&sm.pre[buf][4 * mq];
+                if (HAS_MEAN) { v.x = v.x - pmu; v.y = v.y - pmu; v.z = v.z - pmu; v.w = v.w - pmu; }   // m17_dsp.cpp:217-219
+                sm.x[2][7 + mq] = v.x;
+                sm.x[3][7 + mq] = v.y;
+                sm.x[0][8 + mq] = v.z;
+                sm.x[1][8 + mq] = v.w;
             }
         }
         if (t + 1 < t1) { FE_GATE(t + 1); prefetch(t + 1, buf ^ 1); }
@@ -339,7 +344,12 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
         // ---- emit the block's symbols to the channel's stream
         {
             float *dst = sbuf + M17B_SYM_CARRY + (sym_total - base_g);
-            for (int q = lane; q < n; q += 32) dst[q] = out[q];
+            if (n == 192) {                                                    // no slip in this block: six independent copies
+#pragma unroll
+                for (int k = 0; k < 6; k++) dst[lane + 32 * k] = out[lane + 32 * k];
+            } else {
+                for (int q = lane; q < n; q += 32) dst[q] = out[q];
+            }
             if (lane == 0) nsym[c * T + t] = n;
         }
 
