@@ -356,6 +356,49 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
         PHASE(2);
         // ---- framer (m17_rx_frame.cpp:126-172)
         int p = 0, reset_at = -8;
+        if (flock && fclk + n >= M17B_FRAME_SYMS && fclk + n < 2 * M17B_FRAME_SYMS) {
+            // The common case while locked, straight-line: the frame being collected completes inside this block (after p1 of its
+            // symbols) and the next one takes the rest.  Same steps as the general loop below (m17_rx_frame.cpp:126-157).
+            const int p1 = M17B_FRAME_SYMS - fclk;
+            float w[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) w[k] = (k < fclk) ? sm.head[k] : sm.hist[8 + k - fclk];      // m_f_sym[0..7]
+            const SyncResult r = sync_check8(w);
+            const bool ok = sync_accept(r, true);
+            int flags = ok ? M17B_F_SYNC_OK : 0, fe;
+            bool los = false;
+            if (r.type == M17B_T_EOT) { los = true; fe = ferr; }                       // :137-140
+            else if (ok) { flags |= M17B_F_PARSED; ferr = 0; fe = 0; }                 // :144-146
+            else { ferr++; fe = ferr; if (ferr > 5) los = true; else flags |= M17B_F_PARSED; }   // :147-154
+            if (los) flags |= M17B_F_LOS;
+            if (nfr < fcap && lane < 16) {
+                uint32_t word = 0;
+                if (lane == 0) word = (uint32_t)frame_start;
+                else if (lane == 1) word = (uint32_t)r.type | ((uint32_t)flags << 8);
+                else if (lane == 11) word = ((uint32_t)r.votes << 16) | ((uint32_t)fe << 24);
+                else if (lane == 12) word = __float_as_uint(r.variance);
+                ((uint32_t *)(frames + c * fcap + nfr))[lane] = word;
+            }
+            nfr++;
+            const int fclk_in = fclk;
+            fclk = 0;
+            p = p1;
+            frame_start = sym_total + p1;
+            __syncwarp();                                                               // every lane has read the old head
+            if (los) {
+                if (lane < 8 && lane >= fclk_in) sm.head[lane] = sm.hist[8 + lane - fclk_in];   // (the head as the general loop leaves it)
+                flock = 0;
+                reset_at = p1;                                                          // reset_sync(): window reads as zeros
+                if (lane == 0 && nev < ecap) { events[c * ecap + nev].sym_idx = sym_total + p1 - 1; events[c * ecap + nev].kind = M17B_EV_LOS; }
+                nev++; n_los++;
+            } else {
+                const int rest = n - p1;                                                // < 192: the next frame stays open
+                if (lane < 8 && lane < rest) sm.head[lane] = sm.hist[8 + p1 + lane];
+                fclk = rest;
+                p = n;
+                __syncwarp();
+            }
+        }
         while (p < n) {
             if (!flock) {
                 int found = -1;
