@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
     int nfr = t0 == 0 ? 0 : nframes[c], nev = t0 == 0 ? 0 : nevents[c], n_aos = 0, n_los = 0;
     const int nfr_entry = nfr;
     f32x2 tp[M17B_FN];                      // (matched, derivative) tap pairs of the current polyphase branch
-    int tap_index = -1;
+    int tap_index = -1, trips_prev = 0;
     __syncwarp();
     // The block's samples are fetched one block ahead with cp.async straight into shared memory: completion is tracked by
     // the async-copy group, not by a register scoreboard, so nothing in the timing loop ever waits on the DRAM latency.
@@ -214,6 +214,12 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
         // ---- timing loop (m17_rx_sync.cpp:77-99); m17_rx_lock() is constant inside a block
         const int TH = flock ? 80 : 10;
         int i = 0, m_idx = 0;
+        // Round size is a pure scheduling choice (any speculation length gives the same result).  Locked (threshold 80) a trip is
+        // rare and the whole block goes in one round.  Unlocked (threshold 10) it depends on the input: on a tracked signal the
+        // counter trips less than once per block and the one-round form is ~1/3 cheaper than three 64-symbol rounds; on noise it
+        // trips every few dozen symbols and short rounds waste less.  So: one round if the previous block tripped at most once.
+        const bool whole_block = flock || trips_prev <= 1;
+        int trips = 0;
         while (i < 384) {
             if (clk == 1) {
                 // even-clock sample with no fresh symbol in this round: vote with the carried sum/dif (sync_update :38-42)
@@ -231,7 +237,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
                 tap_index = index;
             }
             dbg_rounds++;
-            if (flock && i <= 1) {
+            if (whole_block && i <= 1) {
                 // Locked, at the start of a block: the threshold is 80, so a trip inside the block is rare -- speculate the
                 // whole block in ONE round, six consecutive symbols per lane (192 symbols, all inside the block for i <= 1).
                 float s6[6], d6[6];
@@ -277,6 +283,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
                     sumc = __shfl_sync(0xffffffffu, ssel, L);
                     difc = __shfl_sync(0xffffffffu, dsel, L);
                     clk = 0;
+                    trips++;
                     __syncwarp();
                     sync_adjust(TH, thr, index, clk, m_idx, out, lane);
                     i = i + 2 * P + 2;
@@ -332,12 +339,14 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
                 sumc = (P & 1) ? s1 : s0;
                 difc = (P & 1) ? d1 : d0;
                 clk = 0;
+                trips++;
                 __syncwarp();
                 sync_adjust(TH, thr, index, clk, m_idx, out, lane);
                 i = i + 2 * P + 2;
             }
         }
         const int n = m_idx < 0 ? 0 : m_idx;
+        trips_prev = trips;
         __syncwarp();
         PHASE(1);
 
