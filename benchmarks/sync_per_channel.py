@@ -34,4 +34,6 @@ elif d[:, 2:7].sum() > 0:
     for j, name in enumerate(("staging", "timing loop", "emission", "framer", "carry")):
         print(f"phase {name}: median {np.median(d[:, 2 + j]) / T:.0f} cycles/block ({100 * np.median(d[:, 2 + j] / tot):.0f} %)")
 w = int(np.argmax(d[:, 0]))
+if os.environ.get("M17B_SYNC_IMPL", "0") in ("0", "") and d[:, 2:7].sum() > 0:
+    print("slowest channel, cycles per block by phase:", {name: int(d[w, 2 + j] / T) for j, name in enumerate(("staging", "timing loop", "emission", "framer", "carry"))})
 print("slowest channel", w, "class", w % 5, "Mcycles", d[w, 0] / 1e6, "rounds", d[w, 1], "frames", fr[w, 0], "aos", fr[w, 4], "los", fr[w, 5])
