@@ -189,12 +189,21 @@ void buff_post(uint8_t *b) { memcpy(g_posted, b, 54); g_nposted++; }
 void gui_cmd_resp(const char *) {}
 void m17_net_parse_msg(uint8_t *b, int len);
 void m17_parse_m17_data(uint8_t *b);
+/* Reference defect (D10): with no reflector name set, m17_net_new_rx_data formats " \0" into an uninitialised char ref[20]
+   (m17_net.cpp:57-60) and m17_encode_call then reads ref[0..8] (m17_bit_utils.cpp:193): the destination call sign depends on stale
+   stack bytes.  Zeroing the stack region the callee's frame will occupy makes the reference deterministic here (bytes 2..8 read as
+   NUL = "no character"), which is also what the restatement encodes. */
+static __attribute__((noinline)) void scrub_stack(void) {
+    volatile char z[16384];
+    for (unsigned i = 0; i < sizeof z; i++) z[i] = 0;
+}
 /* m17_net_new_rx_data (m17_net.cpp:53-74) after the reflector acknowledged the connection: 54-byte datagram out */
 extern "C" int ref_net_rx_data(int frame_id, const uint8_t *lsf30, int fn, const uint8_t *pld16, uint8_t *out54) {
     uint8_t ack[8] = {'A', 'C', 'K', 'N'}, lich[64] = {0}, pl[16];
     m17_net_parse_msg(ack, 4);
     memcpy(lich, lsf30, 30); memcpy(pl, pld16, 16);
     g_udp_len = 0;
+    scrub_stack();
     m17_net_new_rx_data((uint16_t)frame_id, lich, (uint16_t)fn, pl);
     memcpy(out54, g_udp_last, 54);
     return g_udp_len;
