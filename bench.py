@@ -237,6 +237,9 @@ def reference_input(S, T, seed):
     return X
 
 
+RESULT_OUT = sys.stdout
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -275,7 +278,7 @@ def run_reference(args):
                                    f"AWGN on IQ Eb/N0 {{22,24,26,30,inf}} dB, f0 +-1 kHz, one unmodified-reference process per host core"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": f"{S} channels x {T} blocks per step"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line))
+    print(json.dumps(line), file=RESULT_OUT, flush=True)
     return 0
 
 
@@ -465,7 +468,7 @@ def run_cuda(args):
         "check": {"delivered_payloads_exact": f"{ok}/{tot}", "frames": int(stats[0]), "stream_frames": int(stats[1]), "delivered": int(stats[3]),
                   "golay_errors": int(stats[2]), "aos": int(stats[4]), "los": int(stats[5])},
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -482,6 +485,12 @@ def main():
     ap.add_argument("--chan-groups", type=int, default=None, help="independent channel-group chains per call (1 = one chain); default: library default (auto)")
     ap.add_argument("--slice-blocks", type=int, default=None, help="blocks per pipeline slice (0 = stages in sequence); default: library default")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON result: everything else that writes to fd 1 (NCCL's version banner, library
+    # chatter of child processes) is sent to stderr for the lifetime of the process
+    global RESULT_OUT
+    sys.stdout.flush()
+    RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
