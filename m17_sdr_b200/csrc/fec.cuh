@@ -268,6 +268,15 @@ template <int T_> __device__ __forceinline__ float sync_corr(const float *v) {
     for (int i = 1; i < 8; i++) s = ((m >> i) & 1u) ? s - v[i] : s + v[i];   // sums[t] += vect[i]*sframe[t][i]  (a + (-b) == a - b)
     return s;
 }
+// find_variance (m17_rx_frame.cpp:47-60) of a window, compared with a double limit exactly as the callers do
+__device__ __forceinline__ bool sync_variance_lt(const float *v, double limit) {
+    float mn = fabsf(v[0]), mx = mn;
+#pragma unroll
+    for (int i = 1; i < 8; i++) { float a = fabsf(v[i]); if (a > mx) mx = a; else if (a < mn) mn = a; }
+    float var = (mx - mn) / mx;
+    if (var != var) var = 1.0f;
+    return (double)var < limit;
+}
 __device__ __forceinline__ SyncResult sync_check8(const float *v) {
     SyncResult r;
     // find_variance: the 'else' means a sample that raises the max is never tested against the min
@@ -313,7 +322,11 @@ __device__ __forceinline__ bool sync_unlocked_ok(const float *v) {
     for (int i = 0; i < 8; i++) { negm |= (v[i] < 0) ? (1u << i) : 0u; posm |= (v[i] > 0) ? (1u << i) : 0u; }
     if ((negm ^ posm) != 0xFFu) return false;
     if (negm != sync_neg_mask(1) && negm != sync_neg_mask(2) && negm != sync_neg_mask(3) && negm != sync_neg_mask(4)) return false;
-    return sync_accept(sync_check8(v), false);
+    // The signs are exactly those of frame sync word t.  If in addition variance < 0.3, every |v[i]| >= 0.7 max|v|, so any other
+    // template's correlation is smaller by at least 2 * 0.7 max|v| >= 17 % of sum|v| -- far beyond the rounding of eight adds --
+    // and the arg-max is t with zero votes: the variance test alone decides (find_variance, m17_rx_frame.cpp:47-60, compared as
+    // double with 0.3, :82-92).  If variance >= 0.3 the window is rejected whatever the arg-max.
+    return sync_variance_lt(v, 0.3);
 }
 __global__ void k_sync_check(const float *vec, int64_t n, uint8_t *type, uint8_t *votes, float *var) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
