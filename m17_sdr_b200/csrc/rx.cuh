@@ -807,11 +807,17 @@ extern "C" int m17b_dsp_rx_host(m17b_rx *rx, const int16_t *h_iq, int64_t nblock
     cudaStream_t st = as_stream(stream);
     const int64_t T = nblocks;
     if (!rx->copy_stream) {
-        // chunk: about 64 MiB of IQ per staging buffer, at least 32 channels
+        // chunks of about 128 MiB of IQ per staging buffer (at least 32 channels), all of (nearly) the same size: every chunk costs
+        // one full latency of the 250-block timing loop whatever its size, so a ragged little last chunk would add ~1 ms to the
+        // tail after the last copy (measured: 34-channel chunks + a 4-channel one 37.3 ms, even chunks 36.5 ms; PCIe alone 35.4)
         int64_t per_chan = rx->max_blocks * 7680;
-        int64_t chunk = (64ll << 20) / per_chan;
+        int64_t mib = 128;
+        if (const char *e = getenv("M17B_HOST_CHUNK_MIB")) mib = atoi(e) > 0 ? atoi(e) : 128;
+        int64_t chunk = (mib << 20) / per_chan;
         if (chunk < 32) chunk = 32;
         if (chunk > rx->nchan) chunk = rx->nchan;
+        const int64_t nchunks = (rx->nchan + chunk - 1) / chunk;
+        chunk = (rx->nchan + nchunks - 1) / nchunks;              // even split: sizes differ by at most one channel
         rx->stage_chunk = chunk;
         CUDA_TRY(cudaStreamCreateWithFlags(&rx->copy_stream, cudaStreamNonBlocking));
         for (int i = 0; i < 2; i++) {
@@ -821,10 +827,10 @@ extern "C" int m17b_dsp_rx_host(m17b_rx *rx, const int16_t *h_iq, int64_t nblock
         }
     }
     rx->last_launches = 0; rx->last_blocks = nblocks; rx->seam_last = 0;
-    const int64_t chunk = rx->stage_chunk;
+    const int64_t nchunks = (rx->nchan + rx->stage_chunk - 1) / rx->stage_chunk;
     int k = 0;
-    for (int64_t c0 = 0; c0 < rx->nchan; c0 += chunk, k ^= 1) {
-        const int64_t nc = (rx->nchan - c0 < chunk) ? rx->nchan - c0 : chunk;
+    for (int64_t ci = 0; ci < nchunks; ci++, k ^= 1) {
+        const int64_t c0 = ci * rx->nchan / nchunks, nc = (ci + 1) * rx->nchan / nchunks - c0;     // <= stage_chunk
         // the staging buffer may only be overwritten once the kernels that read it two chunks ago are done
         CUDA_TRY(cudaStreamWaitEvent(rx->copy_stream, rx->ev_done[k], 0));
         CUDA_TRY(cudaMemcpyAsync(rx->d_iq_stage[k], h_iq + c0 * T * 3840, (size_t)nc * T * 7680, cudaMemcpyHostToDevice, rx->copy_stream));
