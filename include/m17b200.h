@@ -196,7 +196,7 @@ int m17b_rx_set_slice_blocks(m17b_rx *rx, int blocks);
 /* Scheduling knob: run the batch as `groups` (0..8) contiguous channel groups, each a complete chain on its own stream, so
    that one group's latency-bound timing loop shares the SMs with another group's front end / decode.  Channels are
    independent (m17_dsp_rx keeps all state per receiver), so results do not depend on it.  0 / 1 = one chain; -1 = automatic
-   (the default: 3 groups for 512..1184 channels, one chain otherwise). */
+   (the default: 4 groups for 512..1184 channels, one chain otherwise). */
 int m17b_rx_set_chan_groups(m17b_rx *rx, int groups);
 /* Experimental scheduling mode (off by default; results identical, tested): the front end and the timing loop + framer run as
    two CO-RESIDENT kernels.  The front end walks the batch in time-major order on a capped grid-stride grid and counts finished

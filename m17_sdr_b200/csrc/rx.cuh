@@ -41,7 +41,7 @@ struct m17b_rx {
     // channel-group pipeline (see m17b_dsp_rx): the channels are cut into chan_groups contiguous groups, each running its own
     // front end -> sync -> decode -> post chain on its own stream, so that the latency-bound timing loop of one group shares the SMs
     // with the throughput-bound front end / decode of another.  Channels are independent: results do not depend on it.
-    int chan_groups;                  // -1 = auto (3 groups for 512..1184 channels, measured on B200: 2.18 -> 2.04 ms at 1024 x 250), 0 / 1 = off
+    int chan_groups;                  // -1 = auto (4 groups for 512..1184 channels, measured on B200: 2.07 -> 1.96 ms at 1024 x 250), 0 / 1 = off
     cudaStream_t s_grp[M17B_MAX_GROUPS], s_grp_aux[M17B_MAX_GROUPS];
     cudaEvent_t ev_gfork, ev_gjoin[M17B_MAX_GROUPS], ev_gf[M17B_MAX_GROUPS], ev_gj[M17B_MAX_GROUPS];
     // overlapped mode (see rx_pipeline): front end and timing loop as two co-resident kernels coupled by per-time-slice counters
@@ -401,7 +401,7 @@ static int launch_frontend(const int16_t *d_iq, int64_t nc, int64_t T, int64_t t
 
 // matched filter + timing loop + framer over blocks [t0, t1) of channels [c0, c0+nc)
 static int launch_sync(m17b_rx *rx, int64_t c0, int64_t nc, const float *disc, const float *mean, int64_t T, int t0, int t1, int2 *rng, int commit_fe,
-                       cudaStream_t st, const int *fe_done = nullptr, int fe_slice = 0) {
+                       cudaStream_t st, const int *fe_done = nullptr, int fe_slice = 0, bool shared_gpu = false) {
     m17b_ctx *ctx = rx->ctx;
 #define SYNC_ARGS disc, mean, nc, T, t0, t1, rng, rx->d_state + c0, ctx->d_mf, ctx->d_md, rx->d_syms + c0 * rx->sym_pitch, rx->sym_pitch, rx->d_nsym + c0 * T, \
                   rx->d_sym_base + c0, rx->d_frames + c0 * rx->fcap, rx->fcap, rx->d_nframes + c0, rx->d_events + c0 * rx->ecap, rx->ecap, rx->d_nevents + c0, \
@@ -412,7 +412,9 @@ static int launch_sync(m17b_rx *rx, int64_t c0, int64_t nc, const float *disc, c
     // (108 registers, 16 warps per SM) is 15-23 % faster: 2048 ch 1.64 -> 1.33 ms, 4096 ch 3.26 -> 2.52 ms.
     // beside the front end (fe_done): the 110-register variant, so that two of its CTAs and four front-end CTAs share an SM;
     // only the one-warp-per-channel kernels (0, 33) know how to wait for the front end
-    int impl = rx->sync_impl >= 0 ? rx->sync_impl : (nc <= 256 ? 4 : nc <= 8 * 148 ? 0 : 33);
+    // (shared_gpu: the launch is one of several channel groups running side by side -- the four-warps-per-channel form only pays
+    //  when a small launch has the GPU to itself)
+    int impl = rx->sync_impl >= 0 ? rx->sync_impl : (nc <= 256 && !shared_gpu ? 4 : nc <= 8 * 148 ? 0 : 33);
     if (fe_done && impl != 0 && impl != 33) impl = 33;
     if (fe_done && rx->sync_impl < 0) impl = 33;
     if (impl == 33) {
@@ -570,7 +572,7 @@ static int rx_pipeline(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t *d_iq,
             rx->last_launches += 1;
         }
         STAGE_MARK(1);
-        int rc = launch_sync(rx, c0, nc, disc, mean, T, 0, (int)T, nullptr, commit_fe, st);
+        int rc = launch_sync(rx, c0, nc, disc, mean, T, 0, (int)T, nullptr, commit_fe, st, nullptr, 0, grp >= 0);
         if (rc) return rc;
         STAGE_MARK(2);
         rc = launch_decode(ctx, syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0, nc, nullptr, st,
@@ -652,9 +654,9 @@ static int rx_grouped(m17b_rx *rx, const int16_t *d_iq, const float *d_disc, int
 static int rx_groups_for(const m17b_rx *rx) {
     int G = rx->chan_groups;
     // auto: while every channel's timing loop is resident at once (<= 8 x 148 channels) the sync kernel ends with a tail of slow
-    // channels on mostly idle SMs; three staggered groups fill it with the next group's front end / decode.  Below 512 channels
+    // channels on mostly idle SMs; four staggered groups fill it with the next group's front end / decode.  Below 512 channels
     // and above one wave nothing is gained (benchmarks/chan_groups.py).  More than 4 groups exceed the 8 hardware queues.
-    if (G < 0) G = (rx->nchan >= 512 && rx->nchan <= 8 * 148) ? 3 : 1;
+    if (G < 0) G = (rx->nchan >= 512 && rx->nchan <= 8 * 148) ? 4 : 1;
     if (G > M17B_MAX_GROUPS) G = M17B_MAX_GROUPS;
     if (G < 2 || rx->timing || rx->afc || rx->overlap || rx->nchan < 2 * G) return 1;
     return G;
