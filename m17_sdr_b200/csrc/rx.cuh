@@ -31,7 +31,7 @@ struct m17b_rx {
     int64_t stage_chunk;
     cudaStream_t copy_stream, aux_stream;   // aux: LSF/packet/BERT frame decode runs beside the stream-frame decode
     cudaEvent_t ev_fork, ev_join;
-    cudaEvent_t ev_h2d[2], ev_done[2];
+    cudaEvent_t ev_h2d[2], ev_done[2], ev_tail;
     int afc, bert, last_launches, seam_last;
     // time-sliced pipeline (see rx_pipeline): front end of slice k+1 | timing loop + framer of slice k | frame decode of slice k-1
     int slice_blocks;                 // blocks per slice; 0 = one slice (stages strictly in sequence)
@@ -249,6 +249,7 @@ extern "C" int m17b_rx_destroy(m17b_rx *rx) {
         if (rx->ev_h2d[i]) cudaEventDestroy(rx->ev_h2d[i]);
         if (rx->ev_done[i]) cudaEventDestroy(rx->ev_done[i]);
     }
+    if (rx->ev_tail) cudaEventDestroy(rx->ev_tail);
     cudaFree(rx->d_frame_rng); cudaFree(rx->d_lsf_snap); cudaFree(rx->d_lsf_ver);
     if (rx->s_fe) cudaStreamDestroy(rx->s_fe);
     if (rx->s_sync) cudaStreamDestroy(rx->s_sync);
@@ -801,6 +802,38 @@ extern "C" int m17b_rx_set_slice_blocks(m17b_rx *rx, int blocks) {
 extern "C" int64_t m17b_rx_frame_cap(const m17b_rx *rx) { return rx ? rx->fcap : 0; }
 extern "C" int m17b_rx_last_launches(const m17b_rx *rx) { return rx ? rx->last_launches : 0; }
 
+// The chain for channels [c0, c0+nc) in TIME pieces [bounds[k], bounds[k+1]) on one stream, piece k starting once ready[k] has
+// fired (its samples have arrived): front end, timing loop + framer and frame decode per piece (the kernels' block-range forms,
+// results identical to one pass), the per-channel post stage once at the end.
+static int rx_pipeline_pieces(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t *d_iq, int64_t T, int npieces, const int64_t *bounds, const cudaEvent_t *ready,
+                              cudaStream_t st) {
+    m17b_ctx *ctx = rx->ctx;
+    float *disc_w = rx->d_disc + c0 * T * 384, *mean_w = rx->d_mean + c0 * T;
+    m17b_frame_rec *frames = rx->d_frames + c0 * rx->fcap;
+    float *syms = rx->d_syms + c0 * rx->sym_pitch;
+    if (npieces > M17B_MAX_SLICES) return M17B_E_ARG;
+    for (int k = 0; k < npieces; k++) {
+        const int64_t t0 = bounds[k], t1 = bounds[k + 1];
+        int2 *rng = rx->d_frame_rng + (int64_t)k * rx->nchan + c0;
+        CUDA_TRY(cudaStreamWaitEvent(st, ready[k], 0));
+        int rc = launch_frontend(d_iq, nc, T, t0, t1 - t0, rx->d_state + c0, disc_w, mean_w, st);
+        if (rc) return rc;
+        rc = launch_sync(rx, c0, nc, disc_w, mean_w, T, (int)t0, (int)t1, rng, 1, st);
+        if (rc) return rc;
+        const int64_t span = t1 - t0;
+        rc = launch_decode(ctx, syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0, nc, nullptr, st,
+                           rx->aux_stream, rx->ev_fork, rx->ev_join, rng, span + span / 64 + 4, rx->bert);
+        if (rc) return rc;
+        rx->last_launches += 4;
+    }
+    k_post<<<grid_for(nc, POST_WARPS), POST_WARPS * 32, 0, st>>>(frames, rx->fcap, rx->d_nframes + c0, nc, rx->d_state + c0, ctx->d_crc, rx->d_stats + c0 * 8,
+                                                              rx->d_lsf_snap + c0 * rx->nsnap * 32, rx->nsnap, rx->d_lsf_ver + c0 * rx->fcap,
+                                                              ctx->d_prbs, rx->bert);
+    KERNEL_CHECK();
+    rx->last_launches += 1;
+    return M17B_OK;
+}
+
 // End-to-end entry point with host buffers: channels are processed in chunks so the H2D copy of chunk k+1
 // overlaps the kernels of chunk k (two staging buffers, a dedicated copy stream); records stream back per chunk.
 extern "C" int m17b_dsp_rx_host(m17b_rx *rx, const int16_t *h_iq, int64_t nblocks, m17b_frame_rec *h_frames, int32_t *h_nframes, void *stream) {
@@ -827,6 +860,7 @@ extern "C" int m17b_dsp_rx_host(m17b_rx *rx, const int16_t *h_iq, int64_t nblock
             CUDA_TRY(cudaEventCreateWithFlags(&rx->ev_h2d[i], cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&rx->ev_done[i], cudaEventDisableTiming));
         }
+        CUDA_TRY(cudaEventCreateWithFlags(&rx->ev_tail, cudaEventDisableTiming));
     }
     rx->last_launches = 0; rx->last_blocks = nblocks; rx->seam_last = 0;
     const int64_t nchunks = (rx->nchan + rx->stage_chunk - 1) / rx->stage_chunk;
@@ -835,6 +869,28 @@ extern "C" int m17b_dsp_rx_host(m17b_rx *rx, const int16_t *h_iq, int64_t nblock
         const int64_t c0 = ci * rx->nchan / nchunks, nc = (ci + 1) * rx->nchan / nchunks - c0;     // <= stage_chunk
         // the staging buffer may only be overwritten once the kernels that read it two chunks ago are done
         CUDA_TRY(cudaStreamWaitEvent(rx->copy_stream, rx->ev_done[k], 0));
+        const int64_t tail_blocks = 25;
+        if (ci == nchunks - 1 && !rx->afc && T >= 4 * tail_blocks) {
+            // The LAST chunk arrives in two time pieces and its first T - 25 blocks are processed while the last 25 are still on
+            // the bus: what remains after the final byte has landed is the chain over 25 blocks instead of the timing loop's
+            // latency over all T (every channel's blocks are serial), which is the tail of the whole call.
+            const int64_t bounds[3] = {0, T - tail_blocks, T};
+            const size_t pitch = (size_t)T * 7680;
+            const char *src = (const char *)(h_iq + c0 * T * 3840);
+            char *dst = (char *)rx->d_iq_stage[k];
+            CUDA_TRY(cudaMemcpy2DAsync(dst, pitch, src, pitch, (size_t)bounds[1] * 7680, (size_t)nc, cudaMemcpyHostToDevice, rx->copy_stream));
+            CUDA_TRY(cudaEventRecord(rx->ev_h2d[k], rx->copy_stream));
+            CUDA_TRY(cudaMemcpy2DAsync(dst + bounds[1] * 7680, pitch, src + bounds[1] * 7680, pitch, (size_t)tail_blocks * 7680, (size_t)nc, cudaMemcpyHostToDevice,
+                                       rx->copy_stream));
+            CUDA_TRY(cudaEventRecord(rx->ev_tail, rx->copy_stream));
+            const cudaEvent_t ready[2] = {rx->ev_h2d[k], rx->ev_tail};
+            int rc = rx_pipeline_pieces(rx, c0, nc, rx->d_iq_stage[k], T, 2, bounds, ready, st);
+            if (rc) return rc;
+            CUDA_TRY(cudaEventRecord(rx->ev_done[k], st));
+            CUDA_TRY(cudaMemcpyAsync(h_frames + c0 * rx->fcap, rx->d_frames + c0 * rx->fcap, sizeof(m17b_frame_rec) * nc * rx->fcap, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(h_nframes + c0, rx->d_nframes + c0, sizeof(int32_t) * nc, cudaMemcpyDeviceToHost, st));
+            continue;
+        }
         CUDA_TRY(cudaMemcpyAsync(rx->d_iq_stage[k], h_iq + c0 * T * 3840, (size_t)nc * T * 7680, cudaMemcpyHostToDevice, rx->copy_stream));
         CUDA_TRY(cudaEventRecord(rx->ev_h2d[k], rx->copy_stream));
         CUDA_TRY(cudaStreamWaitEvent(st, rx->ev_h2d[k], 0));
