@@ -72,8 +72,11 @@ __device__ __forceinline__ void fe_limit2(uint32_t raw_a, uint32_t raw_b, LimSam
     // g + (1 - m*g)*g = fma(t, -g, g).  The one input class this cannot round correctly is a divisor whose significand is all
     // ones: the Newton iterate then lands exactly on a rounding midpoint while the true quotient 2^-(e+1) (1 + 2^-24 + ..)
     // lies just above it; its correctly rounded value is known in closed form, 2^-(e+1) (1 + 2^-23) = bits 0x7F000000 - bits(m).
-    f32x2 G = fma2(fma2(M, Y, NEG1), mul2(Y, NEG1), Y);
-    G = fma2(fma2(M, G, NEG1), mul2(G, NEG1), G);
+    // (with -m formed once: fma(-m, g, 1) = 1 - m*g is exactly -(m*g - 1), and fma(1 - m*g, g, g) is the same real number
+    //  g + (1 - m*g)*g as fma(m*g - 1, -g, g), so the results are those of the form in the comment above, with one multiply less)
+    const f32x2 NM = mul2(M, NEG1);
+    f32x2 G = fma2(fma2(NM, Y, ONE), Y, Y);
+    G = fma2(fma2(NM, G, ONE), G, G);
     float ma, mb, ga, gb;
     unpack2(M, ma, mb);
     unpack2(G, ga, gb);
