@@ -11,8 +11,12 @@
 // trip, symbols up to there are committed, the branch is stepped and speculation restarts.  Results are
 // identical to the serial loop, including the forward bit-slip (a zero symbol inserted, one sample skipped),
 // the backward slip (a symbol dropped) and votes that straddle a block boundary.
-// The framer's unlocked search evaluates the 8-symbol sync window at 32 positions per step (warp ballot,
-// first hit wins); the locked path only counts symbols and checks each completed frame's head.
+// While locked -- and while unlocked on a tracked signal (the previous block tripped at most once) -- the round is the whole
+// 40-ms block: six consecutive symbols per lane, twelve independent 31-tap chains.
+// The framer's unlocked search evaluates the 8-symbol sync window at 32 positions per step (exact sign-pattern pre-filter, then
+// the variance test; warp ballot, first hit wins); the locked path only counts symbols and checks each completed frame's head,
+// in straight-line code for the common case of one frame boundary per block.
+// The next block's samples are prefetched as 16-byte cp.async pieces and staged with vector loads.
 #pragma once
 #include "frontend.cuh"
 
