@@ -187,6 +187,75 @@ def payload_check(torch, res_frames, nframes, payload):
     return ok, tot
 
 
+# ------------------------------------------------------------------------------------------------ TX record
+TX_BYTES_PER_FRAME = 18 + 7680          # 18 B in (FN + payload) + 1920 int16 IQ samples out
+TX_FIR_FLOP_PER_FRAME = 192 * 10 * 31 * 2 - 1920   # 119 040 - 1920: 31 products + 30 ordered adds per sample (m17_modulate.cpp:42-48)
+FP32_LANE_ROOF = 148 * 128 * 1.965e9    # non-tensor fp32 instruction roof (lane-ops/s): SMs x lanes x clocks.max.sm
+
+
+def tx_record(ctx, m, torch, C, F, steps, with_cpu):
+    """The TX chain on the same batch shape as the RX workload: m17_send_stream_frame for C channels x F frames =
+    m17b_fmt_stream_frames (k_fmt<2>) + m17b_mod_dibits (k_mod_fused), CUDA events on the launching stream; output 1.97 GB >> L2."""
+    dev = ctx.device
+    g = torch.Generator(device=dev); g.manual_seed(77)
+    payload = torch.randint(0, 256, (C, F, 16), generator=g, device=dev, dtype=torch.int32).to(torch.uint8)
+    lsf = torch.randint(0, 256, (C, 30), generator=g, device=dev, dtype=torch.int32).to(torch.uint8)
+    tx = m.Tx(ctx, C, 10)
+    tx.set_lsf(lsf)
+    iq = torch.empty((C, F * 1920, 2), dtype=torch.int16, device=dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * steps)]
+
+    def one(k=None):
+        if k is not None:
+            ev[3 * k].record()
+        dib = tx.m17_fmt_add_stream_frame(payload)
+        if k is not None:
+            ev[3 * k + 1].record()
+        tx.m17_mod_dibits(dib.view(C, F * 192), out=iq)
+        if k is not None:
+            ev[3 * k + 2].record()
+    for _ in range(3):
+        one()
+    torch.cuda.synchronize()
+    for k in range(steps):
+        one(k)
+    torch.cuda.synchronize()
+    fmt_ms = sum(ev[3 * k].elapsed_time(ev[3 * k + 1]) for k in range(steps)) / steps
+    mod_ms = sum(ev[3 * k + 1].elapsed_time(ev[3 * k + 2]) for k in range(steps)) / steps
+    tot_ms = ev[0].elapsed_time(ev[3 * steps - 1]) / steps
+    scan = tx.debug_scan()
+    tx.close()
+    frames = C * F
+    fps = frames / (tot_ms * 1e-3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    rec = {"workload": f"{C} channels x {F} stream frames per step: m17_send_stream_frame = frame formatter + 4FSK modulator (RRC x10, fp32 phase accumulator, cos/sin, int16 IQ)",
+           "frames_per_s": fps, "channel_s_per_s": fps / 25.0, "ms_per_step": tot_ms, "launches_per_step": 3,
+           "kernels": {"k_fmt<2>": {"ms": round(fmt_ms, 4), "frames_per_s": frames / (fmt_ms * 1e-3)},
+                       "k_mod_fused<10>": {"ms": round(mod_ms, 4), "frames_per_s": frames / (mod_ms * 1e-3),
+                                           "alg_bytes_per_frame": 192 + 7680, "gbs": round((192 + 7680) * frames / (mod_ms * 1e-3) / 1e9, 1),
+                                           "frac_of_hbm": round((192 + 7680) * frames / (mod_ms * 1e-3) / 1e9 / hbm, 4),
+                                           "fir_flop_per_frame": TX_FIR_FLOP_PER_FRAME,
+                                           "fir_lane_ops_per_s": TX_FIR_FLOP_PER_FRAME * frames / (mod_ms * 1e-3),
+                                           "frac_of_fp32_lane_roof_fir_only": round(TX_FIR_FLOP_PER_FRAME * frames / (mod_ms * 1e-3) / FP32_LANE_ROOF, 4),
+                                           "bound": "alu / serial phase chain (one fp32 add per sample + a wrap per symbol per channel: ~107 cycles per symbol, "
+                                                    "a floor of symbols x 107 cycles whatever the batch; DESIGN.md 4)",
+                                           "scan_warp_cycles_per_symbol": round(scan["scan_busy_cycles"] / max(1, scan["ctas"] * F * 192), 1)}},
+           "roofline_bytes_per_frame": TX_BYTES_PER_FRAME, "whole_tx_gbs": round(TX_BYTES_PER_FRAME * frames / (tot_ms * 1e-3) / 1e9, 1)}
+    if with_cpu:
+        ref_bin = os.path.join(ROOT, "oracle", "_ref", "m17ref_bench")
+        cores = os.cpu_count() or 1
+        if os.path.exists(ref_bin):
+            out = json.loads(subprocess.run([ref_bin, "--tx", "20000", str(cores)], capture_output=True, text=True, check=True, env=clean_env()).stdout)
+            rec["cpu_baseline"] = {"value": out["frames_per_s"], "unit": "frames/s", "cores": cores, "kind": "reference",
+                                   "sample": f"m17_send_stream_frame x 20000 per process, one unmodified-reference process per core ({out['secs_max_worker']:.2f} s)"}
+    return rec
+
+
 # ------------------------------------------------------------------------------------------------ CPU baseline
 def cpu_baseline(iq_host_sample, T, budget_s=12.0):
     """Time the reference's own RX chain (oracle/_ref/m17ref_bench, unmodified reference objects) on the host cores,
@@ -388,6 +457,9 @@ def run_cuda(args):
     dec.close()
     del dec_in
 
+    # ---- the TX chain on the same batch shape (outside the RX step; rank 0 reports it)
+    txrec = tx_record(ctx, m, torch, C, T, max(3, min(args.steps, 10)), with_cpu=(rank == 0 and not under_profiler()))
+
     # ---- end-to-end through the C ABI with HOST buffers ("e2e")
     iq_host = torch.empty(iq.shape, dtype=torch.int16).pin_memory()
     iq_host.copy_(iq)
@@ -465,6 +537,7 @@ def run_cuda(args):
                      "stages_measured": "stages strictly in sequence (no time slicing), CUDA events on the launching stream",
                      "ms_per_step_in_sequence": round(ms_step_serial, 4), "records_equal_pipelined": same_serial, "stages": stages},
         "cpu_baseline": cb,
+        "aux": {"tx": txrec},
         "check": {"delivered_payloads_exact": f"{ok}/{tot}", "frames": int(stats[0]), "stream_frames": int(stats[1]), "delivered": int(stats[3]),
                   "golay_errors": int(stats[2]), "aos": int(stats[4]), "los": int(stats[5])},
     }

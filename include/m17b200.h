@@ -249,6 +249,15 @@ int m17b_fmt_bert_frames(m17b_tx *tx, int64_t F, uint8_t *d_dibits, void *stream
 /* m17_mod_dibits / m17_mod_carrier (m17_modulate.cpp:42-61,79-92): d_syms [nchan][nsym] (0..3 dibit, 4 = carrier)
    -> d_iq int16 [nchan][nsym*os][2]; d_freq (optional) float [nchan][nsym*os] = the filtered deviation m_sum */
 int m17b_mod_dibits(m17b_tx *tx, const uint8_t *d_syms, int64_t nsym, int16_t *d_iq, float *d_freq, void *stream);
+/* instrumentation of the last m17b_mod_dibits call, SM cycles summed over the CTAs: h_out8 = {phase-scan warp: waiting for the
+   FIR, walking its rows; chunks walked; CTAs; first worker warp: symbol fill + worker barrier, FIR, waiting for the scan,
+   cos/sin + stores}.  Synchronises the device. */
+int m17b_tx_debug_scan(m17b_tx *tx, uint64_t *h_out8);
+/* exhaustive check that the modulator's fp32 form of mod_fsk's per-symbol phase wrap (m17_modulate.cpp:33-37: divide by 2 pi in
+   double, modf, multiply back, every store rounding to float) equals the double formulation bit-for-bit on the float bit
+   patterns [first, first+count) (Inf/NaN skipped); returns the number of mismatches (must be 0) and optionally the first
+   dump_cap offenders as {input bits, fast result, reference result}.  All 2^32 patterns take well under a second on a B200. */
+int m17b_selftest_tx_wrap(m17b_ctx *ctx, uint64_t first, uint64_t count, uint64_t *h_mismatches, uint32_t *h_dump, int dump_cap, void *stream);
 
 /* ------------------------------------------------------------------ Pluto front-end decimator */
 typedef struct m17b_dec m17b_dec;   /* per-batch decimator state: the 31-sample history m_rx_buff carries (radio.cpp:15,167) */

@@ -256,6 +256,13 @@ class Context:
         self.last_selftest_dump = dump.reshape(-1, 5)[: min(16, n.value)]
         return n.value
 
+    def selftest_tx_wrap(self, first=0, count=1 << 32):
+        n = C.c_uint64()
+        dump = np.zeros(3 * 16, np.uint32)
+        _l.check(self.L.m17b_selftest_tx_wrap(self.h, first, count, C.byref(n), dump.ctypes.data_as(C.c_void_p), 16, _stream()))
+        self.last_selftest_dump = dump.reshape(-1, 3)[: min(16, n.value)]
+        return n.value
+
     def synth_channel(self, iq, sigma=None, f0=None, seed=1):
         _chk_dev(iq, torch.int16, "iq")
         nchan, nsamp = iq.shape[0], iq.shape[1]
@@ -483,6 +490,13 @@ class Tx:
         out = torch.empty((self.nchan, F, 192), dtype=torch.uint8, device=self.ctx.device)
         _l.check(self.L.m17b_fmt_bert_frames(self.h, F, _ptr(out), _stream()))
         return out
+
+    def debug_scan(self):
+        """{wait, busy} cycles of the phase-scan warps, chunks and CTAs of the last m17_mod_dibits call (summed over CTAs)."""
+        out = (C.c_uint64 * 8)()
+        _l.check(self.L.m17b_tx_debug_scan(self.h, out))
+        return {"scan_wait_cycles": int(out[0]), "scan_busy_cycles": int(out[1]), "chunks": int(out[2]), "ctas": int(out[3]),
+                "worker_fill_cycles": int(out[4]), "worker_fir_cycles": int(out[5]), "worker_wait_cycles": int(out[6]), "worker_emit_cycles": int(out[7])}
 
     def m17_mod_dibits(self, syms, want_freq=False, out=None):
         """syms uint8 [nchan][nsym] (0..3 dibits, 4 = blank carrier) -> int16 IQ [nchan][nsym*os][2]."""

@@ -3,12 +3,10 @@
 // Replaces m17_fmt_add_* (m17_tx_routines.cpp:24-31,92-117,143-187,201-255) and m17_mod_dibits / mod_filter /
 // sub_filter / mod_fsk (m17_modulate.cpp:22-61,79-92).
 //
-// Formatter mapping: one thread per OUTPUT DIBIT.  Interleave + randomise + puncture are folded into
-// constant-memory index maps, and a convolutional-code output bit depends on only 5 input bits, so every
-// dibit of every frame is computed independently (fully coalesced stores, no per-frame scratch).
-// Modulator mapping: (1) FIR: thread per output sample, 31 sequential fp32 MACs (the reference's order);
-// (2) phase scan: the accumulator m_acc is a sequential fp32 sum per channel, so one lane per channel walks
-// its samples through [32 ch][32 sample] shared-memory tiles; (3) cos/sin + int16 conversion: thread per sample.
+// Formatter mapping: one thread per OUTPUT DIBIT (see k_fmt): interleave + randomise + puncture are index maps and a
+// convolutional-code output bit is the parity of a masked 5-bit window, so every dibit is computed independently.
+// Modulator: one fused kernel (mod.cuh): FIR by worker warps, the per-channel fp32 phase chain by a scan warp, cos/sin and
+// the int16 stores by the workers again, all through shared memory.
 #pragma once
 #include "rx.cuh"
 
@@ -23,84 +21,108 @@ struct m17b_tx {
     int64_t nchan;
     int os;
     float *d_taps;       // 31*os
+    float *d_devtab;     // dibit -> deviation (rad/sample), m17_modulate.cpp:9; [4] = blank carrier
     TxChanState *d_state;
-    float *d_work; int64_t work_syms;
+    unsigned long long *d_dbg;   // [8] instrumentation of the last m17b_mod_dibits call (m17b_tx_debug_scan)
 };
-__constant__ float c_dev[5];   // dibit -> deviation (rad/sample), m17_modulate.cpp:9; [4] = blank carrier
+#include "mod.cuh"
 
 // ---------------------------------------------------------------- formatters
-struct FmtSrc {
-    const uint8_t *bytes;   // info bytes of this frame (LSF 30 / stream payload 16 / packet chunk 25) or PRBS table
-    int fn;                 // stream: frame number
-    int meta;               // packet: byte 25
-    int prbs0;              // bert: PRBS phase of the frame's first bit
-};
-template <int MODE> __device__ __forceinline__ uint32_t info_bit(const FmtSrc &s, int q) {
-    if (MODE == 1) return (s.bytes[q >> 3] >> (7 - (q & 7))) & 1u;                                   // LSF, 240 bits
-    if (MODE == 2) {                                                                                 // FN(16) + payload(128)
-        if (q < 16) return ((uint32_t)s.fn >> (15 - q)) & 1u;
-        int r = q - 16;
-        return (s.bytes[r >> 3] >> (7 - (r & 7))) & 1u;
-    }
-    if (MODE == 3) {                                                                                 // chunk(200) + meta(8)
-        if (q < 200) return (s.bytes[q >> 3] >> (7 - (q & 7))) & 1u;
-        return ((uint32_t)s.meta >> (207 - q)) & 1u;
-    }
-    return s.bytes[(s.prbs0 + q) % 511];                                                             // BERT, 197 PRBS9 bits
-}
-template <int MODE> __device__ __forceinline__ uint32_t coded_bit(const FmtSrc &s, int p) {
-    constexpr int NB = MODE == 1 ? 240 : MODE == 2 ? 144 : MODE == 3 ? 208 : 197;
-    uint32_t pr = conv_pair(conv_reg([&](int q) { return info_bit<MODE>(s, q); }, p >> 1, NB));
-    return (p & 1) ? (pr & 1u) : (pr >> 1);
-}
-// type-3 bit j (before interleaving) of a frame
-template <int MODE> __device__ __forceinline__ uint32_t type3_bit(const FmtSrc &s, const uint32_t *golay, int j) {
-    if (MODE == 1) return coded_bit<1>(s, c_tx.unp1[j]);
-    if (MODE == 2) {
-        if (j < 96) return (golay[j / 24] >> (23 - (j % 24))) & 1u;                                  // pack_24_to_1
-        return coded_bit<2>(s, c_tx.unp2[j - 96]);
-    }
-    if (MODE == 3) return coded_bit<3>(s, c_tx.unp3[j]);
-    return coded_bit<4>(s, c_tx.unp2[j]);
+// One thread per OUTPUT DIBIT of a frame, a CTA of 192 threads walks frames in batches of FMT_NFB.  Every final bit is
+// "parity of (5-bit window of the frame's bit stream AND mask)": a convolutional-code bit is the parity of 3 or 4 of the 5
+// register bits (m17_conv.cpp:22-31), a LICH Golay bit is a window with a one-bit mask.  Puncture, interleave and randomise
+// are index maps, so a thread's two (window position, mask, randomiser bit) descriptors depend only on its dibit index: they
+// are derived once per thread from the constant-memory maps and reused for every frame the CTA formats.  Per frame the CTA
+// stages a 48-byte record in shared memory: bytes 0..31 the info bits delayed by 4 (the encoder's zero start / zero tail fall
+// out of the padding), bytes 32..43 the four 24-bit Golay words of a stream frame.
+#define FMT_NFB 16
+#define FMT_PITCH 48
+#define FMT_GOLAY_BYTE 32
+template <int MODE> __device__ __forceinline__ uint32_t fmt_info_byte(const uint8_t *__restrict__ src, const uint8_t *__restrict__ meta, const uint8_t *__restrict__ prbs,
+                                                                      int64_t f, int fn, int prbs0, int m) {
+    if (m < 0) return 0;
+    if (MODE == 1) return m < 30 ? src[f * 30 + m] : 0;                                     // LSF, 240 bits
+    if (MODE == 2) return m == 0 ? (uint32_t)(fn >> 8) & 255u : m == 1 ? (uint32_t)fn & 255u : m < 18 ? src[f * 16 + m - 2] : 0;   // FN(16) + payload(128)
+    if (MODE == 3) return m < 25 ? src[f * 25 + m] : m == 25 ? meta[f] : 0;                  // chunk(200) + meta(8)
+    uint32_t v = 0;                                                                         // BERT, 197 PRBS9 bits
+#pragma unroll
+    for (int r = 0; r < 8; r++) { const int q = 8 * m + r; v = (v << 1) | (q < 197 ? (uint32_t)prbs[(prbs0 + q) % 511] : 0u); }
+    return v;
 }
 template <int MODE>
-__global__ void k_fmt(const uint8_t *src, const uint8_t *meta, int64_t nframes, int64_t F, const TxChanState *st, uint8_t *dibits,
-                      const uint16_t *genc, const uint8_t *prbs) {
-    int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= nframes * 192) return;
-    const int64_t f = gid / 192;
-    const int sidx = (int)(gid % 192);
+__global__ void __launch_bounds__(192) k_fmt(const uint8_t *__restrict__ src, const uint8_t *__restrict__ meta, int64_t nframes, int64_t F, const TxChanState *__restrict__ st,
+                                             uint8_t *__restrict__ dibits, const uint16_t *__restrict__ genc, const uint8_t *__restrict__ prbs) {
+    __shared__ __align__(16) uint8_t rec[FMT_NFB][FMT_PITCH];
+    const int d = threadIdx.x;
     constexpr uint32_t SYNCW = MODE == 1 ? 0x55F7u : MODE == 2 ? 0xFF5Du : MODE == 3 ? 0x75FFu : 0xDF55u;
-    if (sidx < 8) { dibits[gid] = (uint8_t)((SYNCW >> (14 - 2 * sidx)) & 3u); return; }               // pack_16_to_2
-    FmtSrc s; s.fn = 0; s.meta = 0; s.prbs0 = 0; s.bytes = nullptr;
-    uint32_t golay[4] = {0, 0, 0, 0};
-    if (MODE == 1) s.bytes = src + f * 30;
-    if (MODE == 3) { s.bytes = src + f * 25; s.meta = meta[f]; }
-    if (MODE == 2 || MODE == 4) {
-        const int64_t c = f / F;
-        const int k = (int)(f % F);
-        const TxChanState &S = st[c];
-        if (MODE == 2) {
-            s.bytes = src + f * 16;
-            s.fn = (S.fn + k) & 0xFFFF;
-            const int lc = (S.lich_count + k) % 6;
-            uint32_t b[6];
+    // this thread's two bit descriptors: interleave (out[pi(j)] = in[j], pi an involution), then randomise, dibit = b[i]<<1 | b[i+1]
+    int pos[2] = {0, 0}; uint32_t msk[2] = {0, 0}, rnd[2] = {0, 0};
+    if (d >= 8) {
 #pragma unroll
-            for (int i = 0; i < 5; i++) b[i] = S.lich[lc * 5 + i];
-            b[5] = (uint32_t)(lc & 7) << 5;
-            uint32_t dw[4] = {(b[0] << 4) | (b[1] >> 4), ((b[1] & 15u) << 8) | b[2], (b[3] << 4) | (b[4] >> 4), ((b[4] & 15u) << 8) | b[5]};
-#pragma unroll
-            for (int i = 0; i < 4; i++) golay[i] = (dw[i] << 12) | __ldg(&genc[dw[i]]);               // m17_golay_encode
-        } else {
-            s.bytes = prbs;
-            s.prbs0 = (S.prbs_idx + k * 197) % 511;
+        for (int e = 0; e < 2; e++) {
+            const int i = 2 * (d - 8) + e;
+            const int j = c_tx.qpp[i];
+            rnd[e] = c_tx.rnd[i];
+            if (MODE == 2 && j < 96) { pos[e] = 8 * FMT_GOLAY_BYTE + j; msk[e] = 0x10u; }          // pack_24_to_1 of the Golay words
+            else {
+                const int p = MODE == 1 ? c_tx.unp1[j] : MODE == 2 ? c_tx.unp2[j - 96] : MODE == 3 ? c_tx.unp3[j] : c_tx.unp2[j];
+                pos[e] = p >> 1;                            // trellis step t: window = info bits t-4 .. t
+                msk[e] = (p & 1) ? 0x17u : 0x19u;           // G2 = b[t]^b[t-1]^b[t-2]^b[t-4], G1 = b[t]^b[t-3]^b[t-4]  (window MSB = b[t-4])
+            }
         }
     }
-    const int i0 = 2 * (sidx - 8), i1 = i0 + 1;
-    // interleave (out[pi(j)] = in[j], pi an involution) then randomise (XOR), then dibit = b[i]<<1 | b[i+1]
-    uint32_t b0 = type3_bit<MODE>(s, golay, c_tx.qpp[i0]) ^ c_tx.rnd[i0];
-    uint32_t b1 = type3_bit<MODE>(s, golay, c_tx.qpp[i1]) ^ c_tx.rnd[i1];
-    dibits[gid] = (uint8_t)((b0 << 1) | b1);
+    const int by0 = pos[0] >> 3, sh0 = 11 - (pos[0] & 7), by1 = pos[1] >> 3, sh1 = 11 - (pos[1] & 7);
+    for (int64_t base = (int64_t)blockIdx.x * FMT_NFB; base < nframes; base += (int64_t)gridDim.x * FMT_NFB) {
+        __syncthreads();
+        for (int idx = d; idx < FMT_NFB * 44; idx += 192) {
+            const int fl = idx / 44, n = idx - fl * 44;
+            const int64_t f = base + fl;
+            if (f >= nframes) continue;
+            uint32_t v = 0;
+            int fn = 0, prbs0 = 0, lc = 0;
+            const TxChanState *S = nullptr;
+            if (MODE == 2 || MODE == 4) {
+                const int k = (int)(f % F);
+                S = st + f / F;
+                fn = (S->fn + k) & 0xFFFF;
+                lc = (S->lich_count + k) % 6;
+                prbs0 = (S->prbs_idx + k * 197) % 511;
+            }
+            if (n < 32) {
+                v = ((fmt_info_byte<MODE>(src, meta, prbs, f, fn, prbs0, n - 1) << 4) | (fmt_info_byte<MODE>(src, meta, prbs, f, fn, prbs0, n) >> 4)) & 255u;
+            } else if (MODE == 2) {
+                // LICH chunk lc of m_lich, byte 5 = lc << 5 -> four 12-bit words -> m17_golay_encode (m17_tx_routines.cpp:151-164)
+                const int w = (n - FMT_GOLAY_BYTE) / 3, kb = (n - FMT_GOLAY_BYTE) - 3 * w;
+                uint32_t b[6];
+#pragma unroll
+                for (int i = 0; i < 5; i++) b[i] = S->lich[lc * 5 + i];
+                b[5] = (uint32_t)(lc & 7) << 5;
+                const uint32_t dw = w == 0 ? (b[0] << 4) | (b[1] >> 4) : w == 1 ? ((b[1] & 15u) << 8) | b[2] : w == 2 ? (b[3] << 4) | (b[4] >> 4) : ((b[4] & 15u) << 8) | b[5];
+                const uint32_t g = (dw << 12) | __ldg(&genc[dw]);
+                v = (g >> (16 - 8 * kb)) & 255u;
+            }
+            rec[fl][n] = (uint8_t)v;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int fl = 0; fl < FMT_NFB; fl++) {
+            const int64_t f = base + fl;
+            if (f >= nframes) break;
+            uint32_t out;
+            if (d < 8) out = (SYNCW >> (14 - 2 * d)) & 3u;                                          // pack_16_to_2
+            else {
+                const uint8_t *r = rec[fl];
+                const uint32_t w0 = ((uint32_t)r[by0] << 8) | r[by0 + 1], w1 = ((uint32_t)r[by1] << 8) | r[by1 + 1];
+                const uint32_t b0 = (__popc((w0 >> sh0) & msk[0]) & 1u) ^ rnd[0], b1 = (__popc((w1 >> sh1) & msk[1]) & 1u) ^ rnd[1];
+                out = (b0 << 1) | b1;
+            }
+            dibits[f * 192 + d] = (uint8_t)out;
+        }
+    }
+}
+static inline unsigned fmt_grid(int64_t nframes) {
+    const int64_t batches = (nframes + FMT_NFB - 1) / FMT_NFB;
+    return (unsigned)(batches < 148 * 8 ? batches : 148 * 8);
 }
 __global__ void k_tx_advance(TxChanState *st, int64_t nchan, int dfn, int dlich, int dprbs) {
     int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -123,14 +145,14 @@ extern "C" int m17b_fmt_eot(uint8_t *d) { if (!d) return M17B_E_ARG; for (int i 
 extern "C" int m17b_fmt_link_setup_frame(m17b_ctx *ctx, const uint8_t *d_lsf, int64_t n, uint8_t *d_dibits, void *stream) {
     if (!ctx || !d_lsf || !d_dibits || n < 0) return M17B_E_ARG;
     if (n == 0) return M17B_OK;
-    k_fmt<1><<<grid_for(n * 192, 192), 192, 0, as_stream(stream)>>>(d_lsf, nullptr, n, 1, nullptr, d_dibits, ctx->d_genc, ctx->d_prbs);
+    k_fmt<1><<<fmt_grid(n), 192, 0, as_stream(stream)>>>(d_lsf, nullptr, n, 1, nullptr, d_dibits, ctx->d_genc, ctx->d_prbs);
     KERNEL_CHECK();
     return M17B_OK;
 }
 extern "C" int m17b_fmt_packet_frames(m17b_ctx *ctx, const uint8_t *d_chunk, const uint8_t *d_meta, int64_t n, uint8_t *d_dibits, void *stream) {
     if (!ctx || !d_chunk || !d_meta || !d_dibits || n < 0) return M17B_E_ARG;
     if (n == 0) return M17B_OK;
-    k_fmt<3><<<grid_for(n * 192, 192), 192, 0, as_stream(stream)>>>(d_chunk, d_meta, n, 1, nullptr, d_dibits, ctx->d_genc, ctx->d_prbs);
+    k_fmt<3><<<fmt_grid(n), 192, 0, as_stream(stream)>>>(d_chunk, d_meta, n, 1, nullptr, d_dibits, ctx->d_genc, ctx->d_prbs);
     KERNEL_CHECK();
     return M17B_OK;
 }
@@ -177,7 +199,7 @@ extern "C" int m17b_send_packet_frames(m17b_ctx *ctx, const uint8_t *d_packets, 
     CUDA_TRY(cudaMallocAsync((void **)&chunk, (size_t)n * max_frames * 25, st));
     CUDA_TRY(cudaMallocAsync((void **)&meta, (size_t)n * max_frames, st));
     k_packet_split<<<grid_for(n, 128), 128, 0, st>>>(d_packets, stride, d_len, n, max_frames, ctx->d_crc, chunk, meta, d_nframes);
-    k_fmt<3><<<grid_for(n * max_frames * 192, 192), 192, 0, st>>>(chunk, meta, n * max_frames, 1, nullptr, d_dibits, ctx->d_genc, ctx->d_prbs);
+    k_fmt<3><<<fmt_grid(n * max_frames), 192, 0, st>>>(chunk, meta, n * max_frames, 1, nullptr, d_dibits, ctx->d_genc, ctx->d_prbs);
     k_packet_blank<<<grid_for(n * max_frames * 192, 256), 256, 0, st>>>(meta, n * max_frames, d_dibits);
     KERNEL_CHECK();
     CUDA_TRY(cudaFreeAsync(chunk, st));
@@ -188,7 +210,7 @@ extern "C" int m17b_fmt_stream_frames(m17b_tx *tx, const uint8_t *d_payload, int
     if (!tx || !d_payload || !d_dibits || F < 0) return M17B_E_ARG;
     if (F == 0) return M17B_OK;
     cudaStream_t st = as_stream(stream);
-    k_fmt<2><<<grid_for(tx->nchan * F * 192, 192), 192, 0, st>>>(d_payload, nullptr, tx->nchan * F, F, tx->d_state, d_dibits, tx->ctx->d_genc, tx->ctx->d_prbs);
+    k_fmt<2><<<fmt_grid(tx->nchan * F), 192, 0, st>>>(d_payload, nullptr, tx->nchan * F, F, tx->d_state, d_dibits, tx->ctx->d_genc, tx->ctx->d_prbs);
     KERNEL_CHECK();
     k_tx_advance<<<grid_for(tx->nchan, 128), 128, 0, st>>>(tx->d_state, tx->nchan, (int)(F & 0xFFFF), (int)(F % 6), 0);
     KERNEL_CHECK();
@@ -198,7 +220,7 @@ extern "C" int m17b_fmt_bert_frames(m17b_tx *tx, int64_t F, uint8_t *d_dibits, v
     if (!tx || !d_dibits || F < 0) return M17B_E_ARG;
     if (F == 0) return M17B_OK;
     cudaStream_t st = as_stream(stream);
-    k_fmt<4><<<grid_for(tx->nchan * F * 192, 192), 192, 0, st>>>(nullptr, nullptr, tx->nchan * F, F, tx->d_state, d_dibits, tx->ctx->d_genc, tx->ctx->d_prbs);
+    k_fmt<4><<<fmt_grid(tx->nchan * F), 192, 0, st>>>(nullptr, nullptr, tx->nchan * F, F, tx->d_state, d_dibits, tx->ctx->d_genc, tx->ctx->d_prbs);
     KERNEL_CHECK();
     k_tx_advance<<<grid_for(tx->nchan, 128), 128, 0, st>>>(tx->d_state, tx->nchan, 0, 0, (int)((F * 197) % 511));
     KERNEL_CHECK();
@@ -211,96 +233,9 @@ extern "C" int m17b_tx_set_lsf(m17b_tx *tx, const uint8_t *d_lsf, void *stream) 
     return M17B_OK;
 }
 
-// ---------------------------------------------------------------- modulator
-// (1) polyphase RRC: sample n of channel c = sum_j s[j] * taps[(os-1-ph) + j*os], s = deviations of symbols k-30..k
-__global__ void k_mod_fir(const uint8_t *syms, int64_t nsym_total, int64_t k0, int64_t nk, int os, const float *__restrict__ taps,
-                          const TxChanState *st, int64_t nchan, float *work, float *freq) {
-    const int64_t per = nk * os;
-    int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= nchan * per) return;
-    const int64_t c = gid / per;
-    const int64_t n = gid % per;
-    const int64_t k = n / os;                  // symbol within the chunk
-    const int ph = (int)(n % os);
-    const float *cf = taps + (os - 1 - ph);
-    const uint8_t *sy = syms + c * nsym_total + k0;
-    const float *hist = st[c].hist;
-    float sum = 0;
-#pragma unroll
-    for (int j = 0; j < 31; j++) {
-        const int64_t kk = k - 30 + j;         // chunk-relative symbol index
-        const float s = (kk >= 0) ? c_dev[sy[kk]] : hist[31 + kk];
-        const float prod = s * __ldg(cf + j * os);
-        sum = (j == 0) ? prod : sum + prod;    // sum = s[0]*c[0]; sum += s[i]*c[i*os]  (m17_modulate.cpp:42-48)
-    }
-    work[gid] = sum;
-    if (freq) freq[c * nsym_total * os + k0 * os + n] = sum;
-}
-// (2) phase accumulation, lane per channel (m17_modulate.cpp:22-37): m_acc += f per sample (fp32), and once per symbol
-// the accumulator is wrapped through double: acc = acc/(2 pi); acc = modf(acc); acc = acc*2 pi, each store rounding to fp32.
-__global__ void __launch_bounds__(128) k_mod_scan(float *work, int64_t per, int os, TxChanState *st, int64_t nchan) {
-    __shared__ float tile[4][32][33];
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t c0 = ((int64_t)blockIdx.x * 4 + wid) * 32;
-    if (c0 >= nchan) return;
-    const int64_t c = c0 + lane;
-    const bool live = c < nchan;
-    float acc = live ? st[c].acc : 0.0f;
-    int cnt = 0;
-    for (int64_t n0 = 0; n0 < per; n0 += 32) {
-        for (int r = 0; r < 32; r++) {
-            float v = 0;
-            if (c0 + r < nchan && n0 + lane < per) v = work[(c0 + r) * per + n0 + lane];
-            tile[wid][r][lane] = v;
-        }
-        __syncwarp();
-        const int lim = (per - n0 < 32) ? (int)(per - n0) : 32;
-        for (int s = 0; s < lim; s++) {
-            acc += tile[wid][lane][s];
-            tile[wid][lane][s] = acc;
-            if (++cnt == os) {
-                cnt = 0;
-                acc = (float)((double)acc / (2.0 * M_PI));
-                double ip = trunc((double)acc);
-                acc = (float)((double)acc - ip);                              // modf fractional part (exact)
-                acc = (float)((double)acc * 2.0 * M_PI);
-            }
-        }
-        __syncwarp();
-        for (int r = 0; r < 32; r++)
-            if (c0 + r < nchan && n0 + lane < per) work[(c0 + r) * per + n0 + lane] = tile[wid][r][lane];
-        __syncwarp();
-    }
-    if (live) st[c].acc = acc;
-}
-// (3) IQ: re = (int16)(cos(acc) * 0x3FFF), im = (int16)(sin(acc) * 0x3FFF), truncating (m17_modulate.cpp:25-26)
-__global__ void k_mod_iq(const float *work, int64_t per, int64_t out_pitch, int64_t out_off, int64_t nchan, int16_t *iq) {
-    int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= nchan * per) return;
-    const int64_t c = gid / per, n = gid % per;
-    float sn, cs;
-    sincosf(work[gid], &sn, &cs);
-    short2 o;
-    o.x = (short)__float2int_rz(cs * 16383.0f);
-    o.y = (short)__float2int_rz(sn * 16383.0f);
-    ((short2 *)iq)[c * out_pitch + out_off + n] = o;
-}
-__global__ void k_mod_hist(const uint8_t *syms, int64_t nsym_total, int64_t k0, int64_t nk, TxChanState *st, int64_t nchan) {
-    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= nchan) return;
-    float nh[31];
-#pragma unroll
-    for (int j = 0; j < 31; j++) {
-        int64_t kk = nk - 31 + j;
-        nh[j] = (kk >= 0) ? c_dev[syms[c * nsym_total + k0 + kk]] : st[c].hist[31 + kk];
-    }
-#pragma unroll
-    for (int j = 0; j < 31; j++) st[c].hist[j] = nh[j];
-}
-
 extern "C" int m17b_tx_destroy(m17b_tx *tx) {
     if (!tx) return M17B_E_ARG;
-    cudaFree(tx->d_taps); cudaFree(tx->d_state); cudaFree(tx->d_work);
+    cudaFree(tx->d_taps); cudaFree(tx->d_devtab); cudaFree(tx->d_state); cudaFree(tx->d_dbg);
     free(tx);
     return M17B_OK;
 }
@@ -325,36 +260,38 @@ extern "C" int m17b_tx_create(m17b_ctx *ctx, int64_t nchan, int os, m17b_tx **ou
     free(h);
     if (rc) { free(tx); return rc; }
     const float dev[5] = {(float)(M_PI / 30.0), (float)(M_PI / 10.0), (float)(-M_PI / 30), (float)(-M_PI / 10.0), 0.0f};
-    CUDA_TRY(cudaMemcpyToSymbol(c_dev, dev, sizeof(dev)));
+    rc = upload(&tx->d_devtab, dev, 5);
+    if (rc) { cudaFree(tx->d_taps); free(tx); return rc; }
     CUDA_TRY(cudaMalloc((void **)&tx->d_state, sizeof(TxChanState) * nchan));
     CUDA_TRY(cudaMemset(tx->d_state, 0, sizeof(TxChanState) * nchan));
+    CUDA_TRY(cudaMalloc((void **)&tx->d_dbg, 64));
+    CUDA_TRY(cudaMemset(tx->d_dbg, 0, 64));
     *out = tx;
     return M17B_OK;
 }
 extern "C" int m17b_mod_dibits(m17b_tx *tx, const uint8_t *d_syms, int64_t nsym, int16_t *d_iq, float *d_freq, void *stream) {
     if (!tx || !d_syms || !d_iq || nsym < 0) return M17B_E_ARG;
     if (nsym == 0) return M17B_OK;
-    cudaStream_t st = as_stream(stream);
-    const int os = tx->os;
-    // chunk the time axis so the fp32 work buffer stays small (about 64 MiB)
-    int64_t chunk = (16ll << 20) / (tx->nchan * os);
-    if (chunk < 192) chunk = 192;
-    if (chunk > nsym) chunk = nsym;
-    if (tx->work_syms < chunk) {
-        if (tx->d_work) CUDA_TRY(cudaFree(tx->d_work));
-        tx->d_work = nullptr;
-        CUDA_TRY(cudaMalloc((void **)&tx->d_work, sizeof(float) * tx->nchan * chunk * os));
-        tx->work_syms = chunk;
+    CUDA_TRY(cudaSetDevice(tx->ctx->device));
+    const ModGeom g = mod_geometry(tx->nchan, tx->os, nsym);
+    const size_t smem = mod_smem_floats(g) * sizeof(float);
+    const unsigned grid = (unsigned)((tx->nchan + g.G - 1) / g.G);
+    CUDA_TRY(cudaMemsetAsync(tx->d_dbg, 0, 64, as_stream(stream)));
+    if (tx->os == 10) {
+        CUDA_TRY(cudaFuncSetAttribute(k_mod_fused<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_mod_fused<10><<<grid, TXM_THREADS, smem, as_stream(stream)>>>(d_syms, g, tx->d_taps, tx->d_devtab, tx->d_state, tx->nchan, d_iq, d_freq, tx->d_dbg);
+    } else {
+        CUDA_TRY(cudaFuncSetAttribute(k_mod_fused<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_mod_fused<0><<<grid, TXM_THREADS, smem, as_stream(stream)>>>(d_syms, g, tx->d_taps, tx->d_devtab, tx->d_state, tx->nchan, d_iq, d_freq, tx->d_dbg);
     }
-    for (int64_t k0 = 0; k0 < nsym; k0 += chunk) {
-        const int64_t nk = (nsym - k0 < chunk) ? nsym - k0 : chunk;
-        const int64_t per = nk * os;
-        k_mod_fir<<<grid_for(tx->nchan * per, 256), 256, 0, st>>>(d_syms, nsym, k0, nk, os, tx->d_taps, tx->d_state, tx->nchan, tx->d_work, d_freq);
-        k_mod_scan<<<grid_for(tx->nchan, 128), 128, 0, st>>>(tx->d_work, per, os, tx->d_state, tx->nchan);
-        k_mod_iq<<<grid_for(tx->nchan * per, 256), 256, 0, st>>>(tx->d_work, per, nsym * os, k0 * os, tx->nchan, d_iq);
-        k_mod_hist<<<grid_for(tx->nchan, 128), 128, 0, st>>>(d_syms, nsym, k0, nk, tx->d_state, tx->nchan);
-        KERNEL_CHECK();
-    }
+    KERNEL_CHECK();
+    return M17B_OK;
+}
+
+extern "C" int m17b_tx_debug_scan(m17b_tx *tx, uint64_t *h_out8) {
+    if (!tx || !h_out8) return M17B_E_ARG;
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(h_out8, tx->d_dbg, 64, cudaMemcpyDeviceToHost));
     return M17B_OK;
 }
 

@@ -5,6 +5,10 @@
  * state in file statics so a process is a channel).  TEST/BENCH INFRASTRUCTURE ONLY.
  *
  *   m17ref_bench <iq.bin> <C> <T> <nproc> [reps]
+ *   m17ref_bench --tx <frames per worker> <nproc>
+ * --tx: the reference TX chain, m17_send_stream_frame = m17_fmt_add_stream_frame + m17_mod_dibits (m17_tx_routines.cpp:306-310,
+ *       m17_modulate.cpp:79-88) at oversample 10, nproc workers each sending <frames> stream frames after one link setup frame;
+ *       radio_transmit_samples discards the IQ.  The clock runs around the send loop only.
  * iq.bin = raw int16 [C][T*1920][2].  nproc workers; each decodes its channels one after another, every channel in a
  * freshly forked child (pristine statics).  The clock runs around the m17_dsp_rx loop only.  Prints one JSON line:
  * frames/s = all frames / slowest worker's summed loop time; delivered = stream payloads passed up in one pass.
@@ -37,7 +41,39 @@ int  udp_send(uint8_t *, int len) { return len; }
 
 static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 
+void m17_send_link_setup_frame(uint48_t dest, uint48_t src, M17Type type, uint8_t *meta);
+void m17_send_stream_frame(uint8_t *payload);
+
+static int tx_main(long frames, int nproc) {
+    struct Res { double secs; long frames; };
+    Res *res = (Res *)mmap(0, sizeof(Res) * nproc, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+    m17_prbs9_init(); m17_crc_init(); m17_init_conv(); m17_init_de_correlate(); m17_dsp_init(); m17_fmt_init();
+    m17_golay_init(); m17_rx_sync_init(); m17_mod_init();
+    for (int w = 0; w < nproc; w++) {
+        if (fork() == 0) {
+            uint8_t meta[14] = {0}, payload[16];
+            M17Type type; memset(&type, 0, sizeof(type));
+            m17_send_link_setup_frame(0xFFFFFFFFFFFFull, 0x123456789Aull + w, type, meta);
+            unsigned x = 12345u + w;
+            for (int i = 0; i < 50; i++) { for (int b = 0; b < 16; b++) { x = x * 1664525u + 1013904223u; payload[b] = x >> 24; } m17_send_stream_frame(payload); }
+            double t0 = now_s();
+            for (long f = 0; f < frames; f++) {
+                for (int b = 0; b < 16; b++) { x = x * 1664525u + 1013904223u; payload[b] = x >> 24; }
+                m17_send_stream_frame(payload);
+            }
+            res[w].secs = now_s() - t0; res[w].frames = frames;
+            _exit(0);
+        }
+    }
+    for (int w = 0; w < nproc; w++) { int st; wait(&st); }
+    double maxs = 0; long tot = 0;
+    for (int w = 0; w < nproc; w++) { if (res[w].secs > maxs) maxs = res[w].secs; tot += res[w].frames; }
+    printf("{\"mode\": \"tx\", \"frames\": %ld, \"secs_max_worker\": %.6f, \"frames_per_s\": %.1f, \"nproc\": %d}\n", tot, maxs, tot / maxs, nproc);
+    return 0;
+}
+
 int main(int argc, char **argv) {
+    if (argc >= 4 && !strcmp(argv[1], "--tx")) return tx_main(atol(argv[2]), atoi(argv[3]));
     if (argc < 5) { fprintf(stderr, "usage: %s iq.bin C T nproc [reps]\n", argv[0]); return 2; }
     long C = atol(argv[2]), T = atol(argv[3]); int nproc = atoi(argv[4]); int reps = argc > 5 ? atoi(argv[5]) : 1;
     int fd = open(argv[1], O_RDONLY);
