@@ -149,10 +149,13 @@ int m17b_rx_create(m17b_ctx *ctx, int64_t nchan, int64_t max_blocks, m17b_rx **o
 int m17b_rx_destroy(m17b_rx *rx);
 /* m17_rx_init + m17_rx_sync_init initial state for every channel (m17_rx_frame.cpp:183-186, m17_rx_sync.cpp:124-127) */
 int m17b_rx_reset(m17b_rx *rx, void *stream);
+/* m17_rx_init / m17_rx_lost alone (m17_rx_frame.cpp:179-186): reset_sync() + m_flock = false for every channel; the timing loop,
+   the discriminator history, the LICH cache and the counters are left as they are */
+int m17b_rx_framer_reset(m17b_rx *rx, void *stream);
 /* radio_set_afc_on / radio_set_afc_off (radio.cpp:146-152): with AFC on, m17b_dsp_rx runs dsp_nco_mixer + radio_afc
    (m17_dsp.cpp:390-408, radio.cpp:196-208) and processes the blocks of a call one at a time (the loop is closed through the
    framer); off (the reference default) uses the block-parallel front end.  No effect on m17b_rx_baseband. */
-int m17b_rx_set_afc(m17b_rx *rx, int on);
+int m17b_rx_set_afc(m17b_rx *rx, int on, void *stream);
 /* BERT receive.  The reference sends BERT frames (m17_fmt_add_bert_frame) but its decode_bert_frame is empty
    (m17_rx_parse.cpp:178-180) and m17_prbs9_rx_check (m17_prbs9.cpp:40-64) is never called.  With on != 0, BERT frames are
    de-punctured (P2, 402 coded bits), Viterbi-decoded (201 steps) into data[0..25) and their 197 PRBS9 bits go through the
@@ -183,6 +186,10 @@ int m17b_rx_get_view(m17b_rx *rx, m17b_rx_view *out);
 /* end-to-end form with HOST buffers (pinned or pageable): H2D of the IQ, the chain, D2H of records.
    h_frames [nchan][frame_cap] (frame_cap from m17b_rx_frame_cap), h_nframes [nchan]; synchronises the stream. */
 int64_t m17b_rx_frame_cap(const m17b_rx *rx);
+/* sticky capacity flags since the last m17b_rx_reset (synchronises the device): bit 0 = m17b_rx_symbols was handed more than
+   max_blocks*200 symbols for some channel and ignored the excess.  Record and event buffers are sized for the worst case of
+   every entry point (frame_cap = ceil(max_blocks*200/192) + 2) and cannot overflow. */
+int m17b_rx_get_overflow(m17b_rx *rx, int *h_flags);
 int m17b_dsp_rx_host(m17b_rx *rx, const int16_t *h_iq, int64_t nblocks, m17b_frame_rec *h_frames, int32_t *h_nframes, void *stream);
 /* bench instrumentation: mark stage boundaries with CUDA events on the launching stream; stage_ms returns the device
    time of {front end, matched filter+timing+framer, frame decode, LICH/packet post} of device call number call_index
@@ -198,15 +205,6 @@ int m17b_rx_set_slice_blocks(m17b_rx *rx, int blocks);
    independent (m17_dsp_rx keeps all state per receiver), so results do not depend on it.  0 / 1 = one chain; -1 = automatic
    (the default: 4 groups for 512..1184 channels, one chain otherwise). */
 int m17b_rx_set_chan_groups(m17b_rx *rx, int groups);
-/* Experimental scheduling mode (off by default; results identical, tested): the front end and the timing loop + framer run as
-   two CO-RESIDENT kernels.  The front end walks the batch in time-major order on a capped grid-stride grid and counts finished
-   (channel, block) items per time slice of `slice_blocks` blocks (0 = keep, default 10); each timing-loop warp waits -- bounded,
-   an expired wait makes the next call fail loudly -- for a slice's counter before fetching the slice's first block.
-   Measured on B200 at 1024 x 250: the pair takes 1.64 ms side by side against 0.63 + 1.02 ms one after the other. */
-int m17b_rx_set_overlap(m17b_rx *rx, int on, int slice_blocks);
-/* instrumentation of the overlapped front end | timing loop mode (M17B_OVERLAP=1): h_out4 = %globaltimer ns of {front end first
-   start, front end last end, timing loop first start, timing loop last end} of the last such call.  Synchronises the device. */
-int m17b_rx_debug_overlap(m17b_rx *rx, uint64_t *h_out4);
 /* instrumentation: d_out uint64 [nchan][8] = {SM cycles, speculation rounds, cycles in staging / timing loop / emission / framer /
    carry (only in builds with -DM17B_PHASE_CLOCKS), spare} the one-warp-per-channel timing-loop kernel spent on each channel in its
    last launch (the kernel's time is that of its slowest channel) */

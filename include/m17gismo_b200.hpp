@@ -10,8 +10,9 @@
 // Differences a caller can observe (all consequences of returning records instead of up-calls):
 //  * RX results arrive through m17b_shim_callbacks (frame records + AOS/LOS events) right after m17_dsp_rx /
 //    m17_rx_symbols returns; the reference's gui_*/m17_db_*/m17_net_new_rx_data up-calls are the caller's to make.
-//  * m17_rx_sync_samples runs the framer too (the kernel is fused); m17_rx_symbols then only dispatches the records.
-//    (Symbols from elsewhere go through the batched ABI's m17b_rx_symbols.)
+//  * m17_rx_sync_samples runs the framer too (the kernel is fused); m17_rx_symbols on the symbols it returned then only
+//    dispatches the records.  Any other symbols (m17_rx_symbols / m17_rx_sym on a caller's own stream) go through the
+//    stand-alone framer (m17b_rx_symbols).
 //  * blocks must be whole: m17_dsp_rx takes 1920 IQ samples, m17_rx_sync_samples 384 samples (as m17_dsp_rx feeds it).
 //  * TX IQ is handed to m17b_shim_callbacks::transmit in 1920-sample blocks (radio_transmit_samples, radio.cpp:178).
 #ifndef M17GISMO_B200_HPP
@@ -46,6 +47,7 @@ void m17_dsp_set_filter_gain(float *filter, float gain, int stride, int ntaps);
 void m17_dsp_rx(scmplx *in, int len);
 int  m17_rx_sync_samples(float *in, float *out, int len);
 void m17_rx_symbols(float *sym, int len);
+void m17_rx_sym(float sym);                                            // m17_rx_frame.cpp:126
 void m17_rx_init(void); void m17_rx_lost(void); bool m17_rx_lock(void);
 void radio_set_afc_on(void); void radio_set_afc_off(void); bool radio_get_afc_status(void);   // radio.cpp:146-155
 void m17_dsp_demap_frame(float *in, float *out);
@@ -75,6 +77,9 @@ void m17_rx_parse(float *s, uint8_t type);     // one frame, record handed to th
 void eq_open(void); void eq_reset(void); void eq_restart(void); float eq_train_known(float *in, float train); float eq_train_unknown(float *in);
 // TX
 uint16_t m17_pack_type(M17Type type);
+M17Type m17_upack_type(uint16_t word);                                // m17_bit_utils.cpp:245-254
+uint48_t m17_encode_call(const char *call);                           // m17_bit_utils.cpp:191-208 (call padded to 9 characters)
+char *m17_decode_call(uint48_t word, char *call);                     // m17_bit_utils.cpp:209-226
 void m17_mod_dibits(uint8_t *dibits, int len); void m17_mod_carrier(void);
 void m17_send_preamble(void);
 void m17_send_link_setup_frame(uint48_t dest, uint48_t src, M17Type type, uint8_t *meta);
@@ -97,6 +102,7 @@ struct State {
     int os = 10, err = 0, prbs_idx = 0;
     uint32_t prbs_rx[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     bool lock = false;
+    int from_sync = 0;                         // symbols of the last m17_rx_sync_samples call that the fused kernel has already framed
     std::vector<scmplx> txbuf;                 // m_tx_samples: flushed every 1920 samples (m17_modulate.cpp:30-33)
     std::vector<m17b_frame_rec> pend_fr; std::vector<m17b_event_rec> pend_ev;
     int chk(int rc) { if (rc) err = rc; return rc; }
@@ -174,11 +180,12 @@ void m17_fmt_init(void) { m17b_shim::S().ensure(); }
 void m17_golay_init(void) { m17b_shim::S().ensure(); }
 void m17_rx_sync_init(void) { auto &s = m17b_shim::S(); if (s.ensure()) { s.chk(m17b_rx_reset(s.rx, nullptr)); s.lock = false; } }
 void m17_mod_init(void) { m17b_shim::S().ensure_tx(); }
-void m17_rx_init(void) { m17_rx_sync_init(); }
-void m17_rx_lost(void) { m17_rx_sync_init(); }
+// m17_rx_init / m17_rx_lost (m17_rx_frame.cpp:179-186): reset_sync() + m_flock = false, nothing else
+void m17_rx_init(void) { auto &s = m17b_shim::S(); if (s.ensure()) { s.chk(m17b_rx_framer_reset(s.rx, nullptr)); s.lock = false; } }
+void m17_rx_lost(void) { m17_rx_init(); }
 bool m17_rx_lock(void) { return m17b_shim::S().lock; }
-void radio_set_afc_on(void) { auto &s = m17b_shim::S(); if (s.ensure() && !s.chk(m17b_rx_set_afc(s.rx, 1))) s.afc = true; }
-void radio_set_afc_off(void) { auto &s = m17b_shim::S(); if (s.ensure() && !s.chk(m17b_rx_set_afc(s.rx, 0))) s.afc = false; }
+void radio_set_afc_on(void) { auto &s = m17b_shim::S(); if (s.ensure() && !s.chk(m17b_rx_set_afc(s.rx, 1, nullptr))) s.afc = true; }
+void radio_set_afc_off(void) { auto &s = m17b_shim::S(); if (s.ensure() && !s.chk(m17b_rx_set_afc(s.rx, 0, nullptr))) s.afc = false; }
 bool radio_get_afc_status(void) { return m17b_shim::S().afc; }
 
 void m17_dsp_build_rrc_filter(float *f, float rolloff, int ntaps, int sps) { m17b_build_rrc_filter(f, rolloff, ntaps, sps); }
@@ -205,9 +212,27 @@ int m17_rx_sync_samples(float *in, float *out, int len) {
     s.down(&n, v.d_nsym, 4);
     s.down(out, v.d_syms + v.sym_carry, sizeof(float) * n);
     s.collect();
+    s.from_sync = n;
     return n;
 }
-void m17_rx_symbols(float *, int) { m17b_shim::S().dispatch(); }
+void m17_rx_symbols(float *sym, int len) {
+    // symbols that m17_rx_sync_samples just returned were framed by the fused kernel already: only the records are dispatched
+    // (m17_dsp_rx's own sequence, m17_dsp.cpp:470-473); any other symbols go through the framer on their own (m17b_rx_symbols)
+    auto &s = m17b_shim::S();
+    if (s.from_sync > 0 && len == s.from_sync) { s.from_sync = 0; s.dispatch(); return; }
+    s.from_sync = 0;
+    if (len <= 0 || !s.ensure()) return;
+    for (int o = 0; o < len; o += 200) {                                 // the batch-1 receiver holds one block: 200 symbols per call
+        const int32_t n = len - o < 200 ? len - o : 200;
+        if (!s.scratch(1024)) return;
+        s.up(s.dA, sym + o, sizeof(float) * n);
+        s.up(s.dC, &n, 4);
+        if (s.chk(m17b_rx_symbols(s.rx, (const float *)s.dA, 200, (const int32_t *)s.dC, nullptr))) return;
+        s.collect();
+    }
+    s.dispatch();
+}
+void m17_rx_sym(float sym) { m17_rx_symbols(&sym, 1); }
 void m17_dsp_demap_frame(float *in, float *out) {
     m17b_shim::unary<float, float>(in, 192, out, 368, [](m17b_shim::State &s, const float *a, float *b) { return m17b_demap_frame(s.ctx, a, 1, b, nullptr); });
 }
@@ -353,6 +378,34 @@ float eq_train_unknown(float *in) { return m17b_shim_eq(in, nullptr); }
 uint16_t m17_pack_type(M17Type t) {           // m17_bit_utils.cpp:230-244 (host-side helper)
     uint16_t w = t.reserved; w <<= 4; w |= t.can; w <<= 2; w |= t.est; w <<= 2; w |= t.et; w <<= 2; w |= t.dt; w <<= 1; w |= t.p_s;
     return w;
+}
+M17Type m17_upack_type(uint16_t w) {          // m17_bit_utils.cpp:245-254
+    M17Type t;
+    t.reserved = (w >> 11) & 0x1F; t.can = (w >> 7) & 0xF; t.est = (w >> 5) & 0x3; t.et = (w >> 3) & 0x3; t.dt = (w >> 1) & 0x3; t.p_s = w & 0x1;
+    return t;
+}
+uint48_t m17_encode_call(const char *call) {  // m17_bit_utils.cpp:191-208: base 40, last character most significant; ' ' and anything else = 0
+    uint48_t word = 0;
+    for (int i = 8; i >= 0; i--) {
+        const char c = call[i];
+        word *= 40;
+        if (c >= 'A' && c <= 'Z') word += c - 'A' + 1;
+        else if (c >= '0' && c <= '9') word += c - '0' + 27;
+        else if (c == '-') word += 37;
+        else if (c == '/') word += 38;
+        else if (c == '.') word += 39;
+    }
+    return word;
+}
+char *m17_decode_call(uint48_t word, char *call) {   // m17_bit_utils.cpp:209-226
+    if (word == 0xFFFFFFFFFFFFull) { memcpy(call, "BROADCAST", 10); return call; }
+    for (int i = 0; i < 9; i++) {
+        const int c = (int)(word % 40);
+        call[i] = c == 0 ? ' ' : c <= 26 ? (char)('A' + c - 1) : c <= 36 ? (char)('0' + c - 27) : c == 37 ? '-' : c == 38 ? '/' : '.';
+        word /= 40;
+    }
+    call[9] = 0;
+    return call;
 }
 void m17_mod_dibits(uint8_t *dibits, int len) { m17b_shim::S().tx_syms(dibits, len); }
 void m17_mod_carrier(void) { uint8_t c[192]; memset(c, 4, sizeof(c)); m17b_shim::S().tx_syms(c, 192); }

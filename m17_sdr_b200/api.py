@@ -295,8 +295,18 @@ class Rx:
     def reset(self):
         _l.check(self.L.m17b_rx_reset(self.h, _stream()))
 
+    def m17_rx_lost(self):
+        """m17_rx_init / m17_rx_lost (m17_rx_frame.cpp:179-186): clear the sync window and the lock flag only."""
+        _l.check(self.L.m17b_rx_framer_reset(self.h, _stream()))
+
     def set_afc(self, on):
-        _l.check(self.L.m17b_rx_set_afc(self.h, int(bool(on))))
+        _l.check(self.L.m17b_rx_set_afc(self.h, int(bool(on)), _stream()))
+
+    def overflow(self):
+        """sticky capacity flags since the last reset (bit 0: the symbol seam was given more symbols than max_blocks*200)"""
+        v = C.c_int()
+        _l.check(self.L.m17b_rx_get_overflow(self.h, C.byref(v)))
+        return v.value
 
     def set_bert(self, on):
         """BERT receive extension: decode BERT frames and run m17_prbs9_rx_check on their bits (off = upstream behaviour)."""
@@ -357,16 +367,6 @@ class Rx:
     def set_slice_blocks(self, blocks):
         """Blocks per pipeline slice (0 = run the stages strictly in sequence); results do not depend on it."""
         _l.check(self.L.m17b_rx_set_slice_blocks(self.h, int(blocks)))
-
-    def set_overlap(self, on, slice_blocks=0):
-        """Experimental: front end and timing loop as two co-resident kernels coupled by per-time-slice counters (results identical)."""
-        _l.check(self.L.m17b_rx_set_overlap(self.h, int(on), int(slice_blocks)))
-
-    def debug_overlap(self):
-        """ns (relative to the front end's first start) of {front end end, timing loop start, timing loop end} of the last overlapped call."""
-        out = (C.c_uint64 * 4)()
-        _l.check(self.L.m17b_rx_debug_overlap(self.h, out))
-        return {"fe_end": int(out[1]) - int(out[0]), "sync_start": int(out[2]) - int(out[0]), "sync_end": int(out[3]) - int(out[0])}
 
     def set_chan_groups(self, groups):
         """Run the batch as `groups` independent channel groups on their own streams (0 / 1 = one chain); results do not depend on it."""

@@ -19,7 +19,7 @@
 // float differs by one ulp.  Parity of this path is therefore stated as: decoded records exact, symbols within 1e-5 relative
 // RMS (they are bit-identical whenever no such sample occurred, which the tests also report).
 #pragma once
-#include "sync_xb.cuh"
+#include "framer.cuh"
 
 #define AFC_WARPS 2              // 2 x 23 KB of shared memory per CTA
 #define AFC_PER_LANE 60            // 1920 / 32

@@ -344,12 +344,9 @@ static int launch_decode(m17b_ctx *ctx, const float *syms, int64_t sym_pitch, in
                          cudaStream_t aux = nullptr, cudaEvent_t ev_fork = nullptr, cudaEvent_t ev_join = nullptr,
                          const int2 *frame_rng = nullptr, int64_t max_frames = 0, int bert_on = 0) {
     const int tiles = (int)(((frame_rng ? max_frames : fcap) + DECODE_NT - 1) / DECODE_NT);
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(k_decode_frames<DECODE_NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_smem<DECODE_NT, true>()));
-        CUDA_TRY(cudaFuncSetAttribute(k_decode_frames<DECODE_NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_smem<DECODE_NT, false>()));
-        attr_set = true;
-    }
+    // (set on every call: the attribute is per device, a process may drive several)
+    CUDA_TRY(cudaFuncSetAttribute(k_decode_frames<DECODE_NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_smem<DECODE_NT, true>()));
+    CUDA_TRY(cudaFuncSetAttribute(k_decode_frames<DECODE_NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_smem<DECODE_NT, false>()));
     if ((int64_t)tiles * nchan > 0x7fffffffLL) return M17B_E_ARG;
     const unsigned grid = (unsigned)(tiles * nchan);
     // the two kernels touch disjoint records: run the (rare, long, sparse) LSF/packet one beside the stream-frame one

@@ -103,28 +103,19 @@ __device__ __forceinline__ LimSample fe_limit(uint32_t raw, float *mo = nullptr,
 // Items are the (channel, block) pairs of blocks [t0, t0+Tc) of a call of T blocks per channel (T is the row pitch of iq,
 // disc and mean); the whole call is t0 = 0, Tc = T.  Sub-ranges let the host pipeline the front end of one time slice with
 // the timing loop of the previous one (rx.cuh).
-// fe_done != NULL (the front end running BESIDE the timing-loop kernel, rx.cuh): items are taken in TIME-major order (all channels
-// of block 0, then of block 1, ..) and every finished unit adds its item count to fe_done[slice] (slice = block / slice_blocks)
-// after a device-scope fence, so that the consumer can start on a time slice as soon as all of its rows are in memory.
-// OVL = false is the plain kernel (one unit per warp, channel-major order, no counters).
-template <bool OVL>
 __global__ void __launch_bounds__(FE_WARPS * 32, 7) k_frontend(const uint32_t *__restrict__ iq, int64_t nchan, int64_t T, int64_t t0, int64_t Tc,
-                                                            RxChanState *st, float *__restrict__ disc, float *__restrict__ mean,
-                                                            int *fe_done, int slice_blocks) {
+                                                            RxChanState *st, float *__restrict__ disc, float *__restrict__ mean) {
     __shared__ float tout[FE_WARPS][32][17];
     __shared__ __align__(16) uint4 stage[FE_WARPS][2][160];      // two 20-sample chunks of the warp's 32 rows
     __shared__ int64_t gsl[FE_WARPS][32];                        // global (channel, block) index of each lane's item
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t nitems = nchan * Tc;
-    unsigned long long *ovl_tm = (OVL && fe_done) ? (unsigned long long *)(fe_done + 1000) : nullptr;   // instrumentation: first start / last end
-    if (OVL && ovl_tm && threadIdx.x == 0) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); atomicMin(ovl_tm + 0, now); }
-    // a warp takes units of 32 items with a grid stride: one unit per warp when the grid covers the batch (the default), several
-    // when the host caps the grid to bound how many front-end CTAs sit on an SM beside the timing-loop kernel (rx.cuh)
-    for (int64_t item0 = ((int64_t)blockIdx.x * FE_WARPS + wid) * 32; item0 < nitems; item0 += OVL ? (int64_t)gridDim.x * FE_WARPS * 32 : nitems) {
+    const int64_t item0 = ((int64_t)blockIdx.x * FE_WARPS + wid) * 32;      // one unit of 32 items per warp, channel-major
+    if (item0 >= nitems) return;
+    {
     const bool live = item0 + lane < nitems;
     const int64_t item = live ? item0 + lane : nitems - 1;       // dead lanes shadow the last item (results discarded)
-    const bool tmajor = OVL && fe_done != nullptr;
-    const int64_t ch = tmajor ? item % nchan : item / Tc, t = t0 + (tmajor ? item / nchan : item % Tc);
+    const int64_t ch = item / Tc, t = t0 + item % Tc;
     const int64_t g = ch * T + t;
     gsl[wid][lane] = g;
     __syncwarp();
@@ -173,7 +164,7 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 7) k_frontend(const uint32_t *_
         const int p = lane + 32 * k, r = p / 5;
         int64_t it = item0 + r;
         if (it >= nitems) it = nitems - 1;
-        const int64_t gr = tmajor ? (it % nchan) * T + t0 + it / nchan : (it / Tc) * T + t0 + it % Tc;
+        const int64_t gr = (it / Tc) * T + t0 + it % Tc;
         off[k] = (int32_t)((gr - gsl[wid][0]) * 480 + (p - 5 * r));
     }
     // two tiles of 160 pieces (one 20-sample chunk of the warp's 32 rows each), filled two chunks ahead with 16-byte cp.async:
@@ -216,144 +207,6 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 7) k_frontend(const uint32_t *_
         mean[g] = (acc * 0.5f) / 1920.0f;                     // offset/len (m17_dsp.cpp:214)
         if (t == T - 1) { st[ch].nz0re = z0re; st[ch].nz0im = z0im; st[ch].nz1re = z1re; st[ch].nz1im = z1im; }
     }
-    if (!OVL) return;
-    asm volatile("cp.async.wait_group 0;");                   // (only empty groups are left; keeps the group count per unit fixed)
-    if (fe_done) {
-        // publish: every lane's stores (discriminator rows, mean) become visible device-wide, then the unit is counted
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) {
-            const int64_t last = (item0 + 31 < nitems ? item0 + 31 : nitems - 1);
-            const int64_t per_slice = nchan * slice_blocks;      // items per full slice (time-major order)
-            const int s_lo = (int)(item0 / per_slice), s_hi = (int)(last / per_slice);
-            if (s_lo == s_hi) atomicAdd(fe_done + s_lo, (int)(last - item0 + 1));
-            else {
-                const int64_t first_hi = (int64_t)s_hi * per_slice;
-                atomicAdd(fe_done + s_lo, (int)(first_hi - item0));
-                atomicAdd(fe_done + s_hi, (int)(last - first_hi + 1));
-            }
-        }
-    }
-    __syncwarp();
-    }
-    if (OVL && ovl_tm && lane == 0) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); atomicMax(ovl_tm + 1, now); }
-}
-
-// ---------------------------------------------------------------- TMA-staged variant
-// Same mapping (one lane per (channel, block) item, 32 items per warp) and the same arithmetic, but the rows no longer come
-// through per-lane 16-byte loads: a warp-wide LDG.128 whose 32 lanes sit 7680 B apart costs 32 L1 tag wavefronts, and that
-// -- not HBM, not issue slots -- is what bounded k_frontend (it ran at the same speed with 10 % fewer instructions).
-// Here every lane streams its row with 1-D bulk copies (cp.async.bulk, the TMA unit: no LSU / L1 involvement, no staging
-// registers) of 240 B = 60 samples into its own slot of a shared-memory ring, FE2_NST stages deep, each copy completing on
-// the lane's own mbarrier.  The lane then reads its slot with 16-byte LDS (slot pitch 60 words = 4 x odd: the 8 lanes of a
-// quarter-warp hit disjoint bank groups).  60 = lcm(4, 5) x 3 keeps both the word alignment and the /5 pattern compile-time.
-// Kept outputs collect in a [32][49] tile flushed with coalesced row stores every 4 stages (240 samples -> 48 values).
-#define FE2_CH 60
-#ifndef FE2_NST
-#define FE2_NST 4
-#endif
-#define FE2_STAGES (M17B_BLOCK_SAMPLES / FE2_CH)      // 32
-struct Fe2WarpSmem {
-    uint32_t ring[FE2_NST][32][FE2_CH];
-    float tout[32][49];
-    unsigned long long mbar[FE2_NST][32];
-    int64_t g[32];
-};
-
-__device__ __forceinline__ void fe2_issue(Fe2WarpSmem &sm, const uint32_t *row, int k, int lane) {
-    const int st = k % FE2_NST;
-    const unsigned bar = (unsigned)__cvta_generic_to_shared(&sm.mbar[st][lane]);
-    const unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.ring[st][lane][0]);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(FE2_CH * 4) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(row + k * FE2_CH), "r"(FE2_CH * 4), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void fe2_wait(Fe2WarpSmem &sm, int k, int lane) {
-    const unsigned bar = (unsigned)__cvta_generic_to_shared(&sm.mbar[k % FE2_NST][lane]);
-    const unsigned parity = (unsigned)((k / FE2_NST) & 1);
-    asm volatile("{\n\t.reg .pred p;\n\tFE2_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra FE2_DONE;\n\tbra FE2_WAIT;\n\tFE2_DONE:\n\t}"
-                 ::"r"(bar), "r"(parity) : "memory");
-}
-
-__global__ void __launch_bounds__(32) k_frontend_tma(const uint32_t *__restrict__ iq, int64_t nchan, int64_t T, int64_t t0, int64_t Tc,
-                                                     RxChanState *st, float *__restrict__ disc, float *__restrict__ mean) {
-    extern __shared__ __align__(16) unsigned char fe2_smem_raw[];
-    Fe2WarpSmem &sm = *(Fe2WarpSmem *)fe2_smem_raw;
-    const int lane = threadIdx.x;
-    const int64_t nitems = nchan * Tc;
-    const int64_t item0 = (int64_t)blockIdx.x * 32;
-    const bool live = item0 + lane < nitems;
-    const int64_t item = live ? item0 + lane : nitems - 1;       // dead lanes shadow the last item (results discarded)
-    const int64_t ch = item / Tc, t = t0 + item % Tc;
-    const int64_t g = ch * T + t;
-    sm.g[lane] = g;
-    const uint32_t *row = iq + g * M17B_BLOCK_SAMPLES;
-#pragma unroll
-    for (int s = 0; s < FE2_NST; s++) {
-        const unsigned bar = (unsigned)__cvta_generic_to_shared(&sm.mbar[s][lane]);
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#pragma unroll
-    for (int k = 0; k < FE2_NST - 1; k++) fe2_issue(sm, row, k, lane);
-
-    float z0re, z0im, z1re, z1im;
-    if (t == 0) { z0re = st[ch].z0re; z0im = st[ch].z0im; z1re = st[ch].z1re; z1im = st[ch].z1im; }
-    else {
-        LimSample a, b;
-        fe_limit2(__ldg(row - 1), __ldg(row - 2), a, b);
-        z0re = a.re; z0im = a.im; z1re = b.re; z1im = b.im;
-    }
-    float acc = 0.0f;
-    for (int k = 0; k < FE2_STAGES; k++) {
-        // the slot of stage k-1 was read completely (its values are in registers / consumed) before this point in program order
-        if (k + FE2_NST - 1 < FE2_STAGES) fe2_issue(sm, row, k + FE2_NST - 1, lane);
-        fe2_wait(sm, k, lane);
-        const uint4 *slot = (const uint4 *)&sm.ring[k % FE2_NST][lane][0];
-        float *trow = &sm.tout[lane][(k & 3) * 12];
-#pragma unroll
-        for (int c3 = 0; c3 < 3; c3++) {
-            uint4 w[5];
-#pragma unroll
-            for (int q = 0; q < 5; q++) w[q] = slot[c3 * 5 + q];
-#pragma unroll
-            for (int s = 0; s < 20; s += 2) {
-                const uint4 q = w[s >> 2];
-                const uint32_t raw0 = (s & 3) == 0 ? q.x : q.z, raw1 = (s & 3) == 0 ? q.y : q.w;
-                LimSample x0, x1;
-                fe_limit2(raw0, raw1, x0, x1);
-                // dsp_arctan_disc2 (m17_dsp.cpp:203-212), two samples
-                const float a0 = z0im * (x0.re - z1re);
-                const float b0 = z0re * (x0.im - z1im);
-                const float u0 = b0 - a0;
-                acc += u0;
-                const float a1 = x0.im * (x1.re - z0re);
-                const float b1 = x0.re * (x1.im - z0im);
-                const float u1 = b1 - a1;
-                acc += u1;
-                if (s % 5 == FE_KEEP) trow[c3 * 4 + s / 5] = u0 * 0.5f;
-                if ((s + 1) % 5 == FE_KEEP) trow[c3 * 4 + (s + 1) / 5] = u1 * 0.5f;
-                z1re = x0.re; z1im = x0.im; z0re = x1.re; z0im = x1.im;
-            }
-        }
-        if ((k & 3) == 3) {
-            __syncwarp();
-            const int o = (k >> 2) * 48;
-#pragma unroll 4
-            for (int r = 0; r < 32; r++) {
-                if (item0 + r < nitems) {
-                    float *d = disc + sm.g[r] * 384 + o;
-                    d[lane] = sm.tout[r][lane];
-                    if (lane < 16) d[32 + lane] = sm.tout[r][32 + lane];
-                }
-            }
-            __syncwarp();
-        }
-    }
-    if (live) {
-        mean[g] = (acc * 0.5f) / 1920.0f;                     // offset/len (m17_dsp.cpp:214)
-        if (t == T - 1) { st[ch].nz0re = z0re; st[ch].nz0im = z0im; st[ch].nz1re = z1re; st[ch].nz1im = z1im; }
     }
 }
 

@@ -13,7 +13,6 @@
 #define M17B_TIMING_RING 64
 #define M17B_MAX_SLICES 16
 #define M17B_MAX_GROUPS 8
-#define M17B_MAX_FE_SLICES 1000         // (the counter array holds 1024 ints; the last 24 are instrumentation)
 struct m17b_rx {
     m17b_ctx *ctx;
     int64_t nchan, max_blocks, last_blocks;
@@ -33,6 +32,7 @@ struct m17b_rx {
     cudaEvent_t ev_fork, ev_join;
     cudaEvent_t ev_h2d[2], ev_done[2], ev_tail;
     int afc, bert, last_launches, seam_last;
+    int *d_overflow;                  // sticky flags (m17b_rx_get_overflow): 1 = the symbol seam was given more symbols than the capacity
     // time-sliced pipeline (see rx_pipeline): front end of slice k+1 | timing loop + framer of slice k | frame decode of slice k-1
     int slice_blocks;                 // blocks per slice; 0 = one slice (stages strictly in sequence)
     cudaStream_t s_fe, s_sync, s_dec;
@@ -44,12 +44,7 @@ struct m17b_rx {
     int chan_groups;                  // -1 = auto (4 groups for 512..1184 channels, measured on B200: 2.07 -> 1.96 ms at 1024 x 250), 0 / 1 = off
     cudaStream_t s_grp[M17B_MAX_GROUPS], s_grp_aux[M17B_MAX_GROUPS];
     cudaEvent_t ev_gfork, ev_gjoin[M17B_MAX_GROUPS], ev_gf[M17B_MAX_GROUPS], ev_gj[M17B_MAX_GROUPS];
-    // overlapped mode (see rx_pipeline): front end and timing loop as two co-resident kernels coupled by per-time-slice counters
-    int overlap;                      // 0 = off
-    int overlap_slice;                // blocks per hand-over slice
-    int *d_fe_done;                   // [M17B_MAX_FE_SLICES] items of each slice the front end has finished
-    int *h_fe_err, *d_fe_err;         // mapped host flag: the timing loop gave up waiting for the front end
-    int sync_impl;                    // -1 auto; 0: warp per channel (sync.cuh); 2 / 4: CTA of that many warps per channel (sync_cta.cuh); 8 / 16 / 32: lanes per channel (sync_g.cuh); 33: 32 lanes with taps in smem; 64: producer/consumer warp pair (sync_pc.cuh); 65: two warps alternating blocks (sync_xb.cuh)
+    int sync_impl;                    // -1 auto; 0: warp per channel (sync.cuh); 2 / 4: CTA of that many warps per channel (sync_cta.cuh); 33: warp per channel with the taps in shared memory (sync_g.cuh)
     int timing;                       // record cudaEvents around each stage of the next calls (bench only)
     cudaEvent_t ev_stage[M17B_TIMING_RING][5];
     int64_t tcount;                   // calls made since timing was enabled
@@ -250,7 +245,7 @@ extern "C" int m17b_rx_destroy(m17b_rx *rx) {
         if (rx->ev_done[i]) cudaEventDestroy(rx->ev_done[i]);
     }
     if (rx->ev_tail) cudaEventDestroy(rx->ev_tail);
-    cudaFree(rx->d_frame_rng); cudaFree(rx->d_lsf_snap); cudaFree(rx->d_lsf_ver);
+    cudaFree(rx->d_frame_rng); cudaFree(rx->d_lsf_snap); cudaFree(rx->d_lsf_ver); cudaFree(rx->d_overflow);
     if (rx->s_fe) cudaStreamDestroy(rx->s_fe);
     if (rx->s_sync) cudaStreamDestroy(rx->s_sync);
     if (rx->s_dec) cudaStreamDestroy(rx->s_dec);
@@ -265,8 +260,6 @@ extern "C" int m17b_rx_destroy(m17b_rx *rx) {
         if (rx->ev_gj[g]) cudaEventDestroy(rx->ev_gj[g]);
     }
     if (rx->ev_gfork) cudaEventDestroy(rx->ev_gfork);
-    if (rx->d_fe_done) cudaFree(rx->d_fe_done);
-    if (rx->h_fe_err) cudaFreeHost(rx->h_fe_err);
     if (rx->copy_stream) cudaStreamDestroy(rx->copy_stream);
     if (rx->aux_stream) cudaStreamDestroy(rx->aux_stream);
     if (rx->ev_fork) cudaEventDestroy(rx->ev_fork);
@@ -278,6 +271,7 @@ extern "C" int m17b_rx_destroy(m17b_rx *rx) {
 
 extern "C" int m17b_rx_reset(m17b_rx *rx, void *stream) {
     if (!rx) return M17B_E_ARG;
+    CUDA_TRY(cudaSetDevice(rx->ctx->device));
     cudaStream_t st = as_stream(stream);
     k_rx_reset<<<grid_for(rx->nchan, 128), 128, 0, st>>>(rx->d_state, rx->nchan);
     KERNEL_CHECK();
@@ -286,6 +280,23 @@ extern "C" int m17b_rx_reset(m17b_rx *rx, void *stream) {
     CUDA_TRY(cudaMemsetAsync(rx->d_stats, 0, sizeof(unsigned long long) * rx->nchan * 8, st));
     CUDA_TRY(cudaMemsetAsync(rx->d_nframes, 0, sizeof(int32_t) * rx->nchan, st));
     CUDA_TRY(cudaMemsetAsync(rx->d_nevents, 0, sizeof(int32_t) * rx->nchan, st));
+    CUDA_TRY(cudaMemsetAsync(rx->d_overflow, 0, sizeof(int), st));
+    return M17B_OK;
+}
+
+// m17_rx_init / m17_rx_lost (m17_rx_frame.cpp:179-186): reset_sync() -- the sliding sync window reads as zeros -- and
+// m_flock = false.  Nothing else: the timing loop, the frame counters and the LICH cache stay as they are.
+__global__ void k_rx_framer_reset(RxChanState *st, int64_t nchan) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchan) return;
+    for (int i = 0; i < 8; i++) st[c].win[i] = 0.0f;
+    st[c].flock = 0;
+}
+extern "C" int m17b_rx_framer_reset(m17b_rx *rx, void *stream) {
+    if (!rx) return M17B_E_ARG;
+    CUDA_TRY(cudaSetDevice(rx->ctx->device));
+    k_rx_framer_reset<<<grid_for(rx->nchan, 128), 128, 0, as_stream(stream)>>>(rx->d_state, rx->nchan);
+    KERNEL_CHECK();
     return M17B_OK;
 }
 
@@ -299,7 +310,8 @@ extern "C" int m17b_rx_create(m17b_ctx *ctx, int64_t nchan, int64_t max_blocks, 
     rx->sync_impl = -1;                // auto: few channels per launch -> 4 warps per channel (latency), many -> 1 warp per channel (fewest instructions)
     if (const char *e = getenv("M17B_SYNC_IMPL")) rx->sync_impl = atoi(e);     // tuning knob: 0 = one warp per channel, 2 / 4 = warps per channel
     rx->sym_pitch = (M17B_SYM_CARRY + max_blocks * M17B_SYM_CAP_PER_BLOCK + 3) & ~(int64_t)3;
-    rx->fcap = max_blocks + max_blocks / 64 + 4;
+    // records: the timing loop yields at most 193 symbols per block, the symbol seam accepts up to 200 per block -- size for the latter
+    rx->fcap = (max_blocks * M17B_SYM_CAP_PER_BLOCK + M17B_FRAME_SYMS - 1) / M17B_FRAME_SYMS + 2;
     rx->ecap = 2 * rx->fcap + 4;
     cudaError_t e = cudaSuccess;
     auto A = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
@@ -319,39 +331,35 @@ extern "C" int m17b_rx_create(m17b_ctx *ctx, int64_t nchan, int64_t max_blocks, 
     if (rx->nsnap > 255) rx->nsnap = 255;
     A((void **)&rx->d_lsf_snap, (size_t)nchan * rx->nsnap * 32);
     A((void **)&rx->d_lsf_ver, (size_t)nchan * rx->fcap);
+    A((void **)&rx->d_overflow, sizeof(int));
     if (e != cudaSuccess) { m17b_set_cuda_error(e, __FILE__, __LINE__); m17b_rx_destroy(rx); return e == cudaErrorMemoryAllocation ? M17B_E_NOMEM : M17B_E_CUDA; }
-    CUDA_TRY(cudaStreamCreateWithFlags(&rx->aux_stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaEventCreateWithFlags(&rx->ev_fork, cudaEventDisableTiming));
-    CUDA_TRY(cudaEventCreateWithFlags(&rx->ev_join, cudaEventDisableTiming));
+#define CREATE_TRY(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { m17b_set_cuda_error(e__, __FILE__, __LINE__); m17b_rx_destroy(rx); return M17B_E_CUDA; } } while (0)
+    CREATE_TRY(cudaStreamCreateWithFlags(&rx->aux_stream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaEventCreateWithFlags(&rx->ev_fork, cudaEventDisableTiming));
+    CREATE_TRY(cudaEventCreateWithFlags(&rx->ev_join, cudaEventDisableTiming));
     {   // the serial chain of the timing loop is the critical path of the pipeline: it gets the highest priority
         int lo = 0, hi = 0;
-        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CUDA_TRY(cudaStreamCreateWithPriority(&rx->s_sync, cudaStreamNonBlocking, hi));
-        CUDA_TRY(cudaStreamCreateWithPriority(&rx->s_dec, cudaStreamNonBlocking, hi < lo ? hi + 1 : lo));
-        CUDA_TRY(cudaStreamCreateWithPriority(&rx->s_fe, cudaStreamNonBlocking, lo));
-        CUDA_TRY(cudaEventCreateWithFlags(&rx->ev_start, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&rx->ev_end, cudaEventDisableTiming));
+        CREATE_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CREATE_TRY(cudaStreamCreateWithPriority(&rx->s_sync, cudaStreamNonBlocking, hi));
+        CREATE_TRY(cudaStreamCreateWithPriority(&rx->s_dec, cudaStreamNonBlocking, hi < lo ? hi + 1 : lo));
+        CREATE_TRY(cudaStreamCreateWithPriority(&rx->s_fe, cudaStreamNonBlocking, lo));
+        CREATE_TRY(cudaEventCreateWithFlags(&rx->ev_start, cudaEventDisableTiming));
+        CREATE_TRY(cudaEventCreateWithFlags(&rx->ev_end, cudaEventDisableTiming));
         for (int i = 0; i < M17B_MAX_SLICES; i++) {
-            CUDA_TRY(cudaEventCreateWithFlags(&rx->ev_fe[i], cudaEventDisableTiming));
-            CUDA_TRY(cudaEventCreateWithFlags(&rx->ev_sy[i], cudaEventDisableTiming));
+            CREATE_TRY(cudaEventCreateWithFlags(&rx->ev_fe[i], cudaEventDisableTiming));
+            CREATE_TRY(cudaEventCreateWithFlags(&rx->ev_sy[i], cudaEventDisableTiming));
         }
     }
     rx->slice_blocks = 0;          // measured on B200: slicing gives no gain at 1024 channels (the kernels contend for issue slots), see DESIGN.md 4
     if (const char *e2 = getenv("M17B_SLICE_BLOCKS")) rx->slice_blocks = atoi(e2);
-    rx->overlap = 0; rx->overlap_slice = 10;
-    if (const char *e4 = getenv("M17B_OVERLAP")) rx->overlap = atoi(e4);
-    if (const char *e5 = getenv("M17B_OVERLAP_SLICE")) rx->overlap_slice = atoi(e5) > 0 ? atoi(e5) : 10;
-    CUDA_TRY(cudaMalloc((void **)&rx->d_fe_done, sizeof(int) * 1024));
-    CUDA_TRY(cudaHostAlloc((void **)&rx->h_fe_err, sizeof(int), cudaHostAllocMapped));
-    *rx->h_fe_err = 0;
-    CUDA_TRY(cudaHostGetDevicePointer((void **)&rx->d_fe_err, rx->h_fe_err, 0));
     rx->chan_groups = -1;
     if (const char *e3 = getenv("M17B_CHAN_GROUPS")) rx->chan_groups = atoi(e3);
     e = cudaMemset(rx->d_syms, 0, sizeof(float) * nchan * rx->sym_pitch);
     if (e != cudaSuccess) { m17b_set_cuda_error(e, __FILE__, __LINE__); m17b_rx_destroy(rx); return M17B_E_CUDA; }
     int rc = m17b_rx_reset(rx, nullptr);
     if (rc) { m17b_rx_destroy(rx); return rc; }
-    CUDA_TRY(cudaStreamSynchronize(nullptr));
+    CREATE_TRY(cudaStreamSynchronize(nullptr));
+#undef CREATE_TRY
     *out = rx;
     return M17B_OK;
 }
@@ -359,41 +367,20 @@ extern "C" int m17b_rx_create(m17b_ctx *ctx, int64_t nchan, int64_t max_blocks, 
 // radio_set_afc_on / radio_set_afc_off (radio.cpp:146-152).  With AFC on, m17b_dsp_rx alternates the AFC front end
 // (afc.cuh) and the sync/framer kernel one block at a time, because the NCO step of a block depends on the framer state and
 // the discriminator mean of the block before it.
-extern "C" int m17b_rx_set_afc(m17b_rx *rx, int on) {
+extern "C" int m17b_rx_set_afc(m17b_rx *rx, int on, void *stream) {
     if (!rx) return M17B_E_ARG;
     if (!on && rx->afc) {
-        k_afc_off<<<grid_for(rx->nchan, 128), 128>>>(rx->d_state, rx->nchan);
+        CUDA_TRY(cudaSetDevice(rx->ctx->device));
+        k_afc_off<<<grid_for(rx->nchan, 128), 128, 0, as_stream(stream)>>>(rx->d_state, rx->nchan);
         KERNEL_CHECK();
     }
     rx->afc = on != 0;
     return M17B_OK;
 }
 
-// front end over blocks [t0, t0+Tc): the per-lane-load kernel; M17B_FE_IMPL=1 selects the TMA-staged variant (measured slower:
-// its 23-38 KB of ring per warp leaves 5-9 warps per SM, too few to cover the limiter's dependency chains)
-static int launch_frontend(const int16_t *d_iq, int64_t nc, int64_t T, int64_t t0, int64_t Tc, RxChanState *state, float *disc, float *mean, cudaStream_t st,
-                           int *fe_done = nullptr, int fe_slice = 0, int cap_override = 0) {
-    static int impl = -1, fe_cap_env = 0, sm_count = 148;
-    if (impl < 0) {
-        int dev = 0;
-        CUDA_TRY(cudaGetDevice(&dev));
-        CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-        if (const char *fc = getenv("M17B_FE_CTAS_PER_SM")) fe_cap_env = atoi(fc);
-        const char *e = getenv("M17B_FE_IMPL");
-        impl = e ? atoi(e) : 0;
-        CUDA_TRY(cudaFuncSetAttribute(k_frontend_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Fe2WarpSmem)));
-        if (const char *cv = getenv("M17B_FE_CARVEOUT")) CUDA_TRY(cudaFuncSetAttribute(k_frontend<false>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
-    }
-    const int fe_cap = fe_cap_env > 0 ? fe_cap_env : cap_override;
-    if (impl == 1 && !fe_done) k_frontend_tma<<<grid_for(nc * Tc, 32), 32, sizeof(Fe2WarpSmem), st>>>((const uint32_t *)d_iq, nc, T, t0, Tc, state, disc, mean);
-    else {
-        // fe_cap > 0: at most that many front-end CTAs per SM (a grid-stride grid), leaving registers and shared memory for the
-        // timing-loop CTAs of the slice before when the two run side by side
-        unsigned g = grid_for(nc * Tc, FE_WARPS * 32);
-        if (fe_cap > 0 && g > (unsigned)(fe_cap * sm_count)) g = (unsigned)(fe_cap * sm_count);
-        if (fe_done || fe_cap > 0) k_frontend<true><<<g, FE_WARPS * 32, 0, st>>>((const uint32_t *)d_iq, nc, T, t0, Tc, state, disc, mean, fe_done, fe_slice);
-        else k_frontend<false><<<g, FE_WARPS * 32, 0, st>>>((const uint32_t *)d_iq, nc, T, t0, Tc, state, disc, mean, nullptr, 0);
-    }
+// front end over blocks [t0, t0+Tc) of channels [.., +nc)
+static int launch_frontend(const int16_t *d_iq, int64_t nc, int64_t T, int64_t t0, int64_t Tc, RxChanState *state, float *disc, float *mean, cudaStream_t st) {
+    k_frontend<<<grid_for(nc * Tc, FE_WARPS * 32), FE_WARPS * 32, 0, st>>>((const uint32_t *)d_iq, nc, T, t0, Tc, state, disc, mean);
     KERNEL_CHECK();
     return M17B_OK;
 }
@@ -402,51 +389,21 @@ static int launch_frontend(const int16_t *d_iq, int64_t nc, int64_t T, int64_t t
 
 // matched filter + timing loop + framer over blocks [t0, t1) of channels [c0, c0+nc)
 static int launch_sync(m17b_rx *rx, int64_t c0, int64_t nc, const float *disc, const float *mean, int64_t T, int t0, int t1, int2 *rng, int commit_fe,
-                       cudaStream_t st, const int *fe_done = nullptr, int fe_slice = 0, bool shared_gpu = false) {
+                       cudaStream_t st, bool shared_gpu = false) {
     m17b_ctx *ctx = rx->ctx;
 #define SYNC_ARGS disc, mean, nc, T, t0, t1, rng, rx->d_state + c0, ctx->d_mf, ctx->d_md, rx->d_syms + c0 * rx->sym_pitch, rx->sym_pitch, rx->d_nsym + c0 * T, \
                   rx->d_sym_base + c0, rx->d_frames + c0 * rx->fcap, rx->fcap, rx->d_nframes + c0, rx->d_events + c0 * rx->ecap, rx->ecap, rx->d_nevents + c0, \
-                  rx->d_stats + c0 * 8, commit_fe, fe_done, fe_slice, rx->d_fe_err
+                  rx->d_stats + c0 * 8, commit_fe
     // auto policy (measured on B200): one warp per channel has the fewest instructions and wins from ~512 channels
-    // up; below that a channel's serial chain is the whole story and four warps per channel shorten it
-    // Beyond one resident wave (8 channels per SM at 178 registers = 1184 on a B200) the tap-pairs-in-shared-memory variant
-    // (108 registers, 16 warps per SM) is 15-23 % faster: 2048 ch 1.64 -> 1.33 ms, 4096 ch 3.26 -> 2.52 ms.
-    // beside the front end (fe_done): the 110-register variant, so that two of its CTAs and four front-end CTAs share an SM;
-    // only the one-warp-per-channel kernels (0, 33) know how to wait for the front end
-    // (shared_gpu: the launch is one of several channel groups running side by side -- the four-warps-per-channel form only pays
-    //  when a small launch has the GPU to itself)
-    int impl = rx->sync_impl >= 0 ? rx->sync_impl : (nc <= 256 && !shared_gpu ? 4 : nc <= 8 * 148 ? 0 : 33);
-    if (fe_done && impl != 0 && impl != 33) impl = 33;
-    if (fe_done && rx->sync_impl < 0) impl = 33;
+    // up; below that a channel's serial chain is the whole story and four warps per channel shorten it (only when the launch has
+    // the GPU to itself: not inside a channel group).  Beyond one resident wave (8 channels per SM at 168 registers = 1184 on a
+    // B200) the tap-pairs-in-shared-memory variant (108 registers, 16 warps per SM) is 15-23 % faster.
+    const int impl = rx->sync_impl >= 0 ? rx->sync_impl : (nc <= 256 && !shared_gpu ? 4 : nc <= 8 * 148 ? 0 : 33);
     if (impl == 33) {
-        // one warp per channel, tap pairs in shared memory: 16 resident warps per SM, for batches that do not fit one wave
         const size_t smem = sizeof(SyncGroupSmem) * SY_WARPS;
         const unsigned g = grid_for(nc, SY_WARPS);
-        if (fe_done)   k_sync_frame_g<true, 32, true, true><<<g, SY_WARPS * 32, smem, st>>>(SYNC_ARGS);      // beside the front end (always HAS_MEAN)
-        else if (mean) k_sync_frame_g<true, 32, true><<<g, SY_WARPS * 32, smem, st>>>(SYNC_ARGS);
-        else           k_sync_frame_g<false, 32, true><<<g, SY_WARPS * 32, smem, st>>>(SYNC_ARGS);
-    } else if (impl == 65) {
-        // two warps per channel alternating blocks: dot products + votes of block t+1 speculated while block t is resolved (sync_xb.cuh)
-        const unsigned g = grid_for(nc, XB_CH);
-        if (mean) k_sync_frame_xb<true><<<g, XB_CH * 64, 0, st>>>(SYNC_ARGS);
-        else      k_sync_frame_xb<false><<<g, XB_CH * 64, 0, st>>>(SYNC_ARGS);
-    } else if (impl == 64) {
-        // two warps per channel, producer (timing loop) / consumer (framer): sync_pc.cuh
-        const unsigned g = grid_for(nc, PC_CH);
-        if (mean) k_sync_frame_pc<true><<<g, PC_CH * 64, 0, st>>>(SYNC_ARGS);
-        else      k_sync_frame_pc<false><<<g, PC_CH * 64, 0, st>>>(SYNC_ARGS);
-    } else if (impl == 8 || impl == 16 || impl == 32) {
-        // G lanes per channel (sync_g.cuh): 32 / G channels share a warp's instruction stream
-#define SYNC_G(GG) do { \
-            const size_t smem = sizeof(SyncGroupSmem) * SY_WARPS * (32 / GG); \
-            static bool attr = false; \
-            if (!attr) { CUDA_TRY(cudaFuncSetAttribute(k_sync_frame_g<true, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-                         CUDA_TRY(cudaFuncSetAttribute(k_sync_frame_g<false, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; } \
-            const unsigned g = grid_for(nc, SY_WARPS * (32 / GG)); \
-            if (mean) k_sync_frame_g<true, GG><<<g, SY_WARPS * 32, smem, st>>>(SYNC_ARGS); \
-            else      k_sync_frame_g<false, GG><<<g, SY_WARPS * 32, smem, st>>>(SYNC_ARGS); } while (0)
-        if (impl == 8) SYNC_G(8); else if (impl == 16) SYNC_G(16); else SYNC_G(32);
-#undef SYNC_G
+        if (mean) k_sync_frame_g<true, 32, true><<<g, SY_WARPS * 32, smem, st>>>(SYNC_ARGS);
+        else      k_sync_frame_g<false, 32, true><<<g, SY_WARPS * 32, smem, st>>>(SYNC_ARGS);
     } else if (impl == 4) {
         if (mean) k_sync_frame_cta<4, true><<<(unsigned)nc, 128, 0, st>>>(SYNC_ARGS);
         else      k_sync_frame_cta<4, false><<<(unsigned)nc, 128, 0, st>>>(SYNC_ARGS);
@@ -455,9 +412,8 @@ static int launch_sync(m17b_rx *rx, int64_t c0, int64_t nc, const float *disc, c
         else      k_sync_frame_cta<2, false><<<(unsigned)nc, 64, 0, st>>>(SYNC_ARGS);
     } else {
         const unsigned g = grid_for(nc, SY_WARPS);
-        if (fe_done)   k_sync_frame<true, true><<<g, SY_WARPS * 32, 0, st>>>(SYNC_ARGS);
-        else if (mean) k_sync_frame<true><<<g, SY_WARPS * 32, 0, st>>>(SYNC_ARGS);
-        else           k_sync_frame<false><<<g, SY_WARPS * 32, 0, st>>>(SYNC_ARGS);
+        if (mean) k_sync_frame<true><<<g, SY_WARPS * 32, 0, st>>>(SYNC_ARGS);
+        else      k_sync_frame<false><<<g, SY_WARPS * 32, 0, st>>>(SYNC_ARGS);
     }
 #undef SYNC_ARGS
     KERNEL_CHECK();
@@ -509,62 +465,6 @@ static int rx_pipeline(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t *d_iq,
         rx->last_launches += (int)(2 * T) + 3;
         return M17B_OK;
     }
-    if (rx->overlap && d_iq && !rx->timing && nc >= 64 && T >= 2 * rx->overlap_slice && (T + rx->overlap_slice - 1) / rx->overlap_slice <= M17B_MAX_FE_SLICES) {
-        // Overlapped mode: the front end (block-parallel, throughput-bound) and the timing loop + framer (one serial chain per
-        // channel, latency-bound, leaves most issue slots idle) run as two CO-RESIDENT kernels.  The front end walks the batch in
-        // time-major order with a capped, grid-stride grid (4 CTAs per SM) and counts finished items per time slice; each
-        // timing-loop warp waits (bounded) for a slice's counter before it fetches the slice's first block.  The front end never
-        // waits for anything, so the pair cannot deadlock whatever the residency.  Results are identical: every kernel reads and
-        // writes exactly what it would have.
-        const int sb2 = rx->overlap_slice;
-        const int nfs = (int)((T + sb2 - 1) / sb2);
-        CUDA_TRY(cudaMemsetAsync(rx->d_fe_done, 0, sizeof(int) * nfs, st));
-        CUDA_TRY(cudaMemsetAsync(rx->d_fe_done + 1000, 0, 32, st));                 // instrumentation: {fe first start, fe last end, sync first start, sync last end}
-        CUDA_TRY(cudaMemsetAsync(rx->d_fe_done + 1000, 0xFF, 8, st));
-        CUDA_TRY(cudaMemsetAsync(rx->d_fe_done + 1004, 0xFF, 8, st));
-        CUDA_TRY(cudaEventRecord(rx->ev_start, st));
-        CUDA_TRY(cudaStreamWaitEvent(rx->s_fe, rx->ev_start, 0));
-        CUDA_TRY(cudaStreamWaitEvent(rx->s_sync, rx->ev_start, 0));
-        // Two things are needed for the pair to be co-resident at all (measured: without either, the timing loop's bounded wait
-        // expires): the front end is launched FIRST, and both kernels ask for the same shared-memory carve-out -- otherwise the
-        // second kernel's CTAs wait for the SMs to drain so that the carve-out can be changed.
-        static int ovl_init = 0, fe_first = 1;
-        if (!ovl_init) {
-            ovl_init = 1;
-            if (const char *o = getenv("M17B_OVL_FE_FIRST")) fe_first = atoi(o);
-            {
-                const char *o = getenv("M17B_OVL_CARVEOUT");
-                const int cv = o ? atoi(o) : 100;
-                CUDA_TRY(cudaFuncSetAttribute(k_frontend<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cv));
-                CUDA_TRY(cudaFuncSetAttribute(k_sync_frame_g<true, 32, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cv));
-                CUDA_TRY(cudaFuncSetAttribute(k_sync_frame<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cv));
-            }
-        }
-        int rc;
-        if (fe_first) {
-            rc = launch_frontend(d_iq, nc, T, 0, T, rx->d_state + c0, disc_w, mean_w, rx->s_fe, rx->d_fe_done, sb2, 4);
-            if (rc) return rc;
-        }
-        rc = launch_sync(rx, c0, nc, disc, mean, T, 0, (int)T, nullptr, commit_fe, rx->s_sync, rx->d_fe_done, sb2);
-        if (rc) return rc;
-        if (!fe_first) {
-            rc = launch_frontend(d_iq, nc, T, 0, T, rx->d_state + c0, disc_w, mean_w, rx->s_fe, rx->d_fe_done, sb2, 4);
-            if (rc) return rc;
-        }
-        CUDA_TRY(cudaEventRecord(rx->ev_fe[0], rx->s_fe));
-        CUDA_TRY(cudaEventRecord(rx->ev_sy[0], rx->s_sync));
-        CUDA_TRY(cudaStreamWaitEvent(st, rx->ev_fe[0], 0));
-        CUDA_TRY(cudaStreamWaitEvent(st, rx->ev_sy[0], 0));
-        rc = launch_decode(ctx, syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0, nc, nullptr, st,
-                           aux_stream, ev_fork, ev_join, nullptr, 0, rx->bert);
-        if (rc) return rc;
-        k_post<<<grid_for(nc, POST_WARPS), POST_WARPS * 32, 0, st>>>(frames, rx->fcap, rx->d_nframes + c0, nc, rx->d_state + c0, ctx->d_crc, rx->d_stats + c0 * 8,
-                                                                  rx->d_lsf_snap + c0 * rx->nsnap * 32, rx->nsnap, rx->d_lsf_ver + c0 * rx->fcap,
-                                                                  ctx->d_prbs, rx->bert);
-        KERNEL_CHECK();
-        rx->last_launches += 5;
-        return M17B_OK;
-    }
     if (nsl < 2) {
         STAGE_MARK(0);
         if (d_iq) {
@@ -573,7 +473,7 @@ static int rx_pipeline(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t *d_iq,
             rx->last_launches += 1;
         }
         STAGE_MARK(1);
-        int rc = launch_sync(rx, c0, nc, disc, mean, T, 0, (int)T, nullptr, commit_fe, st, nullptr, 0, grp >= 0);
+        int rc = launch_sync(rx, c0, nc, disc, mean, T, 0, (int)T, nullptr, commit_fe, st, grp >= 0);
         if (rc) return rc;
         STAGE_MARK(2);
         rc = launch_decode(ctx, syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0, nc, nullptr, st,
@@ -659,14 +559,14 @@ static int rx_groups_for(const m17b_rx *rx) {
     // and above one wave nothing is gained (benchmarks/chan_groups.py).  More than 4 groups exceed the 8 hardware queues.
     if (G < 0) G = (rx->nchan >= 512 && rx->nchan <= 8 * 148) ? 4 : 1;
     if (G > M17B_MAX_GROUPS) G = M17B_MAX_GROUPS;
-    if (G < 2 || rx->timing || rx->afc || rx->overlap || rx->nchan < 2 * G) return 1;
+    if (G < 2 || rx->timing || rx->afc || rx->nchan < 2 * G) return 1;
     return G;
 }
 
 extern "C" int m17b_dsp_rx(m17b_rx *rx, const int16_t *d_iq, int64_t nblocks, void *stream) {
     if (!rx || !d_iq || nblocks <= 0) return M17B_E_ARG;
     if (nblocks > rx->max_blocks) return M17B_E_CAPACITY;
-    if (*(volatile int *)rx->h_fe_err) { m17b_set_cuda_error(cudaErrorLaunchTimeout, __FILE__, __LINE__); return M17B_E_CUDA; }   // the timing loop gave up waiting for the front end
+    CUDA_TRY(cudaSetDevice(rx->ctx->device));
     rx->last_launches = 0; rx->last_blocks = nblocks; rx->seam_last = 0;
     const int G = rx_groups_for(rx);
     int rc = G > 1 ? rx_grouped(rx, d_iq, nullptr, nblocks, as_stream(stream), G) : rx_pipeline(rx, 0, rx->nchan, d_iq, nullptr, nblocks, as_stream(stream));
@@ -677,6 +577,7 @@ extern "C" int m17b_dsp_rx(m17b_rx *rx, const int16_t *d_iq, int64_t nblocks, vo
 extern "C" int m17b_rx_baseband(m17b_rx *rx, const float *d_disc, int64_t nblocks, void *stream) {
     if (!rx || !d_disc || nblocks <= 0 || ((uintptr_t)d_disc & 15)) return M17B_E_ARG;      // rows are fetched in 16-byte pieces
     if (nblocks > rx->max_blocks) return M17B_E_CAPACITY;
+    CUDA_TRY(cudaSetDevice(rx->ctx->device));
     rx->last_launches = 0; rx->last_blocks = nblocks; rx->seam_last = 1;
     const int G = rx_groups_for(rx);
     int rc = G > 1 ? rx_grouped(rx, nullptr, d_disc, nblocks, as_stream(stream), G) : rx_pipeline(rx, 0, rx->nchan, nullptr, d_disc, nblocks, as_stream(stream));
@@ -689,12 +590,13 @@ extern "C" int m17b_rx_baseband(m17b_rx *rx, const float *d_disc, int64_t nblock
 // reported as one "block" (view.nblocks = 1, view.d_nsym[c] = symbols taken).
 extern "C" int m17b_rx_symbols(m17b_rx *rx, const float *d_syms, int64_t pitch, const int32_t *d_nsym, void *stream) {
     if (!rx || !d_syms || !d_nsym || pitch < 0) return M17B_E_ARG;
+    CUDA_TRY(cudaSetDevice(rx->ctx->device));
     m17b_ctx *ctx = rx->ctx;
     cudaStream_t st = as_stream(stream);
     rx->last_launches = 0; rx->last_blocks = 1; rx->seam_last = 2;
     const int64_t cap = rx->sym_pitch - M17B_SYM_CARRY;
     k_framer<<<grid_for(rx->nchan, 4), 128, 0, st>>>(d_syms, pitch, d_nsym, rx->nchan, rx->d_state, rx->d_syms, rx->sym_pitch, cap, rx->d_nsym, rx->d_sym_base,
-                                                   rx->d_frames, rx->fcap, rx->d_nframes, rx->d_events, rx->ecap, rx->d_nevents, rx->d_stats);
+                                                   rx->d_frames, rx->fcap, rx->d_nframes, rx->d_events, rx->ecap, rx->d_nevents, rx->d_stats, rx->d_overflow);
     KERNEL_CHECK();
     int rc = launch_decode(ctx, rx->d_syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base, rx->d_frames, rx->fcap, rx->d_nframes, rx->nchan, nullptr, st,
                            rx->aux_stream, rx->ev_fork, rx->ev_join, nullptr, 0, rx->bert);
@@ -772,21 +674,6 @@ extern "C" int m17b_rx_stage_ms(m17b_rx *rx, int64_t call_index, float *out4) {
     }
     return M17B_OK;
 }
-// instrumentation of the overlapped mode: globaltimer ns of {front end first CTA start, front end last warp end, timing loop first
-// warp start, timing loop last warp end} of the last overlapped call (synchronises)
-extern "C" int m17b_rx_debug_overlap(m17b_rx *rx, uint64_t *h_out4) {
-    if (!rx || !h_out4) return M17B_E_ARG;
-    CUDA_TRY(cudaDeviceSynchronize());
-    CUDA_TRY(cudaMemcpy(h_out4, rx->d_fe_done + 1000, 32, cudaMemcpyDeviceToHost));
-    return M17B_OK;
-}
-// overlapped front end | timing loop mode (experimental, off by default: measured no gain)
-extern "C" int m17b_rx_set_overlap(m17b_rx *rx, int on, int slice_blocks) {
-    if (!rx || slice_blocks < 0) return M17B_E_ARG;
-    rx->overlap = on != 0;
-    if (slice_blocks > 0) rx->overlap_slice = slice_blocks;
-    return M17B_OK;
-}
 // channel groups (0 / 1 = the whole batch as one chain)
 extern "C" int m17b_rx_set_chan_groups(m17b_rx *rx, int groups) {
     if (!rx || groups < -1 || groups > M17B_MAX_GROUPS) return M17B_E_ARG;
@@ -800,6 +687,16 @@ extern "C" int m17b_rx_set_slice_blocks(m17b_rx *rx, int blocks) {
     return M17B_OK;
 }
 extern "C" int64_t m17b_rx_frame_cap(const m17b_rx *rx) { return rx ? rx->fcap : 0; }
+// sticky capacity flags since the last m17b_rx_reset (synchronises the device): bit 0 = m17b_rx_symbols was handed more symbols
+// for a channel than max_blocks * 200; the excess was ignored.  (The record / event buffers are sized for the worst case of either
+// entry point, so they cannot overflow.)
+extern "C" int m17b_rx_get_overflow(m17b_rx *rx, int *h_flags) {
+    if (!rx || !h_flags) return M17B_E_ARG;
+    CUDA_TRY(cudaSetDevice(rx->ctx->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(h_flags, rx->d_overflow, sizeof(int), cudaMemcpyDeviceToHost));
+    return M17B_OK;
+}
 extern "C" int m17b_rx_last_launches(const m17b_rx *rx) { return rx ? rx->last_launches : 0; }
 
 // The chain for channels [c0, c0+nc) in TIME pieces [bounds[k], bounds[k+1]) on one stream, piece k starting once ready[k] has
@@ -839,6 +736,7 @@ static int rx_pipeline_pieces(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t
 extern "C" int m17b_dsp_rx_host(m17b_rx *rx, const int16_t *h_iq, int64_t nblocks, m17b_frame_rec *h_frames, int32_t *h_nframes, void *stream) {
     if (!rx || !h_iq || !h_frames || !h_nframes || nblocks <= 0) return M17B_E_ARG;
     if (nblocks > rx->max_blocks) return M17B_E_CAPACITY;
+    CUDA_TRY(cudaSetDevice(rx->ctx->device));
     cudaStream_t st = as_stream(stream);
     const int64_t T = nblocks;
     if (!rx->copy_stream) {

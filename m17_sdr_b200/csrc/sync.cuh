@@ -34,24 +34,6 @@ struct SyncWarpSmem {
     float pre[2][384 + 4];              // cp.async landing zone for the NEXT block's raw samples (+ its mean), double buffered
 };
 
-// The front end may run BESIDE this kernel (rx.cuh, overlapped mode): the rows of time slice s (blocks [s * fe_slice, ..)) may be
-// read once fe_done[s] has reached the number of (channel, block) items in the slice.  The wait is bounded: a producer that
-// never arrives makes the kernel give up loudly (fe_err) instead of hanging the GPU.
-__device__ __forceinline__ int ld_acquire_gpu(const int *p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
-__device__ __forceinline__ bool fe_wait_slice(const int *fe_done, int s, int target, int *fe_err) {
-    if (ld_acquire_gpu(fe_done + s) >= target) return true;
-    for (int it = 0; it < (1 << 22); it++) {                       // about one second
-        __nanosleep(200);
-        if (ld_acquire_gpu(fe_done + s) >= target) return true;
-    }
-    *fe_err = 1;
-    return false;
-}
-// before block tt is fetched: if it opens a time slice, wait for that slice
-#define FE_GATE(tt) do { if (OVL && fe_done && ((tt) - t0) % fe_slice == 0) { \
-        const int rem__ = (int)(t1 - (tt)); \
-        if (!fe_wait_slice(fe_done, (int)(((tt) - t0) / fe_slice), (int)nchan * (rem__ < fe_slice ? rem__ : fe_slice), fe_err)) return; } } while (0)
-
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += o; }
@@ -114,14 +96,13 @@ __device__ __forceinline__ void dot6(const float (*X)[SY_XQ], int base, const f3
     }
 }
 
-template <bool HAS_MEAN, bool OVL = false>
+template <bool HAS_MEAN>
 __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__restrict__ disc, const float *__restrict__ mean, int64_t nchan, int64_t T,
                                                               int t0, int t1, int2 *frame_rng, RxChanState *st, const float *__restrict__ g_mf, const float *__restrict__ g_md,
                                                               float *syms, int64_t sym_pitch, int32_t *__restrict__ nsym, int32_t *__restrict__ sym_base,
                                                               m17b_frame_rec *frames, int64_t fcap, int32_t *__restrict__ nframes,
                                                               m17b_event_rec *events, int64_t ecap, int32_t *__restrict__ nevents,
-                                                              unsigned long long *stats, int commit_fe,
-                                                              const int *fe_done, int fe_slice, int *fe_err) {
+                                                              unsigned long long *stats, int commit_fe) {
     __shared__ __align__(16) SyncWarpSmem sm_all[SY_WARPS];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t c = (int64_t)blockIdx.x * SY_WARPS + wid;
@@ -168,7 +149,6 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
     __syncwarp();
     // The block's samples are fetched one block ahead with cp.async straight into shared memory: completion is tracked by
     // the async-copy group, not by a register scoreboard, so nothing in the timing loop ever waits on the DRAM latency.
-    float pmu_pf = 0.0f;
     auto prefetch = [&](int64_t tt, int buf) {
         const float *src = disc + (c * T + tt) * 384;
 #pragma unroll
@@ -176,19 +156,12 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
             const unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.pre[buf][4 * (lane + 32 * q)]);
             asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + 4 * (lane + 32 * q)));
         }
-        if (HAS_MEAN) {
-            if (OVL && fe_done) {
-                // beside a running front end the block mean is read from L2 into a register: eight means share a 32-byte
-                // sector that the front end is still writing, so an L1-cached copy could be stale
-                pmu_pf = __ldcg(mean + c * T + tt);
-            } else if (lane == 0) {
-                const unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.pre[buf][384]);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(mean + c * T + tt));
-            }
+        if (HAS_MEAN && lane == 0) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.pre[buf][384]);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(mean + c * T + tt));
         }
         asm volatile("cp.async.commit_group;");
     };
-    FE_GATE(t0);
     prefetch(t0, 0);
 
     for (int64_t t = t0; t < t1; t++) {
@@ -197,7 +170,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
         asm volatile("cp.async.wait_group 0;");
         __syncwarp();
         {
-            const float pmu = !HAS_MEAN ? 0.0f : (OVL && fe_done) ? pmu_pf : sm.pre[buf][384];
+            const float pmu = !HAS_MEAN ? 0.0f : sm.pre[buf][384];
 #pragma unroll
             for (int q = 0; q < 3; q++) {
                 // four consecutive samples 4m .. 4m+3 (m = lane + 32 q) land at n = 30 + 4m + j: residue (2 + j) & 3, slot
@@ -211,7 +184,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
                 sm.x[1][8 + mq] = v.w;
             }
         }
-        if (t + 1 < t1) { FE_GATE(t + 1); prefetch(t + 1, buf ^ 1); }
+        if (t + 1 < t1) prefetch(t + 1, buf ^ 1);
         __syncwarp();
 
         PHASE(0);

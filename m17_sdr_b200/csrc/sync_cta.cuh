@@ -29,8 +29,7 @@ __global__ void __launch_bounds__(NW * 32) k_sync_frame_cta(const float *__restr
                                                             float *syms, int64_t sym_pitch, int32_t *__restrict__ nsym, int32_t *__restrict__ sym_base,
                                                             m17b_frame_rec *frames, int64_t fcap, int32_t *__restrict__ nframes,
                                                             m17b_event_rec *events, int64_t ecap, int32_t *__restrict__ nevents,
-                                                            unsigned long long *stats, int commit_fe,
-        const int * /*fe_done*/, int /*fe_slice*/, int * /*fe_err*/) {
+                                                            unsigned long long *stats, int commit_fe) {
     constexpr int NT = NW * 32;
     constexpr int NQ = (384 + NT - 1) / NT;                       // samples staged per thread and block
     __shared__ SyncCtaSmem sm;

@@ -146,14 +146,13 @@ __device__ __forceinline__ void sync_round(unsigned gmask, int gl, int gshift, c
 // TAPS_SMEM: the 31 tap pairs are read from shared memory (broadcast) instead of living in 62 registers: ~110 registers instead
 // of ~170, i.e. 16 instead of 8 resident warps per SM.  No help while every channel is resident anyway (<= 1184 channels per
 // GPU: the chain's latency rules), but above that the kernel runs in waves and twice the warps hide twice the latency.
-template <bool HAS_MEAN, int G, bool TAPS_SMEM = false, bool OVL = false>
+template <bool HAS_MEAN, int G, bool TAPS_SMEM = false>
 __global__ void __launch_bounds__(SY_WARPS * 32, TAPS_SMEM ? 4 : 2) k_sync_frame_g(const float *__restrict__ disc, const float *__restrict__ mean, int64_t nchan, int64_t T,
                                                                    int t0, int t1, int2 *frame_rng, RxChanState *st, const float *__restrict__ g_mf,
                                                                    const float *__restrict__ g_md, float *syms, int64_t sym_pitch,
                                                                    int32_t *__restrict__ nsym, int32_t *__restrict__ sym_base, m17b_frame_rec *frames,
                                                                    int64_t fcap, int32_t *__restrict__ nframes, m17b_event_rec *events, int64_t ecap,
-                                                                   int32_t *__restrict__ nevents, unsigned long long *stats, int commit_fe,
-                                                                   const int *fe_done, int fe_slice, int *fe_err) {
+                                                                   int32_t *__restrict__ nevents, unsigned long long *stats, int commit_fe) {
     constexpr int CPW = 32 / G;                                    // channels per warp
     constexpr int NSL_LOCKED = (G == 32) ? 6 : 12;                 // symbols per lane and round while locked
     extern __shared__ __align__(16) unsigned char sg_smem_raw[];
@@ -201,7 +200,6 @@ __global__ void __launch_bounds__(SY_WARPS * 32, TAPS_SMEM ? 4 : 2) k_sync_frame
     __syncwarp(gmask);
     // The block's samples are fetched one block ahead with cp.async straight into shared memory: completion is tracked by
     // the async-copy group, not by a register scoreboard, so nothing in the timing loop ever waits on the DRAM latency.
-    float pmu_pf = 0.0f;
     auto prefetch = [&](int64_t tt, int buf) {
         const float *src = disc + (c * T + tt) * 384;
 #pragma unroll
@@ -209,21 +207,12 @@ __global__ void __launch_bounds__(SY_WARPS * 32, TAPS_SMEM ? 4 : 2) k_sync_frame
             const unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.pre[buf][gl + G * q]);
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src + gl + G * q));
         }
-        if (HAS_MEAN) {
-            if (OVL && fe_done) {
-                // beside a running front end the block mean is read from L2 into a register: eight means share a 32-byte
-                // sector that the front end is still writing, so an L1-cached copy could be stale
-                pmu_pf = __ldcg(mean + c * T + tt);
-            } else if (gl == 0) {
-                const unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.pre[buf][384]);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(mean + c * T + tt));
-            }
+        if (HAS_MEAN && gl == 0) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.pre[buf][384]);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(mean + c * T + tt));
         }
         asm volatile("cp.async.commit_group;");
     };
-    unsigned long long *ovl_tm = (OVL && fe_done) ? (unsigned long long *)(fe_done + 1000) : nullptr;   // instrumentation: first start / last end
-    if (OVL && ovl_tm && gl == 0) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); atomicMin(ovl_tm + 2, now); }
-    if (G == 32 && OVL) FE_GATE(t0);
     prefetch(t0, 0);
 
     for (int64_t t = t0; t < t1; t++) {
@@ -232,7 +221,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32, TAPS_SMEM ? 4 : 2) k_sync_frame
         asm volatile("cp.async.wait_group 0;");
         __syncwarp(wmask);
         {
-            const float pmu = !HAS_MEAN ? 0.0f : (OVL && fe_done) ? pmu_pf : sm.pre[buf][384];
+            const float pmu = !HAS_MEAN ? 0.0f : sm.pre[buf][384];
 #pragma unroll
             for (int q = 0; q < 384 / G; q++) {
                 float v = sm.pre[buf][gl + G * q];
@@ -241,7 +230,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32, TAPS_SMEM ? 4 : 2) k_sync_frame
                 sm.x[n & 3][n >> 2] = v;
             }
         }
-        if (t + 1 < t1) { if (G == 32 && OVL) FE_GATE(t + 1); prefetch(t + 1, buf ^ 1); }
+        if (t + 1 < t1) prefetch(t + 1, buf ^ 1);
         __syncwarp(gmask);
 
         // ---- timing loop (m17_rx_sync.cpp:77-99); m17_rx_lock() is constant inside a block
@@ -377,6 +366,5 @@ __global__ void __launch_bounds__(SY_WARPS * 32, TAPS_SMEM ? 4 : 2) k_sync_frame
         unsigned long long *q = stats + c * 8;
         q[0] += (unsigned long long)(nfr - nfr_entry); q[4] += (unsigned long long)n_aos; q[5] += (unsigned long long)n_los;
         q[7] += (unsigned long long)(sym_total - sym_entry);
-        if (OVL && ovl_tm) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); atomicMax(ovl_tm + 3, now); }
     }
 }

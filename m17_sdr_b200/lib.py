@@ -46,7 +46,9 @@ _SIGS = {
     "m17b_rx_create": ([_vp, _i64, _i64, C.POINTER(_vp)], _i32),
     "m17b_rx_destroy": ([_vp], _i32),
     "m17b_rx_reset": ([_vp, _vp], _i32),
-    "m17b_rx_set_afc": ([_vp, _i32], _i32),
+    "m17b_rx_framer_reset": ([_vp, _vp], _i32),
+    "m17b_rx_set_afc": ([_vp, _i32, _vp], _i32),
+    "m17b_rx_get_overflow": ([_vp, C.POINTER(_i32)], _i32),
     "m17b_rx_set_bert": ([_vp, _i32], _i32),
     "m17b_rx_get_bert": ([_vp, _vp, _vp], _i32),
     "m17b_dsp_rx": ([_vp, _vp, _i64, _vp], _i32),
@@ -59,8 +61,6 @@ _SIGS = {
     "m17b_rx_debug_sync": ([_vp, _vp, _vp], _i32),
     "m17b_rx_set_slice_blocks": ([_vp, _i32], _i32),
     "m17b_rx_set_chan_groups": ([_vp, _i32], _i32),
-    "m17b_rx_debug_overlap": ([_vp, _vp], _i32),
-    "m17b_rx_set_overlap": ([_vp, _i32, _i32], _i32),
     "m17b_rx_set_timing": ([_vp, _i32], _i32),
     "m17b_rx_stage_ms": ([_vp, _i64, _vp], _i32),
     "m17b_selftest_frontend": ([_vp, _u64, _u64, C.POINTER(_u64), _vp, _i32, _vp], _i32),

@@ -202,6 +202,22 @@ void m17o_derand_bytes(uint8_t *io, int len) { for (int i = 0; i < len; i++) io[
 void m17o_derand_bits(const uint8_t *in, uint8_t *out, int len) { for (int i = 0; i < len; i++) out[i] = (in[i] ^ t_rand[i % 368]) & 1; }
 void m17o_derand_soft(const float *in, float *out, int len) { for (int i = 0; i < len; i++) out[i] = t_rand[i % 368] ? -in[i] : in[i]; }
 
+/* m17_dsp_demap_symbol (m17_dsp.cpp:35-42): one symbol with the caller's normaliser */
+void m17o_demap_symbol(float in, float mag, float *out) {
+    float m = in * mag;
+    out[0] = -m;
+    out[1] = (float)(fabs(m) - 0.6666);
+}
+/* m17_dsp_decimating_filter (m17_dsp.cpp:438-449): sum starts at 0 and every product is added in tap order */
+int m17o_decimating_filter(const float *in, float *out, const float *coffs, int stride, int flen, int len) {
+    int idx = 0;
+    for (int i = 0; i < len; i += stride) {
+        float sum = 0;
+        for (int j = 0; j < flen; j++) sum += in[i + j] * coffs[j];
+        out[idx++] = sum;
+    }
+    return idx;
+}
 void m17o_demap_frame(const float *s, float *out) {
     /* m17_dsp.cpp:82-95 and :35-42.  cor is a double quotient rounded to float; the LSB soft value is a
        double subtraction (0.6666 is a double literal) rounded to float.  Positive means bit 1. */

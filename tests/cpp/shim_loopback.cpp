@@ -5,6 +5,7 @@
 #define M17GISMO_B200_IMPLEMENTATION
 #include "m17gismo_b200.hpp"
 #include <stdio.h>
+#include <string.h>
 #include <vector>
 
 static std::vector<scmplx> g_iq;
@@ -66,6 +67,14 @@ int main() {
     m17_prbs9_tx_reset();
     eq_open(); eq_restart(); eq_reset();
     EXPECT(m17b_shim_last_error() == 0);
+    // host-side helpers of m17_bit_utils.cpp:191-254
+    char call[10];
+    EXPECT(m17_encode_call("G4GUO    ") == 0x0000025EA29Full);               // the source address used below
+    EXPECT(!strcmp(m17_decode_call(m17_encode_call("AB1CD/P-."), call), "AB1CD/P-."));
+    EXPECT(!strcmp(m17_decode_call(0xFFFFFFFFFFFFull, call), "BROADCAST"));
+    M17Type t0 = {1, 2, 1, 3, 9, 17};
+    M17Type t1 = m17_upack_type(m17_pack_type(t0));
+    EXPECT(t1.p_s == 1 && t1.dt == 2 && t1.et == 1 && t1.est == 3 && t1.can == 9 && t1.reserved == 17);
 
     // ---- one over, looped back
     const int F = 14;
@@ -90,6 +99,25 @@ int main() {
     }
     EXPECT(g_aos == 1 && g_los == 1 && !m17_rx_lock());
     EXPECT(lsf_ok == 1 && stream == F && delivered >= F - 6 && exact == delivered);
+    // ---- m17_rx_lost() only clears the sync window and the lock flag (m17_rx_frame.cpp:179-186); m17_rx_symbols / m17_rx_sym on
+    //      symbols that did not come from m17_rx_sync_samples run the stand-alone framer: feed the over's own symbol stream again
+    {
+        std::vector<float> sy;
+        std::vector<float> disc(384), outsym(400);
+        size_t nf0 = g_frames.size(); int aos0 = g_aos;
+        // a clean stream sync word + payload at the symbol seam: 0xFF5D = +3 +3 +3 +3 -3 -3 +3 -3, then 184 symbols
+        const float sw[8] = {1, 1, 1, 1, -1, -1, 1, -1};
+        for (int f = 0; f < 3; f++) { for (int k = 0; k < 8; k++) sy.push_back(sw[k]); for (int k = 0; k < 184; k++) sy.push_back(((k * 7 + f) & 1) ? 0.333f : -1.0f); }
+        m17_rx_lost();
+        EXPECT(!m17_rx_lock());
+        m17_rx_symbols(sy.data(), 192 + 100);                                // ragged pieces through the symbol seam
+        for (int k = 292; k < 300; k++) m17_rx_sym(sy[k]);
+        m17_rx_symbols(sy.data() + 300, (int)sy.size() - 300);
+        EXPECT(g_aos == aos0 + 1 && m17_rx_lock());
+        EXPECT(g_frames.size() == nf0 + 2 && g_frames[nf0].type == M17B_T_STREAM && g_frames[nf0 + 1].type == M17B_T_STREAM);   // two completed frames, the third still open
+        m17_rx_lost();
+        EXPECT(m17b_shim_last_error() == 0);
+    }
     printf("{\"shim_loopback\": \"%s\", \"frames\": %zu, \"stream\": %d, \"delivered\": %d, \"exact\": %d, \"aos\": %d, \"los\": %d, \"err\": %d}\n",
            g_fail ? "FAIL" : "PASS", g_frames.size(), stream, delivered, exact, g_aos, g_los, m17b_shim_last_error());
     return g_fail || m17b_shim_last_error() ? 1 : 0;

@@ -48,6 +48,12 @@ def main():
     L.refp_init(); L.refp_check(_p(bits), C.c_long(len(bits)))
     st = np.zeros(6, np.uint32); L.refp_state(_p(st))
     g["prbs_bits"], g["prbs_state"] = bits, st
+    # ---- m17_dsp_demap_symbol / m17_dsp_decimating_filter (m17_dsp.cpp:35-42,438-449)
+    sy = rng.normal(0, 1, 500).astype(np.float32); mg = rng.uniform(0.2, 4, 500).astype(np.float32)
+    g["dsym_in"], g["dsym_mag"], g["dsym_out"] = sy, mg, R.demap_symbol(sy, mg)
+    x = rng.normal(0, 1, (3, 230)).astype(np.float32); cf = rng.normal(0, 0.2, 31).astype(np.float32)
+    g["dfil_in"], g["dfil_coffs"] = x, cf
+    g["dfil_out"] = np.stack([R.decimating_filter(r, cf, 5, 200) for r in x])
     out = os.path.join(HERE, "m17_golden_ext.npz")
     np.savez_compressed(out, **g)
     print(out, os.path.getsize(out), "bytes; afc frames", o.counts[:, 2])

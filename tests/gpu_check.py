@@ -90,20 +90,16 @@ def check_primitives(ctx, P, seed=11, n=64):
     assert np.array_equal(ty.cpu().numpy(), np.array([e[0] for e in exp], np.uint8)), "sync type"
     assert np.array_equal(vo.cpu().numpy(), np.array([e[1] for e in exp], np.uint8)), "sync votes"
     assert bits_eq(va.cpu().numpy(), np.array([e[2] for e in exp], np.float32)), "sync variance"
-    # m17_dsp_demap_symbol, m17_dsp_decimating_filter (numpy restatements of m17_dsp.cpp:35-42,438-449), m17_prbs9_rx_check
+    # m17_dsp_demap_symbol, m17_dsp_decimating_filter (m17_dsp.cpp:35-42,438-449): oracle on random inputs, and the reference's
+    # own outputs from the fixture
     sy1 = rng.normal(0, 1, 500).astype(np.float32); mg = rng.uniform(0.2, 4, 500).astype(np.float32)
-    mm = sy1 * mg
-    exp = np.stack([-mm, (np.abs(mm).astype(np.float64) - 0.6666).astype(np.float32)], 1)
-    assert bits_eq(ctx.m17_dsp_demap_symbol(dev(sy1), dev(mg)).cpu().numpy(), exp), "demap symbol"
+    assert bits_eq(ctx.m17_dsp_demap_symbol(dev(sy1), dev(mg)).cpu().numpy(), P.demap_symbol(sy1, mg)), "demap symbol"
     xin = rng.normal(0, 1, (3, 200 + 30)).astype(np.float32); cf = rng.normal(0, 0.2, 31).astype(np.float32)
-    exp = np.zeros((3, 40), np.float32)
-    for r in range(3):
-        for k in range(40):
-            acc = np.float32(0)
-            for j in range(31):
-                acc = np.float32(acc + np.float32(xin[r, 5 * k + j] * cf[j]))
-            exp[r, k] = acc
+    exp = np.stack([P.decimating_filter(r, cf, 5, 200) for r in xin])
     assert bits_eq(ctx.m17_dsp_decimating_filter(dev(xin), dev(cf), 5, 200).cpu().numpy(), exp), "decimating filter"
+    GX = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "m17_golden_ext.npz"))
+    assert bits_eq(ctx.m17_dsp_demap_symbol(dev(GX["dsym_in"]), dev(GX["dsym_mag"])).cpu().numpy(), GX["dsym_out"]), "demap symbol (reference fixture)"
+    assert bits_eq(ctx.m17_dsp_decimating_filter(dev(GX["dfil_in"]), dev(GX["dfil_coffs"]), 5, 200).cpu().numpy(), GX["dfil_out"]), "decimating filter (reference fixture)"
     seq3 = np.tile(P.prbs9(), 3)
     pb = np.stack([seq3[:900], np.roll(seq3, 5)[:900], rng.integers(0, 2, 900).astype(np.uint8)]).astype(np.uint8)
     pb[0, [300, 301, 640]] ^= 1

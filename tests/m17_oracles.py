@@ -220,6 +220,23 @@ class Port:
         self.L.m17o_demap_frame(_p(a), _p(out))
         return out
 
+    def demap_symbol(self, sym, mag):
+        """m17_dsp_demap_symbol for arrays of symbols / normalisers -> [n][2]"""
+        sym = np.ascontiguousarray(sym, np.float32); mag = np.ascontiguousarray(mag, np.float32)
+        out = np.zeros((len(sym), 2), np.float32)
+        self.L.m17o_demap_symbol.argtypes = [C.c_float, C.c_float, C.c_void_p]
+        for i in range(len(sym)):
+            self.L.m17o_demap_symbol(float(sym[i]), float(mag[i]), out[i].ctypes.data_as(C.c_void_p))
+        return out
+
+    def decimating_filter(self, x, coffs, stride, length):
+        """m17_dsp_decimating_filter over one row x (>= length + len(coffs) - 1 samples)"""
+        x = np.ascontiguousarray(x, np.float32); cf = np.ascontiguousarray(coffs, np.float32)
+        out = np.zeros((length + stride - 1) // stride, np.float32)
+        n = self.L.m17o_decimating_filter(_p(x), _p(out), _p(cf), stride, len(cf), length)
+        assert n == len(out)
+        return out
+
     def hard24(self, soft24):
         a = np.ascontiguousarray(soft24, np.float32)
         return self.L.m17o_hard24(_p(a))
@@ -513,6 +530,21 @@ class Ref:
         a = np.array(sym192, np.float32)
         out = np.zeros(368, np.float32)
         self.L.ref_demap_frame(_p(a), _p(out))
+        return out
+
+    def demap_symbol(self, sym, mag):
+        sym = np.ascontiguousarray(sym, np.float32); mag = np.ascontiguousarray(mag, np.float32)
+        out = np.zeros((len(sym), 2), np.float32)
+        self.L.ref_demap_symbol.argtypes = [C.c_float, C.c_float, C.c_void_p]
+        for i in range(len(sym)):
+            self.L.ref_demap_symbol(float(sym[i]), float(mag[i]), out[i].ctypes.data_as(C.c_void_p))
+        return out
+
+    def decimating_filter(self, x, coffs, stride, length):
+        x = np.array(x, np.float32); cf = np.array(coffs, np.float32)
+        out = np.zeros((length + stride - 1) // stride, np.float32)
+        n = self.L.ref_decimating_filter(_p(x), _p(out), _p(cf), stride, len(cf), length)
+        assert n == len(out)
         return out
 
     def hard24(self, soft24):

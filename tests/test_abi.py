@@ -74,3 +74,30 @@ def test_record_layout_matches_oracle():
     assert PROD == REC_DTYPE and PROD.itemsize == 64
     assert [PROD.fields[n][1] for n in ("sym_off", "type", "flags", "golay_err", "nbytes", "lich", "data", "crc", "votes", "frame_errors", "variance", "cor")] == \
         [0, 4, 5, 6, 7, 8, 14, 44, 46, 47, 48, 52]
+
+
+def test_shim_host_helpers_match_the_reference(L):
+    """m17_encode_call / m17_decode_call / m17_pack_type / m17_upack_type of the C++ shim (host code, no GPU) against the
+    oracle restatement and -- where oracle/_ref exists -- the reference's own m17_bit_utils.cpp."""
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from m17_oracles import Port, Ref
+    subprocess.run(["bash", os.path.join(ROOT, "tests", "cpp", "build.sh")], check=True)
+    rng = np.random.default_rng(5)
+    alphabet = " ABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789-/."
+    calls = ["G4GUO    ", "AB1CD/P-.", "         ", "M17-M17 C"] + ["".join(alphabet[i] for i in rng.integers(0, 40, 9)) for _ in range(200)]
+    words = [int(w) for w in rng.integers(0, 40 ** 9, 200)] + [0xFFFFFFFFFFFF, 0]
+    types = [int(w) for w in rng.integers(0, 1 << 16, 100)] + [0x0005, 0x0002, 0xFFFF]
+    req = "".join(f"E {c}\n" for c in calls) + "".join(f"D {w:x}\n" for w in words) + "".join(f"T {t:x}\n" for t in types)
+    out = subprocess.run([os.path.join(ROOT, "tests", "cpp", "bin", "shim_host_helpers")], input=req, capture_output=True, text=True, check=True).stdout.split("\n")
+    P = Port()
+    refs = [P] + ([Ref()] if Ref.available() else [])
+    for R in refs:
+        for i, c in enumerate(calls):
+            assert int(out[i], 16) == R.encode_call(c), (c, out[i])
+        for i, w in enumerate(words):
+            assert out[len(calls) + i] == "[" + R.decode_call(w) + "]", (hex(w), out[len(calls) + i])
+    for i, t in enumerate(types):
+        f = out[len(calls) + len(words) + i].split()
+        assert [int(x) for x in f[:6]] == [t & 1, (t >> 1) & 3, (t >> 3) & 3, (t >> 5) & 3, (t >> 7) & 15, (t >> 11) & 31] and int(f[6], 16) == t

@@ -179,24 +179,14 @@ def test_udp_frames(ctx, port):
     print(gc.check_udp_frames(ctx, port))
 
 
-@pytest.mark.parametrize("impl", [2, 4, 8, 16, 32, 33, 64, 65])
+@pytest.mark.parametrize("impl", [0, 2, 4, 33])
 def test_sync_kernel_variants(ctx, port, impl, monkeypatch):
-    """Every timing-loop / framer kernel variant (CTA per channel, G lanes per channel, taps in shared memory, producer /
-    consumer warp pair) is bit-exact against the oracle on the IQ chain with split calls and on the packet-mode set."""
+    """Every timing-loop / framer kernel the library can select (warp per channel, CTA of 2 / 4 warps per channel, warp per
+    channel with the taps in shared memory) is bit-exact against the oracle on the IQ chain with split calls and on the
+    packet-mode set."""
     monkeypatch.setenv("M17B_SYNC_IMPL", str(impl))
     gc.check_rx_chain(ctx, port, nchan=6, seed=23, split=[1, 7, 2, 1, 13])
     gc.check_rx_packet(ctx, port)
-
-
-def test_frontend_tma_variant(ctx, port, monkeypatch):
-    """The TMA-staged front end (cp.async.bulk ring + mbarriers) produces the same bits as the default kernel.
-    (The selector is read once per process, so this runs the variant in a child process.)"""
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, M17B_FE_IMPL="1")
-    out = subprocess.run([sys.executable, os.path.join(root, "tests", "gpu_check.py"), "rx_chain", "rx_chain_split"], capture_output=True, text=True, env=env)
-    assert out.returncode == 0 and "FAILS 0" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
 def test_rx_symbol_seam(ctx, port):
@@ -266,15 +256,6 @@ def test_full_size_properties(ctx):
         assert np.array_equal(a["frames"].view(np.uint8), b["frames"].view(np.uint8)) and np.array_equal(a["nsym"], b["nsym"]), G
         assert np.array_equal(a["stats"], b["stats"]) and np.array_equal(a["events"], b["events"]) and gc.bits_eq(a["syms"], b["syms"]), G
     rx.set_chan_groups(-1)
-    # overlapped mode (front end and timing loop as co-resident kernels coupled by per-slice counters): same bytes
-    for sl in (10, 7, 125):
-        rx.set_overlap(True, sl)
-        rx.reset()
-        rx.m17_dsp_rx(iq)
-        b = rx.results()
-        assert np.array_equal(a["frames"].view(np.uint8), b["frames"].view(np.uint8)) and np.array_equal(a["nsym"], b["nsym"]), sl
-        assert np.array_equal(a["stats"], b["stats"]) and np.array_equal(a["events"], b["events"]) and gc.bits_eq(a["syms"], b["syms"]), sl
-    rx.set_overlap(False)
     rx.reset()
     parts = [25] * 10
     nf = np.zeros(C, np.int64)

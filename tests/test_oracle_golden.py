@@ -189,3 +189,7 @@ def test_golden_ext(port):
         ok, sid, lsf, fn, pld = port.net_parse(E["udp_frames"][i])
         assert ok and sid == E["udp_sid"][i] and fn == E["udp_fn"][i] and np.array_equal(pld, E["udp_pld"][i]) and np.array_equal(lsf, E["udp_lich"][i])
     assert np.array_equal(port.prbs_check(E["prbs_bits"])[:6], E["prbs_state"])
+    # m17_dsp_demap_symbol / m17_dsp_decimating_filter outputs of the reference itself
+    assert np.array_equal(port.demap_symbol(E["dsym_in"], E["dsym_mag"]).view(np.uint32), E["dsym_out"].view(np.uint32))
+    got = np.stack([port.decimating_filter(r, E["dfil_coffs"], 5, 200) for r in E["dfil_in"]])
+    assert np.array_equal(got.view(np.uint32), E["dfil_out"].view(np.uint32))

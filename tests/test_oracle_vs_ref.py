@@ -31,6 +31,13 @@ def test_primitives_random(port, ref):
         assert a[:2] == b[:2] and feq(a[2], b[2])
     for args in ((0.5, 1240, 80), (0.5, 310, 10), (0.5, 62, 2), (0.5, 2480, 80), (0.35, 101, 4)):
         assert feq(port.rrc(*args), ref.rrc(*args))
+    # m17_dsp_demap_symbol, m17_dsp_decimating_filter (m17_dsp.cpp:35-42,438-449)
+    sy = rng.normal(0, 1, 4000).astype(np.float32); mg = rng.uniform(0.05, 6, 4000).astype(np.float32)
+    sy[:4] = [0.0, -0.0, 0.6666, -0.6666]
+    assert feq(port.demap_symbol(sy, mg), ref.demap_symbol(sy, mg))
+    for stride, flen, ln in ((5, 31, 200), (1, 7, 64), (8, 31, 512), (3, 2, 10)):
+        x = rng.normal(0, 1, ln + flen).astype(np.float32); cf = rng.normal(0, 0.3, flen).astype(np.float32)
+        assert feq(port.decimating_filter(x, cf, stride, ln), ref.decimating_filter(x, cf, stride, ln))
 
 
 def test_tx_iq_exact(port, ref):
