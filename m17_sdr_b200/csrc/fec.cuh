@@ -286,6 +286,18 @@ __device__ __forceinline__ SyncResult sync_check8(const float *v) {
     float var = (mx - mn) / mx;
     if (var != var) var = 1.0f;
     r.variance = var;
+    unsigned negm = 0, posm = 0;                                             // bit i: v[i] < 0 / v[i] > 0 (both clear for 0 and NaN)
+#pragma unroll
+    for (int i = 0; i < 8; i++) { negm |= (v[i] < 0) ? (1u << i) : 0u; posm |= (v[i] > 0) ? (1u << i) : 0u; }
+    // Fast path, exact: no zero / NaN element, the sign pattern IS template t's, and variance < 0.5 (every |v[i]| > 0.5 max|v|).
+    // Template t then correlates at sum|v| and any other template -- they differ from t in at least one position -- at sum|v|
+    // minus at least 2 * 0.5 max|v| >= sum|v| / 8, far beyond the rounding of eight adds: t wins the arg-max, with zero votes.
+    if ((negm ^ posm) == 0xFFu && var < 0.5f) {
+        int t = -1;
+#pragma unroll
+        for (int k = 0; k < 6; k++) if (negm == sync_neg_mask(k)) t = k;
+        if (t >= 0) { r.type = t; r.votes = 0; return r; }
+    }
     // six 8-term correlations, sequential adds; arg-max with strict '>' starting from (0, type 0)
     float best = 0;
     int type = 0;
@@ -298,9 +310,6 @@ __device__ __forceinline__ SyncResult sync_check8(const float *v) {
     r.type = type;
     // votes: vect[i]*sframe[type][i] < 0  <=>  v[i] < 0 where the template is +1, v[i] > 0 where it is -1
     const unsigned m = (unsigned)((0x400DF24FB0AAull >> (8 * type)) & 0xFFu);
-    unsigned negm = 0, posm = 0;                                             // bit i: v[i] < 0 / v[i] > 0 (both clear for 0 and NaN)
-#pragma unroll
-    for (int i = 0; i < 8; i++) { negm |= (v[i] < 0) ? (1u << i) : 0u; posm |= (v[i] > 0) ? (1u << i) : 0u; }
     r.votes = __popc((negm & ~m & 0xFFu) | (posm & m));
     return r;
 }

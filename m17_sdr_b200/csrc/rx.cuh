@@ -399,11 +399,12 @@ static int launch_sync(m17b_rx *rx, int64_t c0, int64_t nc, const float *disc, c
     // the GPU to itself: not inside a channel group).  Beyond one resident wave (8 channels per SM at 168 registers = 1184 on a
     // B200) the tap-pairs-in-shared-memory variant (108 registers, 16 warps per SM) is 15-23 % faster.
     const int impl = rx->sync_impl >= 0 ? rx->sync_impl : (nc <= 256 && !shared_gpu ? 4 : nc <= 8 * 148 ? 0 : 33);
+    const f32x2 one = 0x3F8000003F800000ull;                          // (1.0f, 1.0f), passed as data so that ptxas cannot contract the packed adds (sync.cuh, dot2)
     if (impl == 33) {
         const size_t smem = sizeof(SyncGroupSmem) * SY_WARPS;
         const unsigned g = grid_for(nc, SY_WARPS);
-        if (mean) k_sync_frame_g<true, 32, true><<<g, SY_WARPS * 32, smem, st>>>(SYNC_ARGS);
-        else      k_sync_frame_g<false, 32, true><<<g, SY_WARPS * 32, smem, st>>>(SYNC_ARGS);
+        if (mean) k_sync_frame_g<true, 32, true><<<g, SY_WARPS * 32, smem, st>>>(SYNC_ARGS, one);
+        else      k_sync_frame_g<false, 32, true><<<g, SY_WARPS * 32, smem, st>>>(SYNC_ARGS, one);
     } else if (impl == 4) {
         if (mean) k_sync_frame_cta<4, true><<<(unsigned)nc, 128, 0, st>>>(SYNC_ARGS);
         else      k_sync_frame_cta<4, false><<<(unsigned)nc, 128, 0, st>>>(SYNC_ARGS);
@@ -412,8 +413,8 @@ static int launch_sync(m17b_rx *rx, int64_t c0, int64_t nc, const float *disc, c
         else      k_sync_frame_cta<2, false><<<(unsigned)nc, 64, 0, st>>>(SYNC_ARGS);
     } else {
         const unsigned g = grid_for(nc, SY_WARPS);
-        if (mean) k_sync_frame<true><<<g, SY_WARPS * 32, 0, st>>>(SYNC_ARGS);
-        else      k_sync_frame<false><<<g, SY_WARPS * 32, 0, st>>>(SYNC_ARGS);
+        if (mean) k_sync_frame<true><<<g, SY_WARPS * 32, 0, st>>>(SYNC_ARGS, one);
+        else      k_sync_frame<false><<<g, SY_WARPS * 32, 0, st>>>(SYNC_ARGS, one);
     }
 #undef SYNC_ARGS
     KERNEL_CHECK();

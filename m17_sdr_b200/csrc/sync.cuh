@@ -57,43 +57,42 @@ __device__ __forceinline__ void sync_adjust(int TH, int &thr, int &index, int &c
 // Two consecutive symbols for one lane: windows xs[n0 .. n0+30] and xs[n0+2 .. n0+32], n0 = i + 4*lane.  R = i & 3 is
 // warp-uniform, so array / offset of every tap are compile-time and the 32 lanes read consecutive words.
 template <int R>
-__device__ __forceinline__ void dot2(const float (*X)[SY_XQ], int base, const f32x2 (&tp)[M17B_FN], float &sa, float &da, float &sb, float &db) {
+__device__ __forceinline__ void dot2(const float (*X)[SY_XQ], int base, const f32x2 (&tp)[M17B_FN], f32x2 one, float &sa, float &da, float &sb, float &db) {
     float x[M17B_FN + 2];
 #pragma unroll
     for (int k = 0; k < M17B_FN + 2; k++) x[k] = X[(R + k) & 3][base + ((R + k) >> 2)];
-    // tp[k] = (matched tap k, derivative tap k): one FMUL2 with the sample broadcast gives both rounded products; the running
-    // sums stay scalar adds in the reference's order (sum = in[0]*c[0]; sum += in[i]*c[i], m17_rx_sync.cpp:25-31)
-    unpack2(mul2(tp[0], pack2(x[0], x[0])), sa, da);
-    unpack2(mul2(tp[0], pack2(x[2], x[2])), sb, db);
+    // tp[k] = (matched tap k, derivative tap k): one FMUL2 with the sample broadcast gives both rounded products, and one
+    // FFMA2 (product * 1.0 + running pair) adds them to the two running sums -- each half rounds exactly like the reference's
+    // sum += in[i]*c[i] (m17_rx_sync.cpp:25-31).  `one` comes from memory: with a literal 1.0 ptxas folds the pair into a
+    // contracted FFMA2 (one rounding), -fmad=false notwithstanding.
+    f32x2 a = mul2(tp[0], pack2(x[0], x[0])), b = mul2(tp[0], pack2(x[2], x[2]));
 #pragma unroll
     for (int k = 1; k < M17B_FN; k++) {
-        float pa, qa, pb, qb;
-        unpack2(mul2(tp[k], pack2(x[k], x[k])), pa, qa);
-        unpack2(mul2(tp[k], pack2(x[k + 2], x[k + 2])), pb, qb);
-        sa += pa; da += qa;
-        sb += pb; db += qb;
+        a = fma2(mul2(tp[k], pack2(x[k], x[k])), one, a);
+        b = fma2(mul2(tp[k], pack2(x[k + 2], x[k + 2])), one, b);
     }
+    unpack2(a, sa, da);
+    unpack2(b, sb, db);
 }
 
 // Six consecutive symbols for one lane (a whole 40-ms block in one warp round): windows xs[n0 + 2m .. n0 + 2m + 30], m = 0..5,
 // n0 = i + 12*lane, so the lane loads 41 samples once.  With the residue-split layout consecutive lanes (stride 12 samples =
 // 3 words per residue array) read 32 different banks.
 template <int R>
-__device__ __forceinline__ void dot6(const float (*X)[SY_XQ], int base, const f32x2 (&tp)[M17B_FN], float (&s)[6], float (&d)[6]) {
+__device__ __forceinline__ void dot6(const float (*X)[SY_XQ], int base, const f32x2 (&tp)[M17B_FN], f32x2 one, float (&s)[6], float (&d)[6]) {
     float x[M17B_FN + 10];
 #pragma unroll
     for (int k = 0; k < M17B_FN + 10; k++) x[k] = X[(R + k) & 3][base + ((R + k) >> 2)];
+    f32x2 acc[6];
 #pragma unroll
-    for (int m = 0; m < 6; m++) unpack2(mul2(tp[0], pack2(x[2 * m], x[2 * m])), s[m], d[m]);
+    for (int m = 0; m < 6; m++) acc[m] = mul2(tp[0], pack2(x[2 * m], x[2 * m]));
 #pragma unroll
     for (int k = 1; k < M17B_FN; k++) {
 #pragma unroll
-        for (int m = 0; m < 6; m++) {
-            float p, q;
-            unpack2(mul2(tp[k], pack2(x[2 * m + k], x[2 * m + k])), p, q);
-            s[m] += p; d[m] += q;
-        }
+        for (int m = 0; m < 6; m++) acc[m] = fma2(mul2(tp[k], pack2(x[2 * m + k], x[2 * m + k])), one, acc[m]);
     }
+#pragma unroll
+    for (int m = 0; m < 6; m++) unpack2(acc[m], s[m], d[m]);
 }
 
 template <bool HAS_MEAN>
@@ -102,7 +101,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
                                                               float *syms, int64_t sym_pitch, int32_t *__restrict__ nsym, int32_t *__restrict__ sym_base,
                                                               m17b_frame_rec *frames, int64_t fcap, int32_t *__restrict__ nframes,
                                                               m17b_event_rec *events, int64_t ecap, int32_t *__restrict__ nevents,
-                                                              unsigned long long *stats, int commit_fe) {
+                                                              unsigned long long *stats, int commit_fe, f32x2 one) {
     __shared__ __align__(16) SyncWarpSmem sm_all[SY_WARPS];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t c = (int64_t)blockIdx.x * SY_WARPS + wid;
@@ -218,23 +217,38 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
                 // Locked, at the start of a block: the threshold is 80, so a trip inside the block is rare -- speculate the
                 // whole block in ONE round, six consecutive symbols per lane (192 symbols, all inside the block for i <= 1).
                 float s6[6], d6[6];
-                if (i == 0) dot6<0>(sm.x, 3 * lane, tp, s6, d6); else dot6<1>(sm.x, 3 * lane, tp, s6, d6);
-                int th6[6], run = 0;
+                if (i == 0) dot6<0>(sm.x, 3 * lane, tp, one, s6, d6); else dot6<1>(sm.x, 3 * lane, tp, one, s6, d6);
+                // votes (sync_update, m17_rx_sync.cpp:38-42): every symbol votes on the NEXT sample, so the only symbol of the
+                // block without a vote is the one at sample 383 (i == 1, lane 31, m == 5).  The common case needs no per-symbol
+                // threshold values: the lane keeps the running sum and its prefix extremes, the warp scan supplies the offset,
+                // and a trip exists iff some prefix leaves [-TH, TH].
+                int vt[6], run = 0, pmax = -8, pmin = 8;
 #pragma unroll
                 for (int m = 0; m < 6; m++) {
-                    const int j = i + 2 * (6 * lane + m);
-                    float dd = (s6[m] < 0) ? -d6[m] : d6[m];
-                    if (j + 1 < 384) run += (dd > 0) - (dd < 0);           // the vote happens on the next sample, if it is in this block
-                    th6[m] = run;
+                    const float dd = (s6[m] < 0) ? -d6[m] : d6[m];
+                    int v = (dd > 0) - (dd < 0);
+                    if (m == 5 && i == 1 && lane == 31) v = 0;
+                    vt[m] = v;
+                    run += v;
+                    pmax = max(pmax, run); pmin = min(pmin, run);
                 }
                 const int incl = warp_incl_scan(run, lane);
                 const int off = thr + incl - run;
                 int fm = 6;                                                    // first symbol of this lane whose vote trips
+                int th6[6];
+                if (__any_sync(0xffffffffu, off + pmax > TH || off + pmin < -TH)) {
+                    int r2 = off;
 #pragma unroll
-                for (int m = 5; m >= 0; m--) {
-                    th6[m] += off;
-                    const int j = i + 2 * (6 * lane + m);
-                    if ((j + 1 < 384) && (th6[m] > TH || th6[m] < -TH)) fm = m;
+                    for (int m = 0; m < 6; m++) { r2 += vt[m]; th6[m] = r2; }
+#pragma unroll
+                    for (int m = 5; m >= 0; m--) {
+                        const int j = i + 2 * (6 * lane + m);
+                        if ((j + 1 < 384) && (th6[m] > TH || th6[m] < -TH)) fm = m;
+                    }
+                } else {
+                    th6[5] = off + run;
+#pragma unroll
+                    for (int m = 0; m < 5; m++) th6[m] = 0;
                 }
                 const unsigned trip = __ballot_sync(0xffffffffu, fm < 6);
                 if (!trip) {
@@ -274,10 +288,10 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
             if (valid_a) {
                 const int base = (i >> 2) + lane;
                 switch (i & 3) {
-                    case 0: dot2<0>(sm.x, base, tp, sa, da, sb, db); break;
-                    case 1: dot2<1>(sm.x, base, tp, sa, da, sb, db); break;
-                    case 2: dot2<2>(sm.x, base, tp, sa, da, sb, db); break;
-                    default: dot2<3>(sm.x, base, tp, sa, da, sb, db); break;
+                    case 0: dot2<0>(sm.x, base, tp, one, sa, da, sb, db); break;
+                    case 1: dot2<1>(sm.x, base, tp, one, sa, da, sb, db); break;
+                    case 2: dot2<2>(sm.x, base, tp, one, sa, da, sb, db); break;
+                    default: dot2<3>(sm.x, base, tp, one, sa, da, sb, db); break;
                 }
             }
             // votes happen on the sample after each symbol (sync_update, m17_rx_sync.cpp:38-42) if it is in this block

@@ -34,23 +34,22 @@ __device__ __forceinline__ int group_incl_scan(unsigned gmask, int v, int gl) {
 
 // NSL consecutive symbols for one lane: windows xs[n0 + 2m .. n0 + 2m + 30], m = 0..NSL-1.  R = i & 3 is uniform in the group.
 template <int R, int NSL>
-__device__ __forceinline__ void dotn(const float (*X)[SG_XQ], int base, const f32x2 *tp, float (&s)[NSL], float (&d)[NSL]) {
+__device__ __forceinline__ void dotn(const float (*X)[SG_XQ], int base, const f32x2 *tp, f32x2 one, float (&s)[NSL], float (&d)[NSL]) {
     float x[M17B_FN + 2 * NSL - 2];
 #pragma unroll
     for (int k = 0; k < M17B_FN + 2 * NSL - 2; k++) x[k] = X[(R + k) & 3][base + ((R + k) >> 2)];
-    // tp[k] = (matched tap k, derivative tap k): one FMUL2 with the sample broadcast gives both rounded products; the running
-    // sums stay scalar adds in the reference's order (sum = in[0]*c[0]; sum += in[i]*c[i], m17_rx_sync.cpp:25-31)
+    // tp[k] = (matched tap k, derivative tap k): FMUL2 with the sample broadcast = both rounded products, FFMA2 (product * 1.0 +
+    // running pair) = both running sums, each half rounding as sum += in[i]*c[i] does (m17_rx_sync.cpp:25-31; see sync.cuh dot2)
+    f32x2 acc[NSL];
 #pragma unroll
-    for (int m = 0; m < NSL; m++) unpack2(mul2(tp[0], pack2(x[2 * m], x[2 * m])), s[m], d[m]);
+    for (int m = 0; m < NSL; m++) acc[m] = mul2(tp[0], pack2(x[2 * m], x[2 * m]));
 #pragma unroll
     for (int k = 1; k < M17B_FN; k++) {
 #pragma unroll
-        for (int m = 0; m < NSL; m++) {
-            float p, q;
-            unpack2(mul2(tp[k], pack2(x[2 * m + k], x[2 * m + k])), p, q);
-            s[m] += p; d[m] += q;
-        }
+        for (int m = 0; m < NSL; m++) acc[m] = fma2(mul2(tp[k], pack2(x[2 * m + k], x[2 * m + k])), one, acc[m]);
     }
+#pragma unroll
+    for (int m = 0; m < NSL; m++) unpack2(acc[m], s[m], d[m]);
 }
 
 // m17_sync_adjust (m17_rx_sync.cpp:45-72).  clk is the value m_clk has before the NEXT sample is processed.
@@ -70,7 +69,7 @@ __device__ __forceinline__ void sync_adjust_g(int TH, int &thr, int &index, int 
 // One speculation round: lane gl computes the NSL symbols at samples i + 2 (NSL gl + m); commits up to the first threshold
 // trip (or everything); updates the loop state.  All G lanes of the group call it together.
 template <int G, int NSL>
-__device__ __forceinline__ void sync_round(unsigned gmask, int gl, int gshift, const float (*X)[SG_XQ], float *out, const f32x2 *tp, int TH,
+__device__ __forceinline__ void sync_round(unsigned gmask, int gl, int gshift, const float (*X)[SG_XQ], float *out, const f32x2 *tp, f32x2 one, int TH,
                                            int &i, int &m_idx, int &thr, int &index, int &clk, float &sumc, float &difc) {
     float s[NSL], d[NSL];
     const int q0 = NSL * gl;                                       // first symbol of this lane within the round
@@ -81,10 +80,10 @@ __device__ __forceinline__ void sync_round(unsigned gmask, int gl, int gshift, c
         const int n0 = j0;                                         // window start in history coordinates (sample j sits at n = 30 + j)
         const int base = n0 >> 2;
         switch (n0 & 3) {
-            case 0: dotn<0, NSL>(X, base, tp, s, d); break;
-            case 1: dotn<1, NSL>(X, base, tp, s, d); break;
-            case 2: dotn<2, NSL>(X, base, tp, s, d); break;
-            default: dotn<3, NSL>(X, base, tp, s, d); break;
+            case 0: dotn<0, NSL>(X, base, tp, one, s, d); break;
+            case 1: dotn<1, NSL>(X, base, tp, one, s, d); break;
+            case 2: dotn<2, NSL>(X, base, tp, one, s, d); break;
+            default: dotn<3, NSL>(X, base, tp, one, s, d); break;
         }
     }
     // votes happen on the sample after each symbol (sync_update, m17_rx_sync.cpp:38-42) if it is in this block
@@ -152,7 +151,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32, TAPS_SMEM ? 4 : 2) k_sync_frame
                                                                    const float *__restrict__ g_md, float *syms, int64_t sym_pitch,
                                                                    int32_t *__restrict__ nsym, int32_t *__restrict__ sym_base, m17b_frame_rec *frames,
                                                                    int64_t fcap, int32_t *__restrict__ nframes, m17b_event_rec *events, int64_t ecap,
-                                                                   int32_t *__restrict__ nevents, unsigned long long *stats, int commit_fe) {
+                                                                   int32_t *__restrict__ nevents, unsigned long long *stats, int commit_fe, f32x2 one) {
     constexpr int CPW = 32 / G;                                    // channels per warp
     constexpr int NSL_LOCKED = (G == 32) ? 6 : 12;                 // symbols per lane and round while locked
     extern __shared__ __align__(16) unsigned char sg_smem_raw[];
@@ -257,8 +256,8 @@ __global__ void __launch_bounds__(SY_WARPS * 32, TAPS_SMEM ? 4 : 2) k_sync_frame
                 }
                 tap_index = index;
             }
-            if (flock) sync_round<G, NSL_LOCKED>(gmask, gl, gshift, sm.x, out, tp, TH, i, m_idx, thr, index, clk, sumc, difc);
-            else       sync_round<G, 2>(gmask, gl, gshift, sm.x, out, tp, TH, i, m_idx, thr, index, clk, sumc, difc);
+            if (flock) sync_round<G, NSL_LOCKED>(gmask, gl, gshift, sm.x, out, tp, one, TH, i, m_idx, thr, index, clk, sumc, difc);
+            else       sync_round<G, 2>(gmask, gl, gshift, sm.x, out, tp, one, TH, i, m_idx, thr, index, clk, sumc, difc);
         }
         const int n = m_idx < 0 ? 0 : m_idx;
         __syncwarp(wmask);
