@@ -255,7 +255,7 @@ extern "C" int m17b_demap_frame(m17b_ctx *ctx, const float *d_sym, int64_t n, fl
 }
 
 // ---------------------------------------------------------------- sync-word correlator (m17_rx_frame.cpp:22-81)
-struct SyncResult { int type, votes; float variance; };
+struct SyncResult { int type, votes; float variance; float spread, vmax; };   // spread = max|v| - min|v| (rounded), vmax = max|v|: variance = spread / vmax
 // sync templates as sign masks, bit i set = template[i] is -1 (m17_rx_frame.cpp:5-12): preamble, LSF 0x55F7, stream 0xFF5D,
 // packet 0x75FF, BERT 0xDF55, EOT 0x555D.  Compile-time so the six correlations are plain add/subtract chains.
 __host__ __device__ constexpr unsigned sync_neg_mask(int t) {
@@ -275,24 +275,32 @@ __device__ __forceinline__ bool sync_variance_lt(const float *v, double limit) {
     for (int i = 1; i < 8; i++) { float a = fabsf(v[i]); if (a > mx) mx = a; else if (a < mn) mn = a; }
     float var = (mx - mn) / mx;
     if (var != var) var = 1.0f;
-    return (double)var < limit;
+    // the callers compare (double)var with 0.3 / 0.5 (m17_rx_frame.cpp:82-103).  No float lies in [0.3 (double), 0.3f), and 0.5 is
+    // a float, so the comparison in float with the rounded limit decides identically
+    return var < (float)limit;
 }
+// variance < 0.5 (the locked limit) without waiting for the quotient: for floats d, m > 0 (m not subnormal), fl(d / m) < 0.5
+// <=> d < 0.5 m: any float d below 0.5 m is at least one ulp below it, so d / m <= 0.5 - 2^-25 and rounds below 0.5; d >= 0.5 m
+// gives a quotient >= 0.5.  m = 0 or NaN: the reference's variance is NaN -> 1.0 -> not below 0.5, and the comparison is false too.
+__device__ __forceinline__ bool sync_spread_lt_half(float d, float m) { return m >= 1e-30f ? d < 0.5f * m : (d / m) < 0.5f; }
+__device__ __forceinline__ float sync_variance_of(float d, float m) { float var = d / m; if (var != var) var = 1.0f; return var; }
+// DEFER_VAR: leave r.variance unset (the caller divides later, off the path that decides lock / loss)
+template <bool DEFER_VAR = false>
 __device__ __forceinline__ SyncResult sync_check8(const float *v) {
     SyncResult r;
     // find_variance: the 'else' means a sample that raises the max is never tested against the min
     float mn = fabsf(v[0]), mx = mn;
 #pragma unroll
     for (int i = 1; i < 8; i++) { float a = fabsf(v[i]); if (a > mx) mx = a; else if (a < mn) mn = a; }
-    float var = (mx - mn) / mx;
-    if (var != var) var = 1.0f;
-    r.variance = var;
+    r.spread = mx - mn; r.vmax = mx;
+    r.variance = DEFER_VAR ? 0.0f : sync_variance_of(r.spread, r.vmax);
     unsigned negm = 0, posm = 0;                                             // bit i: v[i] < 0 / v[i] > 0 (both clear for 0 and NaN)
 #pragma unroll
     for (int i = 0; i < 8; i++) { negm |= (v[i] < 0) ? (1u << i) : 0u; posm |= (v[i] > 0) ? (1u << i) : 0u; }
     // Fast path, exact: no zero / NaN element, the sign pattern IS template t's, and variance < 0.5 (every |v[i]| > 0.5 max|v|).
     // Template t then correlates at sum|v| and any other template -- they differ from t in at least one position -- at sum|v|
     // minus at least 2 * 0.5 max|v| >= sum|v| / 8, far beyond the rounding of eight adds: t wins the arg-max, with zero votes.
-    if ((negm ^ posm) == 0xFFu && var < 0.5f) {
+    if ((negm ^ posm) == 0xFFu && sync_spread_lt_half(r.spread, r.vmax)) {
         int t = -1;
 #pragma unroll
         for (int k = 0; k < 6; k++) if (negm == sync_neg_mask(k)) t = k;
@@ -317,7 +325,7 @@ __device__ __forceinline__ SyncResult sync_check8(const float *v) {
 __device__ __forceinline__ bool sync_accept(const SyncResult &r, bool locked) {
     if (r.votes > (locked ? 1 : 0)) return false;
     if (r.type < 1 || r.type > 4) return false;
-    return (double)r.variance < (locked ? 0.5 : 0.3);
+    return locked ? sync_spread_lt_half(r.spread, r.vmax) : r.variance < 0.3f;      // (double)variance < 0.5 / 0.3, see sync_variance_lt
 }
 // m17_unlocked_sync_check on one window, with an exact early-out.  Acceptance needs votes == 0, type in 1..4 and variance < 0.3.
 // variance < 0.3 means every |v[i]| >= 0.7 max|v| > 0, so no element is zero; votes == 0 then means the sign pattern of the

@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
             float w[8];
 #pragma unroll
             for (int k = 0; k < 8; k++) w[k] = (k < fclk) ? sm.head[k] : sm.hist[8 + k - fclk];      // m_f_sym[0..7]
-            const SyncResult r = sync_check8(w);
+            const SyncResult r = sync_check8<true>(w);                                 // (the quotient is only needed for the record)
             const bool ok = sync_accept(r, true);
             int flags = ok ? M17B_F_SYNC_OK : 0, fe;
             bool los = false;
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
                 if (lane == 0) word = (uint32_t)frame_start;
                 else if (lane == 1) word = (uint32_t)r.type | ((uint32_t)flags << 8);
                 else if (lane == 11) word = ((uint32_t)r.votes << 16) | ((uint32_t)fe << 24);
-                else if (lane == 12) word = __float_as_uint(r.variance);
+                else if (lane == 12) word = __float_as_uint(sync_variance_of(r.spread, r.vmax));
                 ((uint32_t *)(frames + c * fcap + nfr))[lane] = word;
             }
             nfr++;
