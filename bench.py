@@ -128,7 +128,7 @@ def bind_to_gpu_numa_node(torch, local):
 
 
 # ------------------------------------------------------------------------------------------------ workload
-def make_workload(ctx, m, torch, C, T, seed):
+def make_workload(ctx, m, torch, C, T, seed, ebn0=EBN0_SWEEP):
     """Synthetic stream-mode channels generated ON THE GPU with the library's own TX path (outside any timed
     region): LSF -> frame formatter -> RRC x10 -> 4FSK -> int16 IQ, then delay / carrier offset / AWGN."""
     dev = ctx.device
@@ -163,7 +163,7 @@ def make_workload(ctx, m, torch, C, T, seed):
         iq32[c0:c0 + 64] = torch.gather(iq32[c0:c0 + 64], 1, idx)
     del idx
     # carrier offset + AWGN
-    eb = np.array([EBN0_SWEEP[c % len(EBN0_SWEEP)] if EBN0_SWEEP[c % len(EBN0_SWEEP)] is not None else np.inf for c in range(C)])
+    eb = np.array([ebn0[c % len(ebn0)] if ebn0[c % len(ebn0)] is not None else np.inf for c in range(C)])
     sigma = np.where(np.isinf(eb), 0.0, np.sqrt(2.5 * 16383.0 ** 2 / 10 ** (eb / 10))).astype(np.float32)
     f0 = (torch.rand((C,), generator=g, device=dev) * 2000.0 - 1000.0) / 48000.0
     ctx.synth_channel(iq, torch.from_numpy(sigma).to(dev), f0.float().contiguous(), seed=seed)
@@ -254,6 +254,166 @@ def tx_record(ctx, m, torch, C, F, steps, with_cpu):
             rec["cpu_baseline"] = {"value": out["frames_per_s"], "unit": "frames/s", "cores": cores, "kind": "reference",
                                    "sample": f"m17_send_stream_frame x 20000 per process, one unmodified-reference process per core ({out['secs_max_worker']:.2f} s)"}
     return rec
+
+
+# ------------------------------------------------------------------------------------------------ aux: configs[2], [3], [4]
+def packet_record(ctx, m, torch, C, steps):
+    """BASELINE configs[2]: packet-mode batch.  Per channel: carrier, 2 preambles, LSF (TYPE 0x0002), one packet of 1..200 bytes
+    cut into 25-byte frames with its CRC (m17_send_packet_frames), EOT; modulated at 384 kS/s and decimated by 8 from a random
+    phase (fractional timing offset), random start delay, carrier offset +-1 kHz, AWGN at 26 / 28 / 30 dB / none.  The RX step
+    is timed; packets are reassembled on the GPU and compared with what was sent."""
+    dev = ctx.device
+    T, MF = 16, 10
+    g = torch.Generator(device=dev); g.manual_seed(333)
+    L = torch.randint(1, 201, (C,), generator=g, device=dev, dtype=torch.int32)
+    pk = torch.randint(0, 256, (C, 256), generator=g, device=dev, dtype=torch.int32).to(torch.uint8)
+    lsf = torch.zeros((C, 30), dtype=torch.uint8, device=dev)
+    lsf[:, 0:6] = 0xFF
+    lsf[:, 11] = 0x2A
+    lsf[:, 13] = 0x02                                                       # TYPE 0x0002: packet, data
+    crc = ctx.m17_crc_array_encode(lsf[:, :28].contiguous()).view(torch.int16).to(torch.int32) & 0xFFFF
+    lsf[:, 28] = ((crc >> 8) & 0xFF).to(torch.uint8); lsf[:, 29] = (crc & 0xFF).to(torch.uint8)
+    tx = m.Tx(ctx, C, 80)
+    dib, nf = tx.m17_send_packet_frames(pk, L, max_frames=MF)               # [C][MF][192], frames used per packet (<= 9)
+    eot = torch.from_numpy(tx.fmt_eot()).to(dev)
+    dib[torch.arange(C, device=dev), nf.long()] = eot                       # EOT directly behind the packet's last frame
+    pre = torch.from_numpy(tx.fmt_preamble()).to(dev).expand(C, 192)
+    car = torch.full((C, 192), 4, dtype=torch.uint8, device=dev)
+    script = torch.cat([car, pre, pre, tx.m17_fmt_add_link_setup_frame(lsf), dib.reshape(C, MF * 192), car, car], 1).contiguous()
+    assert script.shape[1] == T * 192
+    iq80 = tx.m17_mod_dibits(script).view(torch.int32).reshape(C, T * 192 * 80)
+    tx.close()
+    ph = torch.randint(0, 8, (C,), generator=g, device=dev, dtype=torch.int64)
+    delay = torch.randint(0, 1920, (C,), generator=g, device=dev, dtype=torch.int64)
+    n = torch.arange(T * 1920, device=dev, dtype=torch.int64)
+    iq = torch.empty((C, T * 1920), dtype=torch.int32, device=dev)
+    for c0 in range(0, C, 64):
+        idx = ((n[None, :] - delay[c0:c0 + 64, None]).clamp_(min=0)) * 8 + ph[c0:c0 + 64, None]
+        iq[c0:c0 + 64] = torch.gather(iq80[c0:c0 + 64], 1, idx)
+    del iq80, idx
+    iq = iq.view(torch.int16).reshape(C, T * 1920, 2)
+    eb = [26.0, 28.0, 30.0, None]
+    sigma = np.array([0.0 if eb[c % 4] is None else np.sqrt(2.5 * 16383.0 ** 2 / 10 ** (eb[c % 4] / 10)) for c in range(C)], np.float32)
+    f0 = (torch.rand((C,), generator=g, device=dev) * 2000.0 - 1000.0) / 48000.0
+    ctx.synth_channel(iq, torch.from_numpy(sigma).to(dev), f0.float().contiguous(), seed=334)
+    rx = m.Rx(ctx, C, T)
+    for _ in range(3):
+        rx.reset(); rx.m17_dsp_rx(iq)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        rx.reset(); rx.m17_dsp_rx(iq)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    by, pkt, npk = rx.reassemble_packets(bytes_cap=256, max_pkts=2)
+    stats = rx.view()["stats"].sum(0).cpu().numpy()
+    npk_h, pkt_h, by_h, L_h, pk_h = npk.cpu().numpy(), pkt.cpu().numpy(), by.cpu().numpy(), L.cpu().numpy(), pk.cpu().numpy()
+    good = sum(1 for c in range(C) if npk_h[c] >= 1 and pkt_h[c, 0, 2] == 1 and pkt_h[c, 0, 1] == L_h[c] and np.array_equal(by_h[c, :L_h[c]], pk_h[c, :L_h[c]]))
+    crc_ok = int(sum(int(pkt_h[c, k, 2]) for c in range(C) for k in range(min(int(npk_h[c]), 2))))
+    rx.close()
+    return {"workload": f"configs[2]: {C} packet-mode channels x {T} blocks (LSF + one packet of 1..200 bytes in 25-byte frames + EOT), fractional timing offset "
+                        f"(x8 oversampled TX decimated from a random phase), start delay, f0 +-1 kHz, AWGN on IQ Eb/N0 {{26,28,30,inf}} dB",
+            "ms_per_step": ms, "channel_frames_per_s": C * T / (ms * 1e-3), "channel_s_per_s": C * T / (ms * 1e-3) / 25.0,
+            "packets_sent": C, "packets_recovered_exact_with_valid_crc": int(good), "packets_with_valid_crc": crc_ok,
+            "frames": int(stats[0]), "aos": int(stats[4]), "los": int(stats[5]), "reassembly": "on the GPU (m17b_rx_reassemble_packets)"}
+
+
+def viterbi_record(ctx, m, torch, steps):
+    """BASELINE configs[3]: 1M punctured (P2, stream) K=5 r=1/2 soft-decision frames on the int8 grid at Eb/N0 3 dB:
+    depuncture + Viterbi + pack (m17b_viterbi_punctured), ACS throughput against the fp32 lane roof."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("viterbi_micro", os.path.join(ROOT, "benchmarks", "viterbi_micro.py"))
+    vm = importlib.util.module_from_spec(spec); spec.loader.exec_module(vm)
+    n = 1 << 20
+    data, soft = vm.make_frames(ctx, 2, n, 3.0)
+    for _ in range(3):
+        out = ctx.viterbi_punctured(2, soft)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = ctx.viterbi_punctured(2, soft)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    ber = float(np.unpackbits(torch.bitwise_xor(out, data).cpu().numpy()).mean())
+    ops = n * 148 * 52                                   # SURVEY 8d: 4 branch-metric adds + 16 x (2 add + 1 compare) per trellis step
+    return {"workload": "configs[3]: 1 048 576 punctured stream frames (272 soft values each, int8 grid), Eb/N0 3 dB", "ms_per_step": ms,
+            "frames_per_s": n / (ms * 1e-3), "acs_lane_ops_per_s": ops / (ms * 1e-3), "fp32_lane_roof": FP32_LANE_ROOF,
+            "frac_of_alu_roof": ops / (ms * 1e-3) / FP32_LANE_ROOF, "bytes_in_per_frame": 1088, "gbs_in": n * 1088 / (ms * 1e-3) / 1e9,
+            "bit_error_rate": ber}
+
+
+def config5_record(ctx, m, torch, dist, md, rank, world, steps, total=65536, T=25):
+    """BASELINE configs[4]: 65 536 channels sharded over the GPUs (contiguous ranges, dist.shard_range), 25 blocks (1 s) each,
+    Eb/N0(IQ) 26 dB, f0 +-1 kHz: 1024 distinct channels tiled x64 with per-copy sample delays.  Every step ends with the NCCL
+    gather of all decoded-frame records on rank 0 and the all-reduce of the counters.  Rank 0 re-runs a sample of every other
+    rank's channels itself and compares the gathered records byte for byte."""
+    dev = ctx.device
+    base_iq, _ = make_workload(ctx, m, torch, 1024, T, seed=4242, ebn0=(26.0,))
+    base = base_iq.view(torch.int32).reshape(1024, T * 1920)
+    n = torch.arange(T * 1920, device=dev, dtype=torch.int64)
+
+    def channels(gidx):                                   # IQ of the global channels in gidx (int64 tensor)
+        out = torch.empty((len(gidx), T * 1920), dtype=torch.int32, device=dev)
+        for a in range(0, len(gidx), 256):
+            gi = gidx[a:a + 256]
+            idx = (n[None, :] - ((gi // 1024) * 7)[:, None]).clamp_(min=0)
+            out[a:a + 256] = torch.gather(base[gi % 1024], 1, idx)
+        return out.view(torch.int16).reshape(len(gidx), T * 1920, 2)
+    c0, c1 = md.shard_range(total, rank, world)
+    iq = channels(torch.arange(c0, c1, device=dev, dtype=torch.int64))
+    rx = m.Rx(ctx, c1 - c0, T)
+    fr = nf = tot = None
+
+    def step():
+        rx.reset()
+        rx.m17_dsp_rx(iq)
+        v = rx.view()
+        return md.gather_records(v["frames"], v["nframes"], total, dst=0), md.reduce_stats(v["stats"])
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    chain_ms = 0.0
+    t_all0 = torch.cuda.Event(enable_timing=True); t_all0.record()
+    for _ in range(steps):
+        e0.record()
+        rx.reset(); rx.m17_dsp_rx(iq)
+        e1.record()
+        v = rx.view()
+        (fr, nf), tot = md.gather_records(v["frames"], v["nframes"], total, dst=0), md.reduce_stats(v["stats"])
+        e2.record()
+        torch.cuda.synchronize()
+        chain_ms += e0.elapsed_time(e1) / steps
+    t_all1 = torch.cuda.Event(enable_timing=True); t_all1.record()
+    torch.cuda.synchronize()
+    tm = torch.tensor([t_all0.elapsed_time(t_all1) / steps, chain_ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms, chain = float(tm[0]), float(tm[1])
+    same, checked = True, 0
+    if rank == 0:
+        for r in range(1, world):
+            a, b = md.shard_range(total, r, world)
+            gi = torch.linspace(a, b - 1, 32, device=dev).long()
+            rx2 = m.Rx(ctx, len(gi), T)
+            rx2.m17_dsp_rx(channels(gi))
+            v2 = rx2.view()
+            f2, n2 = v2["frames"].cpu().numpy(), v2["nframes"].cpu().numpy()
+            fg, ng = fr[gi].cpu().numpy(), nf[gi].cpu().numpy()
+            for k in range(len(gi)):
+                same = same and ng[k] == n2[k] and np.array_equal(fg[k, :ng[k]], f2[k, :n2[k]])
+                checked += 1
+            rx2.close()
+    cap = rx.frame_cap
+    rx.close()
+    del iq
+    return {"workload": f"configs[4]: {total} channels sharded x{world} ({c1 - c0} per GPU) x {T} blocks, Eb/N0(IQ) 26 dB, f0 +-1 kHz, 1024 distinct channels "
+                        f"tiled x{total // 1024} with per-copy sample delays; every step = RX chain + NCCL gather of all records to rank 0 + all-reduce of the counters",
+            "ms_per_step": ms, "ms_rx_chain_only": chain, "channel_s_per_s": total * T / (ms * 1e-3) / 25.0,
+            "gathered_bytes_per_step": int(total * cap * 64 + total * 4), "frames_total": int(tot[0]) if tot is not None else None,
+            "delivered_total": int(tot[3]) if tot is not None else None,
+            "gathered_records_equal_local_rerun": bool(same), "channels_rechecked_on_rank0": checked}
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
@@ -373,17 +533,37 @@ def run_cuda(args):
     iq, payload = make_workload(ctx, m, torch, C, T, seed=1000 + rank)
     log(f"[rank {rank}] workload {C} ch x {T} blocks generated in {time.time() - t0:.1f}s ({iq.numel() * 2 / 1e9:.2f} GB IQ)")
     rx = m.Rx(ctx, C, T)
-    stats_sum = torch.zeros(8, dtype=torch.int64, device=ctx.device)
+    # The only inter-GPU traffic of the step: an all-reduce of the 8 job-wide counters (NCCL over NVLink).  It is off the
+    # critical path: the step snapshots its counters (one tiny reduction on the step's stream), and a side stream hands the
+    # snapshot to NCCL while the next step's front end already runs; all reductions are complete before the timed region ends.
+    side = torch.cuda.Stream(device=ctx.device) if world > 1 else None
+    slots = torch.zeros((64, 8), dtype=torch.int64, device=ctx.device)
+    pending = []
+    stats_view = []
 
     def step():
         rx.reset()
         rx.m17_dsp_rx(iq)
-        if world > 1:                        # the only inter-GPU traffic: an all-reduce of the counters (NCCL over NVLink)
-            v = rx.view()["stats"].sum(0)
-            dist.all_reduce(v)
-            stats_sum.copy_(v)
+        if world > 1:
+            if not stats_view:
+                stats_view.append(rx.view()["stats"])            # (the library's counter buffer: its address does not change)
+            k = len(pending) % slots.shape[0]
+            torch.sum(stats_view[0], 0, out=slots[k])
+            ev = torch.cuda.Event()
+            ev.record()
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                pending.append(dist.all_reduce(slots[k], async_op=True))
+
+    def drain():
+        for w in pending:
+            w.wait()
+        pending.clear()
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
 
     def sync_all():
+        drain()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -405,6 +585,7 @@ def run_cuda(args):
     e0.record()
     for _ in range(args.steps):
         step()
+    drain()                                   # the counter reductions belong to the timed region
     e1.record()
     sync_all()
     w1 = time.time()
@@ -422,11 +603,12 @@ def run_cuda(args):
     nst = min(args.steps, 16)
     rx.set_timing(True)
     es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    step(); torch.cuda.synchronize()
+    step(); drain(); torch.cuda.synchronize()
     rx.set_timing(True)                      # restart the call counter after the warm-up step
     es0.record()
     for _ in range(nst):
         step()
+    drain()
     es1.record()
     torch.cuda.synchronize()
     ms_step_serial = es0.elapsed_time(es1) / nst
@@ -460,6 +642,17 @@ def run_cuda(args):
     # ---- the TX chain on the same batch shape (outside the RX step; rank 0 reports it)
     txrec = tx_record(ctx, m, torch, C, T, max(3, min(args.steps, 10)), with_cpu=(rank == 0 and not under_profiler()))
 
+    # ---- the other BASELINE configs, so that the driver times them too (rank 0; config 5 needs all ranks)
+    aux = {"tx": txrec}
+    if rank == 0 and not args.no_aux:
+        aux["packet"] = packet_record(ctx, m, torch, 1024, max(3, min(args.steps, 10)))
+        aux["viterbi"] = viterbi_record(ctx, m, torch, max(3, min(args.steps, 10)))
+    if world > 1 and not args.no_aux:
+        from m17_sdr_b200 import dist as md
+        sync_all()
+        aux["config5"] = config5_record(ctx, m, torch, dist, md, rank, world, max(2, min(args.steps, 5)))
+        sync_all()
+
     # ---- end-to-end through the C ABI with HOST buffers ("e2e")
     iq_host = torch.empty(iq.shape, dtype=torch.int16).pin_memory()
     iq_host.copy_(iq)
@@ -475,12 +668,32 @@ def run_cuda(args):
         rx.m17_dsp_rx_host(iq_host, fr_host, nf_host)      # H2D of the IQ, the chain, D2H of the records; returns synchronised
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-    te = torch.tensor([e2e_ms], device=ctx.device)
+    # what bounds it: the same bytes copied host -> device by every rank AT THE SAME TIME, nothing else running (pinned memory,
+    # one cudaMemcpyAsync per rank, 3 repetitions) -- the per-rank PCIe / host-memory rate when N ranks feed their GPUs at once
+    sync_all()
+    dev_buf = torch.empty_like(iq)
+    cp0, cp1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dev_buf.copy_(iq_host, non_blocking=True); torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_ms = float(te.item())
-    e2e_same = bool(np.array_equal(fr_host.numpy().view(m.REC_DTYPE).reshape(C, -1)[0, :nfr[0]], res["frames"][0, :nfr[0]]))
+    cp0.record()
+    for _ in range(3):
+        dev_buf.copy_(iq_host, non_blocking=True)
+    cp1.record()
+    torch.cuda.synchronize()
+    h2d_ms = cp0.elapsed_time(cp1) / 3
+    del dev_buf
+    per_rank = torch.tensor([e2e_ms, h2d_ms], device=ctx.device, dtype=torch.float64)
+    per_rank_all = [torch.zeros_like(per_rank) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(per_rank_all, per_rank)
+    else:
+        per_rank_all = [per_rank]
+    e2e_rank_ms = [round(float(x[0]), 3) for x in per_rank_all]
+    h2d_rank_gbs = [round(C * T * 7680 / (float(x[1]) * 1e-3) / 1e9, 2) for x in per_rank_all]
+    e2e_ms = max(e2e_rank_ms)
+    frh = fr_host.numpy().view(m.REC_DTYPE).reshape(C, -1)
+    e2e_same = bool(np.array_equal(nf_host.numpy(), nfr) and all(np.array_equal(frh[c, :nfr[c]], res["frames"][c, :nfr[c]]) for c in range(C)))
 
     if rank != 0:
         if world > 1:
@@ -525,7 +738,9 @@ def run_cuda(args):
                                f"AWGN on IQ Eb/N0 {{22,24,26,30,inf}} dB, f0 +-1 kHz, random start delay",
                    "channels_per_gpu": C, "blocks": T, "pipeline_slice_blocks": args.slice_blocks or 0, "channel_groups": "auto (4 independent channel-group chains on their own streams at 512..1184 channels)" if args.chan_groups is None else args.chan_groups, "l2": "input 1.97 GB per GPU >> 126 MB L2 (no flush needed)", "parallelism": f"channels sharded x{world}, no data-path collective", "host_numa_node_rank0": numa},
         "e2e": {"value": frames_step / (e2e_ms / 1e3) / 25.0, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(C * T * 7680),
-                "d2h_bytes_per_step": int(C * rx.frame_cap * 64 + 4 * C), "records_equal_device_path": e2e_same},
+                "d2h_bytes_per_step": int(C * rx.frame_cap * 64 + 4 * C), "records_equal_device_path": e2e_same,
+                "per_rank_ms": e2e_rank_ms, "h2d_copy_only_gbs_per_rank_all_ranks_at_once": h2d_rank_gbs,
+                "bound": "PCIe / host memory: compare per_rank_ms with the copy-only rate of the same bytes; every rank moves its own 1.97 GB per step"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": kname[dom],
@@ -537,7 +752,7 @@ def run_cuda(args):
                      "stages_measured": "stages strictly in sequence (no time slicing), CUDA events on the launching stream",
                      "ms_per_step_in_sequence": round(ms_step_serial, 4), "records_equal_pipelined": same_serial, "stages": stages},
         "cpu_baseline": cb,
-        "aux": {"tx": txrec},
+        "aux": aux,
         "check": {"delivered_payloads_exact": f"{ok}/{tot}", "frames": int(stats[0]), "stream_frames": int(stats[1]), "delivered": int(stats[3]),
                   "golay_errors": int(stats[2]), "aos": int(stats[4]), "los": int(stats[5])},
     }
@@ -556,6 +771,7 @@ def main():
     ap.add_argument("--channels", type=int, default=CHANNELS_PER_GPU)
     ap.add_argument("--blocks", type=int, default=BLOCKS)
     ap.add_argument("--chan-groups", type=int, default=None, help="independent channel-group chains per call (1 = one chain); default: library default (auto)")
+    ap.add_argument("--no-aux", action="store_true", help="skip the packet / Viterbi / config-5 records")
     ap.add_argument("--slice-blocks", type=int, default=None, help="blocks per pipeline slice (0 = stages in sequence); default: library default")
     args = ap.parse_args()
     # stdout carries exactly ONE line, the JSON result: everything else that writes to fd 1 (NCCL's version banner, library

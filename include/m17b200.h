@@ -288,6 +288,20 @@ int m17b_net_parse(m17b_ctx *ctx, const uint8_t *d_in, int64_t n, uint8_t *d_ok,
    d_out [nchan][frame_cap][54] (datagrams of a channel packed from slot 0 in record order), d_count [nchan] */
 int m17b_rx_net_frames(m17b_rx *rx, const uint16_t *d_sid, int have_dst, uint64_t dst, uint8_t *d_out, int32_t *d_count, void *stream);
 
+/* ------------------------------------------------------------------ application layer behind the frame decode */
+/* Packet reassembly as parse_packet (m17_rx_parse.cpp:34-51) is meant to work (the reference's own indexing cannot validate a
+   multi-frame packet; that behaviour is reproduced in the per-channel state for parity).  Walks the records of the
+   last m17b_dsp_rx / m17b_rx_baseband / m17b_rx_symbols call in order, per channel: 25 bytes of every non-final packet frame,
+   `count` bytes of the EOF frame, then the CRC-16 appended by m17_send_packet_frames (m17_tx_routines.cpp:323-353) is checked
+   over the whole packet.  A packet may span calls (the partial packet is carried; m17b_rx_reset clears it).
+   d_bytes [nchan][bytes_cap]: payloads (CRC stripped) back to back; d_pkt int32 [nchan][max_pkts][3] = {offset, length, crc_ok};
+   d_npkt [nchan].  Packets that do not fit bytes_cap / max_pkts are dropped. */
+int m17b_rx_reassemble_packets(m17b_rx *rx, uint8_t *d_bytes, int64_t bytes_cap, int32_t *d_pkt, int max_pkts, int32_t *d_npkt, void *stream);
+/* gps_decode (gps.cpp:8-27) on the META field of n link-setup frames (d_lsf: 30-byte LSFs `stride` bytes apart; the reference
+   reads 15 bytes from META, i.e. one byte into the CRC -- reproduced) */
+typedef struct { double lat, lon; int32_t alt, course, speed, object; } m17b_gps_rec;
+int m17b_gps_decode(m17b_ctx *ctx, const uint8_t *d_lsf, int64_t stride, int64_t n, m17b_gps_rec *d_out, void *stream);
+
 /* ------------------------------------------------------------------ equaliser (m17_equalize.cpp) */
 int m17b_eq_create(m17b_ctx *ctx, int64_t nchan, m17b_eq **out);   /* eq_open  :217-224 */
 int m17b_eq_destroy(m17b_eq *eq);

@@ -20,6 +20,7 @@ REC_DTYPE = np.dtype([
     ("variance", "<f4"), ("cor", "<f4"), ("rsvd", "u1", (8,)),
 ])
 EV_DTYPE = np.dtype([("sym_idx", "<i4"), ("kind", "<i4")])
+GPS_DTYPE = np.dtype([("lat", "<f8"), ("lon", "<f8"), ("alt", "<i4"), ("course", "<i4"), ("speed", "<i4"), ("object", "<i4")])
 BLOCK, DISC_PER_BLOCK, FRAME_SYMS = 1920, 384, 192
 STAT_NAMES = ("frames", "stream_frames", "golay_errors", "delivered", "aos", "los", "lsf_events", "symbols")
 
@@ -256,6 +257,14 @@ class Context:
         self.last_selftest_dump = dump.reshape(-1, 5)[: min(16, n.value)]
         return n.value
 
+    def gps_decode(self, lsf):
+        """gps_decode (gps.cpp:8-27) of the META field: lsf uint8 [n][>=30] -> numpy structured array (lat, lon, alt, course, speed, object)."""
+        _chk_dev(lsf, torch.uint8, "lsf")
+        n = lsf.shape[0]
+        out = torch.empty((n, 32), dtype=torch.uint8, device=lsf.device)
+        _l.check(self.L.m17b_gps_decode(self.h, _ptr(lsf), lsf.shape[1], n, _ptr(out), _stream()))
+        return out.cpu().numpy().view(GPS_DTYPE).reshape(n)
+
     def selftest_tx_wrap(self, first=0, count=1 << 32):
         n = C.c_uint64()
         dump = np.zeros(3 * 16, np.uint32)
@@ -348,6 +357,16 @@ class Rx:
             nframes_host = torch.empty((self.nchan,), dtype=torch.int32).pin_memory()
         _l.check(self.L.m17b_dsp_rx_host(self.h, _ptr(iq_host), nblocks, _ptr(frames_host), _ptr(nframes_host), _stream()))
         return frames_host, nframes_host
+
+    def reassemble_packets(self, bytes_cap=1024, max_pkts=8):
+        """Packets carried by the last call's packet frames, per channel (batched on the GPU; a packet may span calls).
+        Returns (bytes uint8 [nchan][bytes_cap], pkt int32 [nchan][max_pkts][3] = offset / length / crc_ok, npkt int32 [nchan])."""
+        dev = self.ctx.device
+        by = torch.empty((self.nchan, bytes_cap), dtype=torch.uint8, device=dev)
+        pk = torch.zeros((self.nchan, max_pkts, 3), dtype=torch.int32, device=dev)
+        npk = torch.empty((self.nchan,), dtype=torch.int32, device=dev)
+        _l.check(self.L.m17b_rx_reassemble_packets(self.h, _ptr(by), bytes_cap, _ptr(pk), max_pkts, _ptr(npk), _stream()))
+        return by, pk, npk
 
     def m17_net_new_rx_data(self, sid, dst=None):
         """Gateway output of the last call: every delivered stream frame as a 54-byte M17-over-UDP datagram.
@@ -568,28 +587,7 @@ class Equalizer:
         return out
 
 
-def reassemble_packets(ctx, frames, nframes):
-    """Packet-mode application layer done right (the reference's parse_packet cannot validate multi-frame packets,
-    SURVEY D4): walk one channel's records in order, concatenate the 25-byte chunks of non-final packet frames and the
-    `count` bytes of the EOF frame, and check the trailing CRC-16 with the GPU primitive.
-    frames: numpy structured array [cap] of one channel, nframes: its record count.
-    Returns a list of (payload_bytes_without_crc, crc_ok)."""
-    out, cur, done = [], b"", []
-    for r in frames[:nframes]:
-        if r["type"] != 3 or not (r["flags"] & 0x02):
-            continue
-        meta = int(r["data"][25])
-        if meta & 0x80:
-            cur += bytes(r["data"][: (meta >> 2) & 0x1F])
-            done.append(cur)
-            cur = b""
-        else:
-            cur += bytes(r["data"][:25])
-    for pkt in done:
-        if len(pkt) < 2:
-            out.append((pkt, False))
-            continue
-        t = torch.frombuffer(bytearray(pkt), dtype=torch.uint8).reshape(1, -1).to(ctx.device)
-        crc = int(ctx.m17_crc_array_encode(t).view(torch.int16).to(torch.int32).item()) & 0xFFFF
-        out.append((pkt[:-2], crc == 0))
-    return out
+def packets_of(bytes_, pkt, npkt, c):
+    """host view of one channel's reassembled packets: list of (payload bytes, crc_ok)"""
+    b = bytes_[c].cpu().numpy(); p = pkt[c].cpu().numpy(); n = int(npkt[c])
+    return [(bytes(b[p[k, 0]: p[k, 0] + p[k, 1]]), bool(p[k, 2])) for k in range(n)]

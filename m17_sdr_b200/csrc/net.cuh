@@ -6,7 +6,7 @@
 // Sockets, the reflector handshake (CONN/ACKN/PING/PONG/DISC) and threads stay with the host application: out of scope.
 // One thread per frame; byte work, HBM-trivial (54 B out per 64-B record in).
 #pragma once
-#include "tx.cuh"
+#include "app.cuh"
 
 __device__ __forceinline__ void net_write_frame(uint8_t *o, uint16_t sid, const uint8_t *lsf28, int have_dst, uint64_t dst, const uint8_t *fn_pld18,
                                                 const uint16_t *tab) {

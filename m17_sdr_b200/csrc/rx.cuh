@@ -32,6 +32,7 @@ struct m17b_rx {
     cudaEvent_t ev_fork, ev_join;
     cudaEvent_t ev_h2d[2], ev_done[2], ev_tail;
     int afc, bert, last_launches, seam_last;
+    void *d_pkt_state;                // [nchan] RxPacketState of m17b_rx_reassemble_packets (app.cuh), allocated on first use
     int *d_overflow;                  // sticky flags (m17b_rx_get_overflow): 1 = the symbol seam was given more symbols than the capacity
     // time-sliced pipeline (see rx_pipeline): front end of slice k+1 | timing loop + framer of slice k | frame decode of slice k-1
     int slice_blocks;                 // blocks per slice; 0 = one slice (stages strictly in sequence)
@@ -245,7 +246,7 @@ extern "C" int m17b_rx_destroy(m17b_rx *rx) {
         if (rx->ev_done[i]) cudaEventDestroy(rx->ev_done[i]);
     }
     if (rx->ev_tail) cudaEventDestroy(rx->ev_tail);
-    cudaFree(rx->d_frame_rng); cudaFree(rx->d_lsf_snap); cudaFree(rx->d_lsf_ver); cudaFree(rx->d_overflow);
+    cudaFree(rx->d_frame_rng); cudaFree(rx->d_lsf_snap); cudaFree(rx->d_lsf_ver); cudaFree(rx->d_overflow); cudaFree(rx->d_pkt_state);
     if (rx->s_fe) cudaStreamDestroy(rx->s_fe);
     if (rx->s_sync) cudaStreamDestroy(rx->s_sync);
     if (rx->s_dec) cudaStreamDestroy(rx->s_dec);
@@ -281,6 +282,7 @@ extern "C" int m17b_rx_reset(m17b_rx *rx, void *stream) {
     CUDA_TRY(cudaMemsetAsync(rx->d_nframes, 0, sizeof(int32_t) * rx->nchan, st));
     CUDA_TRY(cudaMemsetAsync(rx->d_nevents, 0, sizeof(int32_t) * rx->nchan, st));
     CUDA_TRY(cudaMemsetAsync(rx->d_overflow, 0, sizeof(int), st));
+    if (rx->d_pkt_state) CUDA_TRY(cudaMemsetAsync(rx->d_pkt_state, 0, (size_t)832 * rx->nchan, st));     // sizeof(RxPacketState), app.cuh
     return M17B_OK;
 }
 

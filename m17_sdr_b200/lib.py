@@ -91,6 +91,8 @@ _SIGS = {
     "m17b_demap_symbols": ([_vp, _vp, _vp, _i64, _vp, _vp], _i32),
     "m17b_dsp_decimating_filter": ([_vp, _vp, _i64, _vp, _i32, _i32, _i32, _i64, _vp, C.POINTER(_i32), _vp], _i32),
     "m17b_prbs9_rx_check": ([_vp, _vp, _i32, _i64, _vp, _vp], _i32),
+    "m17b_rx_reassemble_packets": ([_vp, _vp, _i64, _vp, _i32, _vp, _vp], _i32),
+    "m17b_gps_decode": ([_vp, _vp, _i64, _i64, _vp, _vp], _i32),
     "m17b_eq_restart": ([_vp, _vp], _i32),
     "m17b_eq_create": ([_vp, _i64, C.POINTER(_vp)], _i32),
     "m17b_eq_destroy": ([_vp], _i32),

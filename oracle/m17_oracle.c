@@ -202,6 +202,18 @@ void m17o_derand_bytes(uint8_t *io, int len) { for (int i = 0; i < len; i++) io[
 void m17o_derand_bits(const uint8_t *in, uint8_t *out, int len) { for (int i = 0; i < len; i++) out[i] = (in[i] ^ t_rand[i % 368]) & 1; }
 void m17o_derand_soft(const float *in, float *out, int len) { for (int i = 0; i < len; i++) out[i] = t_rand[i % 368] ? -in[i] : in[i]; }
 
+/* gps_decode (gps.cpp:8-27): b points at the 14 META bytes of an LSF; 15 bytes are read (the last one is the first CRC byte).
+   out = {lat, lon} doubles, then alt, course, speed, object as int32 */
+void m17o_gps_decode(const uint8_t *b, double *latlon, int32_t *out4) {
+    latlon[0] = (double)(int8_t)b[0] + (double)(uint16_t)((b[1] << 8) | b[2]) / 65536.0;
+    latlon[1] = (double)(int16_t)((b[3] << 8) | b[4]) + (double)(uint16_t)((b[5] << 8) | b[6]) / 65536.0;
+    out4[0] = (int16_t)(((b[7] << 8) | b[8]) - 1500);
+    uint64_t w = 0;
+    for (int k = 0; k < 6; k++) w = (w << 8) | b[9 + k];
+    out4[1] = (uint16_t)(w >> 38);
+    out4[2] = (int32_t)((w >> 28) & 0x3FF);
+    out4[3] = (int32_t)(w & 0xFFFFF);
+}
 /* m17_dsp_demap_symbol (m17_dsp.cpp:35-42): one symbol with the caller's normaliser */
 void m17o_demap_symbol(float in, float mag, float *out) {
     float m = in * mag;

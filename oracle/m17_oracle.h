@@ -49,6 +49,7 @@ void m17o_derand_bytes(uint8_t *io, int len);                                /* 
 void m17o_derand_bits(const uint8_t *in, uint8_t *out, int len);             /* m17_correlate.cpp:16-20 */
 void m17o_derand_soft(const float *in, float *out, int len);                 /* m17_correlate.cpp:27-31 */
 void m17o_demap_frame(const float *sym192, float *soft368);                  /* m17_dsp.cpp:35-42,82-95 */
+void m17o_gps_decode(const uint8_t *meta15, double *latlon2, int32_t *alt_course_speed_object);   /* gps.cpp:8-27 */
 void m17o_demap_symbol(float in, float mag, float *out2);                    /* m17_dsp.cpp:35-42 */
 int  m17o_decimating_filter(const float *in, float *out, const float *coffs, int stride, int flen, int len);   /* m17_dsp.cpp:438-449 */
 uint32_t m17o_hard24(const float *in);                                       /* m17_bit_utils.cpp:180-187 */

@@ -327,6 +327,11 @@ void ref_derand_bits(uint8_t *in, uint8_t *out, int len) { m17_de_correlate_1(in
 void ref_derand_soft(float *in, float *out, int len) { m17_de_correlate_1(in, out, len); }
 void ref_demap_frame(float *in, float *out) { __real__Z19m17_dsp_demap_framePfS_(in, out); }
 void ref_demap_symbol(float in, float mag, float *out) { m17_dsp_demap_symbol(in, mag, out); }
+void ref_gps_decode(uint8_t *b, double *latlon, int32_t *out4) {       /* gps.cpp:8-27, the reference's own object */
+    GpsMsg g; memset(&g, 0, sizeof(g));
+    gps_decode(b, &g);
+    latlon[0] = g.lat; latlon[1] = g.lon; out4[0] = g.alt; out4[1] = g.course; out4[2] = g.speed; out4[3] = (int32_t)g.object;
+}
 int  ref_decimating_filter(float *in, float *out, float *coffs, int stride, int flen, int len) { return m17_dsp_decimating_filter(in, out, coffs, stride, flen, len); }
 uint32_t ref_hard24(float *in) { return hard_decode_24_bits(in); }
 void ref_sync_check(float *v, int *type, int *votes, float *var) { M17Sync s; m17_sync_check(v, &s); *type = s.type; *votes = s.votes; *var = s.variance; }

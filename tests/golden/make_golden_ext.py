@@ -54,6 +54,10 @@ def main():
     x = rng.normal(0, 1, (3, 230)).astype(np.float32); cf = rng.normal(0, 0.2, 31).astype(np.float32)
     g["dfil_in"], g["dfil_coffs"] = x, cf
     g["dfil_out"] = np.stack([R.decimating_filter(r, cf, 5, 200) for r in x])
+    # ---- gps_decode (gps.cpp:8-27) on random LSFs
+    gl = rng.integers(0, 256, (40, 30), dtype=np.uint8)
+    g["gps_lsf"] = gl
+    g["gps_out"] = np.array([R.gps_decode(l) for l in gl], np.float64)
     out = os.path.join(HERE, "m17_golden_ext.npz")
     np.savez_compressed(out, **g)
     print(out, os.path.getsize(out), "bytes; afc frames", o.counts[:, 2])

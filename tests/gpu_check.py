@@ -100,6 +100,13 @@ def check_primitives(ctx, P, seed=11, n=64):
     GX = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "m17_golden_ext.npz"))
     assert bits_eq(ctx.m17_dsp_demap_symbol(dev(GX["dsym_in"]), dev(GX["dsym_mag"])).cpu().numpy(), GX["dsym_out"]), "demap symbol (reference fixture)"
     assert bits_eq(ctx.m17_dsp_decimating_filter(dev(GX["dfil_in"]), dev(GX["dfil_coffs"]), 5, 200).cpu().numpy(), GX["dfil_out"]), "decimating filter (reference fixture)"
+    # gps_decode (gps.cpp:8-27) on the META field: oracle on random LSFs and the reference's outputs from the fixture
+    gl = rng.integers(0, 256, (200, 30), dtype=np.uint8)
+    gg = ctx.gps_decode(dev(gl))
+    for i in range(len(gl)):
+        assert tuple(gg[i].tolist()) == P.gps_decode(gl[i]), ("gps_decode", i)
+    gg = ctx.gps_decode(dev(GX["gps_lsf"]))
+    assert np.array_equal(np.array([tuple(r.tolist()) for r in gg], np.float64), GX["gps_out"]), "gps_decode (reference fixture)"
     seq3 = np.tile(P.prbs9(), 3)
     pb = np.stack([seq3[:900], np.roll(seq3, 5)[:900], rng.integers(0, 2, 900).astype(np.uint8)]).astype(np.uint8)
     pb[0, [300, 301, 640]] ^= 1
@@ -539,22 +546,38 @@ def check_rx_baseband(ctx, P, nchan=14, nframes=30, seed=22, verbose=False, spli
 def check_rx_packet(ctx, P, nchan=12, seed=25, verbose=False):
     """config 3: packet mode with random carrier / fractional-timing offsets; per-frame 26 bytes bit-exact vs the oracle,
     and the host-side reassembly (GPU CRC) recovers every packet the oracle's frames carry"""
-    from m17_sdr_b200.api import reassemble_packets
+    import m17_sdr_b200 as m
+    from m17_sdr_b200.api import packets_of
     eb = ([None, None, 30, 28, 26, 24] * 4)[:nchan]
     X, packets = signals.packet_channels(P, nchan, seed, ebn0=eb)
     o = P.rx_run(X, seam=0)
     res = run_chain(ctx, X, 0)
     compare_chain(res, o, 0, nchan, verbose)
+    # batched reassembly on the GPU, in one call and with the capture cut into three calls (a packet then spans calls)
+    T = X.shape[1] // 1920
+    rx = m.Rx(ctx, nchan, T)
+    rx.m17_dsp_rx(dev(X))
+    whole = rx.reassemble_packets(bytes_cap=8192, max_pkts=64)      # (a noisy channel yields spurious short 'packets': room for all of them)
+    rx.reset()
+    parts = [[] for _ in range(nchan)]
+    cuts = [0, T // 3, T // 3 + 2, T]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        rx.m17_dsp_rx(dev(X[:, a * 1920:b * 1920]))
+        pb = rx.reassemble_packets(bytes_cap=8192, max_pkts=64)
+        for c in range(nchan):
+            parts[c] += packets_of(*pb, c)
+    rx.close()
     good = 0
     for c in range(nchan):
-        got = reassemble_packets(ctx, res["frames"][c], int(res["nframes"][c]))
+        got = packets_of(*whole, c)
+        assert parts[c] == got, ("reassembly across calls", c)
         # oracle-side reassembly of the oracle's own records with the oracle CRC
         buf, exp = b"", []
         for r in o.frames[c, : o.counts[c, 2]]:
             if r["type"] == 3 and r["flags"] & 2:
                 m = int(r["data"][25])
                 if m & 0x80:
-                    buf += bytes(r["data"][: (m >> 2) & 31]); exp.append((buf[:-2], P.crc(buf) == 0) if len(buf) >= 2 else (buf, False)); buf = b""
+                    buf += bytes(r["data"][: (m >> 2) & 31]); exp.append((buf[:-2], P.crc(buf) == 0) if len(buf) >= 2 else (b"", False)); buf = b""      # shorter than its CRC: no payload
                 else:
                     buf += bytes(r["data"][:25])
         assert got == exp, (c, got, exp)

@@ -220,6 +220,13 @@ class Port:
         self.L.m17o_demap_frame(_p(a), _p(out))
         return out
 
+    def gps_decode(self, lsf30):
+        """gps_decode on the META field of one 30-byte LSF -> (lat, lon, alt, course, speed, object)"""
+        b = np.ascontiguousarray(lsf30, np.uint8)[14:30].copy()
+        ll = np.zeros(2, np.float64); o = np.zeros(4, np.int32)
+        self.L.m17o_gps_decode(_p(b), _p(ll), _p(o))
+        return (float(ll[0]), float(ll[1]), int(o[0]), int(o[1]), int(o[2]), int(o[3]))
+
     def demap_symbol(self, sym, mag):
         """m17_dsp_demap_symbol for arrays of symbols / normalisers -> [n][2]"""
         sym = np.ascontiguousarray(sym, np.float32); mag = np.ascontiguousarray(mag, np.float32)
@@ -531,6 +538,12 @@ class Ref:
         out = np.zeros(368, np.float32)
         self.L.ref_demap_frame(_p(a), _p(out))
         return out
+
+    def gps_decode(self, lsf30):
+        b = np.ascontiguousarray(lsf30, np.uint8)[14:30].copy()
+        ll = np.zeros(2, np.float64); o = np.zeros(4, np.int32)
+        self.L.ref_gps_decode(_p(b), _p(ll), _p(o))
+        return (float(ll[0]), float(ll[1]), int(o[0]), int(o[1]), int(o[2]), int(o[3]))
 
     def demap_symbol(self, sym, mag):
         sym = np.ascontiguousarray(sym, np.float32); mag = np.ascontiguousarray(mag, np.float32)

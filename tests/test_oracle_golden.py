@@ -193,3 +193,4 @@ def test_golden_ext(port):
     assert np.array_equal(port.demap_symbol(E["dsym_in"], E["dsym_mag"]).view(np.uint32), E["dsym_out"].view(np.uint32))
     got = np.stack([port.decimating_filter(r, E["dfil_coffs"], 5, 200) for r in E["dfil_in"]])
     assert np.array_equal(got.view(np.uint32), E["dfil_out"].view(np.uint32))
+    assert np.array_equal(np.array([port.gps_decode(l) for l in E["gps_lsf"]], np.float64), E["gps_out"])

@@ -31,6 +31,10 @@ def test_primitives_random(port, ref):
         assert a[:2] == b[:2] and feq(a[2], b[2])
     for args in ((0.5, 1240, 80), (0.5, 310, 10), (0.5, 62, 2), (0.5, 2480, 80), (0.35, 101, 4)):
         assert feq(port.rrc(*args), ref.rrc(*args))
+    # gps_decode (gps.cpp:8-27) on random LSFs, incl. negative latitudes / longitudes and altitudes below the 1500 m offset
+    for _ in range(300):
+        lsf = rng.integers(0, 256, 30, dtype=np.uint8)
+        assert port.gps_decode(lsf) == ref.gps_decode(lsf)
     # m17_dsp_demap_symbol, m17_dsp_decimating_filter (m17_dsp.cpp:35-42,438-449)
     sy = rng.normal(0, 1, 4000).astype(np.float32); mg = rng.uniform(0.05, 6, 4000).astype(np.float32)
     sy[:4] = [0.0, -0.0, 0.6666, -0.6666]
