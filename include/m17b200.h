@@ -153,8 +153,9 @@ int m17b_rx_reset(m17b_rx *rx, void *stream);
    the discriminator history, the LICH cache and the counters are left as they are */
 int m17b_rx_framer_reset(m17b_rx *rx, void *stream);
 /* radio_set_afc_on / radio_set_afc_off (radio.cpp:146-152): with AFC on, m17b_dsp_rx runs dsp_nco_mixer + radio_afc
-   (m17_dsp.cpp:390-408, radio.cpp:196-208) and processes the blocks of a call one at a time (the loop is closed through the
-   framer); off (the reference default) uses the block-parallel front end.  No effect on m17b_rx_baseband. */
+   (m17_dsp.cpp:390-408, radio.cpp:196-208); the loop is closed through the framer, so a channel's blocks are serial through
+   the whole chain: the front end of each block then runs inside the timing-loop kernel (one launch per call).  Off (the
+   reference default) uses the block-parallel front end.  No effect on m17b_rx_baseband. */
 int m17b_rx_set_afc(m17b_rx *rx, int on, void *stream);
 /* BERT receive.  The reference sends BERT frames (m17_fmt_add_bert_frame) but its decode_bert_frame is empty
    (m17_rx_parse.cpp:178-180) and m17_prbs9_rx_check (m17_prbs9.cpp:40-64) is never called.  With on != 0, BERT frames are

@@ -14,7 +14,7 @@
 // (padded by 4 words every 32 so that the 16-byte column reads below are conflict-free); each thread produces four
 // consecutive outputs from 56 staged samples (14 LDS.128) and stores them as one 16-byte word.
 #pragma once
-#include "afc.cuh"
+#include "framer.cuh"
 
 #define DEC_NTAP 31
 #define DEC_TILE 512                       // outputs per CTA

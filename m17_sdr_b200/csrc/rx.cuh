@@ -446,14 +446,20 @@ static int rx_pipeline(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t *d_iq,
     int nsl = (sb > 0 && !rx->timing && allow_slices) ? (int)((T + sb - 1) / sb) : 1;
     if (nsl > M17B_MAX_SLICES) { nsl = M17B_MAX_SLICES; }
     if (rx->afc && d_iq) {
-        // block-serial loop: AFC front end of block t, then timing loop + framer of block t (which decides in_frame for t+1)
+        // AFC on: the NCO step of a block depends on the framer state and the mean of the block before it, so a channel's blocks
+        // are serial through the WHOLE chain -- but only within the channel.  One launch: the warp that owns the channel runs
+        // the AFC front end of each block inside the timing loop's block loop (k_sync_frame<true, true>, afc.cuh).
         STAGE_MARK(0);
         STAGE_MARK(1);
-        for (int64_t t = 0; t < T; t++) {
-            k_frontend_afc<<<grid_for(nc, AFC_WARPS), AFC_WARPS * 32, AFC_WARPS * sizeof(AfcWarpSmem), st>>>((const uint32_t *)d_iq, nc, T, t, rx->d_state + c0, disc_w, mean_w);
+        {
+            const size_t smem = sizeof(AfcWarpSmem) * SY_WARPS;
+            CUDA_TRY(cudaFuncSetAttribute(k_sync_frame<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const f32x2 one = 0x3F8000003F800000ull;
+            k_sync_frame<true, true><<<grid_for(nc, SY_WARPS), SY_WARPS * 32, smem, st>>>(
+                nullptr, nullptr, nc, T, 0, (int)T, nullptr, rx->d_state + c0, ctx->d_mf, ctx->d_md, rx->d_syms + c0 * rx->sym_pitch, rx->sym_pitch,
+                rx->d_nsym + c0 * T, rx->d_sym_base + c0, rx->d_frames + c0 * rx->fcap, rx->fcap, rx->d_nframes + c0, rx->d_events + c0 * rx->ecap, rx->ecap,
+                rx->d_nevents + c0, rx->d_stats + c0 * 8, 0, one, (const uint32_t *)d_iq, disc_w, mean_w);
             KERNEL_CHECK();
-            int rc = launch_sync(rx, c0, nc, disc, mean, T, (int)t, (int)t + 1, nullptr, 0, st);
-            if (rc) return rc;
         }
         STAGE_MARK(2);
         int rc = launch_decode(ctx, syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0, nc, nullptr, st,
@@ -465,7 +471,7 @@ static int rx_pipeline(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t *d_iq,
                                                                   ctx->d_prbs, rx->bert);
         KERNEL_CHECK();
         STAGE_MARK(4);
-        rx->last_launches += (int)(2 * T) + 3;
+        rx->last_launches += 4;
         return M17B_OK;
     }
     if (nsl < 2) {
@@ -562,7 +568,7 @@ static int rx_groups_for(const m17b_rx *rx) {
     // and above one wave nothing is gained (benchmarks/chan_groups.py).  More than 4 groups exceed the 8 hardware queues.
     if (G < 0) G = (rx->nchan >= 512 && rx->nchan <= 8 * 148) ? 4 : 1;
     if (G > M17B_MAX_GROUPS) G = M17B_MAX_GROUPS;
-    if (G < 2 || rx->timing || rx->afc || rx->nchan < 2 * G) return 1;
+    if (G < 2 || rx->timing || rx->nchan < 2 * G) return 1;
     return G;
 }
 

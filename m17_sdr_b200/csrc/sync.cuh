@@ -18,7 +18,7 @@
 // in straight-line code for the common case of one frame boundary per block.
 // The next block's samples are prefetched as 16-byte cp.async pieces and staged with vector loads.
 #pragma once
-#include "frontend.cuh"
+#include "afc.cuh"
 
 #ifndef SY_WARPS
 #define SY_WARPS 4
@@ -95,14 +95,19 @@ __device__ __forceinline__ void dot6(const float (*X)[SY_XQ], int base, const f3
     for (int m = 0; m < 6; m++) unpack2(acc[m], s[m], d[m]);
 }
 
-template <bool HAS_MEAN>
-__global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__restrict__ disc, const float *__restrict__ mean, int64_t nchan, int64_t T,
+// AFC = true (m17b_rx_set_afc): the block's discriminator samples do not come from memory but from the AFC front end run by
+// the same warp at the top of the block loop (afc.cuh): iq = int16 IQ rows, disc / mean are then OUTPUTS (the raw samples and
+// block means the caller may inspect).  23 KB more shared memory per warp: one CTA per SM.
+template <bool HAS_MEAN, bool AFC = false>
+__global__ void __launch_bounds__(SY_WARPS * 32, AFC ? 1 : 2) k_sync_frame(const float *__restrict__ disc, const float *__restrict__ mean, int64_t nchan, int64_t T,
                                                               int t0, int t1, int2 *frame_rng, RxChanState *st, const float *__restrict__ g_mf, const float *__restrict__ g_md,
                                                               float *syms, int64_t sym_pitch, int32_t *__restrict__ nsym, int32_t *__restrict__ sym_base,
                                                               m17b_frame_rec *frames, int64_t fcap, int32_t *__restrict__ nframes,
                                                               m17b_event_rec *events, int64_t ecap, int32_t *__restrict__ nevents,
-                                                              unsigned long long *stats, int commit_fe, f32x2 one) {
+                                                              unsigned long long *stats, int commit_fe, f32x2 one,
+                                                              const uint32_t *__restrict__ iq = nullptr, float *disc_out = nullptr, float *mean_out = nullptr) {
     __shared__ __align__(16) SyncWarpSmem sm_all[SY_WARPS];
+    extern __shared__ __align__(16) unsigned char afc_smem_raw[];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t c = (int64_t)blockIdx.x * SY_WARPS + wid;
     if (c >= nchan) return;
@@ -161,12 +166,24 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
         }
         asm volatile("cp.async.commit_group;");
     };
-    prefetch(t0, 0);
+    // AFC loop state: every lane carries the same values (radio.cpp:8-10, m17_dsp.cpp:391)
+    float afc_delta = 0.0f;
+    double nco_acc = 0.0;
+    int disc_count = 0;
+    AfcWarpSmem *afc_sm = nullptr;
+    if (AFC) {
+        afc_sm = (AfcWarpSmem *)afc_smem_raw + wid;
+        afc_delta = S->afc_delta; nco_acc = S->nco_acc; disc_count = S->disc_count;
+        if (lane == 0) { afc_sm->lim[0] = make_float2(S->z1re, S->z1im); afc_sm->lim[1] = make_float2(S->z0re, S->z0im); }
+        __syncwarp();
+    } else prefetch(t0, 0);
 
     for (int64_t t = t0; t < t1; t++) {
         // ---- stage the block's 384 discriminator samples behind the 30 of history
         const int buf = (int)((t - t0) & 1);
-        asm volatile("cp.async.wait_group 0;");
+        if (AFC) afc_block(*afc_sm, iq + (c * T + t) * M17B_BLOCK_SAMPLES, lane, flock, disc_count, afc_delta, nco_acc, sm.pre[buf], &sm.pre[buf][384],
+                           disc_out + (c * T + t) * M17B_DISC_PER_BLOCK, mean_out + c * T + t);
+        else asm volatile("cp.async.wait_group 0;");
         __syncwarp();
         {
             const float pmu = !HAS_MEAN ? 0.0f : sm.pre[buf][384];
@@ -183,7 +200,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
                 sm.x[1][8 + mq] = v.w;
             }
         }
-        if (t + 1 < t1) prefetch(t + 1, buf ^ 1);
+        if (!AFC && t + 1 < t1) prefetch(t + 1, buf ^ 1);
         __syncwarp();
 
         PHASE(0);
@@ -479,6 +496,11 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
     }
 
     // ---- store state
+    if (AFC && lane == 0) {
+        S->afc_delta = afc_delta; S->nco_acc = nco_acc;
+        const float2 y1 = afc_sm->lim[0], y0 = afc_sm->lim[1];
+        S->z0re = y0.x; S->z0im = y0.y; S->z1re = y1.x; S->z1im = y1.y;
+    }
     if (lane < 30) S->tail[lane] = sm.x[lane & 3][lane >> 2];
     if (lane < 8) { S->win[lane] = sm.hist[lane]; S->head[lane] = sm.head[lane]; }
     if (lane == 0) {
