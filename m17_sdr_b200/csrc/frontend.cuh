@@ -47,7 +47,10 @@ __device__ __forceinline__ LimSample fe_limit_ieee(uint32_t raw, float *mo = nul
 // Every half of every packed operation is an independent IEEE round-to-nearest operation, so the results are those of the
 // scalar formulation, which m17b_selftest_frontend compares with fe_limit_ieee over all 2^32 raw words.
 __device__ __forceinline__ void fe_limit2(uint32_t raw_a, uint32_t raw_b, LimSample &oa, LimSample &ob, float *mo = nullptr, float *go = nullptr) {
-    // int16 -> float: one I2F.S16 per component, reading the half-register directly (exact)
+    // int16 -> float: one I2F.S16 per component, reading the half-register directly (exact).  (Tried in round 2: the
+    // conversion on the ALU / FMA pipes instead -- (x ^ 0x4B008000) as a float minus 2^23 + 32768, exact and verified over all
+    // 2^32 inputs -- to unload the quarter-rate XU pipe: 0.606 -> 0.631 ms.  The kernel is bound by issue slots and the FP32
+    // pipe, not by the XU; the three extra ALU / packed instructions per sample cost more than the two I2F they replace.)
     const f32x2 xa = pack2((float)(short)(raw_a & 0xFFFFu), (float)(short)(raw_a >> 16));
     const f32x2 xb = pack2((float)(short)(raw_b & 0xFFFFu), (float)(short)(raw_b >> 16));
     constexpr float c_hi = 0.00003f;
