@@ -128,7 +128,7 @@ def bind_to_gpu_numa_node(torch, local):
 
 
 # ------------------------------------------------------------------------------------------------ workload
-def make_workload(ctx, m, torch, C, T, seed, ebn0=EBN0_SWEEP):
+def make_workload(ctx, m, torch, C, T, seed, ebn0=EBN0_SWEEP, f0_max=1000.0):
     """Synthetic stream-mode channels generated ON THE GPU with the library's own TX path (outside any timed
     region): LSF -> frame formatter -> RRC x10 -> 4FSK -> int16 IQ, then delay / carrier offset / AWGN."""
     dev = ctx.device
@@ -165,7 +165,7 @@ def make_workload(ctx, m, torch, C, T, seed, ebn0=EBN0_SWEEP):
     # carrier offset + AWGN
     eb = np.array([ebn0[c % len(ebn0)] if ebn0[c % len(ebn0)] is not None else np.inf for c in range(C)])
     sigma = np.where(np.isinf(eb), 0.0, np.sqrt(2.5 * 16383.0 ** 2 / 10 ** (eb / 10))).astype(np.float32)
-    f0 = (torch.rand((C,), generator=g, device=dev) * 2000.0 - 1000.0) / 48000.0
+    f0 = (torch.rand((C,), generator=g, device=dev) * 2.0 - 1.0) * f0_max / 48000.0
     ctx.synth_channel(iq, torch.from_numpy(sigma).to(dev), f0.float().contiguous(), seed=seed)
     torch.cuda.synchronize()
     return iq, payload

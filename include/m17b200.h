@@ -273,6 +273,24 @@ int m17b_dec_get_taps(const m17b_dec *dec, int16_t *h_taps31);
    reference produces 240 per 1920-sample chunk); the 31-sample filter history carries over from call to call */
 int m17b_dec_run(m17b_dec *dec, const int16_t *d_in, int64_t nout, int16_t *d_out, void *stream);
 
+/* ------------------------------------------------------------------ wideband channeliser (second half) */
+/* The Pluto decimator (radio.cpp:18-40) generalised from one channel to a raster: one int16 IQ capture at 1.2 MS/s
+   (25 x 48 kS/s) -> 96 channels spaced 12.5 kHz at 48 kS/s, in the layout m17b_dsp_rx reads.  Integer arithmetic throughout
+   (polyphase int16 FIR with int32 accumulators, fixed-point 96-point DFT, >> 15), stated in plain C by the oracle
+   (m17o_chan_run), which is pinned at M = 1, D = 8 against radio.cpp itself.  taps_per_branch = 4, 8, 12 or 16 (filter length
+   96 x that; 12 gives > 60 dB at the adjacent channel). */
+typedef struct m17b_chan m17b_chan;
+#define M17B_CHAN_M 96
+#define M17B_CHAN_D 25
+int m17b_chan_create(m17b_ctx *ctx, int64_t ncaptures, int taps_per_branch, m17b_chan **out);
+int m17b_chan_destroy(m17b_chan *ch);
+int m17b_chan_reset(m17b_chan *ch, void *stream);
+int m17b_chan_get_taps(const m17b_chan *ch, int16_t *h_taps, int *len);
+/* d_in int16 [ncaptures][25*nout][2] -> d_out int16 [ncaptures*96][out_pitch][2] (out_pitch >= nout samples per row); row
+   capture*96 + k is the channel k * 12.5 kHz above the capture's centre (k >= 48: below it).  Filter history and window phase
+   carry over from call to call. */
+int m17b_chan_run(m17b_chan *ch, const int16_t *d_in, int64_t nout, int16_t *d_out, int64_t out_pitch, void *stream);
+
 /* ------------------------------------------------------------------ M17-over-UDP reflector frame */
 #define M17B_NET_FRAME_BYTES 54
 /* net_add_magic/_stream_id/_lich/_fn/_payload/_crc (m17_net.cpp:25-49), build_lich_to_net + m17_send_stream_frame_to_net

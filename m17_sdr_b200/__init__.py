@@ -10,7 +10,7 @@ from .build import build, LIB  # noqa: F401
 
 def __getattr__(name):
     # api needs torch; keep `import m17_sdr_b200` light for the build check
-    if name in ("Context", "Rx", "Tx", "Equalizer", "Decimator", "REC_DTYPE", "EV_DTYPE", "GPS_DTYPE", "records_to_numpy", "packets_of", "STAT_NAMES"):
+    if name in ("Context", "Rx", "Tx", "Equalizer", "Decimator", "Channelizer", "REC_DTYPE", "EV_DTYPE", "GPS_DTYPE", "records_to_numpy", "packets_of", "STAT_NAMES"):
         from . import api
         return getattr(api, name)
     raise AttributeError(name)

@@ -559,6 +559,42 @@ class Decimator:
         return out
 
 
+class Channelizer:
+    """Wideband channeliser: int16 IQ captures at 1.2 MS/s -> 96 channels x 48 kS/s each (the Pluto decimator of radio.cpp:18-40
+    generalised to a 12.5 kHz raster; integer arithmetic, bit-exact against the oracle)."""
+    M, D = 96, 25
+
+    def __init__(self, ctx, ncap, taps_per_branch=12):
+        self.ctx, self.L, self.ncap = ctx, ctx.L, ncap
+        h = C.c_void_p()
+        _l.check(self.L.m17b_chan_create(ctx.h, ncap, taps_per_branch, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.L.m17b_chan_destroy(self.h)
+            self.h = None
+
+    def reset(self):
+        _l.check(self.L.m17b_chan_reset(self.h, _stream()))
+
+    def taps(self):
+        t = np.zeros(96 * 16, np.int16)
+        n = C.c_int()
+        _l.check(self.L.m17b_chan_get_taps(self.h, t.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return t[: n.value].copy()
+
+    def run(self, wide, out=None):
+        """wide: int16 CUDA tensor [ncap][25*nout][2] -> int16 [ncap*96][nout][2]"""
+        _chk_dev(wide, torch.int16, "wide")
+        assert wide.shape[0] == self.ncap and wide.shape[1] % 25 == 0 and wide.shape[2] == 2
+        nout = wide.shape[1] // 25
+        if out is None:
+            out = torch.empty((self.ncap * 96, nout, 2), dtype=torch.int16, device=wide.device)
+        _l.check(self.L.m17b_chan_run(self.h, _ptr(wide), nout, _ptr(out), out.shape[1], _stream()))
+        return out
+
+
 class Equalizer:
     """Batched eq_train_known / eq_train_unknown (m17_equalize.cpp)."""
 

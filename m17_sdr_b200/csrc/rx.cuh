@@ -8,7 +8,7 @@
 //   k_decode_frames (thread per frame)                            -> decoded bytes, Golay, CRC into the records
 //   k_post          (thread per channel, frames in order)         -> LICH cache, delivery / LSF-event flags, stats
 #pragma once
-#include "dec.cuh"
+#include "chan.cuh"
 
 #define M17B_TIMING_RING 64
 #define M17B_MAX_SLICES 16

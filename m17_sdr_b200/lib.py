@@ -85,6 +85,11 @@ _SIGS = {
     "m17b_dec_reset": ([_vp, _vp], _i32),
     "m17b_dec_get_taps": ([_vp, _vp], _i32),
     "m17b_dec_run": ([_vp, _vp, _i64, _vp, _vp], _i32),
+    "m17b_chan_create": ([_vp, _i64, _i32, C.POINTER(_vp)], _i32),
+    "m17b_chan_destroy": ([_vp], _i32),
+    "m17b_chan_reset": ([_vp, _vp], _i32),
+    "m17b_chan_get_taps": ([_vp, _vp, C.POINTER(_i32)], _i32),
+    "m17b_chan_run": ([_vp, _vp, _i64, _vp, _i64, _vp], _i32),
     "m17b_net_pack": ([_vp, _vp, _vp, _i64, _i32, _u64, _vp, _vp, _i64, _vp, _vp], _i32),
     "m17b_net_parse": ([_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp], _i32),
     "m17b_rx_net_frames": ([_vp, _vp, _i32, _u64, _vp, _vp, _vp], _i32),

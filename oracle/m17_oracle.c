@@ -830,3 +830,121 @@ double m17o_rx_time(const int16_t *iq, long C, long T, int nthreads) {
     j.in = iq; j.seam = 0; j.C = C; j.T = T;
     return run_jobs(&j, nthreads);
 }
+
+/* ================================================================== wideband channeliser (second half)
+   The reference's Pluto path low-pass filters and decimates ONE 384 kS/s channel to 48 kS/s (sub_filter / rx_decimate_filter,
+   radio.cpp:18-40: int16 taps, int32 accumulate, >> 15).  Generalisation to M channels spaced Fs / M out of one capture at
+   Fs = D * 48 kS/s: the same integer FIR, folded into M polyphase branches, followed by an M-point DFT in fixed point.
+     window of output n   : x[nD - L + i], i = 0..L-1          (the reference's window for M = 1, D = 8, L = 31)
+     fold                 : z[p] = sum_q h[p + qM] * x[nD - L + p + qM]                      (int32, wraps like the reference)
+     DFT                  : Z[k] = sum_p z[p] e^{-j 2 pi k p / M}, M = 2^b or 3 * 2^b: prime-factor split 3 x 2^b (no twiddles
+                            between the parts), radix-2 decimation in time; twiddles are Q31 integers, a product is
+                            (int64 a * w) >> 31 per real multiply, twiddles 1 and -j are exact (no multiply)
+     phase of the window  : Y[k] = Z[k] * e^{-j 2 pi k (nD - L) / M}   (Q31 table, index 0 exact)
+     output               : y[k][n] = (int16)(Y[k] >> 15)                                   (the reference's scaling)
+   For M = 1 every step but the fold and the shift is the identity: the output IS radio.cpp's decimator (pinned in
+   tests/test_oracle_vs_ref.py with the reference's own taps).  TEST INFRASTRUCTURE ONLY. */
+static int32_t chq_mul(int32_t a, int32_t w) { return (int32_t)(((int64_t)a * (int64_t)w) >> 31); }
+static int32_t chq_add(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
+static int32_t chq_sub(int32_t a, int32_t b) { return (int32_t)((uint32_t)a - (uint32_t)b); }
+static int32_t chq_tw(double v) { double s = v * 2147483648.0; s = s < 0 ? s - 0.5 : s + 0.5; if (s > 2147483647.0) s = 2147483647.0; if (s < -2147483648.0) s = -2147483648.0; return (int32_t)s; }
+static void chq_cmul(int32_t ar, int32_t ai, int32_t wr, int32_t wi, int32_t *or_, int32_t *oi) {
+    *or_ = chq_sub(chq_mul(ar, wr), chq_mul(ai, wi));
+    *oi = chq_add(chq_mul(ar, wi), chq_mul(ai, wr));
+}
+m17o_chan *m17o_chan_open(int M, int D, int L, const int16_t *taps) {
+    int b = 0, m2 = M, has3 = 0;
+    if (M >= 3 && M % 3 == 0) { has3 = 1; m2 = M / 3; }
+    while ((1 << b) < m2) b++;
+    if ((1 << b) != m2 || M < 1 || D < 1 || L < 1) return NULL;
+    m17o_chan *c = (m17o_chan *)calloc(1, sizeof(*c));
+    c->M = M; c->D = D; c->L = L; c->lg2 = b; c->has3 = has3;
+    c->h = (int16_t *)malloc(sizeof(int16_t) * L); memcpy(c->h, taps, sizeof(int16_t) * L);
+    c->hist = (int16_t *)calloc((size_t)2 * L, sizeof(int16_t));
+    c->tw2 = (int32_t *)calloc((size_t)2 * (m2 > 1 ? m2 / 2 : 1), sizeof(int32_t));
+    for (int j = 0; j < m2 / 2; j++) { c->tw2[2 * j] = chq_tw(cos(2.0 * M_PI * j / m2)); c->tw2[2 * j + 1] = chq_tw(-sin(2.0 * M_PI * j / m2)); }
+    c->rot = (int32_t *)calloc((size_t)2 * M, sizeof(int32_t));
+    for (int r = 0; r < M; r++) { c->rot[2 * r] = chq_tw(cos(2.0 * M_PI * r / M)); c->rot[2 * r + 1] = chq_tw(-sin(2.0 * M_PI * r / M)); }
+    c->s3 = chq_tw(sqrt(3.0) / 2.0);
+    c->n_done = 0;
+    return c;
+}
+void m17o_chan_free(m17o_chan *c) { if (c) { free(c->h); free(c->hist); free(c->tw2); free(c->rot); free(c); } }
+static int chq_bitrev(int v, int bits) { int r = 0; for (int i = 0; i < bits; i++) r |= ((v >> i) & 1) << (bits - 1 - i); return r; }
+/* in-place 2^b-point DFT of (re, im), input in natural order */
+static void chq_fft2(const m17o_chan *c, int32_t *re, int32_t *im) {
+    const int N = 1 << c->lg2;
+    int32_t tr[1024], ti[1024];
+    for (int i = 0; i < N; i++) { tr[i] = re[chq_bitrev(i, c->lg2)]; ti[i] = im[chq_bitrev(i, c->lg2)]; }
+    for (int m = 2; m <= N; m <<= 1) {
+        for (int k = 0; k < N; k += m)
+            for (int j = 0; j < m / 2; j++) {
+                const int ti_ = j * (N / m);                       /* twiddle index of W_N^(j N / m) */
+                int32_t vr = tr[k + j + m / 2], vi = ti[k + j + m / 2], xr, xi;
+                if (ti_ == 0) { xr = vr; xi = vi; }                                   /* W = 1 */
+                else if (4 * ti_ == N) { xr = vi; xi = chq_sub(0, vr); }              /* W = -j */
+                else chq_cmul(vr, vi, c->tw2[2 * ti_], c->tw2[2 * ti_ + 1], &xr, &xi);
+                const int32_t ur = tr[k + j], ui = ti[k + j];
+                tr[k + j] = chq_add(ur, xr); ti[k + j] = chq_add(ui, xi);
+                tr[k + j + m / 2] = chq_sub(ur, xr); ti[k + j + m / 2] = chq_sub(ui, xi);
+            }
+    }
+    for (int i = 0; i < N; i++) { re[i] = tr[i]; im[i] = ti[i]; }
+}
+/* in [D * nout][2] -> out [M][out_pitch][2] (channel k = bin k: centre frequency k Fs / M, k >= M/2 negative) */
+void m17o_chan_run(m17o_chan *c, const int16_t *in, long nout, int16_t *out, long out_pitch) {
+    const int M = c->M, D = c->D, L = c->L, N2 = 1 << c->lg2;
+    const long nin = (long)D * nout;
+    int16_t *x = (int16_t *)malloc(sizeof(int16_t) * 2 * (size_t)(L + nin));      /* history then the new samples */
+    memcpy(x, c->hist, sizeof(int16_t) * 2 * L);
+    memcpy(x + 2 * L, in, sizeof(int16_t) * 2 * nin);
+    int32_t *zr = (int32_t *)malloc(sizeof(int32_t) * M), *zi = (int32_t *)malloc(sizeof(int32_t) * M);
+    int32_t *Zr = (int32_t *)malloc(sizeof(int32_t) * M), *Zi = (int32_t *)malloc(sizeof(int32_t) * M);
+    int32_t br[1024], bi[1024];
+    const int c1 = c->has3 ? N2 * ((N2 % 3 == 1) ? 1 : 2) : 0;                 /* N2 * (N2^-1 mod 3) */
+    int inv3 = 1; while (c->has3 && (3 * inv3) % N2 != 1 % N2) inv3++;
+    const int c2 = c->has3 ? 3 * inv3 : 1;                                     /* 3 * (3^-1 mod N2) */
+    for (long n = 0; n < nout; n++) {
+        /* output n of this call: window x[nD - L .. nD - 1] (the reference's sub_filter(&in[i*8]) over a buffer that starts with
+           the 31 carried samples, radio.cpp:36-38,167) */
+        const int16_t *w = x + 2 * (n * D);
+        for (int p = 0; p < M; p++) {
+            uint32_t sr = 0, si = 0;
+            for (int i = p; i < L; i += M) { sr += (uint32_t)((int32_t)c->h[i] * (int32_t)w[2 * i]); si += (uint32_t)((int32_t)c->h[i] * (int32_t)w[2 * i + 1]); }
+            zr[p] = (int32_t)sr; zi[p] = (int32_t)si;
+        }
+        if (!c->has3) {
+            if (N2 > 1) chq_fft2(c, zr, zi);
+            for (int k = 0; k < M; k++) { Zr[k] = zr[k]; Zi[k] = zi[k]; }
+        } else {
+            for (int k1 = 0; k1 < 3; k1++) {
+                for (int n2 = 0; n2 < N2; n2++) {
+                    const int p0 = (3 * n2) % M, p1 = (N2 + 3 * n2) % M, p2 = (2 * N2 + 3 * n2) % M;
+                    if (k1 == 0) { br[n2] = chq_add(chq_add(zr[p0], zr[p1]), zr[p2]); bi[n2] = chq_add(chq_add(zi[p0], zi[p1]), zi[p2]); }
+                    else {
+                        /* W3 = -1/2 - j sqrt(3)/2: z0 - (z1 + z2)/2 -+ j sqrt(3)/2 (z1 - z2) */
+                        const int32_t t1r = chq_add(zr[p1], zr[p2]), t1i = chq_add(zi[p1], zi[p2]);
+                        const int32_t t2r = chq_sub(zr[p1], zr[p2]), t2i = chq_sub(zi[p1], zi[p2]);
+                        const int32_t m1r = chq_sub(zr[p0], t1r >> 1), m1i = chq_sub(zi[p0], t1i >> 1);
+                        const int32_t m2r = chq_mul(t2r, c->s3), m2i = chq_mul(t2i, c->s3);
+                        if (k1 == 1) { br[n2] = chq_add(m1r, m2i); bi[n2] = chq_sub(m1i, m2r); }      /* m1 - j m2 */
+                        else         { br[n2] = chq_sub(m1r, m2i); bi[n2] = chq_add(m1i, m2r); }      /* m1 + j m2 */
+                    }
+                }
+                if (N2 > 1) chq_fft2(c, br, bi);
+                for (int k2 = 0; k2 < N2; k2++) { const int k = (c1 * k1 + c2 * k2) % M; Zr[k] = br[k2]; Zi[k] = bi[k2]; }
+            }
+        }
+        const long long i0 = (long long)(c->n_done + n) * D - L;             /* absolute index of the window's first sample */
+        for (int k = 0; k < M; k++) {
+            long long r = ((long long)k * (i0 % M)) % M; if (r < 0) r += M;
+            int32_t yr, yi;
+            if (r == 0) { yr = Zr[k]; yi = Zi[k]; } else chq_cmul(Zr[k], Zi[k], c->rot[2 * r], c->rot[2 * r + 1], &yr, &yi);
+            out[2 * ((long)k * out_pitch + n)] = (int16_t)(yr >> 15);
+            out[2 * ((long)k * out_pitch + n) + 1] = (int16_t)(yi >> 15);
+        }
+    }
+    memcpy(c->hist, x + 2 * nin, sizeof(int16_t) * 2 * L);
+    c->n_done += nout;
+    free(x); free(zr); free(zi); free(Zr); free(Zi);
+}

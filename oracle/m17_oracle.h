@@ -127,4 +127,10 @@ double m17o_rx_time(const int16_t *iq, long C, long T, int nthreads);
 #ifdef __cplusplus
 }
 #endif
+/* wideband channeliser: the Pluto decimator (radio.cpp:18-40) generalised to M channels out of one capture (see m17_oracle.c) */
+typedef struct { int M, D, L, lg2, has3; int16_t *h; int32_t *tw2, *rot; int32_t s3; int16_t *hist; long long n_done; } m17o_chan;
+m17o_chan *m17o_chan_open(int M, int D, int L, const int16_t *taps);
+void m17o_chan_free(m17o_chan *c);
+void m17o_chan_run(m17o_chan *c, const int16_t *in, long nout, int16_t *out, long out_pitch);   /* in [D*nout][2] -> out [M][out_pitch][2] */
+
 #endif

@@ -227,6 +227,24 @@ class Port:
         self.L.m17o_gps_decode(_p(b), _p(ll), _p(o))
         return (float(ll[0]), float(ll[1]), int(o[0]), int(o[1]), int(o[2]), int(o[3]))
 
+    def chan_run(self, x, M, D, taps, parts=None):
+        """wideband channeliser: x int16 [nin][2] (nin a multiple of D) -> int16 [M][nin // D][2]; parts = output counts of
+        successive calls (history carried)"""
+        x = np.ascontiguousarray(x, np.int16); taps = np.ascontiguousarray(taps, np.int16)
+        self.L.m17o_chan_open.restype = C.c_void_p
+        h = self.L.m17o_chan_open(M, D, len(taps), _p(taps))
+        assert h, "unsupported channeliser geometry"
+        nout = x.shape[0] // D
+        out = np.zeros((M, nout, 2), np.int16)
+        o = 0
+        for n in (parts or [nout]):
+            y = np.zeros((M, n, 2), np.int16)
+            self.L.m17o_chan_run(C.c_void_p(h), _p(np.ascontiguousarray(x[o * D:(o + n) * D])), C.c_long(n), _p(y), C.c_long(n))
+            out[:, o:o + n] = y
+            o += n
+        self.L.m17o_chan_free(C.c_void_p(h))
+        return out
+
     def demap_symbol(self, sym, mag):
         """m17_dsp_demap_symbol for arrays of symbols / normalisers -> [n][2]"""
         sym = np.ascontiguousarray(sym, np.float32); mag = np.ascontiguousarray(mag, np.float32)

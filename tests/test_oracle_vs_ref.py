@@ -142,3 +142,25 @@ def test_prbs9_rx_checker(port):
         L.refp_state(_p(st))
         got = port.prbs_check(np.concatenate(cases[:k + 1]))      # a fresh restatement fed the same history
         assert np.array_equal(got[:6], st), (k, got, st)
+
+
+def test_channelizer_oracle_pinned_at_the_decimator_point(port):
+    """The wideband channeliser's restatement (m17o_chan_run) at M = 1, D = 8 with the reference's own 31 taps IS the Pluto
+    decimator of radio.cpp:18-40,157-177 -- compared with the reference object itself, in one call and in ragged calls."""
+    from m17_oracles import RefRadio
+    import pytest
+    if not RefRadio.available():
+        pytest.skip("oracle/_ref not built")
+    RR = RefRadio()
+    rng = np.random.default_rng(105)
+    X = rng.integers(-32768, 32768, (2, 3 * 8 * 1920, 2)).astype(np.int16)
+    X[1, :9000] = 32767; X[1, 9000:20000, 1] = -32768
+    ref = RR.pluto_run(X)
+    taps = port.dec_taps()
+    for c in range(2):
+        assert np.array_equal(port.chan_run(X[c], 1, 8, taps), ref[c][None])
+        assert np.array_equal(port.chan_run(X[c], 1, 8, taps, parts=[240, 1, 999, 4520]), ref[c][None])
+    # and the 96-channel form is self-consistent across call boundaries (history + window phase)
+    h = (np.hamming(96 * 4) * 600).astype(np.int16)
+    Y = rng.integers(-20000, 20000, (25 * 90, 2)).astype(np.int16)
+    assert np.array_equal(port.chan_run(Y, 96, 25, h), port.chan_run(Y, 96, 25, h, parts=[1, 30, 59]))
