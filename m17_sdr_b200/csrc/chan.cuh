@@ -2,8 +2,8 @@
 // 1.2 MS/s (= 25 x 48 kS/s) -> 96 channels spaced 12.5 kHz, each at 48 kS/s int16 IQ, laid out as m17b_dsp_rx wants them.
 // It generalises the reference's Pluto receive decimator (sub_filter / rx_decimate_filter, radio.cpp:18-40: int16 taps, int32
 // accumulate, >> 15) from one channel to M: the same integer FIR folded into M = 96 polyphase branches, a 96-point DFT in
-// fixed point (prime-factor split 3 x 32, radix-2 decimation in time, Q31 twiddles, products (int64 a*w) >> 31, twiddles 1 and
-// -j exact), the phase of the sliding window, the reference's >> 15.  Integer arithmetic throughout, so the output is a
+// fixed point (prime-factor split 3 x 32, radix-2 decimation in time, Q30 twiddles, products (int64 a*w) >> 30, so the twiddles
+// 1 and -j act exactly), the phase of the sliding window, the reference's >> 15.  Integer arithmetic throughout, so the output is a
 // well-defined function of the input: oracle/m17_oracle.c (m17o_chan_run) states it in plain C -- pinned at M = 1, D = 8 against
 // radio.cpp itself -- and the kernel below must equal it bit for bit (tests).
 //
@@ -37,7 +37,7 @@ struct m17b_chan {
     int16_t h_taps[CH_M * CH_PMAX];
 };
 
-__device__ __forceinline__ int32_t chq_mul(int32_t a, int32_t w) { return (int32_t)(((long long)a * (long long)w) >> 31); }
+__device__ __forceinline__ int32_t chq_mul(int32_t a, int32_t w) { return (int32_t)(((long long)a * (long long)w) >> 30); }   // Q30 twiddles: +-1.0 exact
 __device__ __forceinline__ void chq_cmul(int32_t ar, int32_t ai, int32_t wr, int32_t wi, int32_t &or_, int32_t &oi) {
     or_ = chq_mul(ar, wr) - chq_mul(ai, wi);
     oi = chq_mul(ar, wi) + chq_mul(ai, wr);
@@ -107,16 +107,13 @@ __global__ void __launch_bounds__(CH_THREADS) k_chan96(const uint32_t *__restric
             const bool lower = (lane & half) != 0;
             const int ti = (lane & (half - 1)) * (16 / half);               // twiddle index j * (32 / m), m = 2 half
             const int32_t wr = tw_s[ti][0], wi = tw_s[ti][1];
+            const bool mj = ti == 8;                                        // W = -j (the only other twiddle of stage 2)
 #pragma unroll
             for (int a = 0; a < 3; a++) {
                 int32_t xr, xi;
-                if (half <= 2) {                                          // stages 1 and 2 only see W = 1 and W = -j
-                    if (ti == 0) { xr = br[a]; xi = bi[a]; } else { xr = bi[a]; xi = -br[a]; }
-                } else {
-                    chq_cmul(br[a], bi[a], wr, wi, xr, xi);
-                    if (ti == 0) { xr = br[a]; xi = bi[a]; }
-                    if (ti == 8) { xr = bi[a]; xi = -br[a]; }
-                }
+                if (half == 1) { xr = br[a]; xi = bi[a]; }                                    // W = 1
+                else if (half == 2) { xr = mj ? bi[a] : br[a]; xi = mj ? -br[a] : bi[a]; }    // W = 1 or -j: what the Q30 product gives, without the multiply
+                else chq_cmul(br[a], bi[a], wr, wi, xr, xi);
                 const int32_t sr = lower ? xr : br[a], si = lower ? xi : bi[a];
                 const int32_t rr = __shfl_xor_sync(0xffffffffu, sr, half), ri = __shfl_xor_sync(0xffffffffu, si, half);
                 br[a] = lower ? rr - xr : br[a] + rr;
@@ -131,8 +128,7 @@ __global__ void __launch_bounds__(CH_THREADS) k_chan96(const uint32_t *__restric
             const int k = (64 * a + 33 * lane) % CH_M;
             const int r = (k * (int)i0) % CH_M;
             int32_t yr, yi;
-            chq_cmul(br[a], bi[a], rot_s[r][0], rot_s[r][1], yr, yi);
-            if (r == 0) { yr = br[a]; yi = bi[a]; }
+            chq_cmul(br[a], bi[a], rot_s[r][0], rot_s[r][1], yr, yi);                  // r = 0: the identity, exactly (Q30)
             outs[k][t] = ((uint32_t)(yr >> 15) & 0xFFFFu) | ((uint32_t)(yi >> 15) << 16);
         }
     }
@@ -165,7 +161,7 @@ extern "C" int m17b_chan_reset(m17b_chan *c, void *stream) {
     c->n_done = 0;
     return M17B_OK;
 }
-static int32_t chan_q31(double v) { double s = v * 2147483648.0; s = s < 0 ? s - 0.5 : s + 0.5; if (s > 2147483647.0) s = 2147483647.0; if (s < -2147483648.0) s = -2147483648.0; return (int32_t)s; }
+static int32_t chan_q31(double v) { double s = v * 1073741824.0; s = s < 0 ? s - 0.5 : s + 0.5; return (int32_t)s; }      // Q30 (the name is historical)
 extern "C" int m17b_chan_create(m17b_ctx *ctx, int64_t ncap, int taps_per_branch, m17b_chan **out) {
     if (!ctx || !out || ncap <= 0 || (taps_per_branch != 4 && taps_per_branch != 8 && taps_per_branch != 12 && taps_per_branch != 16)) return M17B_E_ARG;
     *out = nullptr;

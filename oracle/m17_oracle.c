@@ -838,16 +838,16 @@ double m17o_rx_time(const int16_t *iq, long C, long T, int nthreads) {
      window of output n   : x[nD - L + i], i = 0..L-1          (the reference's window for M = 1, D = 8, L = 31)
      fold                 : z[p] = sum_q h[p + qM] * x[nD - L + p + qM]                      (int32, wraps like the reference)
      DFT                  : Z[k] = sum_p z[p] e^{-j 2 pi k p / M}, M = 2^b or 3 * 2^b: prime-factor split 3 x 2^b (no twiddles
-                            between the parts), radix-2 decimation in time; twiddles are Q31 integers, a product is
-                            (int64 a * w) >> 31 per real multiply, twiddles 1 and -j are exact (no multiply)
-     phase of the window  : Y[k] = Z[k] * e^{-j 2 pi k (nD - L) / M}   (Q31 table, index 0 exact)
+                            between the parts), radix-2 decimation in time; twiddles are Q30 integers (+-1 exact), a product is
+                            (int64 a * w) >> 30 per real multiply, so the twiddles 1 and -j act exactly
+     phase of the window  : Y[k] = Z[k] * e^{-j 2 pi k (nD - L) / M}   (Q30 table, index 0 = the identity)
      output               : y[k][n] = (int16)(Y[k] >> 15)                                   (the reference's scaling)
    For M = 1 every step but the fold and the shift is the identity: the output IS radio.cpp's decimator (pinned in
    tests/test_oracle_vs_ref.py with the reference's own taps).  TEST INFRASTRUCTURE ONLY. */
-static int32_t chq_mul(int32_t a, int32_t w) { return (int32_t)(((int64_t)a * (int64_t)w) >> 31); }
+static int32_t chq_mul(int32_t a, int32_t w) { return (int32_t)(((int64_t)a * (int64_t)w) >> 30); }
 static int32_t chq_add(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
 static int32_t chq_sub(int32_t a, int32_t b) { return (int32_t)((uint32_t)a - (uint32_t)b); }
-static int32_t chq_tw(double v) { double s = v * 2147483648.0; s = s < 0 ? s - 0.5 : s + 0.5; if (s > 2147483647.0) s = 2147483647.0; if (s < -2147483648.0) s = -2147483648.0; return (int32_t)s; }
+static int32_t chq_tw(double v) { double s = v * 1073741824.0; s = s < 0 ? s - 0.5 : s + 0.5; return (int32_t)s; }    /* Q30: 1.0 and -1.0 are exact */
 static void chq_cmul(int32_t ar, int32_t ai, int32_t wr, int32_t wi, int32_t *or_, int32_t *oi) {
     *or_ = chq_sub(chq_mul(ar, wr), chq_mul(ai, wi));
     *oi = chq_add(chq_mul(ar, wi), chq_mul(ai, wr));
@@ -881,9 +881,7 @@ static void chq_fft2(const m17o_chan *c, int32_t *re, int32_t *im) {
             for (int j = 0; j < m / 2; j++) {
                 const int ti_ = j * (N / m);                       /* twiddle index of W_N^(j N / m) */
                 int32_t vr = tr[k + j + m / 2], vi = ti[k + j + m / 2], xr, xi;
-                if (ti_ == 0) { xr = vr; xi = vi; }                                   /* W = 1 */
-                else if (4 * ti_ == N) { xr = vi; xi = chq_sub(0, vr); }              /* W = -j */
-                else chq_cmul(vr, vi, c->tw2[2 * ti_], c->tw2[2 * ti_ + 1], &xr, &xi);
+                chq_cmul(vr, vi, c->tw2[2 * ti_], c->tw2[2 * ti_ + 1], &xr, &xi);   /* (W = 1 and W = -j are exact in Q30) */
                 const int32_t ur = tr[k + j], ui = ti[k + j];
                 tr[k + j] = chq_add(ur, xr); ti[k + j] = chq_add(ui, xi);
                 tr[k + j + m / 2] = chq_sub(ur, xr); ti[k + j + m / 2] = chq_sub(ui, xi);
@@ -939,7 +937,7 @@ void m17o_chan_run(m17o_chan *c, const int16_t *in, long nout, int16_t *out, lon
         for (int k = 0; k < M; k++) {
             long long r = ((long long)k * (i0 % M)) % M; if (r < 0) r += M;
             int32_t yr, yi;
-            if (r == 0) { yr = Zr[k]; yi = Zi[k]; } else chq_cmul(Zr[k], Zi[k], c->rot[2 * r], c->rot[2 * r + 1], &yr, &yi);
+            chq_cmul(Zr[k], Zi[k], c->rot[2 * r], c->rot[2 * r + 1], &yr, &yi);     /* r = 0: exactly the identity (Q30) */
             out[2 * ((long)k * out_pitch + n)] = (int16_t)(yr >> 15);
             out[2 * ((long)k * out_pitch + n) + 1] = (int16_t)(yi >> 15);
         }
