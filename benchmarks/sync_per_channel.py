@@ -12,7 +12,8 @@ torch.cuda.synchronize()
 d = rx.debug_sync().cpu().numpy()
 res = rx.results()
 fr = res["stats"]
-for k, name in enumerate(("22 dB", "24 dB", "26 dB", "30 dB", "clean")):
+NAMES = tuple("clean" if e is None else f"{e:g} dB" for e in bench.EBN0_SWEEP)
+for k, name in enumerate(NAMES):
     cyc = d[k::5, 0] / 1e6; rnd = d[k::5, 1]
     print(f"{name}: Mcycles min/med/max {cyc.min():.2f}/{np.median(cyc):.2f}/{cyc.max():.2f}  rounds med/max {int(np.median(rnd))}/{int(rnd.max())}  frames med {int(np.median(fr[k::5, 0]))} los max {int(fr[k::5, 5].max())}")
 if os.environ.get("M17B_SYNC_IMPL") == "64" and d[:, 2:8].sum() > 0:
@@ -23,7 +24,7 @@ if os.environ.get("M17B_SYNC_IMPL") == "65":
     full, part, miss, unl = rr & 255, (rr >> 8) & 255, (rr >> 16) & 255, (rr >> 24) & 255
     print("blocks of the reporting warp (every second block): predicted + no trip", int(full.sum()), " predicted + trip", int(part.sum()),
           " mispredicted while locked", int(miss.sum()), " unlocked", int(unl.sum()))
-    for k, name in enumerate(("22 dB", "24 dB", "26 dB", "30 dB", "clean")):
+    for k, name in enumerate(NAMES):
         print(f"  {name}: median per channel full/trip/miss/unlocked {int(np.median(full[k::5]))}/{int(np.median(part[k::5]))}/{int(np.median(miss[k::5]))}/{int(np.median(unl[k::5]))}")
 if os.environ.get("M17B_SYNC_IMPL") == "65" and d[:, 2:8].sum() > 0:
     # the warp that ran the channel's last block reports its own clocks: it handled every second block

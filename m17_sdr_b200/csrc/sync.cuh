@@ -25,6 +25,7 @@
 #endif
 #define SY_XQ   106           // (30 + 384 + 2 + 8 pad) / 4 entries per residue class
 #define SY_HIST  (8 + 208)
+#define SY_RECQ  32            // record queue per channel; a block completes at most 2 frames, flushed above SY_RECQ - 3
 
 struct SyncWarpSmem {
     float x[4][SY_XQ];                  // discriminator samples incl. 30 of history: sample n lives at x[n & 3][n >> 2], so the
@@ -32,6 +33,8 @@ struct SyncWarpSmem {
     float hist[SY_HIST];                // [0,8): sliding sync window carried in; [8, 8+n): symbols emitted in this block
     float head[8];                      // m_f_sym[0..7] of the frame being collected
     float pre[2][384 + 4];              // cp.async landing zone for the NEXT block's raw samples (+ its mean), double buffered
+    uint4 rec[SY_RECQ];                 // completed frames whose records are not written yet: (sym_off, type | flags << 8 | votes << 16 |
+                                        // frame_errors << 24, spread, max) -- see flush_records
 };
 
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
@@ -148,6 +151,36 @@ __global__ void __launch_bounds__(SY_WARPS * 32, AFC ? 1 : 2) k_sync_frame(const
     if (lane == 0 && t0 == 0) sym_base[c] = base_g;
     int nfr = t0 == 0 ? 0 : nframes[c], nev = t0 == 0 ? 0 : nevents[c], n_aos = 0, n_los = 0;
     const int nfr_entry = nfr;
+    // Records are queued, not written, where the frame completes: the serial path per block keeps only what the next block's
+    // decisions need (lock, error count, frame clock).  The queue is drained 30 frames at a time with the lanes in parallel --
+    // the variance quotient (an IEEE divide) once per lane instead of once per block, the 64-byte record headers two per store.
+    int nq = 0, nfr_out = nfr;
+    auto push_record = [&](int type, int flags, int votes, int fe, float spread, float vmax) {
+        if (lane == 0) sm.rec[nq] = make_uint4((uint32_t)frame_start, (uint32_t)type | ((uint32_t)flags << 8) | ((uint32_t)votes << 16) | ((uint32_t)fe << 24),
+                                               __float_as_uint(spread), __float_as_uint(vmax));
+        nq++; nfr++;
+    };
+    auto flush_records = [&]() {
+        __syncwarp();
+        if (lane < nq) {
+            const uint4 e = sm.rec[lane];
+            ((uint32_t *)&sm.rec[lane])[2] = __float_as_uint(sync_variance_of(__uint_as_float(e.z), __uint_as_float(e.w)));
+        }
+        __syncwarp();
+        // words of m17b_frame_rec: 0 = sym_off, 1 = type | flags << 8 (golay_err, nbytes zero), 11 = votes << 16 | frame_errors << 24
+        // (crc zero), 12 = variance; the rest zero until the decoder fills them
+        const int wi = lane & 15;
+        const int slot = wi == 0 ? 0 : (wi == 1 || wi == 11) ? 1 : wi == 12 ? 2 : -1;
+        const uint32_t msk = wi == 1 ? 0x0000FFFFu : wi == 11 ? 0xFFFF0000u : 0xFFFFFFFFu;
+        uint32_t *dst = (uint32_t *)(frames + c * fcap + nfr_out);
+        for (int f = lane >> 4; f < nq; f += 2) {
+            const uint32_t v = slot >= 0 ? (((const uint32_t *)&sm.rec[f])[slot] & msk) : 0u;
+            if (nfr_out + f < fcap) dst[16 * f + wi] = v;
+        }
+        nfr_out += nq; nq = 0;
+        __syncwarp();
+    };
+    int nsym_keep = 0;                      // lane l: symbol count of block t0 + 32 k + l, stored 32 blocks at a time
     f32x2 tp[M17B_FN];                      // (matched, derivative) tap pairs of the current polyphase branch
     int tap_index = -1, trips_prev = 0;
     __syncwarp();
@@ -367,12 +400,16 @@ __global__ void __launch_bounds__(SY_WARPS * 32, AFC ? 1 : 2) k_sync_frame(const
             } else {
                 for (int q = lane; q < n; q += 32) dst[q] = out[q];
             }
-            if (lane == 0) nsym[c * T + t] = n;
+            const int tl = (int)(t - t0) & 31;
+            if (lane == tl) nsym_keep = n;
+            if (tl == 31 || t + 1 == t1) { if (lane <= tl) nsym[c * T + (t - tl) + lane] = nsym_keep; }
         }
 
         PHASE(2);
         // ---- framer (m17_rx_frame.cpp:126-172)
         int p = 0, reset_at = -8;
+        bool have_bits = false;
+        unsigned negw[7], posw[7];
         if (flock && fclk + n >= M17B_FRAME_SYMS && fclk + n < 2 * M17B_FRAME_SYMS) {
             // The common case while locked, straight-line: the frame being collected completes inside this block (after p1 of its
             // symbols) and the next one takes the rest.  Same steps as the general loop below (m17_rx_frame.cpp:126-157).
@@ -388,15 +425,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32, AFC ? 1 : 2) k_sync_frame(const
             else if (ok) { flags |= M17B_F_PARSED; ferr = 0; fe = 0; }                 // :144-146
             else { ferr++; fe = ferr; if (ferr > 5) los = true; else flags |= M17B_F_PARSED; }   // :147-154
             if (los) flags |= M17B_F_LOS;
-            if (nfr < fcap && lane < 16) {
-                uint32_t word = 0;
-                if (lane == 0) word = (uint32_t)frame_start;
-                else if (lane == 1) word = (uint32_t)r.type | ((uint32_t)flags << 8);
-                else if (lane == 11) word = ((uint32_t)r.votes << 16) | ((uint32_t)fe << 24);
-                else if (lane == 12) word = __float_as_uint(sync_variance_of(r.spread, r.vmax));
-                ((uint32_t *)(frames + c * fcap + nfr))[lane] = word;
-            }
-            nfr++;
+            push_record(r.type, flags, r.votes, fe, r.spread, r.vmax);
             const int fclk_in = fclk;
             fclk = 0;
             p = p1;
@@ -418,18 +447,46 @@ __global__ void __launch_bounds__(SY_WARPS * 32, AFC ? 1 : 2) k_sync_frame(const
         }
         while (p < n) {
             if (!flock) {
+                // Unlocked search (m17_rx_frame.cpp:158-170): acceptance needs the window's sign pattern to BE one of the four frame sync
+                // words (sync_unlocked_ok, fec.cuh), so the signs of the block's symbols are taken once -- 7 x 2 ballots give the
+                // 8 + n sign bits to every lane -- and the window ending at symbol q is 8 consecutive bits of that string.  All
+                // positions of the block are screened with a few integer operations each; the variance test runs only on the
+                // (rare) windows whose signs match.
+                if (!have_bits) {
+#pragma unroll
+                    for (int k = 0; k < 7; k++) {
+                        const int idx = lane + 32 * k;
+                        const float v = idx < 8 + n ? sm.hist[idx] : 0.0f;
+                        negw[k] = __ballot_sync(0xffffffffu, v < 0);
+                        posw[k] = __ballot_sync(0xffffffffu, v > 0);
+                    }
+                    have_bits = true;
+                }
+                unsigned mine = 0, cm = 0;                                     // windows end at q = 32 k + lane - 1 (bits q + 1 .. q + 8)
+#pragma unroll
+                for (int k = 0; k < 7; k++) {
+                    const int q = 32 * k + lane - 1;
+                    const unsigned ng = __funnelshift_r(negw[k], k < 6 ? negw[k + 1] : 0u, lane) & 0xFFu;
+                    const unsigned ps = __funnelshift_r(posw[k], k < 6 ? posw[k + 1] : 0u, lane) & 0xFFu;
+                    const bool cnd = q >= p && q < n && q - 7 >= reset_at && (ng | ps) == 0xFFu &&
+                                     (ng == sync_neg_mask(1) || ng == sync_neg_mask(2) || ng == sync_neg_mask(3) || ng == sync_neg_mask(4));
+                    const unsigned b = __ballot_sync(0xffffffffu, cnd);
+                    mine |= cnd ? (1u << k) : 0u;
+                    cm |= b ? (1u << k) : 0u;
+                }
                 int found = -1;
-                for (int q0 = p; q0 < n && found < 0; q0 += 32) {
-                    const int q = q0 + lane;
+                while (cm && found < 0) {
+                    const int k = __ffs(cm) - 1;
+                    cm &= cm - 1;
                     bool ok = false;
-                    if (q < n) {
+                    if ((mine >> k) & 1u) {
                         float w[8];
 #pragma unroll
-                        for (int k = 0; k < 8; k++) { int idx = q - 7 + k; w[k] = (idx >= reset_at) ? sm.hist[8 + idx] : 0.0f; }
-                        ok = sync_unlocked_ok(w);
+                        for (int j = 0; j < 8; j++) w[j] = sm.hist[32 * k + lane + j];                 // hist[8 + q - 7 + j]
+                        ok = sync_variance_lt(w, 0.3);
                     }
                     const unsigned m = __ballot_sync(0xffffffffu, ok);
-                    if (m) found = q0 + __ffs(m) - 1;
+                    if (m) found = 32 * k + __ffs(m) - 2;
                 }
                 if (found < 0) { p = n; break; }
                 // acquisition: copy_sync(), m_fclk = 8 (m17_rx_frame.cpp:161-169)
@@ -452,7 +509,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32, AFC ? 1 : 2) k_sync_frame(const
                     float w[8];
 #pragma unroll
                     for (int k = 0; k < 8; k++) w[k] = sm.head[k];
-                    const SyncResult r = sync_check8(w);
+                    const SyncResult r = sync_check8<true>(w);
                     const bool ok = sync_accept(r, true);
                     int flags = ok ? M17B_F_SYNC_OK : 0, fe;
                     bool los = false;
@@ -460,15 +517,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32, AFC ? 1 : 2) k_sync_frame(const
                     else if (ok) { flags |= M17B_F_PARSED; ferr = 0; fe = 0; }                 // :144-146
                     else { ferr++; fe = ferr; if (ferr > 5) los = true; else flags |= M17B_F_PARSED; }   // :147-154
                     if (los) flags |= M17B_F_LOS;
-                    if (nfr < fcap && lane < 16) {
-                        uint32_t word = 0;
-                        if (lane == 0) word = (uint32_t)frame_start;
-                        else if (lane == 1) word = (uint32_t)r.type | ((uint32_t)flags << 8);
-                        else if (lane == 11) word = ((uint32_t)r.votes << 16) | ((uint32_t)fe << 24);
-                        else if (lane == 12) word = __float_as_uint(r.variance);
-                        ((uint32_t *)(frames + c * fcap + nfr))[lane] = word;
-                    }
-                    nfr++;
+                    push_record(r.type, flags, r.votes, fe, r.spread, r.vmax);
                     if (los) {
                         flock = 0;
                         reset_at = p;                                                           // reset_sync(): window reads as zeros
@@ -491,9 +540,11 @@ __global__ void __launch_bounds__(SY_WARPS * 32, AFC ? 1 : 2) k_sync_frame(const
             if (lane < 30) sm.x[lane & 3][lane >> 2] = a;
         }
         sym_total += n;
+        if (nq > SY_RECQ - 3) flush_records();
         __syncwarp();
         PHASE(4);
     }
+    flush_records();
 
     // ---- store state
     if (AFC && lane == 0) {
