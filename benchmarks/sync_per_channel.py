@@ -30,11 +30,19 @@ if os.environ.get("M17B_SYNC_IMPL") == "65" and d[:, 2:8].sum() > 0:
     # the warp that ran the channel's last block reports its own clocks: it handled every second block
     for j, name in enumerate(("staging", "speculative dot products + votes", "wait for the hand-off", "resolve: trip test / commit / fallback rounds", "emission + framer", "hand-off")):
         print(f"phase {name}: median {np.median(d[:, 2 + j]) / (T / 2):.0f} cycles per own block")
+elif d[:, 7].sum() > 0:
+    # -DM17B_PHASE_UNLOCKED: phases accumulated over the blocks a channel entered unlocked only (count in slot 5)
+    nb = d[:, 7].astype(float)
+    sel = nb >= 20
+    print(f"blocks entered unlocked: total {int(nb.sum())}, channels with >= 20: {int(sel.sum())}")
+    for j, name in enumerate(("staging", "timing loop", "emission", "framer", "carry")):
+        print(f"unlocked-block phase {name}: median over those channels {np.median(d[sel, 2 + j] / nb[sel]):.0f} cycles/block")
+    print(f"unlocked block total: median {np.median(d[sel, 2:7].sum(1) / nb[sel]):.0f} cycles/block")
 elif d[:, 2:7].sum() > 0:
     tot = d[:, 0].astype(float)
     for j, name in enumerate(("staging", "timing loop", "emission", "framer", "carry")):
         print(f"phase {name}: median {np.median(d[:, 2 + j]) / T:.0f} cycles/block ({100 * np.median(d[:, 2 + j] / tot):.0f} %)")
 w = int(np.argmax(d[:, 0]))
-if os.environ.get("M17B_SYNC_IMPL", "0") in ("0", "") and d[:, 2:7].sum() > 0:
+if os.environ.get("M17B_SYNC_IMPL", "0") in ("0", "") and d[:, 2:7].sum() > 0 and d[:, 7].sum() == 0:
     print("slowest channel, cycles per block by phase:", {name: int(d[w, 2 + j] / T) for j, name in enumerate(("staging", "timing loop", "emission", "framer", "carry"))})
 print("slowest channel", w, "class", w % 5, "Mcycles", d[w, 0] / 1e6, "rounds", d[w, 1], "frames", fr[w, 0], "aos", fr[w, 4], "los", fr[w, 5])

@@ -279,6 +279,15 @@ __device__ __forceinline__ bool sync_variance_lt(const float *v, double limit) {
     // a float, so the comparison in float with the rounded limit decides identically
     return var < (float)limit;
 }
+// find_variance < 0.3 (the unlocked limit) without the divide: fl(d / m) < 0.3f <=> d / m < MID, the midpoint of 0.3f = 0x3E99999A and
+// its predecessor (a tie rounds to the even 0.3f, which is not below the limit) <=> d < MID * m, and that product of a 25-bit and
+// a 24-bit number is exact in double.  m = 0 or NaN: the reference's NaN -> 1.0 is not below the limit, the comparison is false too.
+__device__ __forceinline__ bool sync_variance_lt03(const float *v) {
+    float mn = fabsf(v[0]), mx = mn;
+#pragma unroll
+    for (int i = 1; i < 8; i++) { float a = fabsf(v[i]); if (a > mx) mx = a; else if (a < mn) mn = a; }
+    return (double)(mx - mn) < 0x1.333333p-2 * (double)mx;
+}
 // variance < 0.5 (the locked limit) without waiting for the quotient: for floats d, m > 0 (m not subnormal), fl(d / m) < 0.5
 // <=> d < 0.5 m: any float d below 0.5 m is at least one ulp below it, so d / m <= 0.5 - 2^-25 and rounds below 0.5; d >= 0.5 m
 // gives a quotient >= 0.5.  m = 0 or NaN: the reference's variance is NaN -> 1.0 -> not below 0.5, and the comparison is false too.

@@ -121,7 +121,9 @@ __global__ void __launch_bounds__(SY_WARPS * 32, AFC ? 1 : 2) k_sync_frame(const
     unsigned dbg_rounds = 0;
 #ifdef M17B_PHASE_CLOCKS
     long long ph[5] = {0, 0, 0, 0, 0}, pt = clk_start;
-#define PHASE(i) do { const long long now__ = clock64(); ph[i] += now__ - pt; pt = now__; } while (0)
+    bool ph_on = true;
+    long long ph_blocks = 0;
+#define PHASE(i) do { const long long now__ = clock64(); if (ph_on) ph[i] += now__ - pt; pt = now__; } while (0)
 #else
 #define PHASE(i) do {} while (0)
 #endif
@@ -214,6 +216,9 @@ __global__ void __launch_bounds__(SY_WARPS * 32, AFC ? 1 : 2) k_sync_frame(const
     for (int64_t t = t0; t < t1; t++) {
         // ---- stage the block's 384 discriminator samples behind the 30 of history
         const int buf = (int)((t - t0) & 1);
+#ifdef M17B_PHASE_UNLOCKED
+        ph_on = !flock; ph_blocks += ph_on;                         // profile the blocks entered unlocked only
+#endif
         if (AFC) afc_block(*afc_sm, iq + (c * T + t) * M17B_BLOCK_SAMPLES, lane, flock, disc_count, afc_delta, nco_acc, sm.pre[buf], &sm.pre[buf][384],
                            disc_out + (c * T + t) * M17B_DISC_PER_BLOCK, mean_out + c * T + t);
         else asm volatile("cp.async.wait_group 0;");
@@ -282,8 +287,12 @@ __global__ void __launch_bounds__(SY_WARPS * 32, AFC ? 1 : 2) k_sync_frame(const
                     run += v;
                     pmax = max(pmax, run); pmin = min(pmin, run);
                 }
-                const int incl = warp_incl_scan(run, lane);
-                const int off = thr + incl - run;
+                // exclusive prefix of the lanes' sums without a shuffle chain: run + 6 is a 4-bit number, one ballot per bit
+                const unsigned e6 = (unsigned)(run + 6);
+                const unsigned q0 = __ballot_sync(0xffffffffu, e6 & 1u), q1 = __ballot_sync(0xffffffffu, e6 & 2u);
+                const unsigned q2 = __ballot_sync(0xffffffffu, e6 & 4u), q3 = __ballot_sync(0xffffffffu, e6 & 8u);
+                const unsigned lt = (1u << lane) - 1u;
+                const int off = thr + __popc(q0 & lt) + 2 * __popc(q1 & lt) + 4 * __popc(q2 & lt) + 8 * __popc(q3 & lt) - 6 * lane;
                 int fm = 6;                                                    // first symbol of this lane whose vote trips
                 int th6[6];
                 if (__any_sync(0xffffffffu, off + pmax > TH || off + pmin < -TH)) {
@@ -296,16 +305,15 @@ __global__ void __launch_bounds__(SY_WARPS * 32, AFC ? 1 : 2) k_sync_frame(const
                         if ((j + 1 < 384) && (th6[m] > TH || th6[m] < -TH)) fm = m;
                     }
                 } else {
-                    th6[5] = off + run;
 #pragma unroll
-                    for (int m = 0; m < 5; m++) th6[m] = 0;
+                    for (int m = 0; m < 6; m++) th6[m] = 0;
                 }
                 const unsigned trip = __ballot_sync(0xffffffffu, fm < 6);
                 if (!trip) {
 #pragma unroll
                     for (int m = 0; m < 6; m++) if (m_idx + 6 * lane + m >= 0) out[m_idx + 6 * lane + m] = s6[m];
                     m_idx += 192;
-                    thr = __shfl_sync(0xffffffffu, th6[5], 31);
+                    thr = thr + __popc(q0) + 2 * __popc(q1) + 4 * __popc(q2) + 8 * __popc(q3) - 192;
                     sumc = __shfl_sync(0xffffffffu, s6[5], 31);
                     difc = __shfl_sync(0xffffffffu, d6[5], 31);
                     if (i == 0) clk = 0; else clk = 1;                         // last symbol at sample 382 (vote at 383) / 383 (vote in the next block)
@@ -349,8 +357,10 @@ __global__ void __launch_bounds__(SY_WARPS * 32, AFC ? 1 : 2) k_sync_frame(const
             int va = 0, vb = 0;
             if (vote_a) { float dd = (sa < 0) ? -da : da; va = (dd > 0) - (dd < 0); }
             if (vote_b) { float dd = (sb < 0) ? -db : db; vb = (dd > 0) - (dd < 0); }
-            const int incl = warp_incl_scan(va + vb, lane);
-            const int th_b = thr + incl, th_a = th_b - vb;
+            const unsigned e2 = (unsigned)(va + vb + 2);                       // 0..4: inclusive prefix from one ballot per bit
+            const unsigned r0 = __ballot_sync(0xffffffffu, e2 & 1u), r1 = __ballot_sync(0xffffffffu, e2 & 2u), r2 = __ballot_sync(0xffffffffu, e2 & 4u);
+            const unsigned le = 0xffffffffu >> (31 - lane);
+            const int th_b = thr + __popc(r0 & le) + 2 * __popc(r1 & le) + 4 * __popc(r2 & le) - 2 * (lane + 1), th_a = th_b - vb;
             const unsigned ta = __ballot_sync(0xffffffffu, vote_a && (th_a > TH || th_a < -TH));
             const unsigned tb = __ballot_sync(0xffffffffu, vote_b && (th_b > TH || th_b < -TH));
             const int pa = ta ? 2 * (__ffs(ta) - 1) : 1 << 20, pb = tb ? 2 * (__ffs(tb) - 1) + 1 : 1 << 20;
@@ -462,7 +472,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32, AFC ? 1 : 2) k_sync_frame(const
                     }
                     have_bits = true;
                 }
-                unsigned mine = 0, cm = 0;                                     // windows end at q = 32 k + lane - 1 (bits q + 1 .. q + 8)
+                unsigned mine = 0;                                     // windows end at q = 32 k + lane - 1 (bits q + 1 .. q + 8)
 #pragma unroll
                 for (int k = 0; k < 7; k++) {
                     const int q = 32 * k + lane - 1;
@@ -470,24 +480,24 @@ __global__ void __launch_bounds__(SY_WARPS * 32, AFC ? 1 : 2) k_sync_frame(const
                     const unsigned ps = __funnelshift_r(posw[k], k < 6 ? posw[k + 1] : 0u, lane) & 0xFFu;
                     const bool cnd = q >= p && q < n && q - 7 >= reset_at && (ng | ps) == 0xFFu &&
                                      (ng == sync_neg_mask(1) || ng == sync_neg_mask(2) || ng == sync_neg_mask(3) || ng == sync_neg_mask(4));
-                    const unsigned b = __ballot_sync(0xffffffffu, cnd);
                     mine |= cnd ? (1u << k) : 0u;
-                    cm |= b ? (1u << k) : 0u;
                 }
-                int found = -1;
-                while (cm && found < 0) {
-                    const int k = __ffs(cm) - 1;
-                    cm &= cm - 1;
-                    bool ok = false;
-                    if ((mine >> k) & 1u) {
-                        float w[8];
+                // every lane tests its own candidates (ascending q; nearly always at most one per lane), the earliest accepted wins
+                int myq = 1 << 20;
+                while (__any_sync(0xffffffffu, mine != 0u)) {
+                    if (mine) {
+                        const int k = __ffs(mine) - 1;
+                        mine &= mine - 1;
+                        if (myq == (1 << 20)) {
+                            float w[8];
 #pragma unroll
-                        for (int j = 0; j < 8; j++) w[j] = sm.hist[32 * k + lane + j];                 // hist[8 + q - 7 + j]
-                        ok = sync_variance_lt(w, 0.3);
+                            for (int j = 0; j < 8; j++) w[j] = sm.hist[32 * k + lane + j];             // hist[8 + q - 7 + j]
+                            if (sync_variance_lt03(w)) myq = 32 * k + lane - 1;
+                        }
                     }
-                    const unsigned m = __ballot_sync(0xffffffffu, ok);
-                    if (m) found = 32 * k + __ffs(m) - 2;
                 }
+                const int fq = __reduce_min_sync(0xffffffffu, myq);
+                const int found = fq < (1 << 20) ? fq : -1;
                 if (found < 0) { p = n; break; }
                 // acquisition: copy_sync(), m_fclk = 8 (m17_rx_frame.cpp:161-169)
                 if (lane < 8) { int idx = found - 7 + lane; sm.head[lane] = (idx >= reset_at) ? sm.hist[8 + idx] : 0.0f; }
@@ -561,6 +571,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32, AFC ? 1 : 2) k_sync_frame(const
         S->dbg_cycles = (unsigned long long)(clock64() - clk_start); S->dbg_rounds = dbg_rounds;
 #ifdef M17B_PHASE_CLOCKS
         for (int q5 = 0; q5 < 5; q5++) S->dbg_phase[q5] = (unsigned long long)ph[q5];
+        S->dbg_phase[5] = (unsigned long long)ph_blocks;
 #endif
         nframes[c] = nfr < fcap ? nfr : (int)fcap;
         nevents[c] = nev < ecap ? nev : (int)ecap;
