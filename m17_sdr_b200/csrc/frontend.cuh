@@ -84,6 +84,11 @@ __device__ __forceinline__ void fe_limit2(uint32_t raw_a, uint32_t raw_b, LimSam
     unpack2(M, ma, mb);
     unpack2(G, ga, gb);
     const uint32_t mab = __float_as_uint(ma), mbb = __float_as_uint(mb);
+    // (Tried in round 2: leave the patch out of the walking loop -- a running VIMNMX3 of bits(m) | 0xFF800000 instead, one warp
+    // vote per 80-sample segment, and a second pass with the patch over the segments that need it, about 1 % of the warp-units
+    // of the bench workload.  Exact (tests/gpu_check.py check_rx_chain_limiter_patch plants the class), 1.5 instructions per
+    // sample fewer, and no faster: 0.608 vs 0.607 ms.  Redoing whole warp-units instead was 0.72 ms -- a unit is half the
+    // kernel's duration, so any unit that runs twice in the second wave extends the kernel by a quarter.)
     if ((mab | 0xFF800000u) == 0xFFFFFFFFu) ga = __uint_as_float(0x7F000000u - mab);
     if ((mbb | 0xFF800000u) == 0xFFFFFFFFu) gb = __uint_as_float(0x7F000000u - mbb);
     if (mo) { mo[0] = ma; mo[1] = mb; go[0] = ga; go[1] = gb; }

@@ -534,6 +534,46 @@ def check_rx_chain(ctx, P, nchan=16, nframes=30, seed=21, verbose=False, split=N
     return f"rx chain ok ({nchan} ch x {X.shape[1] // 1920} blocks, {int(o.counts[:, 2].sum())} frames, {deliv} delivered)"
 
 
+# (|re|, |im|) int16 pairs whose limiter divisor sqrt(re^2 + im^2) has an all-ones fp32 significand: the one input class the
+# front end's Newton reciprocal must patch (frontend.cuh); found by enumeration, see the test
+FE_ALL_ONES = [(3753, 1810), (4078, 855), (7506, 3620), (7879, 2714), (8156, 1710), (12665, 10834), (14136, 8829), (15012, 7240),
+               (16666, 149), (23673, 23467), (24084, 23045), (28738, 16889), (30333, 13821)]
+
+
+def check_rx_chain_limiter_patch(ctx, P, nchan=40, nframes=8, seed=77):
+    """the unpatched fast pass of the front end must detect every sample whose divisor has an all-ones significand and redo
+    the warp-unit exactly: such samples are planted (all sign / swap variants) into real signals, in some rows only, at
+    positions that include the first and last chunk of a block"""
+    X, pl = signals.stream_channels(P, nchan, nframes, seed, ebn0=[26] * nchan, f0_max=500.0)
+    X = X.copy()
+    rng = np.random.default_rng(seed)
+    T = X.shape[1] // 1920
+    # check the table really is the class it claims (numpy float32 sqrt is correctly rounded)
+    for a, b in FE_ALL_ONES:
+        re, im = np.float32(np.float64(a) * 0.00003), np.float32(np.float64(b) * 0.00003)
+        mbits = np.sqrt(np.float32(np.float32(re * re) + np.float32(im * im))).view(np.uint32)
+        assert (int(mbits) | 0xFF800000) == 0xFFFFFFFF, (a, b)
+    planted = 0
+    for c in range(nchan):
+        if c % 3 == 0:
+            continue                                            # rows without any: their units must not change either
+        for t in range(T):
+            if rng.random() < 0.5:
+                continue
+            for pos in set([0, 1, 19, 1900, 1919] if (c + t) % 4 == 0 else []) | set(rng.integers(0, 1920, 3).tolist()):
+                a, b = FE_ALL_ONES[int(rng.integers(len(FE_ALL_ONES)))]
+                if rng.random() < 0.5:
+                    a, b = b, a
+                i = t * 1920 + pos
+                X[c, i, 0] = a * (1 if rng.random() < 0.5 else -1)
+                X[c, i, 1] = b * (1 if rng.random() < 0.5 else -1)
+                planted += 1
+    o = P.rx_run(X, seam=0)
+    res = run_chain(ctx, X, 0)
+    compare_chain(res, o, 0, nchan)
+    return f"limiter patch ok ({planted} planted samples, {int(o.counts[:, 2].sum())} frames)"
+
+
 def check_rx_baseband(ctx, P, nchan=14, nframes=30, seed=22, verbose=False, split=None):
     eb = [None, 12, 10, 8, 6, 4, 2, 0, 12, 10, 8, 6, 4, 2][:nchan]
     D, pl = signals.baseband_channels(P, nchan, nframes, seed, eb)

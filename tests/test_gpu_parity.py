@@ -40,6 +40,10 @@ def test_rx_chain_from_iq(ctx, port):
     gc.check_rx_chain(ctx, port)
 
 
+def test_rx_chain_limiter_patch_class(ctx, port):
+    gc.check_rx_chain_limiter_patch(ctx, port)
+
+
 def test_rx_chain_state_carry_across_calls(ctx, port):
     gc.check_rx_chain(ctx, port, nchan=6, seed=23, split=[1, 7, 2, 1, 13])
     gc.check_rx_baseband(ctx, port, nchan=6, seed=24, split=[3, 1, 1, 9])
