@@ -41,6 +41,14 @@ __device__ __forceinline__ LimSample fe_limit_ieee(uint32_t raw, float *mo = nul
     return s;
 }
 
+// g = bits(m) has an all-ones significand ? 0x7F000000 - bits(m) : g, in two instructions: a LOP3 (~m & 0x7FFFFF) that only
+// writes its "result != 0" predicate, and the predicated subtract (the compiler's own form is LOP3 + ISETP + subtract).
+__device__ __forceinline__ float fe_patch_all_ones(float g, uint32_t mbits) {
+    uint32_t gb = __float_as_uint(g);
+    asm("{ .reg .pred p; .reg .b32 t; lop3.or.b32 t|p, %1, 0x7FFFFF, 0, 0x0C, 0; @!p sub.u32 %0, 0x7F000000, %1; }" : "+r"(gb) : "r"(mbits));
+    return __uint_as_float(gb);
+}
+
 // Two samples at a time.  (re, im) of each sample travel as one packed pair through the scaling, the squares and the final
 // limiter scaling; the Newton / Markstein residual steps for sqrt and reciprocal are packed ACROSS the two samples
 // (one FMUL2 / FFMA2 serves both), with the negated operands the residuals need produced by packed multiplies by -1 (exact).
@@ -89,8 +97,8 @@ __device__ __forceinline__ void fe_limit2(uint32_t raw_a, uint32_t raw_b, LimSam
     // of the bench workload.  Exact (tests/gpu_check.py check_rx_chain_limiter_patch plants the class), 1.5 instructions per
     // sample fewer, and no faster: 0.608 vs 0.607 ms.  Redoing whole warp-units instead was 0.72 ms -- a unit is half the
     // kernel's duration, so any unit that runs twice in the second wave extends the kernel by a quarter.)
-    if ((mab | 0xFF800000u) == 0xFFFFFFFFu) ga = __uint_as_float(0x7F000000u - mab);
-    if ((mbb | 0xFF800000u) == 0xFFFFFFFFu) gb = __uint_as_float(0x7F000000u - mbb);
+    ga = fe_patch_all_ones(ga, mab);
+    gb = fe_patch_all_ones(gb, mbb);
     if (mo) { mo[0] = ma; mo[1] = mb; go[0] = ga; go[1] = gb; }
     unpack2(mul2(va, pack2(ga, ga)), oa.re, oa.im);
     unpack2(mul2(vb, pack2(gb, gb)), ob.re, ob.im);
@@ -165,15 +173,15 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 7) k_frontend(const uint32_t *_
     // pitch = 4 x 5 words, conflict-free for 16-byte row reads), and each lane reads its own row back.  Everything is sized
     // for 28 resident warps per SM (<= 72 registers, 7.5 KB of shared memory per warp): the 8000 warp-units of the 1024 x 250
     // workload then fit in two full waves of 148 x 28.
-    int32_t off[5];                                                // piece offsets (in 16-byte units, signed) relative to the warp's first row
-    const uint4 *base = (const uint4 *)(iq + gsl[wid][0] * 1920);
+    uint32_t off[5];                                               // piece offsets in bytes from the warp's first row (rows ascend with the item)
+    const char *base = (const char *)(iq + gsl[wid][0] * 1920);
 #pragma unroll
     for (int k = 0; k < 5; k++) {
         const int p = lane + 32 * k, r = p / 5;
         int64_t it = item0 + r;
         if (it >= nitems) it = nitems - 1;
         const int64_t gr = (it / Tc) * T + t0 + it % Tc;
-        off[k] = (int32_t)((gr - gsl[wid][0]) * 480 + (p - 5 * r));
+        off[k] = (uint32_t)((gr - gsl[wid][0]) * 7680 + (p - 5 * r) * 16);
     }
     // two tiles of 160 pieces (one 20-sample chunk of the warp's 32 rows each), filled two chunks ahead with 16-byte cp.async:
     // completion is tracked by the async-copy group, NOT by a register scoreboard -- with plain loads into registers the
@@ -182,14 +190,17 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 7) k_frontend(const uint32_t *_
     auto fetch = [&](int c20) {
         if (c20 < 96) {
             uint4 *tl = stage[wid][c20 & 1];
+            const char *bc = base + c20 * 80;                        // warp-uniform; the lane adds its 32-bit piece offset
 #pragma unroll
             for (int k = 0; k < 5; k++) {
                 const unsigned dst = (unsigned)__cvta_generic_to_shared(tl + lane + 32 * k);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(base + off[k] + c20 * 5));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(bc + off[k]));
             }
         }
         asm volatile("cp.async.commit_group;");
     };
+    const int64_t g0 = gsl[wid][0];
+    const bool contig = item0 + 31 < nitems && gsl[wid][31] - g0 == 31;
     fetch(0);
     fetch(1);
     for (int seg = 0; seg < 24; seg++) {                           // 24 segments of 4 chunks = 80 samples -> 16 kept values per row
@@ -205,9 +216,18 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 7) k_frontend(const uint32_t *_
         // flush: 16 kept values per row, half a 128-byte line per row and store
         {
             const int r0 = lane >> 4, col = lane & 15;
+            if (contig) {
+                // the unit's 32 rows are consecutive rows of disc (always, when the call covers whole channels): one pointer,
+                // compile-time row offsets
+                float *d = disc + (g0 + r0) * 384 + seg * 16 + col;
+                const float *tsrc = &tout[wid][r0][col];
+#pragma unroll
+                for (int r = 0; r < 32; r += 2) d[r * 384] = tsrc[r * 17];
+            } else {
 #pragma unroll 4
-            for (int r = 0; r < 32; r += 2)
-                if (item0 + r + r0 < nitems) disc[gsl[wid][r + r0] * 384 + seg * 16 + col] = tout[wid][r + r0][col];
+                for (int r = 0; r < 32; r += 2)
+                    if (item0 + r + r0 < nitems) disc[gsl[wid][r + r0] * 384 + seg * 16 + col] = tout[wid][r + r0][col];
+            }
         }
         __syncwarp();
     }
