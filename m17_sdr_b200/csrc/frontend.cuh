@@ -41,72 +41,79 @@ __device__ __forceinline__ LimSample fe_limit_ieee(uint32_t raw, float *mo = nul
     return s;
 }
 
-// g = bits(m) has an all-ones significand ? 0x7F000000 - bits(m) : g, in two instructions: a LOP3 (~m & 0x7FFFFF) that only
-// writes its "result != 0" predicate, and the predicated subtract (the compiler's own form is LOP3 + ISETP + subtract).
-__device__ __forceinline__ float fe_patch_all_ones(float g, uint32_t mbits) {
+// g = bits(m) has an all-ones significand ? 0x7F000000 - bits(m) : g, given the bits of -m (0x7F000000 - bits(m) = 0xFF000000 -
+// bits(-m)), in two instructions: a LOP3 (~x & 0x7FFFFF) that only writes its "result != 0" predicate, and the predicated
+// subtract (the compiler's own form is LOP3 + ISETP + subtract).
+__device__ __forceinline__ float fe_patch_all_ones(float g, uint32_t nmbits) {
     uint32_t gb = __float_as_uint(g);
-    asm("{ .reg .pred p; .reg .b32 t; lop3.or.b32 t|p, %1, 0x7FFFFF, 0, 0x0C, 0; @!p sub.u32 %0, 0x7F000000, %1; }" : "+r"(gb) : "r"(mbits));
+    asm("{ .reg .pred p; .reg .b32 t; lop3.or.b32 t|p, %1, 0x7FFFFF, 0, 0x0C, 0; @!p sub.u32 %0, 0xFF000000, %1; }" : "+r"(gb) : "r"(nmbits));
     return __uint_as_float(gb);
 }
 
-// Two samples at a time.  (re, im) of each sample travel as one packed pair through the scaling, the squares and the final
-// limiter scaling; the Newton / Markstein residual steps for sqrt and reciprocal are packed ACROSS the two samples
-// (one FMUL2 / FFMA2 serves both), with the negated operands the residuals need produced by packed multiplies by -1 (exact).
-// Every half of every packed operation is an independent IEEE round-to-nearest operation, so the results are those of the
-// scalar formulation, which m17b_selftest_frontend compares with fe_limit_ieee over all 2^32 raw words.
-__device__ __forceinline__ void fe_limit2(uint32_t raw_a, uint32_t raw_b, LimSample &oa, LimSample &ob, float *mo = nullptr, float *go = nullptr) {
+// Two samples at a time, packed ACROSS the two samples: RE = (re_a, re_b), IM = (im_a, im_b).  Scaling, squares, the sum of
+// squares, the Newton / Markstein residual steps for sqrt and reciprocal and the final limiter scaling are then all packed
+// operations on naturally aligned pairs (one FMUL2 / FFMA2 / FADD2 serves both samples), and the outputs XRE = (x_a.re, x_b.re),
+// XIM = (x_a.im, x_b.im) are the form the discriminator wants.  Every half of every packed operation is an independent IEEE
+// round-to-nearest operation, so the results are those of the scalar formulation, which m17b_selftest_frontend compares with
+// fe_limit_ieee over all 2^32 raw words.
+// `one` = (1.0f, 1.0f) from a kernel argument: re^2 + im^2 must be two rounded products and one rounded sum, but ptxas contracts
+// mul.rn.f32x2 followed by add.rn.f32x2 into one FFMA2 (common.cuh); fma2(im^2, one, re^2) is the same rounded sum and cannot be
+// contracted because the multiplier is not a compile-time 1.
+__device__ __forceinline__ void fe_limit_pair(uint32_t raw_a, uint32_t raw_b, f32x2 one, f32x2 &XRE, f32x2 &XIM, float *mo = nullptr, float *go = nullptr) {
     // int16 -> float: one I2F.S16 per component, reading the half-register directly (exact).  (Tried in round 2: the
     // conversion on the ALU / FMA pipes instead -- (x ^ 0x4B008000) as a float minus 2^23 + 32768, exact and verified over all
     // 2^32 inputs -- to unload the quarter-rate XU pipe: 0.606 -> 0.631 ms.  The kernel is bound by issue slots and the FP32
     // pipe, not by the XU; the three extra ALU / packed instructions per sample cost more than the two I2F they replace.)
-    const f32x2 xa = pack2((float)(short)(raw_a & 0xFFFFu), (float)(short)(raw_a >> 16));
-    const f32x2 xb = pack2((float)(short)(raw_b & 0xFFFFu), (float)(short)(raw_b >> 16));
+    const f32x2 xr = pack2((float)(short)(raw_a & 0xFFFFu), (float)(short)(raw_b & 0xFFFFu));
+    const f32x2 xi = pack2((float)(short)(raw_a >> 16), (float)(short)(raw_b >> 16));
     constexpr float c_hi = 0.00003f;
     constexpr float c_lo = (float)(0.00003 - (double)0.00003f);
     const f32x2 CH = pack2(c_hi, c_hi), CL = pack2(c_lo, c_lo);
-    const f32x2 va = fma2(xa, CH, mul2(xa, CL));               // (re, im) = fmaf(x, c_hi, x * c_lo) == (float)((double)x * 0.00003)
-    const f32x2 vb = fma2(xb, CH, mul2(xb, CL));
-    float qa0, qa1, qb0, qb1;
-    unpack2(mul2(va, va), qa0, qa1);
-    unpack2(mul2(vb, vb), qb0, qb1);
-    const float sa = qa0 + qa1, sb = qb0 + qb1;                // two rounded products, one rounded (scalar) sum: no contraction
-    float ya, yb;
+    const f32x2 RE = fma2(xr, CH, mul2(xr, CL));               // fmaf(x, c_hi, x * c_lo) == (float)((double)x * 0.00003)
+    const f32x2 IM = fma2(xi, CH, mul2(xi, CL));
+    const f32x2 S = fma2(mul2(IM, IM), one, mul2(RE, RE));     // two rounded products, one rounded sum (see above)
+    float sa, sb, ya, yb;
+    unpack2(S, sa, sb);
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(ya) : "f"(sa));
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(yb) : "f"(sb));
-    const f32x2 S = pack2(sa, sb), Y = pack2(ya, yb);
-    const f32x2 NEG1 = pack2(-1.0f, -1.0f), HALF = pack2(0.5f, 0.5f), ONE = pack2(1.0f, 1.0f);
-    // m = RN(sqrt(s)): Newton step on the residual s - m*m
-    f32x2 M = mul2(S, Y);
-    const f32x2 H = mul2(Y, HALF);
-    M = fma2(fma2(mul2(M, NEG1), M, S), H, M);
-    // g = RN(1/m): two residual corrections starting from y ~ 1/m (Markstein); t = m*g - 1 = -(1 - m*g) exactly, so
-    // g + (1 - m*g)*g = fma(t, -g, g).  The one input class this cannot round correctly is a divisor whose significand is all
-    // ones: the Newton iterate then lands exactly on a rounding midpoint while the true quotient 2^-(e+1) (1 + 2^-24 + ..)
-    // lies just above it; its correctly rounded value is known in closed form, 2^-(e+1) (1 + 2^-23) = bits 0x7F000000 - bits(m).
-    // (with -m formed once: fma(-m, g, 1) = 1 - m*g is exactly -(m*g - 1), and fma(1 - m*g, g, g) is the same real number
-    //  g + (1 - m*g)*g as fma(m*g - 1, -g, g), so the results are those of the form in the comment above, with one multiply less)
-    const f32x2 NM = mul2(M, NEG1);
+    const f32x2 Y = pack2(ya, yb);
+    const f32x2 NEG1 = pack2(-1.0f, -1.0f), NHALF = pack2(-0.5f, -0.5f), ONE = pack2(1.0f, 1.0f);
+    // -m = -RN(sqrt(s)): Newton step on the residual s - m0*m0, carried out on the negated iterate (round-to-nearest is
+    // symmetric, so fma(r, -y/2, -m0) is exactly -(m0 + r*y/2)); only -m is needed below
+    const f32x2 M0 = mul2(S, Y);
+    const f32x2 NM0 = mul2(M0, NEG1);
+    const f32x2 NM = fma2(fma2(NM0, M0, S), mul2(Y, NHALF), NM0);
+    // g = RN(1/m): two residual corrections starting from y ~ 1/m (Markstein): fma(-m, g, 1) = 1 - m*g, g + (1 - m*g)*g.
+    // The one input class this cannot round correctly is a divisor whose significand is all ones: the Newton iterate then
+    // lands exactly on a rounding midpoint while the true quotient 2^-(e+1) (1 + 2^-24 + ..) lies just above it; its correctly
+    // rounded value is known in closed form, 2^-(e+1) (1 + 2^-23) = bits 0x7F000000 - bits(m).
     f32x2 G = fma2(fma2(NM, Y, ONE), Y, Y);
     G = fma2(fma2(NM, G, ONE), G, G);
-    float ma, mb, ga, gb;
-    unpack2(M, ma, mb);
+    float nma, nmb, ga, gb;
+    unpack2(NM, nma, nmb);
     unpack2(G, ga, gb);
-    const uint32_t mab = __float_as_uint(ma), mbb = __float_as_uint(mb);
     // (Tried in round 2: leave the patch out of the walking loop -- a running VIMNMX3 of bits(m) | 0xFF800000 instead, one warp
     // vote per 80-sample segment, and a second pass with the patch over the segments that need it, about 1 % of the warp-units
     // of the bench workload.  Exact (tests/gpu_check.py check_rx_chain_limiter_patch plants the class), 1.5 instructions per
-    // sample fewer, and no faster: 0.608 vs 0.607 ms.  Redoing whole warp-units instead was 0.72 ms -- a unit is half the
-    // kernel's duration, so any unit that runs twice in the second wave extends the kernel by a quarter.)
-    ga = fe_patch_all_ones(ga, mab);
-    gb = fe_patch_all_ones(gb, mbb);
-    if (mo) { mo[0] = ma; mo[1] = mb; go[0] = ga; go[1] = gb; }
-    unpack2(mul2(va, pack2(ga, ga)), oa.re, oa.im);
-    unpack2(mul2(vb, pack2(gb, gb)), ob.re, ob.im);
+    // sample fewer, and no faster.  Redoing whole warp-units instead was 0.72 ms -- a unit is half the kernel's duration, so
+    // any unit that runs twice in the second wave extends the kernel by a quarter.)
+    ga = fe_patch_all_ones(ga, __float_as_uint(nma));
+    gb = fe_patch_all_ones(gb, __float_as_uint(nmb));
+    if (mo) { mo[0] = -nma; mo[1] = -nmb; go[0] = ga; go[1] = gb; }
+    G = pack2(ga, gb);
+    XRE = mul2(RE, G);
+    XIM = mul2(IM, G);
 }
-__device__ __forceinline__ LimSample fe_limit(uint32_t raw, float *mo = nullptr, float *go = nullptr) {
+__device__ __forceinline__ void fe_limit2(uint32_t raw_a, uint32_t raw_b, f32x2 one, LimSample &oa, LimSample &ob, float *mo = nullptr, float *go = nullptr) {
+    f32x2 XRE, XIM;
+    fe_limit_pair(raw_a, raw_b, one, XRE, XIM, mo, go);
+    unpack2(XRE, oa.re, ob.re);
+    unpack2(XIM, oa.im, ob.im);
+}
+__device__ __forceinline__ LimSample fe_limit(uint32_t raw, f32x2 one, float *mo = nullptr, float *go = nullptr) {
     LimSample a, b;
     float m2[2], g2[2];
-    fe_limit2(raw, raw, a, b, mo ? m2 : nullptr, mo ? g2 : nullptr);
+    fe_limit2(raw, raw, one, a, b, mo ? m2 : nullptr, mo ? g2 : nullptr);
     if (mo) { *mo = m2[0]; *go = g2[0]; }
     return a;
 }
@@ -120,7 +127,7 @@ __device__ __forceinline__ LimSample fe_limit(uint32_t raw, float *mo = nullptr,
 // disc and mean); the whole call is t0 = 0, Tc = T.  Sub-ranges let the host pipeline the front end of one time slice with
 // the timing loop of the previous one (rx.cuh).
 __global__ void __launch_bounds__(FE_WARPS * 32, 7) k_frontend(const uint32_t *__restrict__ iq, int64_t nchan, int64_t T, int64_t t0, int64_t Tc,
-                                                            RxChanState *st, float *__restrict__ disc, float *__restrict__ mean) {
+                                                            RxChanState *st, float *__restrict__ disc, float *__restrict__ mean, f32x2 one) {
     __shared__ float tout[FE_WARPS][32][17];
     __shared__ __align__(16) uint4 stage[FE_WARPS][2][160];      // two 20-sample chunks of the warp's 32 rows
     __shared__ int64_t gsl[FE_WARPS][32];                        // global (channel, block) index of each lane's item
@@ -141,29 +148,36 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 7) k_frontend(const uint32_t *_
     if (t == 0) { z0re = st[ch].z0re; z0im = st[ch].z0im; z1re = st[ch].z1re; z1im = st[ch].z1im; }
     else {
         const uint32_t *prev = iq + g * 1920;
-        LimSample a = fe_limit(__ldg(prev - 1)), b = fe_limit(__ldg(prev - 2));
+        LimSample a = fe_limit(__ldg(prev - 1), one), b = fe_limit(__ldg(prev - 2), one);
         z0re = a.re; z0im = a.im; z1re = b.re; z1im = b.im;
     }
     float acc = 0.0f;                                            // sum of u; sum of u*0.5 == 0.5*sum (exact power-of-two scaling)
+    // the two previous limited samples as the pair the packed discriminator subtracts: (x[n-2], x[n-1]) per component
+    f32x2 PRE = pack2(z1re, z0re), PIM = pack2(z1im, z0im);
     auto process20 = [&](const uint4 *w, int slot) {              // w: the lane's five 16-byte pieces (registers or shared memory)
 #pragma unroll
         for (int s = 0; s < 20; s += 2) {
             const uint4 q = w[s >> 2];
             const uint32_t raw0 = (s & 3) == 0 ? q.x : q.z, raw1 = (s & 3) == 0 ? q.y : q.w;
-            LimSample x0, x1;
-            fe_limit2(raw0, raw1, x0, x1);
-            // dsp_arctan_disc2 (m17_dsp.cpp:203-212), two samples
-            const float a0 = z0im * (x0.re - z1re);
-            const float b0 = z0re * (x0.im - z1im);
-            const float u0 = b0 - a0;
+            f32x2 XRE, XIM;
+            fe_limit_pair(raw0, raw1, one, XRE, XIM);
+            // dsp_arctan_disc2 (m17_dsp.cpp:203-212), two samples: u[n] = x[n-1].re * (x[n].im - x[n-2].im) - x[n-1].im * (x[n].re - x[n-2].re).
+            // The differences of both samples are one packed subtract per component (the subtrahend pair IS the previous
+            // output pair), the four products are scalar (their factors sit in different halves), b - a is packed again.
+            const f32x2 DRE = sub2(XRE, PRE), DIM = sub2(XIM, PIM);
+            float dre0, dre1, dim0, dim1, pre1, pim1, xre0, xim0, pre0_, pim0_, xre1_, xim1_;
+            unpack2(DRE, dre0, dre1); unpack2(DIM, dim0, dim1);
+            unpack2(PRE, pre0_, pre1); unpack2(PIM, pim0_, pim1);
+            unpack2(XRE, xre0, xre1_); unpack2(XIM, xim0, xim1_);
+            const float a0 = pim1 * dre0, b0 = pre1 * dim0;
+            const float a1 = xim0 * dre1, b1 = xre0 * dim1;
+            float u0, u1;
+            unpack2(sub2(pack2(b0, b1), pack2(a0, a1)), u0, u1);
             acc += u0;
-            const float a1 = x0.im * (x1.re - z0re);
-            const float b1 = x0.re * (x1.im - z0im);
-            const float u1 = b1 - a1;
             acc += u1;
             if (s % 5 == FE_KEEP) tout[wid][lane][slot * 4 + s / 5] = u0 * 0.5f;
             if ((s + 1) % 5 == FE_KEEP) tout[wid][lane][slot * 4 + (s + 1) / 5] = u1 * 0.5f;
-            z1re = x0.re; z1im = x0.im; z0re = x1.re; z0im = x1.im;
+            PRE = XRE; PIM = XIM;
         }
     };
     // Loads.  A warp-wide LDG.128 whose lanes each walk their own row (7680 B apart) costs 32 L1 tag wavefronts for 512 B, so
@@ -233,21 +247,24 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 7) k_frontend(const uint32_t *_
     }
     if (live) {
         mean[g] = (acc * 0.5f) / 1920.0f;                     // offset/len (m17_dsp.cpp:214)
-        if (t == T - 1) { st[ch].nz0re = z0re; st[ch].nz0im = z0im; st[ch].nz1re = z1re; st[ch].nz1im = z1im; }
+        if (t == T - 1) {
+            unpack2(PRE, z1re, z0re); unpack2(PIM, z1im, z0im);
+            st[ch].nz0re = z0re; st[ch].nz0im = z0im; st[ch].nz1re = z1re; st[ch].nz1im = z1im;
+        }
     }
     }
 }
 
 // Exhaustive proof-by-enumeration that fe_limit == fe_limit_ieee for every possible int16 IQ pair except (0,0)
 // (which the reference itself turns into NaN).  Counts bitwise mismatches of either output component.
-__global__ void k_selftest_frontend(unsigned long long *mism, uint32_t lo, uint32_t count, uint32_t *dump, int dump_cap) {
+__global__ void k_selftest_frontend(unsigned long long *mism, uint32_t lo, uint32_t count, uint32_t *dump, int dump_cap, f32x2 one) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned bad = 0;
     for (uint32_t k = i; k < count; k += gridDim.x * blockDim.x) {
         const uint32_t raw = lo + k;
         if (raw == 0) continue;
         float m1, g1, m2, g2;
-        const LimSample a = fe_limit(raw, &m1, &g1), b = fe_limit_ieee(raw, &m2, &g2);
+        const LimSample a = fe_limit(raw, one, &m1, &g1), b = fe_limit_ieee(raw, &m2, &g2);
         if ((__float_as_uint(a.re) != __float_as_uint(b.re)) | (__float_as_uint(a.im) != __float_as_uint(b.im))) {
             bad++;
             if (dump) {
@@ -272,7 +289,7 @@ extern "C" int m17b_selftest_frontend(m17b_ctx *ctx, uint64_t first, uint64_t co
     if (h_dump && dump_cap) { CUDA_TRY(cudaMalloc((void **)&d_dump, 4 * (size_t)dump_cap)); CUDA_TRY(cudaMemsetAsync(d_dump, 0, 4 * (size_t)dump_cap, st)); }
     for (uint64_t off = 0; off < count; off += (1ull << 30)) {
         const uint64_t n = count - off < (1ull << 30) ? count - off : (1ull << 30);
-        k_selftest_frontend<<<148 * 16, 256, 0, st>>>(d, (uint32_t)(first + off), (uint32_t)n, d_dump, dump_cap);
+        k_selftest_frontend<<<148 * 16, 256, 0, st>>>(d, (uint32_t)(first + off), (uint32_t)n, d_dump, dump_cap, F32X2_ONE);
     }
     KERNEL_CHECK();
     unsigned long long h = 0;

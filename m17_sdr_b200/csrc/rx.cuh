@@ -382,7 +382,7 @@ extern "C" int m17b_rx_set_afc(m17b_rx *rx, int on, void *stream) {
 
 // front end over blocks [t0, t0+Tc) of channels [.., +nc)
 static int launch_frontend(const int16_t *d_iq, int64_t nc, int64_t T, int64_t t0, int64_t Tc, RxChanState *state, float *disc, float *mean, cudaStream_t st) {
-    k_frontend<<<grid_for(nc * Tc, FE_WARPS * 32), FE_WARPS * 32, 0, st>>>((const uint32_t *)d_iq, nc, T, t0, Tc, state, disc, mean);
+    k_frontend<<<grid_for(nc * Tc, FE_WARPS * 32), FE_WARPS * 32, 0, st>>>((const uint32_t *)d_iq, nc, T, t0, Tc, state, disc, mean, F32X2_ONE);
     KERNEL_CHECK();
     return M17B_OK;
 }
