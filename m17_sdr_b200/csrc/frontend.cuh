@@ -60,10 +60,11 @@ __device__ __forceinline__ float fe_patch_all_ones(float g, uint32_t nmbits) {
 // mul.rn.f32x2 followed by add.rn.f32x2 into one FFMA2 (common.cuh); fma2(im^2, one, re^2) is the same rounded sum and cannot be
 // contracted because the multiplier is not a compile-time 1.
 __device__ __forceinline__ void fe_limit_pair(uint32_t raw_a, uint32_t raw_b, f32x2 one, f32x2 &XRE, f32x2 &XIM, float *mo = nullptr, float *go = nullptr) {
-    // int16 -> float: one I2F.S16 per component, reading the half-register directly (exact).  (Tried in round 2: the
-    // conversion on the ALU / FMA pipes instead -- (x ^ 0x4B008000) as a float minus 2^23 + 32768, exact and verified over all
-    // 2^32 inputs -- to unload the quarter-rate XU pipe: 0.606 -> 0.631 ms.  The kernel is bound by issue slots and the FP32
-    // pipe, not by the XU; the three extra ALU / packed instructions per sample cost more than the two I2F they replace.)
+    // int16 -> float: one I2F.S16 per component, reading the half-register directly (exact).  (Tried twice in round 2: the
+    // conversion on the ALU / FMA pipes instead -- (x ^ 0x8000) in the low mantissa bits of 2^23, minus 2^23 + 32768, exact and
+    // verified over all 2^32 inputs -- to unload the XU pipe, where I2F draws twice its share of the stall samples (mio /
+    // short_sb): 0.606 -> 0.631 ms on the first form of this kernel, 0.526 -> 0.553 ms on this one.  The four extra ALU / packed
+    // instructions per sample cost more than the two I2F they replace.)
     const f32x2 xr = pack2((float)(short)(raw_a & 0xFFFFu), (float)(short)(raw_b & 0xFFFFu));
     const f32x2 xi = pack2((float)(short)(raw_a >> 16), (float)(short)(raw_b >> 16));
     constexpr float c_hi = 0.00003f;
