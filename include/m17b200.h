@@ -219,6 +219,12 @@ int m17b_rx_last_launches(const m17b_rx *rx);
    seconds on a B200. */
 int m17b_selftest_frontend(m17b_ctx *ctx, uint64_t first, uint64_t count, uint64_t *h_mismatches, uint32_t *h_dump, int dump_cap, void *stream);
 
+/* exhaustive check that the frame decoder's fp32 form of the LSB soft value, (float)(fabs(m) - 0.6666) with the subtraction in
+   double (m17_dsp_demap_frame / _symbol, m17_dsp.cpp:40-41,91), and its sign-only hard decision (hard_decode_24_bits,
+   m17_bit_utils.cpp:180-187) equal the double formulation on the float bit patterns [first, first+count) of m = sym * cor;
+   returns the number of mismatches (must be 0) and optionally the first dump_cap offenders as {bits(m), fast, reference}. */
+int m17b_selftest_demap(m17b_ctx *ctx, uint64_t first, uint64_t count, uint64_t *h_mismatches, uint32_t *h_dump, int dump_cap, void *stream);
+
 /* ------------------------------------------------------------------ TX chain */
 /* oversample: radio_get_oversample() (radio.cpp:211-219), 10 or 80; m17_mod_init (m17_modulate.cpp:65-76) */
 int m17b_tx_create(m17b_ctx *ctx, int64_t nchan, int oversample, m17b_tx **out);

@@ -272,6 +272,13 @@ class Context:
         self.last_selftest_dump = dump.reshape(-1, 3)[: min(16, n.value)]
         return n.value
 
+    def selftest_demap(self, first=0, count=1 << 32):
+        n = C.c_uint64()
+        dump = np.zeros(3 * 16, np.uint32)
+        _l.check(self.L.m17b_selftest_demap(self.h, first, count, C.byref(n), dump.ctypes.data_as(C.c_void_p), len(dump), _stream()))
+        self.last_selftest_dump = dump.reshape(-1, 3)[: min(16, n.value)]
+        return n.value
+
     def synth_channel(self, iq, sigma=None, f0=None, seed=1):
         _chk_dev(iq, torch.int16, "iq")
         nchan, nsamp = iq.shape[0], iq.shape[1]

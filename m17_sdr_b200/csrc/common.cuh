@@ -48,7 +48,11 @@ struct __align__(16) GatherMaps {
 };
 // TX-side maps: for final (interleaved, randomised) bit i of a frame -> which type-3 bit feeds it
 // (QPP is an involution) and, per type-3 bit, which coded (pre-puncture) position it is.
-struct __align__(16) PunctSteps { uint8_t keep[3][244]; };   // per trellis step: bit0/bit1 = first/second coded bit survives P1/P2/P3
+#define VP_CHUNK 16          // trellis steps per staged chunk of the stand-alone punctured Viterbi kernel (at most 32 kept inputs)
+struct __align__(16) PunctSteps {
+    uint8_t keep[3][244];      // per trellis step: bit0/bit1 = first/second coded bit survives P1/P2/P3
+    uint16_t koff[3][17];      // kept inputs before trellis step VP_CHUNK * j (prefix of popcount(keep)), j = 0 .. ceil(steps / VP_CHUNK)
+};
 struct __align__(16) TxMaps {
     uint16_t qpp[368];   // pi(i) = (45 i + 92 i^2) mod 368          m17_interleave.cpp:5
     uint8_t  rnd[368];   // randomiser bits, MSB first               m17_correlate.cpp:35-42
@@ -128,7 +132,24 @@ __device__ __forceinline__ uint16_t crc16_step(uint16_t crc, uint8_t byte, const
 
 // demap one soft bit from a frame's symbols (m17_dsp.cpp:35-42): m = sym*cor; MSB soft = -m;
 // LSB soft = (float)(fabs(m) - 0.6666) with the subtraction in double, as the double literal forces.
+// reference formulation of the LSB soft value, kept for the exhaustive self-test
+__device__ __forceinline__ float demap_lsb_ieee(float m) { return __double2float_rn((double)fabsf(m) - 0.6666); }
+// The same value in five fp32 adds (no F2F / DADD: B200's fp64 and conversion pipes made this one expression 30 % of the frame
+// decoder's stall samples).  0.6666 = c_hi + c_lo + 1.1e-16 with c_hi, c_lo floats; s = a - c_hi rounds, e = (-c_hi - s) + a
+// recovers what the rounding dropped wherever it matters, and s + (e - c_lo) rounds once more.  That this equals
+// (float)((double)a - 0.6666) -- two roundings of the exact difference -- for EVERY finite a >= 0 is established by enumeration
+// (m17b_selftest_demap on the GPU, all 2^32 bit patterns of m; benchmarks/demap_lsb_enum.py on the CPU).  a = Inf would turn
+// into NaN in the error term; from 2^25 up the value is a itself, which the guard returns.
+__device__ __forceinline__ float demap_lsb(float m) {
+    const float a = fabsf(m);
+    constexpr float c_hi = 0.6666f;
+    constexpr float c_lo = (float)(0.6666 - (double)0.6666f);
+    const float s = a - c_hi;
+    const float e = (-c_hi - s) + a;
+    const float v = s + (e - c_lo);
+    return a >= 33554432.0f ? a : v;
+}
 __device__ __forceinline__ float demap_soft(float sym, float cor, bool lsb) {
     float m = sym * cor;
-    return lsb ? __double2float_rn((double)fabsf(m) - 0.6666) : -m;
+    return lsb ? demap_lsb(m) : -m;
 }

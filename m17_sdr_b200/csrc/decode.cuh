@@ -134,8 +134,19 @@ struct FrameBert   { static constexpr int STEPS = 201, NBYTES = 25; __device__ s
 __device__ __forceinline__ float gather_soft(const float *row, unsigned e) {
     if (e == MAP_ERASE) return 0.0f;                                        // m17_puncture.cpp:52,63,75
     const float m = row[e & 0xFFu];
-    const float v = (e & MAP_LSB) ? __double2float_rn((double)fabsf(m) - 0.6666) : -m;   // m17_dsp.cpp:40-41
+    const float v = (e & MAP_LSB) ? demap_lsb(m) : -m;                        // m17_dsp.cpp:40-41
     return (e & MAP_NEG) ? -v : v;                                          // m17_correlate.cpp:29
+}
+// hard_decode_24_bits (m17_bit_utils.cpp:180-187) only asks whether the soft value is >= 0, and that needs no arithmetic: the LSB
+// value |m| - 0.6666 is never zero (0.6666 is not a float) and is >= 0 exactly when |m| > 0.6666f rounded down, i.e. |m| >=
+// the float just above 0.6666; the MSB value -m is >= 0 when m <= 0 (-0.0 >= 0 holds).  De-randomising flips the sign, and
+// with it '>=' into '<=' (only the MSB value can be zero).  NaN compares false in the reference in every case, here too.
+__device__ __forceinline__ bool gather_hard(const float *row, unsigned e) {
+    const float m = row[e & 0xFFu];
+    constexpr float c_up = 0.66660005f;                                      // smallest float above 0.6666 (0.6666f is below it)
+    static_assert((double)c_up > 0.6666 && (double)c_up - 0.6666 < 5.9e-8 && (double)0.6666f < 0.6666, "c_up is the float just above 0.6666");
+    if (e & MAP_LSB) return (e & MAP_NEG) ? fabsf(m) < c_up : fabsf(m) >= c_up;
+    return (e & MAP_NEG) ? m >= 0.0f : m <= 0.0f;
 }
 
 // Viterbi + traceback + pack for one frame; row = this thread's scaled symbols in smem (reused as byte scratch
@@ -262,7 +273,7 @@ __global__ void __launch_bounds__(NT) k_decode_frames(const float *__restrict__ 
         for (int k = 0; k < 184; k++) {
             const float m = row[8 + k];
             so[2 * k] = -m;
-            so[2 * k + 1] = __double2float_rn((double)fabsf(m) - 0.6666);
+            so[2 * k + 1] = demap_lsb(m);
         }
     }
     uint32_t golay_e = 0, nbytes = 0, lw01 = 0, lw23 = 0;
@@ -272,7 +283,7 @@ __global__ void __launch_bounds__(NT) k_decode_frames(const float *__restrict__ 
         uint32_t w[4];
         for (int q = 0; q < 4; q++) {
             uint32_t word = 0;
-            for (int b = 0; b < 24; b++) word = (word << 1) | (gather_soft(row, c_maps.lich[24 * q + b]) >= 0 ? 1u : 0u);
+            for (int b = 0; b < 24; b++) word = (word << 1) | (gather_hard(row, c_maps.lich[24 * q + b]) ? 1u : 0u);
             golay_e += (uint32_t)golay_decode_word(word, genc, gerr, &w[q]);
         }
         lw01 = (w[0] << 12) | w[1];                                          // pack_12_to_8_x4x6, m17_bit_utils.cpp:152-172
@@ -377,58 +388,71 @@ extern "C" int m17b_rx_parse_frames(m17b_ctx *ctx, const float *d_sym, const uin
 
 // ---------------------------------------------------------------- config-4 microbenchmark: punctured soft frames in, bytes out
 // d_soft [n][NIN] already de-randomised/de-interleaved (i.e. so[] of m17_rx_parse.cpp:91-95); de-puncture + Viterbi + pack.
-template <class F, int PAT, int NIN, int NT>
-__global__ void __launch_bounds__(NT) k_viterbi_punct(const float *__restrict__ soft, int64_t n, uint8_t *__restrict__ bytes) {
-    extern __shared__ unsigned char smem_raw[];
-    constexpr int PITCH = NIN + 1;
-    float *rows = (float *)smem_raw;                                        // [NT][NIN+1]
-    uint16_t *dec = (uint16_t *)(smem_raw + (((size_t)NT * PITCH * 4 + 15) & ~(size_t)15));
-    const int tid = threadIdx.x, lane = tid & 31, wbase = tid & ~31;
-    const int64_t f0 = (int64_t)blockIdx.x * NT, f = f0 + tid;
-    for (int r = 0; r < 32; r++) {
-        int64_t fr = f0 + wbase + r;
-        if (fr < n) for (int k = lane; k < NIN; k += 32) rows[(wbase + r) * PITCH + k] = __ldg(&soft[fr * NIN + k]);
-    }
-    __syncwarp();
-    if (f >= n) return;
-    const float *row = &rows[tid * PITCH];
+// One thread per frame as in the fused decoder, one warp per CTA.  What bounds this kernel is how many frames an SM can hold:
+// a frame's inputs are consumed in order, so only the next VP_CHUNK trellis steps' worth (at most 32 floats per frame) is staged
+// at a time -- two 4 KB tiles per warp, filled one chunk ahead with cp.async (coalesced 128-byte row pieces, pitch 33 so the
+// per-thread column reads hit 32 banks) -- and the survivor words go to per-thread local memory (interleaved by the hardware,
+// so the accesses coalesce; written once, read once in the traceback).  8.4 KB of shared memory per warp instead of 44 KB.
+template <class F, int PAT, int NIN>
+__global__ void __launch_bounds__(32) k_viterbi_punct(const float *__restrict__ soft, int64_t n, uint8_t *__restrict__ bytes) {
+    __shared__ float tile[2][32][33];
+    constexpr int NCH = (F::STEPS + VP_CHUNK - 1) / VP_CHUNK;
+    static_assert(F::STEPS % 2 == 0 && VP_CHUNK % 2 == 0, "two steps per iteration");
+    const int lane = threadIdx.x;
+    const int64_t f0 = (int64_t)blockIdx.x * 32, f = f0 + lane;
+    const int nrows = (int)min((int64_t)32, n - f0);
+    const float *base = soft + f0 * NIN + lane;
+    auto stage = [&](int c) {                                       // chunk c: inputs [koff[c], koff[c + 1]) of every row
+        if (c < NCH) {
+            const int k0 = c_punct.koff[PAT - 1][c], cnt = min((int)c_punct.koff[PAT - 1][c + 1], NIN) - k0;
+            if (lane < cnt) {
+                const float *src = base + k0;
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(&tile[c & 1][0][lane]);
+#pragma unroll 8
+                for (int r = 0; r < 32; r++)
+                    if (r < nrows) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + r * 33 * 4), "l"(src + (int64_t)r * NIN));
+            }
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    stage(0);
+    stage(1);
+    uint16_t dec[F::STEPS];
     float ma[16], mb[16];
     viterbi_init(ma);
-    int k = 0;
-    static_assert(F::STEPS % 2 == 0, "two steps per iteration");
-    auto fetch = [&](int t, float &a1, float &a2, float &a3, float &a4) {
-        const unsigned k0 = c_punct.keep[PAT - 1][t], k1 = c_punct.keep[PAT - 1][t + 1];      // warp-uniform
-        a1 = (k0 & 1) ? row[k++] : 0.0f;
-        a2 = (k0 & 2) ? row[k++] : 0.0f;
-        a3 = (k1 & 1) ? row[k++] : 0.0f;
-        a4 = (k1 & 2) ? row[k++] : 0.0f;
-    };
-    float s1, s2, s3, s4;
-    fetch(0, s1, s2, s3, s4);
-    for (int t = 0; t < F::STEPS; t += 2) {                                 // next two steps' inputs load behind this pair's ACS
-        float n1 = 0.f, n2 = 0.f, n3 = 0.f, n4 = 0.f;
-        if (t + 2 < F::STEPS) fetch(t + 2, n1, n2, n3, n4);
-        dec[t * NT + tid] = (uint16_t)viterbi_step_pp(ma, mb, s1, s2);
-        dec[(t + 1) * NT + tid] = (uint16_t)viterbi_step_pp(mb, ma, s3, s4);
-        s1 = n1; s2 = n2; s3 = n3; s4 = n4;
+    for (int c = 0; c < NCH; c++) {
+        asm volatile("cp.async.wait_group 1;");                      // chunk c has landed (chunk c + 1 may still be in flight)
+        __syncwarp();
+        const float *row = tile[c & 1][lane];
+        const int t0 = c * VP_CHUNK, t1 = min(t0 + VP_CHUNK, F::STEPS);
+        int k = 0;
+        for (int t = t0; t < t1; t += 2) {
+            const unsigned k0 = c_punct.keep[PAT - 1][t], k1 = c_punct.keep[PAT - 1][t + 1];      // warp-uniform
+            const float s1 = (k0 & 1) ? row[k++] : 0.0f;
+            const float s2 = (k0 & 2) ? row[k++] : 0.0f;
+            const float s3 = (k1 & 1) ? row[k++] : 0.0f;
+            const float s4 = (k1 & 2) ? row[k++] : 0.0f;
+            dec[t] = (uint16_t)viterbi_step_pp(ma, mb, s1, s2);
+            dec[t + 1] = (uint16_t)viterbi_step_pp(mb, ma, s3, s4);
+        }
+        __syncwarp();                                                // every lane is done with the tile: it may be refilled
+        stage(c + 2);
     }
+    if (f >= n) return;
     unsigned s = 0;
     uint8_t *o = bytes + f * F::NBYTES;
-    for (int t = F::STEPS - 1; t > 8 * F::NBYTES; t--) s = trace_prev(s, dec[t * NT + tid]);
+    for (int t = F::STEPS - 1; t > 8 * F::NBYTES; t--) s = trace_prev(s, dec[t]);
     for (int j = F::NBYTES - 1; j >= 0; j--) {
         unsigned d[8], acc = 0;
 #pragma unroll
-        for (int b = 0; b < 8; b++) d[b] = dec[(8 * j + 8 - b) * NT + tid];
+        for (int b = 0; b < 8; b++) d[b] = dec[8 * j + 8 - b];
 #pragma unroll
         for (int b = 0; b < 8; b++) { s = trace_prev(s, d[b]); acc |= ((s >> 3) & 1u) << b; }
         o[j] = (uint8_t)acc;
     }
 }
 template <class F, int PAT, int NIN> static int launch_vp(const float *d_soft, int64_t n, uint8_t *d_bytes, cudaStream_t st) {
-    constexpr int NT = 32;      // one warp per CTA: the smem-limited number of resident warps is highest this way
-    size_t smem = (((size_t)NT * (NIN + 1) * 4 + 15) & ~(size_t)15) + (size_t)F::STEPS * NT * 2;
-    CUDA_TRY(cudaFuncSetAttribute(k_viterbi_punct<F, PAT, NIN, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_viterbi_punct<F, PAT, NIN, NT><<<grid_for(n, NT), NT, smem, st>>>(d_soft, n, d_bytes);
+    k_viterbi_punct<F, PAT, NIN><<<grid_for(n, 32), 32, 0, st>>>(d_soft, n, d_bytes);
     KERNEL_CHECK();
     return M17B_OK;
 }

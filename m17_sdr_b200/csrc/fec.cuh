@@ -254,6 +254,50 @@ extern "C" int m17b_demap_frame(m17b_ctx *ctx, const float *d_sym, int64_t n, fl
     return M17B_OK;
 }
 
+// Exhaustive proof-by-enumeration that demap_lsb == demap_lsb_ieee for every float bit pattern of m (NaN results only have to
+// be NaN in both), and that the sign-only hard decision of the frame decoder agrees with the sign of that value.
+__global__ void k_selftest_demap(unsigned long long *mism, uint32_t lo, uint32_t count, uint32_t *dump, int dump_cap) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned bad = 0;
+    for (uint32_t k = i; k < count; k += gridDim.x * blockDim.x) {
+        const float m = __uint_as_float(lo + k);
+        const float a = demap_lsb(m), b = demap_lsb_ieee(m);
+        const bool same = (a != a && b != b) || __float_as_uint(a) == __float_as_uint(b);
+        const bool hard_ok = ((fabsf(m) >= 0.66660005f) == (b >= 0.0f)) && ((fabsf(m) < 0.66660005f) == (-b >= 0.0f));
+        if (!same || !hard_ok) {
+            bad++;
+            if (dump) {
+                const unsigned long long slot = atomicAdd(mism + 1, 1ull);
+                if (3 * slot + 2 < (unsigned long long)dump_cap) { dump[3 * slot] = lo + k; dump[3 * slot + 1] = __float_as_uint(a); dump[3 * slot + 2] = __float_as_uint(b); }
+            }
+        }
+    }
+    if (bad) atomicAdd(mism, (unsigned long long)bad);
+}
+// h_dump (optional, dump_cap words) receives {bits(m), fast, reference} of the first mismatches found
+extern "C" int m17b_selftest_demap(m17b_ctx *ctx, uint64_t first, uint64_t count, uint64_t *h_mismatches, uint32_t *h_dump, int dump_cap, void *stream) {
+    if (!ctx || !h_mismatches || first + count > (1ull << 32) || dump_cap < 0) return M17B_E_ARG;
+    cudaStream_t st = as_stream(stream);
+    unsigned long long *d;
+    uint32_t *d_dump = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&d, 16));
+    CUDA_TRY(cudaMemsetAsync(d, 0, 16, st));
+    if (h_dump && dump_cap) { CUDA_TRY(cudaMalloc((void **)&d_dump, 4 * (size_t)dump_cap)); CUDA_TRY(cudaMemsetAsync(d_dump, 0, 4 * (size_t)dump_cap, st)); }
+    for (uint64_t off = 0; off < count; off += (1ull << 30)) {
+        const uint64_t n = count - off < (1ull << 30) ? count - off : (1ull << 30);
+        k_selftest_demap<<<148 * 16, 256, 0, st>>>(d, (uint32_t)(first + off), (uint32_t)n, d_dump, dump_cap);
+    }
+    KERNEL_CHECK();
+    unsigned long long h = 0;
+    CUDA_TRY(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, st));
+    if (d_dump) CUDA_TRY(cudaMemcpyAsync(h_dump, d_dump, 4 * (size_t)dump_cap, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaFree(d));
+    if (d_dump) CUDA_TRY(cudaFree(d_dump));
+    *h_mismatches = h;
+    return M17B_OK;
+}
+
 // ---------------------------------------------------------------- sync-word correlator (m17_rx_frame.cpp:22-81)
 struct SyncResult { int type, votes; float variance; float spread, vmax; };   // spread = max|v| - min|v| (rounded), vmax = max|v|: variance = spread / vmax
 // sync templates as sign masks, bit i set = template[i] is -1 (m17_rx_frame.cpp:5-12): preamble, LSF 0x55F7, stream 0xFF5D,

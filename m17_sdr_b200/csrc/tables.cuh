@@ -158,6 +158,13 @@ extern "C" int m17b_ctx_create(int device, m17b_ctx **out) {
     PunctSteps ps;
     for (int pat = 1; pat <= 3; pat++)
         for (int t = 0; t < 244; t++) ps.keep[pat - 1][t] = (uint8_t)((punct_keeps(pat, 2 * t) ? 1 : 0) | (punct_keeps(pat, 2 * t + 1) ? 2 : 0));
+    for (int pat = 1; pat <= 3; pat++) {
+        int k = 0;
+        for (int t = 0; t <= 16 * VP_CHUNK; t++) {
+            if (t % VP_CHUNK == 0) ps.koff[pat - 1][t / VP_CHUNK] = (uint16_t)k;
+            if (t < 244) k += (ps.keep[pat - 1][t] & 1) + ((ps.keep[pat - 1][t] >> 1) & 1);
+        }
+    }
 
     if ((rc = upload(&ctx->d_crc, crc, 256)) || (rc = upload(&ctx->d_genc, genc, 4096)) || (rc = upload(&ctx->d_gerr, gerr, 4096)) ||
         (rc = upload(&ctx->d_mf, ctx->h_mf, M17B_NF * M17B_FN)) || (rc = upload(&ctx->d_md, ctx->h_md, M17B_NF * M17B_FN)) ||

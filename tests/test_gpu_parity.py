@@ -64,6 +64,13 @@ def test_tx_phase_wrap_exhaustive(ctx):
     assert bad == 0, (bad, [[hex(int(x)) for x in r] for r in ctx.last_selftest_dump])
 
 
+def test_demap_lsb_exhaustive(ctx):
+    """the decoder's five-add fp32 LSB soft value == (float)((double)|m| - 0.6666), and its sign-only hard decision agrees
+    with that value's sign, for EVERY float bit pattern of m"""
+    bad = ctx.selftest_demap()
+    assert bad == 0, (bad, [[hex(int(x)) for x in r] for r in ctx.last_selftest_dump])
+
+
 def test_tx_many_channels_ragged(ctx, port):
     """geometry coverage of the fused modulator: channel counts that give every CTA shape (4..32 channels per CTA, a ragged
     last CTA), a symbol count that is not a multiple of the chunk, three calls with carried state; frequency samples
