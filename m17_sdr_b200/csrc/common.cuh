@@ -35,6 +35,7 @@ static inline cudaStream_t as_stream(void *s) { return (cudaStream_t)s; }
 // and de-puncture (m17_puncture.cpp:47-79) are folded together.
 //   bits 0..7 : frame symbol index 8..191        bit 8 : 1 = LSB soft bit (|m|-0.6666), 0 = MSB (-m)
 //   bit 9     : 1 = negate (randomiser bit set)  0xFFFF: punctured position -> 0.0f erasure
+#define STREAM_NIN 272       // kept (unpunctured) trellis inputs of a stream frame: 296 coded bits less the 24 P2 removes
 #define MAP_ERASE 0xFFFFu
 #define MAP_LSB   0x100u
 #define MAP_NEG   0x200u
@@ -70,6 +71,7 @@ struct m17b_ctx {
     float    *d_mf;      // [40][31] matched-filter bank             m17_rx_sync.cpp:13
     float    *d_md;      // [40][31] derivative bank                 m17_rx_sync.cpp:14
     uint8_t  *d_prbs;    // [511]   PRBS9 sequence                   m17_prbs9.cpp:16-26
+    uint16_t *d_smap;    // [272 + 96] stream frame: gather-map entries of the kept trellis inputs in order, then the LICH bits (decode.cuh)
     float     h_mf[M17B_NF * M17B_FN], h_md[M17B_NF * M17B_FN];
 };
 

@@ -130,6 +130,63 @@ struct FrameStream { static constexpr int STEPS = 148, NBYTES = 18; __device__ s
 struct FramePacket { static constexpr int STEPS = 210, NBYTES = 26; __device__ static const uint16_t *map() { return c_maps.p3; } };
 struct FrameBert   { static constexpr int STEPS = 201, NBYTES = 25; __device__ static const uint16_t *map() { return c_maps.bert; } };
 
+// The trellis pass over a warp's 32 rows of kept inputs (row r at base + r * NIN, rows without their bit in rowmask are not
+// touched), survivors into dec; lane_base = base + lane.
+template <class F, int PAT, int NIN>
+__device__ __forceinline__ void viterbi_chunked(const float *lane_base, unsigned rowmask, float (&tile)[2][32][33], int lane, uint16_t (&dec)[F::STEPS]) {
+    constexpr int NCH = (F::STEPS + VP_CHUNK - 1) / VP_CHUNK;
+    static_assert(F::STEPS % 2 == 0 && VP_CHUNK % 2 == 0, "two steps per iteration");
+    auto stage = [&](int c) {                                       // chunk c: inputs [koff[c], koff[c + 1]) of every row
+        if (c < NCH) {
+            const int k0 = c_punct.koff[PAT - 1][c], cnt = min((int)c_punct.koff[PAT - 1][c + 1], NIN) - k0;
+            if (lane < cnt) {
+                const float *src = lane_base + k0;
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(&tile[c & 1][0][lane]);
+#pragma unroll 8
+                for (int r = 0; r < 32; r++)
+                    if ((rowmask >> r) & 1u) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + r * 33 * 4), "l"(src + (int64_t)r * NIN));
+            }
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    stage(0);
+    stage(1);
+    float ma[16], mb[16];
+    viterbi_init(ma);
+    for (int c = 0; c < NCH; c++) {
+        asm volatile("cp.async.wait_group 1;");                      // chunk c has landed (chunk c + 1 may still be in flight)
+        __syncwarp();
+        const float *row = tile[c & 1][lane];
+        const int t0 = c * VP_CHUNK, t1 = min(t0 + VP_CHUNK, F::STEPS);
+        int k = 0;
+        for (int t = t0; t < t1; t += 2) {
+            const unsigned k0 = c_punct.keep[PAT - 1][t], k1 = c_punct.keep[PAT - 1][t + 1];      // warp-uniform
+            const float s1 = (k0 & 1) ? row[k++] : 0.0f;
+            const float s2 = (k0 & 2) ? row[k++] : 0.0f;
+            const float s3 = (k1 & 1) ? row[k++] : 0.0f;
+            const float s4 = (k1 & 2) ? row[k++] : 0.0f;
+            dec[t] = (uint16_t)viterbi_step_pp(ma, mb, s1, s2);
+            dec[t + 1] = (uint16_t)viterbi_step_pp(mb, ma, s3, s4);
+        }
+        __syncwarp();                                                // every lane is done with the tile: it may be refilled
+        stage(c + 2);
+    }
+}
+// traceback from state 0 and byte pack (see decode_conv)
+template <class F>
+__device__ __forceinline__ void viterbi_traceback(const uint16_t (&dec)[F::STEPS], uint8_t *obytes) {
+    unsigned s = 0;
+    for (int t = F::STEPS - 1; t > 8 * F::NBYTES; t--) s = trace_prev(s, dec[t]);
+    for (int j = F::NBYTES - 1; j >= 0; j--) {
+        unsigned d[8], acc = 0;
+#pragma unroll
+        for (int b = 0; b < 8; b++) d[b] = dec[8 * j + 8 - b];
+#pragma unroll
+        for (int b = 0; b < 8; b++) { s = trace_prev(s, d[b]); acc |= ((s >> 3) & 1u) << b; }
+        obytes[j] = (uint8_t)acc;
+    }
+}
+
 // soft value for one gather-map entry; the row already holds m = sym * cor (m17_dsp.cpp:38) for the payload symbols
 __device__ __forceinline__ float gather_soft(const float *row, unsigned e) {
     if (e == MAP_ERASE) return 0.0f;                                        // m17_puncture.cpp:52,63,75
@@ -207,9 +264,9 @@ __device__ __forceinline__ void decode_conv(const float *row, uint16_t *dec_smem
 
 // frames: records pre-filled with sym_off/type/flags by the framer (or by k_parse_init); the symbols of record r
 // of channel c start at syms[c*sym_pitch + sym_carry + (rec.sym_off - sym_base[c])].
-// STREAM = true : handles stream frames only (148-step survivor store -> more CTAs per SM);
-// STREAM = false: handles LSF / packet / BERT frames (244-step store); CTAs without such a frame exit at once.
-template <int NT, bool STREAM>
+// This kernel handles the LSF / packet / BERT frames (a handful per channel and call; CTAs without one exit at once); stream
+// frames go through k_stream_gather + k_stream_acs below.
+template <int NT>
 __global__ void __launch_bounds__(NT) k_decode_frames(const float *__restrict__ syms, int64_t sym_pitch, int sym_carry,
                                                       const int32_t *__restrict__ sym_base, m17b_frame_rec *frames, int64_t fcap,
                                                       const int32_t *__restrict__ nframes, const int2 *__restrict__ frame_rng, int tiles_per_chan, float *soft_out,
@@ -239,7 +296,7 @@ __global__ void __launch_bounds__(NT) k_decode_frames(const float *__restrict__ 
         flags = (hd.y >> 8) & 0xFF;
         src = c * sym_pitch + sym_carry + ((int32_t)hd.x - (sym_base ? sym_base[c] : 0));
     }
-    const bool mine = STREAM ? (type == M17B_T_STREAM) : (type == M17B_T_LSF || type == M17B_T_PACKET || type == M17B_T_BERT);
+    const bool mine = type == M17B_T_LSF || type == M17B_T_PACKET || type == M17B_T_BERT;
     const bool work = (slot < nfr) && (flags & M17B_F_PARSED) && mine;
     if (!__syncthreads_or(work)) return;
     for (int i = tid; i < 256; i += NT) crc_tab[i] = g_crc[i];
@@ -276,21 +333,10 @@ __global__ void __launch_bounds__(NT) k_decode_frames(const float *__restrict__ 
             so[2 * k + 1] = demap_lsb(m);
         }
     }
-    uint32_t golay_e = 0, nbytes = 0, lw01 = 0, lw23 = 0;
+    const uint32_t golay_e = 0, lw01 = 0, lw23 = 0;
+    uint32_t nbytes = 0;
     uint8_t *ob = (uint8_t *)row;                                           // byte scratch AFTER the ACS pass (row no longer needed)
-    if (STREAM) {
-        // 4 x hard_decode_24_bits (m17_bit_utils.cpp:180-187: bit = soft >= 0) + m_17_golay_decode
-        uint32_t w[4];
-        for (int q = 0; q < 4; q++) {
-            uint32_t word = 0;
-            for (int b = 0; b < 24; b++) word = (word << 1) | (gather_hard(row, c_maps.lich[24 * q + b]) ? 1u : 0u);
-            golay_e += (uint32_t)golay_decode_word(word, genc, gerr, &w[q]);
-        }
-        lw01 = (w[0] << 12) | w[1];                                          // pack_12_to_8_x4x6, m17_bit_utils.cpp:152-172
-        lw23 = (w[2] << 12) | w[3];
-        decode_conv<FrameStream, NT>(row, dec, tid, ob);
-        nbytes = FrameStream::NBYTES;
-    } else if (type == M17B_T_LSF) {
+    if (type == M17B_T_LSF) {
         decode_conv<FrameLsf, NT>(row, dec, tid, ob);
         nbytes = FrameLsf::NBYTES;
     } else if (type == M17B_T_PACKET) {
@@ -331,6 +377,128 @@ __global__ void __launch_bounds__(NT) k_decode_frames(const float *__restrict__ 
     r4[0] = q0; r4[1] = q1; r4[2] = q2; r4[3] = q3;
 }
 
+// ---------------------------------------------------------------- stream frames: the decode in two kernels
+// Stream frames are nearly all the frames there are, and the one-kernel form above holds a frame's 192 symbols in shared memory for
+// the whole trellis pass (they are read in interleaver order): 24.7 KB per warp, 9 warps per SM, an issue rate of 45 %.  So the
+// two halves run as separate kernels.  k_stream_gather, one warp per frame: demap, de-randomise, de-interleave, de-puncture into
+// the 272 kept trellis inputs IN TRELLIS ORDER (1088 bytes per frame, written and read back through L2), and the LICH: 96 hard
+// bits by ballot, 4 x Golay(24,12).  k_stream_acs, one thread per frame: the chunk-staged trellis pass of the punctured Viterbi
+// kernel below (8.4 KB of shared memory per warp), traceback, CRC, record.
+struct StreamAux { uint32_t lw01, lw23, golay_e; float cor; };
+#define SG_WARPS 4
+__global__ void __launch_bounds__(SG_WARPS * 32) k_stream_gather(const float *__restrict__ syms, int64_t sym_pitch, int sym_carry, const int32_t *__restrict__ sym_base,
+                                                                 const m17b_frame_rec *__restrict__ frames, int64_t fcap, const int32_t *__restrict__ nframes,
+                                                                 const int2 *__restrict__ frame_rng, int slots_per_chan, int64_t nchan,
+                                                                 const uint16_t *__restrict__ smap, const uint16_t *__restrict__ genc, const uint16_t *__restrict__ gerr,
+                                                                 float *__restrict__ ssoft, StreamAux *__restrict__ saux, float *soft_out) {
+    __shared__ float rowbuf[SG_WARPS][192];
+    __shared__ uint16_t map_s[STREAM_NIN + 96];
+    for (int i = threadIdx.x; i < STREAM_NIN + 96; i += SG_WARPS * 32) map_s[i] = smap[i];
+    __syncthreads();
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t item = (int64_t)blockIdx.x * SG_WARPS + wid;
+    const int64_t c = item / slots_per_chan;
+    if (c >= nchan) return;
+    int lo = 0, nfr;
+    if (frame_rng) { const int2 r = frame_rng[c]; lo = r.x; nfr = r.y; }
+    else nfr = (int)min((int64_t)nframes[c], fcap);
+    const int slot = lo + (int)(item % slots_per_chan);
+    if (slot >= nfr) return;
+    const uint2 hd = *(const uint2 *)(frames + c * fcap + slot);            // (every lane reads the same 8 bytes)
+    if ((hd.y & 0xFF) != M17B_T_STREAM || !((hd.y >> 8) & M17B_F_PARSED)) return;
+    const float *src = syms + c * sym_pitch + sym_carry + ((int32_t)hd.x - (sym_base ? sym_base[c] : 0));
+    float *row = rowbuf[wid];
+    float v[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) v[k] = src[lane + 32 * k];
+    if (lane < 8) row[lane] = v[0];
+    __syncwarp();
+    float hdr[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) hdr[i] = row[i];
+    const float cor = demap_cor(hdr);
+#pragma unroll
+    for (int k = 0; k < 6; k++) if (lane + 32 * k >= 8) row[lane + 32 * k] = v[k] * cor;     // m = in * mag  (m17_dsp.cpp:38), once per symbol
+    __syncwarp();
+    const int64_t fidx = c * fcap + slot;
+    float *o = ssoft + fidx * STREAM_NIN;
+    for (int j = lane; j < STREAM_NIN; j += 32) o[j] = gather_soft(row, map_s[j]);
+    if (soft_out) {
+        float2 *so = (float2 *)(soft_out + fidx * 368);
+        for (int k = lane; k < 184; k += 32) { const float m = row[8 + k]; so[k] = make_float2(-m, demap_lsb(m)); }
+    }
+    // 4 x hard_decode_24_bits (m17_bit_utils.cpp:180-187: bit = soft >= 0) + m_17_golay_decode: ballot bit i = LICH bit i, and
+    // the words are MSB first, so the reversed ballots read as one 96-bit big-endian string
+    const unsigned B0 = __brev(__ballot_sync(0xffffffffu, gather_hard(row, map_s[STREAM_NIN + lane])));
+    const unsigned B1 = __brev(__ballot_sync(0xffffffffu, gather_hard(row, map_s[STREAM_NIN + 32 + lane])));
+    const unsigned B2 = __brev(__ballot_sync(0xffffffffu, gather_hard(row, map_s[STREAM_NIN + 64 + lane])));
+    const uint32_t word = lane == 0 ? B0 >> 8 : lane == 1 ? ((B0 & 0xFFu) << 16) | (B1 >> 16) : lane == 2 ? ((B1 & 0xFFFFu) << 8) | (B2 >> 24) : B2 & 0xFFFFFFu;
+    uint32_t w = 0;
+    int ge = 0;
+    if (lane < 4) ge = golay_decode_word(word, genc, gerr, &w);
+    const uint32_t w0 = __shfl_sync(0xffffffffu, w, 0), w1 = __shfl_sync(0xffffffffu, w, 1), w2 = __shfl_sync(0xffffffffu, w, 2), w3 = __shfl_sync(0xffffffffu, w, 3);
+    ge += __shfl_xor_sync(0xffffffffu, ge, 1);
+    ge += __shfl_xor_sync(0xffffffffu, ge, 2);
+    if (lane == 0) {
+        StreamAux a;
+        a.lw01 = (w0 << 12) | w1;                                            // pack_12_to_8_x4x6, m17_bit_utils.cpp:152-172
+        a.lw23 = (w2 << 12) | w3;
+        a.golay_e = (uint32_t)ge;
+        a.cor = cor;
+        *(uint4 *)(saux + fidx) = *(const uint4 *)&a;
+    }
+}
+__global__ void __launch_bounds__(32) k_stream_acs(const float *__restrict__ ssoft, const StreamAux *__restrict__ saux, m17b_frame_rec *frames, int64_t fcap,
+                                                   const int32_t *__restrict__ nframes, const int2 *__restrict__ frame_rng, int tiles_per_chan,
+                                                   const uint16_t *__restrict__ g_crc) {
+    __shared__ float tile[2][32][33];
+    __shared__ uint16_t crc_tab[256];
+    const int lane = threadIdx.x;
+    const int64_t c = blockIdx.x / tiles_per_chan;
+    const int tl = blockIdx.x % tiles_per_chan;
+    int lo = 0, nfr;
+    if (frame_rng) { const int2 r = frame_rng[c]; lo = r.x; nfr = r.y; }
+    else nfr = (int)min((int64_t)nframes[c], fcap);
+    const int slot = lo + tl * 32 + lane;
+    m17b_frame_rec *rec = frames + c * fcap + slot;
+    int type = -1, flags = 0;
+    uint32_t w0 = 0;
+    if (slot < nfr) { const uint2 hd = *(const uint2 *)rec; w0 = hd.x; type = hd.y & 0xFF; flags = (hd.y >> 8) & 0xFF; }
+    const bool work = slot < nfr && (flags & M17B_F_PARSED) && type == M17B_T_STREAM;
+    const unsigned wmask = __ballot_sync(0xffffffffu, work);
+    if (!wmask) return;
+    for (int i = lane; i < 256; i += 32) crc_tab[i] = g_crc[i];
+    uint16_t dec[FrameStream::STEPS];
+    viterbi_chunked<FrameStream, 2, STREAM_NIN>(ssoft + (c * fcap + lo + tl * 32) * STREAM_NIN + lane, wmask, tile, lane, dec);
+    if (!work) return;
+    __align__(4) uint8_t ob[32];
+    viterbi_traceback<FrameStream>(dec, ob);
+    constexpr uint32_t nbytes = FrameStream::NBYTES;
+    uint16_t k = 0xFFFF;
+    for (uint32_t i = 0; i < nbytes; i++) k = crc16_step(k, ob[i], crc_tab);
+    const uint32_t crc = k;
+    for (uint32_t i = nbytes; i < 32; i++) ob[i] = 0;
+    const uint16_t *oh = (const uint16_t *)ob;                              // data[] as 15 half-words
+    const uint4 ax = *(const uint4 *)(saux + c * fcap + slot);
+    const uint32_t lw01 = ax.x, lw23 = ax.y, golay_e = ax.z;
+    // the 64-byte record: words 0/1 (sym_off, type) and the votes/errors/variance fields come from the framer, the LICH, its
+    // Golay error count and the demap normaliser from k_stream_gather
+    uint32_t *rw = (uint32_t *)rec;
+    const uint32_t w11_old = rw[11], w12 = rw[12];
+    uint4 q0, q1, q2, q3;
+    q0.x = w0;
+    q0.y = (uint32_t)type | ((uint32_t)flags << 8) | (golay_e << 16) | (nbytes << 24);
+    q0.z = ((lw01 >> 16) & 0xFF) | (((lw01 >> 8) & 0xFF) << 8) | ((lw01 & 0xFF) << 16) | (((lw23 >> 16) & 0xFF) << 24);
+    q0.w = ((lw23 >> 8) & 0xFF) | ((lw23 & 0xFF) << 8) | ((uint32_t)oh[0] << 16);
+    q1.x = oh[1] | ((uint32_t)oh[2] << 16);   q1.y = oh[3] | ((uint32_t)oh[4] << 16);
+    q1.z = oh[5] | ((uint32_t)oh[6] << 16);   q1.w = oh[7] | ((uint32_t)oh[8] << 16);
+    q2.x = oh[9] | ((uint32_t)oh[10] << 16);  q2.y = oh[11] | ((uint32_t)oh[12] << 16);
+    q2.z = oh[13] | ((uint32_t)oh[14] << 16); q2.w = crc | (w11_old & 0xFFFF0000u);
+    q3.x = w12; q3.y = ax.w; q3.z = 0; q3.w = 0;
+    uint4 *r4 = (uint4 *)rec;
+    r4[0] = q0; r4[1] = q1; r4[2] = q2; r4[3] = q3;
+}
+
 // stand-alone m17_rx_parse for n independent frames: initialise records, then run the fused decode
 __global__ void k_parse_init(const uint8_t *type, int64_t n, m17b_frame_rec *rec) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -343,30 +511,27 @@ __global__ void k_parse_init(const uint8_t *type, int64_t n, m17b_frame_rec *rec
 __global__ void k_set_i32(int32_t *p, int32_t v) { *p = v; }
 
 #define DECODE_NT 32
-#ifndef M17B_DEC_SMEM
-template <int NT, bool STREAM> static size_t decode_smem() { return (size_t)NT * 193 * 4; }
-#else
-template <int NT, bool STREAM> static size_t decode_smem() { return (size_t)NT * 193 * 4 + (size_t)(STREAM ? 148 : 244) * NT * 2; }
-#endif
+static size_t decode_smem() { return (size_t)DECODE_NT * 193 * 4; }
 
-// frame_rng / max_frames: decode only the records [rng.x, rng.y) of each channel (at most max_frames of them)
+// frame_rng / max_frames: decode only the records [rng.x, rng.y) of each channel (at most max_frames of them).
+// ssoft [nchan * fcap][STREAM_NIN] floats and saux [nchan * fcap] are the scratch between the two stream-frame kernels.
 static int launch_decode(m17b_ctx *ctx, const float *syms, int64_t sym_pitch, int sym_carry, const int32_t *sym_base,
-                         m17b_frame_rec *frames, int64_t fcap, const int32_t *nframes, int64_t nchan, float *soft_out, cudaStream_t st,
+                         m17b_frame_rec *frames, int64_t fcap, const int32_t *nframes, int64_t nchan, float *soft_out, float *ssoft, StreamAux *saux, cudaStream_t st,
                          cudaStream_t aux = nullptr, cudaEvent_t ev_fork = nullptr, cudaEvent_t ev_join = nullptr,
                          const int2 *frame_rng = nullptr, int64_t max_frames = 0, int bert_on = 0) {
     const int tiles = (int)(((frame_rng ? max_frames : fcap) + DECODE_NT - 1) / DECODE_NT);
     // (set on every call: the attribute is per device, a process may drive several)
-    CUDA_TRY(cudaFuncSetAttribute(k_decode_frames<DECODE_NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_smem<DECODE_NT, true>()));
-    CUDA_TRY(cudaFuncSetAttribute(k_decode_frames<DECODE_NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_smem<DECODE_NT, false>()));
-    if ((int64_t)tiles * nchan > 0x7fffffffLL) return M17B_E_ARG;
+    CUDA_TRY(cudaFuncSetAttribute(k_decode_frames<DECODE_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_smem()));
+    if ((int64_t)tiles * nchan * (32 / SG_WARPS) > 0x7fffffffLL) return M17B_E_ARG;
     const unsigned grid = (unsigned)(tiles * nchan);
-    // the two kernels touch disjoint records: run the (rare, long, sparse) LSF/packet one beside the stream-frame one
+    // the kernels touch disjoint records: run the (rare, long, sparse) LSF/packet one beside the stream-frame ones
     cudaStream_t st2 = st;
     if (aux) { CUDA_TRY(cudaEventRecord(ev_fork, st)); CUDA_TRY(cudaStreamWaitEvent(aux, ev_fork, 0)); st2 = aux; }
-    k_decode_frames<DECODE_NT, false><<<grid, DECODE_NT, decode_smem<DECODE_NT, false>(), st2>>>(syms, sym_pitch, sym_carry, sym_base, frames, fcap, nframes,
-                                                                                            frame_rng, tiles, soft_out, ctx->d_crc, ctx->d_genc, ctx->d_gerr, bert_on);
-    k_decode_frames<DECODE_NT, true><<<grid, DECODE_NT, decode_smem<DECODE_NT, true>(), st>>>(syms, sym_pitch, sym_carry, sym_base, frames, fcap, nframes,
-                                                                                          frame_rng, tiles, soft_out, ctx->d_crc, ctx->d_genc, ctx->d_gerr, bert_on);
+    k_decode_frames<DECODE_NT><<<grid, DECODE_NT, decode_smem(), st2>>>(syms, sym_pitch, sym_carry, sym_base, frames, fcap, nframes,
+                                                                       frame_rng, tiles, soft_out, ctx->d_crc, ctx->d_genc, ctx->d_gerr, bert_on);
+    k_stream_gather<<<grid * (32 / SG_WARPS), SG_WARPS * 32, 0, st>>>(syms, sym_pitch, sym_carry, sym_base, frames, fcap, nframes, frame_rng, tiles * 32, nchan,
+                                                                     ctx->d_smap, ctx->d_genc, ctx->d_gerr, ssoft, saux, soft_out);
+    k_stream_acs<<<grid, 32, 0, st>>>(ssoft, saux, frames, fcap, nframes, frame_rng, tiles, ctx->d_crc);
     KERNEL_CHECK();
     if (aux) { CUDA_TRY(cudaEventRecord(ev_join, aux)); CUDA_TRY(cudaStreamWaitEvent(st, ev_join, 0)); }
     return M17B_OK;
@@ -377,12 +542,18 @@ extern "C" int m17b_rx_parse_frames(m17b_ctx *ctx, const float *d_sym, const uin
     if (n == 0) return M17B_OK;
     cudaStream_t st = as_stream(stream);
     int32_t *d_n;
+    float *d_ssoft;
+    StreamAux *d_saux;
     CUDA_TRY(cudaMallocAsync((void **)&d_n, sizeof(int32_t), st));
+    CUDA_TRY(cudaMallocAsync((void **)&d_ssoft, (size_t)n * STREAM_NIN * sizeof(float), st));
+    CUDA_TRY(cudaMallocAsync((void **)&d_saux, (size_t)n * sizeof(StreamAux), st));
     k_set_i32<<<1, 1, 0, st>>>(d_n, (int32_t)n);
     k_parse_init<<<grid_for(n, 256), 256, 0, st>>>(d_type, n, d_rec);
     KERNEL_CHECK();
-    int rc = launch_decode(ctx, d_sym, 0, 0, nullptr, d_rec, n, d_n, 1, d_soft, st);
+    int rc = launch_decode(ctx, d_sym, 0, 0, nullptr, d_rec, n, d_n, 1, d_soft, d_ssoft, d_saux, st);
     CUDA_TRY(cudaFreeAsync(d_n, st));
+    CUDA_TRY(cudaFreeAsync(d_ssoft, st));
+    CUDA_TRY(cudaFreeAsync(d_saux, st));
     return rc;
 }
 
@@ -396,60 +567,13 @@ extern "C" int m17b_rx_parse_frames(m17b_ctx *ctx, const float *d_sym, const uin
 template <class F, int PAT, int NIN>
 __global__ void __launch_bounds__(32) k_viterbi_punct(const float *__restrict__ soft, int64_t n, uint8_t *__restrict__ bytes) {
     __shared__ float tile[2][32][33];
-    constexpr int NCH = (F::STEPS + VP_CHUNK - 1) / VP_CHUNK;
-    static_assert(F::STEPS % 2 == 0 && VP_CHUNK % 2 == 0, "two steps per iteration");
     const int lane = threadIdx.x;
     const int64_t f0 = (int64_t)blockIdx.x * 32, f = f0 + lane;
     const int nrows = (int)min((int64_t)32, n - f0);
-    const float *base = soft + f0 * NIN + lane;
-    auto stage = [&](int c) {                                       // chunk c: inputs [koff[c], koff[c + 1]) of every row
-        if (c < NCH) {
-            const int k0 = c_punct.koff[PAT - 1][c], cnt = min((int)c_punct.koff[PAT - 1][c + 1], NIN) - k0;
-            if (lane < cnt) {
-                const float *src = base + k0;
-                const unsigned dst = (unsigned)__cvta_generic_to_shared(&tile[c & 1][0][lane]);
-#pragma unroll 8
-                for (int r = 0; r < 32; r++)
-                    if (r < nrows) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + r * 33 * 4), "l"(src + (int64_t)r * NIN));
-            }
-        }
-        asm volatile("cp.async.commit_group;");
-    };
-    stage(0);
-    stage(1);
     uint16_t dec[F::STEPS];
-    float ma[16], mb[16];
-    viterbi_init(ma);
-    for (int c = 0; c < NCH; c++) {
-        asm volatile("cp.async.wait_group 1;");                      // chunk c has landed (chunk c + 1 may still be in flight)
-        __syncwarp();
-        const float *row = tile[c & 1][lane];
-        const int t0 = c * VP_CHUNK, t1 = min(t0 + VP_CHUNK, F::STEPS);
-        int k = 0;
-        for (int t = t0; t < t1; t += 2) {
-            const unsigned k0 = c_punct.keep[PAT - 1][t], k1 = c_punct.keep[PAT - 1][t + 1];      // warp-uniform
-            const float s1 = (k0 & 1) ? row[k++] : 0.0f;
-            const float s2 = (k0 & 2) ? row[k++] : 0.0f;
-            const float s3 = (k1 & 1) ? row[k++] : 0.0f;
-            const float s4 = (k1 & 2) ? row[k++] : 0.0f;
-            dec[t] = (uint16_t)viterbi_step_pp(ma, mb, s1, s2);
-            dec[t + 1] = (uint16_t)viterbi_step_pp(mb, ma, s3, s4);
-        }
-        __syncwarp();                                                // every lane is done with the tile: it may be refilled
-        stage(c + 2);
-    }
+    viterbi_chunked<F, PAT, NIN>(soft + f0 * NIN + lane, nrows == 32 ? 0xffffffffu : (1u << nrows) - 1u, tile, lane, dec);
     if (f >= n) return;
-    unsigned s = 0;
-    uint8_t *o = bytes + f * F::NBYTES;
-    for (int t = F::STEPS - 1; t > 8 * F::NBYTES; t--) s = trace_prev(s, dec[t]);
-    for (int j = F::NBYTES - 1; j >= 0; j--) {
-        unsigned d[8], acc = 0;
-#pragma unroll
-        for (int b = 0; b < 8; b++) d[b] = dec[8 * j + 8 - b];
-#pragma unroll
-        for (int b = 0; b < 8; b++) { s = trace_prev(s, d[b]); acc |= ((s >> 3) & 1u) << b; }
-        o[j] = (uint8_t)acc;
-    }
+    viterbi_traceback<F>(dec, bytes + f * F::NBYTES);
 }
 template <class F, int PAT, int NIN> static int launch_vp(const float *d_soft, int64_t n, uint8_t *d_bytes, cudaStream_t st) {
     k_viterbi_punct<F, PAT, NIN><<<grid_for(n, 32), 32, 0, st>>>(d_soft, n, d_bytes);

@@ -170,6 +170,14 @@ extern "C" int m17b_ctx_create(int device, m17b_ctx **out) {
         (rc = upload(&ctx->d_mf, ctx->h_mf, M17B_NF * M17B_FN)) || (rc = upload(&ctx->d_md, ctx->h_md, M17B_NF * M17B_FN)) ||
         (rc = upload(&ctx->d_prbs, prbs, 511))) { free(genc); free(gerr); free(ctx); return rc; }
     free(genc); free(gerr);
+    {
+        uint16_t smap[STREAM_NIN + 96];
+        int k = 0;
+        for (int p = 0; p < 296; p++) if (gm.p2[p] != MAP_ERASE) smap[k++] = gm.p2[p];
+        if (k != STREAM_NIN) { free(ctx); return M17B_E_ARG; }
+        for (int b = 0; b < 96; b++) smap[STREAM_NIN + b] = gm.lich[b];
+        if ((rc = upload(&ctx->d_smap, smap, (size_t)STREAM_NIN + 96))) { free(ctx); return rc; }
+    }
     CUDA_TRY(cudaMemcpyToSymbol(c_maps, &gm, sizeof(gm)));
     CUDA_TRY(cudaMemcpyToSymbol(c_tx, &tm, sizeof(tm)));
     CUDA_TRY(cudaMemcpyToSymbol(c_punct, &ps, sizeof(ps)));
@@ -192,7 +200,7 @@ extern "C" int m17b_ctx_create(int device, m17b_ctx **out) {
 
 extern "C" int m17b_ctx_destroy(m17b_ctx *ctx) {
     if (!ctx) return M17B_E_ARG;
-    cudaFree(ctx->d_crc); cudaFree(ctx->d_genc); cudaFree(ctx->d_gerr); cudaFree(ctx->d_mf); cudaFree(ctx->d_md); cudaFree(ctx->d_prbs);
+    cudaFree(ctx->d_crc); cudaFree(ctx->d_genc); cudaFree(ctx->d_gerr); cudaFree(ctx->d_mf); cudaFree(ctx->d_md); cudaFree(ctx->d_prbs); cudaFree(ctx->d_smap);
     free(ctx);
     return M17B_OK;
 }
