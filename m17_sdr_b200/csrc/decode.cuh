@@ -391,47 +391,56 @@ __global__ void __launch_bounds__(SG_WARPS * 32) k_stream_gather(const float *__
                                                                  const int2 *__restrict__ frame_rng, int slots_per_chan, int64_t nchan,
                                                                  const uint16_t *__restrict__ smap, const uint16_t *__restrict__ genc, const uint16_t *__restrict__ gerr,
                                                                  float *__restrict__ ssoft, StreamAux *__restrict__ saux, float *soft_out) {
-    __shared__ float rowbuf[SG_WARPS][192];
-    __shared__ uint16_t map_s[STREAM_NIN + 96];
+    __shared__ float soft2_s[SG_WARPS][368];                     // the frame's soft values in natural order: (-m, |m| - 0.6666) per payload symbol
+    __shared__ float hdr_s[SG_WARPS][8];
+    __shared__ uint16_t map_s[STREAM_NIN + 96];                  // 2 * (symbol - 8) + lsb, bit 15 = de-randomiser sign
     for (int i = threadIdx.x; i < STREAM_NIN + 96; i += SG_WARPS * 32) map_s[i] = smap[i];
     __syncthreads();
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t item = (int64_t)blockIdx.x * SG_WARPS + wid;
-    const int64_t c = item / slots_per_chan;
+    const unsigned item = blockIdx.x * SG_WARPS + wid;           // (32-bit: the launch checks the grid; a 64-bit divide is a subroutine)
+    const int64_t c = item / (unsigned)slots_per_chan;
     if (c >= nchan) return;
     int lo = 0, nfr;
     if (frame_rng) { const int2 r = frame_rng[c]; lo = r.x; nfr = r.y; }
     else nfr = (int)min((int64_t)nframes[c], fcap);
-    const int slot = lo + (int)(item % slots_per_chan);
+    const int slot = lo + (int)(item - (unsigned)c * (unsigned)slots_per_chan);
     if (slot >= nfr) return;
     const uint2 hd = *(const uint2 *)(frames + c * fcap + slot);            // (every lane reads the same 8 bytes)
     if ((hd.y & 0xFF) != M17B_T_STREAM || !((hd.y >> 8) & M17B_F_PARSED)) return;
     const float *src = syms + c * sym_pitch + sym_carry + ((int32_t)hd.x - (sym_base ? sym_base[c] : 0));
-    float *row = rowbuf[wid];
     float v[6];
 #pragma unroll
     for (int k = 0; k < 6; k++) v[k] = src[lane + 32 * k];
-    if (lane < 8) row[lane] = v[0];
+    if (lane < 8) hdr_s[wid][lane] = v[0];
     __syncwarp();
     float hdr[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) hdr[i] = row[i];
+    for (int i = 0; i < 8; i++) hdr[i] = hdr_s[wid][i];
     const float cor = demap_cor(hdr);
+    // both soft values of every payload symbol once (m = in * mag, m17_dsp.cpp:38-41); the maps below only pick and sign them
+    float2 *s2 = (float2 *)soft2_s[wid];
 #pragma unroll
-    for (int k = 0; k < 6; k++) if (lane + 32 * k >= 8) row[lane + 32 * k] = v[k] * cor;     // m = in * mag  (m17_dsp.cpp:38), once per symbol
+    for (int k = 0; k < 6; k++) {
+        const int idx = lane + 32 * k - 8;
+        if (idx >= 0) { const float m = v[k] * cor; s2[idx] = make_float2(-m, demap_lsb(m)); }
+    }
     __syncwarp();
+    const float *soft2 = soft2_s[wid];
+    // (e & 0x8000) << 16 is the sign bit: m17_de_correlate_1 negates the soft value where the randomiser bit is set (m17_correlate.cpp:29)
+    auto pick = [&](unsigned e) { return __uint_as_float(__float_as_uint(soft2[e & 0x1FFu]) ^ ((e & 0x8000u) << 16)); };
     const int64_t fidx = c * fcap + slot;
     float *o = ssoft + fidx * STREAM_NIN;
-    for (int j = lane; j < STREAM_NIN; j += 32) o[j] = gather_soft(row, map_s[j]);
+#pragma unroll
+    for (int j = 0; j < STREAM_NIN; j += 32) if (j + lane < STREAM_NIN) o[j + lane] = pick(map_s[j + lane]);
     if (soft_out) {
-        float2 *so = (float2 *)(soft_out + fidx * 368);
-        for (int k = lane; k < 184; k += 32) { const float m = row[8 + k]; so[k] = make_float2(-m, demap_lsb(m)); }
+        float *so = soft_out + fidx * 368;
+        for (int k = lane; k < 368; k += 32) so[k] = soft2[k];
     }
     // 4 x hard_decode_24_bits (m17_bit_utils.cpp:180-187: bit = soft >= 0) + m_17_golay_decode: ballot bit i = LICH bit i, and
     // the words are MSB first, so the reversed ballots read as one 96-bit big-endian string
-    const unsigned B0 = __brev(__ballot_sync(0xffffffffu, gather_hard(row, map_s[STREAM_NIN + lane])));
-    const unsigned B1 = __brev(__ballot_sync(0xffffffffu, gather_hard(row, map_s[STREAM_NIN + 32 + lane])));
-    const unsigned B2 = __brev(__ballot_sync(0xffffffffu, gather_hard(row, map_s[STREAM_NIN + 64 + lane])));
+    const unsigned B0 = __brev(__ballot_sync(0xffffffffu, pick(map_s[STREAM_NIN + lane]) >= 0.0f));
+    const unsigned B1 = __brev(__ballot_sync(0xffffffffu, pick(map_s[STREAM_NIN + 32 + lane]) >= 0.0f));
+    const unsigned B2 = __brev(__ballot_sync(0xffffffffu, pick(map_s[STREAM_NIN + 64 + lane]) >= 0.0f));
     const uint32_t word = lane == 0 ? B0 >> 8 : lane == 1 ? ((B0 & 0xFFu) << 16) | (B1 >> 16) : lane == 2 ? ((B1 & 0xFFFFu) << 8) | (B2 >> 24) : B2 & 0xFFFFFFu;
     uint32_t w = 0;
     int ge = 0;
@@ -522,7 +531,7 @@ static int launch_decode(m17b_ctx *ctx, const float *syms, int64_t sym_pitch, in
     const int tiles = (int)(((frame_rng ? max_frames : fcap) + DECODE_NT - 1) / DECODE_NT);
     // (set on every call: the attribute is per device, a process may drive several)
     CUDA_TRY(cudaFuncSetAttribute(k_decode_frames<DECODE_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_smem()));
-    if ((int64_t)tiles * nchan * (32 / SG_WARPS) > 0x7fffffffLL) return M17B_E_ARG;
+    if ((int64_t)tiles * nchan * 32 > 0x7fffffffLL) return M17B_E_ARG;          // the gather kernel indexes (channel, slot) items in 32 bits
     const unsigned grid = (unsigned)(tiles * nchan);
     // the kernels touch disjoint records: run the (rare, long, sparse) LSF/packet one beside the stream-frame ones
     cudaStream_t st2 = st;

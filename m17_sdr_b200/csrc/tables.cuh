@@ -173,9 +173,11 @@ extern "C" int m17b_ctx_create(int device, m17b_ctx **out) {
     {
         uint16_t smap[STREAM_NIN + 96];
         int k = 0;
-        for (int p = 0; p < 296; p++) if (gm.p2[p] != MAP_ERASE) smap[k++] = gm.p2[p];
+        // entry -> index into the frame's 368 soft values in natural order (2 * (symbol - 8) + lsb), bit 15 = negate
+        auto compact = [](uint16_t e) { return (uint16_t)((2 * ((e & 0xFF) - 8) + ((e & MAP_LSB) ? 1 : 0)) | ((e & MAP_NEG) ? 0x8000 : 0)); };
+        for (int p = 0; p < 296; p++) if (gm.p2[p] != MAP_ERASE) smap[k++] = compact(gm.p2[p]);
         if (k != STREAM_NIN) { free(ctx); return M17B_E_ARG; }
-        for (int b = 0; b < 96; b++) smap[STREAM_NIN + b] = gm.lich[b];
+        for (int b = 0; b < 96; b++) smap[STREAM_NIN + b] = compact(gm.lich[b]);
         if ((rc = upload(&ctx->d_smap, smap, (size_t)STREAM_NIN + 96))) { free(ctx); return rc; }
     }
     CUDA_TRY(cudaMemcpyToSymbol(c_maps, &gm, sizeof(gm)));
