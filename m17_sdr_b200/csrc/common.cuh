@@ -66,6 +66,8 @@ struct __align__(16) TxMaps {
 struct m17b_ctx {
     int device;
     uint16_t *d_crc;     // [256]   CRC-16/M17 byte table            m17_crc.cpp:8-24
+    uint16_t *d_crcpos;  // [30][256] + [1]  CRC of a 30-byte LSF as an XOR of per-position contributions (k_post): entry [i][b] = the byte
+                         //          table entry of b carried through the 29 - i zero-byte steps that follow it, [30][0] = the 0xFFFF preset carried through 30
     uint16_t *d_genc;    // [4096]  Golay parity table               m17_golay.cpp:31-40
     uint16_t *d_gerr;    // [4096]  Golay syndrome table             m17_golay.cpp:49-72
     float    *d_mf;      // [40][31] matched-filter bank             m17_rx_sync.cpp:13

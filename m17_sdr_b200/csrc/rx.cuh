@@ -62,41 +62,49 @@ __global__ void k_rx_reset(RxChanState *st, int64_t nchan) {
     st[c].index = 10;
 }
 
-// Sequential per-channel tail of m17_rx_parse (update_lich / parse_packet / delivery gate).  One WARP per channel:
-// the lanes stage 32 record headers at a time into shared memory with one strided 16-byte load each, lane 0 walks
-// them in order against the channel's LICH cache (kept in shared memory for the duration of the call), and the
-// lanes write the updated flag bytes back.  The 30-byte CRC of m_lsf[0] is only recomputed when a LICH chunk
-// actually changes the cache -- while a stream runs the same six chunks repeat, so the cached verdict is reused
-// (identical result: the CRC is a pure function of the 30 bytes).
-#define POST_WARPS 4
+// Sequential per-channel tail of m17_rx_parse (update_lich / parse_packet / delivery gate).  One WARP per channel, 32 records
+// per step, one record header per lane (one strided 16-byte load each).  Only a record that CHANGES per-channel state has to be
+// taken in order: a LICH chunk that differs from the cache, an LSF / packet / BERT frame.  So each step alternates between
+//   (a) all lanes: which of the records not yet done would change the state as it is now?  (ballot -> first such record j);
+//       the records before j only read the state, and their flags follow from it lane-parallel;
+//   (b) the warp together on record j: the five new bytes go into the cache, the 30-byte CRC of m_lsf[0] is ONE table look-up
+//       per lane (position table d_crcpos, tables.cuh) and an XOR reduction, copy_lich / the snapshot are lane-per-byte copies;
+// until the 32 records are done.  While a stream runs the same six chunks repeat and (a) finishes the step at once; on a noisy
+// channel every wrongly corrected chunk costs one round of (b) (~100 cycles instead of a 30-step dependent CRC chain on one lane:
+// 0.107 -> see DESIGN.md).  The CRC verdict of an unchanged cache is carried, never recomputed (a pure function of the 30 bytes).
+#define POST_WARPS 1
 // For the M17-over-UDP gateway output (net.cuh) the kernel also keeps the history of the validated link-setup data m_lsf[1]
 // over the call: snapshot 0 is the cache as the call found it, a new snapshot is taken whenever copy_lich() changes it, and
 // every record gets the number of the snapshot that was current when it was parsed.
-struct PostWarpSmem { uint4 hdr[32]; uint8_t lsf0[32], lsf1[32], ver[32]; };
+struct PostWarpSmem { uint4 hdr[32]; uint8_t lsf0[32], lsf1[32]; };
 __global__ void __launch_bounds__(POST_WARPS * 32) k_post(m17b_frame_rec *frames, int64_t fcap, const int32_t *__restrict__ nframes, int64_t nchan,
-                                                          RxChanState *st, const uint16_t *__restrict__ g_crc, unsigned long long *stats,
+                                                          RxChanState *st, const uint16_t *__restrict__ g_crcpos, unsigned long long *stats,
                                                           uint8_t *__restrict__ lsf_snap, int nsnap, uint8_t *__restrict__ lsf_ver,
                                                           const uint8_t *__restrict__ g_prbs, int bert_on) {
-    __shared__ uint16_t tab[256];
     __shared__ PostWarpSmem sm_all[POST_WARPS];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = g_crc[i];
-    __syncthreads();
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t c = (int64_t)blockIdx.x * POST_WARPS + wid;
     if (c >= nchan) return;
+    constexpr unsigned FULL = 0xffffffffu;
     PostWarpSmem &sm = sm_all[wid];
     RxChanState *S = st + c;
     sm.lsf0[lane] = S->lsf[0][lane];
     sm.lsf1[lane] = S->lsf[1][lane];
     __syncwarp();
-    auto crc30 = [&](const uint8_t *p) { uint16_t k = 0xFFFF; for (int i = 0; i < 30; i++) k = crc16_step(k, p[i], tab); return k; };
-    bool lsf0_ok = false, lsf1_ok = false;
-    if (lane == 0) { lsf0_ok = crc30(sm.lsf0) == 0; lsf1_ok = crc30(sm.lsf1) == 0; }
+    const unsigned crc_preset = __ldg(g_crcpos + 30 * 256);
+    // CRC-16 of 30 bytes, byte `lane` supplied by lane < 30 (m17_crc_array_encode, m17_crc.cpp:26-35); the result is warp-uniform
+    auto crc30 = [&](unsigned byte) {
+        const unsigned v = lane < 30 ? (unsigned)__ldg(g_crcpos + lane * 256 + byte) : 0u;
+        return __reduce_xor_sync(FULL, v) ^ crc_preset;
+    };
+    // warp-uniform channel state
+    bool ok0 = crc30(sm.lsf0[lane]) == 0, ok1 = crc30(sm.lsf1[lane]) == 0;
     uint8_t *snap = lsf_snap + c * (int64_t)nsnap * 32;
     snap[lane] = sm.lsf1[lane];                                               // snapshot 0
-    bool dirty = __any_sync(0xffffffffu, lane < 30 && sm.lsf0[lane] != sm.lsf1[lane]);
+    bool dirty = __any_sync(FULL, lane < 30 && sm.lsf0[lane] != sm.lsf1[lane]);
     int ver = 0;
-    unsigned long long n_stream = 0, n_gerr = 0, n_deliv = 0, n_lsf = 0;
+    int packet_idx = S->packet_idx;
+    unsigned n_stream = 0, n_gerr = 0, n_deliv = 0, n_lsf = 0;
     const int n = nframes[c];
     m17b_frame_rec *base = frames + c * fcap;
     for (int k0 = 0; k0 < n; k0 += 32) {
@@ -105,83 +113,84 @@ __global__ void __launch_bounds__(POST_WARPS * 32) k_post(m17b_frame_rec *frames
         if (k < n) h = *(const uint4 *)(base + k);                 // bytes 0..15: sym_off, type, flags, golay_err, nbytes, lich[6], data[0..1]
         sm.hdr[lane] = h;
         __syncwarp();
-        // Fast path.  While a stream runs the same six LICH chunks repeat, so a batch of 32 records usually changes nothing in
-        // the cache; then every record's flags follow from the cache state alone and the lanes set them in parallel.  Any
-        // record that would modify per-channel state (a new LICH chunk, an LSF / packet / BERT frame) sends the whole batch
-        // down the in-order walk below.
-        {
-            const int type = h.y & 0xFF, fl = (h.y >> 8) & 0xFF;
-            const bool parsed = (k < n) && (fl & M17B_F_PARSED);
-            const int seq = (int)((h.w >> 8) & 0xFF) >> 5;                       // lich[5] >> 5
-            bool simple = true;
-            if (parsed) {
-                if (type == M17B_T_STREAM) {
-                    if (seq < 6) {
-                        const uint8_t l[5] = {(uint8_t)h.z, (uint8_t)(h.z >> 8), (uint8_t)(h.z >> 16), (uint8_t)(h.z >> 24), (uint8_t)h.w};
-#pragma unroll
-                        for (int i = 0; i < 5; i++) simple &= sm.lsf0[seq * 5 + i] == l[i];
-                    }
-                } else if (type == M17B_T_LSF || type == M17B_T_PACKET || (type == M17B_T_BERT && bert_on)) simple = false;
+        const int type = h.y & 0xFF, fl = (h.y >> 8) & 0xFF;
+        const bool parsed = (k < n) && (fl & M17B_F_PARSED);
+        const bool is_stream = parsed && type == M17B_T_STREAM;
+        const int seq = (int)((h.w >> 8) & 0xFF) >> 5;                           // lich[5] >> 5
+        const bool chunk = is_stream && seq < 6;                                 // update_lich stores it, m17_rx_parse.cpp:71-85
+        const bool other = parsed && (type == M17B_T_LSF || type == M17B_T_PACKET || (type == M17B_T_BERT && bert_on));
+        const int ge = is_stream ? (int)((h.y >> 16) & 0xFF) : 0;
+        int nf = fl, myver = 0;
+        int pos = 0;
+        for (;;) {
+            // (a) who would change the state as it is now?
+            bool differs = false;
+            if (chunk && lane >= pos) {
+                const uint8_t *q = &sm.lsf0[seq * 5];
+                differs = q[0] != (uint8_t)h.z || q[1] != (uint8_t)(h.z >> 8) || q[2] != (uint8_t)(h.z >> 16) || q[3] != (uint8_t)(h.z >> 24) || q[4] != (uint8_t)h.w;
             }
-            const int st0 = __shfl_sync(0xffffffffu, (int)lsf0_ok | ((int)lsf1_ok << 1) | ((int)dirty << 2), 0);
-            const int ver0 = __shfl_sync(0xffffffffu, ver, 0);
-            if (__all_sync(0xffffffffu, simple) && !(st0 & 4)) {
-                const bool ok0 = st0 & 1, ok1 = st0 & 2;                         // cache unchanged and clean: lsf[1] == lsf[0]
-                const bool is_stream = parsed && type == M17B_T_STREAM;
-                const bool ev = is_stream && seq < 6 && ok0;                     // update_lich -> copy_lich -> parse_lsf
-                const bool dl = is_stream && (ok1 || ev);                        // :148-158
-                int ge = is_stream ? (int)((h.y >> 16) & 0xFF) : 0;
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) ge += __shfl_xor_sync(0xffffffffu, ge, d);
-                const unsigned ms = __ballot_sync(0xffffffffu, is_stream), me = __ballot_sync(0xffffffffu, ev), md = __ballot_sync(0xffffffffu, dl);
-                if (lane == 0) {
-                    n_stream += __popc(ms); n_gerr += (unsigned)ge; n_lsf += __popc(me); n_deliv += __popc(md);
-                    if (me) lsf1_ok = true;
+            const bool chg = lane >= pos && (other || (chunk && (differs || (ok0 && dirty))));
+            const unsigned mch = __ballot_sync(FULL, chg);
+            const int j = mch ? __ffs(mch) - 1 : 32;
+            const bool inr = lane >= pos && lane < j;                            // read-only records of this round
+            const bool ev = inr && chunk && ok0;                                 // update_lich -> copy_lich (a no-op: the cache is clean) -> parse_lsf
+            const bool dl = inr && is_stream && (ok1 || ev);                     // :148-158
+            const unsigned ms = __ballot_sync(FULL, inr && is_stream), me = __ballot_sync(FULL, ev), md = __ballot_sync(FULL, dl);
+            if (ms) {
+                n_stream += __popc(ms); n_lsf += __popc(me); n_deliv += __popc(md);
+                n_gerr += __reduce_add_sync(FULL, inr ? (unsigned)ge : 0u);
+                if (me) ok1 = true;
+            }
+            if (inr) { nf = fl | (ev ? M17B_F_LSF_EVENT : 0) | (dl ? M17B_F_DELIVERED : 0); myver = parsed ? ver : 0; }
+            if (j == 32) break;
+            // (b) record j, the warp together
+            const uint4 q = sm.hdr[j];
+            const int tj = q.y & 0xFF;
+            int flags = (q.y >> 8) & 0xFF;
+            if (tj == M17B_T_STREAM) {
+                n_stream++;
+                n_gerr += (q.y >> 16) & 0xFF;
+                const int sj = (int)((q.w >> 8) & 0xFF) >> 5;
+                const unsigned nb = lane < 4 ? (q.z >> (8 * lane)) & 0xFFu : q.w & 0xFFu;
+                bool changed = false;
+                if (lane < 5) { changed = sm.lsf0[sj * 5 + lane] != (uint8_t)nb; sm.lsf0[sj * 5 + lane] = (uint8_t)nb; }
+                changed = __any_sync(FULL, changed);
+                __syncwarp();
+                if (changed) { ok0 = crc30(sm.lsf0[lane]) == 0; dirty = true; }
+                if (ok0) {
+                    if (dirty) {
+                        sm.lsf1[lane] = sm.lsf0[lane];                           // copy_lich (bytes 30, 31 of both are zero)
+                        if (ver < nsnap - 1) ver++;
+                        snap[ver * 32 + lane] = lane < 30 ? sm.lsf0[lane] : 0;
+                        dirty = false;
+                    }
+                    ok1 = true;
+                    flags |= M17B_F_LSF_EVENT; n_lsf++;
                 }
-                if (k < n) {
-                    const int nf = fl | (ev ? M17B_F_LSF_EVENT : 0) | (dl ? M17B_F_DELIVERED : 0);
-                    if (nf != fl) ((uint8_t *)(base + k))[5] = (uint8_t)nf;
-                    lsf_ver[c * fcap + k] = parsed ? (uint8_t)ver0 : 0;
+                if (ok1) { flags |= M17B_F_DELIVERED; n_deliv++; }              // :148-158
+                __syncwarp();
+            } else if (tj == M17B_T_LSF) {
+                // decode_link_frame checks the CRC of m_packet, not of the decoded bytes (m17_rx_parse.cpp:98);
+                // the honest verdict for the decoded LSF is the record's crc field
+                if (crc30(lane < 30 ? S->packet[lane] : 0) == 0) { flags |= M17B_F_LSF_EVENT; n_lsf++; }
+            } else if (tj == M17B_T_PACKET) {
+                // parse_packet (m17_rx_parse.cpp:34-51) including its index bug; the copy is clamped to the buffer
+                const m17b_frame_rec *r = base + k0 + j;
+                const int last = r->data[25];
+                const int eof = last >> 7, fn = (last >> 2) & 0x1F;
+                if (eof) {
+                    const int room = 800 - packet_idx, mm = fn < room ? fn : room;
+                    if (lane < mm) S->packet[packet_idx + lane] = r->data[lane];
+                    packet_idx = 0;
+                } else {
+                    if (lane < 25) S->packet[fn * 25 + lane] = r->data[lane];
+                    packet_idx = fn * 25;
                 }
                 __syncwarp();
-                continue;
-            }
-        }
-        if (lane == 0) {
-            const int m = (n - k0 < 32) ? n - k0 : 32;
-            for (int j = 0; j < m; j++) {
-                const uint4 q = sm.hdr[j];
-                const int type = q.y & 0xFF;
-                int flags = (q.y >> 8) & 0xFF;
-                if (!(flags & M17B_F_PARSED)) continue;
-                if (type == M17B_T_LSF) {
-                    // decode_link_frame checks the CRC of m_packet, not of the decoded bytes (m17_rx_parse.cpp:98);
-                    // the honest verdict for the decoded LSF is the record's crc field
-                    if (crc30(S->packet) == 0) { flags |= M17B_F_LSF_EVENT; n_lsf++; }
-                } else if (type == M17B_T_STREAM) {
-                    n_stream++;
-                    n_gerr += (q.y >> 16) & 0xFF;
-                    const uint8_t l[6] = {(uint8_t)q.z, (uint8_t)(q.z >> 8), (uint8_t)(q.z >> 16), (uint8_t)(q.z >> 24), (uint8_t)q.w, (uint8_t)(q.w >> 8)};
-                    const int seq = l[5] >> 5;                                          // update_lich, m17_rx_parse.cpp:71-85
-                    if (seq < 6) {
-                        bool changed = false;
-                        for (int i = 0; i < 5; i++) { changed |= sm.lsf0[seq * 5 + i] != l[i]; sm.lsf0[seq * 5 + i] = l[i]; }
-                        if (changed) { lsf0_ok = crc30(sm.lsf0) == 0; dirty = true; }
-                        if (lsf0_ok) {
-                            for (int i = 0; i < 30; i++) sm.lsf1[i] = sm.lsf0[i];       // copy_lich
-                            lsf1_ok = true;
-                            if (dirty) {
-                                if (ver < nsnap - 1) ver++;
-                                for (int i = 0; i < 32; i++) snap[ver * 32 + i] = i < 30 ? sm.lsf0[i] : 0;
-                                dirty = false;
-                            }
-                            flags |= M17B_F_LSF_EVENT; n_lsf++;
-                        }
-                    }
-                    if (lsf1_ok) { flags |= M17B_F_DELIVERED; n_deliv++; }              // :148-158
-                } else if (type == M17B_T_BERT && bert_on) {
-                    // the decode_bert_frame the reference left empty (m17_rx_parse.cpp:178-180): the frame's 197 PRBS9 bits go
-                    // through m17_prbs9_rx_check (m17_prbs9.cpp:40-64), bit by bit, in order
+            } else if (tj == M17B_T_BERT && bert_on) {
+                // the decode_bert_frame the reference left empty (m17_rx_parse.cpp:178-180): the frame's 197 PRBS9 bits go
+                // through m17_prbs9_rx_check (m17_prbs9.cpp:40-64), bit by bit, in order
+                if (lane == 0) {
                     const m17b_frame_rec *r = base + k0 + j;
                     int idx = S->prbs_idx, state = S->prbs_state;
                     unsigned bad = S->prbs_bad, good = S->prbs_good, eq = S->prbs_eq, dif = S->prbs_dif, nb = 0, ne = 0;
@@ -204,34 +213,22 @@ __global__ void __launch_bounds__(POST_WARPS * 32) k_post(m17b_frame_rec *frames
                     S->prbs_idx = (uint16_t)idx; S->prbs_state = state;
                     S->prbs_bad = (uint16_t)bad; S->prbs_good = (uint16_t)good; S->prbs_eq = (uint16_t)eq; S->prbs_dif = (uint16_t)dif;
                     S->bert_bits += nb; S->bert_errs += ne;
-                } else if (type == M17B_T_PACKET) {
-                    // parse_packet (m17_rx_parse.cpp:34-51) including its index bug; the copy is clamped to the buffer
-                    const m17b_frame_rec *r = base + k0 + j;
-                    const int eof = r->data[25] >> 7, fn = (r->data[25] >> 2) & 0x1F;
-                    if (eof) {
-                        int room = 800 - S->packet_idx, mm = fn < room ? fn : room;
-                        for (int i = 0; i < mm; i++) S->packet[S->packet_idx + i] = r->data[i];
-                        S->packet_idx = 0;
-                    } else {
-                        for (int i = 0; i < 25; i++) S->packet[fn * 25 + i] = r->data[i];
-                        S->packet_idx = fn * 25;
-                    }
                 }
-                sm.hdr[j].y = (q.y & 0xFFFF00FFu) | ((uint32_t)flags << 8);
-                sm.ver[j] = (uint8_t)ver;
+                __syncwarp();
             }
+            if (lane == j) { nf = flags; myver = ver; }
+            pos = j + 1;
         }
-        __syncwarp();
         if (k < n) {
-            const uint32_t y = sm.hdr[lane].y;
-            if (y != h.y) ((uint8_t *)(base + k))[5] = (uint8_t)(y >> 8);
-            lsf_ver[c * fcap + k] = (y >> 8) & M17B_F_PARSED ? sm.ver[lane] : 0;
+            if (nf != fl) ((uint8_t *)(base + k))[5] = (uint8_t)nf;
+            lsf_ver[c * fcap + k] = (uint8_t)myver;
         }
         __syncwarp();
     }
     S->lsf[0][lane] = sm.lsf0[lane];
     S->lsf[1][lane] = sm.lsf1[lane];
     if (lane == 0) {
+        S->packet_idx = packet_idx;
         unsigned long long *q = stats + c * 8;
         q[1] += n_stream; q[2] += n_gerr; q[3] += n_deliv; q[6] += n_lsf;
     }
@@ -469,7 +466,7 @@ static int rx_pipeline(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t *d_iq,
                                aux_stream, ev_fork, ev_join, nullptr, 0, rx->bert);
         if (rc) return rc;
         STAGE_MARK(3);
-        k_post<<<grid_for(nc, POST_WARPS), POST_WARPS * 32, 0, st>>>(frames, rx->fcap, rx->d_nframes + c0, nc, rx->d_state + c0, ctx->d_crc, rx->d_stats + c0 * 8,
+        k_post<<<grid_for(nc, POST_WARPS), POST_WARPS * 32, 0, st>>>(frames, rx->fcap, rx->d_nframes + c0, nc, rx->d_state + c0, ctx->d_crcpos, rx->d_stats + c0 * 8,
                                                                   rx->d_lsf_snap + c0 * rx->nsnap * 32, rx->nsnap, rx->d_lsf_ver + c0 * rx->fcap,
                                                                   ctx->d_prbs, rx->bert);
         KERNEL_CHECK();
@@ -492,7 +489,7 @@ static int rx_pipeline(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t *d_iq,
                            aux_stream, ev_fork, ev_join, nullptr, 0, rx->bert);
         if (rc) return rc;
         STAGE_MARK(3);
-        k_post<<<grid_for(nc, POST_WARPS), POST_WARPS * 32, 0, st>>>(frames, rx->fcap, rx->d_nframes + c0, nc, rx->d_state + c0, ctx->d_crc, rx->d_stats + c0 * 8,
+        k_post<<<grid_for(nc, POST_WARPS), POST_WARPS * 32, 0, st>>>(frames, rx->fcap, rx->d_nframes + c0, nc, rx->d_state + c0, ctx->d_crcpos, rx->d_stats + c0 * 8,
                                                                   rx->d_lsf_snap + c0 * rx->nsnap * 32, rx->nsnap, rx->d_lsf_ver + c0 * rx->fcap,
                                                                   ctx->d_prbs, rx->bert);
         KERNEL_CHECK();
@@ -526,7 +523,7 @@ static int rx_pipeline(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t *d_iq,
         if (rc) return rc;
         rx->last_launches += 3;
     }
-    k_post<<<grid_for(nc, POST_WARPS), POST_WARPS * 32, 0, rx->s_dec>>>(frames, rx->fcap, rx->d_nframes + c0, nc, rx->d_state + c0, ctx->d_crc, rx->d_stats + c0 * 8,
+    k_post<<<grid_for(nc, POST_WARPS), POST_WARPS * 32, 0, rx->s_dec>>>(frames, rx->fcap, rx->d_nframes + c0, nc, rx->d_state + c0, ctx->d_crcpos, rx->d_stats + c0 * 8,
                                                                   rx->d_lsf_snap + c0 * rx->nsnap * 32, rx->nsnap, rx->d_lsf_ver + c0 * rx->fcap,
                                                                   ctx->d_prbs, rx->bert);
     KERNEL_CHECK();
@@ -613,7 +610,7 @@ extern "C" int m17b_rx_symbols(m17b_rx *rx, const float *d_syms, int64_t pitch, 
     int rc = launch_decode(ctx, rx->d_syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base, rx->d_frames, rx->fcap, rx->d_nframes, rx->nchan, nullptr, rx->d_ssoft, rx->d_saux, st,
                            rx->aux_stream, rx->ev_fork, rx->ev_join, nullptr, 0, rx->bert);
     if (rc) return rc;
-    k_post<<<grid_for(rx->nchan, POST_WARPS), POST_WARPS * 32, 0, st>>>(rx->d_frames, rx->fcap, rx->d_nframes, rx->nchan, rx->d_state, ctx->d_crc, rx->d_stats,
+    k_post<<<grid_for(rx->nchan, POST_WARPS), POST_WARPS * 32, 0, st>>>(rx->d_frames, rx->fcap, rx->d_nframes, rx->nchan, rx->d_state, ctx->d_crcpos, rx->d_stats,
                                                                       rx->d_lsf_snap, rx->nsnap, rx->d_lsf_ver, ctx->d_prbs, rx->bert);
     KERNEL_CHECK();
     rx->last_launches = 4;
@@ -735,7 +732,7 @@ static int rx_pipeline_pieces(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t
         if (rc) return rc;
         rx->last_launches += 4;
     }
-    k_post<<<grid_for(nc, POST_WARPS), POST_WARPS * 32, 0, st>>>(frames, rx->fcap, rx->d_nframes + c0, nc, rx->d_state + c0, ctx->d_crc, rx->d_stats + c0 * 8,
+    k_post<<<grid_for(nc, POST_WARPS), POST_WARPS * 32, 0, st>>>(frames, rx->fcap, rx->d_nframes + c0, nc, rx->d_state + c0, ctx->d_crcpos, rx->d_stats + c0 * 8,
                                                               rx->d_lsf_snap + c0 * rx->nsnap * 32, rx->nsnap, rx->d_lsf_ver + c0 * rx->fcap,
                                                               ctx->d_prbs, rx->bert);
     KERNEL_CHECK();

@@ -130,6 +130,22 @@ extern "C" int m17b_ctx_create(int device, m17b_ctx **out) {
         for (int k = 0; k < 8; k++) r = (r & 0x8000) ? (uint16_t)((r << 1) ^ 0x5935) : (uint16_t)(r << 1);
         crc[b] = r;
     }
+    // The CRC register update is linear over GF(2): step(crc, b) = Z(crc) ^ crc[b] with Z(crc) = (crc << 8) ^ crc[crc >> 8] (a zero
+    // byte), so the CRC of 30 bytes is Z^30(0xFFFF) ^ XOR_i Z^(29-i)(crc[b_i]): one table look-up per byte position and an XOR
+    // reduction across the lanes of a warp instead of a 30-step dependent chain (k_post).
+    uint16_t *crcpos = (uint16_t *)malloc(2 * (30 * 256 + 1));
+    {
+        auto Z = [&](uint16_t v) { return (uint16_t)((uint16_t)(v << 8) ^ crc[v >> 8]); };
+        for (int i = 0; i < 30; i++)
+            for (int b = 0; b < 256; b++) {
+                uint16_t v = crc[b];
+                for (int k = 0; k < 29 - i; k++) v = Z(v);
+                crcpos[i * 256 + b] = v;
+            }
+        uint16_t v = 0xFFFF;
+        for (int k = 0; k < 30; k++) v = Z(v);
+        crcpos[30 * 256] = v;
+    }
     // Golay parity (m17_golay.cpp:31-40) and syndrome -> (weight, data error) tables.  The syndrome table is the
     // reference's brute-force scan: all 24-bit words of weight <= 4 in ascending order, last writer wins, after the
     // 0x400 pre-fill of entries 0..0xFFE (m17_golay.cpp:49-72) -- the order decides which 4-bit pattern
@@ -166,10 +182,10 @@ extern "C" int m17b_ctx_create(int device, m17b_ctx **out) {
         }
     }
 
-    if ((rc = upload(&ctx->d_crc, crc, 256)) || (rc = upload(&ctx->d_genc, genc, 4096)) || (rc = upload(&ctx->d_gerr, gerr, 4096)) ||
+    if ((rc = upload(&ctx->d_crc, crc, 256)) || (rc = upload(&ctx->d_crcpos, crcpos, 30 * 256 + 1)) || (rc = upload(&ctx->d_genc, genc, 4096)) || (rc = upload(&ctx->d_gerr, gerr, 4096)) ||
         (rc = upload(&ctx->d_mf, ctx->h_mf, M17B_NF * M17B_FN)) || (rc = upload(&ctx->d_md, ctx->h_md, M17B_NF * M17B_FN)) ||
-        (rc = upload(&ctx->d_prbs, prbs, 511))) { free(genc); free(gerr); free(ctx); return rc; }
-    free(genc); free(gerr);
+        (rc = upload(&ctx->d_prbs, prbs, 511))) { free(genc); free(gerr); free(crcpos); free(ctx); return rc; }
+    free(genc); free(gerr); free(crcpos);
     {
         uint16_t smap[STREAM_NIN + 96];
         int k = 0;
@@ -202,7 +218,7 @@ extern "C" int m17b_ctx_create(int device, m17b_ctx **out) {
 
 extern "C" int m17b_ctx_destroy(m17b_ctx *ctx) {
     if (!ctx) return M17B_E_ARG;
-    cudaFree(ctx->d_crc); cudaFree(ctx->d_genc); cudaFree(ctx->d_gerr); cudaFree(ctx->d_mf); cudaFree(ctx->d_md); cudaFree(ctx->d_prbs); cudaFree(ctx->d_smap);
+    cudaFree(ctx->d_crc); cudaFree(ctx->d_crcpos); cudaFree(ctx->d_genc); cudaFree(ctx->d_gerr); cudaFree(ctx->d_mf); cudaFree(ctx->d_md); cudaFree(ctx->d_prbs); cudaFree(ctx->d_smap);
     free(ctx);
     return M17B_OK;
 }
