@@ -12,8 +12,9 @@
 //      lane l hypothesises acc[60 l] = RN(base + 60 l * delta) -- exact as long as no add was rounded since `base` --
 //      runs its 60 adds, and compares its end value bit for bit with the next lane's start; the first mismatch becomes
 //      the new base for the lanes behind it (adds only round where |acc| crosses a binade upwards: a handful per block);
-//   2. every lane mixes and limits its 60 samples (double sincos, IEEE sqrt / divide) into shared memory;
-//   3. the discriminator runs sample-parallel over the limited samples (coalesced stores of the kept fifth);
+//   2. every lane mixes, limits and discriminates its 60 samples (IEEE sqrt / divide; the two samples of history a lane's first
+//      two values need come from the previous lane by shuffle) -- only the 1920 discriminator values go to shared memory;
+//   3. the kept fifth is stored lane-parallel (coalesced);
 //   4. lane 0 adds the 1920 discriminator values in the reference's order (the fp32 sum is not associative) and updates
 //      the loop: delta -= 0.1 * mean while in a frame, phase wrapped by modf.
 // cos/sin: a lane's phases are covered by one double sincos and a double rotation recurrence (step 2), good to ~1e-14; after
@@ -25,17 +26,41 @@
 
 #define AFC_PER_LANE 60            // 1920 / 32
 
+// 15.4 KB per warp (with the timing loop's 6.2 KB: 8 warps = two CTAs per SM, so that 1024 channels are resident at once).
 struct AfcWarpSmem {
-    float2 lim[M17B_BLOCK_SAMPLES + 2];     // [0], [1] = z[1], z[0] carried in; [2 + i] = limited sample i
+    uint4 raw[M17B_BLOCK_SAMPLES / 4];      // the block's int16 IQ row, fetched with cp.async while the previous block's mean is summed and
+                                            // its timing loop runs (read straight from global memory the 15 loads of a lane cost a quarter
+                                            // of the kernel's time: profiles/r02_afc_lines_before.txt)
     float u[M17B_BLOCK_SAMPLES];            // discriminator values before the x0.5 (m17_dsp.cpp:209)
 };
 
-// One 40-ms block of one channel, by one warp.  Loop state (NCO phase, AFC delta) is carried in registers by the caller (every
-// lane holds the same values); the discriminator history z[1], z[0] lives in sm.lim[0..1] between blocks.  Writes the block's
-// 384 kept discriminator values (not mean-removed) and its mean to out384 / mean_out (shared memory of the timing loop) and
-// to the global rows drow / mrow (the view the tests read).
-__device__ __forceinline__ void afc_block(AfcWarpSmem &sm, const uint32_t *__restrict__ iqrow, int lane, int in_frame, int count0,
-                                          float &afc_delta, double &nco_acc, float *out384, float *mean_out, float *__restrict__ drow, float *__restrict__ mrow) {
+// cp.async of one block's IQ row into sm.raw: 480 pieces of 16 bytes, piece p by lane p % 32 (coalesced); lane l later reads
+// pieces 15 l .. 15 l + 14 (its 60 samples; the 240-byte lane stride is conflict-free for 16-byte accesses).
+__device__ __forceinline__ void afc_prefetch(AfcWarpSmem &sm, const uint32_t *__restrict__ iqrow, int lane) {
+#pragma unroll
+    for (int k = 0; k < M17B_BLOCK_SAMPLES / 4 / 32; k++) {
+        const int p = lane + 32 * k;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.raw[p]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(iqrow + 4 * p));
+    }
+    asm volatile("cp.async.commit_group;");
+}
+
+// m17_dsp.cpp:203-206: x = sample i, z0 = sample i-1, z1 = sample i-2
+__device__ __forceinline__ float afc_disc(float2 x, float2 z0, float2 z1) {
+    const float a = z0.y * (x.x - z1.x);
+    const float b = z0.x * (x.y - z1.y);
+    return b - a;
+}
+
+// One 40-ms block of one channel, by one warp.  Loop state (NCO phase, AFC delta, the discriminator history zc1 = z[1], zc0 = z[0])
+// is carried in registers by the caller (every lane holds the same values).  The block's IQ row is already on its way into
+// sm.raw (afc_prefetch); iq_next (or null) is the row to fetch for the next call.  Writes the block's 384 kept discriminator
+// values (not mean-removed) and its mean to out384 / mean_out (shared memory of the timing loop) and to the global rows
+// drow / mrow (the view the tests read).
+__device__ __forceinline__ void afc_block(AfcWarpSmem &sm, const uint32_t *__restrict__ iq_next, int lane, int in_frame, int count0,
+                                          float &afc_delta, double &nco_acc, float2 &zc1, float2 &zc0,
+                                          float *out384, float *mean_out, float *__restrict__ drow, float *__restrict__ mrow) {
     if (!in_frame) afc_delta = 0.0f;                                // radio_get_afc_delta, radio.cpp:201-208
     const double dl = (double)afc_delta;
     const double acc0 = nco_acc;
@@ -61,25 +86,38 @@ __device__ __forceinline__ void afc_block(AfcWarpSmem &sm, const uint32_t *__res
     }
     const double acc_end = __longlong_as_double(__shfl_sync(0xffffffffu, __double_as_longlong(end), 31));
 
-    // ---- 2. int16 -> float, NCO mixer, limiter
+    // ---- 2. int16 -> float, NCO mixer, limiter, discriminator: each lane walks its 60 samples
     // cos / sin of the lane's 60 phases: one double sincos at the lane's (exactly resolved) start phase, then the rotation by
     // (cos delta, sin delta) in double with FMAs.  The recurrence drifts by ~1e-16 per step, i.e. < 1e-14 after 60 steps --
     // the same order as the distance between CUDA's and glibc's double sincos -- so the values ROUNDED TO FLOAT, which is all
     // the reference uses (float c = cos(acc), m17_dsp.cpp:393-394), differ from a per-sample sincos only when a double result
     // lies within ~1e-14 of a float rounding boundary: about one sample in a few million, by one float ulp (see header).
+    // The discriminator value of sample i needs the limited samples i-1 and i-2: inside the lane's run they are the two
+    // registers behind the walk; the lane's first two values wait for the previous lane's last two samples (one shuffle pair
+    // after the walk; lane 0 takes the history carried in from the previous block).  Nothing but the 1920 discriminator values
+    // goes through shared memory.
+    asm volatile("cp.async.wait_group 0;");
+    __syncwarp();
+    float2 x0 = make_float2(0, 0), x1 = x0, p0 = x0, p1 = x0;       // x0, x1: the lane's first two samples; p0, p1: samples i-1, i-2
     {
-        const uint4 *row = (const uint4 *)(iqrow + AFC_PER_LANE * lane);
+        const uint4 *row = sm.raw + (AFC_PER_LANE / 4) * lane;
+        float4 *urow = (float4 *)(sm.u + AFC_PER_LANE * lane);
         double sd, cd, rs, rc;
         sincos(start, &sd, &cd);
         sincos(dl, &rs, &rc);
+        constexpr float c_hi = 0.00003f;
+        constexpr float c_lo = (float)(0.00003 - (double)0.00003f);
         for (int q = 0; q < AFC_PER_LANE / 4; q++) {
-            const uint4 w = __ldg(row + q);
+            const uint4 w = row[q];
+            float uo[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const uint32_t raw = j == 0 ? w.x : j == 1 ? w.y : j == 2 ? w.z : w.w;
-                const int re_i = (int)(int16_t)(raw & 0xFFFFu), im_i = (int)(int16_t)(raw >> 16);
-                const float re = __double2float_rn((double)re_i * 0.00003);          // dsp_short_to_float :138-139
-                const float im = __double2float_rn((double)im_i * 0.00003);
+                const float xr = (float)(short)(raw & 0xFFFFu), xi = (float)(short)(raw >> 16);
+                // dsp_short_to_float :138-139: fmaf(x, c_hi, x * c_lo) == (float)((double)x * 0.00003) for every int16 x
+                // (part of the exhaustive front-end self-test, frontend.cuh)
+                const float re = fmaf(xr, c_hi, xr * c_lo);
+                const float im = fmaf(xi, c_hi, xi * c_lo);
                 const float cs = __double2float_rn(cd), sn = __double2float_rn(sd);  // float c = cos(acc); float s = sin(acc);
                 const double nc = fma(cd, rc, -(sd * rs)), ns = fma(sd, rc, cd * rs); // acc += delta
                 cd = nc; sd = ns;
@@ -87,31 +125,54 @@ __device__ __forceinline__ void afc_block(AfcWarpSmem &sm, const uint32_t *__res
                 const float nim = (re * sn) + (im * cs);
                 const float m = sqrtf(nre * nre + nim * nim);                          // dsp_limit :414-417
                 const float g = 1.0f / m;                                              // == (float)(1.0 / m) (2p+2 theorem)
-                sm.lim[2 + AFC_PER_LANE * lane + 4 * q + j] = make_float2(nre * g, nim * g);
+                const float2 x = make_float2(nre * g, nim * g);
+                uo[j] = afc_disc(x, p0, p1);                                           // (the lane's first two: placeholders)
+                p1 = p0; p0 = x;
+                if (q == 0 && j == 0) x0 = x;
+                if (q == 0 && j == 1) x1 = x;
             }
+            urow[q] = make_float4(uo[0], uo[1], uo[2], uo[3]);
         }
     }
-    __syncwarp();
-
-    // ---- 3. discriminator, sample-parallel (m17_dsp.cpp:203-212); every 5th value is kept
-    const int keep = 4 - count0;
-    for (int i = lane; i < M17B_BLOCK_SAMPLES; i += 32) {
-        const float2 x = sm.lim[2 + i], z0 = sm.lim[1 + i], z1 = sm.lim[i];
-        const float a = z0.y * (x.x - z1.x);
-        const float b = z0.x * (x.y - z1.y);
-        const float u = b - a;
-        sm.u[i] = u;
-        if (i % 5 == keep) { const float v = u * 0.5f; out384[i / 5] = v; drow[i / 5] = v; }
+    {
+        float2 m1, m2;                                              // samples 60 l - 1, 60 l - 2
+        m1.x = __shfl_up_sync(0xffffffffu, p0.x, 1); m1.y = __shfl_up_sync(0xffffffffu, p0.y, 1);
+        m2.x = __shfl_up_sync(0xffffffffu, p1.x, 1); m2.y = __shfl_up_sync(0xffffffffu, p1.y, 1);
+        if (lane == 0) { m1 = zc0; m2 = zc1; }
+        *(float2 *)(sm.u + AFC_PER_LANE * lane) = make_float2(afc_disc(x0, m1, m2), afc_disc(x1, x0, m1));
+        zc0.x = __shfl_sync(0xffffffffu, p0.x, 31); zc0.y = __shfl_sync(0xffffffffu, p0.y, 31);     // z[0], z[1] for the next block
+        zc1.x = __shfl_sync(0xffffffffu, p1.x, 31); zc1.y = __shfl_sync(0xffffffffu, p1.y, 31);
     }
     __syncwarp();
+    if (iq_next) afc_prefetch(sm, iq_next, lane);                   // every lane is done with sm.raw
+
+    // ---- 3. every 5th value is kept (m17_dsp.cpp:207-211)
+    const int keep = 4 - count0;
+#pragma unroll
+    for (int k = 0; k < M17B_DISC_PER_BLOCK / 32; k++) {
+        const int m = lane + 32 * k;
+        const float v = sm.u[5 * m + keep] * 0.5f;
+        out384[m] = v;
+        drow[m] = v;
+    }
 
     // ---- 4. block mean in the reference's order, AFC loop update
     float mu = 0.0f;
     if (lane == 0) {
+        // 1920 dependent adds; the loads run one batch of 16 values ahead so that the chain never waits for shared memory
         float acc = 0.0f;
         const float4 *u4 = (const float4 *)sm.u;
-#pragma unroll 4
-        for (int i = 0; i < M17B_BLOCK_SAMPLES / 4; i++) { const float4 v = u4[i]; acc += v.x; acc += v.y; acc += v.z; acc += v.w; }
+        float4 a0 = u4[0], a1 = u4[1], a2 = u4[2], a3 = u4[3];
+#pragma unroll 1
+        for (int i = 4; i <= M17B_BLOCK_SAMPLES / 4; i += 4) {
+            float4 b0 = a0, b1 = a1, b2 = a2, b3 = a3;
+            if (i < M17B_BLOCK_SAMPLES / 4) { b0 = u4[i]; b1 = u4[i + 1]; b2 = u4[i + 2]; b3 = u4[i + 3]; }
+            acc += a0.x; acc += a0.y; acc += a0.z; acc += a0.w;
+            acc += a1.x; acc += a1.y; acc += a1.z; acc += a1.w;
+            acc += a2.x; acc += a2.y; acc += a2.z; acc += a2.w;
+            acc += a3.x; acc += a3.y; acc += a3.z; acc += a3.w;
+            a0 = b0; a1 = b1; a2 = b2; a3 = b3;
+        }
         mu = (acc * 0.5f) / 1920.0f;                                 // sum of u*0.5 == 0.5 * sum of u (exact scaling); offset/len :214
         *mean_out = mu;
         *mrow = mu;
@@ -123,11 +184,6 @@ __device__ __forceinline__ void afc_block(AfcWarpSmem &sm, const uint32_t *__res
     a = a * 2.0 * M_PI;
     if (a != a) a = 0;
     nco_acc = a;
-    // z[1], z[0] for the next block
-    float2 y0 = make_float2(0, 0), y1 = y0;
-    if (lane == 0) { y0 = sm.lim[M17B_BLOCK_SAMPLES + 1]; y1 = sm.lim[M17B_BLOCK_SAMPLES]; }
-    __syncwarp();
-    if (lane == 0) { sm.lim[0] = y1; sm.lim[1] = y0; }
     __syncwarp();
 }
 

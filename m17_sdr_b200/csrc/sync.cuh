@@ -100,9 +100,9 @@ __device__ __forceinline__ void dot6(const float (*X)[SY_XQ], int base, const f3
 
 // AFC = true (m17b_rx_set_afc): the block's discriminator samples do not come from memory but from the AFC front end run by
 // the same warp at the top of the block loop (afc.cuh): iq = int16 IQ rows, disc / mean are then OUTPUTS (the raw samples and
-// block means the caller may inspect).  23 KB more shared memory per warp: one CTA per SM.
+// block means the caller may inspect).  15.4 KB more shared memory per warp: still two CTAs per SM.
 template <bool HAS_MEAN, bool AFC = false>
-__global__ void __launch_bounds__(SY_WARPS * 32, AFC ? 1 : 2) k_sync_frame(const float *__restrict__ disc, const float *__restrict__ mean, int64_t nchan, int64_t T,
+__global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__restrict__ disc, const float *__restrict__ mean, int64_t nchan, int64_t T,
                                                               int t0, int t1, int2 *frame_rng, RxChanState *st, const float *__restrict__ g_mf, const float *__restrict__ g_md,
                                                               float *syms, int64_t sym_pitch, int32_t *__restrict__ nsym, int32_t *__restrict__ sym_base,
                                                               m17b_frame_rec *frames, int64_t fcap, int32_t *__restrict__ nframes,
@@ -205,12 +205,13 @@ __global__ void __launch_bounds__(SY_WARPS * 32, AFC ? 1 : 2) k_sync_frame(const
     float afc_delta = 0.0f;
     double nco_acc = 0.0;
     int disc_count = 0;
+    float2 afc_z1 = make_float2(0, 0), afc_z0 = afc_z1;      // dsp_arctan_disc2's z[1], z[0] (m17_dsp.cpp:195-196)
     AfcWarpSmem *afc_sm = nullptr;
     if (AFC) {
         afc_sm = (AfcWarpSmem *)afc_smem_raw + wid;
         afc_delta = S->afc_delta; nco_acc = S->nco_acc; disc_count = S->disc_count;
-        if (lane == 0) { afc_sm->lim[0] = make_float2(S->z1re, S->z1im); afc_sm->lim[1] = make_float2(S->z0re, S->z0im); }
-        __syncwarp();
+        afc_z1 = make_float2(S->z1re, S->z1im); afc_z0 = make_float2(S->z0re, S->z0im);
+        afc_prefetch(*afc_sm, iq + (c * T + t0) * M17B_BLOCK_SAMPLES, lane);
     } else prefetch(t0, 0);
 
     for (int64_t t = t0; t < t1; t++) {
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32, AFC ? 1 : 2) k_sync_frame(const
 #ifdef M17B_PHASE_UNLOCKED
         ph_on = !flock; ph_blocks += ph_on;                         // profile the blocks entered unlocked only
 #endif
-        if (AFC) afc_block(*afc_sm, iq + (c * T + t) * M17B_BLOCK_SAMPLES, lane, flock, disc_count, afc_delta, nco_acc, sm.pre[buf], &sm.pre[buf][384],
+        if (AFC) afc_block(*afc_sm, t + 1 < t1 ? iq + (c * T + t + 1) * M17B_BLOCK_SAMPLES : nullptr, lane, flock, disc_count, afc_delta, nco_acc, afc_z1, afc_z0, sm.pre[buf], &sm.pre[buf][384],
                            disc_out + (c * T + t) * M17B_DISC_PER_BLOCK, mean_out + c * T + t);
         else asm volatile("cp.async.wait_group 0;");
         __syncwarp();
@@ -559,8 +560,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32, AFC ? 1 : 2) k_sync_frame(const
     // ---- store state
     if (AFC && lane == 0) {
         S->afc_delta = afc_delta; S->nco_acc = nco_acc;
-        const float2 y1 = afc_sm->lim[0], y0 = afc_sm->lim[1];
-        S->z0re = y0.x; S->z0im = y0.y; S->z1re = y1.x; S->z1im = y1.y;
+        S->z0re = afc_z0.x; S->z0im = afc_z0.y; S->z1re = afc_z1.x; S->z1im = afc_z1.y;
     }
     if (lane < 30) S->tail[lane] = sm.x[lane & 3][lane >> 2];
     if (lane < 8) { S->win[lane] = sm.hist[lane]; S->head[lane] = sm.head[lane]; }
