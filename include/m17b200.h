@@ -218,6 +218,10 @@ int m17b_rx_last_launches(const m17b_rx *rx);
    of mismatching samples (must be 0) and optionally the first dump_cap offending raw words.  The full range takes a few
    seconds on a B200. */
 int m17b_selftest_frontend(m17b_ctx *ctx, uint64_t first, uint64_t count, uint64_t *h_mismatches, uint32_t *h_dump, int dump_cap, void *stream);
+/* the same for the limiter's normaliser by itself (dsp_limit, m17_dsp.cpp:412-419: m = sqrtf(re*re + im*im), 1.0 / m): the fast
+   form's m and g against IEEE sqrt and division on the float bit patterns [first, first+count) of s = re*re + im*im, whatever
+   re and im were (the AFC front end limits mixer outputs, not int16 grid points); dump = {bits(s), m_fast, m_ieee, g_fast, g_ieee} */
+int m17b_selftest_limiter(m17b_ctx *ctx, uint64_t first, uint64_t count, uint64_t *h_mismatches, uint32_t *h_dump, int dump_cap, void *stream);
 
 /* exhaustive check that the frame decoder's fp32 form of the LSB soft value, (float)(fabs(m) - 0.6666) with the subtraction in
    double (m17_dsp_demap_frame / _symbol, m17_dsp.cpp:40-41,91), and its sign-only hard decision (hard_decode_24_bits,

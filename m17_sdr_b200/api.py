@@ -257,6 +257,14 @@ class Context:
         self.last_selftest_dump = dump.reshape(-1, 5)[: min(16, n.value)]
         return n.value
 
+    def selftest_limiter(self, first=0x00800000, count=0x7F800000 - 0x00800000):
+        """fast limiter normaliser vs IEEE sqrt / divide over float bit patterns of s (default: every positive normal float)"""
+        n = C.c_uint64()
+        dump = np.zeros(5 * 16, np.uint32)
+        _l.check(self.L.m17b_selftest_limiter(self.h, first, count, C.byref(n), dump.ctypes.data_as(C.c_void_p), len(dump), _stream()))
+        self.last_selftest_dump = dump.reshape(-1, 5)[: min(16, n.value)]
+        return n.value
+
     def gps_decode(self, lsf):
         """gps_decode (gps.cpp:8-27) of the META field: lsf uint8 [n][>=30] -> numpy structured array (lat, lon, alt, course, speed, object)."""
         _chk_dev(lsf, torch.uint8, "lsf")

@@ -111,25 +111,32 @@ __device__ __forceinline__ void afc_block(AfcWarpSmem &sm, const uint32_t *__res
             const uint4 w = row[q];
             float uo[4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint32_t raw = j == 0 ? w.x : j == 1 ? w.y : j == 2 ? w.z : w.w;
-                const float xr = (float)(short)(raw & 0xFFFFu), xi = (float)(short)(raw >> 16);
-                // dsp_short_to_float :138-139: fmaf(x, c_hi, x * c_lo) == (float)((double)x * 0.00003) for every int16 x
-                // (part of the exhaustive front-end self-test, frontend.cuh)
-                const float re = fmaf(xr, c_hi, xr * c_lo);
-                const float im = fmaf(xi, c_hi, xi * c_lo);
-                const float cs = __double2float_rn(cd), sn = __double2float_rn(sd);  // float c = cos(acc); float s = sin(acc);
-                const double nc = fma(cd, rc, -(sd * rs)), ns = fma(sd, rc, cd * rs); // acc += delta
-                cd = nc; sd = ns;
-                const float nre = (re * cs) - (im * sn);                               // :396-397 (no contraction)
-                const float nim = (re * sn) + (im * cs);
-                const float m = sqrtf(nre * nre + nim * nim);                          // dsp_limit :414-417
-                const float g = 1.0f / m;                                              // == (float)(1.0 / m) (2p+2 theorem)
-                const float2 x = make_float2(nre * g, nim * g);
-                uo[j] = afc_disc(x, p0, p1);                                           // (the lane's first two: placeholders)
-                p1 = p0; p0 = x;
-                if (q == 0 && j == 0) x0 = x;
-                if (q == 0 && j == 1) x1 = x;
+            for (int jp = 0; jp < 2; jp++) {                                         // two samples at a time (packed normaliser)
+                float nre[2], nim[2], ss[2];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const uint32_t raw = jp == 0 ? (h == 0 ? w.x : w.y) : (h == 0 ? w.z : w.w);
+                    const float xr = (float)(short)(raw & 0xFFFFu), xi = (float)(short)(raw >> 16);
+                    // dsp_short_to_float :138-139: fmaf(x, c_hi, x * c_lo) == (float)((double)x * 0.00003) for every int16 x
+                    // (part of the exhaustive front-end self-test, frontend.cuh)
+                    const float re = fmaf(xr, c_hi, xr * c_lo);
+                    const float im = fmaf(xi, c_hi, xi * c_lo);
+                    const float cs = __double2float_rn(cd), sn = __double2float_rn(sd);  // float c = cos(acc); float s = sin(acc);
+                    const double nc = fma(cd, rc, -(sd * rs)), ns = fma(sd, rc, cd * rs); // acc += delta
+                    cd = nc; sd = ns;
+                    nre[h] = (re * cs) - (im * sn);                                    // :396-397 (no contraction)
+                    nim[h] = (re * sn) + (im * cs);
+                    ss[h] = nre[h] * nre[h] + nim[h] * nim[h];
+                }
+                // dsp_limit :414-417: m = sqrtf(s), 1.0 / m -- the front end's fast normaliser, equal to the IEEE forms for every
+                // float s >= 2^-102 (m17b_selftest_limiter; here s >= 8e-10: a rotated nonzero int16 sample)
+                float nma, nmb, ga, gb;
+                fe_norm_pair(pack2(ss[0], ss[1]), nma, nmb, ga, gb);
+                const float2 xa = make_float2(nre[0] * ga, nim[0] * ga), xb = make_float2(nre[1] * gb, nim[1] * gb);
+                uo[2 * jp] = afc_disc(xa, p0, p1);                                     // (the lane's first two: placeholders)
+                uo[2 * jp + 1] = afc_disc(xb, xa, p0);
+                p1 = xa; p0 = xb;
+                if (q == 0 && jp == 0) { x0 = xa; x1 = xb; }
             }
             urow[q] = make_float4(uo[0], uo[1], uo[2], uo[3]);
         }
@@ -162,17 +169,17 @@ __device__ __forceinline__ void afc_block(AfcWarpSmem &sm, const uint32_t *__res
         // 1920 dependent adds; the loads run one batch of 16 values ahead so that the chain never waits for shared memory
         float acc = 0.0f;
         const float4 *u4 = (const float4 *)sm.u;
-        float4 a0 = u4[0], a1 = u4[1], a2 = u4[2], a3 = u4[3];
+        float4 a0 = u4[0], a1 = u4[1], a2 = u4[2], a3 = u4[3], b0, b1, b2, b3;
+#define AFC_ADD16(v0, v1, v2, v3) acc += v0.x; acc += v0.y; acc += v0.z; acc += v0.w; acc += v1.x; acc += v1.y; acc += v1.z; acc += v1.w; \
+                                  acc += v2.x; acc += v2.y; acc += v2.z; acc += v2.w; acc += v3.x; acc += v3.y; acc += v3.z; acc += v3.w
 #pragma unroll 1
-        for (int i = 4; i <= M17B_BLOCK_SAMPLES / 4; i += 4) {
-            float4 b0 = a0, b1 = a1, b2 = a2, b3 = a3;
-            if (i < M17B_BLOCK_SAMPLES / 4) { b0 = u4[i]; b1 = u4[i + 1]; b2 = u4[i + 2]; b3 = u4[i + 3]; }
-            acc += a0.x; acc += a0.y; acc += a0.z; acc += a0.w;
-            acc += a1.x; acc += a1.y; acc += a1.z; acc += a1.w;
-            acc += a2.x; acc += a2.y; acc += a2.z; acc += a2.w;
-            acc += a3.x; acc += a3.y; acc += a3.z; acc += a3.w;
-            a0 = b0; a1 = b1; a2 = b2; a3 = b3;
+        for (int i = 4; i < M17B_BLOCK_SAMPLES / 4; i += 8) {       // two batches per trip (ping-pong: no register moves)
+            b0 = u4[i]; b1 = u4[i + 1]; b2 = u4[i + 2]; b3 = u4[i + 3];
+            AFC_ADD16(a0, a1, a2, a3);
+            if (i + 4 < M17B_BLOCK_SAMPLES / 4) { a0 = u4[i + 4]; a1 = u4[i + 5]; a2 = u4[i + 6]; a3 = u4[i + 7]; }
+            AFC_ADD16(b0, b1, b2, b3);
         }
+#undef AFC_ADD16
         mu = (acc * 0.5f) / 1920.0f;                                 // sum of u*0.5 == 0.5 * sum of u (exact scaling); offset/len :214
         *mean_out = mu;
         *mrow = mu;

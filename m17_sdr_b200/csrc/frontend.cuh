@@ -50,6 +50,40 @@ __device__ __forceinline__ float fe_patch_all_ones(float g, uint32_t nmbits) {
     return __uint_as_float(gb);
 }
 
+// The limiter's normaliser for a pair of samples: from S = (s_a, s_b), s = re^2 + im^2, to -m = -RN(sqrt(s)) (returned as bit
+// patterns nma, nmb) and g = RN(1 / m) (ga, gb).  Everything here is a function of s alone, so its equality with sqrtf / IEEE
+// division does not depend on where s came from: m17b_selftest_limiter enumerates EVERY normal float s (used by the AFC front
+// end, whose limiter input is the mixer output and not an int16 grid point; the int16 path has its own end-to-end enumeration,
+// m17b_selftest_frontend).
+__device__ __forceinline__ void fe_norm_pair(f32x2 S, float &nma, float &nmb, float &ga, float &gb) {
+    float sa, sb, ya, yb;
+    unpack2(S, sa, sb);
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(ya) : "f"(sa));
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(yb) : "f"(sb));
+    const f32x2 Y = pack2(ya, yb);
+    const f32x2 NEG1 = pack2(-1.0f, -1.0f), NHALF = pack2(-0.5f, -0.5f), ONE = pack2(1.0f, 1.0f);
+    // -m = -RN(sqrt(s)): Newton step on the residual s - m0*m0, carried out on the negated iterate (round-to-nearest is
+    // symmetric, so fma(r, -y/2, -m0) is exactly -(m0 + r*y/2)); only -m is needed below
+    const f32x2 M0 = mul2(S, Y);
+    const f32x2 NM0 = mul2(M0, NEG1);
+    const f32x2 NM = fma2(fma2(NM0, M0, S), mul2(Y, NHALF), NM0);
+    // g = RN(1/m): two residual corrections starting from y ~ 1/m (Markstein): fma(-m, g, 1) = 1 - m*g, g + (1 - m*g)*g.
+    // The one input class this cannot round correctly is a divisor whose significand is all ones: the Newton iterate then
+    // lands exactly on a rounding midpoint while the true quotient 2^-(e+1) (1 + 2^-24 + ..) lies just above it; its correctly
+    // rounded value is known in closed form, 2^-(e+1) (1 + 2^-23) = bits 0x7F000000 - bits(m).
+    f32x2 G = fma2(fma2(NM, Y, ONE), Y, Y);
+    G = fma2(fma2(NM, G, ONE), G, G);
+    unpack2(NM, nma, nmb);
+    unpack2(G, ga, gb);
+    // (Tried in round 2: leave the patch out of the walking loop -- a running VIMNMX3 of bits(m) | 0xFF800000 instead, one warp
+    // vote per 80-sample segment, and a second pass with the patch over the segments that need it, about 1 % of the warp-units
+    // of the bench workload.  Exact (tests/gpu_check.py check_rx_chain_limiter_patch plants the class), 1.5 instructions per
+    // sample fewer, and no faster.  Redoing whole warp-units instead was 0.72 ms -- a unit is half the kernel's duration, so
+    // any unit that runs twice in the second wave extends the kernel by a quarter.)
+    ga = fe_patch_all_ones(ga, __float_as_uint(nma));
+    gb = fe_patch_all_ones(gb, __float_as_uint(nmb));
+}
+
 // Two samples at a time, packed ACROSS the two samples: RE = (re_a, re_b), IM = (im_a, im_b).  Scaling, squares, the sum of
 // squares, the Newton / Markstein residual steps for sqrt and reciprocal and the final limiter scaling are then all packed
 // operations on naturally aligned pairs (one FMUL2 / FFMA2 / FADD2 serves both samples), and the outputs XRE = (x_a.re, x_b.re),
@@ -73,35 +107,10 @@ __device__ __forceinline__ void fe_limit_pair(uint32_t raw_a, uint32_t raw_b, f3
     const f32x2 RE = fma2(xr, CH, mul2(xr, CL));               // fmaf(x, c_hi, x * c_lo) == (float)((double)x * 0.00003)
     const f32x2 IM = fma2(xi, CH, mul2(xi, CL));
     const f32x2 S = fma2(mul2(IM, IM), one, mul2(RE, RE));     // two rounded products, one rounded sum (see above)
-    float sa, sb, ya, yb;
-    unpack2(S, sa, sb);
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(ya) : "f"(sa));
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(yb) : "f"(sb));
-    const f32x2 Y = pack2(ya, yb);
-    const f32x2 NEG1 = pack2(-1.0f, -1.0f), NHALF = pack2(-0.5f, -0.5f), ONE = pack2(1.0f, 1.0f);
-    // -m = -RN(sqrt(s)): Newton step on the residual s - m0*m0, carried out on the negated iterate (round-to-nearest is
-    // symmetric, so fma(r, -y/2, -m0) is exactly -(m0 + r*y/2)); only -m is needed below
-    const f32x2 M0 = mul2(S, Y);
-    const f32x2 NM0 = mul2(M0, NEG1);
-    const f32x2 NM = fma2(fma2(NM0, M0, S), mul2(Y, NHALF), NM0);
-    // g = RN(1/m): two residual corrections starting from y ~ 1/m (Markstein): fma(-m, g, 1) = 1 - m*g, g + (1 - m*g)*g.
-    // The one input class this cannot round correctly is a divisor whose significand is all ones: the Newton iterate then
-    // lands exactly on a rounding midpoint while the true quotient 2^-(e+1) (1 + 2^-24 + ..) lies just above it; its correctly
-    // rounded value is known in closed form, 2^-(e+1) (1 + 2^-23) = bits 0x7F000000 - bits(m).
-    f32x2 G = fma2(fma2(NM, Y, ONE), Y, Y);
-    G = fma2(fma2(NM, G, ONE), G, G);
     float nma, nmb, ga, gb;
-    unpack2(NM, nma, nmb);
-    unpack2(G, ga, gb);
-    // (Tried in round 2: leave the patch out of the walking loop -- a running VIMNMX3 of bits(m) | 0xFF800000 instead, one warp
-    // vote per 80-sample segment, and a second pass with the patch over the segments that need it, about 1 % of the warp-units
-    // of the bench workload.  Exact (tests/gpu_check.py check_rx_chain_limiter_patch plants the class), 1.5 instructions per
-    // sample fewer, and no faster.  Redoing whole warp-units instead was 0.72 ms -- a unit is half the kernel's duration, so
-    // any unit that runs twice in the second wave extends the kernel by a quarter.)
-    ga = fe_patch_all_ones(ga, __float_as_uint(nma));
-    gb = fe_patch_all_ones(gb, __float_as_uint(nmb));
+    fe_norm_pair(S, nma, nmb, ga, gb);
     if (mo) { mo[0] = -nma; mo[1] = -nmb; go[0] = ga; go[1] = gb; }
-    G = pack2(ga, gb);
+    const f32x2 G = pack2(ga, gb);
     XRE = mul2(RE, G);
     XIM = mul2(IM, G);
 }
@@ -278,6 +287,52 @@ __global__ void k_selftest_frontend(unsigned long long *mism, uint32_t lo, uint3
         }
     }
     if (bad) atomicAdd(mism, (unsigned long long)bad);
+}
+// The same proof for the normaliser alone, over float bit patterns of s = re^2 + im^2 (fe_norm_pair): m must equal sqrtf(s) and
+// g must equal 1.0f / m (IEEE) bit for bit.
+__global__ void k_selftest_limiter(unsigned long long *mism, uint32_t lo, uint32_t count, uint32_t *dump, int dump_cap) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned bad = 0;
+    for (uint32_t k = i; k < count; k += gridDim.x * blockDim.x) {
+        const uint32_t sb = lo + k;
+        const float s = __uint_as_float(sb);
+        float nma, nmb, ga, gb;
+        fe_norm_pair(pack2(s, s), nma, nmb, ga, gb);
+        const float m = __fsqrt_rn(s), g = __frcp_rn(m);
+        if ((__float_as_uint(-nma) != __float_as_uint(m)) | (__float_as_uint(ga) != __float_as_uint(g)) | (__float_as_uint(nmb) != __float_as_uint(nma)) | (__float_as_uint(gb) != __float_as_uint(ga))) {
+            bad++;
+            if (dump) {
+                unsigned long long slot = atomicAdd(mism + 1, 1ull);
+                if (5 * slot + 4 < (unsigned long long)dump_cap) {
+                    dump[5 * slot] = sb; dump[5 * slot + 1] = __float_as_uint(-nma); dump[5 * slot + 2] = __float_as_uint(m);
+                    dump[5 * slot + 3] = __float_as_uint(ga); dump[5 * slot + 4] = __float_as_uint(g);
+                }
+            }
+        }
+    }
+    if (bad) atomicAdd(mism, (unsigned long long)bad);
+}
+extern "C" int m17b_selftest_limiter(m17b_ctx *ctx, uint64_t first, uint64_t count, uint64_t *h_mismatches, uint32_t *h_dump, int dump_cap, void *stream) {
+    if (!ctx || !h_mismatches || first + count > (1ull << 32) || dump_cap < 0) return M17B_E_ARG;
+    cudaStream_t st = as_stream(stream);
+    unsigned long long *d;
+    uint32_t *d_dump = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&d, 16));
+    CUDA_TRY(cudaMemsetAsync(d, 0, 16, st));
+    if (h_dump && dump_cap) { CUDA_TRY(cudaMalloc((void **)&d_dump, 4 * (size_t)dump_cap)); CUDA_TRY(cudaMemsetAsync(d_dump, 0, 4 * (size_t)dump_cap, st)); }
+    for (uint64_t off = 0; off < count; off += (1ull << 30)) {
+        const uint64_t n = count - off < (1ull << 30) ? count - off : (1ull << 30);
+        k_selftest_limiter<<<148 * 16, 256, 0, st>>>(d, (uint32_t)(first + off), (uint32_t)n, d_dump, dump_cap);
+    }
+    KERNEL_CHECK();
+    unsigned long long h = 0;
+    CUDA_TRY(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, st));
+    if (d_dump) CUDA_TRY(cudaMemcpyAsync(h_dump, d_dump, 4 * (size_t)dump_cap, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaFree(d));
+    if (d_dump) CUDA_TRY(cudaFree(d_dump));
+    *h_mismatches = h;
+    return M17B_OK;
 }
 // h_dump (optional, dump_cap words) receives {raw, m_fast, m_ieee, g_fast, g_ieee} of the first mismatches found
 extern "C" int m17b_selftest_frontend(m17b_ctx *ctx, uint64_t first, uint64_t count, uint64_t *h_mismatches, uint32_t *h_dump, int dump_cap, void *stream) {

@@ -64,6 +64,7 @@ _SIGS = {
     "m17b_rx_set_timing": ([_vp, _i32], _i32),
     "m17b_rx_stage_ms": ([_vp, _i64, _vp], _i32),
     "m17b_selftest_frontend": ([_vp, _u64, _u64, C.POINTER(_u64), _vp, _i32, _vp], _i32),
+    "m17b_selftest_limiter": ([_vp, _u64, _u64, C.POINTER(_u64), _vp, _i32, _vp], _i32),
     "m17b_selftest_tx_wrap": ([_vp, _u64, _u64, C.POINTER(_u64), _vp, _i32, _vp], _i32),
     "m17b_selftest_demap": ([_vp, _u64, _u64, C.POINTER(_u64), _vp, _i32, _vp], _i32),
     "m17b_tx_debug_scan": ([_vp, _vp], _i32),

@@ -20,6 +20,15 @@ def test_frontend_math_exhaustive(ctx, port):
     gc.check_frontend_math(ctx, port)
 
 
+def test_limiter_normaliser_exhaustive(ctx):
+    """the limiter's fast m = sqrt(s), g = 1 / m (rsqrt seed + residual steps + the all-ones patch) == IEEE sqrtf and division for
+    EVERY float s = re^2 + im^2 from 2^-100 up to the largest finite float -- the AFC front end limits mixer outputs, which are
+    not on the int16 grid that test_frontend_math_exhaustive enumerates (its s >= 8e-10)"""
+    first = (127 - 100) << 23
+    bad = ctx.selftest_limiter(first, 0x7F800000 - first)
+    assert bad == 0, (bad, [[hex(int(x)) for x in r] for r in ctx.last_selftest_dump])
+
+
 def test_primitives(ctx, port):
     gc.check_primitives(ctx, port)
 
