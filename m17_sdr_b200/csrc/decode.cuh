@@ -386,75 +386,111 @@ __global__ void __launch_bounds__(NT) k_decode_frames(const float *__restrict__ 
 // kernel below (8.4 KB of shared memory per warp), traceback, CRC, record.
 struct StreamAux { uint32_t lw01, lw23, golay_e; float cor; };
 #define SG_WARPS 4
+#define SG_FPW   8            // record slots per warp: the per-warp set-up (channel, map entries) is paid once per 8 frames
 __global__ void __launch_bounds__(SG_WARPS * 32) k_stream_gather(const float *__restrict__ syms, int64_t sym_pitch, int sym_carry, const int32_t *__restrict__ sym_base,
                                                                  const m17b_frame_rec *__restrict__ frames, int64_t fcap, const int32_t *__restrict__ nframes,
                                                                  const int2 *__restrict__ frame_rng, int slots_per_chan, int64_t nchan,
                                                                  const uint16_t *__restrict__ smap, const uint16_t *__restrict__ genc, const uint16_t *__restrict__ gerr,
                                                                  float *__restrict__ ssoft, StreamAux *__restrict__ saux, float *soft_out) {
+    // (the first form of this kernel took one frame per warp and staged the map in shared memory per CTA: ~600 warp instructions
+    //  per frame at an issue rate of 90 %, 0.16 ms for 245 000 frames; the map entries a lane uses are the same for every frame)
     __shared__ float soft2_s[SG_WARPS][368];                     // the frame's soft values in natural order: (-m, |m| - 0.6666) per payload symbol
-    __shared__ float hdr_s[SG_WARPS][8];
-    __shared__ uint16_t map_s[STREAM_NIN + 96];                  // 2 * (symbol - 8) + lsb, bit 15 = de-randomiser sign
-    for (int i = threadIdx.x; i < STREAM_NIN + 96; i += SG_WARPS * 32) map_s[i] = smap[i];
-    __syncthreads();
+    constexpr unsigned FULL = 0xffffffffu;
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned item = blockIdx.x * SG_WARPS + wid;           // (32-bit: the launch checks the grid; a 64-bit divide is a subroutine)
-    const int64_t c = item / (unsigned)slots_per_chan;
+    const unsigned item = blockIdx.x * SG_WARPS + wid;           // (channel, group of SG_FPW slots); 32-bit: the launch checks the grid
+    const unsigned groups = (unsigned)slots_per_chan / SG_FPW;
+    const int64_t c = item / groups;
     if (c >= nchan) return;
     int lo = 0, nfr;
     if (frame_rng) { const int2 r = frame_rng[c]; lo = r.x; nfr = r.y; }
     else nfr = (int)min((int64_t)nframes[c], fcap);
-    const int slot = lo + (int)(item - (unsigned)c * (unsigned)slots_per_chan);
-    if (slot >= nfr) return;
-    const uint2 hd = *(const uint2 *)(frames + c * fcap + slot);            // (every lane reads the same 8 bytes)
-    if ((hd.y & 0xFF) != M17B_T_STREAM || !((hd.y >> 8) & M17B_F_PARSED)) return;
-    const float *src = syms + c * sym_pitch + sym_carry + ((int32_t)hd.x - (sym_base ? sym_base[c] : 0));
-    float v[6];
-#pragma unroll
-    for (int k = 0; k < 6; k++) v[k] = src[lane + 32 * k];
-    if (lane < 8) hdr_s[wid][lane] = v[0];
-    __syncwarp();
-    float hdr[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) hdr[i] = hdr_s[wid][i];
-    const float cor = demap_cor(hdr);
-    // both soft values of every payload symbol once (m = in * mag, m17_dsp.cpp:38-41); the maps below only pick and sign them
-    float2 *s2 = (float2 *)soft2_s[wid];
-#pragma unroll
-    for (int k = 0; k < 6; k++) {
-        const int idx = lane + 32 * k - 8;
-        if (idx >= 0) { const float m = v[k] * cor; s2[idx] = make_float2(-m, demap_lsb(m)); }
-    }
-    __syncwarp();
-    const float *soft2 = soft2_s[wid];
+    int slot = lo + (int)(item - (unsigned)c * groups) * SG_FPW;
+    const int send = min(slot + SG_FPW, nfr);
+    if (slot >= send) return;
+    // The lane's entries of the stream-frame map (d_smap: index 2 * (symbol - 8) + lsb into the soft values, bit 15 = de-randomiser
+    // sign) as byte offsets and sign masks: trellis inputs lane, lane + 32, ... and LICH bits lane, lane + 32, lane + 64.
     // (e & 0x8000) << 16 is the sign bit: m17_de_correlate_1 negates the soft value where the randomiser bit is set (m17_correlate.cpp:29)
-    auto pick = [&](unsigned e) { return __uint_as_float(__float_as_uint(soft2[e & 0x1FFu]) ^ ((e & 0x8000u) << 16)); };
-    const int64_t fidx = c * fcap + slot;
-    float *o = ssoft + fidx * STREAM_NIN;
+    unsigned moff[9], msgn[9], loff[3], lsgn[3];
 #pragma unroll
-    for (int j = 0; j < STREAM_NIN; j += 32) if (j + lane < STREAM_NIN) o[j + lane] = pick(map_s[j + lane]);
-    if (soft_out) {
-        float *so = soft_out + fidx * 368;
-        for (int k = lane; k < 368; k += 32) so[k] = soft2[k];
+    for (int j = 0; j < 9; j++) {
+        const int idx = 32 * j + lane;
+        const unsigned e = idx < STREAM_NIN ? (unsigned)__ldg(smap + idx) : 0u;
+        moff[j] = e & 0x1FFu; msgn[j] = (e & 0x8000u) << 16;
     }
-    // 4 x hard_decode_24_bits (m17_bit_utils.cpp:180-187: bit = soft >= 0) + m_17_golay_decode: ballot bit i = LICH bit i, and
-    // the words are MSB first, so the reversed ballots read as one 96-bit big-endian string
-    const unsigned B0 = __brev(__ballot_sync(0xffffffffu, pick(map_s[STREAM_NIN + lane]) >= 0.0f));
-    const unsigned B1 = __brev(__ballot_sync(0xffffffffu, pick(map_s[STREAM_NIN + 32 + lane]) >= 0.0f));
-    const unsigned B2 = __brev(__ballot_sync(0xffffffffu, pick(map_s[STREAM_NIN + 64 + lane]) >= 0.0f));
-    const uint32_t word = lane == 0 ? B0 >> 8 : lane == 1 ? ((B0 & 0xFFu) << 16) | (B1 >> 16) : lane == 2 ? ((B1 & 0xFFFFu) << 8) | (B2 >> 24) : B2 & 0xFFFFFFu;
-    uint32_t w = 0;
-    int ge = 0;
-    if (lane < 4) ge = golay_decode_word(word, genc, gerr, &w);
-    const uint32_t w0 = __shfl_sync(0xffffffffu, w, 0), w1 = __shfl_sync(0xffffffffu, w, 1), w2 = __shfl_sync(0xffffffffu, w, 2), w3 = __shfl_sync(0xffffffffu, w, 3);
-    ge += __shfl_xor_sync(0xffffffffu, ge, 1);
-    ge += __shfl_xor_sync(0xffffffffu, ge, 2);
-    if (lane == 0) {
-        StreamAux a;
-        a.lw01 = (w0 << 12) | w1;                                            // pack_12_to_8_x4x6, m17_bit_utils.cpp:152-172
-        a.lw23 = (w2 << 12) | w3;
-        a.golay_e = (uint32_t)ge;
-        a.cor = cor;
-        *(uint4 *)(saux + fidx) = *(const uint4 *)&a;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const unsigned e = __ldg(smap + STREAM_NIN + 32 * j + lane);
+        loff[j] = e & 0x1FFu; lsgn[j] = (e & 0x8000u) << 16;
+    }
+    const float *sbase = syms + c * sym_pitch + sym_carry;
+    const uint32_t base_g = sym_base ? (uint32_t)sym_base[c] : 0u;
+    const m17b_frame_rec *frec = frames + c * fcap;
+    float *soft2 = soft2_s[wid];
+    float2 *s2 = (float2 *)soft2;
+    // The group's record headers in one load (lane i: slot + i), the symbols of the next stream frame fetched while the current
+    // one is worked on: a warp's frames are a serial chain otherwise (header -> symbols -> normaliser -> picks -> Golay tables).
+    uint2 hdl = make_uint2(0, 0);
+    if (lane < SG_FPW && slot + lane < send) hdl = *(const uint2 *)(frec + slot + lane);
+    const bool mine = (hdl.y & 0xFF) == M17B_T_STREAM && ((hdl.y >> 8) & M17B_F_PARSED);
+    unsigned todo = __ballot_sync(FULL, mine);                                  // bit i: slot + i holds a parsed stream frame
+    if (!todo) return;
+    float v[6], vn[6];
+    auto fetch = [&](int i, float (&dst)[6]) {
+        const uint32_t off = __shfl_sync(FULL, hdl.x, i);
+        const float *src = sbase + (int32_t)(off - base_g);
+#pragma unroll
+        for (int k = 0; k < 6; k++) dst[k] = src[lane + 32 * k];
+    };
+    fetch(__ffs(todo) - 1, v);
+    while (todo) {
+        const int i = __ffs(todo) - 1;
+        todo &= todo - 1;
+        if (todo) fetch(__ffs(todo) - 1, vn);
+        // demap normaliser from the 8 sync symbols, summed in order (m17_dsp.cpp:35-37)
+        float sa = 0.0f;
+#pragma unroll
+        for (int q = 0; q < 8; q++) sa += fabsf(__shfl_sync(FULL, v[0], q));
+        const float cor = 8.0f / sa;
+        // both soft values of every payload symbol once (m = in * mag, m17_dsp.cpp:38-41); the maps only pick and sign them
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            const int idx = lane + 32 * k - 8;
+            if (idx >= 0) { const float m = v[k] * cor; s2[idx] = make_float2(-m, demap_lsb(m)); }
+        }
+        __syncwarp();
+        // 4 x hard_decode_24_bits (m17_bit_utils.cpp:180-187: bit = soft >= 0) + m_17_golay_decode: ballot bit i = LICH bit i, and
+        // the words are MSB first, so the reversed ballots read as one 96-bit big-endian string.  (Before the picks: the two
+        // dependent table look-ups of the Golay decoder are then in flight while the 272 trellis inputs are written.)
+        const unsigned B0 = __brev(__ballot_sync(FULL, __uint_as_float(__float_as_uint(soft2[loff[0]]) ^ lsgn[0]) >= 0.0f));
+        const unsigned B1 = __brev(__ballot_sync(FULL, __uint_as_float(__float_as_uint(soft2[loff[1]]) ^ lsgn[1]) >= 0.0f));
+        const unsigned B2 = __brev(__ballot_sync(FULL, __uint_as_float(__float_as_uint(soft2[loff[2]]) ^ lsgn[2]) >= 0.0f));
+        const uint32_t word = lane == 0 ? B0 >> 8 : lane == 1 ? ((B0 & 0xFFu) << 16) | (B1 >> 16) : lane == 2 ? ((B1 & 0xFFFFu) << 8) | (B2 >> 24) : B2 & 0xFFFFFFu;
+        uint32_t w = 0;
+        int ge = 0;
+        if (lane < 4) ge = golay_decode_word(word, genc, gerr, &w);
+        const int64_t fidx = c * fcap + slot + i;
+        float *o = ssoft + fidx * STREAM_NIN + lane;
+#pragma unroll
+        for (int j = 0; j < 8; j++) o[32 * j] = __uint_as_float(__float_as_uint(soft2[moff[j]]) ^ msgn[j]);
+        if (lane < STREAM_NIN - 256) o[256] = __uint_as_float(__float_as_uint(soft2[moff[8]]) ^ msgn[8]);
+        if (soft_out) {
+            float *so = soft_out + fidx * 368;
+            for (int k = lane; k < 368; k += 32) so[k] = soft2[k];
+        }
+        const uint32_t w0 = __shfl_sync(FULL, w, 0), w1 = __shfl_sync(FULL, w, 1), w2 = __shfl_sync(FULL, w, 2), w3 = __shfl_sync(FULL, w, 3);
+        ge += __shfl_xor_sync(FULL, ge, 1);
+        ge += __shfl_xor_sync(FULL, ge, 2);
+        if (lane == 0) {
+            StreamAux a;
+            a.lw01 = (w0 << 12) | w1;                                            // pack_12_to_8_x4x6, m17_bit_utils.cpp:152-172
+            a.lw23 = (w2 << 12) | w3;
+            a.golay_e = (uint32_t)ge;
+            a.cor = cor;
+            *(uint4 *)(saux + fidx) = *(const uint4 *)&a;
+        }
+        __syncwarp();                                                            // soft2 is rewritten by the next frame
+#pragma unroll
+        for (int k = 0; k < 6; k++) v[k] = vn[k];
     }
 }
 __global__ void __launch_bounds__(32) k_stream_acs(const float *__restrict__ ssoft, const StreamAux *__restrict__ saux, m17b_frame_rec *frames, int64_t fcap,
@@ -538,7 +574,7 @@ static int launch_decode(m17b_ctx *ctx, const float *syms, int64_t sym_pitch, in
     if (aux) { CUDA_TRY(cudaEventRecord(ev_fork, st)); CUDA_TRY(cudaStreamWaitEvent(aux, ev_fork, 0)); st2 = aux; }
     k_decode_frames<DECODE_NT><<<grid, DECODE_NT, decode_smem(), st2>>>(syms, sym_pitch, sym_carry, sym_base, frames, fcap, nframes,
                                                                        frame_rng, tiles, soft_out, ctx->d_crc, ctx->d_genc, ctx->d_gerr, bert_on);
-    k_stream_gather<<<grid * (32 / SG_WARPS), SG_WARPS * 32, 0, st>>>(syms, sym_pitch, sym_carry, sym_base, frames, fcap, nframes, frame_rng, tiles * 32, nchan,
+    k_stream_gather<<<(grid * (32 / SG_FPW) + SG_WARPS - 1) / SG_WARPS, SG_WARPS * 32, 0, st>>>(syms, sym_pitch, sym_carry, sym_base, frames, fcap, nframes, frame_rng, tiles * 32, nchan,
                                                                      ctx->d_smap, ctx->d_genc, ctx->d_gerr, ssoft, saux, soft_out);
     k_stream_acs<<<grid, 32, 0, st>>>(ssoft, saux, frames, fcap, nframes, frame_rng, tiles, ctx->d_crc);
     KERNEL_CHECK();
