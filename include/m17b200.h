@@ -58,7 +58,9 @@ enum { M17B_T_PREAMBLE = 0, M17B_T_LSF = 1, M17B_T_STREAM = 2, M17B_T_PACKET = 3
  * m17_rx_parse.cpp:20-32,128,145,153-157; m17_rx_frame.cpp:139,149,169).
  */
 typedef struct {
-    int32_t  sym_off;      /* index of the frame's first symbol in the channel's emitted symbol stream */
+    int32_t  sym_off;      /* index of the frame's first symbol in the channel's emitted symbol stream: a counter modulo 2^32
+                              since the last m17b_rx_reset (it wraps after 10.3 days of continuous symbols at 4800/s; all kernels
+                              only ever use differences of indices, consumers should compare (int32_t)(a - b) likewise)   */
     uint8_t  type;         /* M17B_T_*  (m17_sync_check winner)                                        */
     uint8_t  flags;        /* M17B_F_*                                                                 */
     uint8_t  golay_err;    /* stream frames: sum of the 4 Golay error counts                            */

@@ -135,11 +135,14 @@ struct State {
     }
     void dispatch() {
         // events and frames are merged in stream order: an event belongs before the first frame that ends after it
+        // (stream indices are counters modulo 2^32 -- they wrap after 10.3 days at 4800 symbols/s -- so positions are compared
+        //  through their wrapped difference, never directly)
         size_t e = 0;
+        auto rel = [](const m17b_event_rec &ev, const m17b_frame_rec &f) { return (int32_t)((uint32_t)ev.sym_idx - ((uint32_t)f.sym_off + 191u)); };
         for (auto &f : pend_fr) {
-            while (e < pend_ev.size() && pend_ev[e].sym_idx <= f.sym_off + 191 && !(pend_ev[e].kind == M17B_EV_LOS && pend_ev[e].sym_idx == f.sym_off + 191)) fire(pend_ev[e++]);
+            while (e < pend_ev.size() && rel(pend_ev[e], f) <= 0 && !(pend_ev[e].kind == M17B_EV_LOS && rel(pend_ev[e], f) == 0)) fire(pend_ev[e++]);
             if (cb.frame) cb.frame(&f, cb.user);
-            while (e < pend_ev.size() && pend_ev[e].kind == M17B_EV_LOS && pend_ev[e].sym_idx == f.sym_off + 191) fire(pend_ev[e++]);
+            while (e < pend_ev.size() && pend_ev[e].kind == M17B_EV_LOS && rel(pend_ev[e], f) == 0) fire(pend_ev[e++]);
         }
         while (e < pend_ev.size()) fire(pend_ev[e++]);
         pend_fr.clear(); pend_ev.clear();

@@ -366,9 +366,9 @@ extern "C" int m17b_rx_create(m17b_ctx *ctx, int64_t nchan, int64_t max_blocks, 
     return M17B_OK;
 }
 
-// radio_set_afc_on / radio_set_afc_off (radio.cpp:146-152).  With AFC on, m17b_dsp_rx alternates the AFC front end
-// (afc.cuh) and the sync/framer kernel one block at a time, because the NCO step of a block depends on the framer state and
-// the discriminator mean of the block before it.
+// radio_set_afc_on / radio_set_afc_off (radio.cpp:146-152).  With AFC on, the NCO step of a block depends on the framer state and
+// the discriminator mean of the block before it, so a channel's blocks are serial through the whole chain: m17b_dsp_rx then runs
+// the AFC front end of each block (afc.cuh) inside the timing-loop kernel's block loop, one launch per call.
 extern "C" int m17b_rx_set_afc(m17b_rx *rx, int on, void *stream) {
     if (!rx) return M17B_E_ARG;
     if (!on && rx->afc) {

@@ -575,7 +575,7 @@ def check_rx_chain_limiter_patch(ctx, P, nchan=40, nframes=8, seed=77):
 
 
 def check_rx_baseband(ctx, P, nchan=14, nframes=30, seed=22, verbose=False, split=None):
-    eb = [None, 12, 10, 8, 6, 4, 2, 0, 12, 10, 8, 6, 4, 2][:nchan]
+    eb = ([None, 12, 10, 8, 6, 4, 2, 0, 12, 10, 8, 6, 4, 2] * ((nchan + 13) // 14))[:nchan]
     D, pl = signals.baseband_channels(P, nchan, nframes, seed, eb)
     o = P.rx_run(D, seam=1)
     res = run_chain(ctx, D, 1, split)

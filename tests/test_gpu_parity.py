@@ -45,6 +45,12 @@ def test_rx_baseband_ebn0_sweep(ctx, port):
     gc.check_rx_baseband(ctx, port)
 
 
+def test_rx_baseband_ebn0_sweep_1024_channels(ctx, port):
+    """BASELINE configs[1] width at the 2-sps baseband seam: 1024 channels, Eb/N0 0..12 dB in 2-dB steps and noise-free, every
+    channel compared bit for bit with the oracle (symbols, records, events, counters)"""
+    print(gc.check_rx_baseband(ctx, port, nchan=1024, nframes=24, seed=1024))
+
+
 def test_rx_chain_from_iq(ctx, port):
     gc.check_rx_chain(ctx, port)
 
