@@ -442,6 +442,26 @@ __global__ void __launch_bounds__(SG_WARPS * 32) k_stream_gather(const float *__
         for (int k = 0; k < 6; k++) dst[k] = src[lane + 32 * k];
     };
     fetch(__ffs(todo) - 1, v);
+    // the frame whose Golay decode is still in flight: received word (lanes 0..3), its parity look-up, record index, normaliser
+    bool pend = false;
+    uint32_t pword = 0, pe1 = 0;
+    int64_t pfidx = 0;
+    float pcor = 0.0f;
+    auto lich_finish = [&](uint32_t e, uint32_t wd, int64_t fi, float cr) {      // e = gerr[syndrome]: error weight << 12 | data error pattern
+        const uint32_t w = lane < 4 ? ((wd >> 12) & 0xFFF) ^ (e & 0xFFF) : 0u;
+        int ge = lane < 4 ? (int)(e >> 12) : 0;
+        const uint32_t w0 = __shfl_sync(FULL, w, 0), w1 = __shfl_sync(FULL, w, 1), w2 = __shfl_sync(FULL, w, 2), w3 = __shfl_sync(FULL, w, 3);
+        ge += __shfl_xor_sync(FULL, ge, 1);
+        ge += __shfl_xor_sync(FULL, ge, 2);
+        if (lane == 0) {
+            StreamAux a;
+            a.lw01 = (w0 << 12) | w1;                                            // pack_12_to_8_x4x6, m17_bit_utils.cpp:152-172
+            a.lw23 = (w2 << 12) | w3;
+            a.golay_e = (uint32_t)ge;
+            a.cor = cr;
+            *(uint4 *)(saux + fi) = *(const uint4 *)&a;
+        }
+    };
     while (todo) {
         const int i = __ffs(todo) - 1;
         todo &= todo - 1;
@@ -465,9 +485,14 @@ __global__ void __launch_bounds__(SG_WARPS * 32) k_stream_gather(const float *__
         const unsigned B1 = __brev(__ballot_sync(FULL, __uint_as_float(__float_as_uint(soft2[loff[1]]) ^ lsgn[1]) >= 0.0f));
         const unsigned B2 = __brev(__ballot_sync(FULL, __uint_as_float(__float_as_uint(soft2[loff[2]]) ^ lsgn[2]) >= 0.0f));
         const uint32_t word = lane == 0 ? B0 >> 8 : lane == 1 ? ((B0 & 0xFFu) << 16) | (B1 >> 16) : lane == 2 ? ((B1 & 0xFFFFu) << 8) | (B2 >> 24) : B2 & 0xFFFFFFu;
-        uint32_t w = 0;
-        int ge = 0;
-        if (lane < 4) ge = golay_decode_word(word, genc, gerr, &w);
+        // m_17_golay_decode (m17_golay.cpp:103-116) is two dependent table look-ups; they are spread over two frames so that
+        // nothing waits for them: this frame's parity look-up and the previous frame's syndrome look-up are issued here, the
+        // previous frame's LICH record is completed after this frame's picks.
+        uint32_t e2 = 0, e1 = 0;
+        if (lane < 4) {
+            if (pend) e2 = __ldg(&gerr[(pword & 0xFFF) ^ pe1]);
+            e1 = __ldg(&genc[(word >> 12) & 0xFFF]);
+        }
         const int64_t fidx = c * fcap + slot + i;
         float *o = ssoft + fidx * STREAM_NIN + lane;
 #pragma unroll
@@ -477,20 +502,16 @@ __global__ void __launch_bounds__(SG_WARPS * 32) k_stream_gather(const float *__
             float *so = soft_out + fidx * 368;
             for (int k = lane; k < 368; k += 32) so[k] = soft2[k];
         }
-        const uint32_t w0 = __shfl_sync(FULL, w, 0), w1 = __shfl_sync(FULL, w, 1), w2 = __shfl_sync(FULL, w, 2), w3 = __shfl_sync(FULL, w, 3);
-        ge += __shfl_xor_sync(FULL, ge, 1);
-        ge += __shfl_xor_sync(FULL, ge, 2);
-        if (lane == 0) {
-            StreamAux a;
-            a.lw01 = (w0 << 12) | w1;                                            // pack_12_to_8_x4x6, m17_bit_utils.cpp:152-172
-            a.lw23 = (w2 << 12) | w3;
-            a.golay_e = (uint32_t)ge;
-            a.cor = cor;
-            *(uint4 *)(saux + fidx) = *(const uint4 *)&a;
-        }
+        if (pend) lich_finish(e2, pword, pfidx, pcor);
+        pend = true; pword = word; pe1 = e1; pfidx = fidx; pcor = cor;
         __syncwarp();                                                            // soft2 is rewritten by the next frame
 #pragma unroll
         for (int k = 0; k < 6; k++) v[k] = vn[k];
+    }
+    if (pend) {
+        uint32_t e2 = 0;
+        if (lane < 4) e2 = __ldg(&gerr[(pword & 0xFFF) ^ pe1]);
+        lich_finish(e2, pword, pfidx, pcor);
     }
 }
 __global__ void __launch_bounds__(32) k_stream_acs(const float *__restrict__ ssoft, const StreamAux *__restrict__ saux, m17b_frame_rec *frames, int64_t fcap,
