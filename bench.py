@@ -852,7 +852,7 @@ def run_cuda(args):
         "config": {"workload": f"configs[1]: {C} concurrent stream-mode channels per GPU x {T} blocks (10 s each), full m17_dsp_rx chain from int16 IQ "
                                f"(limiter, discriminator, RRC matched filter + timing loop, sync/framer, demap+gather, Viterbi, Golay, CRC, LICH), "
                                f"AWGN on IQ Eb/N0 {{22,24,26,30,inf}} dB, f0 +-1 kHz, random start delay",
-                   "channels_per_gpu": C, "blocks": T, "pipeline_slice_blocks": args.slice_blocks or 0, "channel_groups": "auto (4 independent channel-group chains on their own streams at 512..1184 channels)" if args.chan_groups is None else args.chan_groups, "l2": "input 1.97 GB per GPU >> 126 MB L2 (no flush needed)", "parallelism": f"channels sharded x{world}, no data-path collective", "host_numa_node_rank0": numa},
+                   "channels_per_gpu": C, "blocks": T, "pipeline_slice_blocks": args.slice_blocks or 0, "channel_groups": "auto (4 independent channel-group chains on their own streams from 512 channels up)" if args.chan_groups is None else args.chan_groups, "l2": "input 1.97 GB per GPU >> 126 MB L2 (no flush needed)", "parallelism": f"channels sharded x{world}, no data-path collective", "host_numa_node_rank0": numa},
         "e2e": {"value": frames_step / (e2e_ms / 1e3) / 25.0, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(C * T * 7680),
                 "d2h_bytes_per_step": int(C * rx.frame_cap * 64 + 4 * C), "records_equal_device_path": e2e_same,
                 "per_rank_ms": e2e_rank_ms, "h2d_copy_only_gbs_per_rank_all_ranks_at_once": h2d_rank_gbs,

@@ -206,7 +206,7 @@ int m17b_rx_set_slice_blocks(m17b_rx *rx, int blocks);
 /* Scheduling knob: run the batch as `groups` (0..8) contiguous channel groups, each a complete chain on its own stream, so
    that one group's latency-bound timing loop shares the SMs with another group's front end / decode.  Channels are
    independent (m17_dsp_rx keeps all state per receiver), so results do not depend on it.  0 / 1 = one chain; -1 = automatic
-   (the default: 4 groups for 512..1184 channels, one chain otherwise). */
+   (the default: 4 groups from 512 channels up, one chain below). */
 int m17b_rx_set_chan_groups(m17b_rx *rx, int groups);
 /* instrumentation: d_out uint64 [nchan][8] = {SM cycles, speculation rounds, cycles in staging / timing loop / emission / framer /
    carry (only in builds with -DM17B_PHASE_CLOCKS), spare} the one-warp-per-channel timing-loop kernel spent on each channel in its

@@ -43,7 +43,7 @@ struct m17b_rx {
     // channel-group pipeline (see m17b_dsp_rx): the channels are cut into chan_groups contiguous groups, each running its own
     // front end -> sync -> decode -> post chain on its own stream, so that the latency-bound timing loop of one group shares the SMs
     // with the throughput-bound front end / decode of another.  Channels are independent: results do not depend on it.
-    int chan_groups;                  // -1 = auto (4 groups for 512..1184 channels, measured on B200: 2.07 -> 1.96 ms at 1024 x 250), 0 / 1 = off
+    int chan_groups;                  // -1 = auto (4 groups from 512 channels up, see rx_groups_for), 0 / 1 = off
     cudaStream_t s_grp[M17B_MAX_GROUPS], s_grp_aux[M17B_MAX_GROUPS];
     cudaEvent_t ev_gfork, ev_gjoin[M17B_MAX_GROUPS], ev_gf[M17B_MAX_GROUPS], ev_gj[M17B_MAX_GROUPS];
     int sync_impl;                    // -1 auto; 0: warp per channel (sync.cuh); 2 / 4: CTA of that many warps per channel (sync_cta.cuh); 33: warp per channel with the taps in shared memory (sync_g.cuh)
@@ -563,10 +563,11 @@ static int rx_grouped(m17b_rx *rx, const int16_t *d_iq, const float *d_disc, int
 }
 static int rx_groups_for(const m17b_rx *rx) {
     int G = rx->chan_groups;
-    // auto: while every channel's timing loop is resident at once (<= 8 x 148 channels) the sync kernel ends with a tail of slow
-    // channels on mostly idle SMs; four staggered groups fill it with the next group's front end / decode.  Below 512 channels
-    // and above one wave nothing is gained (benchmarks/chan_groups.py).  More than 4 groups exceed the 8 hardware queues.
-    if (G < 0) G = (rx->nchan >= 512 && rx->nchan <= 8 * 148) ? 4 : 1;
+    // auto: the sync kernel ends with a tail of slow channels on mostly idle SMs, and its serial chains leave most issue slots
+    // free; four staggered groups fill both with the neighbours' front end / decode.  Measured with the round-2 kernels
+    // (benchmarks/chan_groups.py, profiles/r02f_chan_groups.jsonl): 1024 channels 1.56 -> 1.52 ms, 2048: 3.12 -> 2.83, 4096: 5.72 -> 5.23,
+    // 8192 x 100 blocks: 4.73 -> 4.54; below 512 channels nothing is gained.  More than 4 groups exceed the 8 hardware queues.
+    if (G < 0) G = rx->nchan >= 512 ? 4 : 1;
     if (G > M17B_MAX_GROUPS) G = M17B_MAX_GROUPS;
     if (G < 2 || rx->timing || rx->nchan < 2 * G) return 1;
     return G;
