@@ -805,7 +805,7 @@ def run_cuda(args):
         "ms": round(dec_ms, 4), "alg_bytes_per_frame": DECIMATOR_BYTES, "channel_frames": C * dec_blocks,
         "gbs": round(DECIMATOR_BYTES * C * dec_blocks / (dec_ms * 1e-3) / 1e9, 1)}
     achieved = STAGE_BYTES[dom] * C * T / (stage[dom] * 1e-3) / 1e9
-    kname = {"frontend": "k_frontend", "sync_frame": "k_sync_frame", "decode": "k_decode_frames", "post": "k_post"}
+    kname = {"frontend": "k_frontend", "sync_frame": "k_sync_frame", "decode": "k_stream_acs", "post": "k_post"}
     traffic = None
     try:                                       # dram__bytes_read+write per launch from the ncu --set full capture (profiles/)
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
