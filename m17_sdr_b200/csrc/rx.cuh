@@ -12,6 +12,7 @@
 
 #define M17B_TIMING_RING 64
 #define M17B_MAX_SLICES 16
+#define M17B_HOST_TAIL_PIECES 6       // m17b_dsp_rx_host: time pieces of the last channel chunk
 #define M17B_MAX_GROUPS 8
 struct m17b_rx {
     m17b_ctx *ctx;
@@ -31,7 +32,7 @@ struct m17b_rx {
     int64_t stage_chunk;
     cudaStream_t copy_stream, aux_stream;   // aux: LSF/packet/BERT frame decode runs beside the stream-frame decode
     cudaEvent_t ev_fork, ev_join;
-    cudaEvent_t ev_h2d[2], ev_done[2], ev_tail;
+    cudaEvent_t ev_h2d[2], ev_done[2], ev_piece[M17B_HOST_TAIL_PIECES];
     int afc, bert, last_launches, seam_last;
     void *d_pkt_state;                // [nchan] RxPacketState of m17b_rx_reassemble_packets (app.cuh), allocated on first use
     int *d_overflow;                  // sticky flags (m17b_rx_get_overflow): 1 = the symbol seam was given more symbols than the capacity
@@ -243,7 +244,7 @@ extern "C" int m17b_rx_destroy(m17b_rx *rx) {
         if (rx->ev_h2d[i]) cudaEventDestroy(rx->ev_h2d[i]);
         if (rx->ev_done[i]) cudaEventDestroy(rx->ev_done[i]);
     }
-    if (rx->ev_tail) cudaEventDestroy(rx->ev_tail);
+    for (int i = 0; i < M17B_HOST_TAIL_PIECES; i++) if (rx->ev_piece[i]) cudaEventDestroy(rx->ev_piece[i]);
     cudaFree(rx->d_frame_rng); cudaFree(rx->d_lsf_snap); cudaFree(rx->d_lsf_ver); cudaFree(rx->d_overflow); cudaFree(rx->d_pkt_state); cudaFree(rx->d_ssoft); cudaFree(rx->d_saux);
     if (rx->s_fe) cudaStreamDestroy(rx->s_fe);
     if (rx->s_sync) cudaStreamDestroy(rx->s_sync);
@@ -709,7 +710,7 @@ extern "C" int m17b_rx_get_overflow(m17b_rx *rx, int *h_flags) {
 }
 extern "C" int m17b_rx_last_launches(const m17b_rx *rx) { return rx ? rx->last_launches : 0; }
 
-// The chain for channels [c0, c0+nc) in TIME pieces [bounds[k], bounds[k+1]) on one stream, piece k starting once ready[k] has
+// The chain for channels [c0, c0+nc) in TIME pieces [bounds[k], bounds[k+1]), piece k starting once ready[k] has
 // fired (its samples have arrived): front end, timing loop + framer and frame decode per piece (the kernels' block-range forms,
 // results identical to one pass), the per-channel post stage once at the end.
 static int rx_pipeline_pieces(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t *d_iq, int64_t T, int npieces, const int64_t *bounds, const cudaEvent_t *ready,
@@ -719,25 +720,39 @@ static int rx_pipeline_pieces(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t
     m17b_frame_rec *frames = rx->d_frames + c0 * rx->fcap;
     float *syms = rx->d_syms + c0 * rx->sym_pitch;
     if (npieces > M17B_MAX_SLICES) return M17B_E_ARG;
+    // Three streams, as in the time-sliced pipeline: the front end of a piece starts when its samples have landed -- a lane walks a
+    // whole 1920-sample block, ~0.27 ms whatever the piece size -- beside the timing loop of the piece before it; the timing loop
+    // and the decode of the pieces stay in order.  What remains after the last byte is one front-end latency + the chain over the
+    // last piece.
+    CUDA_TRY(cudaEventRecord(rx->ev_start, st));
+    CUDA_TRY(cudaStreamWaitEvent(rx->s_fe, rx->ev_start, 0));
+    CUDA_TRY(cudaStreamWaitEvent(rx->s_sync, rx->ev_start, 0));
+    CUDA_TRY(cudaStreamWaitEvent(rx->s_dec, rx->ev_start, 0));
     for (int k = 0; k < npieces; k++) {
         const int64_t t0 = bounds[k], t1 = bounds[k + 1];
         int2 *rng = rx->d_frame_rng + (int64_t)k * rx->nchan + c0;
-        CUDA_TRY(cudaStreamWaitEvent(st, ready[k], 0));
-        int rc = launch_frontend(d_iq, nc, T, t0, t1 - t0, rx->d_state + c0, disc_w, mean_w, st);
+        CUDA_TRY(cudaStreamWaitEvent(rx->s_fe, ready[k], 0));
+        int rc = launch_frontend(d_iq, nc, T, t0, t1 - t0, rx->d_state + c0, disc_w, mean_w, rx->s_fe);
         if (rc) return rc;
-        rc = launch_sync(rx, c0, nc, disc_w, mean_w, T, (int)t0, (int)t1, rng, 1, st);
+        CUDA_TRY(cudaEventRecord(rx->ev_fe[k], rx->s_fe));
+        CUDA_TRY(cudaStreamWaitEvent(rx->s_sync, rx->ev_fe[k], 0));
+        rc = launch_sync(rx, c0, nc, disc_w, mean_w, T, (int)t0, (int)t1, rng, 1, rx->s_sync);
         if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(rx->ev_sy[k], rx->s_sync));
+        CUDA_TRY(cudaStreamWaitEvent(rx->s_dec, rx->ev_sy[k], 0));
         const int64_t span = t1 - t0;
-        rc = launch_decode(ctx, syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0, nc, nullptr, rx->d_ssoft + c0 * rx->fcap * STREAM_NIN, rx->d_saux + c0 * rx->fcap, st,
+        rc = launch_decode(ctx, syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0, nc, nullptr, rx->d_ssoft + c0 * rx->fcap * STREAM_NIN, rx->d_saux + c0 * rx->fcap, rx->s_dec,
                            rx->aux_stream, rx->ev_fork, rx->ev_join, rng, span + span / 64 + 4, rx->bert);
         if (rc) return rc;
         rx->last_launches += 4;
     }
-    k_post<<<grid_for(nc, POST_WARPS), POST_WARPS * 32, 0, st>>>(frames, rx->fcap, rx->d_nframes + c0, nc, rx->d_state + c0, ctx->d_crcpos, rx->d_stats + c0 * 8,
+    k_post<<<grid_for(nc, POST_WARPS), POST_WARPS * 32, 0, rx->s_dec>>>(frames, rx->fcap, rx->d_nframes + c0, nc, rx->d_state + c0, ctx->d_crcpos, rx->d_stats + c0 * 8,
                                                               rx->d_lsf_snap + c0 * rx->nsnap * 32, rx->nsnap, rx->d_lsf_ver + c0 * rx->fcap,
                                                               ctx->d_prbs, rx->bert);
     KERNEL_CHECK();
     rx->last_launches += 1;
+    CUDA_TRY(cudaEventRecord(rx->ev_end, rx->s_dec));
+    CUDA_TRY(cudaStreamWaitEvent(st, rx->ev_end, 0));
     return M17B_OK;
 }
 
@@ -768,7 +783,7 @@ extern "C" int m17b_dsp_rx_host(m17b_rx *rx, const int16_t *h_iq, int64_t nblock
             CUDA_TRY(cudaEventCreateWithFlags(&rx->ev_h2d[i], cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&rx->ev_done[i], cudaEventDisableTiming));
         }
-        CUDA_TRY(cudaEventCreateWithFlags(&rx->ev_tail, cudaEventDisableTiming));
+        for (int i = 0; i < M17B_HOST_TAIL_PIECES; i++) CUDA_TRY(cudaEventCreateWithFlags(&rx->ev_piece[i], cudaEventDisableTiming));
     }
     rx->last_launches = 0; rx->last_blocks = nblocks; rx->seam_last = 0;
     const int64_t nchunks = (rx->nchan + rx->stage_chunk - 1) / rx->stage_chunk;
@@ -777,22 +792,27 @@ extern "C" int m17b_dsp_rx_host(m17b_rx *rx, const int16_t *h_iq, int64_t nblock
         const int64_t c0 = ci * rx->nchan / nchunks, nc = (ci + 1) * rx->nchan / nchunks - c0;     // <= stage_chunk
         // the staging buffer may only be overwritten once the kernels that read it two chunks ago are done
         CUDA_TRY(cudaStreamWaitEvent(rx->copy_stream, rx->ev_done[k], 0));
-        const int64_t tail_blocks = 25;
-        if (ci == nchunks - 1 && !rx->afc && T >= 4 * tail_blocks) {
-            // The LAST chunk arrives in two time pieces and its first T - 25 blocks are processed while the last 25 are still on
-            // the bus: what remains after the final byte has landed is the chain over 25 blocks instead of the timing loop's
-            // latency over all T (every channel's blocks are serial), which is the tail of the whole call.
-            const int64_t bounds[3] = {0, T - tail_blocks, T};
+        const int64_t piece_min = 25;
+        if (ci == nchunks - 1 && !rx->afc && T >= 4 * piece_min) {
+            // The LAST chunk arrives in up to six time pieces (each at least 25 blocks), and every piece is processed while the
+            // later ones are still on the bus: what remains after the final byte has landed is the chain over the last piece
+            // instead of the timing loop's latency over all T (every channel's blocks are serial), which is the tail of the whole
+            // call.  (Two pieces, the second of 25 blocks, run on one stream: 36.4 ms; pieces pipelined on three streams: see DESIGN.md.)
+            int np = (int)(T / piece_min);
+            if (np > M17B_HOST_TAIL_PIECES) np = M17B_HOST_TAIL_PIECES;
+            int64_t bounds[M17B_HOST_TAIL_PIECES + 1];
+            cudaEvent_t ready[M17B_HOST_TAIL_PIECES];
+            for (int q = 0; q <= np; q++) bounds[q] = q * T / np;
             const size_t pitch = (size_t)T * 7680;
             const char *src = (const char *)(h_iq + c0 * T * 3840);
             char *dst = (char *)rx->d_iq_stage[k];
-            CUDA_TRY(cudaMemcpy2DAsync(dst, pitch, src, pitch, (size_t)bounds[1] * 7680, (size_t)nc, cudaMemcpyHostToDevice, rx->copy_stream));
-            CUDA_TRY(cudaEventRecord(rx->ev_h2d[k], rx->copy_stream));
-            CUDA_TRY(cudaMemcpy2DAsync(dst + bounds[1] * 7680, pitch, src + bounds[1] * 7680, pitch, (size_t)tail_blocks * 7680, (size_t)nc, cudaMemcpyHostToDevice,
-                                       rx->copy_stream));
-            CUDA_TRY(cudaEventRecord(rx->ev_tail, rx->copy_stream));
-            const cudaEvent_t ready[2] = {rx->ev_h2d[k], rx->ev_tail};
-            int rc = rx_pipeline_pieces(rx, c0, nc, rx->d_iq_stage[k], T, 2, bounds, ready, st);
+            for (int q = 0; q < np; q++) {
+                CUDA_TRY(cudaMemcpy2DAsync(dst + bounds[q] * 7680, pitch, src + bounds[q] * 7680, pitch, (size_t)(bounds[q + 1] - bounds[q]) * 7680, (size_t)nc,
+                                           cudaMemcpyHostToDevice, rx->copy_stream));
+                CUDA_TRY(cudaEventRecord(rx->ev_piece[q], rx->copy_stream));
+                ready[q] = rx->ev_piece[q];
+            }
+            int rc = rx_pipeline_pieces(rx, c0, nc, rx->d_iq_stage[k], T, np, bounds, ready, st);
             if (rc) return rc;
             CUDA_TRY(cudaEventRecord(rx->ev_done[k], st));
             CUDA_TRY(cudaMemcpyAsync(h_frames + c0 * rx->fcap, rx->d_frames + c0 * rx->fcap, sizeof(m17b_frame_rec) * nc * rx->fcap, cudaMemcpyDeviceToHost, st));
