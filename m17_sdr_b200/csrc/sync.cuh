@@ -59,33 +59,41 @@ __device__ __forceinline__ void sync_adjust(int TH, int &thr, int &index, int &c
 
 // Two consecutive symbols for one lane: windows xs[n0 .. n0+30] and xs[n0+2 .. n0+32], n0 = i + 4*lane.  R = i & 3 is
 // warp-uniform, so array / offset of every tap are compile-time and the 32 lanes read consecutive words.
+// The window load depends on the residue R of the first sample (compile-time indices into the split array); the arithmetic
+// does not.  Each kernel calls load_window<R> under its switch on R and then ONE copy of the arithmetic: with dot2<0..3> and
+// dot6<0..1> inlined whole, the packed dot products alone were 1240 of the kernel's 4500 SASS instructions, and instruction
+// fetch is one of this kernel's stall reasons (no_instruction, profiles/r02f_ncu_hotspots.txt).
+template <int R, int NX>
+__device__ __forceinline__ void load_window(const float (*X)[SY_XQ], int base, float (&x)[NX]) {
+#pragma unroll
+    for (int k = 0; k < NX; k++) x[k] = X[(R + k) & 3][base + ((R + k) >> 2)];
+}
+// Two consecutive symbols for one lane: windows xs[n0 .. n0+30] and xs[n0+2 .. n0+32], n0 = i + 4*lane.  R = i & 3 is
+// warp-uniform, so array / offset of every tap are compile-time and the 32 lanes read consecutive words.
+// tp[k] = (matched tap k, derivative tap k): one FMUL2 with the sample broadcast gives both rounded products, and one
+// FFMA2 (product * 1.0 + running pair) adds them to the two running sums -- each half rounds exactly like the reference's
+// sum += in[i]*c[i] (m17_rx_sync.cpp:25-31).  `one` comes from memory: with a literal 1.0 ptxas folds the pair into a
+// contracted FFMA2 (one rounding), -fmad=false notwithstanding.
+__device__ __forceinline__ void dot2_core(const float (&x)[M17B_FN + 2], const f32x2 (&tp)[M17B_FN], f32x2 one, float &sa, float &da, float &sb, float &db) {
+    f32x2 acc0 = mul2(tp[0], pack2(x[0], x[0])), acc1 = mul2(tp[0], pack2(x[2], x[2]));
+#pragma unroll
+    for (int k = 1; k < M17B_FN; k++) {
+        acc0 = fma2(mul2(tp[k], pack2(x[k], x[k])), one, acc0);
+        acc1 = fma2(mul2(tp[k], pack2(x[k + 2], x[k + 2])), one, acc1);
+    }
+    unpack2(acc0, sa, da);
+    unpack2(acc1, sb, db);
+}
 template <int R>
 __device__ __forceinline__ void dot2(const float (*X)[SY_XQ], int base, const f32x2 (&tp)[M17B_FN], f32x2 one, float &sa, float &da, float &sb, float &db) {
     float x[M17B_FN + 2];
-#pragma unroll
-    for (int k = 0; k < M17B_FN + 2; k++) x[k] = X[(R + k) & 3][base + ((R + k) >> 2)];
-    // tp[k] = (matched tap k, derivative tap k): one FMUL2 with the sample broadcast gives both rounded products, and one
-    // FFMA2 (product * 1.0 + running pair) adds them to the two running sums -- each half rounds exactly like the reference's
-    // sum += in[i]*c[i] (m17_rx_sync.cpp:25-31).  `one` comes from memory: with a literal 1.0 ptxas folds the pair into a
-    // contracted FFMA2 (one rounding), -fmad=false notwithstanding.
-    f32x2 a = mul2(tp[0], pack2(x[0], x[0])), b = mul2(tp[0], pack2(x[2], x[2]));
-#pragma unroll
-    for (int k = 1; k < M17B_FN; k++) {
-        a = fma2(mul2(tp[k], pack2(x[k], x[k])), one, a);
-        b = fma2(mul2(tp[k], pack2(x[k + 2], x[k + 2])), one, b);
-    }
-    unpack2(a, sa, da);
-    unpack2(b, sb, db);
+    load_window<R>(X, base, x);
+    dot2_core(x, tp, one, sa, da, sb, db);
 }
-
 // Six consecutive symbols for one lane (a whole 40-ms block in one warp round): windows xs[n0 + 2m .. n0 + 2m + 30], m = 0..5,
 // n0 = i + 12*lane, so the lane loads 41 samples once.  With the residue-split layout consecutive lanes (stride 12 samples =
 // 3 words per residue array) read 32 different banks.
-template <int R>
-__device__ __forceinline__ void dot6(const float (*X)[SY_XQ], int base, const f32x2 (&tp)[M17B_FN], f32x2 one, float (&s)[6], float (&d)[6]) {
-    float x[M17B_FN + 10];
-#pragma unroll
-    for (int k = 0; k < M17B_FN + 10; k++) x[k] = X[(R + k) & 3][base + ((R + k) >> 2)];
+__device__ __forceinline__ void dot6_core(const float (&x)[M17B_FN + 10], const f32x2 (&tp)[M17B_FN], f32x2 one, float (&s)[6], float (&d)[6]) {
     f32x2 acc[6];
 #pragma unroll
     for (int m = 0; m < 6; m++) acc[m] = mul2(tp[0], pack2(x[2 * m], x[2 * m]));
@@ -96,6 +104,12 @@ __device__ __forceinline__ void dot6(const float (*X)[SY_XQ], int base, const f3
     }
 #pragma unroll
     for (int m = 0; m < 6; m++) unpack2(acc[m], s[m], d[m]);
+}
+template <int R>
+__device__ __forceinline__ void dot6(const float (*X)[SY_XQ], int base, const f32x2 (&tp)[M17B_FN], f32x2 one, float (&s)[6], float (&d)[6]) {
+    float x[M17B_FN + 10];
+    load_window<R>(X, base, x);
+    dot6_core(x, tp, one, s, d);
 }
 
 // AFC = true (m17b_rx_set_afc): the block's discriminator samples do not come from memory but from the AFC front end run by
@@ -273,7 +287,11 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
                 // Locked, at the start of a block: the threshold is 80, so a trip inside the block is rare -- speculate the
                 // whole block in ONE round, six consecutive symbols per lane (192 symbols, all inside the block for i <= 1).
                 float s6[6], d6[6];
-                if (i == 0) dot6<0>(sm.x, 3 * lane, tp, one, s6, d6); else dot6<1>(sm.x, 3 * lane, tp, one, s6, d6);
+                {
+                    float xw[M17B_FN + 10];
+                    if (i == 0) load_window<0>(sm.x, 3 * lane, xw); else load_window<1>(sm.x, 3 * lane, xw);
+                    dot6_core(xw, tp, one, s6, d6);
+                }
                 // votes (sync_update, m17_rx_sync.cpp:38-42): every symbol votes on the NEXT sample, so the only symbol of the
                 // block without a vote is the one at sample 383 (i == 1, lane 31, m == 5).  The common case needs no per-symbol
                 // threshold values: the lane keeps the running sum and its prefix extremes, the warp scan supplies the offset,
@@ -346,12 +364,14 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
             float sa = 0.0f, da = 0.0f, sb = 0.0f, db = 0.0f;
             if (valid_a) {
                 const int base = (i >> 2) + lane;
+                float xw[M17B_FN + 2];
                 switch (i & 3) {
-                    case 0: dot2<0>(sm.x, base, tp, one, sa, da, sb, db); break;
-                    case 1: dot2<1>(sm.x, base, tp, one, sa, da, sb, db); break;
-                    case 2: dot2<2>(sm.x, base, tp, one, sa, da, sb, db); break;
-                    default: dot2<3>(sm.x, base, tp, one, sa, da, sb, db); break;
+                    case 0: load_window<0>(sm.x, base, xw); break;
+                    case 1: load_window<1>(sm.x, base, xw); break;
+                    case 2: load_window<2>(sm.x, base, xw); break;
+                    default: load_window<3>(sm.x, base, xw); break;
                 }
+                dot2_core(xw, tp, one, sa, da, sb, db);
             }
             // votes happen on the sample after each symbol (sync_update, m17_rx_sync.cpp:38-42) if it is in this block
             const bool vote_a = valid_a && (ja + 1 < 384), vote_b = valid_b && (jb + 1 < 384);
