@@ -177,6 +177,9 @@ template <class F>
 __device__ __forceinline__ void viterbi_traceback(const uint16_t (&dec)[F::STEPS], uint8_t *obytes) {
     unsigned s = 0;
     for (int t = F::STEPS - 1; t > 8 * F::NBYTES; t--) s = trace_prev(s, dec[t]);
+    // (fully unrolled over the bytes: 900 of the trellis kernel's 1800 SASS instructions, run once per frame.  One byte per trip --
+    //  784 instructions, 64 registers, the output bytes in local memory -- was tried for the instruction cache's sake: no change
+    //  in the step, 1.82 -> 1.76 G frames/s on the stand-alone kernel.)
     for (int j = F::NBYTES - 1; j >= 0; j--) {
         unsigned d[8], acc = 0;
 #pragma unroll

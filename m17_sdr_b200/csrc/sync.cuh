@@ -571,11 +571,10 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
             if (lane < 30) sm.x[lane & 3][lane >> 2] = a;
         }
         sym_total += n;
-        if (nq > SY_RECQ - 3) flush_records();
+        if (nq > SY_RECQ - 3 || t + 1 == t1) flush_records();       // (the only call site: the kernel's code footprint matters)
         __syncwarp();
         PHASE(4);
     }
-    flush_records();
 
     // ---- store state
     if (AFC && lane == 0) {
