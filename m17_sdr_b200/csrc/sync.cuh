@@ -21,7 +21,8 @@
 #include "afc.cuh"
 
 #ifndef SY_WARPS
-#define SY_WARPS 4
+#define SY_WARPS 2            // channels (warps) per CTA.  1024 channels are 6.9 warps per SM: with 4-warp CTAs 108 SMs hold 8 warps and 40
+                              // hold 4; 2-warp CTAs spread them 6..8 (bench step 1.496 -> 1.484 ms; one warp per CTA: 1.510)
 #endif
 #define SY_XQ   106           // (30 + 384 + 2 + 8 pad) / 4 entries per residue class
 #define SY_HIST  (8 + 208)
