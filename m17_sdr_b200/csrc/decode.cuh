@@ -267,12 +267,15 @@ __device__ __forceinline__ void decode_conv(const float *row, uint16_t *dec_smem
 
 // frames: records pre-filled with sym_off/type/flags by the framer (or by k_parse_init); the symbols of record r
 // of channel c start at syms[c*sym_pitch + sym_carry + (rec.sym_off - sym_base[c])].
-// This kernel handles the LSF / packet / BERT frames (a handful per channel and call; CTAs without one exit at once); stream
-// frames go through k_stream_gather + k_stream_acs below.
+// This kernel handles the LSF / packet / BERT frames (a handful per channel and call); stream frames go through k_stream_gather +
+// k_stream_acs below.  Its frames come as a compact list (dlist[0] = count, dlist[1 + i] = channel * fcap + slot, appended by
+// k_stream_gather, which sees every record header anyway): thread i of the grid takes list entry i, so the warps are full.  (The
+// first form mapped a CTA to 32 consecutive slots of one channel: one or two active lanes per warp -- 65 536 channels x 25 blocks
+// spent more time here, one LSF per channel, than in the front end.)  CTAs beyond the list exit at once.
 template <int NT>
 __global__ void __launch_bounds__(NT) k_decode_frames(const float *__restrict__ syms, int64_t sym_pitch, int sym_carry,
                                                       const int32_t *__restrict__ sym_base, m17b_frame_rec *frames, int64_t fcap,
-                                                      const int32_t *__restrict__ nframes, const int2 *__restrict__ frame_rng, int tiles_per_chan, float *soft_out,
+                                                      const int32_t *__restrict__ dlist, float *soft_out,
                                                       const uint16_t *__restrict__ g_crc, const uint16_t *__restrict__ genc,
                                                       const uint16_t *__restrict__ gerr, int bert_on) {
     extern __shared__ unsigned char smem_raw[];
@@ -281,28 +284,28 @@ __global__ void __launch_bounds__(NT) k_decode_frames(const float *__restrict__ 
     uint16_t *dec = (uint16_t *)(smem_raw + (size_t)NT * PITCH * 4);        // [148 or 244][NT]
     __shared__ uint16_t crc_tab[256];
     const int tid = threadIdx.x, lane = tid & 31, wbase = tid & ~31;
-    const int64_t c = blockIdx.x / tiles_per_chan;
-    const int tile = blockIdx.x % tiles_per_chan;
-    // records [lo, nfr) of the channel: the whole call, or the slice a pipelined sync kernel just completed
-    int lo = 0, nfr;
-    if (frame_rng) { const int2 r = frame_rng[c]; lo = r.x; nfr = r.y; }
-    else nfr = min((int64_t)nframes[c], fcap);
-    const int slot = lo + tile * NT + tid;
-    m17b_frame_rec *rec = frames + c * fcap + slot;
+    const int64_t nlist = dlist[0];
+    if ((int64_t)blockIdx.x * NT >= nlist) return;
+    for (int i = tid; i < 256; i += NT) crc_tab[i] = g_crc[i];
+    // a small grid walks the list (the host does not know its length: a grid sized for the worst case was 9216 CTAs of 24.7 KB
+    // shared memory each to dispatch, nearly all empty, ahead of the trellis kernel launched beside this one)
+    for (int64_t b0 = (int64_t)blockIdx.x * NT; b0 < nlist; b0 += (int64_t)gridDim.x * NT) {
+    const int64_t li = b0 + tid;
+    const bool work = li < nlist;
+    const int64_t fi = work ? (int64_t)dlist[1 + li] : 0;               // channel * fcap + slot (every entry is a parsed LSF / packet / BERT record)
+    const int64_t c = fi / fcap;
+    const int slot = (int)(fi - c * fcap);
+    m17b_frame_rec *rec = frames + fi;
     int type = -1, flags = 0;
     uint32_t w0 = 0;
     int64_t src = 0;
-    if (slot < nfr) {
+    if (work) {
         const uint2 hd = *(const uint2 *)rec;
         w0 = hd.x;
         type = (hd.y & 0xFF);
         flags = (hd.y >> 8) & 0xFF;
-        src = c * sym_pitch + sym_carry + ((int32_t)hd.x - (sym_base ? sym_base[c] : 0));
+        src = c * sym_pitch + sym_carry + (int32_t)(hd.x - (sym_base ? (uint32_t)sym_base[c] : 0u));
     }
-    const bool mine = type == M17B_T_LSF || type == M17B_T_PACKET || type == M17B_T_BERT;
-    const bool work = (slot < nfr) && (flags & M17B_F_PARSED) && mine;
-    if (!__syncthreads_or(work)) return;
-    for (int i = tid; i < 256; i += NT) crc_tab[i] = g_crc[i];
     // stage: each warp loads the rows of its own 32 frames (coalesced 128-byte requests)
     // (asynchronous copies: all 32 x 6 row pieces are in flight together -- with plain loads every row's stores waited for that
     //  row's loads, 12 % of the kernel's stall samples)
@@ -321,7 +324,7 @@ __global__ void __launch_bounds__(NT) k_decode_frames(const float *__restrict__ 
     asm volatile("cp.async.commit_group;");
     asm volatile("cp.async.wait_group 0;");
     __syncthreads();
-    if (!work) return;
+    if (work) {
     float *row = &rows[tid * PITCH];
     float hdr[8];
 #pragma unroll
@@ -378,6 +381,9 @@ __global__ void __launch_bounds__(NT) k_decode_frames(const float *__restrict__ 
     q3.x = w12; q3.y = __float_as_uint(cor); q3.z = 0; q3.w = 0;
     uint4 *r4 = (uint4 *)rec;
     r4[0] = q0; r4[1] = q1; r4[2] = q2; r4[3] = q3;
+    }
+    __syncthreads();                                                        // the rows are restaged by the next trip
+    }
 }
 
 // ---------------------------------------------------------------- stream frames: the decode in two kernels
@@ -394,7 +400,7 @@ __global__ void __launch_bounds__(SG_WARPS * 32) k_stream_gather(const float *__
                                                                  const m17b_frame_rec *__restrict__ frames, int64_t fcap, const int32_t *__restrict__ nframes,
                                                                  const int2 *__restrict__ frame_rng, int slots_per_chan, int64_t nchan,
                                                                  const uint16_t *__restrict__ smap, const uint16_t *__restrict__ genc, const uint16_t *__restrict__ gerr,
-                                                                 float *__restrict__ ssoft, StreamAux *__restrict__ saux, float *soft_out) {
+                                                                 float *__restrict__ ssoft, StreamAux *__restrict__ saux, float *soft_out, int32_t *dlist) {
     // (the first form of this kernel took one frame per warp and staged the map in shared memory per CTA: ~600 warp instructions
     //  per frame at an issue rate of 90 %, 0.16 ms for 245 000 frames; the map entries a lane uses are the same for every frame)
     __shared__ float soft2_s[SG_WARPS][368];                     // the frame's soft values in natural order: (-m, |m| - 0.6666) per payload symbol
@@ -434,7 +440,18 @@ __global__ void __launch_bounds__(SG_WARPS * 32) k_stream_gather(const float *__
     // one is worked on: a warp's frames are a serial chain otherwise (header -> symbols -> normaliser -> picks -> Golay tables).
     uint2 hdl = make_uint2(0, 0);
     if (lane < SG_FPW && slot + lane < send) hdl = *(const uint2 *)(frec + slot + lane);
-    const bool mine = (hdl.y & 0xFF) == M17B_T_STREAM && ((hdl.y >> 8) & M17B_F_PARSED);
+    const bool parsed = (hdl.y >> 8) & M17B_F_PARSED;
+    const int htype = hdl.y & 0xFF;
+    const bool mine = htype == M17B_T_STREAM && parsed;
+    // the other frame types go on k_decode_frames' list (dlist[0] = count): one atomic per warp that has any
+    const bool other = parsed && (htype == M17B_T_LSF || htype == M17B_T_PACKET || htype == M17B_T_BERT);
+    const unsigned om = __ballot_sync(FULL, other);
+    if (om) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(dlist, __popc(om));
+        base = __shfl_sync(FULL, base, 0);
+        if (other) dlist[1 + base + __popc(om & ((1u << lane) - 1u))] = (int32_t)(c * fcap + slot + lane);
+    }
     unsigned todo = __ballot_sync(FULL, mine);                                  // bit i: slot + i holds a parsed stream frame
     if (!todo) return;
     float v[6], vn[6];
@@ -585,21 +602,24 @@ static size_t decode_smem() { return (size_t)DECODE_NT * 193 * 4; }
 // frame_rng / max_frames: decode only the records [rng.x, rng.y) of each channel (at most max_frames of them).
 // ssoft [nchan * fcap][STREAM_NIN] floats and saux [nchan * fcap] are the scratch between the two stream-frame kernels.
 static int launch_decode(m17b_ctx *ctx, const float *syms, int64_t sym_pitch, int sym_carry, const int32_t *sym_base,
-                         m17b_frame_rec *frames, int64_t fcap, const int32_t *nframes, int64_t nchan, float *soft_out, float *ssoft, StreamAux *saux, cudaStream_t st,
+                         m17b_frame_rec *frames, int64_t fcap, const int32_t *nframes, int64_t nchan, float *soft_out, float *ssoft, StreamAux *saux, int32_t *dlist, cudaStream_t st,
                          cudaStream_t aux = nullptr, cudaEvent_t ev_fork = nullptr, cudaEvent_t ev_join = nullptr,
                          const int2 *frame_rng = nullptr, int64_t max_frames = 0, int bert_on = 0) {
     const int tiles = (int)(((frame_rng ? max_frames : fcap) + DECODE_NT - 1) / DECODE_NT);
     // (set on every call: the attribute is per device, a process may drive several)
     CUDA_TRY(cudaFuncSetAttribute(k_decode_frames<DECODE_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_smem()));
-    if ((int64_t)tiles * nchan * 32 > 0x7fffffffLL) return M17B_E_ARG;          // the gather kernel indexes (channel, slot) items in 32 bits
+    if ((int64_t)tiles * nchan * 32 > 0x7fffffffLL || nchan * fcap > 0x7fffffffLL) return M17B_E_ARG;          // (channel, slot) items and list entries are 32-bit
     const unsigned grid = (unsigned)(tiles * nchan);
-    // the kernels touch disjoint records: run the (rare, long, sparse) LSF/packet one beside the stream-frame ones
+    // dlist [1 + nchan * fcap]: the gather kernel walks every record header, decodes the stream frames' inputs and lists the others
+    CUDA_TRY(cudaMemsetAsync(dlist, 0, sizeof(int32_t), st));
+    k_stream_gather<<<(grid * (32 / SG_FPW) + SG_WARPS - 1) / SG_WARPS, SG_WARPS * 32, 0, st>>>(syms, sym_pitch, sym_carry, sym_base, frames, fcap, nframes, frame_rng, tiles * 32, nchan,
+                                                                     ctx->d_smap, ctx->d_genc, ctx->d_gerr, ssoft, saux, soft_out, dlist);
+    // the kernels touch disjoint records: run the (rare, long) LSF / packet one beside the stream frames' trellis pass
     cudaStream_t st2 = st;
     if (aux) { CUDA_TRY(cudaEventRecord(ev_fork, st)); CUDA_TRY(cudaStreamWaitEvent(aux, ev_fork, 0)); st2 = aux; }
-    k_decode_frames<DECODE_NT><<<grid, DECODE_NT, decode_smem(), st2>>>(syms, sym_pitch, sym_carry, sym_base, frames, fcap, nframes,
-                                                                       frame_rng, tiles, soft_out, ctx->d_crc, ctx->d_genc, ctx->d_gerr, bert_on);
-    k_stream_gather<<<(grid * (32 / SG_FPW) + SG_WARPS - 1) / SG_WARPS, SG_WARPS * 32, 0, st>>>(syms, sym_pitch, sym_carry, sym_base, frames, fcap, nframes, frame_rng, tiles * 32, nchan,
-                                                                     ctx->d_smap, ctx->d_genc, ctx->d_gerr, ssoft, saux, soft_out);
+    const unsigned dgrid = grid < 4u * 148u ? grid : 4u * 148u;
+    k_decode_frames<DECODE_NT><<<dgrid, DECODE_NT, decode_smem(), st2>>>(syms, sym_pitch, sym_carry, sym_base, frames, fcap, dlist, soft_out,
+                                                                       ctx->d_crc, ctx->d_genc, ctx->d_gerr, bert_on);
     k_stream_acs<<<grid, 32, 0, st>>>(ssoft, saux, frames, fcap, nframes, frame_rng, tiles, ctx->d_crc);
     KERNEL_CHECK();
     if (aux) { CUDA_TRY(cudaEventRecord(ev_join, aux)); CUDA_TRY(cudaStreamWaitEvent(st, ev_join, 0)); }
@@ -616,10 +636,13 @@ extern "C" int m17b_rx_parse_frames(m17b_ctx *ctx, const float *d_sym, const uin
     CUDA_TRY(cudaMallocAsync((void **)&d_n, sizeof(int32_t), st));
     CUDA_TRY(cudaMallocAsync((void **)&d_ssoft, (size_t)n * STREAM_NIN * sizeof(float), st));
     CUDA_TRY(cudaMallocAsync((void **)&d_saux, (size_t)n * sizeof(StreamAux), st));
+    int32_t *d_dlist;
+    CUDA_TRY(cudaMallocAsync((void **)&d_dlist, (size_t)(n + 1) * sizeof(int32_t), st));
     k_set_i32<<<1, 1, 0, st>>>(d_n, (int32_t)n);
     k_parse_init<<<grid_for(n, 256), 256, 0, st>>>(d_type, n, d_rec);
     KERNEL_CHECK();
-    int rc = launch_decode(ctx, d_sym, 0, 0, nullptr, d_rec, n, d_n, 1, d_soft, d_ssoft, d_saux, st);
+    int rc = launch_decode(ctx, d_sym, 0, 0, nullptr, d_rec, n, d_n, 1, d_soft, d_ssoft, d_saux, d_dlist, st);
+    CUDA_TRY(cudaFreeAsync(d_dlist, st));
     CUDA_TRY(cudaFreeAsync(d_n, st));
     CUDA_TRY(cudaFreeAsync(d_ssoft, st));
     CUDA_TRY(cudaFreeAsync(d_saux, st));

@@ -25,6 +25,8 @@ struct m17b_rx {
     m17b_frame_rec *d_frames;
     m17b_event_rec *d_events;
     unsigned long long *d_stats;
+    int32_t *d_dlist;                  // [nchan][fcap + 1]: per launch over channels [c0, c0 + nc) the region at c0 * (fcap + 1) holds {count, entries} of the
+                                      // LSF / packet / BERT frames k_decode_frames has to take (decode.cuh)
     float *d_ssoft; StreamAux *d_saux; // scratch between the two stream-frame decode kernels: [nchan * fcap][272] kept trellis inputs, [nchan * fcap] LICH words / normaliser
     uint8_t *d_lsf_snap, *d_lsf_ver;  // [nchan][nsnap][32] link-setup data as it stood (version 0 = at the start of the call), [nchan][fcap] version per record
     int nsnap;
@@ -256,7 +258,7 @@ extern "C" int m17b_rx_destroy(m17b_rx *rx) {
         if (rx->ev_done[i]) cudaEventDestroy(rx->ev_done[i]);
     }
     for (int i = 0; i < M17B_HOST_TAIL_PIECES; i++) if (rx->ev_piece[i]) cudaEventDestroy(rx->ev_piece[i]);
-    cudaFree(rx->d_frame_rng); cudaFree(rx->d_lsf_snap); cudaFree(rx->d_lsf_ver); cudaFree(rx->d_overflow); cudaFree(rx->d_pkt_state); cudaFree(rx->d_ssoft); cudaFree(rx->d_saux);
+    cudaFree(rx->d_frame_rng); cudaFree(rx->d_lsf_snap); cudaFree(rx->d_lsf_ver); cudaFree(rx->d_overflow); cudaFree(rx->d_pkt_state); cudaFree(rx->d_ssoft); cudaFree(rx->d_saux); cudaFree(rx->d_dlist);
     if (rx->s_fe) cudaStreamDestroy(rx->s_fe);
     if (rx->s_sync) cudaStreamDestroy(rx->s_sync);
     if (rx->s_dec) cudaStreamDestroy(rx->s_dec);
@@ -339,10 +341,17 @@ extern "C" int m17b_rx_create(m17b_ctx *ctx, int64_t nchan, int64_t max_blocks, 
     A((void **)&rx->d_lsf_ver, (size_t)nchan * rx->fcap);
     A((void **)&rx->d_ssoft, (size_t)nchan * rx->fcap * STREAM_NIN * sizeof(float));
     A((void **)&rx->d_saux, (size_t)nchan * rx->fcap * sizeof(StreamAux));
+    A((void **)&rx->d_dlist, (size_t)nchan * (rx->fcap + 1) * sizeof(int32_t));
     A((void **)&rx->d_overflow, sizeof(int));
     if (e != cudaSuccess) { m17b_set_cuda_error(e, __FILE__, __LINE__); m17b_rx_destroy(rx); return e == cudaErrorMemoryAllocation ? M17B_E_NOMEM : M17B_E_CUDA; }
 #define CREATE_TRY(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { m17b_set_cuda_error(e__, __FILE__, __LINE__); m17b_rx_destroy(rx); return M17B_E_CUDA; } } while (0)
-    CREATE_TRY(cudaStreamCreateWithFlags(&rx->aux_stream, cudaStreamNonBlocking));
+    {   // The LSF / packet decode kernel is launched beside the stream frames' trellis kernel and after the same predecessor; a few
+        // long CTAs against thousands of short ones.  CTAs are dispatched kernel by kernel unless a priority says otherwise: at
+        // equal priority the trellis kernel's 9216 CTAs went first and the LSF kernel ran after them instead of beside them.
+        int lo = 0, hi = 0;
+        CREATE_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CREATE_TRY(cudaStreamCreateWithPriority(&rx->aux_stream, cudaStreamNonBlocking, hi));
+    }
     CREATE_TRY(cudaEventCreateWithFlags(&rx->ev_fork, cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreateWithFlags(&rx->ev_join, cudaEventDisableTiming));
     {   // the serial chain of the timing loop is the critical path of the pipeline: it gets the highest priority
@@ -468,7 +477,7 @@ static int rx_pipeline(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t *d_iq,
             KERNEL_CHECK();
         }
         STAGE_MARK(2);
-        int rc = launch_decode(ctx, syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0, nc, nullptr, rx->d_ssoft + c0 * rx->fcap * STREAM_NIN, rx->d_saux + c0 * rx->fcap, st,
+        int rc = launch_decode(ctx, syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0, nc, nullptr, rx->d_ssoft + c0 * rx->fcap * STREAM_NIN, rx->d_saux + c0 * rx->fcap, rx->d_dlist + c0 * (rx->fcap + 1), st,
                                aux_stream, ev_fork, ev_join, nullptr, 0, rx->bert);
         if (rc) return rc;
         STAGE_MARK(3);
@@ -491,7 +500,7 @@ static int rx_pipeline(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t *d_iq,
         int rc = launch_sync(rx, c0, nc, disc, mean, T, 0, (int)T, nullptr, commit_fe, st, grp >= 0);
         if (rc) return rc;
         STAGE_MARK(2);
-        rc = launch_decode(ctx, syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0, nc, nullptr, rx->d_ssoft + c0 * rx->fcap * STREAM_NIN, rx->d_saux + c0 * rx->fcap, st,
+        rc = launch_decode(ctx, syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0, nc, nullptr, rx->d_ssoft + c0 * rx->fcap * STREAM_NIN, rx->d_saux + c0 * rx->fcap, rx->d_dlist + c0 * (rx->fcap + 1), st,
                            aux_stream, ev_fork, ev_join, nullptr, 0, rx->bert);
         if (rc) return rc;
         STAGE_MARK(3);
@@ -524,7 +533,7 @@ static int rx_pipeline(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t *d_iq,
         CUDA_TRY(cudaEventRecord(rx->ev_sy[k], rx->s_sync));
         CUDA_TRY(cudaStreamWaitEvent(rx->s_dec, rx->ev_sy[k], 0));
         const int64_t span = t1 - t0;
-        rc = launch_decode(ctx, syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0, nc, nullptr, rx->d_ssoft + c0 * rx->fcap * STREAM_NIN, rx->d_saux + c0 * rx->fcap, rx->s_dec,
+        rc = launch_decode(ctx, syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0, nc, nullptr, rx->d_ssoft + c0 * rx->fcap * STREAM_NIN, rx->d_saux + c0 * rx->fcap, rx->d_dlist + c0 * (rx->fcap + 1), rx->s_dec,
                            aux_stream, ev_fork, ev_join, rng, span + span / 64 + 4, rx->bert);
         if (rc) return rc;
         rx->last_launches += 3;
@@ -548,7 +557,7 @@ static int rx_grouped(m17b_rx *rx, const int16_t *d_iq, const float *d_disc, int
         CUDA_TRY(cudaEventCreateWithFlags(&rx->ev_gfork, cudaEventDisableTiming));
         for (int g = 0; g < M17B_MAX_GROUPS; g++) {
             CUDA_TRY(cudaStreamCreateWithPriority(&rx->s_grp[g], cudaStreamNonBlocking, lo));
-            CUDA_TRY(cudaStreamCreateWithPriority(&rx->s_grp_aux[g], cudaStreamNonBlocking, lo));
+            CUDA_TRY(cudaStreamCreateWithPriority(&rx->s_grp_aux[g], cudaStreamNonBlocking, hi));   // (see aux_stream)
             CUDA_TRY(cudaEventCreateWithFlags(&rx->ev_gjoin[g], cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&rx->ev_gf[g], cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&rx->ev_gj[g], cudaEventDisableTiming));
@@ -614,7 +623,7 @@ extern "C" int m17b_rx_symbols(m17b_rx *rx, const float *d_syms, int64_t pitch, 
     k_framer<<<grid_for(rx->nchan, 4), 128, 0, st>>>(d_syms, pitch, d_nsym, rx->nchan, rx->d_state, rx->d_syms, rx->sym_pitch, cap, rx->d_nsym, rx->d_sym_base,
                                                    rx->d_frames, rx->fcap, rx->d_nframes, rx->d_events, rx->ecap, rx->d_nevents, rx->d_stats, rx->d_overflow);
     KERNEL_CHECK();
-    int rc = launch_decode(ctx, rx->d_syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base, rx->d_frames, rx->fcap, rx->d_nframes, rx->nchan, nullptr, rx->d_ssoft, rx->d_saux, st,
+    int rc = launch_decode(ctx, rx->d_syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base, rx->d_frames, rx->fcap, rx->d_nframes, rx->nchan, nullptr, rx->d_ssoft, rx->d_saux, rx->d_dlist, st,
                            rx->aux_stream, rx->ev_fork, rx->ev_join, nullptr, 0, rx->bert);
     if (rc) return rc;
     k_post<<<grid_for(rx->nchan, POST_WARPS), POST_WARPS * 32, 0, st>>>(rx->d_frames, rx->fcap, rx->d_nframes, rx->nchan, rx->d_state, ctx->d_crcpos, rx->d_stats,
@@ -746,7 +755,7 @@ static int rx_pipeline_pieces(m17b_rx *rx, int64_t c0, int64_t nc, const int16_t
         CUDA_TRY(cudaEventRecord(rx->ev_sy[k], rx->s_sync));
         CUDA_TRY(cudaStreamWaitEvent(rx->s_dec, rx->ev_sy[k], 0));
         const int64_t span = t1 - t0;
-        rc = launch_decode(ctx, syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0, nc, nullptr, rx->d_ssoft + c0 * rx->fcap * STREAM_NIN, rx->d_saux + c0 * rx->fcap, rx->s_dec,
+        rc = launch_decode(ctx, syms, rx->sym_pitch, M17B_SYM_CARRY, rx->d_sym_base + c0, frames, rx->fcap, rx->d_nframes + c0, nc, nullptr, rx->d_ssoft + c0 * rx->fcap * STREAM_NIN, rx->d_saux + c0 * rx->fcap, rx->d_dlist + c0 * (rx->fcap + 1), rx->s_dec,
                            rx->aux_stream, rx->ev_fork, rx->ev_join, rng, span + span / 64 + 4, rx->bert);
         if (rc) return rc;
         rx->last_launches += 4;
