@@ -1,15 +1,19 @@
-// decode.cuh -- K=5 rate-1/2 soft Viterbi and the fused per-frame decode:
-//   192 symbols -> demap -> de-randomise -> de-interleave -> de-puncture (one constant-memory gather map)
+// decode.cuh -- K=5 rate-1/2 soft Viterbi and the per-frame decode:
+//   192 symbols -> demap -> de-randomise -> de-interleave -> de-puncture (one gather map)
 //   -> Golay(24,12) x4 (stream) -> Viterbi -> byte pack -> CRC-16 -> 64-byte record.
 // Replaces m17_rx_parse / decode_link_frame / decode_stream_frame / decode_packet_frame
 // (m17_rx_parse.cpp:86-226), m17_viterbi_decode (m17_conv.cpp:73-113,148-168).
 //
-// Mapping: ONE THREAD PER FRAME.  The 16 path metrics live in registers (no shuffles, 16 independent
-// butterflies per step give the ILP), the 16 survivor decisions of a step are one uint16 in shared memory
-// laid out [step][thread] (conflict-free), and the traceback is a per-thread pointer chase through that
-// column.  Frames of a warp are staged into shared memory with coalesced row loads (pitch 193 floats, so
-// the per-thread column reads that follow hit 32 different banks).  The gather map index is uniform across
-// the warp, so constant-memory reads broadcast.
+// The trellis pass is ONE THREAD PER FRAME everywhere: the 16 path metrics live in registers (no shuffles, 16 independent
+// butterflies per step give the ILP, packed adds), the 16 survivor decisions of a step are one uint16 in per-thread local memory
+// (interleaved by the hardware, so the accesses coalesce), the traceback is a per-thread pointer chase.
+// Three kernels share it:
+//   k_stream_gather + k_stream_acs  stream frames (nearly all frames): a warp per 8 record slots produces the 272 kept trellis
+//                                   inputs in trellis order + the LICH / Golay words, and lists the frames of the other types;
+//                                   the trellis kernel stages 16 steps of 32 frames at a time (8.4 KB of shared memory per warp);
+//   k_decode_frames                 LSF / packet / BERT frames from that list, whole 192-symbol rows staged (pitch 193 floats, so the
+//                                   per-thread column reads hit 32 banks), gather map read warp-uniformly from constant memory;
+//   k_viterbi / k_viterbi_punct     the stand-alone batched decoders (m17b_viterbi_decode, m17b_viterbi_punctured).
 #pragma once
 #include "fec.cuh"
 
