@@ -61,12 +61,17 @@ __device__ __forceinline__ void fe_norm_pair(f32x2 S, float &nma, float &nmb, fl
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(ya) : "f"(sa));
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(yb) : "f"(sb));
     const f32x2 Y = pack2(ya, yb);
-    const f32x2 NEG1 = pack2(-1.0f, -1.0f), NHALF = pack2(-0.5f, -0.5f), ONE = pack2(1.0f, 1.0f);
+    const f32x2 NEG1 = pack2(-1.0f, -1.0f), ONE = pack2(1.0f, 1.0f);
     // -m = -RN(sqrt(s)): Newton step on the residual s - m0*m0, carried out on the negated iterate (round-to-nearest is
     // symmetric, so fma(r, -y/2, -m0) is exactly -(m0 + r*y/2)); only -m is needed below
     const f32x2 M0 = mul2(S, Y);
     const f32x2 NM0 = mul2(M0, NEG1);
-    const f32x2 NM = fma2(fma2(NM0, M0, S), mul2(Y, NHALF), NM0);
+    // -y/2 on the ALU pipe instead of a packed multiply on the FMA pipe (which the packed arithmetic of this kernel keeps busiest):
+    // one integer add per half flips the sign and decrements the exponent.  Exact whenever y and y/2 are normal: y = rsqrt(s) has
+    // an exponent of about -e(s)/2, so that holds for every normal s (m17b_selftest_limiter enumerates them).  0.523 -> 0.516 ms on
+    // the bench workload; doing the same for -m0 (a sign flip by LOP3) gains as much alone (0.518) and nothing on top (0.518).
+    const f32x2 NHY = pack2(__uint_as_float(__float_as_uint(ya) + 0x7F800000u), __uint_as_float(__float_as_uint(yb) + 0x7F800000u));
+    const f32x2 NM = fma2(fma2(NM0, M0, S), NHY, NM0);
     // g = RN(1/m): two residual corrections starting from y ~ 1/m (Markstein): fma(-m, g, 1) = 1 - m*g, g + (1 - m*g)*g.
     // The one input class this cannot round correctly is a divisor whose significand is all ones: the Newton iterate then
     // lands exactly on a rounding midpoint while the true quotient 2^-(e+1) (1 + 2^-24 + ..) lies just above it; its correctly

@@ -513,6 +513,9 @@ struct m17o_rx {
     int   afc_on; float afc_delta;                       /* radio.cpp:8-10 */
     /* timing loop */
     float buff[M17O_FN]; int clk, thr, index; float sum, dif;   /* m17_rx_sync.cpp:7-12,78 */
+    /* equaliser option (m17_equalize.cpp has no call site upstream): the matched filter's output half a
+       symbol before each symbol instant, and the equaliser's statics */
+    int   eq_on; float mid; m17o_eq eq;
     /* framer */
     float fsym[192], win[8]; int flock, fclk, ferr;      /* m17_rx_frame.cpp:14-18,104 */
     /* parser */
@@ -537,6 +540,7 @@ m17o_rx *m17o_rx_new(void) {
 void m17o_rx_free(m17o_rx *r) { free(r); }
 void m17o_rx_set_afc(m17o_rx *r, int on) { r->afc_on = on; }
 void m17o_rx_set_bert(m17o_rx *r, int on) { r->bert_on = on; }
+void m17o_rx_set_eq(m17o_rx *r, int on) { r->eq_on = on; if (on) m17o_eq_open(&r->eq); }
 void m17o_rx_get_bert(const m17o_rx *r, uint32_t *o) {
     o[0] = (uint32_t)r->prbs_state; o[1] = r->prbs_idx; o[2] = r->prbs_bad; o[3] = r->prbs_good; o[4] = r->prbs_eq; o[5] = r->prbs_dif;
     o[6] = r->bert_bits; o[7] = r->bert_errs;
@@ -618,7 +622,11 @@ void m17o_frontend(m17o_rx *r, const int16_t *iq, int nsamp, float *disc, int *n
 
 /* ---- matched filter + symbol-timing loop (m17_rx_sync.cpp:25-99) */
 static float dot31(const float *in, const float *c) { float s = in[0] * c[0]; for (int i = 1; i < M17O_FN; i++) s += in[i] * c[i]; return s; }
-int m17o_sync_samples(m17o_rx *r, const float *in, float *out, int len) {
+/* `mid` (optional): the T/2-spaced companion of every symbol for the equaliser option -- the SAME matched filter branch
+   (rx_sync_filter(m_buff, m_mf[m_index], FN), m17_rx_sync.cpp:25-31,84) evaluated on the sample before the symbol instant,
+   i.e. on the "else" sample of the loop below after m17_sync_adjust has run, so that both halves of a pair use one branch.
+   A symbol inserted by a forward bit slip (:56-58) gets mid = 0 like the symbol itself. */
+static int sync_samples_mid(m17o_rx *r, const float *in, float *out, float *mid, int len) {
     int m_idx = 0;                        /* may legally reach -1 on a backward slip at block start:
                                              the next symbol is then written to out[-1], i.e. lost */
     const int thresh = r->flock ? 80 : 10;   /* m17_rx_lock() cannot change inside a block (:91-94) */
@@ -629,7 +637,7 @@ int m17o_sync_samples(m17o_rx *r, const float *in, float *out, int len) {
         if (r->clk) {
             r->sum = dot31(r->buff, t_mf[r->index]);
             r->dif = dot31(r->buff, t_md[r->index]);
-            if (m_idx >= 0) out[m_idx] = r->sum;
+            if (m_idx >= 0) { out[m_idx] = r->sum; if (mid) mid[m_idx] = r->mid; }
             m_idx++;
         } else {
             float dif = r->dif;                                  /* sync_update :38-42 */
@@ -638,16 +646,18 @@ int m17o_sync_samples(m17o_rx *r, const float *in, float *out, int len) {
             if (dif < 0) r->thr--;
             if (r->thr > thresh) {                               /* m17_sync_adjust :45-72 */
                 r->index = (r->index + 1) % M17O_NF; r->thr = 0;
-                if (r->index == 0) { r->clk = 1; if (m_idx >= 0) out[m_idx] = 0; m_idx++; }
+                if (r->index == 0) { r->clk = 1; if (m_idx >= 0) { out[m_idx] = 0; if (mid) mid[m_idx] = 0; } m_idx++; }
             }
             if (r->thr < -thresh) {
                 r->thr = 0; r->index = (r->index + M17O_NF - 1) % M17O_NF;
                 if (r->index == M17O_NF - 1) { r->clk = 1; m_idx--; }
             }
+            if (mid) r->mid = dot31(r->buff, t_mf[r->index]);
         }
     }
     return m_idx < 0 ? 0 : m_idx;
 }
+int m17o_sync_samples(m17o_rx *r, const float *in, float *out, int len) { return sync_samples_mid(r, in, out, 0, len); }
 
 /* ---- frame decode (m17_rx_parse.cpp:86-226) */
 static void pack_bits(const uint8_t *bits, uint8_t *out, int nbits) {
@@ -769,7 +779,15 @@ static void rx_symbols(m17o_rx *r, const float *sym, int n) {
 void m17o_rx_baseband(m17o_rx *r, const float *disc, int n) {
     float tmp[960];
     if (r->t_disc && n <= 384) memcpy(&r->t_disc[r->n_blocks * 384], disc, sizeof(float) * (size_t)n);
-    int k = m17o_sync_samples(r, disc, tmp + 1, n);     /* +1: room for the D6 out[-1] write */
+    int k;
+    if (r->eq_on) {
+        /* equaliser option: eq_train_unknown (m17_equalize.cpp:185-213) on every (half-symbol, symbol) pair, its output is the
+           symbol the framer sees (between m17_rx_sync.cpp:77 and m17_rx_frame.cpp:173) */
+        float mid[960];
+        k = sync_samples_mid(r, disc, tmp + 1, mid + 1, n);
+        for (int q = 0; q < k; q++) { float in2[2] = { mid[1 + q], tmp[1 + q] }; tmp[1 + q] = m17o_eq_train_unknown(&r->eq, in2); }
+    } else
+    k = m17o_sync_samples(r, disc, tmp + 1, n);     /* +1: room for the D6 out[-1] write */
     if (r->t_nsym) r->t_nsym[r->n_blocks] = k;
     rx_symbols(r, tmp + 1, k);
     r->n_blocks++;
@@ -798,6 +816,7 @@ static void *job_main(void *p) {
                       j->syms ? j->syms + c * j->symcap : 0, j->symcap, j->frames ? j->frames + c * j->fcap : 0, j->fcap,
                       j->soft ? j->soft + c * j->fcap * 368 : 0, j->events ? j->events + c * j->ecap : 0, j->ecap);
         if (j->seam & 32) m17o_rx_set_bert(r, 1);         /* seam flag 32: BERT receive extension on */
+        if (j->seam & 64) m17o_rx_set_eq(r, 1);           /* seam flag 64: equaliser option on */
         if (j->seam & 16) m17o_rx_set_afc(r, 1);          /* seam flag 16: AFC on (radio_set_afc_on, radio.cpp:146-148) */
         if ((j->seam & 15) == 0) { const int16_t *iq = (const int16_t *)j->in + c * j->T * 3840; for (long t = 0; t < j->T; t++) m17o_dsp_rx(r, iq + t * 3840, 1920); }
         else { const float *d = (const float *)j->in + c * j->T * 384; for (long t = 0; t < j->T; t++) m17o_rx_baseband(r, d + t * 384, 384); }
