@@ -23,7 +23,9 @@
 #pragma once
 #include "decode.cuh"
 
+#ifndef FE_WARPS
 #define FE_WARPS 4
+#endif
 
 struct LimSample { float re, im; };
 
@@ -99,13 +101,18 @@ __device__ __forceinline__ void fe_norm_pair(f32x2 S, float &nma, float &nmb, fl
 // mul.rn.f32x2 followed by add.rn.f32x2 into one FFMA2 (common.cuh); fma2(im^2, one, re^2) is the same rounded sum and cannot be
 // contracted because the multiplier is not a compile-time 1.
 __device__ __forceinline__ void fe_limit_pair(uint32_t raw_a, uint32_t raw_b, f32x2 one, f32x2 &XRE, f32x2 &XIM, float *mo = nullptr, float *go = nullptr) {
-    // int16 -> float: one I2F.S16 per component, reading the half-register directly (exact).  (Tried twice in round 2: the
+    // int16 -> float (exact either way): I2F.S16 reads the half-register directly on the XU pipe.  (Tried twice in round 2: the
     // conversion on the ALU / FMA pipes instead -- (x ^ 0x8000) in the low mantissa bits of 2^23, minus 2^23 + 32768, exact and
     // verified over all 2^32 inputs -- to unload the XU pipe, where I2F draws twice its share of the stall samples (mio /
     // short_sb): 0.606 -> 0.631 ms on the first form of this kernel, 0.526 -> 0.553 ms on this one.  The four extra ALU / packed
     // instructions per sample cost more than the two I2F they replace.)
-    const f32x2 xr = pack2((float)(short)(raw_a & 0xFFFFu), (float)(short)(raw_b & 0xFFFFu));
-    const f32x2 xi = pack2((float)(short)(raw_a >> 16), (float)(short)(raw_b >> 16));
+    // (Round 2, last: the real component alone converted on the ALU pipe -- PRMT sign-extends the low half, I2FP.F32.S32 converts --
+    // while the imaginary one keeps its I2F.S16: one instruction more per sample, two XU slots per pair fewer, 0.5125 -> 0.5095 ms.
+    // The imaginary component alone the same way: no change; both: 0.5117.)
+    auto cvt_lo = [](uint32_t raw) -> float { int v; asm("prmt.b32 %0, %1, 0, 0x9910;" : "=r"(v) : "r"(raw)); return __int2float_rn(v); };
+    auto cvt_hi = [](uint32_t raw) -> float { return (float)(short)(raw >> 16); };
+    const f32x2 xr = pack2(cvt_lo(raw_a), cvt_lo(raw_b));
+    const f32x2 xi = pack2(cvt_hi(raw_a), cvt_hi(raw_b));
     constexpr float c_hi = 0.00003f;
     constexpr float c_lo = (float)(0.00003 - (double)0.00003f);
     const f32x2 CH = pack2(c_hi, c_hi), CL = pack2(c_lo, c_lo);
@@ -141,7 +148,7 @@ __device__ __forceinline__ LimSample fe_limit(uint32_t raw, f32x2 one, float *mo
 // Items are the (channel, block) pairs of blocks [t0, t0+Tc) of a call of T blocks per channel (T is the row pitch of iq,
 // disc and mean); the whole call is t0 = 0, Tc = T.  Sub-ranges let the host pipeline the front end of one time slice with
 // the timing loop of the previous one (rx.cuh).
-__global__ void __launch_bounds__(FE_WARPS * 32, 7) k_frontend(const uint32_t *__restrict__ iq, int64_t nchan, int64_t T, int64_t t0, int64_t Tc,
+__global__ void __launch_bounds__(FE_WARPS * 32, 28 / FE_WARPS) k_frontend(const uint32_t *__restrict__ iq, int64_t nchan, int64_t T, int64_t t0, int64_t Tc,
                                                             RxChanState *st, float *__restrict__ disc, float *__restrict__ mean, f32x2 one) {
     __shared__ float tout[FE_WARPS][32][17];
     __shared__ __align__(16) uint4 stage[FE_WARPS][2][160];      // two 20-sample chunks of the warp's 32 rows
