@@ -164,3 +164,53 @@ def test_channelizer_oracle_pinned_at_the_decimator_point(port):
     h = (np.hamming(96 * 4) * 600).astype(np.int16)
     Y = rng.integers(-20000, 20000, (25 * 90, 2)).astype(np.int16)
     assert np.array_equal(port.chan_run(Y, 96, 25, h), port.chan_run(Y, 96, 25, h, parts=[1, 30, 59]))
+
+
+def test_equaliser_live_chain_probe_pinned(port):
+    """The oracle's equaliser option (seam flag 64: eq_open + eq_train_unknown on T/2 pairs between the timing loop and the framer,
+    SURVEY 8f rank 3) against the SAME wiring built from the reference's own functions (oracle/ref/eq_shim.cpp: unmodified
+    m17_rx_sync_samples fed one sample per call, rx_sync_filter on its statics for the half-symbol output, eq_train_unknown,
+    m17_rx_symbols).  One pristine reference process per channel.  This pins the probe whose numbers DESIGN.md quotes; the option
+    is NOT part of the product (it breaks the chain: benchmarks/eq_live_chain_probe.py)."""
+    import ctypes as C
+    import os
+    import pytest
+    from m17_oracles import ORACLE_DIR, _p, _alloc_rx_out, shared_array, BLOCK
+    path = os.path.join(ORACLE_DIR, "_ref", "libm17ref_eq.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libm17ref_eq.so not built")
+    D, _ = signals.baseband_channels(port, 4, 12, 109, [None, 10, 6, 2])
+    Cn, T = D.shape[0], D.shape[1] // 384
+    a = _alloc_rx_out(Cn, T, True, False, np.zeros)
+    port.L.m17o_rx_run(_p(D), 1 | 64, Cn, T, 4, _p(a.disc), _p(a.nsym), _p(a.syms), a.symcap, _p(a.frames), a.fcap, _p(a.soft),
+                       _p(a.events), a.ecap, _p(a.counts))
+    b = _alloc_rx_out(Cn, T, False, False, shared_array)
+    for c in range(Cn):
+        pid = os.fork()
+        if pid == 0:
+            try:
+                L = C.CDLL(path)
+                L.ref_init(10)
+                L.refe_open()
+                L.ref_trace_begin(None, None, _p(b.syms[c]), C.c_long(b.symcap), _p(b.frames[c]), C.c_long(b.fcap), None, _p(b.events[c]), C.c_long(b.ecap))
+                for t in range(T):
+                    blk = np.ascontiguousarray(D[c, t * 384:(t + 1) * 384])
+                    b.nsym[c, t] = L.refe_block(_p(blk), 384)
+                k = np.zeros(4, np.int64)
+                L.ref_trace_counts(_p(k))
+                b.counts[c] = k
+                os._exit(0)
+            except BaseException:
+                os._exit(1)
+        _, st = os.waitpid(pid, 0)
+        assert os.WIFEXITED(st) and os.WEXITSTATUS(st) == 0, "reference child failed"
+    assert np.array_equal(a.nsym, b.nsym)
+    for c in range(Cn):
+        n = int(a.nsym[c].sum())
+        assert n == int(b.counts[c, 1]) and feq(a.syms[c, :n], b.syms[c, :n]), c
+        nf = int(a.counts[c, 2])
+        assert nf == int(b.counts[c, 2]), (c, nf, b.counts[c])
+        for f in ("type", "flags", "lich", "data", "crc", "votes", "frame_errors", "sym_off"):
+            assert np.array_equal(a.frames[c, :nf][f], b.frames[c, :nf][f]), (c, f)
+    off = port.rx_run(D, seam=1)
+    assert not feq(a.syms, off.syms)               # the equaliser really sat in the chain
