@@ -159,6 +159,14 @@ int m17b_rx_framer_reset(m17b_rx *rx, void *stream);
    the whole chain: the front end of each block then runs inside the timing-loop kernel (one launch per call).  Off (the
    reference default) uses the block-parallel front end.  No effect on m17b_rx_baseband. */
 int m17b_rx_set_afc(m17b_rx *rx, int on, void *stream);
+/* Equaliser option.  The reference ships a 5-tap T/2 RLS equaliser (m17_equalize.cpp) that nothing calls.  With the
+   option on, every symbol of the timing loop is paired with the matched filter's output half a symbol earlier (the same polyphase
+   branch, rx_sync_filter m17_rx_sync.cpp:25-31 one sample before), the pairs go through eq_train_unknown (m17_equalize.cpp:185-213)
+   and the framer (m17_rx_symbols, m17_rx_frame.cpp:173) sees the equaliser's output; eq_open (:217-224) runs when the option is turned
+   on and on m17b_rx_reset.  Off (the default) is upstream behaviour.  Not available together with AFC (M17B_E_ARG).  As upstream's
+   code stands the option degrades reception (its decision levels assume unit-scale symbols): it exists to evaluate the
+   reference's equaliser in the chain, bit-exact against the same wiring of the reference's own functions. */
+int m17b_rx_set_equaliser(m17b_rx *rx, int on, void *stream);
 /* BERT receive.  The reference sends BERT frames (m17_fmt_add_bert_frame) but its decode_bert_frame is empty
    (m17_rx_parse.cpp:178-180) and m17_prbs9_rx_check (m17_prbs9.cpp:40-64) is never called.  With on != 0, BERT frames are
    de-punctured (P2, 402 coded bits), Viterbi-decoded (201 steps) into data[0..25) and their 197 PRBS9 bits go through the

@@ -326,6 +326,11 @@ class Rx:
     def set_afc(self, on):
         _l.check(self.L.m17b_rx_set_afc(self.h, int(bool(on)), _stream()))
 
+    def set_equaliser(self, on):
+        """Equaliser option: eq_train_unknown (m17_equalize.cpp:185-213) on T/2 pairs between the timing loop and the framer
+        (no call site upstream; off = upstream behaviour).  Not together with AFC."""
+        _l.check(self.L.m17b_rx_set_equaliser(self.h, int(bool(on)), _stream()))
+
     def overflow(self):
         """sticky capacity flags since the last reset (bit 0: the symbol seam was given more symbols than max_blocks*200)"""
         v = C.c_int()

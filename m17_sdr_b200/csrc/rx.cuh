@@ -37,6 +37,8 @@ struct m17b_rx {
     cudaEvent_t ev_h2d[2], ev_done[2], ev_piece[M17B_HOST_TAIL_PIECES];
     int afc, bert, last_launches, seam_last;
     void *d_pkt_state;                // [nchan] RxPacketState of m17b_rx_reassemble_packets (app.cuh), allocated on first use
+    RxEqState *d_eq;                  // [nchan] equaliser option (m17b_rx_set_equaliser): allocated on first use, nullptr = off
+    int eq_on;
     int *d_overflow;                  // sticky flags (m17b_rx_get_overflow): 1 = the symbol seam was given more symbols than the capacity
     // time-sliced pipeline (see rx_pipeline): front end of slice k+1 | timing loop + framer of slice k | frame decode of slice k-1
     int slice_blocks;                 // blocks per slice; 0 = one slice (stages strictly in sequence)
@@ -258,7 +260,7 @@ extern "C" int m17b_rx_destroy(m17b_rx *rx) {
         if (rx->ev_done[i]) cudaEventDestroy(rx->ev_done[i]);
     }
     for (int i = 0; i < M17B_HOST_TAIL_PIECES; i++) if (rx->ev_piece[i]) cudaEventDestroy(rx->ev_piece[i]);
-    cudaFree(rx->d_frame_rng); cudaFree(rx->d_lsf_snap); cudaFree(rx->d_lsf_ver); cudaFree(rx->d_overflow); cudaFree(rx->d_pkt_state); cudaFree(rx->d_ssoft); cudaFree(rx->d_saux); cudaFree(rx->d_dlist);
+    cudaFree(rx->d_frame_rng); cudaFree(rx->d_lsf_snap); cudaFree(rx->d_lsf_ver); cudaFree(rx->d_overflow); cudaFree(rx->d_eq); cudaFree(rx->d_pkt_state); cudaFree(rx->d_ssoft); cudaFree(rx->d_saux); cudaFree(rx->d_dlist);
     if (rx->s_fe) cudaStreamDestroy(rx->s_fe);
     if (rx->s_sync) cudaStreamDestroy(rx->s_sync);
     if (rx->s_dec) cudaStreamDestroy(rx->s_dec);
@@ -282,6 +284,12 @@ extern "C" int m17b_rx_destroy(m17b_rx *rx) {
     return M17B_OK;
 }
 
+__global__ void k_rx_eq_open(RxEqState *e, int64_t nchan) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchan) return;
+    eq_init(e[c].e, true, true);
+    e[c].mid = 0.0f; e[c].pad[0] = e[c].pad[1] = e[c].pad[2] = 0.0f;
+}
 extern "C" int m17b_rx_reset(m17b_rx *rx, void *stream) {
     if (!rx) return M17B_E_ARG;
     CUDA_TRY(cudaSetDevice(rx->ctx->device));
@@ -289,6 +297,10 @@ extern "C" int m17b_rx_reset(m17b_rx *rx, void *stream) {
     k_rx_reset<<<grid_for(rx->nchan, 4), 128, 0, st>>>(rx->d_state, rx->nchan, rx->d_syms, rx->sym_pitch, rx->d_stats, rx->d_nframes, rx->d_nevents, rx->d_overflow,
                                                        (uint32_t *)rx->d_pkt_state, 832 / 4);                  // sizeof(RxPacketState) = 832, app.cuh
     KERNEL_CHECK();
+    if (rx->d_eq) {                                                                                             // eq_open, m17_equalize.cpp:217-224
+        k_rx_eq_open<<<grid_for(rx->nchan, 128), 128, 0, st>>>(rx->d_eq, rx->nchan);
+        KERNEL_CHECK();
+    }
     return M17B_OK;
 }
 
@@ -381,6 +393,23 @@ extern "C" int m17b_rx_create(m17b_ctx *ctx, int64_t nchan, int64_t max_blocks, 
     return M17B_OK;
 }
 
+// Equaliser option: eq_open (m17_equalize.cpp:217-224) once, then eq_train_unknown (:185-213) on every
+// (half-symbol, symbol) pair of the matched filter, its output to the framer -- between m17_rx_sync.cpp:77 and m17_rx_frame.cpp:173.
+// The reference itself never calls its equaliser; off (the default) is upstream behaviour.  Turning it on (re)opens the equaliser of
+// every channel; m17b_rx_reset does the same.  Not available together with AFC.  Runs in the warp-per-channel timing-loop kernel.
+extern "C" int m17b_rx_set_equaliser(m17b_rx *rx, int on, void *stream) {
+    if (!rx) return M17B_E_ARG;
+    if (on && rx->afc) return M17B_E_ARG;
+    if (on) {
+        CUDA_TRY(cudaSetDevice(rx->ctx->device));
+        if (!rx->d_eq) CUDA_TRY(cudaMalloc((void **)&rx->d_eq, sizeof(RxEqState) * rx->nchan));
+        k_rx_eq_open<<<grid_for(rx->nchan, 128), 128, 0, as_stream(stream)>>>(rx->d_eq, rx->nchan);
+        KERNEL_CHECK();
+    }
+    rx->eq_on = on != 0;
+    return M17B_OK;
+}
+
 // radio_set_afc_on / radio_set_afc_off (radio.cpp:146-152).  With AFC on, the NCO step of a block depends on the framer state and
 // the discriminator mean of the block before it, so a channel's blocks are serial through the whole chain: m17b_dsp_rx then runs
 // the AFC front end of each block (afc.cuh) inside the timing-loop kernel's block loop, one launch per call.
@@ -391,6 +420,7 @@ extern "C" int m17b_rx_set_afc(m17b_rx *rx, int on, void *stream) {
         k_afc_off<<<grid_for(rx->nchan, 128), 128, 0, as_stream(stream)>>>(rx->d_state, rx->nchan);
         KERNEL_CHECK();
     }
+    if (on && rx->eq_on) return M17B_E_ARG;          // the equaliser option and AFC are not combined
     rx->afc = on != 0;
     return M17B_OK;
 }
@@ -417,7 +447,12 @@ static int launch_sync(m17b_rx *rx, int64_t c0, int64_t nc, const float *disc, c
     // B200) the tap-pairs-in-shared-memory variant (108 registers, 16 warps per SM) is 15-23 % faster.
     const int impl = rx->sync_impl >= 0 ? rx->sync_impl : (nc <= 256 && !shared_gpu ? 4 : nc <= 8 * 148 ? 0 : 33);
     const f32x2 one = 0x3F8000003F800000ull;                          // (1.0f, 1.0f), passed as data so that ptxas cannot contract the packed adds (sync.cuh, dot2)
-    if (impl == 33) {
+    if (rx->eq_on) {
+        const size_t smem = sizeof(float) * SY_HIST * SY_WARPS;       // the half-symbol values of a block, per warp
+        const unsigned g = grid_for(nc, SY_WARPS);
+        if (mean) k_sync_frame<true, false, true><<<g, SY_WARPS * 32, smem, st>>>(SYNC_ARGS, one, nullptr, nullptr, nullptr, rx->d_eq + c0);
+        else      k_sync_frame<false, false, true><<<g, SY_WARPS * 32, smem, st>>>(SYNC_ARGS, one, nullptr, nullptr, nullptr, rx->d_eq + c0);
+    } else if (impl == 33) {
         const size_t smem = sizeof(SyncGroupSmem) * SY_WARPS;
         const unsigned g = grid_for(nc, SY_WARPS);
         if (mean) k_sync_frame_g<true, 32, true><<<g, SY_WARPS * 32, smem, st>>>(SYNC_ARGS, one);

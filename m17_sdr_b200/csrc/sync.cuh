@@ -18,7 +18,7 @@
 // in straight-line code for the common case of one frame boundary per block.
 // The next block's samples are prefetched as 16-byte cp.async pieces and staged with vector loads.
 #pragma once
-#include "afc.cuh"
+#include "eq.cuh"
 
 #ifndef SY_WARPS
 #define SY_WARPS 2            // channels (warps) per CTA.  1024 channels are 6.9 warps per SM: with 4-warp CTAs 108 SMs hold 8 warps and 40
@@ -45,11 +45,11 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 }
 
 // m17_sync_adjust (m17_rx_sync.cpp:45-72).  clk is the value m_clk has before the NEXT sample is processed.
-__device__ __forceinline__ void sync_adjust(int TH, int &thr, int &index, int &clk, int &m_idx, float *out, int lane) {
+__device__ __forceinline__ void sync_adjust(int TH, int &thr, int &index, int &clk, int &m_idx, float *out, int lane, float *mid = nullptr) {
     if (thr > TH) {
         index = (index + 1 == M17B_NF) ? 0 : index + 1;
         thr = 0;
-        if (index == 0) { clk = 1; if (m_idx >= 0 && lane == 0) out[m_idx] = 0.0f; m_idx++; }
+        if (index == 0) { clk = 1; if (m_idx >= 0 && lane == 0) { out[m_idx] = 0.0f; if (mid) mid[m_idx] = 0.0f; } m_idx++; }
     }
     if (thr < -TH) {
         thr = 0;
@@ -113,17 +113,35 @@ __device__ __forceinline__ void dot6(const float (*X)[SY_XQ], int base, const f3
     dot6_core(x, tp, one, s, d);
 }
 
+// Equaliser option (EQ = true): the matched filter's output HALF A SYMBOL before a symbol instant -- the same polyphase branch on the
+// window one sample earlier, xm1 = that window's first sample and x[0 .. 29] the rest -- summed in tap order like rx_sync_filter
+// (m17_rx_sync.cpp:25-31).  tp[k]'s low half is the matched tap.
+template <int NX>
+__device__ __forceinline__ float dot_mid(float xm1, const float (&x)[NX], int first, const f32x2 (&tp)[M17B_FN]) {
+    float t, td;
+    unpack2(tp[0], t, td);
+    float acc = (first == 0 ? xm1 : x[first - 1]) * t;
+#pragma unroll
+    for (int k = 1; k < M17B_FN; k++) { unpack2(tp[k], t, td); acc += x[first - 1 + k] * t; }
+    return acc;
+}
+
 // AFC = true (m17b_rx_set_afc): the block's discriminator samples do not come from memory but from the AFC front end run by
 // the same warp at the top of the block loop (afc.cuh): iq = int16 IQ rows, disc / mean are then OUTPUTS (the raw samples and
 // block means the caller may inspect).  15.4 KB more shared memory per warp: still two CTAs per SM.
-template <bool HAS_MEAN, bool AFC = false>
+// EQ = true (m17b_rx_set_equaliser; not together with AFC): every symbol is paired with the matched filter's output half a symbol
+// earlier (dot_mid), the block's pairs go through eq_train_unknown (eq.cuh) and the framer sees the equaliser's output.  Upstream has
+// no call site for its equaliser; this is the wiring SURVEY 8f rank 3 describes, checked against the oracle's seam flag 64, which is
+// itself pinned to the reference's functions (oracle/ref/eq_shim.cpp).  The half-symbol values live in dynamic shared memory.
+template <bool HAS_MEAN, bool AFC = false, bool EQ = false>
 __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__restrict__ disc, const float *__restrict__ mean, int64_t nchan, int64_t T,
                                                               int t0, int t1, int2 *frame_rng, RxChanState *st, const float *__restrict__ g_mf, const float *__restrict__ g_md,
                                                               float *syms, int64_t sym_pitch, int32_t *__restrict__ nsym, int32_t *__restrict__ sym_base,
                                                               m17b_frame_rec *frames, int64_t fcap, int32_t *__restrict__ nframes,
                                                               m17b_event_rec *events, int64_t ecap, int32_t *__restrict__ nevents,
                                                               unsigned long long *stats, int commit_fe, f32x2 one,
-                                                              const uint32_t *__restrict__ iq = nullptr, float *disc_out = nullptr, float *mean_out = nullptr) {
+                                                              const uint32_t *__restrict__ iq = nullptr, float *disc_out = nullptr, float *mean_out = nullptr,
+                                                              RxEqState *eqs = nullptr) {
     __shared__ __align__(16) SyncWarpSmem sm_all[SY_WARPS];
     extern __shared__ __align__(16) unsigned char afc_smem_raw[];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -132,6 +150,9 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
     SyncWarpSmem &sm = sm_all[wid];
     RxChanState *S = st + c;
     float *out = sm.hist + 8;
+    float *mid = EQ ? (float *)afc_smem_raw + wid * SY_HIST + 8 : nullptr;   // mid[q] pairs with out[q]
+    float mid_carry = 0.0f;                                                   // the half-symbol value in front of the next block's sample 0
+    if (EQ) mid_carry = eqs[c].mid;
     const long long clk_start = clock64();
     unsigned dbg_rounds = 0;
 #ifdef M17B_PHASE_CLOCKS
@@ -274,7 +295,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
                 if (dd > 0) thr++;
                 if (dd < 0) thr--;
                 clk = 0;
-                sync_adjust(TH, thr, index, clk, m_idx, out, lane);
+                sync_adjust(TH, thr, index, clk, m_idx, out, lane, mid);
                 i++;
                 continue;
             }
@@ -287,11 +308,19 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
             if (whole_block && i <= 1) {
                 // Locked, at the start of a block: the threshold is 80, so a trip inside the block is rare -- speculate the
                 // whole block in ONE round, six consecutive symbols per lane (192 symbols, all inside the block for i <= 1).
-                float s6[6], d6[6];
+                float s6[6], d6[6], mid6[6];
                 {
                     float xw[M17B_FN + 10];
                     if (i == 0) load_window<0>(sm.x, 3 * lane, xw); else load_window<1>(sm.x, 3 * lane, xw);
                     dot6_core(xw, tp, one, s6, d6);
+                    if (EQ) {
+                        // xw[0] is sample n0 = 12 lane + i of the staged array; the one before it (none for the block's first sample:
+                        // that pair's half-symbol value was computed at the end of the previous block)
+                        const float xm1 = i == 1 ? sm.x[0][3 * lane] : (lane > 0 ? sm.x[3][3 * lane - 1] : 0.0f);
+#pragma unroll
+                        for (int m = 0; m < 6; m++) mid6[m] = dot_mid(xm1, xw, 2 * m, tp);
+                        if (i == 0 && lane == 0) mid6[0] = mid_carry;
+                    }
                 }
                 // votes (sync_update, m17_rx_sync.cpp:38-42): every symbol votes on the NEXT sample, so the only symbol of the
                 // block without a vote is the one at sample 383 (i == 1, lane 31, m == 5).  The common case needs no per-symbol
@@ -331,7 +360,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
                 const unsigned trip = __ballot_sync(0xffffffffu, fm < 6);
                 if (!trip) {
 #pragma unroll
-                    for (int m = 0; m < 6; m++) if (m_idx + 6 * lane + m >= 0) out[m_idx + 6 * lane + m] = s6[m];
+                    for (int m = 0; m < 6; m++) if (m_idx + 6 * lane + m >= 0) { out[m_idx + 6 * lane + m] = s6[m]; if (EQ) mid[m_idx + 6 * lane + m] = mid6[m]; }
                     m_idx += 192;
                     thr = thr + __popc(q0) + 2 * __popc(q1) + 4 * __popc(q2) + 8 * __popc(q3) - 192;
                     sumc = __shfl_sync(0xffffffffu, s6[5], 31);
@@ -343,7 +372,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
                     const int fmL = __shfl_sync(0xffffffffu, fm, L);
                     const int P = 6 * L + fmL;
 #pragma unroll
-                    for (int m = 0; m < 6; m++) if (6 * lane + m <= P && m_idx + 6 * lane + m >= 0) out[m_idx + 6 * lane + m] = s6[m];
+                    for (int m = 0; m < 6; m++) if (6 * lane + m <= P && m_idx + 6 * lane + m >= 0) { out[m_idx + 6 * lane + m] = s6[m]; if (EQ) mid[m_idx + 6 * lane + m] = mid6[m]; }
                     m_idx += P + 1;
                     int tsel = th6[0]; float ssel = s6[0], dsel = d6[0];
 #pragma unroll
@@ -354,7 +383,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
                     clk = 0;
                     trips++;
                     __syncwarp();
-                    sync_adjust(TH, thr, index, clk, m_idx, out, lane);
+                    sync_adjust(TH, thr, index, clk, m_idx, out, lane, mid);
                     i = i + 2 * P + 2;
                 }
                 continue;
@@ -362,7 +391,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
             // speculate: lane l computes the symbols at samples ja = i + 4l and jb = ja + 2
             const int ja = i + 4 * lane, jb = ja + 2;
             const bool valid_a = ja < 384, valid_b = jb < 384;
-            float sa = 0.0f, da = 0.0f, sb = 0.0f, db = 0.0f;
+            float sa = 0.0f, da = 0.0f, sb = 0.0f, db = 0.0f, mida = 0.0f, midb = 0.0f;
             if (valid_a) {
                 const int base = (i >> 2) + lane;
                 float xw[M17B_FN + 2];
@@ -373,6 +402,13 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
                     default: load_window<3>(sm.x, base, xw); break;
                 }
                 dot2_core(xw, tp, one, sa, da, sb, db);
+                if (EQ) {
+                    const int n0 = ja;                                     // staged index of xw[0]
+                    const float xm1 = n0 > 0 ? sm.x[(n0 - 1) & 3][(n0 - 1) >> 2] : 0.0f;
+                    mida = dot_mid(xm1, xw, 0, tp);
+                    midb = dot_mid(xm1, xw, 2, tp);
+                    if (n0 == 0) mida = mid_carry;
+                }
             }
             // votes happen on the sample after each symbol (sync_update, m17_rx_sync.cpp:38-42) if it is in this block
             const bool vote_a = valid_a && (ja + 1 < 384), vote_b = valid_b && (jb + 1 < 384);
@@ -389,8 +425,8 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
             const int P = pa < pb ? pa : pb;                                  // first symbol (in stream order) whose vote trips
             if (P >= (1 << 20)) {
                 const int nv = __popc(__ballot_sync(0xffffffffu, valid_a)) + __popc(__ballot_sync(0xffffffffu, valid_b));
-                if (valid_a && m_idx + 2 * lane >= 0) out[m_idx + 2 * lane] = sa;
-                if (valid_b && m_idx + 2 * lane + 1 >= 0) out[m_idx + 2 * lane + 1] = sb;
+                if (valid_a && m_idx + 2 * lane >= 0) { out[m_idx + 2 * lane] = sa; if (EQ) mid[m_idx + 2 * lane] = mida; }
+                if (valid_b && m_idx + 2 * lane + 1 >= 0) { out[m_idx + 2 * lane + 1] = sb; if (EQ) mid[m_idx + 2 * lane + 1] = midb; }
                 m_idx += nv;
                 thr = __shfl_sync(0xffffffffu, th_b, 31);
                 const int L = (nv - 1) >> 1;
@@ -402,8 +438,8 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
                 if (last_j + 1 < 384) { i = last_j + 2; clk = 0; } else { i = 384; clk = 1; }
             } else {
                 const int L = P >> 1;
-                if (2 * lane <= P && m_idx + 2 * lane >= 0) out[m_idx + 2 * lane] = sa;
-                if (2 * lane + 1 <= P && m_idx + 2 * lane + 1 >= 0) out[m_idx + 2 * lane + 1] = sb;
+                if (2 * lane <= P && m_idx + 2 * lane >= 0) { out[m_idx + 2 * lane] = sa; if (EQ) mid[m_idx + 2 * lane] = mida; }
+                if (2 * lane + 1 <= P && m_idx + 2 * lane + 1 >= 0) { out[m_idx + 2 * lane + 1] = sb; if (EQ) mid[m_idx + 2 * lane + 1] = midb; }
                 m_idx += P + 1;
                 const int thr0 = __shfl_sync(0xffffffffu, th_a, L), thr1 = __shfl_sync(0xffffffffu, th_b, L);
                 const float s0 = __shfl_sync(0xffffffffu, sa, L), s1 = __shfl_sync(0xffffffffu, sb, L);
@@ -414,13 +450,25 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
                 clk = 0;
                 trips++;
                 __syncwarp();
-                sync_adjust(TH, thr, index, clk, m_idx, out, lane);
+                sync_adjust(TH, thr, index, clk, m_idx, out, lane, mid);
                 i = i + 2 * P + 2;
             }
         }
         const int n = m_idx < 0 ? 0 : m_idx;
         trips_prev = trips;
         __syncwarp();
+        if (EQ) {
+            // the next block's sample 0 is a symbol instant iff clk == 0 now; its half-symbol companion is this block's last sample
+            // through the branch that symbol will use (the index cannot change in between)
+            if (clk == 0) {
+                const float *mfb = g_mf + index * M17B_FN;
+                float acc = sm.x[383 & 3][383 >> 2] * __ldg(mfb);
+                for (int k = 1; k < M17B_FN; k++) acc += sm.x[(383 + k) & 3][(383 + k) >> 2] * __ldg(mfb + k);
+                mid_carry = acc;
+            }
+            eq_block(&eqs[c].e, out, mid, n, lane);
+            __syncwarp();
+        }
         PHASE(1);
 
         // ---- emit the block's symbols to the channel's stream
@@ -584,6 +632,7 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 2) k_sync_frame(const float *__
     }
     if (lane < 30) S->tail[lane] = sm.x[lane & 3][lane >> 2];
     if (lane < 8) { S->win[lane] = sm.hist[lane]; S->head[lane] = sm.head[lane]; }
+    if (EQ && lane == 0) eqs[c].mid = mid_carry;
     if (lane == 0) {
         S->clk = clk; S->thr = thr; S->index = index; S->sum = sumc; S->dif = difc;
         S->flock = flock; S->fclk = fclk; S->ferr = ferr; S->frame_start = frame_start; S->sym_total = sym_total;

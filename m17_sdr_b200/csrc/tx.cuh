@@ -296,67 +296,20 @@ extern "C" int m17b_tx_debug_scan(m17b_tx *tx, uint64_t *h_out8) {
 }
 
 // ---------------------------------------------------------------- equaliser (m17_equalize.cpp), thread per channel
-struct EqState { float c[5], g[5], u[5][5], d[5], E, q, y, fbr, samples[5]; };
+// (EqState and the training step live in eq.cuh, shared with the equaliser option of the live chain)
 struct m17b_eq { m17b_ctx *ctx; int64_t nchan; EqState *d_state; };
 __global__ void k_eq_reset(EqState *st, int64_t nchan, int full) {
     int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nchan) return;
-    EqState &e = st[c];
-    if (full) {                                     // eq_open :217-224 (statics start at zero)
-        float *w = (float *)&e;
-        for (int i = 0; i < (int)(sizeof(EqState) / 4); i++) w[i] = 0.0f;
-        e.q = 0.08f; e.E = 0.01f;
-    }
-    for (int j = 0; j < 5; j++) { for (int i = 0; i < j; i++) e.u[i][j] = 0.0f; e.d[j] = 0.1f; }   // eq_k_reset_ud :25-36
-    for (int i = 0; i < 5; i++) e.c[i] = 0.0f;                                                     // eq_k_reset_coffs :14-22
+    eq_init(st[c], full != 0, true);
 }
 __global__ void k_eq_train(EqState *st, int64_t nchan, const float *in, const float *train, int64_t nsym, float *out) {
     int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nchan) return;
     EqState e = st[c];
     const float *x2 = in + c * nsym * 2;
-    for (int64_t n = 0; n < nsym; n++) {
-        // eq_update_samples :152-159
-        e.samples[0] = e.samples[2]; e.samples[1] = e.samples[3]; e.samples[2] = e.samples[4];
-        e.samples[3] = x2[2 * n]; e.samples[4] = x2[2 * n + 1];
-        // eq_equalize :122-135
-        float sym = e.samples[0] * e.c[0];
-#pragma unroll
-        for (int i = 1; i < 5; i++) sym += e.samples[i] * e.c[i];
-        float tr;
-        if (train) tr = train[c * nsym + n];
-        else if (sym > 0) tr = ((double)sym >= 0.66) ? 1.0f : 0.333f;                              // :195-205 (double literals)
-        else tr = ((double)sym <= -0.66) ? -1.0f : -0.333f;
-        float err = tr - sym;
-        // eq_k_calculate :40-100
-        float f[5], h[5], a[5];
-        const float *x = e.samples;
-        f[0] = x[0];
-#pragma unroll
-        for (int j = 1; j < 5; j++) { f[j] = e.u[0][j] * x[0] + x[j]; for (int i = 1; i < j; i++) f[j] += e.u[i][j] * x[i]; }
-#pragma unroll
-        for (int j = 0; j < 5; j++) e.g[j] = e.d[j] * f[j];
-        a[0] = e.E + e.g[0] * f[0];
-#pragma unroll
-        for (int j = 1; j < 5; j++) a[j] = a[j - 1] + e.g[j] * f[j];
-        const float hq = 1 + e.q, ht = a[4] * e.q;
-        e.y = 1.0f / (a[0] + ht);
-        e.d[0] = e.d[0] * hq * (e.E + ht) * e.y;
-#pragma unroll
-        for (int j = 1; j < 5; j++) {
-            const float B = a[j - 1] + ht;
-            h[j] = -f[j] * e.y;
-            e.y = 1.0f / (a[j] + ht);
-            e.d[j] = e.d[j] * hq * B * e.y;
-            for (int i = 0; i < j; i++) { const float B0 = e.u[i][j]; e.u[i][j] = B0 + h[j] * e.g[i]; e.g[i] += e.g[j] * B0; }
-        }
-        // eq_k_update :105-121
-        err *= e.y;
-#pragma unroll
-        for (int i = 0; i < 5; i++) e.c[i] += err * e.g[i];
-        e.fbr = tr;
-        out[c * nsym + n] = sym;
-    }
+    for (int64_t n = 0; n < nsym; n++)
+        out[c * nsym + n] = eq_step(e, x2[2 * n], x2[2 * n + 1], train != nullptr, train ? train[c * nsym + n] : 0.0f);
     st[c] = e;
 }
 extern "C" int m17b_eq_create(m17b_ctx *ctx, int64_t nchan, m17b_eq **out) {

@@ -48,6 +48,7 @@ _SIGS = {
     "m17b_rx_reset": ([_vp, _vp], _i32),
     "m17b_rx_framer_reset": ([_vp, _vp], _i32),
     "m17b_rx_set_afc": ([_vp, _i32, _vp], _i32),
+    "m17b_rx_set_equaliser": ([_vp, _i32, _vp], _i32),
     "m17b_rx_get_overflow": ([_vp, C.POINTER(_i32)], _i32),
     "m17b_rx_set_bert": ([_vp, _i32], _i32),
     "m17b_rx_get_bert": ([_vp, _vp, _vp], _i32),

@@ -474,7 +474,42 @@ def check_rx_afc(ctx, P, seed=31, nchan=12, nframes=30):
     return "rx afc ok (%d ch, bit-identical=%s, rel rms %.1e, %d frames)" % (nchan, exact, rel, int(o.counts[:, 2].sum()))
 
 
-def run_chain(ctx, X, seam=0, split=None, afc=False):
+def check_rx_equaliser(ctx, P, seed=61):
+    """Equaliser option (m17b_rx_set_equaliser): eq_train_unknown on (half-symbol, symbol) pairs between the timing
+    loop and the framer, bit for bit against the oracle's seam flag 64 (itself pinned to the reference's own functions,
+    tests/test_oracle_vs_ref.py) -- nsym, the equalised symbol stream, records, events.  Baseband seam with noise down to 0 dB
+    (threshold trips and bit slips while unlocked), the IQ path, and both again split over several calls (equaliser state and the
+    half-symbol value carried across calls).  The option and AFC exclude each other."""
+    import m17_sdr_b200 as m
+    D, _ = signals.baseband_channels(P, 8, 14, seed, [None, 12, 10, 6, 4, 2, 0, -3])
+    X, _ = signals.stream_channels(P, 6, 12, seed + 1, ebn0=[None, 30, 24, 20, 16, 12], f0_max=1200.0)
+    nfr = 0
+    for data, seam in ((D, 1), (X, 0)):
+        o = P.rx_run(data, seam=seam, eq=True)
+        off = P.rx_run(data, seam=seam)
+        assert not bits_eq(o.syms, off.syms)
+        for split in (None, [2, 1, 5, 1]):
+            compare_chain(run_chain(ctx, data, seam, split, eq=True), o, seam, data.shape[0], verbose=True)
+        nfr += int(o.counts[:, 2].sum())
+    rx = m.Rx(ctx, 2, 2)
+    rx.set_afc(True)
+    try:
+        rx.set_equaliser(True)
+        raise AssertionError("equaliser + AFC accepted")
+    except m.M17Error:
+        pass
+    rx.set_afc(False)
+    rx.set_equaliser(True)
+    try:
+        rx.set_afc(True)
+        raise AssertionError("AFC + equaliser accepted")
+    except m.M17Error:
+        pass
+    rx.close()
+    return "rx equaliser option ok (%d + %d ch, %d frame records)" % (D.shape[0], X.shape[0], nfr)
+
+
+def run_chain(ctx, X, seam=0, split=None, afc=False, eq=False):
     """Run the CUDA chain over X; split = list of block counts to process in successive calls (state carry)."""
     import m17_sdr_b200 as m
     Cn = X.shape[0]
@@ -487,6 +522,8 @@ def run_chain(ctx, X, seam=0, split=None, afc=False):
     rx = m.Rx(ctx, Cn, max(parts))
     if afc:
         rx.set_afc(True)
+    if eq:
+        rx.set_equaliser(True)
     out = []
     t0 = 0
     for nb in parts:
@@ -738,6 +775,7 @@ CHECKS = [
     ("rx_chain_split", lambda c, P: check_rx_chain(c, P, nchan=6, seed=23, verbose=True, split=[1, 7, 2, 1, 13])),
     ("rx_packet", lambda c, P: check_rx_packet(c, P, verbose=True)),
     ("rx_afc", lambda c, P: check_rx_afc(c, P)),
+    ("rx_equaliser", lambda c, P: check_rx_equaliser(c, P)),
     ("rx_symbols", lambda c, P: check_rx_symbols(c, P)),
     ("rx_bert", lambda c, P: check_rx_bert(c, P)),
     ("decimator", lambda c, P: check_decimator(c, P)),

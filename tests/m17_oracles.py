@@ -419,7 +419,7 @@ class Port:
         self.L.m17o_rx_free(_vp(r))
         return out
 
-    def rx_run(self, x, seam=0, nthreads=None, want_disc=True, want_soft=False, afc=False, bert=False):
+    def rx_run(self, x, seam=0, nthreads=None, want_disc=True, want_soft=False, afc=False, bert=False, eq=False):
         x = np.ascontiguousarray(x)
         if seam == 0:
             assert x.dtype == np.int16 and x.ndim == 3 and x.shape[2] == 2 and x.shape[1] % BLOCK == 0
@@ -432,7 +432,7 @@ class Port:
         if bert:
             o["bert"] = np.zeros((Cn, 8), np.uint32)
             self.L.m17o_set_bert_out(_p(o["bert"]))
-        seam_flags = seam | (16 if afc else 0) | (32 if bert else 0)
+        seam_flags = seam | (16 if afc else 0) | (32 if bert else 0) | (64 if eq else 0)      # 64: equaliser option (probe)
         self.L.m17o_rx_run(_p(x), seam_flags, Cn, T, nthreads, _p(o.disc), _p(o.nsym), _p(o.syms), o.symcap, _p(o.frames), o.fcap,
                            _p(o.soft), _p(o.events), o.ecap, _p(o.counts))
         self.L.m17o_set_bert_out(None)

@@ -225,6 +225,11 @@ def test_rx_bert(ctx, port):
     print(gc.check_rx_bert(ctx, port))
 
 
+def test_rx_chain_equaliser_option(ctx, port):
+    """the reference's equaliser wired between the timing loop and the framer (off by default as upstream)."""
+    print(gc.check_rx_equaliser(ctx, port))
+
+
 def test_rx_chain_afc(ctx, port):
     """m17_dsp_rx with radio_set_afc_on(): NCO mixer + AFC loop closed through the framer, block-serial path."""
     print(gc.check_rx_afc(ctx, port))
