@@ -3,11 +3,11 @@
 eq_open() + eq_train_unknown() on (half-symbol, symbol) pairs of the matched filter between m17_rx_sync_samples and m17_rx_symbols
 (m17_rx_sync.cpp:77 -> m17_rx_frame.cpp:173; the half-symbol output is the same polyphase branch one sample earlier).
 Prints, per channel class, stream frames delivered with the exact payload with the equaliser off / on, and the symbol scale.
-usage: python benchmarks/eq_live_chain_probe.py"""
+usage: python tests/eq_live_chain_probe.py"""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))  # the oracle is test infrastructure: this probe lives under tests/
 import m17_oracles as O, signals
 
 P = O.Port()

@@ -171,7 +171,7 @@ def test_equaliser_live_chain_probe_pinned(port):
     SURVEY 8f rank 3) against the SAME wiring built from the reference's own functions (oracle/ref/eq_shim.cpp: unmodified
     m17_rx_sync_samples fed one sample per call, rx_sync_filter on its statics for the half-symbol output, eq_train_unknown,
     m17_rx_symbols).  One pristine reference process per channel.  This pins the probe whose numbers DESIGN.md quotes; the option
-    is NOT part of the product (it breaks the chain: benchmarks/eq_live_chain_probe.py)."""
+    is off by default in the product, as upstream (wired literally it breaks the chain: tests/eq_live_chain_probe.py)."""
     import ctypes as C
     import os
     import pytest
