@@ -105,7 +105,7 @@ m17o_rx *m17o_rx_new(void);
 void     m17o_rx_free(m17o_rx *r);
 void     m17o_rx_set_afc(m17o_rx *r, int on);
 void     m17o_rx_set_bert(m17o_rx *r, int on);                               /* BERT receive extension (decode_bert_frame is empty upstream) */
-void     m17o_rx_set_eq(m17o_rx *r, int on);                                 /* equaliser option (eq_open + eq_train_unknown on T/2 pairs; no call site upstream) */
+void     m17o_rx_set_eq(m17o_rx *r, int on);                                 /* equaliser option (eq_open + eq_train_unknown on T/2 pairs; no call site upstream; pinned by oracle/ref/eq_shim.cpp) */
 void     m17o_rx_get_bert(const m17o_rx *r, uint32_t *out8);                 /* state, idx, bad, good, eq, dif (m17_prbs9.cpp:7-12), bits, errs */
 void     m17o_prbs9_rx_check(m17o_rx *r, uint8_t bit);                       /* m17_prbs9.cpp:40-64 */
 void     m17o_set_bert_out(uint32_t *p);

@@ -432,7 +432,7 @@ class Port:
         if bert:
             o["bert"] = np.zeros((Cn, 8), np.uint32)
             self.L.m17o_set_bert_out(_p(o["bert"]))
-        seam_flags = seam | (16 if afc else 0) | (32 if bert else 0) | (64 if eq else 0)      # 64: equaliser option (probe)
+        seam_flags = seam | (16 if afc else 0) | (32 if bert else 0) | (64 if eq else 0)      # 64: equaliser option (checker of m17b_rx_set_equaliser)
         self.L.m17o_rx_run(_p(x), seam_flags, Cn, T, nthreads, _p(o.disc), _p(o.nsym), _p(o.syms), o.symcap, _p(o.frames), o.fcap,
                            _p(o.soft), _p(o.events), o.ecap, _p(o.counts))
         self.L.m17o_set_bert_out(None)
